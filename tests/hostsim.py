@@ -1,0 +1,59 @@
+"""ctypes binding of tests/hostsim/libggr_hostsim.so - the host simulation of the device code."""
+import ctypes as C
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DIR = os.path.join(ROOT, "tests", "hostsim")
+LIB = os.path.join(DIR, "libggr_hostsim.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.check_call(["make", "-s", "-C", DIR])
+        L = C.CDLL(LIB)
+        L.hs_schema_new.restype = C.c_void_p
+        L.hs_schema_new.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_char_p, C.c_size_t]
+        L.hs_msg_index.argtypes = [C.c_void_p, C.c_char_p]
+        L.hs_encode.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p,
+                                C.c_uint32, C.POINTER(C.c_uint32)]
+        if hasattr(L, "hs_decode"):
+            L.hs_decode.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                    C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32)]
+        _lib = L
+    return _lib
+
+
+class Schema:
+    def __init__(self, fds, order=0):
+        err = C.create_string_buffer(256)
+        self.h = lib().hs_schema_new(fds, len(fds), order, err, 256)
+        if not self.h:
+            raise ValueError(err.value.decode())
+
+    def msg(self, name):
+        i = lib().hs_msg_index(self.h, name.encode())
+        if i < 0:
+            raise KeyError(name)
+        return i
+
+    def encode(self, name, data, in_off=0, out_off=0):
+        cap = len(data) + 64
+        out = C.create_string_buffer(cap)
+        n = C.c_uint32()
+        rc = lib().hs_encode(self.h, self.msg(name), data, len(data), in_off, out_off, out, cap, C.byref(n))
+        return rc, out.raw[: n.value]
+
+    def decode(self, name, data, flags=0, in_off=0, out_off=0):
+        cap = len(data) * 8 + 256
+        out = C.create_string_buffer(cap)
+        n = C.c_uint32()
+        rc = lib().hs_decode(self.h, self.msg(name), data, len(data), in_off, out_off, flags, out, cap, C.byref(n))
+        return rc, out.raw[: n.value]
+
+
+def load_schema(order=0):
+    with open(os.path.join(ROOT, "tests", "golden", "schemas.binpb"), "rb") as fh:
+        return Schema(fh.read(), order)

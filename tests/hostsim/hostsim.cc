@@ -1,0 +1,118 @@
+// hostsim.cc - HOST SIMULATION of the per-thread device code (tests only).
+//
+// The build container has no GPU.  The per-message device functions in ggrmcp_b200/csrc/*.cuh are
+// written against a tiny load/store shim (ggr_prim.cuh) so that exactly the same parser / emitter
+// code can be compiled here with g++ and run one "thread" at a time against the oracle.  This
+// library is never loaded by the product; the shipped .so contains only the sm_100a build and
+// fails loudly without a CUDA device.
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../ggrmcp_b200/csrc/ggr_schema.h"
+#include "../../ggrmcp_b200/csrc/ggr_encode.cuh"
+#ifdef GGR_HAVE_DECODE
+#include "../../ggrmcp_b200/csrc/ggr_decode.cuh"
+#endif
+
+struct HsSchema {
+  ggr::CompiledSchema cs;
+  uint8_t* blob;  // 16-byte aligned copy
+};
+
+extern "C" {
+
+void* hs_schema_new(const uint8_t* fds, size_t n, int order, char* err, size_t cap) {
+  HsSchema* s = new HsSchema();
+  std::string e;
+  if (!ggr::compile_schema(fds, n, (ggr::WireOrder)order, &s->cs, &e)) {
+    snprintf(err, cap, "%s", e.c_str());
+    delete s;
+    return nullptr;
+  }
+  s->blob = (uint8_t*)aligned_alloc(256, (s->cs.blob.size() + 255) / 256 * 256 + 256);
+  memcpy(s->blob, s->cs.blob.data(), s->cs.blob.size());
+  return s;
+}
+void hs_schema_free(void* h) {
+  HsSchema* s = (HsSchema*)h;
+  free(s->blob);
+  delete s;
+}
+int hs_msg_index(void* h, const char* name) {
+  HsSchema* s = (HsSchema*)h;
+  auto it = s->cs.msg_index.find(name);
+  return it == s->cs.msg_index.end() ? -1 : it->second;
+}
+
+// One simulated thread: JSON args -> wire.  `in_off`/`out_off` place the item at arbitrary
+// alignments inside padded buffers the way a batch does.
+int hs_encode(void* h, int msg, const uint8_t* json, uint32_t n, uint32_t in_off, uint32_t out_off, uint8_t* out,
+              uint32_t out_cap, uint32_t* out_n) {
+  HsSchema* s = (HsSchema*)h;
+  std::vector<uint8_t> inbuf_raw(in_off + n + 64 + 16, 0xEE);
+  uint8_t* in = (uint8_t*)(((uintptr_t)inbuf_raw.data() + 15) & ~(uintptr_t)15);
+  memcpy(in + in_off, json, n);
+  uint32_t ir_cap = n / 2 + 8;
+  uint8_t* ir = (uint8_t*)aligned_alloc(16, (size_t)ir_cap * 16);
+  Tables T = ggr_tables(s->blob);
+  EncResult res;
+  int st = encode_parse(T, (u32)msg, in, in_off, in_off + n, ir, ir_cap, &res);
+  *out_n = 0;
+  if (st == GST_OK) {
+    if (res.size > out_cap) {
+      free(ir);
+      return GST_NO_SPACE;
+    }
+    std::vector<uint8_t> ob_raw(out_off + res.size + 64, 0xDD);
+    uint8_t* ob = (uint8_t*)(((uintptr_t)ob_raw.data() + 15) & ~(uintptr_t)15);
+    std::vector<uint8_t> before(ob, ob + out_off + res.size + 32);
+    Wr w;
+    w.init(ob, out_off);
+    encode_emit(in, in_off + n, ir, res.first, w);
+    w.finish();
+    if (w.pos != out_off + res.size) st = 100;  // size pass and write pass disagree
+    // nothing outside [out_off, out_off+size) may be touched
+    for (uint32_t i = 0; i < out_off && st == GST_OK; i++)
+      if (ob[i] != before[i]) st = 101;
+    for (uint32_t i = out_off + res.size; i < out_off + res.size + 32 && st == GST_OK; i++)
+      if (ob[i] != before[i]) st = 102;
+    memcpy(out, ob + out_off, res.size);
+    *out_n = res.size;
+  }
+  free(ir);
+  return st;
+}
+
+#ifdef GGR_HAVE_DECODE
+int hs_decode(void* h, int msg, const uint8_t* wire, uint32_t n, uint32_t in_off, uint32_t out_off, uint32_t flags,
+              uint8_t* out, uint32_t out_cap, uint32_t* out_n) {
+  HsSchema* s = (HsSchema*)h;
+  std::vector<uint8_t> inbuf_raw(in_off + n + 64 + 16, 0xEE);
+  uint8_t* in = (uint8_t*)(((uintptr_t)inbuf_raw.data() + 15) & ~(uintptr_t)15);
+  memcpy(in + in_off, wire, n);
+  Tables T = ggr_tables(s->blob);
+  DecResult res;
+  int st = decode_size(T, (u32)msg, in, in_off, in_off + n, flags, &res);
+  *out_n = 0;
+  if (st == GST_OK) {
+    if (res.size > out_cap) return GST_NO_SPACE;
+    std::vector<uint8_t> ob_raw(out_off + res.size + 64, 0xDD);
+    uint8_t* ob = (uint8_t*)(((uintptr_t)ob_raw.data() + 15) & ~(uintptr_t)15);
+    std::vector<uint8_t> before(ob, ob + out_off + res.size + 32);
+    uint32_t end_pos = 0;
+    st = decode_write(T, (u32)msg, in, in_off, in_off + n, flags, res.mode, ob, out_off, &end_pos);
+    if (st == GST_OK && end_pos != out_off + res.size) st = 100;
+    for (uint32_t i = 0; i < out_off && st == GST_OK; i++)
+      if (ob[i] != before[i]) st = 101;
+    for (uint32_t i = out_off + res.size; i < out_off + res.size + 32 && st == GST_OK; i++)
+      if (ob[i] != before[i]) st = 102;
+    memcpy(out, ob + out_off, res.size);
+    *out_n = res.size;
+  }
+  return st;
+}
+#endif
+
+}  // extern "C"
