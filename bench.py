@@ -1,0 +1,352 @@
+#!/usr/bin/env python3
+"""bench.py - MCP tools/call transcodes/sec on B200 (BASELINE.json metric).
+
+One step = one pass of the hot path over one synthetic batch: the request side (arguments JSON ->
+protobuf wire) followed by the reply side (protobuf wire -> protojson text) for every item.
+Default workload: BASELINE.json configs[2] (nested+repeated messages from the reference's
+complex.proto descriptors, ~4 KB JSON, 65 536 items per GPU) - the config the target is quoted on.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload nested|flat|blob] [--items M]
+  python bench.py --impl reference ...      (the CPU path: oracle port on all host cores)
+
+Under torchrun (N > 1) every rank owns one GPU and its own shard of the batch (items shard by
+index, no collective on the data path); rank 0 prints one JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "tools_call_transcodes_per_sec"
+UNIT = "transcodes/s"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def load_fds():
+    with open(os.path.join(ROOT, "tests", "golden", "schemas.binpb"), "rb") as fh:
+        return fh.read()
+
+
+def make_workload(kind, n, msg_index, first):
+    import benchgen
+    if kind == "nested":
+        return benchgen.nested(n, msg_index, first=first)
+    if kind == "flat":
+        return benchgen.flat(n, msg_index, first=first)
+    if kind == "blob":
+        return benchgen.blob(n, msg_index, first=first)
+    raise SystemExit("unknown workload " + kind)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                parts = [p.strip() for p in out.split(",")]
+                self.samples.append(float(parts[0]))
+                self.max_mhz = float(parts[1])
+                for nm, v in zip(names, parts[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=10)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_oracle_rate(kind, sample_items, threads, repeats=1):
+    """transcodes/s of the CPU oracle (port of the reference path) on a bounded sample"""
+    import orc
+    S = orc.Schema(load_fds())
+    wl = make_workload(kind, sample_items, S.msg, 0)
+    t_total = 0.0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        if wl.req_json is not None:
+            S.encode_batch(wl.req_msg, wl.req_json, wl.req_off, threads=threads)
+        S.decode_batch(wl.rep_msg, wl.rep_wire, wl.rep_off, threads=threads, cap=int(len(wl.rep_wire) * 2 + 64 * wl.n + 4096))
+        t_total += time.perf_counter() - t0
+    return sample_items * repeats / t_total, t_total
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  The Go reference cannot be
+    built in this image (no Go toolchain), so this arm times the oracle port on all host cores."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = min(args.items, 8192 if args.workload != "blob" else 256)
+    for _ in range(args.warmup):
+        cpu_oracle_rate(args.workload, min(sample, 512), cores)
+    t0 = time.perf_counter()
+    rate_sum, t_sum = 0.0, 0.0
+    for _ in range(args.steps):
+        r, t = cpu_oracle_rate(args.workload, sample, cores)
+        t_sum += t
+    value = sample * args.steps / t_sum
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * t_sum / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": args.workload, "items_per_step": sample, "boundary": "InvokeMethod (arguments JSON <-> wire <-> protojson)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d items of the %s workload per step, oracle C++ port, %d threads" % (sample, args.workload, cores)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--workload", default="nested", choices=["nested", "flat", "blob"])
+    ap.add_argument("--items", type=int, default=0, help="items per GPU per step (default: config size)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer measurement (default: min(steps, 5))")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.items == 0:
+        args.items = 4096 if args.workload == "blob" else 65536
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import ggrmcp_b200
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    eng = ggrmcp_b200.Engine(local)
+    schema = eng.register(load_fds())
+    n = args.items
+    wl = make_workload(args.workload, n, schema.message, rank * n)
+    have_req = wl.req_json is not None
+
+    dev = torch.device("cuda", local)
+
+    def to_dev(a, pad=0):
+        t = torch.empty(a.nbytes + pad, dtype=torch.uint8, device=dev)
+        t[: a.nbytes] = torch.from_numpy(a.view(np.uint8).reshape(-1))
+        if pad:
+            t[a.nbytes:] = 0
+        return t
+
+    J_in = int(len(wl.req_json)) if have_req else 0
+    W_in = int(len(wl.rep_wire))
+    d_rep = to_dev(wl.rep_wire, 64)
+    d_rep_off = to_dev(wl.rep_off)
+    d_rep_msg = to_dev(wl.rep_msg)
+    rep_cap = int(W_in * 2.5 + 64 * n + 4096)
+    d_rep_out = torch.empty(rep_cap, dtype=torch.uint8, device=dev)
+    d_rep_out_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    d_rep_st = torch.empty(n, dtype=torch.int32, device=dev)
+    if have_req:
+        d_req = to_dev(wl.req_json, 64)
+        d_req_off = to_dev(wl.req_off)
+        d_req_msg = to_dev(wl.req_msg)
+        req_cap = int(J_in + 64)
+        d_req_out = torch.empty(req_cap, dtype=torch.uint8, device=dev)
+        d_req_out_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        d_req_st = torch.empty(n, dtype=torch.int32, device=dev)
+
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+
+    def step_resident():
+        if have_req:
+            eng.encode_batch_dev(schema, n, d_req_msg.data_ptr(), d_req.data_ptr(), d_req_off.data_ptr(), J_in, d_req_out.data_ptr(),
+                                 req_cap, d_req_out_off.data_ptr(), d_req_st.data_ptr(), 0, sp)
+        eng.decode_batch_dev(schema, n, d_rep_msg.data_ptr(), d_rep.data_ptr(), d_rep_off.data_ptr(), W_in, d_rep_out.data_ptr(),
+                             rep_cap, d_rep_out_off.data_ptr(), d_rep_st.data_ptr(), 0, sp)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also sizes the engine's scratch) ----
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+    if have_req:
+        assert int((d_req_st != 0).sum()) == 0, "request-side items failed"
+    assert int((d_rep_st != 0).sum()) == 0, "reply-side items failed"
+    W_out = int(d_req_out_off[n].item()) if have_req else 0
+    J_out = int(d_rep_out_off[n].item())
+
+    # ---- timed region: K steps, CUDA events on the launching stream, max over ranks ----
+    eng.profile_enable(True)
+    eng.profile_read()
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = eng.launch_count() - launches0
+    prof = eng.profile_read()
+    eng.profile_enable(False)
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    value = world * n * args.steps / (ms_max / 1000.0)
+
+    # ---- end-to-end: host (pinned) buffers through the public C-ABI call, copies included ----
+    e2e_steps = args.e2e_steps or min(args.steps, 5)
+    L = ggrmcp_b200.engine._load()
+
+    def pinned(a):
+        t = torch.empty(a.nbytes, dtype=torch.uint8).pin_memory()
+        t.numpy()[:] = a.view(np.uint8).reshape(-1)
+        return t
+
+    h_rep, h_rep_off, h_rep_msg = pinned(wl.rep_wire), pinned(wl.rep_off), pinned(wl.rep_msg)
+    h_rep_out = torch.empty(rep_cap, dtype=torch.uint8).pin_memory()
+    h_rep_out_off = torch.empty((n + 1) * 8, dtype=torch.uint8).pin_memory()
+    h_rep_st = torch.empty(n * 4, dtype=torch.uint8).pin_memory()
+    if have_req:
+        h_req, h_req_off, h_req_msg = pinned(wl.req_json), pinned(wl.req_off), pinned(wl.req_msg)
+        h_req_out = torch.empty(req_cap, dtype=torch.uint8).pin_memory()
+        h_req_out_off = torch.empty((n + 1) * 8, dtype=torch.uint8).pin_memory()
+        h_req_st = torch.empty(n * 4, dtype=torch.uint8).pin_memory()
+
+    def step_host():
+        if have_req:
+            rc = L.ggr_encode_batch(eng.h, schema.h, n, h_req_msg.data_ptr(), h_req.data_ptr(), h_req_off.data_ptr(), h_req_out.data_ptr(),
+                                    req_cap, h_req_out_off.data_ptr(), h_req_st.data_ptr(), 0)
+            assert rc == 0, rc
+        rc = L.ggr_decode_batch(eng.h, schema.h, n, h_rep_msg.data_ptr(), h_rep.data_ptr(), h_rep_off.data_ptr(), h_rep_out.data_ptr(),
+                                rep_cap, h_rep_out_off.data_ptr(), h_rep_st.data_ptr(), 0)
+        assert rc == 0, rc
+
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    t_e = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * e2e_steps / float(t_e.item())
+    # parity spot check of the host path result against the resident path
+    assert bytes(h_rep_out.numpy()[:64]) == bytes(d_rep_out[:64].cpu().numpy())
+    h2d = J_in + W_in + 2 * (n + 1) * 8 * (2 if have_req else 1) // 2 + n * 4 * (2 if have_req else 1)
+    d2h = W_out + J_out + ((n + 1) * 8 + n * 4) * (2 if have_req else 1)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (device time from CUDA events around each launch) ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg = {"encode_parse": J_in, "encode_emit": W_out, "decode_size": W_in, "decode_write": J_out,
+           "encode_scan": 0, "decode_scan": 0}
+    kern = {}
+    for k, (tot_ms, cnt) in prof.items():
+        if cnt:
+            avg = tot_ms / cnt
+            kern[k] = {"avg_ms": avg, "launches": cnt, "algorithmic_bytes": alg[k],
+                       "gbs": (alg[k] / (avg / 1000.0) / 1e9) if avg > 0 else None}
+    dom = max(kern, key=lambda k: kern[k]["avg_ms"]) if kern else None
+    step_ms = ms_max / args.steps
+    roofline = None
+    if dom:
+        a = kern[dom]["gbs"]
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
+                    "traffic": None, "peak_source": peak_src,
+                    "step_read_gbs": (J_in + W_in) / (step_ms / 1000.0) / 1e9,
+                    "step_total_gbs": (J_in + W_in + W_out + J_out) / (step_ms / 1000.0) / 1e9,
+                    "kernels": kern}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample = min(n, 16384 if args.workload != "blob" else 512)
+        rate, secs = cpu_oracle_rate(args.workload, sample, cores, repeats=2)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d items of the %s workload x2, oracle C++ port on %d threads (%.1f s)" % (sample, args.workload, cores, secs)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": {"nested": "configs[2] nested+repeated ~4KB JSON (complex.proto ProcessNodeRequest/CreateDocumentRequest; replies Node/GetUserProfileResponse)",
+                                "flat": "configs[1] 64K flat-scalar bench.Flat ~256B JSON",
+                                "blob": "configs[3] bench.Blob 64KiB bytes replies (reply side only)"}[args.workload],
+                   "items_per_gpu": n, "boundary": "InvokeMethod (arguments JSON -> wire, wire -> protojson)",
+                   "avg_bytes": {"J_in": J_in / n, "W_out": W_out / n, "W_in": W_in / n, "J_out": J_out / n},
+                   "l2": "inputs exceed L2 (%.0f MB read per step)" % ((J_in + W_in) / 1e6), "parallelism": "shard-by-index x%d, no collective" % world},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                "timing": "wall clock around the C-ABI host-buffer calls (pinned buffers), max over ranks"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

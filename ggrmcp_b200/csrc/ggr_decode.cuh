@@ -1,0 +1,1207 @@
+// ggr_decode.cuh - response side: protobuf wire bytes -> protojson text.
+//
+// Replaces, per item, proto.Unmarshal into a dynamicpb message (inside conn.Invoke) followed by
+// protojson.Marshal (/root/reference/pkg/grpc/reflection.go:363,373,381).  JSON has no length
+// prefixes, so the text streams out in one walk of the wire bytes; the walk runs twice with the
+// same code - once over a counting writer to size the item, once over the real writer at the
+// item's final offset.
+//
+//  fast walk : wire fields arrive in declaration order, singular fields once, repeated elements
+//              contiguous (what every generated-code backend emits when declaration order ==
+//              field-number order).  Map entries are put in key order on the fly.
+//  slow walk : anything else (out-of-order fields, duplicates with last-wins, split repeated
+//              fields): for each field in declaration order, scan the payload for its
+//              occurrences.  The size pass detects the need and records it per item.
+// Semantics restated from [upstream proto/decode.go unmarshalMessageSlow,
+// encoding/protojson/encode.go, internal/encoding/json/encode.go, internal/order];
+// oracle/orc_dyn.h + orc_protojson.h hold the line-by-line restatement the tests compare against.
+#pragma once
+#include "ggr_prim.cuh"
+#include "ggr_json_in.cuh"
+
+#define GGR_DEC_MAX_DEPTH 32
+#ifndef GGR_F_COMMA_SPACE
+#define GGR_F_COMMA_SPACE 1u
+#endif
+
+#define GGR_MODE_FAST 0u
+#define GGR_MODE_SLOW 1u
+#define GGR_NEED_SLOW 1000  /* internal: fast walk met an ordering it cannot stream */
+
+struct DecResult {
+  u32 size;
+  u32 mode;
+};
+
+// ---- wire readers ----
+GGR_DEV void rd_jump(Rd& r, u32 pos) {
+  u32 e = r.end;
+  r.init(r.base, pos, e);
+}
+// protowire.ConsumeVarint bounded by `lim`
+GGR_DEV bool rd_varint(Rd& r, u32 lim, u64* out) {
+  u64 v = 0;
+  for (int i = 0; i < 10; i++) {
+    if (r.pos >= lim) return false;
+    u32 c = r.peek();
+    r.skip(1);
+    if (i == 9 && c > 1) return false;
+    v |= (u64)(c & 0x7F) << (7 * i);
+    if (c < 0x80) {
+      *out = v;
+      return true;
+    }
+  }
+  return false;
+}
+GGR_DEV bool rd_fixed32(Rd& r, u32 lim, u32* out) {
+  if (lim - r.pos < 4 || r.pos > lim) return false;
+  *out = r.peek4();
+  r.skip(4);
+  return true;
+}
+GGR_DEV bool rd_fixed64(Rd& r, u32 lim, u64* out) {
+  u32 lo, hi;
+  if (!rd_fixed32(r, lim, &lo) || !rd_fixed32(r, lim, &hi)) return false;
+  *out = (u64)lo | ((u64)hi << 32);
+  return true;
+}
+// skips the value of an unknown field (after its tag)
+GGR_DEV bool rd_skip_value(Rd& r, u32 lim, u32 num, u32 wt) {
+  u64 v;
+  switch (wt) {
+    case 0: return rd_varint(r, lim, &v);
+    case 1: if (lim - r.pos < 8) return false; rd_jump(r, r.pos + 8); return true;
+    case 5: if (lim - r.pos < 4) return false; r.skip(4); return true;
+    case 2:
+      if (!rd_varint(r, lim, &v) || v > (u64)(lim - r.pos)) return false;
+      rd_jump(r, r.pos + (u32)v);
+      return true;
+    case 3: {
+      u32 nums[8];
+      int sp = 0;
+      nums[sp++] = num;
+      while (sp > 0) {
+        u64 tag;
+        if (!rd_varint(r, lim, &tag)) return false;
+        u64 n2 = tag >> 3;
+        u32 w2 = (u32)(tag & 7);
+        if (n2 == 0 || n2 > 0x1FFFFFFFull) return false;
+        if (w2 == 4) {
+          if ((u32)n2 != nums[sp - 1]) return false;
+          sp--;
+        } else if (w2 == 3) {
+          if (sp >= 8) return false;
+          nums[sp++] = (u32)n2;
+        } else if (!rd_skip_value(r, lim, (u32)n2, w2)) {
+          return false;
+        }
+      }
+      return true;
+    }
+    default: return false;
+  }
+}
+
+// ---- JSON writers ----
+template <class W>
+GGR_DEV void put_pool(W& w, const u8* pool, u32 off, u32 len) {
+  Rd p;
+  p.init(pool, off, off + len);
+  while (len >= 4) {
+    w.put(p.peek4(), 4);
+    p.skip(4);
+    len -= 4;
+  }
+  if (len) w.put(p.peek4() & (0xFFFFFFFFu >> (8 * (4 - len))), (int)len);
+}
+template <class W>
+GGR_DEV void put_group8(W& w, u64 p, int k) {  // k digits, most significant in the lowest byte
+  if (k > 4) {
+    w.put((u32)p, 4);
+    w.put((u32)(p >> 32) & (0xFFFFFFFFu >> (8 * (8 - k))), k - 4);
+  } else if (k > 0) {
+    w.put((u32)p & (0xFFFFFFFFu >> (8 * (4 - k))), k);
+  }
+}
+template <class W>
+GGR_DEV void put_dec_u64(W& w, u64 v) {
+  u64 p0 = 0, p1 = 0, p2 = 0;
+  int n = 0;
+  if ((v >> 32) == 0) {
+    u32 x = (u32)v;
+    do {
+      u32 q = x / 10u;
+      u32 d = x - q * 10u;
+      if (n < 8) p0 = (p0 << 8) | (u64)('0' + d);
+      else p1 = (p1 << 8) | (u64)('0' + d);
+      n++;
+      x = q;
+    } while (x);
+  } else {
+    do {
+      u64 q = v / 10u;
+      u32 d = (u32)(v - q * 10u);
+      if (n < 8) p0 = (p0 << 8) | (u64)('0' + d);
+      else if (n < 16) p1 = (p1 << 8) | (u64)('0' + d);
+      else p2 = (p2 << 8) | (u64)('0' + d);
+      n++;
+      v = q;
+    } while (v);
+  }
+  if (n > 16) put_group8(w, p2, n - 16);
+  if (n > 8) put_group8(w, p1, n > 16 ? 8 : n - 8);
+  put_group8(w, p0, n > 8 ? 8 : n);
+}
+template <class W>
+GGR_DEV void put_dec_i64(W& w, i64 v) {
+  if (v < 0) {
+    w.put1('-');
+    put_dec_u64(w, (u64)0 - (u64)v);
+  } else {
+    put_dec_u64(w, (u64)v);
+  }
+}
+template <class W>
+GGR_DEV void put_2d(W& w, u32 v) { w.put(('0' + v / 10) | (('0' + v % 10) << 8), 2); }
+
+// protojson string: reader `r` positioned at the first payload byte, `len` bytes long.
+// [upstream internal/encoding/json appendString]
+template <class W>
+GGR_DEV int put_json_string(W& w, Rd& r, u32 len) {
+  u32 save_end = r.end;
+  r.end = r.pos + len;
+  w.put1('"');
+  int st = GST_OK;
+  for (;;) {
+    while (r.left() >= 4) {
+      u32 x = r.peek4();
+      if (json_special_mask(x)) break;
+      w.put(x, 4);
+      r.skip(4);
+    }
+    if (r.eof()) break;
+    u32 c = r.peek();
+    if (c >= 0x80) {
+      int k = utf8_seq_len(r);
+      if (k == 0) {
+        st = GST_INVALID_UTF8;
+        break;
+      }
+      w.put(r.peek4() & (0xFFFFFFFFu >> (8 * (4 - k))), k);
+      r.skip(k);
+      continue;
+    }
+    if (c >= 0x20 && c != '"' && c != '\\') {
+      w.put1(c);
+      r.skip(1);
+      continue;
+    }
+    u32 e;
+    switch (c) {
+      case '"': e = '"'; break;
+      case '\\': e = '\\'; break;
+      case 8: e = 'b'; break;
+      case 12: e = 'f'; break;
+      case 10: e = 'n'; break;
+      case 13: e = 'r'; break;
+      case 9: e = 't'; break;
+      default: e = 0; break;
+    }
+    if (e) {
+      w.put('\\' | (e << 8), 2);
+    } else {
+      u32 hi = c >> 4, lo = c & 15;
+      w.put(LIT4('\\', 'u', '0', '0'), 4);
+      w.put(('0' + hi) | ((lo < 10 ? '0' + lo : 'a' + lo - 10) << 8), 2);
+    }
+    r.skip(1);
+  }
+  w.put1('"');
+  if (st != GST_OK) rd_jump(r, r.end);
+  r.end = save_end;
+  return st;
+}
+
+GGR_DEV u32 b64_char(u32 v) {
+  return v + 65u + (v >= 26u ? 6u : 0u) - (v >= 52u ? 75u : 0u) - (v >= 62u ? 15u : 0u) + (v >= 63u ? 3u : 0u);
+}
+template <class W>
+GGR_DEV void put_base64(W& w, Rd& r, u32 len) {
+  w.put1('"');
+  while (len >= 3) {
+    u32 x = r.peek4();
+    u32 v = ((x & 0xFF) << 16) | (x & 0xFF00) | ((x >> 16) & 0xFF);
+    w.put(b64_char(v >> 18) | (b64_char((v >> 12) & 63) << 8) | (b64_char((v >> 6) & 63) << 16) | (b64_char(v & 63) << 24), 4);
+    r.skip(3);
+    len -= 3;
+  }
+  if (len == 1) {
+    u32 v = (r.peek() & 0xFF) << 16;
+    w.put(b64_char(v >> 18) | (b64_char((v >> 12) & 63) << 8) | ('=' << 16) | ('=' << 24), 4);
+    r.skip(1);
+  } else if (len == 2) {
+    u32 x = r.peek4();
+    u32 v = ((x & 0xFF) << 16) | (x & 0xFF00);
+    w.put(b64_char(v >> 18) | (b64_char((v >> 12) & 63) << 8) | (b64_char((v >> 6) & 63) << 16) | ('=' << 24), 4);
+    r.skip(2);
+  }
+  w.put1('"');
+}
+
+// google.protobuf.Timestamp -> "YYYY-MM-DDTHH:MM:SS[.fff[fff[fff]]]Z" [upstream marshalTimestamp]
+template <class W>
+GGR_DEV int put_timestamp(W& w, i64 secs, i64 nanos) {
+  if (secs < -62135596800ll || secs > 253402300799ll) return GST_RANGE;
+  if (nanos < 0 || nanos > 1000000000ll) return GST_RANGE;
+  if (nanos == 1000000000ll) {  // time.Unix normalizes
+    secs += 1;
+    nanos = 0;
+  }
+  i64 days = secs / 86400, rem = secs % 86400;
+  if (rem < 0) {
+    rem += 86400;
+    days--;
+  }
+  // civil_from_days
+  i64 z = days + 719468;
+  i64 era = (z >= 0 ? z : z - 146096) / 146097;
+  u32 doe = (u32)(z - era * 146097);
+  u32 yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+  i64 y = (i64)yoe + era * 400;
+  u32 doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+  u32 mp = (5 * doy + 2) / 153;
+  u32 d = doy - (153 * mp + 2) / 5 + 1;
+  u32 m = mp < 10 ? mp + 3 : mp - 9;
+  y += m <= 2;
+  u32 yy = (u32)y;  // 1..9999 (range-checked above); the year 10000 cannot occur
+  w.put1('"');
+  put_2d(w, yy / 100);
+  put_2d(w, yy % 100);
+  w.put1('-');
+  put_2d(w, m);
+  w.put1('-');
+  put_2d(w, d);
+  w.put1('T');
+  u32 sod = (u32)rem;
+  put_2d(w, sod / 3600);
+  w.put1(':');
+  put_2d(w, sod % 3600 / 60);
+  w.put1(':');
+  put_2d(w, sod % 60);
+  u32 ns = (u32)nanos;
+  if (ns != 0) {
+    w.put1('.');
+    u32 a = ns / 1000000, b = ns / 1000 % 1000, c = ns % 1000;
+    w.put(('0' + a / 100) | (('0' + a / 10 % 10) << 8) | (('0' + a % 10) << 16), 3);
+    if (b != 0 || c != 0) {
+      w.put(('0' + b / 100) | (('0' + b / 10 % 10) << 8) | (('0' + b % 10) << 16), 3);
+      if (c != 0) w.put(('0' + c / 100) | (('0' + c / 10 % 10) << 8) | (('0' + c % 10) << 16), 3);
+    }
+  }
+  w.put('Z' | ('"' << 8), 2);
+  return GST_OK;
+}
+
+struct DecCtx {
+  Tables T;
+  const u8* in;
+  u32 flags;
+};
+
+template <class W>
+GGR_DEV void put_sep(W& w, const DecCtx& cx, u32& first) {
+  if (!first) {
+    w.put1(',');
+    if (cx.flags & GGR_F_COMMA_SPACE) w.put1(' ');
+  }
+  first = 0;
+}
+
+// field lookup by number; returns emit index or -1
+GGR_DEV i32 find_field(const Tables& T, const MsgD& md, u32 num) {
+  if (num < md.lut_n) return (i32)ggr_u16(T, md.lut_first + num) - 1;
+  for (u32 i = 0; i < md.n_fields; i++) {
+    U4 a = ggr_ld16(T.fields + (size_t)(md.field_first + i) * 32);
+    if (a.x == num) return (i32)i;
+  }
+  return -1;
+}
+
+// Reads a google.protobuf.Timestamp payload [r.pos, lim): last value wins, unknown fields skipped.
+GGR_DEV int read_timestamp_payload(Rd& r, u32 lim, i64* secs, i64* nanos) {
+  *secs = 0;
+  *nanos = 0;
+  while (r.pos < lim) {
+    u64 tag, v;
+    if (!rd_varint(r, lim, &tag)) return GST_BAD_WIRE;
+    u64 num = tag >> 3;
+    u32 wt = (u32)(tag & 7);
+    if (num == 0 || num > 0x1FFFFFFFull || wt == 4) return GST_BAD_WIRE;
+    if (num == 1 && wt == 0) {
+      if (!rd_varint(r, lim, &v)) return GST_BAD_WIRE;
+      *secs = (i64)v;
+    } else if (num == 2 && wt == 0) {
+      if (!rd_varint(r, lim, &v)) return GST_BAD_WIRE;
+      *nanos = (i64)(i32)(u32)v;
+    } else if (!rd_skip_value(r, lim, (u32)num, wt)) {
+      return GST_BAD_WIRE;
+    }
+  }
+  return r.pos == lim ? GST_OK : GST_BAD_WIRE;
+}
+
+// One scalar (non-message) value of field f read at r and written as JSON.
+// *zero is set when the value is the zero value of its kind (implicit-presence elision).
+// With EMIT=false the value is only read (and validated).
+template <class W, bool EMIT>
+GGR_DEV int scalar_value(W& w, const DecCtx& cx, Rd& r, u32 lim, u32 kind, i32 child, bool quoted_key, bool* zero) {
+  u64 v = 0;
+  switch (kind) {
+    case GK_INT32: case GK_INT64: case GK_UINT32: case GK_UINT64: case GK_SINT32: case GK_SINT64: case GK_BOOL: case GK_ENUM:
+      if (!rd_varint(r, lim, &v)) return GST_BAD_WIRE;
+      break;
+    case GK_FIXED32: case GK_SFIXED32: case GK_FLOAT: {
+      u32 x;
+      if (!rd_fixed32(r, lim, &x)) return GST_BAD_WIRE;
+      v = x;
+      break;
+    }
+    case GK_FIXED64: case GK_SFIXED64: case GK_DOUBLE:
+      if (!rd_fixed64(r, lim, &v)) return GST_BAD_WIRE;
+      break;
+    case GK_STRING: case GK_BYTES: {
+      u64 len;
+      if (!rd_varint(r, lim, &len) || len > (u64)(lim - r.pos)) return GST_BAD_WIRE;
+      *zero = len == 0;
+      if (kind == GK_STRING) {
+        // validation happens even for elided/unwritten strings (proto.Unmarshal rejects bad UTF-8)
+        if (EMIT) return put_json_string(w, r, (u32)len);
+        Cnt c;
+        c.pos = 0;
+        return put_json_string(c, r, (u32)len);
+      }
+      if (EMIT) put_base64(w, r, (u32)len);
+      else rd_jump(r, r.pos + (u32)len);
+      return GST_OK;
+    }
+    default: return GST_UNSUPPORTED;
+  }
+  i64 sv = 0;
+  bool is_signed = false, is64 = false;
+  switch (kind) {
+    case GK_INT32: case GK_ENUM: sv = (i64)(i32)(u32)v; is_signed = true; break;
+    case GK_SINT32: { u32 x = (u32)v; sv = (i64)(i32)((x >> 1) ^ (0u - (x & 1))); is_signed = true; break; }
+    case GK_SFIXED32: sv = (i64)(i32)(u32)v; is_signed = true; break;
+    case GK_UINT32: case GK_FIXED32: v = (u32)v; break;
+    case GK_INT64: case GK_SFIXED64: sv = (i64)v; is_signed = true; is64 = true; break;
+    case GK_SINT64: sv = (i64)((v >> 1) ^ (0ull - (v & 1))); is_signed = true; is64 = true; break;
+    case GK_UINT64: case GK_FIXED64: is64 = true; break;
+    case GK_BOOL: v = v != 0; break;
+    case GK_FLOAT: case GK_DOUBLE: return GST_UNSUPPORTED;  // shortest float printing lands with the float kernels
+    default: break;
+  }
+  *zero = is_signed ? sv == 0 : v == 0;
+  if (!EMIT) return GST_OK;
+  if (kind == GK_BOOL) {
+    if (quoted_key) w.put1('"');
+    if (v) w.put(LIT4('t', 'r', 'u', 'e'), 4);
+    else {
+      w.put(LIT4('f', 'a', 'l', 's'), 4);
+      w.put1('e');
+    }
+    if (quoted_key) w.put1('"');
+    return GST_OK;
+  }
+  if (kind == GK_ENUM) {
+    // protoreflect EnumValueDescriptors.ByNumber: binary search over the distinct numbers
+    U4 e = ggr_ld16(cx.T.enums + (size_t)child * 16);
+    u32 lo = 0, hi = e.y;
+    while (lo < hi) {
+      u32 mid = (lo + hi) >> 1;
+      U4 ev = ggr_ld16(cx.T.evals + (size_t)(e.x + mid) * 16);
+      i32 num = (i32)ev.x;
+      if (num == (i32)sv) {
+        w.put1('"');
+        put_pool(w, cx.T.pool, ev.y, ev.z);
+        w.put1('"');
+        return GST_OK;
+      }
+      if (num < (i32)sv) lo = mid + 1;
+      else hi = mid;
+    }
+    put_dec_i64(w, sv);
+    return GST_OK;
+  }
+  bool q = is64 || quoted_key;
+  if (q) w.put1('"');
+  if (is_signed) put_dec_i64(w, sv);
+  else put_dec_u64(w, v);
+  if (q) w.put1('"');
+  return GST_OK;
+}
+
+// ---- map entries ----
+struct MapEnt {
+  u64 key;      // numeric key / (pos | len << 32) of a string key's payload
+  u32 val_pos;  // position of the value's payload-or-varint start (after its tag); 0 = absent
+  u32 val_len;  // for LEN values: payload length
+  u32 end;      // end of the entry payload
+};
+// Parses one map entry payload [r.pos, lim): key (field 1) and value (field 2), last wins.
+GGR_DEV int parse_map_entry(Rd& r, u32 lim, const FieldD& kf, const FieldD& vf, MapEnt* me) {
+  me->key = 0;
+  me->val_pos = 0;
+  me->val_len = 0;
+  me->end = lim;
+  bool str_key = kf.kind == GK_STRING;
+  if (str_key) me->key = (u64)r.pos;  // empty string key: len 0 at any position
+  u32 val_seen = 0;
+  while (r.pos < lim) {
+    u64 tag, v;
+    if (!rd_varint(r, lim, &tag)) return GST_BAD_WIRE;
+    u64 num = tag >> 3;
+    u32 wt = (u32)(tag & 7);
+    if (num == 0 || num > 0x1FFFFFFFull || wt == 4) return GST_BAD_WIRE;
+    if (num == 1 && wt == kf.wt) {
+      if (str_key) {
+        if (!rd_varint(r, lim, &v) || v > (u64)(lim - r.pos)) return GST_BAD_WIRE;
+        me->key = (u64)r.pos | (v << 32);
+        rd_jump(r, r.pos + (u32)v);
+      } else if (wt == 0) {
+        if (!rd_varint(r, lim, &v)) return GST_BAD_WIRE;
+        switch (kf.kind) {
+          case GK_INT32: v = (u64)(i64)(i32)(u32)v; break;
+          case GK_SINT32: { u32 x = (u32)v; v = (u64)(i64)(i32)((x >> 1) ^ (0u - (x & 1))); break; }
+          case GK_SINT64: v = (v >> 1) ^ (0ull - (v & 1)); break;
+          case GK_UINT32: v = (u32)v; break;
+          case GK_BOOL: v = v != 0; break;
+          default: break;
+        }
+        me->key = v;
+      } else if (wt == 5) {
+        u32 x;
+        if (!rd_fixed32(r, lim, &x)) return GST_BAD_WIRE;
+        me->key = kf.kind == GK_SFIXED32 ? (u64)(i64)(i32)x : (u64)x;
+      } else {
+        if (!rd_fixed64(r, lim, &me->key)) return GST_BAD_WIRE;
+      }
+    } else if (num == 2 && wt == vf.wt) {
+      if (vf.kind == GK_MESSAGE && val_seen) return GST_UNSUPPORTED;  // merging split map values
+      val_seen = 1;
+      me->val_pos = r.pos;
+      if (wt == 2) {
+        if (!rd_varint(r, lim, &v) || v > (u64)(lim - r.pos)) return GST_BAD_WIRE;
+        me->val_pos = r.pos;
+        me->val_len = (u32)v;
+        rd_jump(r, r.pos + (u32)v);
+      } else if (!rd_skip_value(r, lim, 2, wt)) {
+        return GST_BAD_WIRE;
+      }
+    } else if (!rd_skip_value(r, lim, (u32)num, wt)) {
+      return GST_BAD_WIRE;
+    }
+  }
+  return r.pos == lim ? GST_OK : GST_BAD_WIRE;
+}
+// order.GenericKeyOrder: bool false<true, signed/unsigned numeric, strings bytewise
+GGR_DEV int cmp_map_keys(const DecCtx& cx, u32 kkind, u64 a, u64 b) {
+  if (kkind == GK_STRING) {
+    u32 la = (u32)(a >> 32), lb = (u32)(b >> 32);
+    Rd ra, rb;
+    ra.init(cx.in, (u32)a, (u32)a + la);
+    rb.init(cx.in, (u32)b, (u32)b + lb);
+    u32 n = la < lb ? la : lb;
+    while (n >= 4) {
+      u32 x = ra.peek4(), y = rb.peek4();
+      if (x != y) {
+        // first differing byte decides (little-endian: lowest differing byte)
+        u32 d = x ^ y;
+        int sh = ggr_ctz32(d) & ~7;
+        u32 bx = (x >> sh) & 0xFF, by = (y >> sh) & 0xFF;
+        return bx < by ? -1 : 1;
+      }
+      ra.skip(4);
+      rb.skip(4);
+      n -= 4;
+    }
+    while (n > 0) {
+      u32 x = ra.peek(), y = rb.peek();
+      if (x != y) return x < y ? -1 : 1;
+      ra.skip(1);
+      rb.skip(1);
+      n--;
+    }
+    return la < lb ? -1 : (la > lb ? 1 : 0);
+  }
+  bool uns = kkind == GK_UINT32 || kkind == GK_UINT64 || kkind == GK_FIXED32 || kkind == GK_FIXED64 || kkind == GK_BOOL;
+  if (uns) return a < b ? -1 : (a > b ? 1 : 0);
+  return (i64)a < (i64)b ? -1 : ((i64)a > (i64)b ? 1 : 0);
+}
+
+template <class W>
+GGR_DEV int put_map_key(W& w, const DecCtx& cx, u32 kkind, u64 key) {
+  if (kkind == GK_STRING) {
+    Rd r;
+    r.init(cx.in, (u32)key, (u32)key + (u32)(key >> 32));
+    return put_json_string(w, r, (u32)(key >> 32));
+  }
+  w.put1('"');
+  if (kkind == GK_BOOL) {
+    if (key) w.put(LIT4('t', 'r', 'u', 'e'), 4);
+    else {
+      w.put(LIT4('f', 'a', 'l', 's'), 4);
+      w.put1('e');
+    }
+  } else {
+    bool uns = kkind == GK_UINT32 || kkind == GK_UINT64 || kkind == GK_FIXED32 || kkind == GK_FIXED64;
+    if (uns) put_dec_u64(w, key);
+    else put_dec_i64(w, (i64)key);
+  }
+  w.put1('"');
+  return GST_OK;
+}
+
+struct DFrame {
+  u32 end;        // payload end
+  u32 msg;        // message index
+  i32 last_decl;  // declaration index of the last field seen (fast) / cursor (slow)
+  u32 open;       // fast: emit index + 1 of the repeated field whose '[' is open
+  u32 first;      // nothing written yet inside this object
+  u32 elem_first; // nothing written yet inside the open array
+  u32 oneofs;     // oneofs already written
+  // slow walk state
+  u32 start;      // payload start
+  u32 scan;       // resume position of the current field's occurrence scan
+  u32 cur_emit;   // emit index of the field being scanned
+  u32 state;      // slow: 0 = advance to next field, 1 = inside repeated occurrences
+};
+
+// Emits all entries of map field `f` found as a contiguous run of tags starting at r.pos
+// (fast walk) or anywhere in [scan_from, lim) (slow walk, contiguous=false).  Entries come out
+// in key order with last-wins on duplicate keys.  Message-valued entries are handled by
+// returning to the caller one at a time: see walk loops.
+//
+// To keep the walkers simple, message-valued map entries are written through a nested call of
+// the walker entry point for the value payload (depth-bounded); scalars are written here.
+#define GGR_DEC_MAX_REC 3 /* message-valued map entries nest by (bounded) recursion */
+template <class W, bool SLOW>
+GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 msg, u32 start, u32 end, int rec);
+
+template <class W, bool SLOW>
+GGR_DEV int put_map_value(W& w, const DecCtx& cx, const FieldD& vf, const MapEnt& me, int rec) {
+  if (vf.kind == GK_MESSAGE) {
+    MsgD vd = ggr_msg(cx.T, (u32)vf.child);
+    if (vd.wkt == GGR_WKT_TIMESTAMP) {
+      i64 s = 0, n = 0;
+      if (me.val_pos) {
+        Rd r;
+        r.init(cx.in, me.val_pos, me.val_pos + me.val_len);
+        int st = read_timestamp_payload(r, me.val_pos + me.val_len, &s, &n);
+        if (st != GST_OK) return st;
+      }
+      return put_timestamp(w, s, n);
+    }
+    if (vd.wkt != GGR_WKT_NONE) return GST_UNSUPPORTED;
+    if (!me.val_pos) {
+      w.put('{' | ('}' << 8), 2);
+      return GST_OK;
+    }
+    return walk_message<W, SLOW>(w, cx, (u32)vf.child, me.val_pos, me.val_pos + me.val_len, rec + 1);
+  }
+  if (!me.val_pos) {
+    // absent value: zero value of the kind
+    switch (vf.kind) {
+      case GK_STRING: case GK_BYTES: w.put('"' | ('"' << 8), 2); return GST_OK;
+      case GK_BOOL: w.put(LIT4('f', 'a', 'l', 's'), 4); w.put1('e'); return GST_OK;
+      case GK_INT64: case GK_UINT64: case GK_SINT64: case GK_FIXED64: case GK_SFIXED64: w.put('"' | ('0' << 8) | ('"' << 16), 3); return GST_OK;
+      case GK_FLOAT: case GK_DOUBLE: w.put1('0'); return GST_OK;
+      case GK_ENUM: break;  // name of number 0 or the number itself: fall through to the generic writer
+      default: w.put1('0'); return GST_OK;
+    }
+    if (vf.kind == GK_ENUM) {
+      // run the generic writer over a synthetic zero varint: simplest is the name lookup inline
+      U4 e = ggr_ld16(cx.T.enums + (size_t)vf.child * 16);
+      u32 lo = 0, hi = e.y;
+      while (lo < hi) {
+        u32 mid = (lo + hi) >> 1;
+        U4 ev = ggr_ld16(cx.T.evals + (size_t)(e.x + mid) * 16);
+        if ((i32)ev.x == 0) {
+          w.put1('"');
+          put_pool(w, cx.T.pool, ev.y, ev.z);
+          w.put1('"');
+          return GST_OK;
+        }
+        if ((i32)ev.x < 0) lo = mid + 1;
+        else hi = mid;
+      }
+      w.put1('0');
+      return GST_OK;
+    }
+  }
+  Rd r;
+  u32 lim = me.end;
+  r.init(cx.in, me.val_pos, lim);
+  if (vf.wt == 2) {
+    // scalar_value re-reads the length prefix: step back is not possible, so emit directly
+    bool z;
+    if (vf.kind == GK_STRING) return put_json_string(w, r, me.val_len);
+    put_base64(w, r, me.val_len);
+    return GST_OK;
+  }
+  bool z;
+  return scalar_value<W, true>(w, cx, r, lim, vf.kind, vf.child, false, &z);
+}
+
+// Map field writer.  `r` is positioned right after the tag of the first entry (fast walk) and is
+// left after the last entry of the run.  In the slow walk the entries are all occurrences of the
+// field inside [pstart, pend).
+template <class W, bool SLOW>
+GGR_DEV int put_map_field(W& w, const DecCtx& cx, Rd& r, const FieldD& f, u32 pstart, u32 pend, int rec) {
+  MsgD ed = ggr_msg(cx.T, (u32)f.child);
+  FieldD kf = ggr_field(cx.T, ed.field_first), vf = ggr_field(cx.T, ed.field_first + 1);
+  // pass 1: find the run / all occurrences, validate, check ordering
+  u32 run_start, run_end;
+  bool sorted = true;
+  u32 count = 0;
+  {
+    u64 prev = 0;
+    if (!SLOW) {
+      run_start = r.pos;  // after the first tag
+      bool first = true;
+      for (;;) {
+        if (!first) {
+          // peek the next tag: same field and LEN?
+          Rd t = r;
+          u64 tag;
+          if (t.pos >= pend || !rd_varint(t, pend, &tag) || tag != (u64)f.tag) break;
+          r = t;
+        }
+        first = false;
+        u64 len;
+        if (!rd_varint(r, pend, &len) || len > (u64)(pend - r.pos)) return GST_BAD_WIRE;
+        MapEnt me;
+        u32 lim = r.pos + (u32)len;
+        int st = parse_map_entry(r, lim, kf, vf, &me);
+        if (st != GST_OK) return st;
+        if (count > 0 && cmp_map_keys(cx, kf.kind, prev, me.key) >= 0) sorted = false;
+        prev = me.key;
+        count++;
+      }
+      run_end = r.pos;
+    } else {
+      run_start = pstart;
+      run_end = pend;
+      Rd t;
+      t.init(cx.in, pstart, pend);
+      while (t.pos < pend) {
+        u64 tag;
+        if (!rd_varint(t, pend, &tag)) return GST_BAD_WIRE;
+        u32 wt = (u32)(tag & 7);
+        if (tag == (u64)f.tag) {
+          u64 len;
+          if (!rd_varint(t, pend, &len) || len > (u64)(pend - t.pos)) return GST_BAD_WIRE;
+          MapEnt me;
+          int st = parse_map_entry(t, t.pos + (u32)len, kf, vf, &me);
+          if (st != GST_OK) return st;
+          if (count > 0 && cmp_map_keys(cx, kf.kind, prev, me.key) >= 0) sorted = false;
+          prev = me.key;
+          count++;
+        } else if (!rd_skip_value(t, pend, (u32)(tag >> 3), wt)) {
+          return GST_BAD_WIRE;
+        }
+      }
+    }
+  }
+  if (count == 0) return GST_OK;
+  // pass 2: emit in key order.  Already sorted (the usual case for deterministic backends): one
+  // sweep.  Otherwise selection by key: each round picks the smallest key above the last one
+  // written, taking the LAST occurrence of that key (map semantics: last wins).
+  w.put1('{');
+  u32 efirst = 1;
+  u64 last_key = 0;
+  bool have_last = false;
+  u32 rounds = sorted ? 1u : count;
+  for (u32 round = 0; round < rounds; round++) {
+    MapEnt best;
+    bool have_best = false;
+    Rd t;
+    t.init(cx.in, run_start, run_end);
+    bool first_in_run = !SLOW;
+    while (t.pos < run_end) {
+      if (!first_in_run) {
+        u64 tag;
+        if (!rd_varint(t, run_end, &tag)) return GST_BAD_WIRE;
+        if (tag != (u64)f.tag) {
+          if (!rd_skip_value(t, run_end, (u32)(tag >> 3), (u32)(tag & 7))) return GST_BAD_WIRE;
+          continue;
+        }
+      }
+      first_in_run = false;
+      u64 len;
+      if (!rd_varint(t, run_end, &len)) return GST_BAD_WIRE;
+      MapEnt me;
+      int st = parse_map_entry(t, t.pos + (u32)len, kf, vf, &me);
+      if (st != GST_OK) return st;
+      if (sorted) {
+        put_sep(w, cx, efirst);
+        st = put_map_key(w, cx, kf.kind, me.key);
+        if (st != GST_OK) return st;
+        w.put1(':');
+        st = put_map_value<W, SLOW>(w, cx, vf, me, rec);
+        if (st != GST_OK) return st;
+        continue;
+      }
+      if (have_last && cmp_map_keys(cx, kf.kind, me.key, last_key) <= 0) continue;
+      if (!have_best || cmp_map_keys(cx, kf.kind, me.key, best.key) <= 0) {
+        best = me;  // smaller key, or a later occurrence of the same key
+        have_best = true;
+      }
+    }
+    if (sorted) break;
+    if (!have_best) break;
+    put_sep(w, cx, efirst);
+    int st = put_map_key(w, cx, kf.kind, best.key);
+    if (st != GST_OK) return st;
+    w.put1(':');
+    st = put_map_value<W, SLOW>(w, cx, vf, best, rec);
+    if (st != GST_OK) return st;
+    last_key = best.key;
+    have_last = true;
+  }
+  w.put1('}');
+  return GST_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The walker.  Recursion is only used for message values inside map entries and is bounded by
+// `depth`; ordinary nesting uses the explicit frame stack.
+// ---------------------------------------------------------------------------------------------
+template <class W, bool SLOW>
+GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 end, int rec) {
+  if (rec > GGR_DEC_MAX_REC) return GST_DEPTH;
+  const Tables& T = cx.T;
+  DFrame stk[GGR_DEC_MAX_DEPTH];
+  int depth = 0;
+  Rd r;
+  r.init(cx.in, start, end);
+  DFrame fr;
+  fr.end = end; fr.msg = root_msg; fr.last_decl = -1; fr.open = 0; fr.first = 1; fr.elem_first = 1; fr.oneofs = 0;
+  fr.start = start; fr.scan = start; fr.cur_emit = 0; fr.state = 0;
+  MsgD md = ggr_msg(T, root_msg);
+  if (md.wkt == GGR_WKT_TIMESTAMP) {
+    i64 s, n;
+    int st = read_timestamp_payload(r, end, &s, &n);
+    if (st != GST_OK) return st;
+    return put_timestamp(w, s, n);
+  }
+  if (md.wkt != GGR_WKT_NONE) return GST_UNSUPPORTED;
+  w.put1('{');
+
+  for (;;) {
+    if (!SLOW) {
+      // ================= fast walk =================
+      if (r.pos >= fr.end) {
+        if (r.pos != fr.end) return GST_BAD_WIRE;
+        if (fr.open) w.put1(']');
+        w.put1('}');
+        if (depth == 0) return GST_OK;
+        fr = stk[--depth];
+        md = ggr_msg(T, fr.msg);
+        continue;
+      }
+      u64 tag;
+      if (!rd_varint(r, fr.end, &tag)) return GST_BAD_WIRE;
+      u64 num64 = tag >> 3;
+      u32 wt = (u32)(tag & 7);
+      if (num64 == 0 || num64 > 0x1FFFFFFFull || wt == 4 || wt > 5) return GST_BAD_WIRE;
+      u32 num = (u32)num64;
+      i32 ei = find_field(T, md, num);
+      if (ei < 0) {
+        if (!rd_skip_value(r, fr.end, num, wt)) return GST_BAD_WIRE;
+        continue;
+      }
+      FieldD f = ggr_field(T, md.field_first + (u32)ei);
+      bool packed_in = (f.flags & GF_PACKABLE) && wt == 2;
+      if (wt != f.wt && !packed_in) {  // wire type mismatch: treated as an unknown field
+        if (!rd_skip_value(r, fr.end, num, wt)) return GST_BAD_WIRE;
+        continue;
+      }
+      if (f.flags & GF_MAP) {
+        if (fr.open) { w.put1(']'); fr.open = 0; }
+        if ((i32)f.decl_index <= fr.last_decl) return GGR_NEED_SLOW;
+        fr.last_decl = (i32)f.decl_index;
+        // the key text is written only when the map has entries (always true here)
+        put_sep(w, cx, fr.first);
+        put_pool(w, T.pool, f.name_off, f.name_len);
+        int st = put_map_field<W, false>(w, cx, r, f, r.pos, fr.end, rec);
+        if (st != GST_OK) return st;
+        continue;
+      }
+      if (f.flags & GF_REPEATED) {
+        if (fr.open != (u32)ei + 1) {
+          if (fr.open) w.put1(']');
+          fr.open = 0;
+          if ((i32)f.decl_index <= fr.last_decl) return GGR_NEED_SLOW;
+          // a packed field with an empty payload contributes no elements: dynamicpb then holds
+          // an empty list, which protojson omits.  Look ahead before writing the key.
+          if (packed_in) {
+            Rd t = r;
+            u64 len;
+            if (!rd_varint(t, fr.end, &len) || len > (u64)(fr.end - t.pos)) return GST_BAD_WIRE;
+            if (len == 0) {
+              r = t;
+              continue;
+            }
+          }
+          fr.last_decl = (i32)f.decl_index;
+          put_sep(w, cx, fr.first);
+          put_pool(w, T.pool, f.name_off, f.name_len);
+          w.put1('[');
+          fr.open = (u32)ei + 1;
+          fr.elem_first = 1;
+        }
+        if (packed_in) {
+          u64 len;
+          if (!rd_varint(r, fr.end, &len) || len > (u64)(fr.end - r.pos)) return GST_BAD_WIRE;
+          u32 lim = r.pos + (u32)len;
+          while (r.pos < lim) {
+            put_sep(w, cx, fr.elem_first);
+            bool z;
+            int st = scalar_value<W, true>(w, cx, r, lim, f.kind, f.child, false, &z);
+            if (st != GST_OK) return st;
+          }
+          if (r.pos != lim) return GST_BAD_WIRE;
+          continue;
+        }
+        put_sep(w, cx, fr.elem_first);
+        if (f.kind != GK_MESSAGE) {
+          bool z;
+          int st = scalar_value<W, true>(w, cx, r, fr.end, f.kind, f.child, false, &z);
+          if (st != GST_OK) return st;
+          continue;
+        }
+        // message element: falls through to the message push below
+      } else {
+        if (fr.open) { w.put1(']'); fr.open = 0; }
+        if ((i32)f.decl_index <= fr.last_decl) return GGR_NEED_SLOW;
+        if (f.oneof >= 0) {
+          u32 bit = 1u << (f.oneof & 31);
+          if (fr.oneofs & bit) return GGR_NEED_SLOW;  // last member wins: needs the slow walk
+          fr.oneofs |= bit;
+        }
+        fr.last_decl = (i32)f.decl_index;
+        if (f.kind != GK_MESSAGE) {
+          if (!(f.flags & GF_PRESENCE)) {
+            // implicit presence: a zero value is not "set" (dynamicpb isSet) - read ahead.
+            // Strings and bytes only need their length prefix for that.
+            Rd t = r;
+            bool z;
+            if (f.wt == 2) {
+              u64 len;
+              if (!rd_varint(t, fr.end, &len) || len > (u64)(fr.end - t.pos)) return GST_BAD_WIRE;
+              z = len == 0;
+            } else {
+              Cnt c;
+              c.pos = 0;
+              int st = scalar_value<Cnt, false>(c, cx, t, fr.end, f.kind, f.child, false, &z);
+              if (st != GST_OK) return st;
+            }
+            if (z) {
+              r = t;
+              continue;
+            }
+          }
+          put_sep(w, cx, fr.first);
+          put_pool(w, T.pool, f.name_off, f.name_len);
+          bool z;
+          int st = scalar_value<W, true>(w, cx, r, fr.end, f.kind, f.child, false, &z);
+          if (st != GST_OK) return st;
+          continue;
+        }
+        put_sep(w, cx, fr.first);
+        put_pool(w, T.pool, f.name_off, f.name_len);
+      }
+      // ---- message value (singular or repeated element) ----
+      {
+        u64 len;
+        if (!rd_varint(r, fr.end, &len) || len > (u64)(fr.end - r.pos)) return GST_BAD_WIRE;
+        u32 lim = r.pos + (u32)len;
+        MsgD cd = ggr_msg(T, (u32)f.child);
+        if (cd.wkt == GGR_WKT_TIMESTAMP) {
+          i64 s, n;
+          int st = read_timestamp_payload(r, lim, &s, &n);
+          if (st != GST_OK) return st;
+          st = put_timestamp(w, s, n);
+          if (st != GST_OK) return st;
+          continue;
+        }
+        if (cd.wkt != GGR_WKT_NONE) return GST_UNSUPPORTED;
+        if (depth >= GGR_DEC_MAX_DEPTH - 1) return GST_DEPTH;
+        stk[depth++] = fr;
+        fr.end = lim; fr.msg = (u32)f.child; fr.last_decl = -1; fr.open = 0; fr.first = 1; fr.elem_first = 1; fr.oneofs = 0;
+        fr.start = r.pos; fr.scan = r.pos; fr.cur_emit = 0; fr.state = 0;
+        md = cd;
+        w.put1('{');
+        continue;
+      }
+    } else {
+      // ================= slow walk =================
+      // fr.last_decl + 1 is the next declaration index to handle; fr.state == 1 means we are in
+      // the middle of a repeated message field (resume scanning at fr.scan)
+      if (fr.state == 0) {
+        fr.last_decl++;
+        if ((u32)fr.last_decl >= md.n_fields) {
+          // validate the whole payload once more for unknown-field well-formedness is done by
+          // the per-field scans (each scan walks every tag); nothing left to do
+          if (md.n_fields == 0) {
+            // still need to validate the bytes
+            Rd t;
+            t.init(cx.in, fr.start, fr.end);
+            while (t.pos < fr.end) {
+              u64 tag;
+              if (!rd_varint(t, fr.end, &tag)) return GST_BAD_WIRE;
+              u64 n2 = tag >> 3;
+              if (n2 == 0 || n2 > 0x1FFFFFFFull || (tag & 7) == 4 || (tag & 7) > 5) return GST_BAD_WIRE;
+              if (!rd_skip_value(t, fr.end, (u32)n2, (u32)(tag & 7))) return GST_BAD_WIRE;
+            }
+          }
+          w.put1('}');
+          if (depth == 0) return GST_OK;
+          fr = stk[--depth];
+          md = ggr_msg(T, fr.msg);
+          continue;
+        }
+        fr.cur_emit = ggr_u16(T, md.decl_first + (u32)fr.last_decl);
+        fr.scan = fr.start;
+        fr.elem_first = 1;
+        fr.open = 0;
+      }
+      FieldD f = ggr_field(T, md.field_first + fr.cur_emit);
+      if (f.flags & GF_MAP) {
+        fr.state = 0;
+        // does the map have any entry?  put_map_field writes nothing for an empty map, but the
+        // key must not be written either: count first with a counting writer
+        Cnt c;
+        c.pos = 0;
+        Rd t;
+        t.init(cx.in, fr.start, fr.end);
+        int st = put_map_field<Cnt, true>(c, cx, t, f, fr.start, fr.end, rec);
+        if (st != GST_OK) return st;
+        if (c.pos == 0) continue;
+        put_sep(w, cx, fr.first);
+        put_pool(w, T.pool, f.name_off, f.name_len);
+        st = put_map_field<W, true>(w, cx, t, f, fr.start, fr.end, rec);
+        if (st != GST_OK) return st;
+        continue;
+      }
+      bool repeated = (f.flags & GF_REPEATED) != 0;
+      // scan for occurrences from fr.scan
+      Rd t;
+      t.init(cx.in, fr.scan, fr.end);
+      u32 last_pos = 0, last_wt = 0;  // singular: position after the tag of the last occurrence
+      u32 n_occ = 0;
+      bool pushed = false;
+      while (t.pos < fr.end) {
+        u64 tag;
+        if (!rd_varint(t, fr.end, &tag)) return GST_BAD_WIRE;
+        u64 n2 = tag >> 3;
+        u32 wt = (u32)(tag & 7);
+        if (n2 == 0 || n2 > 0x1FFFFFFFull || wt == 4 || wt > 5) return GST_BAD_WIRE;
+        bool packed_in = (f.flags & GF_PACKABLE) && wt == 2;
+        if ((u32)n2 != f.number || (wt != f.wt && !packed_in)) {
+          if (!rd_skip_value(t, fr.end, (u32)n2, wt)) return GST_BAD_WIRE;
+          continue;
+        }
+        if (!repeated) {
+          last_pos = t.pos;
+          last_wt = wt;
+          n_occ++;
+          if (!rd_skip_value(t, fr.end, (u32)n2, wt)) return GST_BAD_WIRE;
+          continue;
+        }
+        // repeated occurrence
+        if (packed_in) {
+          u64 len;
+          if (!rd_varint(t, fr.end, &len) || len > (u64)(fr.end - t.pos)) return GST_BAD_WIRE;
+          u32 lim = t.pos + (u32)len;
+          while (t.pos < lim) {
+            if (!fr.open) {
+              put_sep(w, cx, fr.first);
+              put_pool(w, T.pool, f.name_off, f.name_len);
+              w.put1('[');
+              fr.open = 1;
+            }
+            put_sep(w, cx, fr.elem_first);
+            bool z;
+            int st = scalar_value<W, true>(w, cx, t, lim, f.kind, f.child, false, &z);
+            if (st != GST_OK) return st;
+          }
+          if (t.pos != lim) return GST_BAD_WIRE;
+          continue;
+        }
+        if (!fr.open) {
+          put_sep(w, cx, fr.first);
+          put_pool(w, T.pool, f.name_off, f.name_len);
+          w.put1('[');
+          fr.open = 1;
+        }
+        put_sep(w, cx, fr.elem_first);
+        if (f.kind != GK_MESSAGE) {
+          bool z;
+          int st = scalar_value<W, true>(w, cx, t, fr.end, f.kind, f.child, false, &z);
+          if (st != GST_OK) return st;
+          continue;
+        }
+        // message element: push a frame, resume this scan afterwards
+        u64 len;
+        if (!rd_varint(t, fr.end, &len) || len > (u64)(fr.end - t.pos)) return GST_BAD_WIRE;
+        u32 lim = t.pos + (u32)len;
+        MsgD cd = ggr_msg(T, (u32)f.child);
+        if (cd.wkt == GGR_WKT_TIMESTAMP) {
+          i64 s, n;
+          int st = read_timestamp_payload(t, lim, &s, &n);
+          if (st != GST_OK) return st;
+          st = put_timestamp(w, s, n);
+          if (st != GST_OK) return st;
+          continue;
+        }
+        if (cd.wkt != GGR_WKT_NONE) return GST_UNSUPPORTED;
+        if (depth >= GGR_DEC_MAX_DEPTH - 1) return GST_DEPTH;
+        fr.state = 1;
+        fr.scan = lim;
+        stk[depth++] = fr;
+        fr.end = lim; fr.msg = (u32)f.child; fr.last_decl = -1; fr.open = 0; fr.first = 1; fr.elem_first = 1; fr.oneofs = 0;
+        fr.start = t.pos; fr.scan = t.pos; fr.cur_emit = 0; fr.state = 0;
+        md = cd;
+        w.put1('{');
+        pushed = true;
+        break;
+      }
+      if (pushed) continue;
+      if (repeated) {
+        if (fr.open) w.put1(']');
+        fr.open = 0;
+        fr.state = 0;
+        continue;
+      }
+      fr.state = 0;
+      if (n_occ == 0) continue;
+      // oneof: only the member set last on the wire survives
+      if (f.oneof >= 0) {
+        bool later = false;
+        Rd q;
+        q.init(cx.in, last_pos, fr.end);
+        if (!rd_skip_value(q, fr.end, f.number, last_wt)) return GST_BAD_WIRE;
+        while (q.pos < fr.end && !later) {
+          u64 tag;
+          if (!rd_varint(q, fr.end, &tag)) return GST_BAD_WIRE;
+          u32 n3 = (u32)(tag >> 3), w3 = (u32)(tag & 7);
+          i32 e3 = find_field(T, md, n3);
+          if (e3 >= 0 && (u32)e3 != fr.cur_emit) {
+            FieldD g = ggr_field(T, md.field_first + (u32)e3);
+            if (g.oneof == f.oneof && (w3 == g.wt)) later = true;
+          }
+          if (!rd_skip_value(q, fr.end, n3, w3)) return GST_BAD_WIRE;
+        }
+        if (later) continue;
+      }
+      if (f.kind == GK_MESSAGE) {
+        if (n_occ > 1) return GST_UNSUPPORTED;  // merging split sub-messages is not implemented
+        Rd q;
+        q.init(cx.in, last_pos, fr.end);
+        u64 len;
+        if (!rd_varint(q, fr.end, &len) || len > (u64)(fr.end - q.pos)) return GST_BAD_WIRE;
+        u32 lim = q.pos + (u32)len;
+        MsgD cd = ggr_msg(T, (u32)f.child);
+        put_sep(w, cx, fr.first);
+        put_pool(w, T.pool, f.name_off, f.name_len);
+        if (cd.wkt == GGR_WKT_TIMESTAMP) {
+          i64 s, n;
+          int st = read_timestamp_payload(q, lim, &s, &n);
+          if (st != GST_OK) return st;
+          st = put_timestamp(w, s, n);
+          if (st != GST_OK) return st;
+          continue;
+        }
+        if (cd.wkt != GGR_WKT_NONE) return GST_UNSUPPORTED;
+        if (depth >= GGR_DEC_MAX_DEPTH - 1) return GST_DEPTH;
+        stk[depth++] = fr;
+        fr.end = lim; fr.msg = (u32)f.child; fr.last_decl = -1; fr.open = 0; fr.first = 1; fr.elem_first = 1; fr.oneofs = 0;
+        fr.start = q.pos; fr.scan = q.pos; fr.cur_emit = 0; fr.state = 0;
+        md = cd;
+        w.put1('{');
+        continue;
+      }
+      // singular scalar: the last occurrence wins; every occurrence must still be valid
+      {
+        Rd q;
+        q.init(cx.in, fr.start, fr.end);
+        // validate all occurrences (strings: UTF-8) the way proto.Unmarshal would
+        while (q.pos < fr.end) {
+          u64 tag;
+          if (!rd_varint(q, fr.end, &tag)) return GST_BAD_WIRE;
+          u32 n3 = (u32)(tag >> 3), w3 = (u32)(tag & 7);
+          if (n3 == f.number && w3 == f.wt && f.kind == GK_STRING) {
+            bool z;
+            Cnt c;
+            c.pos = 0;
+            int st = scalar_value<Cnt, false>(c, cx, q, fr.end, f.kind, f.child, false, &z);
+            if (st != GST_OK) return st;
+          } else if (!rd_skip_value(q, fr.end, n3, w3)) {
+            return GST_BAD_WIRE;
+          }
+        }
+        q.init(cx.in, last_pos, fr.end);
+        if (!(f.flags & GF_PRESENCE)) {
+          Rd t2 = q;
+          bool z;
+          Cnt c;
+          c.pos = 0;
+          int st = scalar_value<Cnt, false>(c, cx, t2, fr.end, f.kind, f.child, false, &z);
+          if (st != GST_OK) return st;
+          if (z) continue;
+        }
+        put_sep(w, cx, fr.first);
+        put_pool(w, T.pool, f.name_off, f.name_len);
+        bool z;
+        int st = scalar_value<W, true>(w, cx, q, fr.end, f.kind, f.child, false, &z);
+        if (st != GST_OK) return st;
+      }
+    }
+  }
+}
+
+// Size pass: tries the fast walk, falls back to the slow walk for the whole item.
+GGR_DEV int decode_size(const Tables& T, u32 msg, const u8* in, u32 start, u32 end, u32 flags, DecResult* res) {
+  DecCtx cx;
+  cx.T = T;
+  cx.in = in;
+  cx.flags = flags;
+  Cnt c;
+  c.pos = 0;
+  int st = walk_message<Cnt, false>(c, cx, msg, start, end, 0);
+  res->mode = GGR_MODE_FAST;
+  if (st == GGR_NEED_SLOW) {
+    c.pos = 0;
+    st = walk_message<Cnt, true>(c, cx, msg, start, end, 0);
+    res->mode = GGR_MODE_SLOW;
+  }
+  res->size = c.pos;
+  return st;
+}
+
+GGR_DEV int decode_write(const Tables& T, u32 msg, const u8* in, u32 start, u32 end, u32 flags, u32 mode, u8* out,
+                         u32 out_off, u32* end_pos) {
+  DecCtx cx;
+  cx.T = T;
+  cx.in = in;
+  cx.flags = flags;
+  Wr w;
+  w.init(out, out_off);
+  int st = mode == GGR_MODE_SLOW ? walk_message<Wr, true>(w, cx, msg, start, end, 0)
+                                 : walk_message<Wr, false>(w, cx, msg, start, end, 0);
+  w.finish();
+  *end_pos = w.pos;
+  return st;
+}

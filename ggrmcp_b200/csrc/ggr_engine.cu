@@ -1,0 +1,524 @@
+// ggr_engine.cu - sm_100a kernels and the C ABI of include/ggrmcp_b200.h.
+//
+// Kernel plan (one item = one tools/call message, one thread per item, 128-thread blocks):
+//   request side : k_encode_parse  (pass A: JSON -> IR + exact size, block sums)
+//                  k_scan_blocks   (exclusive scan of the block sums, single block)
+//                  k_encode_emit   (block-local scan -> final offsets; pass B: IR -> wire bytes)
+//   reply side   : k_decode_size   (size pass over the wire bytes, block sums)
+//                  k_scan_blocks
+//                  k_decode_write  (block-local scan -> final offsets; write pass)
+// Items shard across GPUs by batch index on the caller's side (one engine per device); there is
+// no cross-GPU exchange on this path.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ggrmcp_b200.h"
+#include "ggr_decode.cuh"
+#include "ggr_encode.cuh"
+#include "ggr_schema.h"
+
+#define GGR_BLOCK 128
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 warp_incl_scan(u32 v) {
+  const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    u32 t = __shfl_up_sync(0xFFFFFFFFu, v, d);
+    if (lane >= (unsigned)d) v += t;
+  }
+  return v;
+}
+// exclusive scan over the block (GGR_BLOCK threads); returns the exclusive prefix and the total
+__device__ __forceinline__ u32 block_excl_scan(u32 v, u32* total) {
+  __shared__ u32 warp_tot[GGR_BLOCK / 32];
+  u32 inc = warp_incl_scan(v);
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 31) warp_tot[wid] = inc;
+  __syncthreads();
+  u32 base = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < GGR_BLOCK / 32; i++) {
+    u32 t = warp_tot[i];
+    if ((unsigned)i < wid) base += t;
+    tot += t;
+  }
+  *total = tot;
+  return base + inc - v;
+}
+
+__global__ void __launch_bounds__(GGR_BLOCK)
+k_encode_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const i32* __restrict__ msg_id,
+               const u8* __restrict__ in, const u64* __restrict__ in_off, u8* __restrict__ ir,
+               u32* __restrict__ size, u32* __restrict__ first, i32* __restrict__ status,
+               u64* __restrict__ block_sums) {
+  long long i = (long long)blockIdx.x * GGR_BLOCK + threadIdx.x;
+  u32 sz = 0;
+  if (i < n) {
+    u64 a = in_off[i], b = in_off[i + 1];
+    i32 m = msg_id[i];
+    int st;
+    EncResult res;
+    res.size = 0;
+    res.first = GGR_NIL;
+    if (m < 0 || (u32)m >= n_msgs || b < a) {
+      st = GST_UNSUPPORTED;
+    } else if (b - a > 0x1FFFF0ull) {  // IR links are 20 bits: at most 2^20 nodes per item
+      st = GST_TOO_LARGE;
+    } else {
+      Tables T = ggr_tables(blob);
+      u64 node_off = (a >> 1) + 8ull * (u64)i;
+      u32 cap = (u32)(((b >> 1) + 8ull * (u64)(i + 1)) - node_off);
+      const u8* base = in + (a & ~15ull);  // per-item rebasing keeps positions in 32 bits
+      u32 s0 = (u32)(a & 15ull);
+      st = encode_parse(T, (u32)m, base, s0, s0 + (u32)(b - a), ir + node_off * 16, cap, &res);
+    }
+    if (st != GST_OK) res.size = 0;
+    sz = res.size;
+    size[i] = sz;
+    first[i] = res.first;
+    status[i] = st;
+  }
+  u32 tot;
+  block_excl_scan(sz, &tot);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+// Single block: exclusive scan of nb block sums in place; writes the grand total to *total_out.
+__global__ void __launch_bounds__(1024) k_scan_blocks(u64* __restrict__ sums, long long nb, u64* __restrict__ total_out) {
+  __shared__ u64 part[1024];
+  const int t = threadIdx.x;
+  long long per = (nb + 1023) / 1024;
+  long long lo = (long long)t * per, hi = lo + per < nb ? lo + per : nb;
+  u64 s = 0;
+  for (long long k = lo; k < hi; k++) s += sums[k];
+  part[t] = s;
+  __syncthreads();
+  // Hillis-Steele over 1024 partials
+  for (int d = 1; d < 1024; d <<= 1) {
+    u64 v = t >= d ? part[t - d] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  u64 run = part[t] - s;
+  for (long long k = lo; k < hi; k++) {
+    u64 v = sums[k];
+    sums[k] = run;
+    run += v;
+  }
+  if (t == 1023) *total_out = part[1023];
+}
+
+__global__ void __launch_bounds__(GGR_BLOCK)
+k_encode_emit(long long n, const u8* __restrict__ in, const u64* __restrict__ in_off, const u8* __restrict__ ir,
+              const u32* __restrict__ size, const u32* __restrict__ first, i32* __restrict__ status,
+              const u64* __restrict__ block_prefix, u8* __restrict__ out, u64 out_cap, u64* __restrict__ out_off) {
+  long long i = (long long)blockIdx.x * GGR_BLOCK + threadIdx.x;
+  u32 sz = i < n ? size[i] : 0;
+  u32 tot;
+  u32 excl = block_excl_scan(sz, &tot);
+  if (i >= n) return;
+  u64 off = block_prefix[blockIdx.x] + excl;
+  out_off[i] = off;
+  if (sz == 0 || status[i] != GST_OK) return;
+  if (off + sz > out_cap) {
+    status[i] = GST_NO_SPACE;
+    return;
+  }
+  u64 a = in_off[i], b = in_off[i + 1];
+  u64 node_off = (a >> 1) + 8ull * (u64)i;
+  const u8* base = in + (a & ~15ull);
+  u32 s0 = (u32)(a & 15ull);
+  Wr w;
+  w.init(out + (off & ~7ull), (u32)(off & 7ull));
+  encode_emit(base, s0 + (u32)(b - a), ir + node_off * 16, first[i], w);
+  w.finish();
+}
+
+__global__ void __launch_bounds__(GGR_BLOCK)
+k_decode_size(const u8* __restrict__ blob, long long n, u32 n_msgs, const i32* __restrict__ msg_id,
+              const u8* __restrict__ in, const u64* __restrict__ in_off, u32 flags, u32* __restrict__ size,
+              u32* __restrict__ mode, i32* __restrict__ status, u64* __restrict__ block_sums) {
+  long long i = (long long)blockIdx.x * GGR_BLOCK + threadIdx.x;
+  u32 sz = 0;
+  if (i < n) {
+    u64 a = in_off[i], b = in_off[i + 1];
+    i32 m = msg_id[i];
+    int st;
+    DecResult res;
+    res.size = 0;
+    res.mode = GGR_MODE_FAST;
+    if (m < 0 || (u32)m >= n_msgs || b < a) {
+      st = GST_UNSUPPORTED;
+    } else if (b - a > 0x7FFFFFF0ull) {
+      st = GST_TOO_LARGE;
+    } else {
+      Tables T = ggr_tables(blob);
+      const u8* base = in + (a & ~15ull);
+      u32 s0 = (u32)(a & 15ull);
+      st = decode_size(T, (u32)m, base, s0, s0 + (u32)(b - a), flags, &res);
+    }
+    if (st != GST_OK) res.size = 0;
+    sz = res.size;
+    size[i] = sz;
+    mode[i] = res.mode;
+    status[i] = st;
+  }
+  u32 tot;
+  block_excl_scan(sz, &tot);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(GGR_BLOCK)
+k_decode_write(const u8* __restrict__ blob, long long n, const i32* __restrict__ msg_id, const u8* __restrict__ in,
+               const u64* __restrict__ in_off, u32 flags, const u32* __restrict__ size, const u32* __restrict__ mode,
+               i32* __restrict__ status, const u64* __restrict__ block_prefix, u8* __restrict__ out, u64 out_cap,
+               u64* __restrict__ out_off) {
+  long long i = (long long)blockIdx.x * GGR_BLOCK + threadIdx.x;
+  u32 sz = i < n ? size[i] : 0;
+  u32 tot;
+  u32 excl = block_excl_scan(sz, &tot);
+  if (i >= n) return;
+  u64 off = block_prefix[blockIdx.x] + excl;
+  out_off[i] = off;
+  if (sz == 0 || status[i] != GST_OK) return;
+  if (off + sz > out_cap) {
+    status[i] = GST_NO_SPACE;
+    return;
+  }
+  u64 a = in_off[i], b = in_off[i + 1];
+  Tables T = ggr_tables(blob);
+  const u8* base = in + (a & ~15ull);
+  u32 s0 = (u32)(a & 15ull);
+  u32 end_pos;
+  int st = decode_write(T, (u32)msg_id[i], base, s0, s0 + (u32)(b - a), flags, mode[i], out + (off & ~7ull),
+                        (u32)(off & 7ull), &end_pos);
+  if (st != GST_OK) status[i] = st;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct ggr_schema {
+  ggr_engine* eng;
+  ggr::CompiledSchema cs;
+  u8* d_blob;
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct ggr_engine {
+  int device = 0;
+  ggr::WireOrder order = ggr::ORDER_FIELD_NUMBER;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  std::mutex mu;
+  // scratch (device)
+  DevBuf ir, size, aux, sums, total;
+  // staging for the host-buffer entry points (device)
+  DevBuf d_in, d_off, d_msg, d_out, d_out_off, d_status;
+  // per-kernel timing
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct Span { int slot; size_t a, b; };
+  std::vector<Span> spans;
+};
+
+static cudaEvent_t prof_mark(ggr_engine* e, cudaStream_t st, size_t* idx) {
+  if (e->ev_used == e->ev_pool.size()) {
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    e->ev_pool.push_back(ev);
+  }
+  *idx = e->ev_used++;
+  cudaEventRecord(e->ev_pool[*idx], st);
+  return e->ev_pool[*idx];
+}
+
+static bool cuda_ok(ggr_engine* e, cudaError_t rc, const char* what) {
+  if (rc == cudaSuccess) return true;
+  e->err = std::string(what) + ": " + cudaGetErrorString(rc);
+  return false;
+}
+static bool ensure(ggr_engine* e, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return true;
+  if (b.p) {
+    cudaStreamSynchronize(e->stream);
+    cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t want = bytes + bytes / 4 + 4096;
+  if (!cuda_ok(e, cudaMalloc(&b.p, want), "cudaMalloc")) return false;
+  b.cap = want;
+  return true;
+}
+
+extern "C" {
+
+const char* ggr_status_string(int32_t st) {
+  static const char* names[] = {"ok", "syntax", "unknown_field", "invalid_value", "range", "invalid_utf8", "duplicate",
+                                "oneof_conflict", "depth", "too_large", "bad_wire", "unsupported", "no_space"};
+  if (st < 0 || st > 12) return "?";
+  return names[st];
+}
+
+int ggr_engine_create(const ggr_config* cfg, ggr_engine** out) {
+  if (!out) return GGR_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return GGR_ERR_NO_DEVICE;
+  int dev = cfg ? cfg->device : 0;
+  if (dev < 0 || dev >= ndev) return GGR_ERR_INVALID_ARGUMENT;
+  if (cudaSetDevice(dev) != cudaSuccess) return GGR_ERR_NO_DEVICE;
+  // the library carries sm_100a code only: make sure the kernels are loadable here
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, (const void*)k_encode_parse) != cudaSuccess) {
+    cudaGetLastError();
+    return GGR_ERR_NO_DEVICE;
+  }
+  ggr_engine* e = new ggr_engine();
+  e->device = dev;
+  e->order = (cfg && cfg->wire_order == GGR_ORDER_GO_LEGACY) ? ggr::ORDER_GO_LEGACY : ggr::ORDER_FIELD_NUMBER;
+  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete e;
+    return GGR_ERR_CUDA;
+  }
+  // message-valued map entries recurse (bounded, GGR_DEC_MAX_REC); give the walkers room
+  cudaFuncAttributes fw;
+  size_t need = 4096;
+  if (cudaFuncGetAttributes(&fw, (const void*)k_decode_write) == cudaSuccess) need += fw.localSizeBytes;
+  cudaDeviceSetLimit(cudaLimitStackSize, 4096 + (GGR_DEC_MAX_REC + 1) * 3072);
+  (void)need;
+  *out = e;
+  return GGR_SUCCESS;
+}
+
+void ggr_engine_destroy(ggr_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  DevBuf* bufs[] = {&e->ir, &e->size, &e->aux, &e->sums, &e->total, &e->d_in, &e->d_off, &e->d_msg, &e->d_out, &e->d_out_off, &e->d_status};
+  for (DevBuf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
+  cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+const char* ggr_last_error(const ggr_engine* e) { return e ? e->err.c_str() : "null engine"; }
+uint64_t ggr_launch_count(const ggr_engine* e) { return e ? e->launches : 0; }
+
+int ggr_schema_register(ggr_engine* e, const uint8_t* fds, size_t n, ggr_schema** out) {
+  if (!e || !fds || !out) return GGR_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  ggr_schema* s = new ggr_schema();
+  s->eng = e;
+  s->d_blob = nullptr;
+  std::string err;
+  if (!ggr::compile_schema(fds, n, e->order, &s->cs, &err)) {
+    e->err = err;
+    delete s;
+    return GGR_ERR_SCHEMA;
+  }
+  cudaSetDevice(e->device);
+  if (!cuda_ok(e, cudaMalloc((void**)&s->d_blob, s->cs.blob.size() + 256), "cudaMalloc(schema)") ||
+      !cuda_ok(e, cudaMemset(s->d_blob, 0, s->cs.blob.size() + 256), "cudaMemset(schema)") ||
+      !cuda_ok(e, cudaMemcpy(s->d_blob, s->cs.blob.data(), s->cs.blob.size(), cudaMemcpyHostToDevice), "cudaMemcpy(schema)")) {
+    if (s->d_blob) cudaFree(s->d_blob);
+    delete s;
+    return GGR_ERR_CUDA;
+  }
+  *out = s;
+  return GGR_SUCCESS;
+}
+void ggr_schema_release(ggr_schema* s) {
+  if (!s) return;
+  cudaSetDevice(s->eng->device);
+  cudaStreamSynchronize(s->eng->stream);
+  cudaFree(s->d_blob);
+  delete s;
+}
+int32_t ggr_message_lookup(const ggr_schema* s, const char* full_name) {
+  if (!s || !full_name) return -1;
+  auto it = s->cs.msg_index.find(full_name);
+  return it == s->cs.msg_index.end() ? -1 : it->second;
+}
+int32_t ggr_method_count(const ggr_schema* s) { return s ? (int32_t)s->cs.methods.size() : 0; }
+int ggr_method_get(const ggr_schema* s, int32_t i, ggr_method_info* o) {
+  if (!s || !o || i < 0 || i >= (int32_t)s->cs.methods.size()) return GGR_ERR_INVALID_ARGUMENT;
+  const ggr::MethodInfo& m = s->cs.methods[i];
+  o->name = m.name.c_str();
+  o->full_name = m.full_name.c_str();
+  o->service_name = m.service_name.c_str();
+  o->tool_name = m.tool_name.c_str();
+  o->grpc_path = m.grpc_path.c_str();
+  o->input_msg = m.input_msg;
+  o->output_msg = m.output_msg;
+  o->client_streaming = m.client_streaming;
+  o->server_streaming = m.server_streaming;
+  return GGR_SUCCESS;
+}
+int32_t ggr_tool_lookup(const ggr_schema* s, const char* tool) {
+  if (!s || !tool) return -1;
+  auto it = s->cs.tool_index.find(tool);
+  return it == s->cs.tool_index.end() ? -1 : it->second;
+}
+
+int ggr_profile_enable(ggr_engine* e, int on) {
+  if (!e) return GGR_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(e->mu);
+  e->profiling = on != 0;
+  return GGR_SUCCESS;
+}
+int ggr_profile_read(ggr_engine* e, double* ms, uint64_t* launches) {
+  if (!e || !ms || !launches) return GGR_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(e->mu);
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < 6; i++) { ms[i] = 0; launches[i] = 0; }
+  for (auto& sp : e->spans) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, e->ev_pool[sp.a], e->ev_pool[sp.b]) == cudaSuccess) {
+      ms[sp.slot] += t;
+      launches[sp.slot]++;
+    }
+  }
+  e->spans.clear();
+  e->ev_used = 0;
+  return GGR_SUCCESS;
+}
+
+int ggr_synchronize(ggr_engine* e) {
+  if (!e) return GGR_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(e->device);
+  return cuda_ok(e, cudaStreamSynchronize(e->stream), "cudaStreamSynchronize") ? GGR_SUCCESS : GGR_ERR_CUDA;
+}
+
+static int run_dev(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, const int32_t* msg_id, const uint8_t* in,
+                   const uint64_t* in_off, uint64_t in_bytes, uint8_t* out, uint64_t out_cap, uint64_t* out_off,
+                   int32_t* status, uint32_t flags, cudaStream_t st) {
+  if (!e || !s || n < 0 || (n > 0 && (!msg_id || !in || !in_off || !out_off || !status))) return GGR_ERR_INVALID_ARGUMENT;
+  if (((uintptr_t)in & 15) || ((uintptr_t)out & 7)) return GGR_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(e->device);
+  if (n == 0) {
+    return cuda_ok(e, cudaMemsetAsync(out_off, 0, sizeof(uint64_t), st), "memset") ? GGR_SUCCESS : GGR_ERR_CUDA;
+  }
+  long long nb = (n + GGR_BLOCK - 1) / GGR_BLOCK;
+  if (!ensure(e, e->size, (size_t)n * 4) || !ensure(e, e->aux, (size_t)n * 4) || !ensure(e, e->sums, (size_t)nb * 8)) return GGR_ERR_CUDA;
+  if (encode && !ensure(e, e->ir, (size_t)in_bytes * 8 + (size_t)n * 128 + 256)) return GGR_ERR_CUDA;
+  u32 n_msgs = (u32)s->cs.msg_names.size();
+  const bool prof = e->profiling && e->ev_used + 4 <= 65536;
+  size_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+  if (prof) prof_mark(e, st, &m0);
+  if (encode) {
+    k_encode_parse<<<(unsigned)nb, GGR_BLOCK, 0, st>>>(s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)e->ir.p, (u32*)e->size.p,
+                                                       (u32*)e->aux.p, status, (u64*)e->sums.p);
+    if (prof) prof_mark(e, st, &m1);
+    k_scan_blocks<<<1, 1024, 0, st>>>((u64*)e->sums.p, nb, out_off + n);
+    if (prof) prof_mark(e, st, &m2);
+    k_encode_emit<<<(unsigned)nb, GGR_BLOCK, 0, st>>>(n, in, in_off, (const u8*)e->ir.p, (const u32*)e->size.p,
+                                                      (const u32*)e->aux.p, status, (const u64*)e->sums.p, out, out_cap, out_off);
+  } else {
+    k_decode_size<<<(unsigned)nb, GGR_BLOCK, 0, st>>>(s->d_blob, n, n_msgs, msg_id, in, in_off, flags, (u32*)e->size.p,
+                                                      (u32*)e->aux.p, status, (u64*)e->sums.p);
+    if (prof) prof_mark(e, st, &m1);
+    k_scan_blocks<<<1, 1024, 0, st>>>((u64*)e->sums.p, nb, out_off + n);
+    if (prof) prof_mark(e, st, &m2);
+    k_decode_write<<<(unsigned)nb, GGR_BLOCK, 0, st>>>(s->d_blob, n, msg_id, in, in_off, flags, (const u32*)e->size.p,
+                                                       (const u32*)e->aux.p, status, (const u64*)e->sums.p, out, out_cap, out_off);
+  }
+  if (prof) {
+    prof_mark(e, st, &m3);
+    int base = encode ? 0 : 3;
+    e->spans.push_back({base + 0, m0, m1});
+    e->spans.push_back({base + 1, m1, m2});
+    e->spans.push_back({base + 2, m2, m3});
+  }
+  e->launches += 3;
+  return cuda_ok(e, cudaGetLastError(), "kernel launch") ? GGR_SUCCESS : GGR_ERR_CUDA;
+}
+
+int ggr_encode_batch_dev(ggr_engine* e, const ggr_schema* s, int64_t n, const int32_t* msg_id, const uint8_t* in,
+                         const uint64_t* in_off, uint64_t in_bytes, uint8_t* out, uint64_t out_cap, uint64_t* out_off,
+                         int32_t* status, uint32_t flags, void* stream) {
+  if (!e) return GGR_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(e->mu);
+  return run_dev(e, s, true, n, msg_id, in, in_off, in_bytes, out, out_cap, out_off, status, flags,
+                 stream ? (cudaStream_t)stream : e->stream);
+}
+int ggr_decode_batch_dev(ggr_engine* e, const ggr_schema* s, int64_t n, const int32_t* msg_id, const uint8_t* in,
+                         const uint64_t* in_off, uint64_t in_bytes, uint8_t* out, uint64_t out_cap, uint64_t* out_off,
+                         int32_t* status, uint32_t flags, void* stream) {
+  if (!e) return GGR_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(e->mu);
+  return run_dev(e, s, false, n, msg_id, in, in_off, in_bytes, out, out_cap, out_off, status, flags,
+                 stream ? (cudaStream_t)stream : e->stream);
+}
+
+// Host-buffer entry points: H2D, kernels, D2H on the engine stream.
+static int run_host(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, const int32_t* msg_id, const uint8_t* in,
+                    const uint64_t* in_off, uint8_t* out, uint64_t out_cap, uint64_t* out_off, int32_t* status, uint32_t flags) {
+  if (!e || !s || n < 0 || !out_off) return GGR_ERR_INVALID_ARGUMENT;
+  if (n == 0) {
+    out_off[0] = 0;
+    return GGR_SUCCESS;
+  }
+  if (!msg_id || !in || !in_off || !status || (!out && out_cap)) return GGR_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(e->mu);
+  cudaSetDevice(e->device);
+  uint64_t base = in_off[0], in_bytes = in_off[n] - base;
+  // offsets are shipped as given; the device copy of the payload starts at a 16-byte phase equal
+  // to base & 15 so that offsets need no rewriting
+  uint64_t phase = base & 15ull;
+  if (!ensure(e, e->d_in, (size_t)(in_bytes + phase + 128)) || !ensure(e, e->d_off, (size_t)(n + 1) * 8) ||
+      !ensure(e, e->d_msg, (size_t)n * 4) || !ensure(e, e->d_out, (size_t)out_cap + 64) ||
+      !ensure(e, e->d_out_off, (size_t)(n + 1) * 8) || !ensure(e, e->d_status, (size_t)n * 4))
+    return GGR_ERR_CUDA;
+  cudaStream_t st = e->stream;
+  u8* d_in = (u8*)e->d_in.p;
+  if (!cuda_ok(e, cudaMemcpyAsync(d_in + phase, in + base, in_bytes, cudaMemcpyHostToDevice, st), "H2D payload") ||
+      !cuda_ok(e, cudaMemsetAsync(d_in + phase + in_bytes, 0, 64, st), "pad") ||
+      !cuda_ok(e, cudaMemcpyAsync(e->d_off.p, in_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st), "H2D offsets") ||
+      !cuda_ok(e, cudaMemcpyAsync(e->d_msg.p, msg_id, (size_t)n * 4, cudaMemcpyHostToDevice, st), "H2D ids"))
+    return GGR_ERR_CUDA;
+  // kernels address the payload as d_in - (base - phase) + offset
+  const u8* d_in_virtual = d_in + phase - base;
+  int rc = run_dev(e, s, encode, n, (const int32_t*)e->d_msg.p, d_in_virtual, (const uint64_t*)e->d_off.p, in_bytes,
+                   (uint8_t*)e->d_out.p, out_cap, (uint64_t*)e->d_out_off.p, (int32_t*)e->d_status.p, flags, st);
+  if (rc != GGR_SUCCESS) return rc;
+  if (!cuda_ok(e, cudaMemcpyAsync(out_off, e->d_out_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H offsets") ||
+      !cuda_ok(e, cudaMemcpyAsync(status, e->d_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st), "D2H status") ||
+      !cuda_ok(e, cudaStreamSynchronize(st), "sync"))
+    return GGR_ERR_CUDA;
+  uint64_t total = out_off[n];
+  if (total > out_cap) return GGR_ERR_NO_SPACE;
+  if (total && (!cuda_ok(e, cudaMemcpyAsync(out, e->d_out.p, total, cudaMemcpyDeviceToHost, st), "D2H payload") ||
+                !cuda_ok(e, cudaStreamSynchronize(st), "sync")))
+    return GGR_ERR_CUDA;
+  return GGR_SUCCESS;
+}
+
+int ggr_encode_batch(ggr_engine* e, const ggr_schema* s, int64_t n, const int32_t* msg_id, const uint8_t* json,
+                     const uint64_t* json_off, uint8_t* out, uint64_t out_cap, uint64_t* out_off, int32_t* status, uint32_t flags) {
+  return run_host(e, s, true, n, msg_id, json, json_off, out, out_cap, out_off, status, flags);
+}
+int ggr_decode_batch(ggr_engine* e, const ggr_schema* s, int64_t n, const int32_t* msg_id, const uint8_t* wire,
+                     const uint64_t* wire_off, uint8_t* out, uint64_t out_cap, uint64_t* out_off, int32_t* status, uint32_t flags) {
+  return run_host(e, s, false, n, msg_id, wire, wire_off, out, out_cap, out_off, status, flags);
+}
+
+}  // extern "C"

@@ -223,6 +223,8 @@ struct NumTok {
   u64 m;
   i32 k;
   u32 sig;        // significant digits accumulated into m
+  u32 int_digits; // digits of the integer part ("0" counts as none, like upstream's intp)
+  i32 exp;        // exponent as written (clamped)
 };
 
 GGR_DEV bool mul10_add(u64& m, u32 d) {  // false on overflow
@@ -240,6 +242,8 @@ GGR_DEV bool parse_number(It& it, NumTok* t) {
   t->is_plain = true;
   t->m = 0;
   t->sig = 0;
+  t->int_digits = 0;
+  t->exp = 0;
   u32 pend = 0;       // zeros seen since the last nonzero digit
   u32 frac_total = 0;
   i64 exp = 0;
@@ -265,6 +269,7 @@ GGR_DEV bool parse_number(It& it, NumTok* t) {
   } else if (c - '1' < 9u) {
     do {
       digit(c - '0');
+      t->int_digits++;
       it.adv();
       c = it.get();
     } while (c - '0' < 10u);
@@ -309,6 +314,7 @@ GGR_DEV bool parse_number(It& it, NumTok* t) {
   if (k > 1000000) k = 1000000;
   if (k < -1000000) k = -1000000;
   t->k = (i32)k;
+  t->exp = (i32)exp;
   return true;
 }
 
@@ -321,6 +327,8 @@ GGR_DEV bool num_to_int(const NumTok& t, bool is_signed, int bits, u64* out) {
     return true;
   }
   if (t.ovf || t.k < 0 || t.k > 19) return false;
+  // upstream's digit-count guard: integer-part digits + exponent may not exceed 20
+  if (t.exp >= 0 && (i64)t.int_digits + t.exp > 20) return false;
   u64 v = t.m;
   for (int i = 0; i < t.k; i++)
     if (!mul10_add(v, 0)) return false;

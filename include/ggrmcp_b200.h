@@ -1,0 +1,146 @@
+/*
+ * ggrmcp_b200.h - C ABI of the B200 transcoding engine for ggRMCP's tools/call hot path.
+ *
+ * Drop-in boundary.  The reference has no FFI; every entry point below
+ * names the reference interface it stands in for, so that a cgo shim can sit
+ * behind the unchanged Go surfaces:
+ *
+ *   grpc.ReflectionClient.InvokeMethod(ctx, headers, method types.MethodInfo, inputJSON string)
+ *        (string, error)                          /root/reference/pkg/grpc/interfaces.go:60-72
+ *     request half  = protojson.Unmarshal + proto.Marshal   reflection.go:351-357,373
+ *                     -> ggr_encode_batch
+ *     reply half    = proto.Unmarshal + protojson.Marshal   reflection.go:363,373,381
+ *                     -> ggr_decode_batch
+ *   types.MethodInfo{InputDescriptor, OutputDescriptor, ToolName, FullName}
+ *                                                 /root/reference/pkg/types/service.go:15-61
+ *                     -> ggr_schema_register / ggr_message_lookup / ggr_method_*
+ *   descriptor sources: .binpb (pkg/descriptors/loader.go:33-64) or reflection
+ *                       FileDescriptorProtos (pkg/grpc/reflection.go:235-243)
+ *                     -> the serialized FileDescriptorSet handed to ggr_schema_register
+ *
+ * Plain C types only, no callbacks, no torch types.  All buffers are borrowed for the duration of
+ * the call.  One bad item never fails the batch: every item gets its own status.
+ * There is no CPU fallback: every transcode runs in the sm_100a kernels; without a CUDA device
+ * ggr_engine_create fails with GGR_ERR_NO_DEVICE.
+ */
+#ifndef GGRMCP_B200_H_
+#define GGRMCP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ggr_engine ggr_engine;
+typedef struct ggr_schema ggr_schema;
+
+/* call-level return codes */
+enum {
+  GGR_SUCCESS = 0,
+  GGR_ERR_INVALID_ARGUMENT = -1,
+  GGR_ERR_NO_DEVICE = -2,   /* no usable CUDA device / kernels not loadable: no fallback exists */
+  GGR_ERR_CUDA = -3,
+  GGR_ERR_SCHEMA = -4,      /* malformed or unresolvable FileDescriptorSet */
+  GGR_ERR_NO_SPACE = -5,    /* output capacity too small; out_off[n] holds the bytes needed */
+  GGR_ERR_TOO_LARGE = -6    /* batch exceeds 4 GiB - 64 KiB of input */
+};
+
+/* per-item status: category of the error protojson / proto would have returned
+ * (texts carry the prefixes of reflection.go:356,375,383 on the Go side) */
+enum {
+  GGR_ST_OK = 0,
+  GGR_ST_SYNTAX = 1,         /* "syntax error" / "unexpected token"                       */
+  GGR_ST_UNKNOWN_FIELD = 2,  /* "unknown field" (pinned by tests/real_grpc_invocation_test.go:244) */
+  GGR_ST_INVALID_VALUE = 3,  /* "invalid value for <kind> field"                          */
+  GGR_ST_RANGE = 4,          /* well-known-type value out of range                        */
+  GGR_ST_INVALID_UTF8 = 5,
+  GGR_ST_DUPLICATE = 6,      /* "duplicate field" / "duplicate map key"                   */
+  GGR_ST_ONEOF = 7,          /* "oneof ... is already set"                                */
+  GGR_ST_DEPTH = 8,          /* nesting beyond the engine's frame stack                   */
+  GGR_ST_TOO_LARGE = 9,
+  GGR_ST_BAD_WIRE = 10,      /* "cannot parse invalid wire-format data"                   */
+  GGR_ST_UNSUPPORTED = 11,   /* construct outside the implemented subset  */
+  GGR_ST_NO_SPACE = 12
+};
+
+/* ggr_config.wire_order */
+enum {
+  GGR_ORDER_FIELD_NUMBER = 0, /* ascending field number (C++/Java/upb, Go generated code)      */
+  GGR_ORDER_GO_LEGACY = 1     /* Go order.LegacyFieldOrder (proto.MarshalOptions{Deterministic}) */
+};
+
+/* flags of the batch calls */
+#define GGR_F_COMMA_SPACE 0x1u /* protojson's per-binary detrand bit: ", " after commas */
+
+typedef struct {
+  int32_t device;        /* CUDA device ordinal */
+  uint32_t wire_order;   /* GGR_ORDER_* */
+  uint32_t reserved[6];
+} ggr_config;
+
+int ggr_engine_create(const ggr_config* cfg, ggr_engine** out);
+void ggr_engine_destroy(ggr_engine* e);
+const char* ggr_last_error(const ggr_engine* e); /* NUL-terminated, valid until the next call */
+const char* ggr_status_string(int32_t status);
+uint64_t ggr_launch_count(const ggr_engine* e);  /* kernels launched by this engine so far */
+
+/* Registers a serialized google.protobuf.FileDescriptorSet; tables are compiled once and kept in
+ * HBM.  Re-register after a Reconnect (pkg/grpc/discovery.go:187-235). */
+int ggr_schema_register(ggr_engine* e, const uint8_t* file_descriptor_set, size_t n, ggr_schema** out);
+void ggr_schema_release(ggr_schema* s);
+int32_t ggr_message_lookup(const ggr_schema* s, const char* full_name); /* -1 if unknown */
+
+/* Service methods found in the descriptor set (host-side mirror of types.MethodInfo). */
+typedef struct {
+  const char* name;          /* "SayHello" */
+  const char* full_name;     /* "hello.HelloService.SayHello" */
+  const char* service_name;  /* "hello.HelloService" */
+  const char* tool_name;     /* GenerateToolName(): "hello_helloservice_sayhello" */
+  const char* grpc_path;     /* "/hello.HelloService/SayHello" (reflection.go:367) */
+  int32_t input_msg, output_msg;
+  int32_t client_streaming, server_streaming;
+} ggr_method_info;
+int32_t ggr_method_count(const ggr_schema* s);
+int ggr_method_get(const ggr_schema* s, int32_t index, ggr_method_info* out);
+int32_t ggr_tool_lookup(const ggr_schema* s, const char* tool_name); /* getMethodByTool; -1 if unknown */
+
+/*
+ * Request half of InvokeMethod for n items.  Item i is the canonical arguments string
+ * json[json_off[i] .. json_off[i+1]) (what handler.go:224-231 produced) for message msg_id[i].
+ * On return out[out_off[i] .. out_off[i+1]) holds its wire bytes (empty when status[i] != 0).
+ * Host pointers; the copies to and from HBM are part of the call.
+ */
+int ggr_encode_batch(ggr_engine* e, const ggr_schema* s, int64_t n, const int32_t* msg_id, const uint8_t* json,
+                     const uint64_t* json_off, uint8_t* out, uint64_t out_cap, uint64_t* out_off,
+                     int32_t* status, uint32_t flags);
+/* Reply half: wire bytes of message msg_id[i] -> protojson text. */
+int ggr_decode_batch(ggr_engine* e, const ggr_schema* s, int64_t n, const int32_t* msg_id, const uint8_t* wire,
+                     const uint64_t* wire_off, uint8_t* out, uint64_t out_cap, uint64_t* out_off,
+                     int32_t* status, uint32_t flags);
+
+/*
+ * Same operations on buffers already resident in HBM (all pointers are device pointers on the
+ * engine's device; `in` must be 16-byte aligned and readable 64 bytes past its end).  Work is
+ * enqueued on `stream` (a cudaStream_t, NULL = the engine's own stream) and not synchronized.
+ */
+int ggr_encode_batch_dev(ggr_engine* e, const ggr_schema* s, int64_t n, const int32_t* msg_id, const uint8_t* in,
+                         const uint64_t* in_off, uint64_t in_bytes, uint8_t* out, uint64_t out_cap,
+                         uint64_t* out_off, int32_t* status, uint32_t flags, void* stream);
+int ggr_decode_batch_dev(ggr_engine* e, const ggr_schema* s, int64_t n, const int32_t* msg_id, const uint8_t* in,
+                         const uint64_t* in_off, uint64_t in_bytes, uint8_t* out, uint64_t out_cap,
+                         uint64_t* out_off, int32_t* status, uint32_t flags, void* stream);
+int ggr_synchronize(ggr_engine* e);
+
+/* Per-kernel device timing (CUDA events recorded around every kernel the engine launches).
+ * slots: 0 encode_parse, 1 encode_scan, 2 encode_emit, 3 decode_size, 4 decode_scan, 5 decode_write.
+ * ggr_profile_read synchronizes, adds up the elapsed milliseconds and launch counts since the
+ * last read into ms[6] / launches[6], and resets the recorder. */
+int ggr_profile_enable(ggr_engine* e, int on);
+int ggr_profile_read(ggr_engine* e, double* ms, uint64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

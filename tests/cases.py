@@ -1,0 +1,206 @@
+"""Shared parity cases: the reference's own pinned inputs, hand-written
+edge cases per protojson rule, and seeded random generators.  Used by the oracle tests, the host
+simulation tests (CPU) and the GPU parity tests."""
+import random
+
+import pbgen
+import wiremut
+
+P = "com.example.complex."
+
+# (message, canonical arguments JSON, expected request wire hex) - SURVEY.md Appendix C K1..K5,
+# built from /root/reference/README.md:212-214 and tests/real_grpc_invocation_test.go:25,48,91-112,158-176,298-306
+K_REQUESTS = [
+    ("hello.HelloRequest", b'{"email":"test@example.com","name":"World"}',
+     "0a05576f726c64121074657374406578616d706c652e636f6d"),
+    (P + "GetUserProfileRequest", b'{"user_id":"premium"}', "0a077072656d69756d"),
+    (P + "GetUserProfileRequest", '{"user_id":"张三"}'.encode(), "0a06e5bca0e4b889"),
+    (P + "CreateDocumentRequest",
+     b'{"document":{"content":"This is a test document","document_id":"doc1","simple_summary":"A test","title":"Test Document"}}',
+     "0a360a04646f6331120d5465737420446f63756d656e741a17546869732069732061207465737420646f63756d656e742206412074657374"),
+    (P + "CreateDocumentRequest",
+     b'{"document":{"content":"This is a complex document","document_id":"doc2","structured_metadata_wrapper":{"data":{"author":"John Doe","category":"Technical","version":"1.0"}},"title":"Complex Document"}}',
+     "0a710a04646f63321210436f6d706c657820446f63756d656e741a1a54686973206973206120636f6d706c657820646f63756d656e742a3b0a120a06617574686f7212084a6f686e20446f650a150a0863617465676f72791209546563686e6963616c0a0e0a0776657273696f6e1203312e30"),
+    (P + "ProcessNodeRequest",
+     b'{"root_node":{"children":[{"id":"child1","value":"Child 1"},{"children":[{"id":"grandchild1","value":"Grandchild 1"}],"id":"child2","value":"Child 2"}],"id":"root","value":"Root Node"}}',
+     "0a540a04726f6f741209526f6f74204e6f64651a110a066368696c643112074368696c6420311a2e0a066368696c643212074368696c6420321a1b0a0b6772616e646368696c6431120c4772616e646368696c642031"),
+]
+
+# (message, reply wire hex, expected protojson text)
+K_REPLIES = [
+    ("hello.HelloReply",
+     "0a2b48656c6c6f20576f726c642120596f757220656d61696c2069732074657374406578616d706c652e636f6d",
+     b'{"message":"Hello World! Your email is test@example.com"}'),
+    (P + "GetUserProfileResponse",
+     "0a3e0a087374616e646172641212546573742055736572207374616e646172641a147374616e64617264406578616d706c652e636f6d20012a0608c0d2caac06",
+     b'{"profile":{"userId":"standard","displayName":"Test User standard","email":"standard@example.com","userType":"STANDARD","lastLogin":"2024-01-01T12:00:00Z"}}'),
+    (P + "GetUserProfileResponse",
+     "0a3b0a077072656d69756d1211546573742055736572207072656d69756d1a137072656d69756d406578616d706c652e636f6d20022a0608c0d2caac06",
+     b'{"profile":{"userId":"premium","displayName":"Test User premium","email":"premium@example.com","userType":"PREMIUM","lastLogin":"2024-01-01T12:00:00Z"}}'),
+    (P + "GetUserProfileResponse",
+     "0a380a06e5bca0e4b889121054657374205573657220e5bca0e4b8891a12e5bca0e4b889406578616d706c652e636f6d20012a0608c0d2caac06",
+     '{"profile":{"userId":"张三","displayName":"Test User 张三","email":"张三@example.com","userType":"STANDARD","lastLogin":"2024-01-01T12:00:00Z"}}'.encode()),
+    (P + "CreateDocumentResponse", "0a11646f632d546573742d446f63756d656e741001",
+     b'{"documentId":"doc-Test-Document","success":true}'),
+    (P + "ProcessNodeResponse", "0a2450726f6365737365642074726565207769746820726f6f742027526f6f74204e6f6465271004",
+     b'{"processedSummary":"Processed tree with root \'Root Node\'","totalNodes":4}'),
+]
+
+A = "bench.All"
+# (message, json, expected status name or None for "whatever the oracle says")
+ENCODE_EDGE = [
+    (A, b"", None), (A, b"{}", None), (A, b" { } ", None), (A, b"null", None), (A, b"[]", None), (A, b"{", None),
+    (A, b'{"f_int32":1,}', None), (A, b'{"f_int32":1 "f_int64":2}', None), (A, b'{"f_int32":1}x', None),
+    (A, b'{"f_int32":1} \n\t ', None), (A, b'{"unknown":1}', None), (A, b'{"fInt32":1,"f_int32":2}', None),
+    (A, b'{"f_int32":null,"f_int32":2}', None), (A, b'{"f_int32":null}', None),
+    (A, b'{"f_int32":"12"}', None), (A, b'{"f_int32":"1e2"}', None), (A, b'{"f_int32":1.0}', None),
+    (A, b'{"f_int32":1.5}', None), (A, b'{"f_int32":1e2}', None), (A, b'{"f_int32":100e-2}', None),
+    (A, b'{"f_int32":10e-2}', None), (A, b'{"f_int32":-0}', None), (A, b'{"f_int32":-0.0e5}', None),
+    (A, b'{"f_int32":2147483647}', None), (A, b'{"f_int32":2147483648}', None), (A, b'{"f_int32":-2147483648}', None),
+    (A, b'{"f_int32":-2147483649}', None), (A, b'{"f_int32":01}', None), (A, b'{"f_int32":+1}', None),
+    (A, b'{"f_int32":" 1"}', None), (A, b'{"f_int32":"1 "}', None), (A, b'{"f_int32":"1 2"}', None),
+    (A, b'{"f_int32":""}', None), (A, b'{"f_int32":"\\u0031\\u0032"}', None), (A, b'{"f_int32":true}', None),
+    (A, b'{"f_int32":{}}', None), (A, b'{"f_int32":[1]}', None), (A, b'{"f_int32":1x}', None),
+    (A, b'{"f_uint32":4294967295}', None), (A, b'{"f_uint32":4294967296}', None), (A, b'{"f_uint32":-1}', None),
+    (A, b'{"f_uint32":-0}', None), (A, b'{"f_uint64":"18446744073709551615"}', None),
+    (A, b'{"f_uint64":18446744073709551616}', None), (A, b'{"f_uint64":1e19}', None), (A, b'{"f_uint64":1e20}', None),
+    (A, b'{"f_int64":"-9223372036854775808"}', None), (A, b'{"f_int64":-9223372036854775809}', None),
+    (A, b'{"f_int64":9223372036854775807}', None), (A, b'{"f_int64":1000000000000000000000e-5}', None),
+    (A, b'{"f_int64":0.000000000000000000001e21}', None), (A, b'{"f_int64":1.00000000000000000000000000}', None),
+    (A, b'{"f_sint32":-1,"f_sint64":"-1","f_sfixed32":-5,"f_sfixed64":-6,"f_fixed32":7,"f_fixed64":"8"}', None),
+    (A, b'{"f_bool":true}', None), (A, b'{"f_bool":false}', None), (A, b'{"f_bool":"true"}', None),
+    (A, b'{"f_bool":1}', None), (A, b'{"f_bool":tru}', None), (A, b'{"f_bool":truex}', None),
+    (A, b'{"f_string":"a\\"b\\\\c\\/d\\b\\f\\n\\r\\t\\u00e9\\ud83d\\ude00"}', None), (A, b'{"f_string":"\\ud83d"}', None),
+    (A, b'{"f_string":"\\ude00"}', None), (A, b'{"f_string":"\\ud83dx"}', None), (A, b'{"f_string":"\\x"}', None),
+    (A, b'{"f_string":"a\nb"}', None), (A, b'{"f_string":"\xff"}', None), (A, b'{"f_string":"\xc0\x80"}', None),
+    (A, b'{"f_string":"\xed\xa0\x80"}', None), (A, b'{"f_string":"\xf4\x90\x80\x80"}', None), (A, b'{"f_string":"abc', None),
+    (A, b'{"f_string":1}', None), (A, b'{"f_string":"\\u0000"}', None), (A, b'{"f_string":"\\u003c\\u003e\\u0026\\u2028"}', None),
+    (A, b'{"f_bytes":"aGVsbG8="}', None), (A, b'{"f_bytes":"aGVsbG8"}', None), (A, b'{"f_bytes":"aGVsbG8=="}', None),
+    (A, b'{"f_bytes":"-_-_"}', None), (A, b'{"f_bytes":"+/+/"}', None), (A, b'{"f_bytes":"-/+_"}', None),
+    (A, b'{"f_bytes":"aGVs\\nbG8="}', None), (A, b'{"f_bytes":"a"}', None), (A, b'{"f_bytes":"aG=="}', None),
+    (A, b'{"f_bytes":"aG="}', None), (A, b'{"f_bytes":"aGVsbG8=x"}', None), (A, b'{"f_bytes":""}', None),
+    (A, b'{"f_bytes":"a b="}', None), (A, b'{"f_bytes":"YQ==YQ=="}', None),
+    (A, b'{"f_enum":"RED"}', None), (A, b'{"f_enum":"NOPE"}', None), (A, b'{"f_enum":2}', None), (A, b'{"f_enum":-5}', None),
+    (A, b'{"f_enum":12345}', None), (A, b'{"f_enum":"2"}', None), (A, b'{"f_enum":2.0}', None), (A, b'{"f_enum":3e9}', None),
+    (A, b'{"f_enum":null}', None), (A, b'{"f_enum":0}', None), (A, b'{"f_enum":"COLOR_UNSPECIFIED"}', None),
+    (A, b'{"f_msg":{}}', None), (A, b'{"f_msg":{"x":0}}', None), (A, b'{"f_msg":null}', None), (A, b'{"f_msg":[]}', None),
+    (A, b'{"f_msg":"x"}', None), (A, b'{"f_msg":{"x":1,"y":"z"}}', None),
+    (A, b'{"r_int32":[]}', None), (A, b'{"r_int32":[1,2,3]}', None), (A, b'{"r_int32":[1,]}', None), (A, b'{"r_int32":[,1]}', None),
+    (A, b'{"r_int32":[null]}', None), (A, b'{"r_int32":null}', None), (A, b'{"r_int32":1}', None), (A, b'{"r_int32":[[1]]}', None),
+    (A, b'{"r_unpacked":[1,0,300]}', None), (A, b'{"r_string":["","a"]}', None), (A, b'{"r_msg":[{},{"x":1}]}', None),
+    (A, b'{"r_msg":[null]}', None), (A, b'{"r_bool":[true,false]}', None), (A, b'{"r_enum":["RED",2,"BIG"]}', None),
+    (A, b'{"r_sint64":["-1",2]}', None), (A, b'{"r_fixed64":["1"]}', None), (A, b'{"r_bytes":["YQ==",""]}', None),
+    (A, b'{"m_str_int32":{}}', None), (A, b'{"m_str_int32":{"b":2,"a":1}}', None), (A, b'{"m_str_int32":{"a":1,"a":2}}', None),
+    (A, b'{"m_str_int32":{"a":null}}', None), (A, b'{"m_str_int32":null}', None), (A, b'{"m_str_int32":[]}', None),
+    (A, b'{"m_str_int32":{"\\u0061":1,"a":2}}', None), (A, b'{"m_str_int32":{"":0}}', None),
+    (A, b'{"m_int32_str":{"10":"x","9":"y","-1":"z"}}', None), (A, b'{"m_int32_str":{"1":"x","01":"y"}}', None),
+    (A, b'{"m_int32_str":{"+1":"x"}}', None), (A, b'{"m_int32_str":{"1.0":"x"}}', None), (A, b'{"m_int32_str":{"":"x"}}', None),
+    (A, b'{"m_int32_str":{"2147483648":"x"}}', None), (A, b'{"m_int64_msg":{"5":{"x":1},"-5":{}}}', None),
+    (A, b'{"m_int64_msg":{"5":null}}', None), (A, b'{"m_bool_double":{}}', None), (A, b'{"m_uint64_bytes":{"18446744073709551615":"YQ=="}}', None),
+    (A, b'{"m_uint64_bytes":{"-1":"YQ=="}}', None), (A, b'{"m_str_enum":{"k":"RED","j":0}}', None),
+    (A, b'{"m_fixed64_sfixed32":{"7":-1}}', None),
+    (A, b'{"o_int32":1,"o_string":"x"}', None), (A, b'{"o_int32":null,"o_string":"x"}', None), (A, b'{"o_int32":0}', None),
+    (A, b'{"o_string":""}', None), (A, b'{"o_msg":{}}', None), (A, b'{"o_bool":false}', None), (A, b'{"o_enum":0}', None),
+    (A, b'{"opt_int32":0,"opt_string":"","opt_bool":false}', None), (A, b'{"opt_int32":0,"opt_int32":1}', None),
+    (A, b'{"ts":"2024-01-01T12:00:00Z"}', None), (A, b'{"ts":"2024-01-01T12:00:00.5Z"}', None),
+    (A, b'{"ts":"2024-01-01T12:00:00.123456789Z"}', None), (A, b'{"ts":"2024-01-01T12:00:00.1234567891Z"}', None),
+    (A, b'{"ts":"2024-01-01T12:00:00,1234567891Z"}', None), (A, b'{"ts":"2024-01-01T12:00:00+05:30"}', None),
+    (A, b'{"ts":"2024-01-01T12:00:00-08:00"}', None), (A, b'{"ts":"2024-01-01t12:00:00Z"}', None),
+    (A, b'{"ts":"2024-01-01T1:00:00Z"}', None), (A, b'{"ts":"2024-02-30T12:00:00Z"}', None), (A, b'{"ts":"2024-02-29T12:00:00Z"}', None),
+    (A, b'{"ts":"2023-02-29T12:00:00Z"}', None), (A, b'{"ts":"0000-01-01T00:00:00Z"}', None), (A, b'{"ts":"0001-01-01T00:00:00Z"}', None),
+    (A, b'{"ts":"9999-12-31T23:59:59.999999999Z"}', None), (A, b'{"ts":"2024-01-01T24:00:00Z"}', None),
+    (A, b'{"ts":"2024-01-01T12:00:60Z"}', None), (A, b'{"ts":"2024-01-01T12:00:00"}', None), (A, b'{"ts":"2024-01-01T12:00:00.Z"}', None),
+    (A, b'{"ts":"2024-01-01T12:00:00Z "}', None), (A, b'{"ts":1}', None), (A, b'{"ts":null}', None), (A, b'{"ts":{}}', None),
+    (A, b'{"ts":"1970-01-01T00:00:00Z"}', None), (A, b'{"ts":"1969-12-31T23:59:59.5Z"}', None), (A, b'{"ts":"2024-01-01T12:00:00+24:60"}', None),
+    (A, b'{"r_ts":["2024-01-01T12:00:00Z","1970-01-01T00:00:00.000000001Z"]}', None),
+    (A, b'{"recursive":{"recursive":{"recursive":{"f_int32":1}}}}', None), (A, b'{"CustomJSON":"a","zLast":"b","lateLow":3}', None),
+    (A, b'{"custom":"a","z_last":"b","late_low":3}', None), (A, b'{"custom":"a","CustomJSON":"b"}', None),
+    (A, b'{"[ext]":1}', None), (A, b'{"f\\u005fint32":5}', None), (A, b'{"f_float":1.5}', None), (A, b'{"f_double":1.5}', None),
+    (P + "ProcessNodeRequest", b'{"invalid_field":"value"}', "unknown_field"),
+    ("google.protobuf.Timestamp", b'"2024-01-01T12:00:00Z"', None), ("google.protobuf.Timestamp", b'{}', None),
+]
+
+DECODE_EDGE_HEX = [
+    (A, ""), (A, "0800"), (A, "08001001"), (A, "0801"), (A, "08ffffffffffffffffff01"), (A, "08ffffffffffffffffff7f"),
+    (A, "08808080808080808080"), (A, "7200"), (A, "720161"), (A, "7202c080"), (A, "7201ff"), (A, "7a00"), (A, "7a03010203"),
+    (A, "8a0100"), (A, "8a01020801"), (A, "8a0103080100"), (A, "aa0100"), (A, "aa01050102ff7f03"), (A, "a801ff01"),
+    (A, "a80101a80102"), (A, "aa010101a801020a"), (A, "b00201b00200b00280808080808080808001"),
+    (A, "c2020508010a0161"), (A, "ca02021801"), (A, "ca0200"), (A, "ca02040a026162"), (A, "ca020612016108b960"),
+    (A, "ca02050a01610802ca02050a01620801ca02050a01610803"), (A, "d202060803120178d20206080112017a"),
+    (A, "9803019803009803"), (A, "9803"), (A, "ba0400"), (A, "ba040208c0"), (A, "ba040608c0d2caac06"),
+    (A, "ba040c08c0d2caac061080cab5ee01"), (A, "ba040b08c0d2caac06108094ebdc03"), (A, "ba040b08c0d2caac06108194ebdc03"),
+    (A, "ba040a08ffffffffffffffff7f"), (A, "ba0407088092b8c398fe0f"), (A, "ba04021001"), (A, "ba040210ffffffffffffffffff01"),
+    (A, "0b0c"), (A, "0b08010c"), (A, "0b0b0c0c"), (A, "0b1c"), (A, "0c"), (A, "0f"), (A, "00"), (A, "f8ffffff0f01"), (A, "f8ffffff1f01"),
+    (A, "0a0101"), (A, "0d01000000"), (A, "09"), (A, "0d0000"), (A, "72ff"), (A, "72ffffffffffffffffff01"),
+    (A, "9001009001"), (A, "900109"), (A, "800107"), (A, "8001fbffffffffffffffff01"), (A, "8001e8c0a207"),
+    (A, "980201"), (A, "a20201" + "05"), (A, "aa0203" + "414243"), (A, "900300" + "9a0300"), (A, "9a03016190030598030ab203020801"),
+    (A, "e8030fea030178f00301"), (A, "d2050163a2060171900107"), (A, "a20601719001070801"),
+    (P + "Node", "1a001a020a00"), (P + "Node", "0a0161" * 3), (P + "Node", "1a040a0161" "0a0162" "1a040a0163"),
+    (P + "StructuredMetadata", "0a060a01621201320a060a0161120131"), (P + "StructuredMetadata", "0a00"),
+    (P + "StructuredMetadata", "0a0212000a020a00"), (P + "StructuredMetadata", "0a060a0161120131" * 2),
+    (P + "StructuredMetadata", "0a0612013112016b"), (P + "StructuredMetadata", "0a080a016b0a016a120176"),
+    ("google.protobuf.Timestamp", "08c0d2caac06"), ("google.protobuf.Timestamp", ""),
+]
+
+
+def random_encode_cases(n_per_msg=150, seed0=0, floats=False):
+    """(message, json bytes) pairs rendered by python-protobuf in both key spellings."""
+    names = [A, P + "CreateDocumentRequest", P + "ProcessNodeRequest", P + "GetUserProfileResponse", "bench.Flat", "bench.Blob"]
+    out = []
+    for name in names:
+        for seed in range(seed0, seed0 + n_per_msg):
+            m = pbgen.random_message(name, seed, floats=floats)
+            out.append((name, pbgen.to_json(m, seed % 2 == 0).encode()))
+    return out
+
+
+def mutate_json(j, rng):
+    """byte-level damage to exercise the tokenizer's error paths"""
+    a = bytearray(j)
+    if not a:
+        return bytes(a)
+    k = rng.randrange(6)
+    i = rng.randrange(len(a))
+    if k == 0:
+        del a[i]
+    elif k == 1:
+        a.insert(i, rng.choice(b'{}[]",:\\ntf0-e.'))
+    elif k == 2:
+        a[i] = rng.getrandbits(8)
+    elif k == 3:
+        a = a[:i]
+    elif k == 4:
+        a[i:i] = b"\\u00e9" if rng.random() < 0.5 else b" \n\t"
+    else:
+        j2 = rng.randrange(len(a))
+        a[i], a[j2] = a[j2], a[i]
+    return bytes(a)
+
+
+def random_decode_cases(n_per_msg=150, seed0=0, floats=False, mutators=True):
+    names = [A, P + "CreateDocumentRequest", P + "StructuredMetadata", P + "Node", P + "GetUserProfileResponse", "bench.Flat",
+             P + "ProcessNodeResponse"]
+    out = []
+    for name in names:
+        for seed in range(seed0, seed0 + n_per_msg):
+            rng = random.Random(seed)
+            m = pbgen.random_message(name, seed, floats=floats)
+            w = pbgen.wire(m)
+            out.append((name, w))
+            if mutators:
+                for mut in (wiremut.shuffle, wiremut.duplicate_some, wiremut.inject_unknown, wiremut.truncate, wiremut.corrupt):
+                    out.append((name, mut(w, rng)))
+    return out
+
+
+# both sides report an error, but the engine's multi-scan walk meets problems in a different
+# order than a sequential parser: these categories are interchangeable for damaged wire
+WIRE_ERRS = {5, 10, 11}
+
+
+def status_compatible(oracle_st, engine_st):
+    if oracle_st == engine_st:
+        return True
+    if oracle_st in WIRE_ERRS and engine_st in WIRE_ERRS:
+        return True
+    return False
