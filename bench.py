@@ -62,13 +62,13 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
@@ -80,10 +80,10 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._halt.wait(0.1)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=10)
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
@@ -193,8 +193,11 @@ def main():
         d_req_out_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
         d_req_st = torch.empty(n, dtype=torch.int32, device=dev)
 
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-NULL) stream: the engine enqueues its kernels on it and the CUDA events
+    # that bracket the timed region are recorded on the same stream
+    stream = torch.cuda.Stream(device=dev)
     sp = stream.cuda_stream
+    assert sp != 0
 
     def step_resident():
         if have_req:

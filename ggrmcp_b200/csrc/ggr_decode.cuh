@@ -586,7 +586,7 @@ struct DFrame {
 // the walker entry point for the value payload (depth-bounded); scalars are written here.
 #define GGR_DEC_MAX_REC 3 /* message-valued map entries nest by (bounded) recursion */
 template <class W, bool SLOW>
-GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 msg, u32 start, u32 end, int rec);
+GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 msg, u32 start, u32 end, int rec, bool active, unsigned mask);
 
 template <class W, bool SLOW>
 GGR_DEV int put_map_value(W& w, const DecCtx& cx, const FieldD& vf, const MapEnt& me, int rec) {
@@ -607,7 +607,8 @@ GGR_DEV int put_map_value(W& w, const DecCtx& cx, const FieldD& vf, const MapEnt
       w.put('{' | ('}' << 8), 2);
       return GST_OK;
     }
-    return walk_message<W, SLOW>(w, cx, (u32)vf.child, me.val_pos, me.val_pos + me.val_len, rec + 1);
+    // nested walk: only the lanes that arrive here together vote with each other
+    return walk_message<W, SLOW>(w, cx, (u32)vf.child, me.val_pos, me.val_pos + me.val_len, rec + 1, true, ggr_activemask());
   }
   if (!me.val_pos) {
     // absent value: zero value of the kind
@@ -778,27 +779,47 @@ GGR_DEV int put_map_field(W& w, const DecCtx& cx, Rd& r, const FieldD& f, u32 ps
 // `depth`; ordinary nesting uses the explicit frame stack.
 // ---------------------------------------------------------------------------------------------
 template <class W, bool SLOW>
-GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 end, int rec) {
-  if (rec > GGR_DEC_MAX_REC) return GST_DEPTH;
+GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 end, int rec, bool active, unsigned mask) {
   const Tables& T = cx.T;
   DFrame stk[GGR_DEC_MAX_DEPTH];
   int depth = 0;
+  bool finished = !active;
+  int result = GST_OK;
   Rd r;
-  r.init(cx.in, start, end);
   DFrame fr;
   fr.end = end; fr.msg = root_msg; fr.last_decl = -1; fr.open = 0; fr.first = 1; fr.elem_first = 1; fr.oneofs = 0;
   fr.start = start; fr.scan = start; fr.cur_emit = 0; fr.state = 0;
-  MsgD md = ggr_msg(T, root_msg);
-  if (md.wkt == GGR_WKT_TIMESTAMP) {
-    i64 s, n;
-    int st = read_timestamp_payload(r, end, &s, &n);
-    if (st != GST_OK) return st;
-    return put_timestamp(w, s, n);
+  MsgD md;
+  if (!finished && rec > GGR_DEC_MAX_REC) {
+    result = GST_DEPTH;
+    finished = true;
   }
-  if (md.wkt != GGR_WKT_NONE) return GST_UNSUPPORTED;
-  w.put1('{');
+  if (!finished) {
+    r.init(cx.in, start, end);
+    md = ggr_msg(T, root_msg);
+    if (md.wkt == GGR_WKT_TIMESTAMP) {
+      i64 s, n;
+      result = read_timestamp_payload(r, end, &s, &n);
+      if (result == GST_OK) result = put_timestamp(w, s, n);
+      finished = true;
+    } else if (md.wkt != GGR_WKT_NONE) {
+      result = GST_UNSUPPORTED;
+      finished = true;
+    } else {
+      w.put1('{');
+    }
+  } else {
+    r.base = cx.in; r.pos = r.end = r.fetch = 0; r.avail = 0; r.cur = 0; r.ch.x = r.ch.y = r.ch.z = r.ch.w = 0;
+    md.field_first = md.n_fields = md.wkt = md.flags = md.key_hash_first = md.key_hash_mask = md.decl_first = md.lut_first = md.lut_n = md.n_oneofs = 0;
+  }
 
-  for (;;) {
+  // one step = one wire field (fast walk) / one declared field scan (slow walk); the lanes of
+  // `mask` re-converge at the vote after every step
+  while (ggr_any(mask, !finished)) {
+   if (!finished) {
+    int rr = [&]() -> int {
+  for (int once = 0;; once++) {
+    if (once) return GGR_STEP_CONT;
     if (!SLOW) {
       // ================= fast walk =================
       if (r.pos >= fr.end) {
@@ -1170,21 +1191,33 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
       }
     }
   }
+    }();
+    if (rr != GGR_STEP_CONT) {
+      finished = true;
+      result = rr;
+    }
+   }
+  }
+  return result;
 }
 
 // Size pass: tries the fast walk, falls back to the slow walk for the whole item.
-GGR_DEV int decode_size(const Tables& T, u32 msg, const u8* in, u32 start, u32 end, u32 flags, DecResult* res) {
+// All lanes of `mask` call this together; lanes without an item pass active = false.
+GGR_DEV int decode_size(const Tables& T, u32 msg, const u8* in, u32 start, u32 end, u32 flags, DecResult* res,
+                        bool active = true, unsigned mask = GGR_FULL_MASK) {
   DecCtx cx;
   cx.T = T;
   cx.in = in;
   cx.flags = flags;
   Cnt c;
   c.pos = 0;
-  int st = walk_message<Cnt, false>(c, cx, msg, start, end, 0);
+  int st = walk_message<Cnt, false>(c, cx, msg, start, end, 0, active, mask);
   res->mode = GGR_MODE_FAST;
-  if (st == GGR_NEED_SLOW) {
-    c.pos = 0;
-    st = walk_message<Cnt, true>(c, cx, msg, start, end, 0);
+  bool need_slow = active && st == GGR_NEED_SLOW;
+  if (need_slow) c.pos = 0;
+  int st2 = walk_message<Cnt, true>(c, cx, msg, start, end, 0, need_slow, mask);
+  if (need_slow) {
+    st = st2;
     res->mode = GGR_MODE_SLOW;
   }
   res->size = c.pos;
@@ -1192,16 +1225,17 @@ GGR_DEV int decode_size(const Tables& T, u32 msg, const u8* in, u32 start, u32 e
 }
 
 GGR_DEV int decode_write(const Tables& T, u32 msg, const u8* in, u32 start, u32 end, u32 flags, u32 mode, u8* out,
-                         u32 out_off, u32* end_pos) {
+                         u32 out_off, u32* end_pos, bool active = true, unsigned mask = GGR_FULL_MASK) {
   DecCtx cx;
   cx.T = T;
   cx.in = in;
   cx.flags = flags;
   Wr w;
   w.init(out, out_off);
-  int st = mode == GGR_MODE_SLOW ? walk_message<Wr, true>(w, cx, msg, start, end, 0)
-                                 : walk_message<Wr, false>(w, cx, msg, start, end, 0);
-  w.finish();
+  bool slow = mode == GGR_MODE_SLOW;
+  int st_f = walk_message<Wr, false>(w, cx, msg, start, end, 0, active && !slow, mask);
+  int st_s = walk_message<Wr, true>(w, cx, msg, start, end, 0, active && slow, mask);
+  if (active) w.finish();
   *end_pos = w.pos;
-  return st;
+  return slow ? st_s : st_f;
 }

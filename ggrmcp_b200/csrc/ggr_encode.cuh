@@ -503,11 +503,16 @@ struct EncResult {
   u32 first;  // first top-level node (GGR_NIL when the message is empty)
 };
 
-GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start, u32 end, u8* ir, u32 ir_cap, EncResult* res) {
+// `active` is false for lanes that have no item (they only take part in the convergence votes);
+// `mask` names the lanes that call this function together.
+GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start, u32 end, u8* ir, u32 ir_cap, EncResult* res,
+                         bool active = true, unsigned mask = GGR_FULL_MASK) {
   res->size = 0;
   res->first = GGR_NIL;
+  bool finished = !active;
+  int result = GST_OK;
   // reflection.go:354: "" and "{}" skip protojson entirely
-  if (end == start) return GST_OK;
+  if (end == start) finished = true;
   EncCtx cx;
   cx.T = T;
   cx.in = in;
@@ -516,8 +521,12 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
   cx.ir_cap = ir_cap;
   cx.n_nodes = 0;
   Rd r;
-  r.init(in, start, end);
-  if (end - start == 2 && (r.peek4() & 0xFFFFu) == (u32)('{' | ('}' << 8))) return GST_OK;
+  if (!finished) {
+    r.init(in, start, end);
+    if (end - start == 2 && (r.peek4() & 0xFFFFu) == (u32)('{' | ('}' << 8))) finished = true;
+  } else {
+    r.base = in; r.pos = r.end = r.fetch = 0; r.avail = 0; r.cur = 0; r.ch.x = r.ch.y = r.ch.z = r.ch.w = 0;
+  }
 
   Frame stk[GGR_MAX_DEPTH];
   int depth = 0;
@@ -536,8 +545,13 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
   fr.key_body = 0;
   fr.tail_key = 0;
 
-  // state shared between "value start" and "container close"
-  for (;;) {
+  // One step = one member / element / container close.  All lanes of `mask` re-converge at the
+  // vote after every step (see ggr_prim.cuh).
+  while (ggr_any(mask, !finished)) {
+   if (!finished) {
+    int rr = [&]() -> int {
+  for (int once = 0;; once++) {
+    if (once) return GGR_STEP_CONT;  // `continue` in the body below ends the step
     skip_ws(r);
     // ---- what does the current container expect? ----
     FieldD f;          // field the upcoming value belongs to
@@ -874,6 +888,14 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
     continue;
   }
   }
+    }();
+    if (rr != GGR_STEP_CONT) {
+      finished = true;
+      result = rr;
+    }
+   }
+  }
+  return result;
 }
 
 // --------------------------------------------------------------------------------------------
@@ -902,11 +924,18 @@ GGR_DEV void copy_string(W& w, const u8* in, u32 quote_pos, u32 end, u32 dec_len
 }
 
 template <class W>
-GGR_DEV void encode_emit(const u8* in, u32 end, const u8* ir, u32 first, W& w) {
+GGR_DEV void encode_emit(const u8* in, u32 end, const u8* ir, u32 first, W& w, bool active = true,
+                         unsigned mask = GGR_FULL_MASK) {
   u32 stk[GGR_MAX_DEPTH * 3];
   int sp = 0;
   u32 cur = first;
-  for (;;) {
+  bool finished = !active;
+  // one step = one IR node; lanes re-converge at the vote after every step
+  while (ggr_any(mask, !finished)) {
+   if (!finished) {
+    int rr = [&]() -> int {
+  for (int once = 0;; once++) {
+    if (once) return GGR_STEP_CONT;
     if (cur == GGR_NIL) {
       if (sp == 0) break;
       cur = stk[--sp];
@@ -973,5 +1002,10 @@ GGR_DEV void encode_emit(const u8* in, u32 end, const u8* ir, u32 first, W& w) {
         continue;
     }
     cur = next;
+  }
+      return 0;
+    }();
+    if (rr != GGR_STEP_CONT) finished = true;
+   }
   }
 }

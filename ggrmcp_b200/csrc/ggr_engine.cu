@@ -39,6 +39,10 @@ __device__ __forceinline__ u32 warp_incl_scan(u32 v) {
 // exclusive scan over the block (GGR_BLOCK threads); returns the exclusive prefix and the total
 __device__ __forceinline__ u32 block_excl_scan(u32 v, u32* total) {
   __shared__ u32 warp_tot[GGR_BLOCK / 32];
+  // The walkers before this point are data-dependent; __syncthreads() is an *aligned* barrier
+  // (undefined when a warp reaches it divergently - compute-sanitizer synccheck caught exactly
+  // that), so re-converge the warp explicitly first.
+  __syncwarp();
   u32 inc = warp_incl_scan(v);
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (lane == 31) warp_tot[wid] = inc;
@@ -61,25 +65,32 @@ k_encode_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const i32* 
                u64* __restrict__ block_sums) {
   long long i = (long long)blockIdx.x * GGR_BLOCK + threadIdx.x;
   u32 sz = 0;
+  // every lane enters the parser (lanes without a valid item only take part in the votes)
+  u64 a = 0, b = 0;
+  i32 m = 0;
+  int st = GST_OK;
+  bool active = false;
   if (i < n) {
-    u64 a = in_off[i], b = in_off[i + 1];
-    i32 m = msg_id[i];
-    int st;
-    EncResult res;
-    res.size = 0;
-    res.first = GGR_NIL;
-    if (m < 0 || (u32)m >= n_msgs || b < a) {
-      st = GST_UNSUPPORTED;
-    } else if (b - a > 0x1FFFF0ull) {  // IR links are 20 bits: at most 2^20 nodes per item
-      st = GST_TOO_LARGE;
-    } else {
-      Tables T = ggr_tables(blob);
-      u64 node_off = (a >> 1) + 8ull * (u64)i;
-      u32 cap = (u32)(((b >> 1) + 8ull * (u64)(i + 1)) - node_off);
-      const u8* base = in + (a & ~15ull);  // per-item rebasing keeps positions in 32 bits
-      u32 s0 = (u32)(a & 15ull);
-      st = encode_parse(T, (u32)m, base, s0, s0 + (u32)(b - a), ir + node_off * 16, cap, &res);
-    }
+    a = in_off[i];
+    b = in_off[i + 1];
+    m = msg_id[i];
+    if (m < 0 || (u32)m >= n_msgs || b < a) st = GST_UNSUPPORTED;
+    else if (b - a > 0x1FFFF0ull) st = GST_TOO_LARGE;  // IR links are 20 bits: at most 2^20 nodes per item
+    else active = true;
+  }
+  EncResult res;
+  res.size = 0;
+  res.first = GGR_NIL;
+  {
+    Tables T = ggr_tables(blob);
+    u64 node_off = (a >> 1) + 8ull * (u64)i;
+    u32 cap = active ? (u32)(((b >> 1) + 8ull * (u64)(i + 1)) - node_off) : 0u;
+    const u8* base = in + (a & ~15ull);  // per-item rebasing keeps positions in 32 bits
+    u32 s0 = (u32)(a & 15ull);
+    int r = encode_parse(T, (u32)m, base, s0, s0 + (u32)(b - a), ir + node_off * 16, cap, &res, active, GGR_FULL_MASK);
+    if (active) st = r;
+  }
+  if (i < n) {
     if (st != GST_OK) res.size = 0;
     sz = res.size;
     size[i] = sz;
@@ -125,22 +136,33 @@ k_encode_emit(long long n, const u8* __restrict__ in, const u64* __restrict__ in
   u32 sz = i < n ? size[i] : 0;
   u32 tot;
   u32 excl = block_excl_scan(sz, &tot);
-  if (i >= n) return;
   u64 off = block_prefix[blockIdx.x] + excl;
-  out_off[i] = off;
-  if (sz == 0 || status[i] != GST_OK) return;
-  if (off + sz > out_cap) {
-    status[i] = GST_NO_SPACE;
-    return;
+  bool active = false;
+  u64 a = 0, b = 0;
+  u32 fst = GGR_NIL;
+  if (i < n) {
+    out_off[i] = off;
+    if (sz != 0 && status[i] == GST_OK) {
+      if (off + sz > out_cap) {
+        status[i] = GST_NO_SPACE;
+      } else {
+        active = true;
+        a = in_off[i];
+        b = in_off[i + 1];
+        fst = first[i];
+      }
+    }
   }
-  u64 a = in_off[i], b = in_off[i + 1];
   u64 node_off = (a >> 1) + 8ull * (u64)i;
   const u8* base = in + (a & ~15ull);
   u32 s0 = (u32)(a & 15ull);
   Wr w;
   w.init(out + (off & ~7ull), (u32)(off & 7ull));
-  encode_emit(base, s0 + (u32)(b - a), ir + node_off * 16, first[i], w);
-  w.finish();
+  encode_emit(base, s0 + (u32)(b - a), ir + node_off * 16, fst, w, active, GGR_FULL_MASK);
+  if (active) {
+    w.finish();
+    if (w.pos != (u32)(off & 7ull) + sz) status[i] = GST_INTERNAL;
+  }
 }
 
 __global__ void __launch_bounds__(GGR_BLOCK)
@@ -149,23 +171,29 @@ k_decode_size(const u8* __restrict__ blob, long long n, u32 n_msgs, const i32* _
               u32* __restrict__ mode, i32* __restrict__ status, u64* __restrict__ block_sums) {
   long long i = (long long)blockIdx.x * GGR_BLOCK + threadIdx.x;
   u32 sz = 0;
+  u64 a = 0, b = 0;
+  i32 m = 0;
+  int st = GST_OK;
+  bool active = false;
   if (i < n) {
-    u64 a = in_off[i], b = in_off[i + 1];
-    i32 m = msg_id[i];
-    int st;
-    DecResult res;
-    res.size = 0;
-    res.mode = GGR_MODE_FAST;
-    if (m < 0 || (u32)m >= n_msgs || b < a) {
-      st = GST_UNSUPPORTED;
-    } else if (b - a > 0x7FFFFFF0ull) {
-      st = GST_TOO_LARGE;
-    } else {
-      Tables T = ggr_tables(blob);
-      const u8* base = in + (a & ~15ull);
-      u32 s0 = (u32)(a & 15ull);
-      st = decode_size(T, (u32)m, base, s0, s0 + (u32)(b - a), flags, &res);
-    }
+    a = in_off[i];
+    b = in_off[i + 1];
+    m = msg_id[i];
+    if (m < 0 || (u32)m >= n_msgs || b < a) st = GST_UNSUPPORTED;
+    else if (b - a > 0x7FFFFFF0ull) st = GST_TOO_LARGE;
+    else active = true;
+  }
+  DecResult res;
+  res.size = 0;
+  res.mode = GGR_MODE_FAST;
+  {
+    Tables T = ggr_tables(blob);
+    const u8* base = in + (a & ~15ull);
+    u32 s0 = (u32)(a & 15ull);
+    int r = decode_size(T, (u32)m, base, s0, s0 + (u32)(b - a), flags, &res, active, GGR_FULL_MASK);
+    if (active) st = r;
+  }
+  if (i < n) {
     if (st != GST_OK) res.size = 0;
     sz = res.size;
     size[i] = sz;
@@ -186,22 +214,35 @@ k_decode_write(const u8* __restrict__ blob, long long n, const i32* __restrict__
   u32 sz = i < n ? size[i] : 0;
   u32 tot;
   u32 excl = block_excl_scan(sz, &tot);
-  if (i >= n) return;
   u64 off = block_prefix[blockIdx.x] + excl;
-  out_off[i] = off;
-  if (sz == 0 || status[i] != GST_OK) return;
-  if (off + sz > out_cap) {
-    status[i] = GST_NO_SPACE;
-    return;
+  bool active = false;
+  u64 a = 0, b = 0;
+  u32 md = GGR_MODE_FAST;
+  i32 m = 0;
+  if (i < n) {
+    out_off[i] = off;
+    if (sz != 0 && status[i] == GST_OK) {
+      if (off + sz > out_cap) {
+        status[i] = GST_NO_SPACE;
+      } else {
+        active = true;
+        a = in_off[i];
+        b = in_off[i + 1];
+        md = mode[i];
+        m = msg_id[i];
+      }
+    }
   }
-  u64 a = in_off[i], b = in_off[i + 1];
   Tables T = ggr_tables(blob);
   const u8* base = in + (a & ~15ull);
   u32 s0 = (u32)(a & 15ull);
-  u32 end_pos;
-  int st = decode_write(T, (u32)msg_id[i], base, s0, s0 + (u32)(b - a), flags, mode[i], out + (off & ~7ull),
-                        (u32)(off & 7ull), &end_pos);
-  if (st != GST_OK) status[i] = st;
+  u32 end_pos = 0;
+  int st = decode_write(T, (u32)m, base, s0, s0 + (u32)(b - a), flags, md, out + (off & ~7ull), (u32)(off & 7ull), &end_pos,
+                        active, GGR_FULL_MASK);
+  if (active) {
+    if (st == GST_OK && end_pos != (u32)(off & 7ull) + sz) st = GST_INTERNAL;
+    if (st != GST_OK) status[i] = st;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -271,8 +312,8 @@ extern "C" {
 
 const char* ggr_status_string(int32_t st) {
   static const char* names[] = {"ok", "syntax", "unknown_field", "invalid_value", "range", "invalid_utf8", "duplicate",
-                                "oneof_conflict", "depth", "too_large", "bad_wire", "unsupported", "no_space"};
-  if (st < 0 || st > 12) return "?";
+                                "oneof_conflict", "depth", "too_large", "bad_wire", "unsupported", "no_space", "internal"};
+  if (st < 0 || st > 13) return "?";
   return names[st];
 }
 
@@ -298,11 +339,25 @@ int ggr_engine_create(const ggr_config* cfg, ggr_engine** out) {
     return GGR_ERR_CUDA;
   }
   // message-valued map entries recurse (bounded, GGR_DEC_MAX_REC); give the walkers room
-  cudaFuncAttributes fw;
-  size_t need = 4096;
-  if (cudaFuncGetAttributes(&fw, (const void*)k_decode_write) == cudaSuccess) need += fw.localSizeBytes;
-  cudaDeviceSetLimit(cudaLimitStackSize, 4096 + (GGR_DEC_MAX_REC + 1) * 3072);
-  (void)need;
+  {
+    size_t want = 4096 + (size_t)(GGR_DEC_MAX_REC + 1) * 4096, cur = 0;
+    if (const char* ev = getenv("GGR_STACK_BYTES")) want = (size_t)strtoull(ev, nullptr, 10);
+    cudaDeviceGetLimit(&cur, cudaLimitStackSize);
+    if (cur < want) {
+      cudaError_t rc = cudaDeviceSetLimit(cudaLimitStackSize, want);
+      if (rc != cudaSuccess) {
+        e->err = std::string("cudaDeviceSetLimit(stack): ") + cudaGetErrorString(rc);
+        cudaStreamDestroy(e->stream);
+        delete e;
+        return GGR_ERR_CUDA;
+      }
+    }
+    if (getenv("GGR_DEBUG")) {
+      size_t now = 0;
+      cudaDeviceGetLimit(&now, cudaLimitStackSize);
+      fprintf(stderr, "[ggr] stack limit was %zu, wanted %zu, now %zu\n", cur, want, now);
+    }
+  }
   *out = e;
   return GGR_SUCCESS;
 }

@@ -98,5 +98,6 @@ struct GgrHashEnt {  // 16 bytes; name_len == 0xFFFFFFFF marks an empty slot
 enum {
   GST_OK = 0, GST_SYNTAX = 1, GST_UNKNOWN_FIELD = 2, GST_INVALID_VALUE = 3, GST_RANGE = 4,
   GST_INVALID_UTF8 = 5, GST_DUPLICATE = 6, GST_ONEOF = 7, GST_DEPTH = 8, GST_TOO_LARGE = 9,
-  GST_BAD_WIRE = 10, GST_UNSUPPORTED = 11, GST_NO_SPACE = 12
+  GST_BAD_WIRE = 10, GST_UNSUPPORTED = 11, GST_NO_SPACE = 12,
+  GST_INTERNAL = 13  /* size pass and write pass disagreed: engine bug, never expected */
 };

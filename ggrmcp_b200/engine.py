@@ -18,7 +18,7 @@ F_COMMA_SPACE = 1
 ORDER_FIELD_NUMBER = 0
 ORDER_GO_LEGACY = 1
 STATUS_NAMES = ["ok", "syntax", "unknown_field", "invalid_value", "range", "invalid_utf8", "duplicate",
-                "oneof_conflict", "depth", "too_large", "bad_wire", "unsupported", "no_space"]
+                "oneof_conflict", "depth", "too_large", "bad_wire", "unsupported", "no_space", "internal"]
 
 
 class EngineError(RuntimeError):

@@ -62,7 +62,8 @@ enum {
   GGR_ST_TOO_LARGE = 9,
   GGR_ST_BAD_WIRE = 10,      /* "cannot parse invalid wire-format data"                   */
   GGR_ST_UNSUPPORTED = 11,   /* construct outside the implemented subset  */
-  GGR_ST_NO_SPACE = 12
+  GGR_ST_NO_SPACE = 12,
+  GGR_ST_INTERNAL = 13       /* engine self-check failed (size pass != write pass)            */
 };
 
 /* ggr_config.wire_order */

@@ -34,7 +34,7 @@ def test_status_strings():
     lib.ggr_status_string.restype = ctypes.c_char_p
     assert lib.ggr_status_string(0) == b"ok"
     assert lib.ggr_status_string(2) == b"unknown_field"
-    assert [lib.ggr_status_string(i).decode() for i in range(13)] == ggrmcp_b200.STATUS_NAMES
+    assert [lib.ggr_status_string(i).decode() for i in range(14)] == ggrmcp_b200.STATUS_NAMES
 
 
 def test_no_cpu_fallback():
