@@ -18,8 +18,12 @@
 #pragma once
 #include "ggr_prim.cuh"
 #include "ggr_json_in.cuh"
+#include "ggr_float.cuh"
 
 #define GGR_DEC_MAX_DEPTH 32
+#ifndef GGR_RET
+#define GGR_RET(x) do { rr = (x); goto step_end; } while (0)
+#endif
 #ifndef GGR_F_COMMA_SPACE
 #define GGR_F_COMMA_SPACE 1u
 #endif
@@ -398,7 +402,10 @@ GGR_DEV int scalar_value(W& w, const DecCtx& cx, Rd& r, u32 lim, u32 kind, i32 c
     case GK_SINT64: sv = (i64)((v >> 1) ^ (0ull - (v & 1))); is_signed = true; is64 = true; break;
     case GK_UINT64: case GK_FIXED64: is64 = true; break;
     case GK_BOOL: v = v != 0; break;
-    case GK_FLOAT: case GK_DOUBLE: return GST_UNSUPPORTED;  // shortest float printing lands with the float kernels
+    case GK_FLOAT: case GK_DOUBLE:
+      *zero = v == 0;  // bit pattern: -0.0 is set (dynamicpb isSet)
+      if (EMIT) put_float_go(w, v, kind == GK_FLOAT);
+      return GST_OK;
     default: break;
   }
   *zero = is_signed ? sv == 0 : v == 0;
@@ -817,59 +824,59 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
   // `mask` re-converge at the vote after every step
   while (ggr_any(mask, !finished)) {
    if (!finished) {
-    int rr = [&]() -> int {
+    int rr = GGR_STEP_CONT;
   for (int once = 0;; once++) {
-    if (once) return GGR_STEP_CONT;
+    if (once) break;
     if (!SLOW) {
       // ================= fast walk =================
       if (r.pos >= fr.end) {
-        if (r.pos != fr.end) return GST_BAD_WIRE;
+        if (r.pos != fr.end) GGR_RET(GST_BAD_WIRE);
         if (fr.open) w.put1(']');
         w.put1('}');
-        if (depth == 0) return GST_OK;
+        if (depth == 0) GGR_RET(GST_OK);
         fr = stk[--depth];
         md = ggr_msg(T, fr.msg);
         continue;
       }
       u64 tag;
-      if (!rd_varint(r, fr.end, &tag)) return GST_BAD_WIRE;
+      if (!rd_varint(r, fr.end, &tag)) GGR_RET(GST_BAD_WIRE);
       u64 num64 = tag >> 3;
       u32 wt = (u32)(tag & 7);
-      if (num64 == 0 || num64 > 0x1FFFFFFFull || wt == 4 || wt > 5) return GST_BAD_WIRE;
+      if (num64 == 0 || num64 > 0x1FFFFFFFull || wt == 4 || wt > 5) GGR_RET(GST_BAD_WIRE);
       u32 num = (u32)num64;
       i32 ei = find_field(T, md, num);
       if (ei < 0) {
-        if (!rd_skip_value(r, fr.end, num, wt)) return GST_BAD_WIRE;
+        if (!rd_skip_value(r, fr.end, num, wt)) GGR_RET(GST_BAD_WIRE);
         continue;
       }
       FieldD f = ggr_field(T, md.field_first + (u32)ei);
       bool packed_in = (f.flags & GF_PACKABLE) && wt == 2;
       if (wt != f.wt && !packed_in) {  // wire type mismatch: treated as an unknown field
-        if (!rd_skip_value(r, fr.end, num, wt)) return GST_BAD_WIRE;
+        if (!rd_skip_value(r, fr.end, num, wt)) GGR_RET(GST_BAD_WIRE);
         continue;
       }
       if (f.flags & GF_MAP) {
         if (fr.open) { w.put1(']'); fr.open = 0; }
-        if ((i32)f.decl_index <= fr.last_decl) return GGR_NEED_SLOW;
+        if ((i32)f.decl_index <= fr.last_decl) GGR_RET(GGR_NEED_SLOW);
         fr.last_decl = (i32)f.decl_index;
         // the key text is written only when the map has entries (always true here)
         put_sep(w, cx, fr.first);
         put_pool(w, T.pool, f.name_off, f.name_len);
         int st = put_map_field<W, false>(w, cx, r, f, r.pos, fr.end, rec);
-        if (st != GST_OK) return st;
+        if (st != GST_OK) GGR_RET(st);
         continue;
       }
       if (f.flags & GF_REPEATED) {
         if (fr.open != (u32)ei + 1) {
           if (fr.open) w.put1(']');
           fr.open = 0;
-          if ((i32)f.decl_index <= fr.last_decl) return GGR_NEED_SLOW;
+          if ((i32)f.decl_index <= fr.last_decl) GGR_RET(GGR_NEED_SLOW);
           // a packed field with an empty payload contributes no elements: dynamicpb then holds
           // an empty list, which protojson omits.  Look ahead before writing the key.
           if (packed_in) {
             Rd t = r;
             u64 len;
-            if (!rd_varint(t, fr.end, &len) || len > (u64)(fr.end - t.pos)) return GST_BAD_WIRE;
+            if (!rd_varint(t, fr.end, &len) || len > (u64)(fr.end - t.pos)) GGR_RET(GST_BAD_WIRE);
             if (len == 0) {
               r = t;
               continue;
@@ -884,31 +891,31 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
         }
         if (packed_in) {
           u64 len;
-          if (!rd_varint(r, fr.end, &len) || len > (u64)(fr.end - r.pos)) return GST_BAD_WIRE;
+          if (!rd_varint(r, fr.end, &len) || len > (u64)(fr.end - r.pos)) GGR_RET(GST_BAD_WIRE);
           u32 lim = r.pos + (u32)len;
           while (r.pos < lim) {
             put_sep(w, cx, fr.elem_first);
             bool z;
             int st = scalar_value<W, true>(w, cx, r, lim, f.kind, f.child, false, &z);
-            if (st != GST_OK) return st;
+            if (st != GST_OK) GGR_RET(st);
           }
-          if (r.pos != lim) return GST_BAD_WIRE;
+          if (r.pos != lim) GGR_RET(GST_BAD_WIRE);
           continue;
         }
         put_sep(w, cx, fr.elem_first);
         if (f.kind != GK_MESSAGE) {
           bool z;
           int st = scalar_value<W, true>(w, cx, r, fr.end, f.kind, f.child, false, &z);
-          if (st != GST_OK) return st;
+          if (st != GST_OK) GGR_RET(st);
           continue;
         }
         // message element: falls through to the message push below
       } else {
         if (fr.open) { w.put1(']'); fr.open = 0; }
-        if ((i32)f.decl_index <= fr.last_decl) return GGR_NEED_SLOW;
+        if ((i32)f.decl_index <= fr.last_decl) GGR_RET(GGR_NEED_SLOW);
         if (f.oneof >= 0) {
           u32 bit = 1u << (f.oneof & 31);
-          if (fr.oneofs & bit) return GGR_NEED_SLOW;  // last member wins: needs the slow walk
+          if (fr.oneofs & bit) GGR_RET(GGR_NEED_SLOW);  // last member wins: needs the slow walk
           fr.oneofs |= bit;
         }
         fr.last_decl = (i32)f.decl_index;
@@ -920,13 +927,13 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
             bool z;
             if (f.wt == 2) {
               u64 len;
-              if (!rd_varint(t, fr.end, &len) || len > (u64)(fr.end - t.pos)) return GST_BAD_WIRE;
+              if (!rd_varint(t, fr.end, &len) || len > (u64)(fr.end - t.pos)) GGR_RET(GST_BAD_WIRE);
               z = len == 0;
             } else {
               Cnt c;
               c.pos = 0;
               int st = scalar_value<Cnt, false>(c, cx, t, fr.end, f.kind, f.child, false, &z);
-              if (st != GST_OK) return st;
+              if (st != GST_OK) GGR_RET(st);
             }
             if (z) {
               r = t;
@@ -937,7 +944,7 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
           put_pool(w, T.pool, f.name_off, f.name_len);
           bool z;
           int st = scalar_value<W, true>(w, cx, r, fr.end, f.kind, f.child, false, &z);
-          if (st != GST_OK) return st;
+          if (st != GST_OK) GGR_RET(st);
           continue;
         }
         put_sep(w, cx, fr.first);
@@ -946,19 +953,19 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
       // ---- message value (singular or repeated element) ----
       {
         u64 len;
-        if (!rd_varint(r, fr.end, &len) || len > (u64)(fr.end - r.pos)) return GST_BAD_WIRE;
+        if (!rd_varint(r, fr.end, &len) || len > (u64)(fr.end - r.pos)) GGR_RET(GST_BAD_WIRE);
         u32 lim = r.pos + (u32)len;
         MsgD cd = ggr_msg(T, (u32)f.child);
         if (cd.wkt == GGR_WKT_TIMESTAMP) {
           i64 s, n;
           int st = read_timestamp_payload(r, lim, &s, &n);
-          if (st != GST_OK) return st;
+          if (st != GST_OK) GGR_RET(st);
           st = put_timestamp(w, s, n);
-          if (st != GST_OK) return st;
+          if (st != GST_OK) GGR_RET(st);
           continue;
         }
-        if (cd.wkt != GGR_WKT_NONE) return GST_UNSUPPORTED;
-        if (depth >= GGR_DEC_MAX_DEPTH - 1) return GST_DEPTH;
+        if (cd.wkt != GGR_WKT_NONE) GGR_RET(GST_UNSUPPORTED);
+        if (depth >= GGR_DEC_MAX_DEPTH - 1) GGR_RET(GST_DEPTH);
         stk[depth++] = fr;
         fr.end = lim; fr.msg = (u32)f.child; fr.last_decl = -1; fr.open = 0; fr.first = 1; fr.elem_first = 1; fr.oneofs = 0;
         fr.start = r.pos; fr.scan = r.pos; fr.cur_emit = 0; fr.state = 0;
@@ -981,14 +988,14 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
             t.init(cx.in, fr.start, fr.end);
             while (t.pos < fr.end) {
               u64 tag;
-              if (!rd_varint(t, fr.end, &tag)) return GST_BAD_WIRE;
+              if (!rd_varint(t, fr.end, &tag)) GGR_RET(GST_BAD_WIRE);
               u64 n2 = tag >> 3;
-              if (n2 == 0 || n2 > 0x1FFFFFFFull || (tag & 7) == 4 || (tag & 7) > 5) return GST_BAD_WIRE;
-              if (!rd_skip_value(t, fr.end, (u32)n2, (u32)(tag & 7))) return GST_BAD_WIRE;
+              if (n2 == 0 || n2 > 0x1FFFFFFFull || (tag & 7) == 4 || (tag & 7) > 5) GGR_RET(GST_BAD_WIRE);
+              if (!rd_skip_value(t, fr.end, (u32)n2, (u32)(tag & 7))) GGR_RET(GST_BAD_WIRE);
             }
           }
           w.put1('}');
-          if (depth == 0) return GST_OK;
+          if (depth == 0) GGR_RET(GST_OK);
           fr = stk[--depth];
           md = ggr_msg(T, fr.msg);
           continue;
@@ -1008,12 +1015,12 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
         Rd t;
         t.init(cx.in, fr.start, fr.end);
         int st = put_map_field<Cnt, true>(c, cx, t, f, fr.start, fr.end, rec);
-        if (st != GST_OK) return st;
+        if (st != GST_OK) GGR_RET(st);
         if (c.pos == 0) continue;
         put_sep(w, cx, fr.first);
         put_pool(w, T.pool, f.name_off, f.name_len);
         st = put_map_field<W, true>(w, cx, t, f, fr.start, fr.end, rec);
-        if (st != GST_OK) return st;
+        if (st != GST_OK) GGR_RET(st);
         continue;
       }
       bool repeated = (f.flags & GF_REPEATED) != 0;
@@ -1025,26 +1032,26 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
       bool pushed = false;
       while (t.pos < fr.end) {
         u64 tag;
-        if (!rd_varint(t, fr.end, &tag)) return GST_BAD_WIRE;
+        if (!rd_varint(t, fr.end, &tag)) GGR_RET(GST_BAD_WIRE);
         u64 n2 = tag >> 3;
         u32 wt = (u32)(tag & 7);
-        if (n2 == 0 || n2 > 0x1FFFFFFFull || wt == 4 || wt > 5) return GST_BAD_WIRE;
+        if (n2 == 0 || n2 > 0x1FFFFFFFull || wt == 4 || wt > 5) GGR_RET(GST_BAD_WIRE);
         bool packed_in = (f.flags & GF_PACKABLE) && wt == 2;
         if ((u32)n2 != f.number || (wt != f.wt && !packed_in)) {
-          if (!rd_skip_value(t, fr.end, (u32)n2, wt)) return GST_BAD_WIRE;
+          if (!rd_skip_value(t, fr.end, (u32)n2, wt)) GGR_RET(GST_BAD_WIRE);
           continue;
         }
         if (!repeated) {
           last_pos = t.pos;
           last_wt = wt;
           n_occ++;
-          if (!rd_skip_value(t, fr.end, (u32)n2, wt)) return GST_BAD_WIRE;
+          if (!rd_skip_value(t, fr.end, (u32)n2, wt)) GGR_RET(GST_BAD_WIRE);
           continue;
         }
         // repeated occurrence
         if (packed_in) {
           u64 len;
-          if (!rd_varint(t, fr.end, &len) || len > (u64)(fr.end - t.pos)) return GST_BAD_WIRE;
+          if (!rd_varint(t, fr.end, &len) || len > (u64)(fr.end - t.pos)) GGR_RET(GST_BAD_WIRE);
           u32 lim = t.pos + (u32)len;
           while (t.pos < lim) {
             if (!fr.open) {
@@ -1056,9 +1063,9 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
             put_sep(w, cx, fr.elem_first);
             bool z;
             int st = scalar_value<W, true>(w, cx, t, lim, f.kind, f.child, false, &z);
-            if (st != GST_OK) return st;
+            if (st != GST_OK) GGR_RET(st);
           }
-          if (t.pos != lim) return GST_BAD_WIRE;
+          if (t.pos != lim) GGR_RET(GST_BAD_WIRE);
           continue;
         }
         if (!fr.open) {
@@ -1071,24 +1078,24 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
         if (f.kind != GK_MESSAGE) {
           bool z;
           int st = scalar_value<W, true>(w, cx, t, fr.end, f.kind, f.child, false, &z);
-          if (st != GST_OK) return st;
+          if (st != GST_OK) GGR_RET(st);
           continue;
         }
         // message element: push a frame, resume this scan afterwards
         u64 len;
-        if (!rd_varint(t, fr.end, &len) || len > (u64)(fr.end - t.pos)) return GST_BAD_WIRE;
+        if (!rd_varint(t, fr.end, &len) || len > (u64)(fr.end - t.pos)) GGR_RET(GST_BAD_WIRE);
         u32 lim = t.pos + (u32)len;
         MsgD cd = ggr_msg(T, (u32)f.child);
         if (cd.wkt == GGR_WKT_TIMESTAMP) {
           i64 s, n;
           int st = read_timestamp_payload(t, lim, &s, &n);
-          if (st != GST_OK) return st;
+          if (st != GST_OK) GGR_RET(st);
           st = put_timestamp(w, s, n);
-          if (st != GST_OK) return st;
+          if (st != GST_OK) GGR_RET(st);
           continue;
         }
-        if (cd.wkt != GGR_WKT_NONE) return GST_UNSUPPORTED;
-        if (depth >= GGR_DEC_MAX_DEPTH - 1) return GST_DEPTH;
+        if (cd.wkt != GGR_WKT_NONE) GGR_RET(GST_UNSUPPORTED);
+        if (depth >= GGR_DEC_MAX_DEPTH - 1) GGR_RET(GST_DEPTH);
         fr.state = 1;
         fr.scan = lim;
         stk[depth++] = fr;
@@ -1113,26 +1120,26 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
         bool later = false;
         Rd q;
         q.init(cx.in, last_pos, fr.end);
-        if (!rd_skip_value(q, fr.end, f.number, last_wt)) return GST_BAD_WIRE;
+        if (!rd_skip_value(q, fr.end, f.number, last_wt)) GGR_RET(GST_BAD_WIRE);
         while (q.pos < fr.end && !later) {
           u64 tag;
-          if (!rd_varint(q, fr.end, &tag)) return GST_BAD_WIRE;
+          if (!rd_varint(q, fr.end, &tag)) GGR_RET(GST_BAD_WIRE);
           u32 n3 = (u32)(tag >> 3), w3 = (u32)(tag & 7);
           i32 e3 = find_field(T, md, n3);
           if (e3 >= 0 && (u32)e3 != fr.cur_emit) {
             FieldD g = ggr_field(T, md.field_first + (u32)e3);
             if (g.oneof == f.oneof && (w3 == g.wt)) later = true;
           }
-          if (!rd_skip_value(q, fr.end, n3, w3)) return GST_BAD_WIRE;
+          if (!rd_skip_value(q, fr.end, n3, w3)) GGR_RET(GST_BAD_WIRE);
         }
         if (later) continue;
       }
       if (f.kind == GK_MESSAGE) {
-        if (n_occ > 1) return GST_UNSUPPORTED;  // merging split sub-messages is not implemented
+        if (n_occ > 1) GGR_RET(GST_UNSUPPORTED);  // merging split sub-messages is not implemented
         Rd q;
         q.init(cx.in, last_pos, fr.end);
         u64 len;
-        if (!rd_varint(q, fr.end, &len) || len > (u64)(fr.end - q.pos)) return GST_BAD_WIRE;
+        if (!rd_varint(q, fr.end, &len) || len > (u64)(fr.end - q.pos)) GGR_RET(GST_BAD_WIRE);
         u32 lim = q.pos + (u32)len;
         MsgD cd = ggr_msg(T, (u32)f.child);
         put_sep(w, cx, fr.first);
@@ -1140,13 +1147,13 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
         if (cd.wkt == GGR_WKT_TIMESTAMP) {
           i64 s, n;
           int st = read_timestamp_payload(q, lim, &s, &n);
-          if (st != GST_OK) return st;
+          if (st != GST_OK) GGR_RET(st);
           st = put_timestamp(w, s, n);
-          if (st != GST_OK) return st;
+          if (st != GST_OK) GGR_RET(st);
           continue;
         }
-        if (cd.wkt != GGR_WKT_NONE) return GST_UNSUPPORTED;
-        if (depth >= GGR_DEC_MAX_DEPTH - 1) return GST_DEPTH;
+        if (cd.wkt != GGR_WKT_NONE) GGR_RET(GST_UNSUPPORTED);
+        if (depth >= GGR_DEC_MAX_DEPTH - 1) GGR_RET(GST_DEPTH);
         stk[depth++] = fr;
         fr.end = lim; fr.msg = (u32)f.child; fr.last_decl = -1; fr.open = 0; fr.first = 1; fr.elem_first = 1; fr.oneofs = 0;
         fr.start = q.pos; fr.scan = q.pos; fr.cur_emit = 0; fr.state = 0;
@@ -1161,16 +1168,16 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
         // validate all occurrences (strings: UTF-8) the way proto.Unmarshal would
         while (q.pos < fr.end) {
           u64 tag;
-          if (!rd_varint(q, fr.end, &tag)) return GST_BAD_WIRE;
+          if (!rd_varint(q, fr.end, &tag)) GGR_RET(GST_BAD_WIRE);
           u32 n3 = (u32)(tag >> 3), w3 = (u32)(tag & 7);
           if (n3 == f.number && w3 == f.wt && f.kind == GK_STRING) {
             bool z;
             Cnt c;
             c.pos = 0;
             int st = scalar_value<Cnt, false>(c, cx, q, fr.end, f.kind, f.child, false, &z);
-            if (st != GST_OK) return st;
+            if (st != GST_OK) GGR_RET(st);
           } else if (!rd_skip_value(q, fr.end, n3, w3)) {
-            return GST_BAD_WIRE;
+            GGR_RET(GST_BAD_WIRE);
           }
         }
         q.init(cx.in, last_pos, fr.end);
@@ -1180,18 +1187,18 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
           Cnt c;
           c.pos = 0;
           int st = scalar_value<Cnt, false>(c, cx, t2, fr.end, f.kind, f.child, false, &z);
-          if (st != GST_OK) return st;
+          if (st != GST_OK) GGR_RET(st);
           if (z) continue;
         }
         put_sep(w, cx, fr.first);
         put_pool(w, T.pool, f.name_off, f.name_len);
         bool z;
         int st = scalar_value<W, true>(w, cx, q, fr.end, f.kind, f.child, false, &z);
-        if (st != GST_OK) return st;
+        if (st != GST_OK) GGR_RET(st);
       }
     }
   }
-    }();
+  step_end:
     if (rr != GGR_STEP_CONT) {
       finished = true;
       result = rr;

@@ -16,8 +16,11 @@
 // tests compare against.
 #pragma once
 #include "ggr_json_in.cuh"
+#include "ggr_float.cuh"
 
 #define GGR_MAX_DEPTH 32
+// leave the current step with a result (used inside the convergent step loops)
+#define GGR_RET(x) do { rr = (x); goto step_end; } while (0)
 #define GGR_NIL 0xFFFFFu
 #define GGR_MAX_NODES 0xFFFFFu
 
@@ -60,6 +63,8 @@ struct Frame {
   // FR_MAP: entry under construction
   u32 ent_node, key_node, key_body;
   u64 tail_key;  // FR_MAP: numeric key of tail entry / source position of its string key
+  // FR_MSG: this message's key table and first field (cached from GgrMsg)
+  u32 kh_first, kh_mask, field_first;
 };
 
 struct EncCtx {
@@ -317,14 +322,12 @@ GGR_DEV int parse_scalar(EncCtx& cx, Rd& r, u32 kind, i32 child, Leaf* l) {
     case GK_ENUM: {
       if (c == '"') {
         u32 q = r.pos;
-        StrInfo si;
-        int st = scan_string<false>(r, &si);
+        KeyInfo ki;
+        int st = scan_key(r, &ki);
         if (st != GST_OK) return st;
-        u32 h, len;
-        hash_string(cx.in, q, cx.end, &h, &len);
         U4 e = ggr_ld16(cx.T.enums + (size_t)child * 16);
         i32 num;
-        if (!hash_lookup(cx.T, e.z, e.w, h, len, cx.in, q, cx.end, &num)) return GST_INVALID_VALUE;
+        if (!hash_lookup(cx.T, e.z, e.w, ki, cx.in, q, cx.end, &num)) return GST_INVALID_VALUE;
         leaf_from_int(GK_ENUM, (u64)(i64)num, l);
         return GST_OK;
       }
@@ -372,8 +375,57 @@ GGR_DEV int parse_scalar(EncCtx& cx, Rd& r, u32 kind, i32 child, Leaf* l) {
       l->zero = n == 0;
       return GST_OK;
     }
-    case GK_FLOAT: case GK_DOUBLE:
-      return GST_UNSUPPORTED;  // decimal -> binary conversion lands with the float kernels
+    case GK_FLOAT: case GK_DOUBLE: {
+      // [upstream protojson unmarshalFloat]: number token, or a string holding NaN / Infinity /
+      // -Infinity / one number token; strconv.ParseFloat decides, a range error is an error.
+      const bool is32 = kind == GK_FLOAT;
+      NumTok t;
+      u64 bits = 0;
+      bool ok;
+      if (c == '"') {
+        u32 q = r.pos;
+        StrInfo si;
+        int st = scan_string<false>(r, &si);
+        if (st != GST_OK) return st;
+        if (str_token_is(cx.in, q, cx.end, "NaN", 3)) {
+          bits = is32 ? 0x7FC00000ull : 0x7FF8000000000001ull;  // float32(math.NaN()) / math.NaN()
+          ok = true;
+        } else if (str_token_is(cx.in, q, cx.end, "Infinity", 8)) {
+          bits = is32 ? 0x7F800000ull : 0x7FF0000000000000ull;
+          ok = true;
+        } else if (str_token_is(cx.in, q, cx.end, "-Infinity", 9)) {
+          bits = is32 ? 0xFF800000ull : 0xFFF0000000000000ull;
+          ok = true;
+        } else {
+          if (si.dec_len == 0) return GST_INVALID_VALUE;
+          StrIter it;
+          it.init(cx.in, q, cx.end);
+          if (!parse_number(it, &t)) return GST_INVALID_VALUE;
+          StrIter e2;
+          e2.init(cx.in, q, cx.end);
+          u32 last = 0;
+          while (!e2.eof()) { last = e2.peek(); e2.adv(); }
+          if (last == ' ' || (last - 9u) < 5u) return GST_INVALID_VALUE;
+          StrIter again;
+          again.init(cx.in, q, cx.end);
+          ok = float_from_token(again, t, is32, &bits);
+        }
+      } else if (c == '-' || c - '0' < 10u) {
+        Rd start = r;
+        RawIter it = {&r};
+        if (!parse_number(it, &t)) return GST_SYNTAX;
+        RawIter again = {&start};
+        ok = float_from_token(again, t, is32, &bits);
+      } else {
+        break;
+      }
+      if (!ok) return GST_INVALID_VALUE;
+      l->flags = 0;
+      l->zero = bits == 0;  // -0.0 is "set" (dynamicpb isSet: value != 0 || signbit)
+      if (is32) { l->type = N_FIX32; l->a = (u32)bits; l->b = 0; l->body = 4; }
+      else { l->type = N_FIX64; l->a = (u32)bits; l->b = (u32)(bits >> 32); l->body = 8; }
+      return GST_OK;
+    }
     default:
       return GST_UNSUPPORTED;
   }
@@ -544,14 +596,15 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
   fr.ent_node = fr.key_node = GGR_NIL;
   fr.key_body = 0;
   fr.tail_key = 0;
+  fr.kh_first = fr.kh_mask = fr.field_first = 0;
 
   // One step = one member / element / container close.  All lanes of `mask` re-converge at the
   // vote after every step (see ggr_prim.cuh).
   while (ggr_any(mask, !finished)) {
    if (!finished) {
-    int rr = [&]() -> int {
+    int rr = GGR_STEP_CONT;
   for (int once = 0;; once++) {
-    if (once) return GGR_STEP_CONT;  // `continue` in the body below ends the step
+    if (once) break;  // `continue` in the body below ends the step
     skip_ws(r);
     // ---- what does the current container expect? ----
     FieldD f;          // field the upcoming value belongs to
@@ -571,10 +624,10 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
         f.number = 0; f.wt = 2; f.decl_index = 0; f.name_off = 0; f.name_len = 0;
         want_value = true;
       } else {
-        if (!r.eof()) return GST_SYNTAX;
+        if (!r.eof()) GGR_RET(GST_SYNTAX);
         res->size = fr.size;
         res->first = fr.head;
-        return GST_OK;
+        GGR_RET(GST_OK);
       }
     } else if (fr.kind == FR_MSG || fr.kind == FR_MAP) {
       u32 c = r.get();
@@ -583,73 +636,74 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
         goto close_container;
       }
       if (fr.st == 1) {
-        if (c != ',') return GST_SYNTAX;
+        if (c != ',') GGR_RET(GST_SYNTAX);
         r.skip(1);
         skip_ws(r);
         c = r.get();
       }
-      if (c != '"') return GST_SYNTAX;
+      if (c != '"') GGR_RET(GST_SYNTAX);
       u32 key_pos = r.pos;
       StrInfo ks;
-      int st = scan_string<false>(r, &ks);
-      if (st != GST_OK) return st;
+      KeyInfo ki;
+      ks.dec_len = 0; ks.flags = 0;
+      int st = (fr.kind == FR_MSG) ? scan_key(r, &ki) : scan_string<false>(r, &ks);
+      if (st != GST_OK) GGR_RET(st);
       skip_ws(r);
-      if (r.get() != ':') return GST_SYNTAX;
+      if (r.get() != ':') GGR_RET(GST_SYNTAX);
       r.skip(1);
       skip_ws(r);
       fr.st = 1;
       if (fr.kind == FR_MSG) {
-        MsgD md = ggr_msg(T, fr.ref);
-        u32 h, len;
-        hash_string(in, key_pos, end, &h, &len);
         i32 ei;
-        if (!hash_lookup(T, md.key_hash_first, md.key_hash_mask, h, len, in, key_pos, end, &ei)) return GST_UNKNOWN_FIELD;
+        if (!hash_lookup(T, fr.kh_first, fr.kh_mask, ki, in, key_pos, end, &ei)) GGR_RET(GST_UNKNOWN_FIELD);
         emit = (u32)ei;
-        f = ggr_field(T, md.field_first + emit);
+        f = ggr_field(T, fr.field_first + emit);
         // JSON null: the field is skipped, but it still counts for duplicate detection
         if (r.get() == 'n') {
-          if (!match_literal(r, LIT4('n', 'u', 'l', 'l'), 4, 0)) return GST_SYNTAX;
+          if (!match_literal(r, LIT4('n', 'u', 'l', 'l'), 4, 0)) GGR_RET(GST_SYNTAX);
           u32 idx, nx;
           st = enc_new_node(cx, &idx);
-          if (st != GST_OK) return st;
+          if (st != GST_OK) GGR_RET(st);
           st = frame_add(cx, fr, idx, emit, 0, 0, false, &nx);
-          if (st != GST_OK) return st;
+          if (st != GST_OK) GGR_RET(st);
           node_store(ir, idx, 0, 0, nx, emit, node_meta(N_SKIP, 0, 0));
           continue;
         }
         if (f.flags & GF_MAP) {
-          if (r.get() != '{') return GST_SYNTAX;
+          if (r.get() != '{') GGR_RET(GST_SYNTAX);
           r.skip(1);
-          if (depth >= GGR_MAX_DEPTH - 1) return GST_DEPTH;
+          if (depth >= GGR_MAX_DEPTH - 1) GGR_RET(GST_DEPTH);
           u32 idx;
           st = enc_new_node(cx, &idx);
-          if (st != GST_OK) return st;
+          if (st != GST_OK) GGR_RET(st);
           stk[depth++] = fr;
           Frame nf;
           nf.kind = FR_MAP; nf.st = 0; nf.size = 0; nf.head = nf.tail = GGR_NIL; nf.node = idx;
-          nf.ref = md.field_first + emit; nf.emit = emit; nf.tag = f.tag; nf.oneofs = 0; nf.tail_emit = 0;
+          nf.ref = fr.field_first + emit; nf.emit = emit; nf.tag = f.tag; nf.oneofs = 0; nf.tail_emit = 0;
+          nf.kh_first = nf.kh_mask = nf.field_first = 0;
           nf.ent_node = nf.key_node = GGR_NIL; nf.key_body = 0; nf.tail_key = 0;
           fr = nf;
           continue;
         }
         if (f.flags & GF_REPEATED) {
-          if (r.get() != '[') return GST_SYNTAX;
+          if (r.get() != '[') GGR_RET(GST_SYNTAX);
           r.skip(1);
-          if (depth >= GGR_MAX_DEPTH - 1) return GST_DEPTH;
+          if (depth >= GGR_MAX_DEPTH - 1) GGR_RET(GST_DEPTH);
           u32 idx;
           st = enc_new_node(cx, &idx);
-          if (st != GST_OK) return st;
+          if (st != GST_OK) GGR_RET(st);
           stk[depth++] = fr;
           Frame nf;
           nf.kind = FR_LIST; nf.st = 0; nf.size = 0; nf.head = nf.tail = GGR_NIL; nf.node = idx;
-          nf.ref = md.field_first + emit; nf.emit = emit; nf.tag = f.tag; nf.oneofs = 0; nf.tail_emit = 0;
+          nf.ref = fr.field_first + emit; nf.emit = emit; nf.tag = f.tag; nf.oneofs = 0; nf.tail_emit = 0;
+          nf.kh_first = nf.kh_mask = nf.field_first = 0;
           nf.ent_node = nf.key_node = GGR_NIL; nf.key_body = 0; nf.tail_key = 0;
           fr = nf;
           continue;
         }
         if (f.oneof >= 0) {
           u32 bit = 1u << (f.oneof & 31);
-          if (fr.oneofs & bit) return GST_ONEOF;
+          if (fr.oneofs & bit) GGR_RET(GST_ONEOF);
           fr.oneofs |= bit;
         }
         want_value = true;
@@ -663,9 +717,9 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
         map_key_pos = key_pos;
         u32 kidx, eidx;
         st = enc_new_node(cx, &eidx);
-        if (st != GST_OK) return st;
+        if (st != GST_OK) GGR_RET(st);
         st = enc_new_node(cx, &kidx);
-        if (st != GST_OK) return st;
+        if (st != GST_OK) GGR_RET(st);
         fr.ent_node = eidx;
         fr.key_node = kidx;
         Leaf kl;
@@ -676,12 +730,12 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
           // "true" / "false" exactly
           if (str_token_is(in, key_pos, end, "true", 4)) map_key_val = 1;
           else if (str_token_is(in, key_pos, end, "false", 5)) map_key_val = 0;
-          else return GST_INVALID_VALUE;
+          else GGR_RET(GST_INVALID_VALUE);
           leaf_from_int(GK_BOOL, map_key_val, &kl);
         } else {
           StrIter it;
           it.init(in, key_pos, end);
-          if (!parse_key_int(it, kind_is_signed(kf.kind), kind_bits(kf.kind), &map_key_val)) return GST_INVALID_VALUE;
+          if (!parse_key_int(it, kind_is_signed(kf.kind), kind_bits(kf.kind), &map_key_val)) GGR_RET(GST_INVALID_VALUE);
           leaf_from_int(kf.kind, map_key_val, &kl);
         }
         fr.key_body = 1 + kl.body;  // key tag is one byte (field 1)
@@ -690,8 +744,8 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
         else node_store(ir, kidx, (u32)map_key_val, (u32)(map_key_val >> 32), GGR_NIL, kf.kind, node_meta(kl.type, NF_RAWKEY, kf.tag));
         if (r.get() == 'n' ) {
           // null map values are invalid for every value kind we support
-          if (!match_literal(r, LIT4('n', 'u', 'l', 'l'), 4, 0)) return GST_SYNTAX;
-          return f.kind == GK_MESSAGE ? GST_SYNTAX : GST_INVALID_VALUE;
+          if (!match_literal(r, LIT4('n', 'u', 'l', 'l'), 4, 0)) GGR_RET(GST_SYNTAX);
+          GGR_RET(f.kind == GK_MESSAGE ? GST_SYNTAX : GST_INVALID_VALUE);
         }
         want_value = true;
       }
@@ -702,16 +756,16 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
         goto close_container;
       }
       if (fr.st == 1) {
-        if (c != ',') return GST_SYNTAX;
+        if (c != ',') GGR_RET(GST_SYNTAX);
         r.skip(1);
         skip_ws(r);
-        if (r.get() == ']') return GST_SYNTAX;
+        if (r.get() == ']') GGR_RET(GST_SYNTAX);
       }
       fr.st = 1;
       f = ggr_field(T, fr.ref);
       if (r.get() == 'n') {
-        if (!match_literal(r, LIT4('n', 'u', 'l', 'l'), 4, 0)) return GST_SYNTAX;
-        return f.kind == GK_MESSAGE ? GST_SYNTAX : GST_INVALID_VALUE;
+        if (!match_literal(r, LIT4('n', 'u', 'l', 'l'), 4, 0)) GGR_RET(GST_SYNTAX);
+        GGR_RET(f.kind == GK_MESSAGE ? GST_SYNTAX : GST_INVALID_VALUE);
       }
       want_value = true;
     }
@@ -721,30 +775,30 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
         vmsg = (u32)f.child;
         MsgD vd = ggr_msg(T, vmsg);
         if (vd.wkt == GGR_WKT_TIMESTAMP) {
-          if (r.get() != '"') return GST_SYNTAX;
+          if (r.get() != '"') GGR_RET(GST_SYNTAX);
           u32 q = r.pos;
           StrInfo si;
           int st = scan_string<false>(r, &si);
-          if (st != GST_OK) return st;
+          if (st != GST_OK) GGR_RET(st);
           StrIter it;
           it.init(in, q, end);
           i64 secs;
           i32 nanos;
           st = parse_timestamp(it, &secs, &nanos);
-          if (st != GST_OK) return st;
+          if (st != GST_OK) GGR_RET(st);
           u32 midx, sidx = GGR_NIL, nidx = GGR_NIL;
           st = enc_new_node(cx, &midx);
-          if (st != GST_OK) return st;
+          if (st != GST_OK) GGR_RET(st);
           u32 payload = 0;
           if (nanos != 0) {
             st = enc_new_node(cx, &nidx);
-            if (st != GST_OK) return st;
+            if (st != GST_OK) GGR_RET(st);
             node_store(ir, nidx, (u32)nanos, 0, GGR_NIL, 1, node_meta(N_VARINT, 0, 16));
             payload += 1 + varint_size((u64)(u32)nanos);
           }
           if (secs != 0) {
             st = enc_new_node(cx, &sidx);
-            if (st != GST_OK) return st;
+            if (st != GST_OK) GGR_RET(st);
             node_store(ir, sidx, (u32)(u64)secs, (u32)((u64)secs >> 32), nidx, 0, node_meta(N_VARINT, 0, 8));
             payload += 1 + varint_size((u64)secs);
           }
@@ -755,25 +809,25 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
             node_store(ir, midx, payload, first, GGR_NIL, 1, node_meta(N_MSG, 0, f.tag));
             node_set_next(ir, fr.key_node, midx);
             st = map_entry_done(cx, fr, mapf, map_key_kind, map_key_val, map_key_pos, body);
-            if (st != GST_OK) return st;
+            if (st != GST_OK) GGR_RET(st);
           } else if (fr.kind == FR_ROOT) {
             fr.size = payload;
             fr.head = first;
           } else {
             u32 nx;
             st = frame_add(cx, fr, midx, emit, f.tag_len, body, true, &nx);
-            if (st != GST_OK) return st;
+            if (st != GST_OK) GGR_RET(st);
             node_store(ir, midx, payload, first, nx, emit, node_meta(N_MSG, 0, f.tag));
           }
           continue;
         }
-        if (vd.wkt != GGR_WKT_NONE) return GST_UNSUPPORTED;
-        if (r.get() != '{') return GST_SYNTAX;
+        if (vd.wkt != GGR_WKT_NONE) GGR_RET(GST_UNSUPPORTED);
+        if (r.get() != '{') GGR_RET(GST_SYNTAX);
         r.skip(1);
-        if (depth >= GGR_MAX_DEPTH - 1) return GST_DEPTH;
+        if (depth >= GGR_MAX_DEPTH - 1) GGR_RET(GST_DEPTH);
         u32 idx;
         int st = enc_new_node(cx, &idx);
-        if (st != GST_OK) return st;
+        if (st != GST_OK) GGR_RET(st);
         if (fr.kind == FR_MAP) {
           // remember the pending key for when this message closes (FR_MAP frames do not use
           // tail_emit / oneofs otherwise; the numeric key rides in the child's tail_key)
@@ -785,36 +839,37 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
         nf.kind = FR_MSG; nf.st = 0; nf.size = 0; nf.head = nf.tail = GGR_NIL; nf.node = idx;
         nf.ref = vmsg; nf.emit = emit; nf.tag = f.tag; nf.oneofs = 0; nf.tail_emit = 0;
         nf.ent_node = nf.key_node = GGR_NIL; nf.key_body = f.tag_len; nf.tail_key = map_key_val;
+        nf.kh_first = vd.key_hash_first; nf.kh_mask = vd.key_hash_mask; nf.field_first = vd.field_first;
         fr = nf;
         continue;
       }
       // ---- scalar ----
       Leaf l;
       int st = parse_scalar(cx, r, f.kind, f.child, &l);
-      if (st != GST_OK) return st;
+      if (st != GST_OK) GGR_RET(st);
       u32 idx;
       st = enc_new_node(cx, &idx);
-      if (st != GST_OK) return st;
+      if (st != GST_OK) GGR_RET(st);
       if (fr.kind == FR_MSG) {
         bool live = (f.flags & GF_PRESENCE) || !l.zero;
         u32 nx;
         st = frame_add(cx, fr, idx, emit, f.tag_len, l.body, live, &nx);
-        if (st != GST_OK) return st;
+        if (st != GST_OK) GGR_RET(st);
         node_store(ir, idx, l.a, l.b, nx, emit, live ? node_meta(l.type, l.flags, f.tag) : node_meta(N_SKIP, 0, 0));
       } else if (fr.kind == FR_LIST) {
         bool packed = (f.flags & GF_PACKED) != 0;
         u32 nx;
         st = frame_add(cx, fr, idx, 0, packed ? 0 : f.tag_len, l.body, true, &nx);
-        if (st != GST_OK) return st;
+        if (st != GST_OK) GGR_RET(st);
         // element tag: the unpacked wire type (f.tag is the LEN tag when packed)
         node_store(ir, idx, l.a, l.b, GGR_NIL, 0, node_meta(l.type, l.flags, packed ? 0 : f.tag));
       } else if (fr.kind == FR_MAP) {
         node_store(ir, idx, l.a, l.b, GGR_NIL, 1, node_meta(l.type, l.flags, f.tag));
         node_set_next(ir, fr.key_node, idx);
         st = map_entry_done(cx, fr, mapf, map_key_kind, map_key_val, map_key_pos, l.body);
-        if (st != GST_OK) return st;
+        if (st != GST_OK) GGR_RET(st);
       } else {
-        return GST_SYNTAX;  // scalar at the root
+        GGR_RET(GST_SYNTAX);  // scalar at the root
       }
       continue;
     }
@@ -835,12 +890,12 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
       if (fr.kind == FR_MSG) {
         u32 nx;
         int st = frame_add(cx, fr, done.node, done.emit, done.key_body, body, true, &nx);
-        if (st != GST_OK) return st;
+        if (st != GST_OK) GGR_RET(st);
         node_store(ir, done.node, payload, done.head, nx, done.emit, node_meta(N_MSG, 0, done.tag));
       } else if (fr.kind == FR_LIST) {
         u32 nx;
         int st = frame_add(cx, fr, done.node, 0, done.key_body, body, true, &nx);
-        if (st != GST_OK) return st;
+        if (st != GST_OK) GGR_RET(st);
         node_store(ir, done.node, payload, done.head, GGR_NIL, 0, node_meta(N_MSG, 0, done.tag));
       } else {  // FR_MAP: message-valued entry
         FieldD mf = ggr_field(T, fr.ref);
@@ -850,7 +905,7 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
         fr.tail_emit = 0;
         fr.oneofs = 0;
         int st = map_entry_done(cx, fr, mf, kkind, done.tail_key, kpos, body);
-        if (st != GST_OK) return st;
+        if (st != GST_OK) GGR_RET(st);
       }
       continue;
     }
@@ -861,18 +916,18 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
       u32 nx;
       if (done.head == GGR_NIL) {  // empty list: field absent
         int st = frame_add(cx, fr, done.node, done.emit, 0, 0, false, &nx);
-        if (st != GST_OK) return st;
+        if (st != GST_OK) GGR_RET(st);
         node_store(ir, done.node, 0, 0, nx, done.emit, node_meta(N_SKIP, 0, 0));
         continue;
       }
       if (packed) {
         u32 body = varint_size(done.size) + done.size;
         int st = frame_add(cx, fr, done.node, done.emit, pf.tag_len, body, true, &nx);
-        if (st != GST_OK) return st;
+        if (st != GST_OK) GGR_RET(st);
         node_store(ir, done.node, done.size, done.head, nx, done.emit, node_meta(N_LIST, NF_PACKED, pf.tag));
       } else {
         int st = frame_add(cx, fr, done.node, done.emit, 0, done.size, true, &nx);
-        if (st != GST_OK) return st;
+        if (st != GST_OK) GGR_RET(st);
         node_store(ir, done.node, done.size, done.head, nx, done.emit, node_meta(N_LIST, 0, 0));
       }
       continue;
@@ -882,13 +937,13 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
       u32 nx;
       bool live = done.head != GGR_NIL;
       int st = frame_add(cx, fr, done.node, done.emit, 0, done.size, live, &nx);
-      if (st != GST_OK) return st;
+      if (st != GST_OK) GGR_RET(st);
       node_store(ir, done.node, done.size, done.head, nx, done.emit, live ? node_meta(N_MAP, 0, 0) : node_meta(N_SKIP, 0, 0));
     }
     continue;
   }
   }
-    }();
+  step_end:
     if (rr != GGR_STEP_CONT) {
       finished = true;
       result = rr;
@@ -933,9 +988,9 @@ GGR_DEV void encode_emit(const u8* in, u32 end, const u8* ir, u32 first, W& w, b
   // one step = one IR node; lanes re-converge at the vote after every step
   while (ggr_any(mask, !finished)) {
    if (!finished) {
-    int rr = [&]() -> int {
+    bool more = false;
   for (int once = 0;; once++) {
-    if (once) return GGR_STEP_CONT;
+    if (once) { more = true; break; }
     if (cur == GGR_NIL) {
       if (sp == 0) break;
       cur = stk[--sp];
@@ -1003,9 +1058,7 @@ GGR_DEV void encode_emit(const u8* in, u32 end, const u8* ir, u32 first, W& w, b
     }
     cur = next;
   }
-      return 0;
-    }();
-    if (rr != GGR_STEP_CONT) finished = true;
+    if (!more) finished = true;
    }
   }
 }

@@ -58,7 +58,7 @@ __device__ __forceinline__ u32 block_excl_scan(u32 v, u32* total) {
   return base + inc - v;
 }
 
-__global__ void __launch_bounds__(GGR_BLOCK)
+__global__ void __launch_bounds__(GGR_BLOCK, 4)
 k_encode_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const i32* __restrict__ msg_id,
                const u8* __restrict__ in, const u64* __restrict__ in_off, u8* __restrict__ ir,
                u32* __restrict__ size, u32* __restrict__ first, i32* __restrict__ status,
@@ -267,7 +267,9 @@ struct ggr_engine {
   uint64_t launches = 0;
   std::mutex mu;
   // scratch (device)
-  DevBuf ir, size, aux, sums, total;
+  // scratch (device); size/aux/sums exist once per direction so that a request batch and a reply
+  // batch can be in flight on two streams at the same time
+  DevBuf ir, size[2], aux[2], sums[2];
   // staging for the host-buffer entry points (device)
   DevBuf d_in, d_off, d_msg, d_out, d_out_off, d_status;
   // per-kernel timing
@@ -297,7 +299,7 @@ static bool cuda_ok(ggr_engine* e, cudaError_t rc, const char* what) {
 static bool ensure(ggr_engine* e, DevBuf& b, size_t bytes) {
   if (bytes <= b.cap) return true;
   if (b.p) {
-    cudaStreamSynchronize(e->stream);
+    cudaDeviceSynchronize();  // growth is rare; callers may have work in flight on other streams
     cudaFree(b.p);
     b.p = nullptr;
     b.cap = 0;
@@ -366,7 +368,7 @@ void ggr_engine_destroy(ggr_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  DevBuf* bufs[] = {&e->ir, &e->size, &e->aux, &e->sums, &e->total, &e->d_in, &e->d_off, &e->d_msg, &e->d_out, &e->d_out_off, &e->d_status};
+  DevBuf* bufs[] = {&e->ir, &e->size[0], &e->size[1], &e->aux[0], &e->aux[1], &e->sums[0], &e->sums[1], &e->d_in, &e->d_off, &e->d_msg, &e->d_out, &e->d_out_off, &e->d_status};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
@@ -473,28 +475,29 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, c
     return cuda_ok(e, cudaMemsetAsync(out_off, 0, sizeof(uint64_t), st), "memset") ? GGR_SUCCESS : GGR_ERR_CUDA;
   }
   long long nb = (n + GGR_BLOCK - 1) / GGR_BLOCK;
-  if (!ensure(e, e->size, (size_t)n * 4) || !ensure(e, e->aux, (size_t)n * 4) || !ensure(e, e->sums, (size_t)nb * 8)) return GGR_ERR_CUDA;
+  const int d = encode ? 0 : 1;
+  if (!ensure(e, e->size[d], (size_t)n * 4) || !ensure(e, e->aux[d], (size_t)n * 4) || !ensure(e, e->sums[d], (size_t)nb * 8)) return GGR_ERR_CUDA;
   if (encode && !ensure(e, e->ir, (size_t)in_bytes * 8 + (size_t)n * 128 + 256)) return GGR_ERR_CUDA;
   u32 n_msgs = (u32)s->cs.msg_names.size();
   const bool prof = e->profiling && e->ev_used + 4 <= 65536;
   size_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
   if (prof) prof_mark(e, st, &m0);
   if (encode) {
-    k_encode_parse<<<(unsigned)nb, GGR_BLOCK, 0, st>>>(s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)e->ir.p, (u32*)e->size.p,
-                                                       (u32*)e->aux.p, status, (u64*)e->sums.p);
+    k_encode_parse<<<(unsigned)nb, GGR_BLOCK, 0, st>>>(s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)e->ir.p, (u32*)e->size[d].p,
+                                                       (u32*)e->aux[d].p, status, (u64*)e->sums[d].p);
     if (prof) prof_mark(e, st, &m1);
-    k_scan_blocks<<<1, 1024, 0, st>>>((u64*)e->sums.p, nb, out_off + n);
+    k_scan_blocks<<<1, 1024, 0, st>>>((u64*)e->sums[d].p, nb, out_off + n);
     if (prof) prof_mark(e, st, &m2);
-    k_encode_emit<<<(unsigned)nb, GGR_BLOCK, 0, st>>>(n, in, in_off, (const u8*)e->ir.p, (const u32*)e->size.p,
-                                                      (const u32*)e->aux.p, status, (const u64*)e->sums.p, out, out_cap, out_off);
+    k_encode_emit<<<(unsigned)nb, GGR_BLOCK, 0, st>>>(n, in, in_off, (const u8*)e->ir.p, (const u32*)e->size[d].p,
+                                                      (const u32*)e->aux[d].p, status, (const u64*)e->sums[d].p, out, out_cap, out_off);
   } else {
-    k_decode_size<<<(unsigned)nb, GGR_BLOCK, 0, st>>>(s->d_blob, n, n_msgs, msg_id, in, in_off, flags, (u32*)e->size.p,
-                                                      (u32*)e->aux.p, status, (u64*)e->sums.p);
+    k_decode_size<<<(unsigned)nb, GGR_BLOCK, 0, st>>>(s->d_blob, n, n_msgs, msg_id, in, in_off, flags, (u32*)e->size[d].p,
+                                                      (u32*)e->aux[d].p, status, (u64*)e->sums[d].p);
     if (prof) prof_mark(e, st, &m1);
-    k_scan_blocks<<<1, 1024, 0, st>>>((u64*)e->sums.p, nb, out_off + n);
+    k_scan_blocks<<<1, 1024, 0, st>>>((u64*)e->sums[d].p, nb, out_off + n);
     if (prof) prof_mark(e, st, &m2);
-    k_decode_write<<<(unsigned)nb, GGR_BLOCK, 0, st>>>(s->d_blob, n, msg_id, in, in_off, flags, (const u32*)e->size.p,
-                                                       (const u32*)e->aux.p, status, (const u64*)e->sums.p, out, out_cap, out_off);
+    k_decode_write<<<(unsigned)nb, GGR_BLOCK, 0, st>>>(s->d_blob, n, msg_id, in, in_off, flags, (const u32*)e->size[d].p,
+                                                       (const u32*)e->aux[d].p, status, (const u64*)e->sums[d].p, out, out_cap, out_off);
   }
   if (prof) {
     prof_mark(e, st, &m3);

@@ -382,7 +382,105 @@ GGR_DEV bool parse_key_int(StrIter& it, bool is_signed, int bits, u64* out) {
   return true;
 }
 
-GGR_DEV u32 fnv_step(u32 h, u32 byte) { return (h ^ byte) * 16777619u; }
+// ------------------------------------------------------------------------------------------
+// Key hashing.  Keys are hashed a little-endian 32-bit word at a time (the last word zero padded)
+// so that the common key - plain ASCII, no escapes - is hashed straight from the reader's 4-byte
+// window while it is being validated; the table entry carries the first 16 bytes of the name
+// inline, so a hit needs no second pass over the key and no pool access.
+// (ggr_schema.cc computes the same function on the host: ggr::key_hash.)
+// ------------------------------------------------------------------------------------------
+struct KeyInfo {
+  u32 len;     // decoded length
+  u32 hash;
+  u32 w[4];    // first 16 decoded bytes, zero padded
+};
+GGR_DEV u32 khash_mix(u32 h, u32 word) {
+  h = (h ^ word) * 0x9E3779B1u;
+  return h ^ (h >> 15);
+}
+GGR_DEV u32 khash_finish(u32 h, u32 len) {
+  h ^= len;
+  h *= 0x85EBCA6Bu;
+  return h ^ (h >> 13);
+}
+#define GGR_KHASH_SEED 0x811C9DC5u
+
+// Scans a key token (reader at the opening quote; left after the closing quote), validating it
+// exactly like scan_string and filling KeyInfo on the way.  Returns GST_OK / GST_SYNTAX /
+// GST_INVALID_UTF8.
+GGR_DEV int scan_key(Rd& r, KeyInfo* k) {
+  r.skip(1);
+  u32 n = 0, h = GGR_KHASH_SEED;
+  u32 w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+  u32 part = 0;  // bytes of the word under construction (n & 3 of them)
+  for (;;) {
+    // whole plain words
+    while ((n & 3u) == 0 && r.left() >= 4) {
+      u32 x = r.peek4();
+      if (json_special_mask(x)) break;
+      h = khash_mix(h, x);
+      u32 i = n >> 2;
+      if (i == 0) w0 = x;
+      else if (i == 1) w1 = x;
+      else if (i == 2) w2 = x;
+      else if (i == 3) w3 = x;
+      r.skip(4);
+      n += 4;
+    }
+    if (r.eof()) return GST_SYNTAX;
+    u32 c = r.peek();
+    u32 bytes, nb;
+    if (c == '"') {
+      r.skip(1);
+      break;
+    }
+    if (c == '\\') {
+      nb = (u32)read_escape(r, &bytes);
+      if (nb == 0) return GST_SYNTAX;
+    } else if (c < 0x20) {
+      return GST_SYNTAX;
+    } else if (c < 0x80) {
+      bytes = c;
+      nb = 1;
+      r.skip(1);
+    } else {
+      int q = utf8_seq_len(r);
+      if (q == 0) return GST_INVALID_UTF8;
+      bytes = r.peek4() & (0xFFFFFFFFu >> (8 * (4 - q)));
+      nb = (u32)q;
+      r.skip(q);
+    }
+    // feed nb decoded bytes
+    for (u32 j = 0; j < nb; j++) {
+      part |= ((bytes >> (8 * j)) & 0xFFu) << (8 * (n & 3u));
+      n++;
+      if ((n & 3u) == 0) {
+        h = khash_mix(h, part);
+        u32 i = (n >> 2) - 1;
+        if (i == 0) w0 = part;
+        else if (i == 1) w1 = part;
+        else if (i == 2) w2 = part;
+        else if (i == 3) w3 = part;
+        part = 0;
+      }
+    }
+  }
+  if (n & 3u) {
+    h = khash_mix(h, part);
+    u32 i = n >> 2;
+    if (i == 0) w0 = part;
+    else if (i == 1) w1 = part;
+    else if (i == 2) w2 = part;
+    else if (i == 3) w3 = part;
+  }
+  k->len = n;
+  k->hash = khash_finish(h, n);
+  k->w[0] = w0;
+  k->w[1] = w1;
+  k->w[2] = w2;
+  k->w[3] = w3;
+  return GST_OK;
+}
 
 // Compares the decoded bytes of the string token at `quote_pos` with pool[off, off+len).
 GGR_DEV bool str_equals_pool(const u8* base, u32 quote_pos, u32 end, const u8* pool, u32 off, u32 len) {
@@ -409,37 +507,28 @@ GGR_DEV bool str_token_is(const u8* base, u32 quote_pos, u32 end, const char* li
   return it.eof();
 }
 
-// Looks a decoded string up in an open-addressing GgrHashEnt table.  Returns value or -1.
-GGR_DEV bool hash_lookup(const Tables& t, u32 first, u32 mask, u32 h, u32 len, const u8* base, u32 quote_pos, u32 end,
+// Looks a scanned key up in an open-addressing GgrHashEnt table (32-byte entries: hash, pool
+// offset, length, value, first 16 name bytes).  Names longer than 16 bytes compare their tail
+// against the pool.
+GGR_DEV bool hash_lookup(const Tables& t, u32 first, u32 mask, const KeyInfo& k, const u8* base, u32 quote_pos, u32 end,
                          i32* value) {
-  u32 slot = h & mask;
+  u32 slot = k.hash & mask;
   for (u32 probes = 0; probes <= mask; probes++) {
-    U4 e = ggr_ld16(t.hash + (size_t)(first + slot) * 16);
+    const u8* ep = t.hash + (size_t)(first + slot) * 32;
+    U4 e = ggr_ld16(ep);
     if (e.z == 0xFFFFFFFFu) return false;
-    if (e.x == h && e.z == len) {
-      // pool is 16-byte aligned within the blob only by section; Rd needs an aligned base:
-      if (str_equals_pool(base, quote_pos, end, t.pool, e.y, len)) {
-        *value = (i32)e.w;
-        return true;
+    if (e.x == k.hash && e.z == k.len) {
+      U4 nm = ggr_ld16(ep + 16);
+      if (nm.x == k.w[0] && nm.y == k.w[1] && nm.z == k.w[2] && nm.w == k.w[3]) {
+        if (k.len <= 16 || str_equals_pool(base, quote_pos, end, t.pool, e.y, k.len)) {
+          *value = (i32)e.w;
+          return true;
+        }
       }
     }
     slot = (slot + 1) & mask;
   }
   return false;
-}
-
-// Hash (FNV-1a over decoded bytes) and decoded length of a validated string token.
-GGR_DEV void hash_string(const u8* base, u32 quote_pos, u32 end, u32* h, u32* len) {
-  StrIter it;
-  it.init(base, quote_pos, end);
-  u32 hh = 2166136261u, n = 0;
-  while (!it.eof()) {
-    hh = fnv_step(hh, it.peek());
-    it.adv();
-    n++;
-  }
-  *h = hh;
-  *len = n;
 }
 
 // true/false/null literal with delimiter check; returns 1 on match (consumed), 0 otherwise

@@ -6,13 +6,18 @@
 
 namespace ggr {
 
-uint32_t fnv1a(const uint8_t* p, size_t n) {
-  uint32_t h = 2166136261u;
-  for (size_t i = 0; i < n; i++) {
-    h ^= p[i];
-    h *= 16777619u;
+// must match khash_mix / khash_finish in ggr_json_in.cuh
+uint32_t key_hash(const uint8_t* p, size_t n) {
+  uint32_t h = 0x811C9DC5u;
+  for (size_t i = 0; i < n; i += 4) {
+    uint32_t w = 0;
+    for (size_t j = 0; j < 4 && i + j < n; j++) w |= (uint32_t)p[i + j] << (8 * j);
+    h = (h ^ w) * 0x9E3779B1u;
+    h ^= h >> 15;
   }
-  return h;
+  h ^= (uint32_t)n;
+  h *= 0x85EBCA6Bu;
+  return h ^ (h >> 13);
 }
 
 namespace {
@@ -266,10 +271,10 @@ struct Blob {
     uint32_t size = 4;
     while (size < items.size() * 2 + 1) size <<= 1;
     uint32_t first = (uint32_t)hash.size();
-    GgrHashEnt empty = {0, 0, 0xFFFFFFFFu, -1};
+    GgrHashEnt empty = {0, 0, 0xFFFFFFFFu, -1, {0, 0, 0, 0}};
     hash.resize(first + size, empty);
     for (auto& it : items) {
-      uint32_t h = fnv1a((const uint8_t*)it.first.data(), it.first.size());
+      uint32_t h = key_hash((const uint8_t*)it.first.data(), it.first.size());
       uint32_t slot = h & (size - 1);
       while (hash[first + slot].name_len != 0xFFFFFFFFu) slot = (slot + 1) & (size - 1);
       GgrHashEnt& e = hash[first + slot];
@@ -277,6 +282,7 @@ struct Blob {
       e.name_off = intern(it.first);
       e.name_len = (uint32_t)it.first.size();
       e.value = it.second;
+      for (size_t j = 0; j < 16 && j < it.first.size(); j++) e.w[j / 4] |= (uint32_t)(uint8_t)it.first[j] << (8 * (j % 4));
     }
     *mask = size - 1;
     return first;

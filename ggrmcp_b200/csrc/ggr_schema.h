@@ -40,6 +40,6 @@ struct CompiledSchema {
 // Returns false and fills *err on malformed or unresolvable input.
 bool compile_schema(const uint8_t* fds, size_t n, WireOrder order, CompiledSchema* out, std::string* err);
 
-uint32_t fnv1a(const uint8_t* p, size_t n);
+uint32_t key_hash(const uint8_t* p, size_t n);
 
 }  // namespace ggr

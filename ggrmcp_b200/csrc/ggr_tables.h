@@ -87,11 +87,12 @@ struct GgrEnumValue {  // 16 bytes; per enum sorted by number, one entry per dis
   uint32_t pad;
 };
 
-struct GgrHashEnt {  // 16 bytes; name_len == 0xFFFFFFFF marks an empty slot
-  uint32_t hash;      // FNV-1a 32 of the name bytes
+struct GgrHashEnt {  // 32 bytes; name_len == 0xFFFFFFFF marks an empty slot
+  uint32_t hash;      // ggr::key_hash of the name bytes (word-wise, see ggr_json_in.cuh)
   uint32_t name_off;
   uint32_t name_len;
   int32_t value;      // key tables: emit index of the field; enum tables: the enum number
+  uint32_t w[4];      // first 16 bytes of the name, zero padded (hits need no pool access)
 };
 
 // per-item status (mirrors ggr_status in include/ggrmcp_b200.h)

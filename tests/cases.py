@@ -143,7 +143,7 @@ DECODE_EDGE_HEX = [
 ]
 
 
-def random_encode_cases(n_per_msg=150, seed0=0, floats=False):
+def random_encode_cases(n_per_msg=150, seed0=0, floats=True):
     """(message, json bytes) pairs rendered by python-protobuf in both key spellings."""
     names = [A, P + "CreateDocumentRequest", P + "ProcessNodeRequest", P + "GetUserProfileResponse", "bench.Flat", "bench.Blob"]
     out = []
@@ -177,7 +177,7 @@ def mutate_json(j, rng):
     return bytes(a)
 
 
-def random_decode_cases(n_per_msg=150, seed0=0, floats=False, mutators=True):
+def random_decode_cases(n_per_msg=150, seed0=0, floats=True, mutators=True):
     names = [A, P + "CreateDocumentRequest", P + "StructuredMetadata", P + "Node", P + "GetUserProfileResponse", "bench.Flat",
              P + "ProcessNodeResponse"]
     out = []
