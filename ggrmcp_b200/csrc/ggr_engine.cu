@@ -18,89 +18,15 @@
 #include <vector>
 
 #include "../../include/ggrmcp_b200.h"
-#include "ggr_decode.cuh"
-#include "ggr_encode.cuh"
+#include "ggr_kernels.h"
 #include "ggr_schema.h"
+#include "ggr_tables.h"
 
+typedef uint8_t u8;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int32_t i32;
 #define GGR_BLOCK 128
-
-// ---------------------------------------------------------------------------------------------
-// device helpers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ u32 warp_incl_scan(u32 v) {
-  const unsigned lane = threadIdx.x & 31;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    u32 t = __shfl_up_sync(0xFFFFFFFFu, v, d);
-    if (lane >= (unsigned)d) v += t;
-  }
-  return v;
-}
-// exclusive scan over the block (GGR_BLOCK threads); returns the exclusive prefix and the total
-__device__ __forceinline__ u32 block_excl_scan(u32 v, u32* total) {
-  __shared__ u32 warp_tot[GGR_BLOCK / 32];
-  // The walkers before this point are data-dependent; __syncthreads() is an *aligned* barrier
-  // (undefined when a warp reaches it divergently - compute-sanitizer synccheck caught exactly
-  // that), so re-converge the warp explicitly first.
-  __syncwarp();
-  u32 inc = warp_incl_scan(v);
-  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 31) warp_tot[wid] = inc;
-  __syncthreads();
-  u32 base = 0, tot = 0;
-#pragma unroll
-  for (int i = 0; i < GGR_BLOCK / 32; i++) {
-    u32 t = warp_tot[i];
-    if ((unsigned)i < wid) base += t;
-    tot += t;
-  }
-  *total = tot;
-  return base + inc - v;
-}
-
-__global__ void __launch_bounds__(GGR_BLOCK, 4)
-k_encode_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const i32* __restrict__ msg_id,
-               const u8* __restrict__ in, const u64* __restrict__ in_off, u8* __restrict__ ir,
-               u32* __restrict__ size, u32* __restrict__ first, i32* __restrict__ status,
-               u64* __restrict__ block_sums) {
-  long long i = (long long)blockIdx.x * GGR_BLOCK + threadIdx.x;
-  u32 sz = 0;
-  // every lane enters the parser (lanes without a valid item only take part in the votes)
-  u64 a = 0, b = 0;
-  i32 m = 0;
-  int st = GST_OK;
-  bool active = false;
-  if (i < n) {
-    a = in_off[i];
-    b = in_off[i + 1];
-    m = msg_id[i];
-    if (m < 0 || (u32)m >= n_msgs || b < a) st = GST_UNSUPPORTED;
-    else if (b - a > 0x1FFFF0ull) st = GST_TOO_LARGE;  // IR links are 20 bits: at most 2^20 nodes per item
-    else active = true;
-  }
-  EncResult res;
-  res.size = 0;
-  res.first = GGR_NIL;
-  {
-    Tables T = ggr_tables(blob);
-    u64 node_off = (a >> 1) + 8ull * (u64)i;
-    u32 cap = active ? (u32)(((b >> 1) + 8ull * (u64)(i + 1)) - node_off) : 0u;
-    const u8* base = in + (a & ~15ull);  // per-item rebasing keeps positions in 32 bits
-    u32 s0 = (u32)(a & 15ull);
-    int r = encode_parse(T, (u32)m, base, s0, s0 + (u32)(b - a), ir + node_off * 16, cap, &res, active, GGR_FULL_MASK);
-    if (active) st = r;
-  }
-  if (i < n) {
-    if (st != GST_OK) res.size = 0;
-    sz = res.size;
-    size[i] = sz;
-    first[i] = res.first;
-    status[i] = st;
-  }
-  u32 tot;
-  block_excl_scan(sz, &tot);
-  if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
-}
 
 // Single block: exclusive scan of nb block sums in place; writes the grand total to *total_out.
 __global__ void __launch_bounds__(1024) k_scan_blocks(u64* __restrict__ sums, long long nb, u64* __restrict__ total_out) {
@@ -128,123 +54,6 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(u64* __restrict__ sums, lo
   if (t == 1023) *total_out = part[1023];
 }
 
-__global__ void __launch_bounds__(GGR_BLOCK)
-k_encode_emit(long long n, const u8* __restrict__ in, const u64* __restrict__ in_off, const u8* __restrict__ ir,
-              const u32* __restrict__ size, const u32* __restrict__ first, i32* __restrict__ status,
-              const u64* __restrict__ block_prefix, u8* __restrict__ out, u64 out_cap, u64* __restrict__ out_off) {
-  long long i = (long long)blockIdx.x * GGR_BLOCK + threadIdx.x;
-  u32 sz = i < n ? size[i] : 0;
-  u32 tot;
-  u32 excl = block_excl_scan(sz, &tot);
-  u64 off = block_prefix[blockIdx.x] + excl;
-  bool active = false;
-  u64 a = 0, b = 0;
-  u32 fst = GGR_NIL;
-  if (i < n) {
-    out_off[i] = off;
-    if (sz != 0 && status[i] == GST_OK) {
-      if (off + sz > out_cap) {
-        status[i] = GST_NO_SPACE;
-      } else {
-        active = true;
-        a = in_off[i];
-        b = in_off[i + 1];
-        fst = first[i];
-      }
-    }
-  }
-  u64 node_off = (a >> 1) + 8ull * (u64)i;
-  const u8* base = in + (a & ~15ull);
-  u32 s0 = (u32)(a & 15ull);
-  Wr w;
-  w.init(out + (off & ~7ull), (u32)(off & 7ull));
-  encode_emit(base, s0 + (u32)(b - a), ir + node_off * 16, fst, w, active, GGR_FULL_MASK);
-  if (active) {
-    w.finish();
-    if (w.pos != (u32)(off & 7ull) + sz) status[i] = GST_INTERNAL;
-  }
-}
-
-__global__ void __launch_bounds__(GGR_BLOCK)
-k_decode_size(const u8* __restrict__ blob, long long n, u32 n_msgs, const i32* __restrict__ msg_id,
-              const u8* __restrict__ in, const u64* __restrict__ in_off, u32 flags, u32* __restrict__ size,
-              u32* __restrict__ mode, i32* __restrict__ status, u64* __restrict__ block_sums) {
-  long long i = (long long)blockIdx.x * GGR_BLOCK + threadIdx.x;
-  u32 sz = 0;
-  u64 a = 0, b = 0;
-  i32 m = 0;
-  int st = GST_OK;
-  bool active = false;
-  if (i < n) {
-    a = in_off[i];
-    b = in_off[i + 1];
-    m = msg_id[i];
-    if (m < 0 || (u32)m >= n_msgs || b < a) st = GST_UNSUPPORTED;
-    else if (b - a > 0x7FFFFFF0ull) st = GST_TOO_LARGE;
-    else active = true;
-  }
-  DecResult res;
-  res.size = 0;
-  res.mode = GGR_MODE_FAST;
-  {
-    Tables T = ggr_tables(blob);
-    const u8* base = in + (a & ~15ull);
-    u32 s0 = (u32)(a & 15ull);
-    int r = decode_size(T, (u32)m, base, s0, s0 + (u32)(b - a), flags, &res, active, GGR_FULL_MASK);
-    if (active) st = r;
-  }
-  if (i < n) {
-    if (st != GST_OK) res.size = 0;
-    sz = res.size;
-    size[i] = sz;
-    mode[i] = res.mode;
-    status[i] = st;
-  }
-  u32 tot;
-  block_excl_scan(sz, &tot);
-  if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
-}
-
-__global__ void __launch_bounds__(GGR_BLOCK)
-k_decode_write(const u8* __restrict__ blob, long long n, const i32* __restrict__ msg_id, const u8* __restrict__ in,
-               const u64* __restrict__ in_off, u32 flags, const u32* __restrict__ size, const u32* __restrict__ mode,
-               i32* __restrict__ status, const u64* __restrict__ block_prefix, u8* __restrict__ out, u64 out_cap,
-               u64* __restrict__ out_off) {
-  long long i = (long long)blockIdx.x * GGR_BLOCK + threadIdx.x;
-  u32 sz = i < n ? size[i] : 0;
-  u32 tot;
-  u32 excl = block_excl_scan(sz, &tot);
-  u64 off = block_prefix[blockIdx.x] + excl;
-  bool active = false;
-  u64 a = 0, b = 0;
-  u32 md = GGR_MODE_FAST;
-  i32 m = 0;
-  if (i < n) {
-    out_off[i] = off;
-    if (sz != 0 && status[i] == GST_OK) {
-      if (off + sz > out_cap) {
-        status[i] = GST_NO_SPACE;
-      } else {
-        active = true;
-        a = in_off[i];
-        b = in_off[i + 1];
-        md = mode[i];
-        m = msg_id[i];
-      }
-    }
-  }
-  Tables T = ggr_tables(blob);
-  const u8* base = in + (a & ~15ull);
-  u32 s0 = (u32)(a & 15ull);
-  u32 end_pos = 0;
-  int st = decode_write(T, (u32)m, base, s0, s0 + (u32)(b - a), flags, md, out + (off & ~7ull), (u32)(off & 7ull), &end_pos,
-                        active, GGR_FULL_MASK);
-  if (active) {
-    if (st == GST_OK && end_pos != (u32)(off & 7ull) + sz) st = GST_INTERNAL;
-    if (st != GST_OK) status[i] = st;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -265,6 +74,7 @@ struct ggr_engine {
   cudaStream_t stream = nullptr;
   std::string err;
   uint64_t launches = 0;
+  bool use_coop = true;  // GGR_NO_COOP=1 disables the warp-cooperative reply-side kernels (A/B runs)
   std::mutex mu;
   // scratch (device)
   // scratch (device); size/aux/sums exist once per direction so that a request batch and a reply
@@ -329,20 +139,21 @@ int ggr_engine_create(const ggr_config* cfg, ggr_engine** out) {
   if (cudaSetDevice(dev) != cudaSuccess) return GGR_ERR_NO_DEVICE;
   // the library carries sm_100a code only: make sure the kernels are loadable here
   cudaFuncAttributes fa;
-  if (cudaFuncGetAttributes(&fa, (const void*)k_encode_parse) != cudaSuccess) {
+  if (cudaFuncGetAttributes(&fa, ggr_kernel_encode_parse()) != cudaSuccess) {
     cudaGetLastError();
     return GGR_ERR_NO_DEVICE;
   }
   ggr_engine* e = new ggr_engine();
   e->device = dev;
+  if (const char* nc = getenv("GGR_NO_COOP")) e->use_coop = !(nc[0] == '1');
   e->order = (cfg && cfg->wire_order == GGR_ORDER_GO_LEGACY) ? ggr::ORDER_GO_LEGACY : ggr::ORDER_FIELD_NUMBER;
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete e;
     return GGR_ERR_CUDA;
   }
-  // message-valued map entries recurse (bounded, GGR_DEC_MAX_REC); give the walkers room
+  // message-valued map entries recurse (bounded, ggr_decode_max_rec()); give the walkers room
   {
-    size_t want = 4096 + (size_t)(GGR_DEC_MAX_REC + 1) * 4096, cur = 0;
+    size_t want = 4096 + (size_t)(ggr_decode_max_rec() + 1) * 4096, cur = 0;
     if (const char* ev = getenv("GGR_STACK_BYTES")) want = (size_t)strtoull(ev, nullptr, 10);
     cudaDeviceGetLimit(&cur, cudaLimitStackSize);
     if (cur < want) {
@@ -446,7 +257,7 @@ int ggr_profile_read(ggr_engine* e, double* ms, uint64_t* launches) {
   std::lock_guard<std::mutex> g(e->mu);
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
-  for (int i = 0; i < 6; i++) { ms[i] = 0; launches[i] = 0; }
+  for (int i = 0; i < 8; i++) { ms[i] = 0; launches[i] = 0; }
   for (auto& sp : e->spans) {
     float t = 0;
     if (cudaEventElapsedTime(&t, e->ev_pool[sp.a], e->ev_pool[sp.b]) == cudaSuccess) {
@@ -479,25 +290,51 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, c
   if (!ensure(e, e->size[d], (size_t)n * 4) || !ensure(e, e->aux[d], (size_t)n * 4) || !ensure(e, e->sums[d], (size_t)nb * 8)) return GGR_ERR_CUDA;
   if (encode && !ensure(e, e->ir, (size_t)in_bytes * 8 + (size_t)n * 128 + 256)) return GGR_ERR_CUDA;
   u32 n_msgs = (u32)s->cs.msg_names.size();
-  const bool prof = e->profiling && e->ev_used + 4 <= 65536;
+  const bool prof = e->profiling && e->ev_used + 8 <= 65536;
   size_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
   if (prof) prof_mark(e, st, &m0);
   if (encode) {
-    k_encode_parse<<<(unsigned)nb, GGR_BLOCK, 0, st>>>(s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)e->ir.p, (u32*)e->size[d].p,
-                                                       (u32*)e->aux[d].p, status, (u64*)e->sums[d].p);
+    ggr_launch_encode_parse(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)e->ir.p, (u32*)e->size[d].p,
+                            (u32*)e->aux[d].p, status, (u64*)e->sums[d].p);
     if (prof) prof_mark(e, st, &m1);
     k_scan_blocks<<<1, 1024, 0, st>>>((u64*)e->sums[d].p, nb, out_off + n);
     if (prof) prof_mark(e, st, &m2);
-    k_encode_emit<<<(unsigned)nb, GGR_BLOCK, 0, st>>>(n, in, in_off, (const u8*)e->ir.p, (const u32*)e->size[d].p,
-                                                      (const u32*)e->aux[d].p, status, (const u64*)e->sums[d].p, out, out_cap, out_off);
+    ggr_launch_encode_emit(st, (unsigned)nb, n, in, in_off, (const u8*)e->ir.p, (const u32*)e->size[d].p,
+                           (const u32*)e->aux[d].p, status, (const u64*)e->sums[d].p, out, out_cap, out_off);
   } else {
-    k_decode_size<<<(unsigned)nb, GGR_BLOCK, 0, st>>>(s->d_blob, n, n_msgs, msg_id, in, in_off, flags, (u32*)e->size[d].p,
-                                                      (u32*)e->aux[d].p, status, (u64*)e->sums[d].p);
+    // Reply side: the warp-cooperative kernels take every regular item; the per-thread kernels
+    // then walk only what was left pending (irregular field order, maps, malformed wire, ...).
+    const bool coop = e->use_coop;
+    size_t c0 = 0, c1 = 0;
+    if (coop) {
+      ggr_launch_decode_coop_size(st, n, s->d_blob, n_msgs, msg_id, in, in_off, flags, (u32*)e->size[d].p, (u32*)e->aux[d].p, status);
+      if (prof) {
+        prof_mark(e, st, &c0);
+        e->spans.push_back({6, m0, c0});
+        m0 = c0;
+      }
+    }
+    ggr_launch_decode_size(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, flags, (u32*)e->size[d].p,
+                           (u32*)e->aux[d].p, status, (u64*)e->sums[d].p, coop ? 1 : 0);
     if (prof) prof_mark(e, st, &m1);
     k_scan_blocks<<<1, 1024, 0, st>>>((u64*)e->sums[d].p, nb, out_off + n);
     if (prof) prof_mark(e, st, &m2);
-    k_decode_write<<<(unsigned)nb, GGR_BLOCK, 0, st>>>(s->d_blob, n, msg_id, in, in_off, flags, (const u32*)e->size[d].p,
-                                                       (const u32*)e->aux[d].p, status, (const u64*)e->sums[d].p, out, out_cap, out_off);
+    ggr_launch_decode_write(st, (unsigned)nb, s->d_blob, n, msg_id, in, in_off, flags, (const u32*)e->size[d].p,
+                            (const u32*)e->aux[d].p, status, (const u64*)e->sums[d].p, out, out_cap, out_off);
+    if (coop) {
+      if (prof) prof_mark(e, st, &c1);
+      ggr_launch_decode_coop_write(st, n, s->d_blob, msg_id, in, in_off, flags, (const u32*)e->size[d].p, (const u32*)e->aux[d].p,
+                                   status, out, out_off);
+      if (prof) {
+        prof_mark(e, st, &m3);
+        e->spans.push_back({3, m0, m1});
+        e->spans.push_back({4, m1, m2});
+        e->spans.push_back({5, m2, c1});
+        e->spans.push_back({7, c1, m3});
+      }
+      e->launches += 5;
+      return cuda_ok(e, cudaGetLastError(), "kernel launch") ? GGR_SUCCESS : GGR_ERR_CUDA;
+    }
   }
   if (prof) {
     prof_mark(e, st, &m3);

@@ -1,0 +1,27 @@
+// ggr_kernels.h - host-callable launchers of the sm_100a kernels (one translation unit per
+// direction so they compile in parallel).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+void ggr_launch_encode_parse(cudaStream_t st, unsigned nb, const uint8_t* blob, long long n, uint32_t n_msgs, const int32_t* msg_id,
+                             const uint8_t* in, const uint64_t* in_off, uint8_t* ir, uint32_t* size, uint32_t* first,
+                             int32_t* status, uint64_t* block_sums);
+void ggr_launch_encode_emit(cudaStream_t st, unsigned nb, long long n, const uint8_t* in, const uint64_t* in_off, const uint8_t* ir,
+                            const uint32_t* size, const uint32_t* first, int32_t* status, const uint64_t* block_prefix,
+                            uint8_t* out, uint64_t out_cap, uint64_t* out_off);
+void ggr_launch_decode_size(cudaStream_t st, unsigned nb, const uint8_t* blob, long long n, uint32_t n_msgs, const int32_t* msg_id,
+                            const uint8_t* in, const uint64_t* in_off, uint32_t flags, uint32_t* size, uint32_t* mode,
+                            int32_t* status, uint64_t* block_sums, int after_coop);
+void ggr_launch_decode_write(cudaStream_t st, unsigned nb, const uint8_t* blob, long long n, const int32_t* msg_id,
+                             const uint8_t* in, const uint64_t* in_off, uint32_t flags, const uint32_t* size,
+                             const uint32_t* mode, int32_t* status, const uint64_t* block_prefix, uint8_t* out,
+                             uint64_t out_cap, uint64_t* out_off);
+void ggr_launch_decode_coop_size(cudaStream_t st, long long n, const uint8_t* blob, uint32_t n_msgs, const int32_t* msg_id,
+                                 const uint8_t* in, const uint64_t* in_off, uint32_t flags, uint32_t* size, uint32_t* mode,
+                                 int32_t* status);
+void ggr_launch_decode_coop_write(cudaStream_t st, long long n, const uint8_t* blob, const int32_t* msg_id, const uint8_t* in,
+                                  const uint64_t* in_off, uint32_t flags, const uint32_t* size, const uint32_t* mode,
+                                  int32_t* status, uint8_t* out, const uint64_t* out_off);
+const void* ggr_kernel_encode_parse();  // for cudaFuncGetAttributes (is the sm_100a image loadable?)
+int ggr_decode_max_rec();

@@ -1,0 +1,109 @@
+// ggr_kernels_dec.cu - reply-side kernels (wire bytes -> protojson text).
+#include "ggr_kernels.h"
+#include "ggr_decode.cuh"
+#include "ggr_scan.cuh"
+
+__global__ void __launch_bounds__(GGR_BLOCK)
+k_decode_size(const u8* __restrict__ blob, long long n, u32 n_msgs, const i32* __restrict__ msg_id,
+              const u8* __restrict__ in, const u64* __restrict__ in_off, u32 flags, u32* __restrict__ size,
+              u32* __restrict__ mode, i32* __restrict__ status, u64* __restrict__ block_sums, int after_coop) {
+  long long i = (long long)blockIdx.x * GGR_BLOCK + threadIdx.x;
+  u32 sz = 0;
+  u64 a = 0, b = 0;
+  i32 m = 0;
+  int st = GST_OK;
+  bool active = false;
+  bool done_by_coop = false;
+  if (i < n) {
+    // after the cooperative kernel only the items it left pending are walked here
+    if (after_coop && mode[i] == 2u /* GGR_MODE_COOP */) {
+      done_by_coop = true;
+    } else {
+      a = in_off[i];
+      b = in_off[i + 1];
+      m = msg_id[i];
+      if (m < 0 || (u32)m >= n_msgs || b < a) st = GST_UNSUPPORTED;
+      else if (b - a > 0x7FFFFFF0ull) st = GST_TOO_LARGE;
+      else active = true;
+    }
+  }
+  DecResult res;
+  res.size = 0;
+  res.mode = GGR_MODE_FAST;
+  {
+    Tables T = ggr_tables(blob);
+    const u8* base = in + (a & ~15ull);
+    u32 s0 = (u32)(a & 15ull);
+    int r = decode_size(T, (u32)m, base, s0, s0 + (u32)(b - a), flags, &res, active, GGR_FULL_MASK);
+    if (active) st = r;
+  }
+  if (i < n) {
+    if (done_by_coop) {
+      sz = size[i];
+    } else {
+      if (st != GST_OK) res.size = 0;
+      sz = res.size;
+      size[i] = sz;
+      mode[i] = res.mode;
+      status[i] = st;
+    }
+  }
+  u32 tot;
+  block_excl_scan(sz, &tot);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(GGR_BLOCK)
+k_decode_write(const u8* __restrict__ blob, long long n, const i32* __restrict__ msg_id, const u8* __restrict__ in,
+               const u64* __restrict__ in_off, u32 flags, const u32* __restrict__ size, const u32* __restrict__ mode,
+               i32* __restrict__ status, const u64* __restrict__ block_prefix, u8* __restrict__ out, u64 out_cap,
+               u64* __restrict__ out_off) {
+  long long i = (long long)blockIdx.x * GGR_BLOCK + threadIdx.x;
+  u32 sz = i < n ? size[i] : 0;
+  u32 tot;
+  u32 excl = block_excl_scan(sz, &tot);
+  u64 off = block_prefix[blockIdx.x] + excl;
+  bool active = false;
+  u64 a = 0, b = 0;
+  u32 md = GGR_MODE_FAST;
+  i32 m = 0;
+  if (i < n) {
+    out_off[i] = off;
+    if (sz != 0 && status[i] == GST_OK) {
+      if (off + sz > out_cap) {
+        status[i] = GST_NO_SPACE;
+      } else {
+        md = mode[i];
+        if (md != 2u /* GGR_MODE_COOP: written by k_decode_coop_write */) {
+          active = true;
+          a = in_off[i];
+          b = in_off[i + 1];
+          m = msg_id[i];
+        }
+      }
+    }
+  }
+  Tables T = ggr_tables(blob);
+  const u8* base = in + (a & ~15ull);
+  u32 s0 = (u32)(a & 15ull);
+  u32 end_pos = 0;
+  int st = decode_write(T, (u32)m, base, s0, s0 + (u32)(b - a), flags, md, out + (off & ~7ull), (u32)(off & 7ull), &end_pos,
+                        active, GGR_FULL_MASK);
+  if (active) {
+    if (st == GST_OK && end_pos != (u32)(off & 7ull) + sz) st = GST_INTERNAL;
+    if (st != GST_OK) status[i] = st;
+  }
+}
+
+void ggr_launch_decode_size(cudaStream_t st, unsigned nb, const uint8_t* blob, long long n, uint32_t n_msgs, const int32_t* msg_id,
+                            const uint8_t* in, const uint64_t* in_off, uint32_t flags, uint32_t* size, uint32_t* mode,
+                            int32_t* status, uint64_t* block_sums, int after_coop) {
+  k_decode_size<<<nb, GGR_BLOCK, 0, st>>>(blob, n, n_msgs, msg_id, in, (const u64*)in_off, flags, size, mode, status, (u64*)block_sums, after_coop);
+}
+void ggr_launch_decode_write(cudaStream_t st, unsigned nb, const uint8_t* blob, long long n, const int32_t* msg_id,
+                             const uint8_t* in, const uint64_t* in_off, uint32_t flags, const uint32_t* size,
+                             const uint32_t* mode, int32_t* status, const uint64_t* block_prefix, uint8_t* out,
+                             uint64_t out_cap, uint64_t* out_off) {
+  k_decode_write<<<nb, GGR_BLOCK, 0, st>>>(blob, n, msg_id, in, (const u64*)in_off, flags, size, mode, status, (const u64*)block_prefix, out, (u64)out_cap, (u64*)out_off);
+}
+int ggr_decode_max_rec() { return GGR_DEC_MAX_REC; }

@@ -1,0 +1,97 @@
+// ggr_kernels_enc.cu - request-side kernels (JSON arguments -> wire bytes).
+#include "ggr_kernels.h"
+#include "ggr_encode.cuh"
+#include "ggr_scan.cuh"
+
+__global__ void __launch_bounds__(GGR_BLOCK, 4)
+k_encode_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const i32* __restrict__ msg_id,
+               const u8* __restrict__ in, const u64* __restrict__ in_off, u8* __restrict__ ir,
+               u32* __restrict__ size, u32* __restrict__ first, i32* __restrict__ status,
+               u64* __restrict__ block_sums) {
+  long long i = (long long)blockIdx.x * GGR_BLOCK + threadIdx.x;
+  u32 sz = 0;
+  // every lane enters the parser (lanes without a valid item only take part in the votes)
+  u64 a = 0, b = 0;
+  i32 m = 0;
+  int st = GST_OK;
+  bool active = false;
+  if (i < n) {
+    a = in_off[i];
+    b = in_off[i + 1];
+    m = msg_id[i];
+    if (m < 0 || (u32)m >= n_msgs || b < a) st = GST_UNSUPPORTED;
+    else if (b - a > 0x1FFFF0ull) st = GST_TOO_LARGE;  // IR links are 20 bits: at most 2^20 nodes per item
+    else active = true;
+  }
+  EncResult res;
+  res.size = 0;
+  res.first = GGR_NIL;
+  {
+    Tables T = ggr_tables(blob);
+    u64 node_off = (a >> 1) + 8ull * (u64)i;
+    u32 cap = active ? (u32)(((b >> 1) + 8ull * (u64)(i + 1)) - node_off) : 0u;
+    const u8* base = in + (a & ~15ull);  // per-item rebasing keeps positions in 32 bits
+    u32 s0 = (u32)(a & 15ull);
+    int r = encode_parse(T, (u32)m, base, s0, s0 + (u32)(b - a), ir + node_off * 16, cap, &res, active, GGR_FULL_MASK);
+    if (active) st = r;
+  }
+  if (i < n) {
+    if (st != GST_OK) res.size = 0;
+    sz = res.size;
+    size[i] = sz;
+    first[i] = res.first;
+    status[i] = st;
+  }
+  u32 tot;
+  block_excl_scan(sz, &tot);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(GGR_BLOCK)
+k_encode_emit(long long n, const u8* __restrict__ in, const u64* __restrict__ in_off, const u8* __restrict__ ir,
+              const u32* __restrict__ size, const u32* __restrict__ first, i32* __restrict__ status,
+              const u64* __restrict__ block_prefix, u8* __restrict__ out, u64 out_cap, u64* __restrict__ out_off) {
+  long long i = (long long)blockIdx.x * GGR_BLOCK + threadIdx.x;
+  u32 sz = i < n ? size[i] : 0;
+  u32 tot;
+  u32 excl = block_excl_scan(sz, &tot);
+  u64 off = block_prefix[blockIdx.x] + excl;
+  bool active = false;
+  u64 a = 0, b = 0;
+  u32 fst = GGR_NIL;
+  if (i < n) {
+    out_off[i] = off;
+    if (sz != 0 && status[i] == GST_OK) {
+      if (off + sz > out_cap) {
+        status[i] = GST_NO_SPACE;
+      } else {
+        active = true;
+        a = in_off[i];
+        b = in_off[i + 1];
+        fst = first[i];
+      }
+    }
+  }
+  u64 node_off = (a >> 1) + 8ull * (u64)i;
+  const u8* base = in + (a & ~15ull);
+  u32 s0 = (u32)(a & 15ull);
+  Wr w;
+  w.init(out + (off & ~7ull), (u32)(off & 7ull));
+  encode_emit(base, s0 + (u32)(b - a), ir + node_off * 16, fst, w, active, GGR_FULL_MASK);
+  if (active) {
+    w.finish();
+    if (w.pos != (u32)(off & 7ull) + sz) status[i] = GST_INTERNAL;
+  }
+}
+
+void ggr_launch_encode_parse(cudaStream_t st, unsigned nb, const uint8_t* blob, long long n, uint32_t n_msgs, const int32_t* msg_id,
+                             const uint8_t* in, const uint64_t* in_off, uint8_t* ir, uint32_t* size, uint32_t* first,
+                             int32_t* status, uint64_t* block_sums) {
+  k_encode_parse<<<nb, GGR_BLOCK, 0, st>>>(blob, n, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first, status, (u64*)block_sums);
+}
+void ggr_launch_encode_emit(cudaStream_t st, unsigned nb, long long n, const uint8_t* in, const uint64_t* in_off, const uint8_t* ir,
+                            const uint32_t* size, const uint32_t* first, int32_t* status, const uint64_t* block_prefix,
+                            uint8_t* out, uint64_t out_cap, uint64_t* out_off) {
+  k_encode_emit<<<nb, GGR_BLOCK, 0, st>>>(n, in, (const u64*)in_off, ir, size, first, status, (const u64*)block_prefix, out, (u64)out_cap, (u64*)out_off);
+}
+const void* ggr_kernel_encode_parse() { return (const void*)k_encode_parse; }

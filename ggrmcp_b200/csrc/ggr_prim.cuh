@@ -17,7 +17,7 @@
 
 #if defined(__CUDACC__)
 #define GGR_DEV __device__ __forceinline__
-#define GGR_DEVN __device__ __noinline__
+#define GGR_DEVN static __device__ __noinline__
 #else
 #define GGR_DEV inline
 #define GGR_DEVN inline

@@ -190,15 +190,16 @@ class Engine:
         if rc != 0:
             self._err(rc, "ggr_decode_batch_dev")
 
-    KERNELS = ["encode_parse", "encode_scan", "encode_emit", "decode_size", "decode_scan", "decode_write"]
+    KERNELS = ["encode_parse", "encode_scan", "encode_emit", "decode_size", "decode_scan", "decode_write",
+               "decode_coop_size", "decode_coop_write"]
 
     def profile_enable(self, on=True):
         _load().ggr_profile_enable(self.h, 1 if on else 0)
 
     def profile_read(self):
         """-> {kernel: (total_ms, launches)} since the last read (synchronizes the device)."""
-        ms = (C.c_double * 6)()
-        ln = (C.c_uint64 * 6)()
+        ms = (C.c_double * 8)()
+        ln = (C.c_uint64 * 8)()
         _load().ggr_profile_read(self.h, ms, ln)
         return {k: (ms[i], int(ln[i])) for i, k in enumerate(self.KERNELS)}
 

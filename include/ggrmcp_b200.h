@@ -135,9 +135,10 @@ int ggr_decode_batch_dev(ggr_engine* e, const ggr_schema* s, int64_t n, const in
 int ggr_synchronize(ggr_engine* e);
 
 /* Per-kernel device timing (CUDA events recorded around every kernel the engine launches).
- * slots: 0 encode_parse, 1 encode_scan, 2 encode_emit, 3 decode_size, 4 decode_scan, 5 decode_write.
+ * slots: 0 encode_parse, 1 encode_scan, 2 encode_emit, 3 decode_size, 4 decode_scan, 5 decode_write,
+ *        6 decode_coop_size, 7 decode_coop_write (the warp-cooperative reply-side kernels).
  * ggr_profile_read synchronizes, adds up the elapsed milliseconds and launch counts since the
- * last read into ms[6] / launches[6], and resets the recorder. */
+ * last read into ms[8] / launches[8], and resets the recorder. */
 int ggr_profile_enable(ggr_engine* e, int on);
 int ggr_profile_read(ggr_engine* e, double* ms, uint64_t* launches);
 

@@ -19,6 +19,9 @@ def lib():
         L.hs_msg_index.argtypes = [C.c_void_p, C.c_char_p]
         L.hs_encode.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p,
                                 C.c_uint32, C.POINTER(C.c_uint32)]
+        if hasattr(L, "hs_decode_coop"):
+            L.hs_decode_coop.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                         C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32)]
         if hasattr(L, "hs_decode"):
             L.hs_decode.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                     C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32)]
@@ -52,6 +55,17 @@ class Schema:
         n = C.c_uint32()
         rc = lib().hs_decode(self.h, self.msg(name), data, len(data), in_off, out_off, flags, out, cap, C.byref(n))
         return rc, out.raw[: n.value]
+
+
+def _decode_coop(self, name, data, flags=0, in_off=0, out_off=0):
+    cap = len(data) * 8 + 256
+    out = C.create_string_buffer(cap)
+    n = C.c_uint32()
+    rc = lib().hs_decode_coop(self.h, self.msg(name), data, len(data), in_off, out_off, flags, out, cap, C.byref(n))
+    return rc, out.raw[: n.value]
+
+
+Schema.decode_coop = _decode_coop
 
 
 def load_schema(order=0):

@@ -14,6 +14,7 @@
 #include "../../ggrmcp_b200/csrc/ggr_encode.cuh"
 #ifdef GGR_HAVE_DECODE
 #include "../../ggrmcp_b200/csrc/ggr_decode.cuh"
+#include "../../ggrmcp_b200/csrc/ggr_coop.cuh"
 #endif
 
 struct HsSchema {
@@ -111,6 +112,40 @@ int hs_decode(void* h, int msg, const uint8_t* wire, uint32_t n, uint32_t in_off
     memcpy(out, ob + out_off, res.size);
     *out_n = res.size;
   }
+  return st;
+}
+
+// Cooperative reply-side path with the lanes run in sequence (nlanes = 1).  Returns 200 when
+// the cooperative code leaves the item to the general kernels.
+int hs_decode_coop(void* h, int msg, const uint8_t* wire, uint32_t n, uint32_t in_off, uint32_t out_off, uint32_t flags,
+                   uint8_t* out, uint32_t out_cap, uint32_t* out_n) {
+  HsSchema* s = (HsSchema*)h;
+  std::vector<uint8_t> inbuf_raw(in_off + n + 64 + 16, 0xEE);
+  uint8_t* in = (uint8_t*)(((uintptr_t)inbuf_raw.data() + 15) & ~(uintptr_t)15);
+  memcpy(in + in_off, wire, n);
+  DecCtx cx;
+  cx.T = ggr_tables(s->blob);
+  cx.in = in;
+  cx.flags = flags;
+  static CoopShared S;
+  uint32_t size = 0;
+  int ws = GST_OK;
+  *out_n = 0;
+  if (!coop_decode_item(S, cx, (u32)msg, in_off, in_off + n, 0, 1, nullptr, 0, &size, &ws)) return 200;
+  if (size > out_cap) return GST_NO_SPACE;
+  std::vector<uint8_t> ob_raw(out_off + size + 64, 0xDD);
+  uint8_t* ob = (uint8_t*)(((uintptr_t)ob_raw.data() + 15) & ~(uintptr_t)15);
+  std::vector<uint8_t> before(ob, ob + out_off + size + 32);
+  uint32_t size2 = 0;
+  if (!coop_decode_item(S, cx, (u32)msg, in_off, in_off + n, 0, 1, ob, out_off, &size2, &ws)) return 201;
+  int st = ws;
+  if (st == GST_OK && size2 != size) st = 100;
+  for (uint32_t i = 0; i < out_off && st == GST_OK; i++)
+    if (ob[i] != before[i]) st = 101;
+  for (uint32_t i = out_off + size; i < out_off + size + 32 && st == GST_OK; i++)
+    if (ob[i] != before[i]) st = 102;
+  memcpy(out, ob + out_off, size);
+  *out_n = size;
   return st;
 }
 #endif
