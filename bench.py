@@ -4,7 +4,7 @@
 One step = one pass of the hot path over one synthetic batch: the request side (arguments JSON ->
 protobuf wire) followed by the reply side (protobuf wire -> protojson text) for every item.
 Default workload: BASELINE.json configs[2] (nested+repeated messages from the reference's
-complex.proto descriptors, ~4 KB JSON, 65 536 items per GPU) - the config the target is quoted on.
+complex.proto descriptors, ~4 KB JSON, 151 552 items per GPU) - the config the target is quoted on.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload nested|flat|blob] [--items M]
   python bench.py --impl reference ...      (the CPU path: oracle port on all host cores)
@@ -155,7 +155,8 @@ def main():
     ap.add_argument("--one-stream", action="store_true", help="serialize request and reply side on one stream")
     args = ap.parse_args()
     if args.items == 0:
-        args.items = 4096 if args.workload == "blob" else 65536
+        # thread-per-item kernels: whole waves of 148 SMs x 8 blocks x 128 threads
+        args.items = 4096 if args.workload == "blob" else 148 * 1024
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -331,7 +332,8 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     alg = {"encode_parse": J_in, "encode_emit": W_out, "decode_size": W_in, "decode_write": J_out,
-           "encode_scan": 0, "decode_scan": 0, "decode_coop_size": W_in, "decode_coop_write": W_in + J_out}
+           "encode_scan": 0, "decode_scan": 0, "decode_coop_size": W_in, "decode_coop_write": W_in + J_out,
+           "encode_coop_parse": J_in, "encode_block_sums": 4 * n}
     kern = {}
     for k, (tot_ms, cnt) in prof.items():
         if cnt:

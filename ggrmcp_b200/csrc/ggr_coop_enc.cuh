@@ -1,0 +1,587 @@
+// ggr_coop_enc.cuh - lock-step request side, pass A: one warp per item, JSON arguments -> IR.
+//
+// The per-thread parser (ggr_encode.cuh) spends 32 unrelated state machines per warp; here the 32
+// lanes of a warp work on ONE item and execute the same code on different data:
+//   T1 tokenize : every lane classifies one 16-byte chunk per round with bit masks (quotes,
+//                 backslashes, structural characters, white space), the in-string state is carried
+//                 across lanes by ballots; the result is a structural index in shared memory
+//                 (one entry per { } [ ] : , string and scalar literal) plus the list of quotes
+//   T2 match    : bracket matching by level (prefix counts + match_any), 32 tokens per round
+//   T3 walk     : level by level, one lane per JSON object: resolves member names against the
+//                 descriptor tables, appends one node per value (children kept in wire-emit order,
+//                 which is also how duplicates are caught), nested objects are queued for the
+//                 next level and skipped in O(1) through the bracket index
+//   T4 leaves   : leaf nodes bucketed by kind, then one lane per leaf runs the very same scalar
+//                 parsers as the per-thread path (parse_scalar), so accepted values are identical
+//   T5 sizes    : bottom-up by depth, containers add their finished size to their parent
+// The output is the same IR (ggr_encode.cuh) the per-thread parser writes, so pass B
+// (k_encode_emit) is shared.  Only regular input is handled: any anomaly - syntax or type error,
+// unknown or duplicate field, map field, table overflow - sets `bail` and the item is left,
+// untouched, to the per-thread parser, which owns the error semantics.
+#pragma once
+#include "ggr_encode.cuh"
+#include "ggr_warp.cuh"
+
+#ifndef CE_MAX_TOK
+#define CE_MAX_TOK 1024
+#endif
+#ifndef CE_MAX_Q
+#define CE_MAX_Q 512
+#endif
+#ifndef CE_MAX_NODE
+#define CE_MAX_NODE 224
+#endif
+#define CE_MAX_DEPTH 24
+#define CE_MAX_INPUT 65000u
+#define CE_NIL 0xFFFFu
+
+enum { TK_LBRACE = 1, TK_RBRACE = 2, TK_LBRACK = 3, TK_RBRACK = 4, TK_COLON = 5, TK_COMMA = 6, TK_STR = 7, TK_SCALAR = 8 };
+#define TK_POS(t) ((t) & 0xFFFFu)
+#define TK_KIND(t) (((t) >> 16) & 0xFu)
+#define TK_AUX(t) ((t) >> 20)
+
+// node classes; everything >= CC_NULL is finished in the leaf phase
+enum { CC_MSG = 0, CC_LIST = 1, CC_NULL = 2, CC_STR = 3, CC_BYTES = 4, CC_INT = 5, CC_FLOAT = 6, CC_TS = 7, CC_N = 8 };
+
+struct CNode {       // 20 bytes
+  u16 tok;           // token index of the value
+  u16 parent;
+  u16 next;          // next sibling in emit order (lists: document order)
+  u16 head;          // containers: first child
+  u16 emit;          // emit index within the parent message
+  u16 gfield;        // global field index
+  u16 msg;           // CC_MSG: message type
+  u8 cls, depth;
+  u32 body;          // containers: payload bytes accumulated from the children
+};
+
+struct CoopEnc {
+  u32 tok[CE_MAX_TOK];  // pos(16) | kind(4) | aux(12): aux = matching bracket / index into qpos
+  u16 qpos[CE_MAX_Q];   // positions of all unescaped quotes, in order
+  CNode node[CE_MAX_NODE];
+  u16 order[CE_MAX_NODE];
+  u16 queue[CE_MAX_NODE];
+  u16 last_open[32];
+  u32 cls_cnt[CC_N], cls_cur[CC_N];
+  u32 n_tok, n_q, n_node, q_end, n_leaf, max_depth, bail, cap;
+};
+
+// byte classes for the tokenizer, one byte lane per class so that eight bytes accumulate in one word
+#define CE_LQ 0x00000001u
+#define CE_LB 0x00000100u
+#define CE_LS 0x00010000u
+#define CE_LW 0x01000000u
+GGR_DEV u32 ce_class(u32 b) {
+  if (b == '"') return CE_LQ;
+  if (b == '\\') return CE_LB;
+  if (b == '{' || b == '}' || b == '[' || b == ']' || b == ':' || b == ',') return CE_LS;
+  if (b == ' ' || b == '\t' || b == '\n' || b == '\r') return CE_LW;
+  return 0;
+}
+
+// Escaped positions of a 16-byte chunk from its backslash mask (the branch-free run-parity
+// computation simdjson uses, on 16 bits); cin: the first byte is escaped by the previous chunk.
+GGR_DEV u32 ce_escaped(u32 B, u32 cin, u32* cout) {
+  B &= ~cin;
+  u32 follows = (B << 1) | cin;
+  const u32 EVEN = 0x5555u;
+  u32 odd_starts = B & ~EVEN & ~follows;
+  u32 sum = odd_starts + B;
+  *cout = (sum >> 16) & 1u;
+  return (EVEN ^ (sum << 1)) & follows & 0xFFFFu;
+}
+GGR_DEV u32 ce_prefix_xor16(u32 x) {
+  x ^= x << 1;
+  x ^= x << 2;
+  x ^= x << 4;
+  x ^= x << 8;
+  return x & 0xFFFFu;
+}
+GGR_DEV u32 ce_struct_kind(u32 c) {
+  return c == '{' ? TK_LBRACE : c == '}' ? TK_RBRACE : c == '[' ? TK_LBRACK : c == ']' ? TK_RBRACK : c == ':' ? TK_COLON : TK_COMMA;
+}
+
+// T1.  All lanes.  lut: 256-entry class table (shared memory on the device).
+GGR_DEV void ce_tokenize(CoopEnc& S, const u32* lut, const u8* in, u32 start, u32 end) {
+  const u32 lane = wp_lane();
+  const u32 lt = (1u << lane) - 1u;
+  const u32 nchunks = (end + 15u) >> 4;
+  u32 c_carry = 0, in_carry = 0, n_carry = 0;  // warp-uniform carries between rounds
+  u32 tbase = 0, qbase = 0;
+  for (u32 cb = 0; cb < nchunks; cb += 32) {
+    const u32 ci = cb + lane;
+    const u32 off = ci << 4;
+    u32 Q = 0, B = 0, X = 0, W = 0xFFFFu;
+    U4 v;
+    v.x = v.y = v.z = v.w = 0;
+    if (ci < nchunks) {
+      v = ggr_ld16(in + off);
+      u32 lo = 0, hi = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        lo |= lut[(v.x >> (8 * j)) & 0xFFu] << j;
+        lo |= lut[(v.y >> (8 * j)) & 0xFFu] << (j + 4);
+        hi |= lut[(v.z >> (8 * j)) & 0xFFu] << j;
+        hi |= lut[(v.w >> (8 * j)) & 0xFFu] << (j + 4);
+      }
+      Q = (lo & 0xFFu) | ((hi & 0xFFu) << 8);
+      B = ((lo >> 8) & 0xFFu) | (((hi >> 8) & 0xFFu) << 8);
+      X = ((lo >> 16) & 0xFFu) | (((hi >> 16) & 0xFFu) << 8);
+      W = ((lo >> 24) & 0xFFu) | (((hi >> 24) & 0xFFu) << 8);
+      // bytes outside [start, end) count as white space
+      u32 valid = 0xFFFFu;
+      if (off < start) valid &= 0xFFFFu << (start - off);
+      if (off + 16u > end) valid &= 0xFFFFu >> (off + 16u - end);
+      Q &= valid;
+      B &= valid;
+      X &= valid;
+      W = (W | ~valid) & 0xFFFFu;
+    }
+    // escaped bytes: the carry into a chunk only matters through an all-backslash chunk
+    u32 co0, co1;
+    u32 E0 = ce_escaped(B, 0, &co0);
+    u32 E1 = ce_escaped(B, 1, &co1);
+    u32 Pm = WP_BALLOT(co0 != co1);
+    u32 Gm = WP_BALLOT(co0 != 0);
+    u32 np = ~Pm & lt;
+    u32 cin = np ? ((Gm >> (31u - wp_clz(np))) & 1u) : c_carry;
+    u32 E = cin ? E1 : E0;
+    u32 cout = cin ? co1 : co0;
+    c_carry = WP_SHFL(cout, 31);
+    u32 RQ = Q & ~E;
+    // in-string state at the start of the chunk
+    u32 PB = WP_BALLOT((wp_popc(RQ) & 1u) != 0);
+    u32 in0 = (wp_popc(PB & lt) + in_carry) & 1u;
+    in_carry = (in_carry + wp_popc(PB)) & 1u;
+    u32 IS = ce_prefix_xor16(RQ) ^ (in0 ? 0xFFFFu : 0u);  // opening quote and content; closing quote excluded
+    u32 SO = RQ & IS, SC = RQ & ~IS;
+    u32 ST = X & ~IS;
+    u32 N = ~(W | X | IS | SC) & 0xFFFFu;  // bytes of scalar literals
+    u32 pn = WP_SHFL_UP(N >> 15, 1);
+    if (lane == 0) pn = n_carry;
+    n_carry = WP_SHFL(N >> 15, 31);
+    u32 NS = N & ~((N << 1) | pn);
+    u32 T = ST | SO | NS;
+    u32 tot;
+    u32 ex = WP_EXCL_SCAN(wp_popc(T) | (wp_popc(RQ) << 16), &tot);
+    u32 ti = tbase + (ex & 0xFFFFu), qi = qbase + (ex >> 16);
+    tbase += tot & 0xFFFFu;
+    qbase += tot >> 16;
+    const u32 qi0 = qi;
+    for (u32 m = RQ; m; m &= m - 1u) {
+      if (qi < CE_MAX_Q) S.qpos[qi] = (u16)(off + wp_ffs0(m));
+      qi++;
+    }
+    for (u32 m = T; m; m &= m - 1u) {
+      u32 j = wp_ffs0(m), bit = 1u << j;
+      u32 kind, aux = 0;
+      if (SO & bit) {
+        kind = TK_STR;
+        aux = qi0 + wp_popc(RQ & (bit - 1u));
+      } else if (NS & bit) {
+        kind = TK_SCALAR;
+      } else {
+        u32 w = j < 4 ? v.x : j < 8 ? v.y : j < 12 ? v.z : v.w;
+        kind = ce_struct_kind((w >> (8 * (j & 3u))) & 0xFFu);
+      }
+      if (ti < CE_MAX_TOK) S.tok[ti] = (off + j) | (kind << 16) | (aux << 20);
+      ti++;
+    }
+  }
+  if (lane == 0) {
+    S.n_tok = tbase;
+    S.n_q = qbase;
+    if (tbase > CE_MAX_TOK || qbase > CE_MAX_Q || in_carry || tbase == 0) S.bail = 1;
+  }
+  WP_SYNC();
+}
+
+// T2.  All lanes.  Fills the aux field of every bracket token with the index of its partner.
+GGR_DEV void ce_match(CoopEnc& S) {
+  const u32 lane = wp_lane();
+  const u32 lt = (1u << lane) - 1u, le = lt | (1u << lane);
+  const u32 n = S.n_tok;
+  i32 depth = 0;
+  for (u32 base = 0; base < n; base += 32) {
+    const u32 i = base + lane;
+    const u32 t = i < n ? S.tok[i] : 0u;
+    const u32 k = TK_KIND(t);
+    const bool op = k == TK_LBRACE || k == TK_LBRACK, cl = k == TK_RBRACE || k == TK_RBRACK;
+    const u32 OM = WP_BALLOT(op), CM = WP_BALLOT(cl);
+    // level of an opening bracket: depth after it; of a closing bracket: depth before it
+    const i32 lvl = depth + (i32)wp_popc(OM & le) - (i32)wp_popc(CM & lt);
+    const bool bad = (op || cl) && (lvl < 1 || lvl >= 32);
+    const u32 m = WP_MATCH_ANY((op || cl) ? (u32)lvl : 0x10000u + lane);
+    if (bad) S.bail = 1;
+    if (cl && !bad) {
+      u32 cand = m & OM & lt;
+      u32 mt = cand ? base + 31u - wp_clz(cand) : (u32)S.last_open[lvl];
+      if (mt >= i || TK_KIND(S.tok[mt]) + 1u != k) {
+        S.bail = 1;
+      } else {
+        S.tok[i] = t | (mt << 20);
+        S.tok[mt] |= i << 20;
+      }
+    }
+    WP_SYNC();
+    if (op && !bad && (m & OM & ~le) == 0) S.last_open[lvl] = (u16)i;
+    WP_SYNC();
+    depth += (i32)wp_popc(OM) - (i32)wp_popc(CM);
+    if (depth < 0) depth = 0;  // already flagged by the lane that underflowed
+  }
+  if (depth != 0 && lane == 0) S.bail = 1;
+  WP_SYNC();
+}
+
+GGR_DEV u32 ce_new_node(CoopEnc& S, u32 tok, u32 parent, u32 gfield, u32 emit, u32 cls, u32 depth) {
+  u32 idx = wp_atomic_add(&S.n_node, 1u);
+  if (idx >= S.cap || gfield >= 0xFFFFu || emit >= 0xFFFu) {
+    S.bail = 1;
+    return CE_NIL;
+  }
+  CNode nd;
+  nd.tok = (u16)tok;
+  nd.parent = (u16)parent;
+  nd.next = CE_NIL;
+  nd.head = CE_NIL;
+  nd.emit = (u16)emit;
+  nd.gfield = (u16)gfield;
+  nd.msg = 0;
+  nd.cls = (u8)cls;
+  nd.depth = (u8)depth;
+  nd.body = 0;
+  S.node[idx] = nd;
+  return idx;
+}
+GGR_DEV u32 ce_leaf_class(const FieldD& f, bool timestamp) {
+  if (timestamp) return CC_TS;
+  switch (f.kind) {
+    case GK_STRING: return CC_STR;
+    case GK_BYTES: return CC_BYTES;
+    case GK_FLOAT: case GK_DOUBLE: return CC_FLOAT;
+    default: return CC_INT;
+  }
+}
+// `null`, exactly, followed by a delimiter
+GGR_DEV bool ce_is_null(const EncCtx& cx, u32 pos) {
+  Rd r;
+  r.init(cx.in, pos, cx.end);
+  if (!match_literal(r, LIT4('n', 'u', 'l', 'l'), 4, 0)) return false;
+  if (r.eof()) return true;
+  u32 c = r.peek();
+  return ggr_is_ws(c) || c == ',' || c == '}' || c == ']';
+}
+
+// T3, one lane: members of the JSON object behind message node `ni`.
+GGR_DEV void ce_walk_object(CoopEnc& S, const EncCtx& cx, u32 ni) {
+  const Tables& T = cx.T;
+  const u32 open = S.node[ni].tok;
+  const u32 depth = S.node[ni].depth;
+  const MsgD md = ggr_msg(T, S.node[ni].msg);
+  if (md.wkt != GGR_WKT_NONE || depth + 2u >= CE_MAX_DEPTH) { S.bail = 1; return; }
+  const u32 close = TK_AUX(S.tok[open]);
+  u32 head = CE_NIL, tail = CE_NIL, tail_emit = 0, oneofs = 0;
+  u32 t = open + 1;
+  bool first = true;
+  while (t != close) {
+    if (!first) {
+      if (TK_KIND(S.tok[t]) != TK_COMMA) { S.bail = 1; return; }
+      t++;
+    }
+    first = false;
+    // "key" : value
+    if (t + 2u >= close) { S.bail = 1; return; }
+    const u32 kt = S.tok[t];
+    if (TK_KIND(kt) != TK_STR || TK_KIND(S.tok[t + 1]) != TK_COLON) { S.bail = 1; return; }
+    const u32 key_pos = TK_POS(kt);
+    KeyInfo ki;
+    {
+      Rd r;
+      r.init(cx.in, key_pos, cx.end);
+      if (scan_key(r, &ki) != GST_OK) { S.bail = 1; return; }
+    }
+    i32 ei;
+    if (!hash_lookup(T, md.key_hash_first, md.key_hash_mask, ki, cx.in, key_pos, cx.end, &ei)) { S.bail = 1; return; }
+    const u32 emit = (u32)ei;
+    const u32 gf = md.field_first + emit;
+    const FieldD f = ggr_field(T, gf);
+    t += 2;
+    const u32 vt = S.tok[t];
+    const u32 vk = TK_KIND(vt);
+    u32 child;
+    if (vk == TK_SCALAR && ce_is_null(cx, TK_POS(vt))) {
+      child = ce_new_node(S, t, ni, gf, emit, CC_NULL, depth + 1);
+      t++;
+    } else if (f.flags & GF_MAP) {
+      S.bail = 1;  // maps: per-thread path
+      return;
+    } else if (f.flags & GF_REPEATED) {
+      if (vk != TK_LBRACK) { S.bail = 1; return; }
+      const u32 aend = TK_AUX(vt);
+      child = ce_new_node(S, t, ni, gf, emit, CC_LIST, depth + 1);
+      if (child == CE_NIL) return;
+      bool ts = false, msg = false;
+      if (f.kind == GK_MESSAGE) {
+        u32 w = ggr_msg(T, (u32)f.child).wkt;
+        ts = w == GGR_WKT_TIMESTAMP;
+        msg = w == GGR_WKT_NONE;
+        if (!ts && !msg) { S.bail = 1; return; }
+      }
+      const u32 lcls = ce_leaf_class(f, ts);
+      u32 u = t + 1, ltail = CE_NIL;
+      bool lfirst = true;
+      while (u != aend) {
+        if (!lfirst) {
+          if (TK_KIND(S.tok[u]) != TK_COMMA) { S.bail = 1; return; }
+          u++;
+          if (u == aend) { S.bail = 1; return; }
+        }
+        lfirst = false;
+        const u32 et = S.tok[u];
+        const u32 ek = TK_KIND(et);
+        u32 el;
+        if (msg) {
+          if (ek != TK_LBRACE) { S.bail = 1; return; }
+          el = ce_new_node(S, u, child, gf, 0, CC_MSG, depth + 2);
+          if (el == CE_NIL) return;
+          S.node[el].msg = (u16)f.child;
+          S.queue[wp_atomic_add(&S.q_end, 1u)] = (u16)el;
+          u = TK_AUX(et) + 1u;
+        } else {
+          if (ek != TK_STR && ek != TK_SCALAR) { S.bail = 1; return; }
+          if (ek == TK_SCALAR && ce_is_null(cx, TK_POS(et))) { S.bail = 1; return; }
+          el = ce_new_node(S, u, child, gf, 0, lcls, depth + 2);
+          if (el == CE_NIL) return;
+          u++;
+        }
+        if (ltail == CE_NIL) S.node[child].head = (u16)el;
+        else S.node[ltail].next = (u16)el;
+        ltail = el;
+      }
+      wp_atomic_max(&S.max_depth, depth + 2);
+      t = aend + 1;
+    } else {
+      if (f.oneof >= 0) {
+        u32 bit = 1u << (f.oneof & 31);
+        if (oneofs & bit) { S.bail = 1; return; }
+        oneofs |= bit;
+      }
+      if (f.kind == GK_MESSAGE) {
+        u32 w = ggr_msg(T, (u32)f.child).wkt;
+        if (w == GGR_WKT_TIMESTAMP) {
+          if (vk != TK_STR) { S.bail = 1; return; }
+          child = ce_new_node(S, t, ni, gf, emit, CC_TS, depth + 1);
+          t++;
+        } else if (w == GGR_WKT_NONE) {
+          if (vk != TK_LBRACE || (u32)f.child >= 0xFFFFu) { S.bail = 1; return; }
+          child = ce_new_node(S, t, ni, gf, emit, CC_MSG, depth + 1);
+          if (child == CE_NIL) return;
+          S.node[child].msg = (u16)f.child;
+          S.queue[wp_atomic_add(&S.q_end, 1u)] = (u16)child;
+          t = TK_AUX(vt) + 1u;
+        } else {
+          S.bail = 1;
+          return;
+        }
+      } else {
+        if (vk != TK_STR && vk != TK_SCALAR) { S.bail = 1; return; }
+        child = ce_new_node(S, t, ni, gf, emit, ce_leaf_class(f, false), depth + 1);
+        t++;
+      }
+    }
+    if (child == CE_NIL) return;
+    if (t > close) { S.bail = 1; return; }
+    // children in emit order; equal emit = the same field twice
+    if (head == CE_NIL) {
+      head = tail = child;
+      tail_emit = emit;
+    } else if (emit > tail_emit) {
+      S.node[tail].next = (u16)child;
+      tail = child;
+      tail_emit = emit;
+    } else if (emit == tail_emit) {
+      S.bail = 1;
+      return;
+    } else {
+      u32 prev = CE_NIL, cur = head;
+      for (;;) {
+        u32 e = S.node[cur].emit;
+        if (e == emit) { S.bail = 1; return; }
+        if (e > emit) break;
+        prev = cur;
+        cur = S.node[cur].next;
+      }
+      S.node[child].next = (u16)cur;
+      if (prev == CE_NIL) head = child;
+      else S.node[prev].next = (u16)child;
+    }
+  }
+  S.node[ni].head = (u16)head;
+  wp_atomic_max(&S.max_depth, depth + 1);
+}
+
+GGR_DEV u32 ce_link(u32 x) { return x == CE_NIL ? GGR_NIL : x; }
+
+// T4, one lane: finish leaf node `ni` (IR node + size into its parent).
+GGR_DEV void ce_leaf(CoopEnc& S, EncCtx& cx, u32 ni) {
+  const CNode nd = S.node[ni];
+  const u32 next = ce_link(nd.next);
+  if (nd.cls == CC_NULL) {
+    node_store(cx.ir, ni, 0, 0, next, nd.emit, node_meta(N_SKIP, 0, 0));
+    return;
+  }
+  const FieldD f = ggr_field(cx.T, nd.gfield);
+  const u32 tk = S.tok[nd.tok];
+  const bool in_list = S.node[nd.parent].cls == CC_LIST;
+  const bool packed = in_list && (f.flags & GF_PACKED);
+  const u32 tag = packed ? 0u : f.tag, tag_len = packed ? 0u : f.tag_len;
+  Rd r;
+  r.init(cx.in, TK_POS(tk), cx.end);
+  if (nd.cls == CC_TS) {
+    const u32 q = r.pos;
+    StrInfo si;
+    if (scan_string<false>(r, &si) != GST_OK) { S.bail = 1; return; }
+    StrIter it;
+    it.init(cx.in, q, cx.end);
+    i64 secs;
+    i32 nanos;
+    if (parse_timestamp(it, &secs, &nanos) != GST_OK) { S.bail = 1; return; }
+    u32 sidx = GGR_NIL, nidx = GGR_NIL, payload = 0;
+    if (nanos != 0) {
+      nidx = wp_atomic_add(&S.n_node, 1u);
+      if (nidx >= S.cap) { S.bail = 1; return; }
+      node_store(cx.ir, nidx, (u32)nanos, 0, GGR_NIL, 1, node_meta(N_VARINT, 0, 16));
+      payload += 1 + varint_size((u64)(u32)nanos);
+    }
+    if (secs != 0) {
+      sidx = wp_atomic_add(&S.n_node, 1u);
+      if (sidx >= S.cap) { S.bail = 1; return; }
+      node_store(cx.ir, sidx, (u32)(u64)secs, (u32)((u64)secs >> 32), nidx, 0, node_meta(N_VARINT, 0, 8));
+      payload += 1 + varint_size((u64)secs);
+    }
+    node_store(cx.ir, ni, payload, sidx != GGR_NIL ? sidx : nidx, next, nd.emit, node_meta(N_MSG, 0, f.tag));
+    wp_atomic_add(&S.node[nd.parent].body, f.tag_len + varint_size(payload) + payload);
+    return;
+  }
+  Leaf l;
+  if (parse_scalar(cx, r, f.kind, f.child, &l) != GST_OK) { S.bail = 1; return; }
+  if (TK_KIND(tk) == TK_SCALAR && !r.eof()) {  // the literal must end where the parser stopped
+    u32 c = r.peek();
+    if (!(ggr_is_ws(c) || c == ',' || c == '}' || c == ']')) { S.bail = 1; return; }
+  }
+  const bool live = in_list || (f.flags & GF_PRESENCE) || !l.zero;
+  node_store(cx.ir, ni, l.a, l.b, next, nd.emit, live ? node_meta(l.type, l.flags, tag) : node_meta(N_SKIP, 0, 0));
+  if (live) wp_atomic_add(&S.node[nd.parent].body, tag_len + l.body);
+}
+
+// T5, one lane: container `ni` is complete; write its IR node and add its size to the parent.
+GGR_DEV void ce_close_container(CoopEnc& S, EncCtx& cx, u32 ni) {
+  const CNode nd = S.node[ni];
+  const FieldD f = ggr_field(cx.T, nd.gfield);
+  const u32 next = ce_link(nd.next), head = ce_link(nd.head);
+  u32 full;
+  if (nd.cls == CC_MSG) {
+    node_store(cx.ir, ni, nd.body, head, next, nd.emit, node_meta(N_MSG, 0, f.tag));
+    full = f.tag_len + varint_size(nd.body) + nd.body;
+  } else if (nd.head == CE_NIL) {
+    node_store(cx.ir, ni, 0, 0, next, nd.emit, node_meta(N_SKIP, 0, 0));
+    full = 0;
+  } else if (f.flags & GF_PACKED) {
+    node_store(cx.ir, ni, nd.body, head, next, nd.emit, node_meta(N_LIST, NF_PACKED, f.tag));
+    full = f.tag_len + varint_size(nd.body) + nd.body;
+  } else {
+    node_store(cx.ir, ni, nd.body, head, next, nd.emit, node_meta(N_LIST, 0, 0));
+    full = nd.body;
+  }
+  wp_atomic_add(&S.node[nd.parent].body, full);
+}
+
+// One item, all 32 lanes.  Returns true when the item was handled (IR written, *res filled);
+// false leaves it to the per-thread parser.
+GGR_DEV bool ce_parse_item(CoopEnc& S, const u32* lut, const Tables& T, u32 root_msg, const u8* in, u32 start, u32 end, u8* ir,
+                           u32 ir_cap, EncResult* res) {
+  const u32 lane = wp_lane();
+  res->size = 0;
+  res->first = GGR_NIL;
+  if (end > CE_MAX_INPUT || ir_cap == 0) return false;
+  if (end == start) return true;  // reflection.go:354: "" skips protojson
+  if (lane == 0) {
+    S.bail = 0;
+    S.n_node = 0;
+    S.q_end = 0;
+    S.max_depth = 0;
+    S.cap = ir_cap < CE_MAX_NODE ? ir_cap : CE_MAX_NODE;
+  }
+  WP_SYNC();
+  ce_tokenize(S, lut, in, start, end);
+  if (S.bail) return false;
+  ce_match(S);
+  if (S.bail) return false;
+  const u32 n_tok = S.n_tok;
+  // exactly one top-level value, an object
+  if (TK_KIND(S.tok[0]) != TK_LBRACE || TK_AUX(S.tok[0]) != n_tok - 1u) return false;
+  EncCtx cx;
+  cx.T = T;
+  cx.in = in;
+  cx.end = end;
+  cx.ir = ir;
+  cx.ir_cap = ir_cap;
+  cx.n_nodes = 0;
+  if (lane == 0) {
+    u32 r0 = ce_new_node(S, 0, CE_NIL, 0, 0, CC_MSG, 0);
+    S.node[r0].msg = (u16)root_msg;
+    S.queue[0] = (u16)r0;
+    S.q_end = 1;
+  }
+  WP_SYNC();
+  if (root_msg >= 0xFFFFu) return false;
+  // T3: level by level
+  u32 qb = 0;
+  for (;;) {
+    const u32 qe = S.q_end;
+    if (qb == qe) break;
+    WP_SYNC();  // everyone has read q_end before the walkers append to the queue
+    for (u32 i = qb + lane; i < qe; i += 32) ce_walk_object(S, cx, S.queue[i]);
+    WP_SYNC();
+    if (S.bail) return false;
+    qb = qe;
+  }
+  const u32 n = S.n_node;
+  // T4: bucket the leaves by class, then one lane per leaf
+  if (lane < CC_N) S.cls_cnt[lane] = 0;
+  WP_SYNC();
+  for (u32 i = lane; i < n; i += 32) {
+    u32 c = S.node[i].cls;
+    if (c >= CC_NULL) wp_atomic_add(&S.cls_cnt[c], 1u);
+  }
+  WP_SYNC();
+  if (lane == 0) {
+    u32 run = 0;
+    for (u32 c = 0; c < CC_N; c++) {
+      S.cls_cur[c] = run;
+      run += S.cls_cnt[c];
+    }
+    S.n_leaf = run;
+  }
+  WP_SYNC();
+  for (u32 i = lane; i < n; i += 32) {
+    u32 c = S.node[i].cls;
+    if (c >= CC_NULL) S.order[wp_atomic_add(&S.cls_cur[c], 1u)] = (u16)i;
+  }
+  WP_SYNC();
+  const u32 n_leaf = S.n_leaf;
+  for (u32 k = lane; k < n_leaf; k += 32) ce_leaf(S, cx, S.order[k]);
+  WP_SYNC();
+  if (S.bail) return false;
+  // T5: containers, deepest first (the root, depth 0, has no node of its own in the IR)
+  for (u32 d = S.max_depth; d >= 1; d--) {
+    for (u32 i = lane; i < n; i += 32) {
+      CNode nd = S.node[i];
+      if (nd.depth == d && nd.cls <= CC_LIST) ce_close_container(S, cx, i);
+    }
+    WP_SYNC();
+  }
+  res->size = S.node[0].body;
+  res->first = ce_link(S.node[0].head);
+  return true;
+}

@@ -74,12 +74,13 @@ struct ggr_engine {
   cudaStream_t stream = nullptr;
   std::string err;
   uint64_t launches = 0;
-  bool use_coop = true;  // GGR_NO_COOP=1 disables the warp-cooperative reply-side kernels (A/B runs)
+  bool use_coop = false;  // GGR_COOP=1 enables the warp-cooperative reply-side kernels (slower than the per-thread ones so far)
   std::mutex mu;
   // scratch (device)
   // scratch (device); size/aux/sums exist once per direction so that a request batch and a reply
   // batch can be in flight on two streams at the same time
-  DevBuf ir, size[2], aux[2], sums[2];
+  DevBuf ir, size[2], aux[2], sums[2], pend;
+  bool use_coop_enc = true;  // GGR_COOP_ENC=0 disables the lock-step request-side parser (A/B runs)
   // staging for the host-buffer entry points (device)
   DevBuf d_in, d_off, d_msg, d_out, d_out_off, d_status;
   // per-kernel timing
@@ -145,7 +146,8 @@ int ggr_engine_create(const ggr_config* cfg, ggr_engine** out) {
   }
   ggr_engine* e = new ggr_engine();
   e->device = dev;
-  if (const char* nc = getenv("GGR_NO_COOP")) e->use_coop = !(nc[0] == '1');
+  if (const char* nc = getenv("GGR_COOP")) e->use_coop = nc[0] == '1';
+  if (const char* nc = getenv("GGR_COOP_ENC")) e->use_coop_enc = nc[0] != '0';
   e->order = (cfg && cfg->wire_order == GGR_ORDER_GO_LEGACY) ? ggr::ORDER_GO_LEGACY : ggr::ORDER_FIELD_NUMBER;
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete e;
@@ -179,7 +181,7 @@ void ggr_engine_destroy(ggr_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  DevBuf* bufs[] = {&e->ir, &e->size[0], &e->size[1], &e->aux[0], &e->aux[1], &e->sums[0], &e->sums[1], &e->d_in, &e->d_off, &e->d_msg, &e->d_out, &e->d_out_off, &e->d_status};
+  DevBuf* bufs[] = {&e->ir, &e->size[0], &e->size[1], &e->aux[0], &e->aux[1], &e->sums[0], &e->sums[1], &e->pend, &e->d_in, &e->d_off, &e->d_msg, &e->d_out, &e->d_out_off, &e->d_status};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
@@ -257,7 +259,7 @@ int ggr_profile_read(ggr_engine* e, double* ms, uint64_t* launches) {
   std::lock_guard<std::mutex> g(e->mu);
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
-  for (int i = 0; i < 8; i++) { ms[i] = 0; launches[i] = 0; }
+  for (int i = 0; i < GGR_PROFILE_SLOTS; i++) { ms[i] = 0; launches[i] = 0; }
   for (auto& sp : e->spans) {
     float t = 0;
     if (cudaEventElapsedTime(&t, e->ev_pool[sp.a], e->ev_pool[sp.b]) == cudaSuccess) {
@@ -294,9 +296,33 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, c
   size_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
   if (prof) prof_mark(e, st, &m0);
   if (encode) {
-    ggr_launch_encode_parse(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)e->ir.p, (u32*)e->size[d].p,
-                            (u32*)e->aux[d].p, status, (u64*)e->sums[d].p);
-    if (prof) prof_mark(e, st, &m1);
+    if (e->use_coop_enc) {
+      // lock-step parser first (one warp per item); what it leaves goes to the per-thread parser
+      if (!ensure(e, e->pend, (size_t)n * 4 + 16)) return GGR_ERR_CUDA;
+      u32* n_pending = (u32*)e->pend.p;
+      u32* pending = n_pending + 4;
+      size_t c0 = 0, c1 = 0;
+      if (!cuda_ok(e, cudaMemsetAsync(n_pending, 0, 16, st), "memset")) return GGR_ERR_CUDA;
+      if (prof) prof_mark(e, st, &m0);
+      ggr_launch_encode_coop_parse(st, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)e->ir.p, (u32*)e->size[d].p,
+                                   (u32*)e->aux[d].p, status, pending, n_pending);
+      if (prof) prof_mark(e, st, &c0);
+      ggr_launch_encode_parse(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)e->ir.p, (u32*)e->size[d].p,
+                              (u32*)e->aux[d].p, status, (u64*)e->sums[d].p, pending, n_pending);
+      if (prof) prof_mark(e, st, &c1);
+      ggr_launch_block_sums(st, (unsigned)nb, n, (const u32*)e->size[d].p, (u64*)e->sums[d].p);
+      if (prof) {
+        e->spans.push_back({8, m0, c0});
+        e->spans.push_back({0, c0, c1});
+        prof_mark(e, st, &m1);
+        e->spans.push_back({9, c1, m1});
+      }
+      e->launches += 2;
+    } else {
+      ggr_launch_encode_parse(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)e->ir.p, (u32*)e->size[d].p,
+                              (u32*)e->aux[d].p, status, (u64*)e->sums[d].p, nullptr, nullptr);
+      if (prof) prof_mark(e, st, &m1);
+    }
     k_scan_blocks<<<1, 1024, 0, st>>>((u64*)e->sums[d].p, nb, out_off + n);
     if (prof) prof_mark(e, st, &m2);
     ggr_launch_encode_emit(st, (unsigned)nb, n, in, in_off, (const u8*)e->ir.p, (const u32*)e->size[d].p,
@@ -339,7 +365,7 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, c
   if (prof) {
     prof_mark(e, st, &m3);
     int base = encode ? 0 : 3;
-    e->spans.push_back({base + 0, m0, m1});
+    if (!(encode && e->use_coop_enc)) e->spans.push_back({base + 0, m0, m1});
     e->spans.push_back({base + 1, m1, m2});
     e->spans.push_back({base + 2, m2, m3});
   }

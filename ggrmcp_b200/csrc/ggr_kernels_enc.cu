@@ -3,12 +3,21 @@
 #include "ggr_encode.cuh"
 #include "ggr_scan.cuh"
 
-__global__ void __launch_bounds__(GGR_BLOCK, 4)
+#ifndef GGR_PARSE_MINB
+#define GGR_PARSE_MINB 4
+#endif
+__global__ void __launch_bounds__(GGR_BLOCK, GGR_PARSE_MINB)
 k_encode_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const i32* __restrict__ msg_id,
                const u8* __restrict__ in, const u64* __restrict__ in_off, u8* __restrict__ ir,
                u32* __restrict__ size, u32* __restrict__ first, i32* __restrict__ status,
-               u64* __restrict__ block_sums) {
+               u64* __restrict__ block_sums, const u32* __restrict__ list, const u32* __restrict__ list_n) {
+  // list mode (after the lock-step parser): thread t takes item list[t]; block sums come later
   long long i = (long long)blockIdx.x * GGR_BLOCK + threadIdx.x;
+  if (list) {
+    const u32 cnt = *list_n;
+    if ((u32)blockIdx.x * GGR_BLOCK >= cnt) return;
+    i = (u32)i < cnt ? (long long)list[i] : n;
+  }
   u32 sz = 0;
   // every lane enters the parser (lanes without a valid item only take part in the votes)
   u64 a = 0, b = 0;
@@ -42,8 +51,17 @@ k_encode_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const i32* 
     first[i] = res.first;
     status[i] = st;
   }
+  if (list) return;
   u32 tot;
   block_excl_scan(sz, &tot);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+// block_sums[b] = sum of size[i] over block b's items (list mode of k_encode_parse skips them)
+__global__ void __launch_bounds__(GGR_BLOCK) k_block_sums(long long n, const u32* __restrict__ size, u64* __restrict__ block_sums) {
+  long long i = (long long)blockIdx.x * GGR_BLOCK + threadIdx.x;
+  u32 tot;
+  block_excl_scan(i < n ? size[i] : 0u, &tot);
   if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
 }
 
@@ -86,8 +104,12 @@ k_encode_emit(long long n, const u8* __restrict__ in, const u64* __restrict__ in
 
 void ggr_launch_encode_parse(cudaStream_t st, unsigned nb, const uint8_t* blob, long long n, uint32_t n_msgs, const int32_t* msg_id,
                              const uint8_t* in, const uint64_t* in_off, uint8_t* ir, uint32_t* size, uint32_t* first,
-                             int32_t* status, uint64_t* block_sums) {
-  k_encode_parse<<<nb, GGR_BLOCK, 0, st>>>(blob, n, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first, status, (u64*)block_sums);
+                             int32_t* status, uint64_t* block_sums, const uint32_t* list, const uint32_t* list_n) {
+  k_encode_parse<<<nb, GGR_BLOCK, 0, st>>>(blob, n, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first, status, (u64*)block_sums,
+                                           list, list_n);
+}
+void ggr_launch_block_sums(cudaStream_t st, unsigned nb, long long n, const uint32_t* size, uint64_t* block_sums) {
+  k_block_sums<<<nb, GGR_BLOCK, 0, st>>>(n, size, (u64*)block_sums);
 }
 void ggr_launch_encode_emit(cudaStream_t st, unsigned nb, long long n, const uint8_t* in, const uint64_t* in_off, const uint8_t* ir,
                             const uint32_t* size, const uint32_t* first, int32_t* status, const uint64_t* block_prefix,

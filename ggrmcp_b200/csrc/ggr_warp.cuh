@@ -1,0 +1,210 @@
+// ggr_warp.cuh - warp collectives for the lock-step (one warp per item) kernels.
+//
+// Device build: thin wrappers over the sm_100a warp intrinsics, full mask, all 32 lanes call
+// together.  Host build (tests/hostsim only): the same source runs as 32 cooperative fibers, one
+// per lane; every collective is a rendezvous through an exchange array, and every rendezvous
+// carries the source line it was called from so that lanes that reach different collectives
+// (a divergence bug that would be undefined behaviour on the device) are reported instead of
+// silently paired.
+#pragma once
+#include "ggr_prim.cuh"
+
+#if defined(__CUDA_ARCH__)
+
+GGR_DEV u32 wp_lane() { return threadIdx.x & 31u; }
+GGR_DEV void wp_sync_(int) { __syncwarp(); }
+GGR_DEV u32 wp_ballot_(bool p, int) { return __ballot_sync(0xFFFFFFFFu, p); }
+GGR_DEV u32 wp_shfl_(u32 v, u32 src, int) { return __shfl_sync(0xFFFFFFFFu, v, (int)(src & 31u)); }
+GGR_DEV u32 wp_shfl_up_(u32 v, u32 d, int) { return __shfl_up_sync(0xFFFFFFFFu, v, d); }
+GGR_DEV u32 wp_match_any_(u32 v, int) { return __match_any_sync(0xFFFFFFFFu, v); }
+GGR_DEV u32 wp_atomic_add(u32* p, u32 v) { return atomicAdd(p, v); }
+GGR_DEV u32 wp_atomic_or(u32* p, u32 v) { return atomicOr(p, v); }
+GGR_DEV u32 wp_atomic_max(u32* p, u32 v) { return atomicMax(p, v); }
+
+#else  // ---------------------------------------------------------------- host fibers
+
+#include <ucontext.h>
+
+#include <cstdio>
+#include <cstdlib>
+
+struct HostWarp {
+  ucontext_t main_ctx;
+  ucontext_t fib[32];
+  char* stacks = nullptr;
+  u32 cur = 0;
+  bool done[32];
+  u32 alive = 0;
+  u32 exch[32];
+  u32 arrived = 0, gen = 0;
+  int tag = 0;
+  int error = 0;  // 1: lanes met at different collectives
+  void (*body)(void*, u32) = nullptr;
+  void* arg = nullptr;
+};
+inline HostWarp*& hw_current() {
+  static thread_local HostWarp* h = nullptr;
+  return h;
+}
+inline void hw_rendezvous(int tag) {
+  HostWarp* h = hw_current();
+  if (h->arrived == 0) h->tag = tag;
+  else if (h->tag != tag) {
+    if (!h->error) fprintf(stderr, "[host warp] divergence: lane %u at line %d, others at line %d\n", h->cur, tag, h->tag);
+    h->error = 1;
+  }
+  u32 my = h->gen;
+  if (++h->arrived >= h->alive) {
+    h->arrived = 0;
+    h->gen++;
+    return;
+  }
+  while (h->gen == my) swapcontext(&h->fib[h->cur], &h->main_ctx);
+}
+inline void hw_trampoline() {
+  HostWarp* h = hw_current();
+  u32 lane = h->cur;
+  h->body(h->arg, lane);
+  h->done[lane] = true;
+  h->alive--;
+  // a lane that leaves while others wait may complete their rendezvous
+  if (h->alive && h->arrived >= h->alive) {
+    h->arrived = 0;
+    h->gen++;
+  }
+  swapcontext(&h->fib[lane], &h->main_ctx);
+}
+// Runs body(arg, lane) on 32 lock-step lanes.  Returns 0, or 1 when a divergence was detected.
+inline int hw_run_warp(void (*body)(void*, u32), void* arg) {
+  static thread_local HostWarp* H = nullptr;
+  const size_t STK = 256 * 1024;
+  if (!H) {
+    H = new HostWarp();
+    H->stacks = (char*)malloc(32 * STK);
+  }
+  HostWarp* h = H;
+  hw_current() = h;
+  h->body = body;
+  h->arg = arg;
+  h->alive = 32;
+  h->arrived = 0;
+  h->error = 0;
+  for (u32 l = 0; l < 32; l++) {
+    h->done[l] = false;
+    getcontext(&h->fib[l]);
+    h->fib[l].uc_stack.ss_sp = h->stacks + l * STK;
+    h->fib[l].uc_stack.ss_size = STK;
+    h->fib[l].uc_link = &h->main_ctx;
+    makecontext(&h->fib[l], (void (*)())hw_trampoline, 0);
+  }
+  u32 guard = 0;
+  while (h->alive) {
+    for (u32 l = 0; l < 32; l++) {
+      if (h->done[l]) continue;
+      h->cur = l;
+      swapcontext(&h->main_ctx, &h->fib[l]);
+    }
+    if (++guard > (1u << 28)) {
+      fprintf(stderr, "[host warp] did not finish\n");
+      h->error = 2;
+      break;
+    }
+  }
+  return h->error;
+}
+
+inline u32 wp_lane() { return hw_current()->cur; }
+inline void wp_sync_(int tag) { hw_rendezvous(tag); }
+inline u32 wp_ballot_(bool p, int tag) {
+  HostWarp* h = hw_current();
+  h->exch[h->cur] = p ? 1u : 0u;
+  hw_rendezvous(tag);
+  u32 m = 0;
+  for (u32 i = 0; i < 32; i++)
+    if (!h->done[i] && h->exch[i]) m |= 1u << i;
+  hw_rendezvous(tag);
+  return m;
+}
+inline u32 wp_shfl_(u32 v, u32 src, int tag) {
+  HostWarp* h = hw_current();
+  h->exch[h->cur] = v;
+  hw_rendezvous(tag);
+  u32 r = h->exch[src & 31u];
+  hw_rendezvous(tag);
+  return r;
+}
+inline u32 wp_shfl_up_(u32 v, u32 d, int tag) {
+  HostWarp* h = hw_current();
+  h->exch[h->cur] = v;
+  hw_rendezvous(tag);
+  u32 r = h->cur >= d ? h->exch[h->cur - d] : v;
+  hw_rendezvous(tag);
+  return r;
+}
+inline u32 wp_match_any_(u32 v, int tag) {
+  HostWarp* h = hw_current();
+  h->exch[h->cur] = v;
+  hw_rendezvous(tag);
+  u32 m = 0;
+  for (u32 i = 0; i < 32; i++)
+    if (!h->done[i] && h->exch[i] == v) m |= 1u << i;
+  hw_rendezvous(tag);
+  return m;
+}
+inline u32 wp_atomic_add(u32* p, u32 v) {
+  u32 o = *p;
+  *p = o + v;
+  return o;
+}
+inline u32 wp_atomic_or(u32* p, u32 v) {
+  u32 o = *p;
+  *p = o | v;
+  return o;
+}
+inline u32 wp_atomic_max(u32* p, u32 v) {
+  u32 o = *p;
+  if (v > o) *p = v;
+  return o;
+}
+#endif
+
+#define WP_SYNC() wp_sync_(__LINE__)
+#define WP_BALLOT(p) wp_ballot_((p), __LINE__)
+#define WP_SHFL(v, src) wp_shfl_((v), (src), __LINE__)
+#define WP_SHFL_UP(v, d) wp_shfl_up_((v), (d), __LINE__)
+#define WP_MATCH_ANY(v) wp_match_any_((v), __LINE__)
+#define WP_ANY(p) (WP_BALLOT(p) != 0u)
+
+GGR_DEV u32 wp_popc(u32 x) {
+#if defined(__CUDA_ARCH__)
+  return (u32)__popc(x);
+#else
+  return (u32)__builtin_popcount(x);
+#endif
+}
+GGR_DEV u32 wp_clz(u32 x) {
+#if defined(__CUDA_ARCH__)
+  return (u32)__clz((int)x);
+#else
+  return x ? (u32)__builtin_clz(x) : 32u;
+#endif
+}
+GGR_DEV u32 wp_ffs0(u32 x) {  // index of the lowest set bit (x != 0)
+#if defined(__CUDA_ARCH__)
+  return (u32)__ffs((int)x) - 1u;
+#else
+  return (u32)__builtin_ctz(x);
+#endif
+}
+// exclusive prefix sum over the lanes; *total = sum over all lanes
+GGR_DEV u32 wp_excl_scan_(u32 v, u32* total, int tag) {
+  u32 lane = wp_lane();
+  u32 x = v;
+  for (u32 d = 1; d < 32; d <<= 1) {
+    u32 y = wp_shfl_up_(x, d, tag);
+    if (lane >= d) x += y;
+  }
+  *total = wp_shfl_(x, 31, tag);
+  return x - v;
+}
+#define WP_EXCL_SCAN(v, total) wp_excl_scan_((v), (total), __LINE__)

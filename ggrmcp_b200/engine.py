@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(HERE, "libggrmcp_b200.so")
+_LIB_PATH = os.environ.get("GGR_LIB_PATH") or os.path.join(HERE, "libggrmcp_b200.so")  # override: A/B builds only
 
 F_COMMA_SPACE = 1
 ORDER_FIELD_NUMBER = 0
@@ -191,15 +191,15 @@ class Engine:
             self._err(rc, "ggr_decode_batch_dev")
 
     KERNELS = ["encode_parse", "encode_scan", "encode_emit", "decode_size", "decode_scan", "decode_write",
-               "decode_coop_size", "decode_coop_write"]
+               "decode_coop_size", "decode_coop_write", "encode_coop_parse", "encode_block_sums"]
 
     def profile_enable(self, on=True):
         _load().ggr_profile_enable(self.h, 1 if on else 0)
 
     def profile_read(self):
         """-> {kernel: (total_ms, launches)} since the last read (synchronizes the device)."""
-        ms = (C.c_double * 8)()
-        ln = (C.c_uint64 * 8)()
+        ms = (C.c_double * len(self.KERNELS))()
+        ln = (C.c_uint64 * len(self.KERNELS))()
         _load().ggr_profile_read(self.h, ms, ln)
         return {k: (ms[i], int(ln[i])) for i, k in enumerate(self.KERNELS)}
 

@@ -31,10 +31,29 @@ def hsim(fds_bytes):
     return hostsim.Schema(fds_bytes)
 
 
-@pytest.fixture(scope="session")
-def engine():
+# every GPU test runs against each kernel path: the default (lock-step request parser in front of
+# the per-thread kernels), the per-thread kernels alone, and the warp-cooperative reply kernels
+_ENGINE_PATHS = {
+    "default": {},
+    "per_thread": {"GGR_COOP_ENC": "0", "GGR_COOP": "0"},
+    "coop_reply": {"GGR_COOP": "1"},
+}
+
+
+@pytest.fixture(scope="session", params=list(_ENGINE_PATHS))
+def engine(request):
     import ggrmcp_b200
-    e = ggrmcp_b200.Engine(0)
+    env = _ENGINE_PATHS[request.param]
+    saved = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        e = ggrmcp_b200.Engine(0)  # the engine reads its switches at creation
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     yield e
     e.close()
 

@@ -12,6 +12,7 @@
 
 #include "../../ggrmcp_b200/csrc/ggr_schema.h"
 #include "../../ggrmcp_b200/csrc/ggr_encode.cuh"
+#include "../../ggrmcp_b200/csrc/ggr_coop_enc.cuh"
 #ifdef GGR_HAVE_DECODE
 #include "../../ggrmcp_b200/csrc/ggr_decode.cuh"
 #include "../../ggrmcp_b200/csrc/ggr_coop.cuh"
@@ -82,6 +83,86 @@ int hs_encode(void* h, int msg, const uint8_t* json, uint32_t n, uint32_t in_off
     memcpy(out, ob + out_off, res.size);
     *out_n = res.size;
   }
+  free(ir);
+  return st;
+}
+
+// Lock-step request-side pass A (one warp per item) on 32 fibers, then the shared pass B.
+// Returns 200 when the lock-step parser leaves the item to the per-thread parser, 300 + n when
+// the fiber warp detected a divergence bug.
+struct CoopEncArgs {
+  CoopEnc* S;
+  const u32* lut;
+  Tables T;
+  u32 msg;
+  const u8* in;
+  u32 start, end;
+  u8* ir;
+  u32 ir_cap;
+  EncResult res[32];
+  bool ok[32];
+};
+static void coop_enc_body(void* p, u32 lane) {
+  CoopEncArgs* a = (CoopEncArgs*)p;
+  a->ok[lane] = ce_parse_item(*a->S, a->lut, a->T, a->msg, a->in, a->start, a->end, a->ir, a->ir_cap, &a->res[lane]);
+}
+int hs_encode_coop(void* h, int msg, const uint8_t* json, uint32_t n, uint32_t in_off, uint32_t out_off, uint8_t* out,
+                   uint32_t out_cap, uint32_t* out_n) {
+  HsSchema* s = (HsSchema*)h;
+  static u32 lut[256];
+  static bool lut_ok = false;
+  if (!lut_ok) {
+    for (u32 b = 0; b < 256; b++) lut[b] = ce_class(b);
+    lut_ok = true;
+  }
+  std::vector<uint8_t> inbuf_raw(in_off + n + 64 + 16, 0xEE);
+  uint8_t* in = (uint8_t*)(((uintptr_t)inbuf_raw.data() + 15) & ~(uintptr_t)15);
+  memcpy(in + in_off, json, n);
+  uint32_t ir_cap = n / 2 + 8;
+  uint8_t* ir = (uint8_t*)aligned_alloc(16, (size_t)ir_cap * 16);
+  memset(ir, 0xCC, (size_t)ir_cap * 16);
+  static CoopEnc S;
+  memset(&S, 0xAB, sizeof S);  // stale shared memory must not matter
+  CoopEncArgs a;
+  a.S = &S;
+  a.lut = lut;
+  a.T = ggr_tables(s->blob);
+  a.msg = (u32)msg;
+  a.in = in;
+  a.start = in_off;
+  a.end = in_off + n;
+  a.ir = ir;
+  a.ir_cap = ir_cap;
+  int werr = hw_run_warp(coop_enc_body, &a);
+  *out_n = 0;
+  if (werr) {
+    free(ir);
+    return 300 + werr;
+  }
+  for (int l = 1; l < 32; l++)
+    if (a.ok[l] != a.ok[0] || (a.ok[0] && (a.res[l].size != a.res[0].size || a.res[l].first != a.res[0].first))) {
+      free(ir);
+      return 310;  // lanes disagree about the result
+    }
+  if (!a.ok[0]) {
+    free(ir);
+    return 200;
+  }
+  EncResult res = a.res[0];
+  int st = GST_OK;
+  if (res.size > out_cap) {
+    free(ir);
+    return GST_NO_SPACE;
+  }
+  std::vector<uint8_t> ob_raw(out_off + res.size + 64, 0xDD);
+  uint8_t* ob = (uint8_t*)(((uintptr_t)ob_raw.data() + 15) & ~(uintptr_t)15);
+  Wr w;
+  w.init(ob, out_off);
+  encode_emit(in, in_off + n, ir, res.first, w);
+  w.finish();
+  if (w.pos != out_off + res.size) st = 100;
+  memcpy(out, ob + out_off, res.size);
+  *out_n = res.size;
   free(ir);
   return st;
 }

@@ -95,3 +95,54 @@ def test_decode_random(oracle, hsim):
             gaps += 1
     # documented gap: a singular sub-message split over several wire occurrences (merge)
     assert gaps < total * 0.06
+
+
+# ---- lock-step request-side parser (ggr_coop_enc.cuh) on 32 fibers ---------------------------
+def _check_coop_encode(hsim, name, js, i=0):
+    """the lock-step parser either leaves the item alone (200) or produces exactly the bytes of the
+    per-thread path; 3xx = the fiber warp caught lanes at different collectives"""
+    rc, out = hsim.encode_coop(name, js, i % 16, (i * 5) % 16)
+    assert rc in (0, 200), (name, js, rc)
+    if rc == 200:
+        return False
+    est, ew = hsim.encode(name, js, i % 16, (i * 5) % 16)
+    assert est == 0 and out == ew, (name, js, est, ew.hex(), out.hex())
+    return True
+
+
+def test_coop_encode_vectors_and_edges(hsim):
+    handled = 0
+    for name, js, wire in cases.K_REQUESTS:
+        rc, out = hsim.encode_coop(name, js, 3, 5)
+        assert rc in (0, 200) and (rc == 200 or out.hex() == wire)
+        handled += rc == 0
+    for i, (name, js, want) in enumerate(cases.ENCODE_EDGE):
+        handled += _check_coop_encode(hsim, name, js, i)
+    assert handled > 60
+
+
+def test_coop_encode_random_and_damaged(hsim):
+    rng = random.Random(23)
+    handled = 0
+    for i, (name, js) in enumerate(cases.random_encode_cases(150, seed0=4000)):
+        handled += _check_coop_encode(hsim, name, js, i)
+        handled += _check_coop_encode(hsim, name, cases.mutate_json(js, rng), i + 1)
+    assert handled > 500
+
+
+def test_coop_encode_bench_shapes(hsim):
+    import benchgen
+    names = {}
+
+    def mi(name):
+        names[hsim.msg(name)] = name
+        return hsim.msg(name)
+
+    for kind, n, want in (("nested", 200, 150), ("flat", 100, 100)):
+        wl = getattr(benchgen, kind)(n, mi)
+        blob = wl.req_json.tobytes()
+        handled = 0
+        for i in range(n):
+            js = blob[int(wl.req_off[i]):int(wl.req_off[i + 1])]
+            handled += _check_coop_encode(hsim, names[int(wl.req_msg[i])], js, i)
+        assert handled >= want, (kind, handled)
