@@ -16,21 +16,13 @@
 //   T5 sizes    : bottom-up by depth, containers add their finished size to their parent
 // The output is the same IR (ggr_encode.cuh) the per-thread parser writes, so pass B
 // (k_encode_emit) is shared.  Only regular input is handled: any anomaly - syntax or type error,
-// unknown or duplicate field, map field, table overflow - sets `bail` and the item is left,
-// untouched, to the per-thread parser, which owns the error semantics.
+// unknown or duplicate field, non-string map key, table overflow - sets `bail` and the item is left,
+// untouched, to the next tier (the same code with larger tables, then the per-thread parser, which
+// owns the error semantics).
 #pragma once
 #include "ggr_encode.cuh"
 #include "ggr_warp.cuh"
 
-#ifndef CE_MAX_TOK
-#define CE_MAX_TOK 1024
-#endif
-#ifndef CE_MAX_Q
-#define CE_MAX_Q 512
-#endif
-#ifndef CE_MAX_NODE
-#define CE_MAX_NODE 224
-#endif
 #define CE_MAX_DEPTH 24
 #define CE_MAX_INPUT 65000u
 #define CE_NIL 0xFFFFu
@@ -40,8 +32,8 @@ enum { TK_LBRACE = 1, TK_RBRACE = 2, TK_LBRACK = 3, TK_RBRACK = 4, TK_COLON = 5,
 #define TK_KIND(t) (((t) >> 16) & 0xFu)
 #define TK_AUX(t) ((t) >> 20)
 
-// node classes; everything >= CC_NULL is finished in the leaf phase
-enum { CC_MSG = 0, CC_LIST = 1, CC_NULL = 2, CC_STR = 3, CC_BYTES = 4, CC_INT = 5, CC_FLOAT = 6, CC_TS = 7, CC_N = 8 };
+// node classes: containers first; everything >= CC_NULL is finished in the leaf phase
+enum { CC_MSG = 0, CC_LIST = 1, CC_MAP = 2, CC_ENTRY = 3, CC_NULL = 4, CC_STR = 5, CC_BYTES = 6, CC_INT = 7, CC_FLOAT = 8, CC_TS = 9, CC_N = 10 };
 
 struct CNode {       // 20 bytes
   u16 tok;           // token index of the value
@@ -55,15 +47,28 @@ struct CNode {       // 20 bytes
   u32 body;          // containers: payload bytes accumulated from the children
 };
 
-struct CoopEnc {
-  u32 tok[CE_MAX_TOK];  // pos(16) | kind(4) | aux(12): aux = matching bracket / index into qpos
-  u16 qpos[CE_MAX_Q];   // positions of all unescaped quotes, in order
-  CNode node[CE_MAX_NODE];
-  u16 order[CE_MAX_NODE];
-  u16 queue[CE_MAX_NODE];
+// Per-warp working set (shared memory).  MT tokens / MQ quotes / MN nodes; aux is 12 bits, so
+// MT, MQ <= 4096.
+template <int MT, int MQ, int MN>
+struct CoopEncT {
+  static const u32 MAX_TOK = MT, MAX_Q = MQ, MAX_NODE = MN;
+  u32 tok[MT];     // pos(16) | kind(4) | aux(12): aux = matching bracket / index into qpos
+  u16 qpos[MQ];    // positions of all unescaped quotes, in order
+  u16 qesc[MQ];    // number of simple escape sequences (\" \\ \/ \b \f \n \r \t) before each quote, mod 2^16
+  u16 qslow[MQ];   // number of bytes that need the full scanner (< 0x20, \u, bad escape) before each quote
+  CNode node[MN];
+  u16 order[MN];
+  u16 queue[MN];
   u16 last_open[32];
   u32 cls_cnt[CC_N], cls_cur[CC_N];
   u32 n_tok, n_q, n_node, q_end, n_leaf, max_depth, bail, cap;
+};
+typedef CoopEncT<1024, 512, 224> CoopEnc;        // tier 1: ~12 KB per warp
+typedef CoopEncT<4096, 2048, 1024> CoopEncBig;   // tier 2: ~48 KB per warp
+
+struct CeLut {
+  u32 cls[256];  // CE_L* class bits
+  u8 kind[256];  // TK_* of the structural characters; bit 7: valid character after a backslash (simple escapes)
 };
 
 // byte classes for the tokenizer, one byte lane per class so that eight bytes accumulate in one word
@@ -98,20 +103,40 @@ GGR_DEV u32 ce_prefix_xor16(u32 x) {
   return x & 0xFFFFu;
 }
 GGR_DEV u32 ce_struct_kind(u32 c) {
-  return c == '{' ? TK_LBRACE : c == '}' ? TK_RBRACE : c == '[' ? TK_LBRACK : c == ']' ? TK_RBRACK : c == ':' ? TK_COLON : TK_COMMA;
+  return c == '{' ? TK_LBRACE : c == '}' ? TK_RBRACE : c == '[' ? TK_LBRACK : c == ']' ? TK_RBRACK : c == ':' ? TK_COLON : c == ',' ? TK_COMMA : 0;
+}
+GGR_DEV void ce_lut_init(CeLut& L, u32 first, u32 step) {
+  for (u32 b = first; b < 256; b += step) {
+    L.cls[b] = ce_class(b);
+    bool simple = b == '"' || b == '\\' || b == '/' || b == 'b' || b == 'f' || b == 'n' || b == 'r' || b == 't';
+    L.kind[b] = (u8)(ce_struct_kind(b) | (simple ? 0x80u : 0u));
+  }
+}
+// flags in bit 7 of every byte -> 4 contiguous bits
+GGR_DEV u32 ce_pack4(u32 x) { return (((x >> 7) * 0x00204081u) >> 21) & 0xFu; }
+// per byte of w (bit 7 flags): control character (< 0x20)
+GGR_DEV u32 ce_ctrl_flags(u32 w) {
+  u32 ge20 = ((w & 0x7F7F7F7Fu) + 0x60606060u) | w;  // bit 7 set: byte >= 0x20
+  return ~ge20 & 0x80808080u;
+}
+GGR_DEV u32 ce_byte16(const U4& v, u32 j) {  // byte j of a 16-byte chunk
+  u32 w = j < 4 ? v.x : j < 8 ? v.y : j < 12 ? v.z : v.w;
+  return (w >> (8 * (j & 3u))) & 0xFFu;
 }
 
 // T1.  All lanes.  lut: 256-entry class table (shared memory on the device).
-GGR_DEV void ce_tokenize(CoopEnc& S, const u32* lut, const u8* in, u32 start, u32 end) {
+template <class SH>
+GGR_DEV void ce_tokenize(SH& S, const CeLut& L, const u8* in, u32 start, u32 end) {
+  const u32* lut = L.cls;
   const u32 lane = wp_lane();
   const u32 lt = (1u << lane) - 1u;
   const u32 nchunks = (end + 15u) >> 4;
-  u32 c_carry = 0, in_carry = 0, n_carry = 0;  // warp-uniform carries between rounds
-  u32 tbase = 0, qbase = 0;
+  u32 c_carry = 0, in_carry = 0, n_carry = 0, u_carry = 0;  // warp-uniform carries between rounds
+  u32 tbase = 0, qbase = 0, dbase = 0, ebase = 0;
   for (u32 cb = 0; cb < nchunks; cb += 32) {
     const u32 ci = cb + lane;
     const u32 off = ci << 4;
-    u32 Q = 0, B = 0, X = 0, W = 0xFFFFu;
+    u32 Q = 0, B = 0, X = 0, W = 0xFFFFu, D = 0, HI = 0;
     U4 v;
     v.x = v.y = v.z = v.w = 0;
     if (ci < nchunks) {
@@ -136,6 +161,33 @@ GGR_DEV void ce_tokenize(CoopEnc& S, const u32* lut, const u8* in, u32 start, u3
       B &= valid;
       X &= valid;
       W = (W | ~valid) & 0xFFFFu;
+      D = (ce_pack4(ce_ctrl_flags(v.x)) | (ce_pack4(ce_ctrl_flags(v.y)) << 4) | (ce_pack4(ce_ctrl_flags(v.z)) << 8) |
+           (ce_pack4(ce_ctrl_flags(v.w)) << 12)) & valid;
+      HI = (ce_pack4(v.x & 0x80808080u) | (ce_pack4(v.y & 0x80808080u) << 4) | (ce_pack4(v.z & 0x80808080u) << 8) |
+            (ce_pack4(v.w & 0x80808080u) << 12)) & valid;
+    }
+    // UTF-8 over the whole text (structure and quotes are ASCII, so a malformed sequence anywhere
+    // makes the item an error: left to the per-thread parser).  Lead bytes say where continuation
+    // bytes must be; that mask, carried over the chunk boundary, has to equal the actual one.
+    if (WP_ANY(HI != 0) || u_carry) {
+      u32 C6 = 0, EC = 0;
+      if (HI) {
+        C6 = (ce_pack4((v.x << 1) & 0x80808080u) | (ce_pack4((v.y << 1) & 0x80808080u) << 4) |
+              (ce_pack4((v.z << 1) & 0x80808080u) << 8) | (ce_pack4((v.w << 1) & 0x80808080u) << 12));
+        for (u32 m = HI & C6; m; m &= m - 1u) {  // lead bytes (11xxxxxx)
+          const u32 j = wp_ffs0(m);
+          const u32 b0 = ce_byte16(v, j);
+          const u32 b1 = j < 15 ? ce_byte16(v, j + 1) : (ggr_ld4(in + off + 16) & 0xFFu);
+          u32 len = b0 < 0xC2u ? 0u : b0 < 0xE0u ? 2u : b0 < 0xF0u ? 3u : b0 < 0xF5u ? 4u : 0u;
+          if ((b0 == 0xE0u && b1 < 0xA0u) || (b0 == 0xEDu && b1 >= 0xA0u) || (b0 == 0xF0u && b1 < 0x90u) || (b0 == 0xF4u && b1 >= 0x90u)) len = 0;
+          if (len == 0) S.bail = 1;
+          else EC |= ((1u << (len - 1u)) - 1u) << (j + 1u);
+        }
+      }
+      u32 ci = WP_SHFL_UP(EC >> 16, 1);
+      if (lane == 0) ci = u_carry;
+      u_carry = WP_SHFL(EC >> 16, 31);
+      if (((EC & 0xFFFFu) | ci) != (HI & ~C6)) S.bail = 1;
     }
     // escaped bytes: the carry into a chunk only matters through an all-backslash chunk
     u32 co0, co1;
@@ -149,6 +201,12 @@ GGR_DEV void ce_tokenize(CoopEnc& S, const u32* lut, const u8* in, u32 start, u3
     u32 cout = cin ? co1 : co0;
     c_carry = WP_SHFL(cout, 31);
     u32 RQ = Q & ~E;
+    // escape sequences: introducers, and escaped characters outside the simple set (incl. \u)
+    const u32 EI = B & ~E;
+    for (u32 m = E; m; m &= m - 1u) {
+      u32 j = wp_ffs0(m);
+      if (!(L.kind[ce_byte16(v, j)] & 0x80u)) D |= 1u << j;
+    }
     // in-string state at the start of the chunk
     u32 PB = WP_BALLOT((wp_popc(RQ) & 1u) != 0);
     u32 in0 = (wp_popc(PB & lt) + in_carry) & 1u;
@@ -163,13 +221,24 @@ GGR_DEV void ce_tokenize(CoopEnc& S, const u32* lut, const u8* in, u32 start, u3
     u32 NS = N & ~((N << 1) | pn);
     u32 T = ST | SO | NS;
     u32 tot;
+    // counters carried by prefix scans: tokens, quotes / escape introducers, slow bytes (each at most 512 per round)
     u32 ex = WP_EXCL_SCAN(wp_popc(T) | (wp_popc(RQ) << 16), &tot);
     u32 ti = tbase + (ex & 0xFFFFu), qi = qbase + (ex >> 16);
     tbase += tot & 0xFFFFu;
     qbase += tot >> 16;
+    u32 tot2;
+    const u32 ex2 = WP_EXCL_SCAN(wp_popc(EI) | (wp_popc(D) << 16), &tot2);
+    const u32 ei = ebase + (ex2 & 0xFFFFu), di = dbase + (ex2 >> 16);
+    ebase += tot2 & 0xFFFFu;
+    dbase += tot2 >> 16;
     const u32 qi0 = qi;
     for (u32 m = RQ; m; m &= m - 1u) {
-      if (qi < CE_MAX_Q) S.qpos[qi] = (u16)(off + wp_ffs0(m));
+      u32 j = wp_ffs0(m);
+      if (qi < SH::MAX_Q) {
+        S.qpos[qi] = (u16)(off + j);
+        S.qesc[qi] = (u16)(ei + wp_popc(EI & ((1u << j) - 1u)));
+        S.qslow[qi] = (u16)(di + wp_popc(D & ((1u << j) - 1u)));
+      }
       qi++;
     }
     for (u32 m = T; m; m &= m - 1u) {
@@ -181,23 +250,23 @@ GGR_DEV void ce_tokenize(CoopEnc& S, const u32* lut, const u8* in, u32 start, u3
       } else if (NS & bit) {
         kind = TK_SCALAR;
       } else {
-        u32 w = j < 4 ? v.x : j < 8 ? v.y : j < 12 ? v.z : v.w;
-        kind = ce_struct_kind((w >> (8 * (j & 3u))) & 0xFFu);
+        kind = L.kind[ce_byte16(v, j)] & 0xFu;
       }
-      if (ti < CE_MAX_TOK) S.tok[ti] = (off + j) | (kind << 16) | (aux << 20);
+      if (ti < SH::MAX_TOK) S.tok[ti] = (off + j) | (kind << 16) | (aux << 20);
       ti++;
     }
   }
   if (lane == 0) {
     S.n_tok = tbase;
     S.n_q = qbase;
-    if (tbase > CE_MAX_TOK || qbase > CE_MAX_Q || in_carry || tbase == 0) S.bail = 1;
+    if (tbase > SH::MAX_TOK || qbase > SH::MAX_Q || in_carry || u_carry || tbase == 0) S.bail = 1;
   }
   WP_SYNC();
 }
 
 // T2.  All lanes.  Fills the aux field of every bracket token with the index of its partner.
-GGR_DEV void ce_match(CoopEnc& S) {
+template <class SH>
+GGR_DEV void ce_match(SH& S) {
   const u32 lane = wp_lane();
   const u32 lt = (1u << lane) - 1u, le = lt | (1u << lane);
   const u32 n = S.n_tok;
@@ -233,7 +302,8 @@ GGR_DEV void ce_match(CoopEnc& S) {
   WP_SYNC();
 }
 
-GGR_DEV u32 ce_new_node(CoopEnc& S, u32 tok, u32 parent, u32 gfield, u32 emit, u32 cls, u32 depth) {
+template <class SH>
+GGR_DEV u32 ce_new_node(SH& S, u32 tok, u32 parent, u32 gfield, u32 emit, u32 cls, u32 depth) {
   u32 idx = wp_atomic_add(&S.n_node, 1u);
   if (idx >= S.cap || gfield >= 0xFFFFu || emit >= 0xFFFu) {
     S.bail = 1;
@@ -273,7 +343,8 @@ GGR_DEV bool ce_is_null(const EncCtx& cx, u32 pos) {
 }
 
 // T3, one lane: members of the JSON object behind message node `ni`.
-GGR_DEV void ce_walk_object(CoopEnc& S, const EncCtx& cx, u32 ni) {
+template <class SH>
+GGR_DEV void ce_walk_object(SH& S, const EncCtx& cx, u32 ni) {
   const Tables& T = cx.T;
   const u32 open = S.node[ni].tok;
   const u32 depth = S.node[ni].depth;
@@ -313,8 +384,11 @@ GGR_DEV void ce_walk_object(CoopEnc& S, const EncCtx& cx, u32 ni) {
       child = ce_new_node(S, t, ni, gf, emit, CC_NULL, depth + 1);
       t++;
     } else if (f.flags & GF_MAP) {
-      S.bail = 1;  // maps: per-thread path
-      return;
+      if (vk != TK_LBRACE) { S.bail = 1; return; }
+      child = ce_new_node(S, t, ni, gf, emit, CC_MAP, depth + 1);
+      if (child == CE_NIL) return;
+      S.queue[wp_atomic_add(&S.q_end, 1u)] = (u16)child;
+      t = TK_AUX(vt) + 1u;
     } else if (f.flags & GF_REPEATED) {
       if (vk != TK_LBRACK) { S.bail = 1; return; }
       const u32 aend = TK_AUX(vt);
@@ -420,10 +494,100 @@ GGR_DEV void ce_walk_object(CoopEnc& S, const EncCtx& cx, u32 ni) {
   wp_atomic_max(&S.max_depth, depth + 1);
 }
 
+// T3, one lane: entries of the JSON object behind map node `ni` (string keys only).  Every entry
+// becomes ENTRY{key leaf, value}; entries are kept in key order (decoded bytes, as Go compares
+// strings), equal keys are left to the per-thread path.
+template <class SH>
+GGR_DEV void ce_walk_map(SH& S, const EncCtx& cx, u32 ni) {
+  const Tables& T = cx.T;
+  const u32 open = S.node[ni].tok;
+  const u32 depth = S.node[ni].depth;
+  const u32 mgf = S.node[ni].gfield;
+  const FieldD mapf = ggr_field(T, mgf);
+  const MsgD ed = ggr_msg(T, (u32)mapf.child);
+  const u32 kgf = ed.field_first, vgf = ed.field_first + 1u;
+  const FieldD kf = ggr_field(T, kgf);
+  const FieldD vf = ggr_field(T, vgf);
+  if (kf.kind != GK_STRING || depth + 3u >= CE_MAX_DEPTH) { S.bail = 1; return; }
+  bool ts = false, msg = false;
+  if (vf.kind == GK_MESSAGE) {
+    u32 w = ggr_msg(T, (u32)vf.child).wkt;
+    ts = w == GGR_WKT_TIMESTAMP;
+    msg = w == GGR_WKT_NONE;
+    if ((!ts && !msg) || (u32)vf.child >= 0xFFFFu) { S.bail = 1; return; }
+  }
+  const u32 vcls = ce_leaf_class(vf, ts);
+  const u32 close = TK_AUX(S.tok[open]);
+  u32 head = CE_NIL, tail = CE_NIL, tail_key = 0;
+  u32 t = open + 1;
+  bool first = true;
+  while (t != close) {
+    if (!first) {
+      if (TK_KIND(S.tok[t]) != TK_COMMA) { S.bail = 1; return; }
+      t++;
+    }
+    first = false;
+    if (t + 2u >= close) { S.bail = 1; return; }
+    const u32 kt = S.tok[t];
+    if (TK_KIND(kt) != TK_STR || TK_KIND(S.tok[t + 1]) != TK_COLON) { S.bail = 1; return; }
+    const u32 key_pos = TK_POS(kt);
+    const u32 vt = S.tok[t + 2];
+    const u32 vk = TK_KIND(vt);
+    const u32 ent = ce_new_node(S, t, ni, mgf, 0, CC_ENTRY, depth + 1);
+    const u32 key = ce_new_node(S, t, ent, kgf, 0, CC_STR, depth + 2);
+    if (ent == CE_NIL || key == CE_NIL) return;
+    u32 val;
+    if (msg) {
+      if (vk != TK_LBRACE) { S.bail = 1; return; }
+      val = ce_new_node(S, t + 2, ent, vgf, 1, CC_MSG, depth + 2);
+      if (val == CE_NIL) return;
+      S.node[val].msg = (u16)vf.child;
+      S.queue[wp_atomic_add(&S.q_end, 1u)] = (u16)val;
+      t = TK_AUX(vt) + 1u;
+    } else {
+      if (vk != TK_STR && vk != TK_SCALAR) { S.bail = 1; return; }
+      if (vk == TK_SCALAR && ce_is_null(cx, TK_POS(vt))) { S.bail = 1; return; }
+      val = ce_new_node(S, t + 2, ent, vgf, 1, vcls, depth + 2);
+      if (val == CE_NIL) return;
+      t += 3;
+    }
+    if (t > close) { S.bail = 1; return; }
+    S.node[ent].head = (u16)key;
+    S.node[key].next = (u16)val;
+    if (head == CE_NIL) {
+      head = tail = ent;
+      tail_key = key_pos;
+    } else {
+      int c = cmp_str_tokens(cx.in, key_pos, tail_key, cx.end);
+      if (c == 0) { S.bail = 1; return; }
+      if (c > 0) {
+        S.node[tail].next = (u16)ent;
+        tail = ent;
+        tail_key = key_pos;
+      } else {
+        u32 prev = CE_NIL, cur = head;
+        for (;;) {
+          int cc = cmp_str_tokens(cx.in, key_pos, TK_POS(S.tok[S.node[cur].tok]), cx.end);
+          if (cc == 0) { S.bail = 1; return; }
+          if (cc < 0) break;
+          prev = cur;
+          cur = S.node[cur].next;
+        }
+        S.node[ent].next = (u16)cur;
+        if (prev == CE_NIL) head = ent;
+        else S.node[prev].next = (u16)ent;
+      }
+    }
+  }
+  S.node[ni].head = (u16)head;
+  wp_atomic_max(&S.max_depth, depth + 2);
+}
+
 GGR_DEV u32 ce_link(u32 x) { return x == CE_NIL ? GGR_NIL : x; }
 
 // T4, one lane: finish leaf node `ni` (IR node + size into its parent).
-GGR_DEV void ce_leaf(CoopEnc& S, EncCtx& cx, u32 ni) {
+template <class SH>
+GGR_DEV void ce_leaf(SH& S, EncCtx& cx, u32 ni) {
   const CNode nd = S.node[ni];
   const u32 next = ce_link(nd.next);
   if (nd.cls == CC_NULL) {
@@ -432,8 +596,9 @@ GGR_DEV void ce_leaf(CoopEnc& S, EncCtx& cx, u32 ni) {
   }
   const FieldD f = ggr_field(cx.T, nd.gfield);
   const u32 tk = S.tok[nd.tok];
-  const bool in_list = S.node[nd.parent].cls == CC_LIST;
-  const bool packed = in_list && (f.flags & GF_PACKED);
+  const u32 pcls = S.node[nd.parent].cls;
+  const bool in_list = pcls == CC_LIST || pcls == CC_ENTRY;  // no zero elision in lists and map entries
+  const bool packed = pcls == CC_LIST && (f.flags & GF_PACKED);
   const u32 tag = packed ? 0u : f.tag, tag_len = packed ? 0u : f.tag_len;
   Rd r;
   r.init(cx.in, TK_POS(tk), cx.end);
@@ -464,10 +629,30 @@ GGR_DEV void ce_leaf(CoopEnc& S, EncCtx& cx, u32 ni) {
     return;
   }
   Leaf l;
-  if (parse_scalar(cx, r, f.kind, f.child, &l) != GST_OK) { S.bail = 1; return; }
-  if (TK_KIND(tk) == TK_SCALAR && !r.eof()) {  // the literal must end where the parser stopped
-    u32 c = r.peek();
-    if (!(ggr_is_ws(c) || c == ',' || c == '}' || c == ']')) { S.bail = 1; return; }
+  bool done = false;
+  if (nd.cls == CC_STR && TK_KIND(tk) == TK_STR) {
+    // the tokenizer validated UTF-8 and counted simple escapes and the bytes that need the full
+    // scanner (control characters, \u, bad escapes): without the latter the string is valid and its
+    // decoded length known
+    const u32 k = TK_AUX(tk);
+    if (S.qslow[k] == S.qslow[k + 1]) {
+      const u32 nesc = (u16)(S.qesc[k + 1] - S.qesc[k]);
+      const u32 q = TK_POS(tk), len = (u32)S.qpos[k + 1] - q - 1u - nesc;  // a simple escape decodes 2 bytes to 1
+      l.type = N_STR;
+      l.a = q;
+      l.b = len;
+      l.flags = nesc ? NF_ESC : 0;
+      l.body = varint_size(len) + len;
+      l.zero = len == 0;
+      done = true;
+    }
+  }
+  if (!done) {
+    if (parse_scalar(cx, r, f.kind, f.child, &l) != GST_OK) { S.bail = 1; return; }
+    if (TK_KIND(tk) == TK_SCALAR && !r.eof()) {  // the literal must end where the parser stopped
+      u32 c = r.peek();
+      if (!(ggr_is_ws(c) || c == ',' || c == '}' || c == ']')) { S.bail = 1; return; }
+    }
   }
   const bool live = in_list || (f.flags & GF_PRESENCE) || !l.zero;
   node_store(cx.ir, ni, l.a, l.b, next, nd.emit, live ? node_meta(l.type, l.flags, tag) : node_meta(N_SKIP, 0, 0));
@@ -475,12 +660,19 @@ GGR_DEV void ce_leaf(CoopEnc& S, EncCtx& cx, u32 ni) {
 }
 
 // T5, one lane: container `ni` is complete; write its IR node and add its size to the parent.
-GGR_DEV void ce_close_container(CoopEnc& S, EncCtx& cx, u32 ni) {
+template <class SH>
+GGR_DEV void ce_close_container(SH& S, EncCtx& cx, u32 ni) {
   const CNode nd = S.node[ni];
   const FieldD f = ggr_field(cx.T, nd.gfield);
   const u32 next = ce_link(nd.next), head = ce_link(nd.head);
   u32 full;
-  if (nd.cls == CC_MSG) {
+  if (nd.cls == CC_ENTRY) {
+    node_store(cx.ir, ni, nd.body, head, next, 0, node_meta(N_ENTRY, 0, f.tag));
+    full = f.tag_len + varint_size(nd.body) + nd.body;
+  } else if (nd.cls == CC_MAP) {
+    node_store(cx.ir, ni, nd.body, head, next, nd.emit, nd.head == CE_NIL ? node_meta(N_SKIP, 0, 0) : node_meta(N_MAP, 0, 0));
+    full = nd.body;
+  } else if (nd.cls == CC_MSG) {
     node_store(cx.ir, ni, nd.body, head, next, nd.emit, node_meta(N_MSG, 0, f.tag));
     full = f.tag_len + varint_size(nd.body) + nd.body;
   } else if (nd.head == CE_NIL) {
@@ -498,19 +690,21 @@ GGR_DEV void ce_close_container(CoopEnc& S, EncCtx& cx, u32 ni) {
 
 // One item, all 32 lanes.  Returns true when the item was handled (IR written, *res filled);
 // false leaves it to the per-thread parser.
-GGR_DEV bool ce_parse_item(CoopEnc& S, const u32* lut, const Tables& T, u32 root_msg, const u8* in, u32 start, u32 end, u8* ir,
+template <class SH>
+GGR_DEV bool ce_parse_item(SH& S, const CeLut& lut, const Tables& T, u32 root_msg, const u8* in, u32 start, u32 end, u8* ir,
                            u32 ir_cap, EncResult* res) {
   const u32 lane = wp_lane();
   res->size = 0;
   res->first = GGR_NIL;
   if (end > CE_MAX_INPUT || ir_cap == 0) return false;
   if (end == start) return true;  // reflection.go:354: "" skips protojson
+  WP_SYNC();  // persistent warps: nobody still reads the previous item's state
   if (lane == 0) {
     S.bail = 0;
     S.n_node = 0;
     S.q_end = 0;
     S.max_depth = 0;
-    S.cap = ir_cap < CE_MAX_NODE ? ir_cap : CE_MAX_NODE;
+    S.cap = ir_cap < SH::MAX_NODE ? ir_cap : SH::MAX_NODE;
   }
   WP_SYNC();
   ce_tokenize(S, lut, in, start, end);
@@ -541,7 +735,11 @@ GGR_DEV bool ce_parse_item(CoopEnc& S, const u32* lut, const Tables& T, u32 root
     const u32 qe = S.q_end;
     if (qb == qe) break;
     WP_SYNC();  // everyone has read q_end before the walkers append to the queue
-    for (u32 i = qb + lane; i < qe; i += 32) ce_walk_object(S, cx, S.queue[i]);
+    for (u32 i = qb + lane; i < qe; i += 32) {
+      const u32 ni = S.queue[i];
+      if (S.node[ni].cls == CC_MAP) ce_walk_map(S, cx, ni);
+      else ce_walk_object(S, cx, ni);
+    }
     WP_SYNC();
     if (S.bail) return false;
     qb = qe;
@@ -577,7 +775,7 @@ GGR_DEV bool ce_parse_item(CoopEnc& S, const u32* lut, const Tables& T, u32 root
   for (u32 d = S.max_depth; d >= 1; d--) {
     for (u32 i = lane; i < n; i += 32) {
       CNode nd = S.node[i];
-      if (nd.depth == d && nd.cls <= CC_LIST) ce_close_container(S, cx, i);
+      if (nd.depth == d && nd.cls <= CC_ENTRY) ce_close_container(S, cx, i);
     }
     WP_SYNC();
   }

@@ -70,6 +70,7 @@ struct DevBuf {
 
 struct ggr_engine {
   int device = 0;
+  int sm_count = 148;
   ggr::WireOrder order = ggr::ORDER_FIELD_NUMBER;
   cudaStream_t stream = nullptr;
   std::string err;
@@ -146,9 +147,16 @@ int ggr_engine_create(const ggr_config* cfg, ggr_engine** out) {
   }
   ggr_engine* e = new ggr_engine();
   e->device = dev;
+  cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (e->sm_count <= 0) e->sm_count = 148;
   if (const char* nc = getenv("GGR_COOP")) e->use_coop = nc[0] == '1';
   if (const char* nc = getenv("GGR_COOP_ENC")) e->use_coop_enc = nc[0] != '0';
   e->order = (cfg && cfg->wire_order == GGR_ORDER_GO_LEGACY) ? ggr::ORDER_GO_LEGACY : ggr::ORDER_FIELD_NUMBER;
+  if (ggr_encode_coop_init() != 0) {
+    cudaGetLastError();
+    delete e;
+    return GGR_ERR_CUDA;
+  }
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete e;
     return GGR_ERR_CUDA;
@@ -298,17 +306,20 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, c
   if (encode) {
     if (e->use_coop_enc) {
       // lock-step parser first (one warp per item); what it leaves goes to the per-thread parser
-      if (!ensure(e, e->pend, (size_t)n * 4 + 16)) return GGR_ERR_CUDA;
-      u32* n_pending = (u32*)e->pend.p;
-      u32* pending = n_pending + 4;
+      if (!ensure(e, e->pend, (size_t)n * 8 + 64)) return GGR_ERR_CUDA;
+      u32* counters = (u32*)e->pend.p;  // [0] left by tier 1, [4] left by tier 2
+      u32* pend1 = counters + 16;
+      u32* pend2 = pend1 + n;
       size_t c0 = 0, c1 = 0;
-      if (!cuda_ok(e, cudaMemsetAsync(n_pending, 0, 16, st), "memset")) return GGR_ERR_CUDA;
+      if (!cuda_ok(e, cudaMemsetAsync(counters, 0, 64, st), "memset")) return GGR_ERR_CUDA;
       if (prof) prof_mark(e, st, &m0);
-      ggr_launch_encode_coop_parse(st, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)e->ir.p, (u32*)e->size[d].p,
-                                   (u32*)e->aux[d].p, status, pending, n_pending);
+      ggr_launch_encode_coop_parse(st, 0, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)e->ir.p, (u32*)e->size[d].p,
+                                   (u32*)e->aux[d].p, status, nullptr, nullptr, pend1, counters, e->sm_count);
+      ggr_launch_encode_coop_parse(st, 1, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)e->ir.p, (u32*)e->size[d].p,
+                                   (u32*)e->aux[d].p, status, pend1, counters, pend2, counters + 4, e->sm_count);
       if (prof) prof_mark(e, st, &c0);
       ggr_launch_encode_parse(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)e->ir.p, (u32*)e->size[d].p,
-                              (u32*)e->aux[d].p, status, (u64*)e->sums[d].p, pending, n_pending);
+                              (u32*)e->aux[d].p, status, (u64*)e->sums[d].p, pend2, counters + 4);
       if (prof) prof_mark(e, st, &c1);
       ggr_launch_block_sums(st, (unsigned)nb, n, (const u32*)e->size[d].p, (u64*)e->sums[d].p);
       if (prof) {
@@ -317,7 +328,7 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, c
         prof_mark(e, st, &m1);
         e->spans.push_back({9, c1, m1});
       }
-      e->launches += 2;
+      e->launches += 3;
     } else {
       ggr_launch_encode_parse(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)e->ir.p, (u32*)e->size[d].p,
                               (u32*)e->aux[d].p, status, (u64*)e->sums[d].p, nullptr, nullptr);

@@ -19,7 +19,7 @@ def lib():
         L.hs_msg_index.argtypes = [C.c_void_p, C.c_char_p]
         L.hs_encode.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p,
                                 C.c_uint32, C.POINTER(C.c_uint32)]
-        L.hs_encode_coop.argtypes = L.hs_encode.argtypes
+        L.hs_encode_coop.argtypes = L.hs_encode.argtypes + [C.c_int]
         if hasattr(L, "hs_decode_coop"):
             L.hs_decode_coop.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                          C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32)]
@@ -69,11 +69,11 @@ def _decode_coop(self, name, data, flags=0, in_off=0, out_off=0):
 Schema.decode_coop = _decode_coop
 
 
-def _encode_coop(self, name, data, in_off=0, out_off=0):
+def _encode_coop(self, name, data, in_off=0, out_off=0, tier=0):
     cap = len(data) + 64
     out = C.create_string_buffer(cap)
     n = C.c_uint32()
-    rc = lib().hs_encode_coop(self.h, self.msg(name), data, len(data), in_off, out_off, out, cap, C.byref(n))
+    rc = lib().hs_encode_coop(self.h, self.msg(name), data, len(data), in_off, out_off, out, cap, C.byref(n), tier)
     return rc, out.raw[: n.value]
 
 

@@ -87,12 +87,14 @@ int hs_encode(void* h, int msg, const uint8_t* json, uint32_t n, uint32_t in_off
   return st;
 }
 
+}  // extern "C"
 // Lock-step request-side pass A (one warp per item) on 32 fibers, then the shared pass B.
 // Returns 200 when the lock-step parser leaves the item to the per-thread parser, 300 + n when
 // the fiber warp detected a divergence bug.
+template <class SH>
 struct CoopEncArgs {
-  CoopEnc* S;
-  const u32* lut;
+  SH* S;
+  const CeLut* lut;
   Tables T;
   u32 msg;
   const u8* in;
@@ -102,17 +104,19 @@ struct CoopEncArgs {
   EncResult res[32];
   bool ok[32];
 };
+template <class SH>
 static void coop_enc_body(void* p, u32 lane) {
-  CoopEncArgs* a = (CoopEncArgs*)p;
-  a->ok[lane] = ce_parse_item(*a->S, a->lut, a->T, a->msg, a->in, a->start, a->end, a->ir, a->ir_cap, &a->res[lane]);
+  CoopEncArgs<SH>* a = (CoopEncArgs<SH>*)p;
+  a->ok[lane] = ce_parse_item(*a->S, *a->lut, a->T, a->msg, a->in, a->start, a->end, a->ir, a->ir_cap, &a->res[lane]);
 }
-int hs_encode_coop(void* h, int msg, const uint8_t* json, uint32_t n, uint32_t in_off, uint32_t out_off, uint8_t* out,
-                   uint32_t out_cap, uint32_t* out_n) {
+template <class SH>
+static int hs_encode_coop_t(void* h, int msg, const uint8_t* json, uint32_t n, uint32_t in_off, uint32_t out_off, uint8_t* out,
+                            uint32_t out_cap, uint32_t* out_n) {
   HsSchema* s = (HsSchema*)h;
-  static u32 lut[256];
+  static CeLut lut;
   static bool lut_ok = false;
   if (!lut_ok) {
-    for (u32 b = 0; b < 256; b++) lut[b] = ce_class(b);
+    ce_lut_init(lut, 0, 1);
     lut_ok = true;
   }
   std::vector<uint8_t> inbuf_raw(in_off + n + 64 + 16, 0xEE);
@@ -121,11 +125,11 @@ int hs_encode_coop(void* h, int msg, const uint8_t* json, uint32_t n, uint32_t i
   uint32_t ir_cap = n / 2 + 8;
   uint8_t* ir = (uint8_t*)aligned_alloc(16, (size_t)ir_cap * 16);
   memset(ir, 0xCC, (size_t)ir_cap * 16);
-  static CoopEnc S;
+  static SH S;
   memset(&S, 0xAB, sizeof S);  // stale shared memory must not matter
-  CoopEncArgs a;
+  CoopEncArgs<SH> a;
   a.S = &S;
-  a.lut = lut;
+  a.lut = &lut;
   a.T = ggr_tables(s->blob);
   a.msg = (u32)msg;
   a.in = in;
@@ -133,7 +137,7 @@ int hs_encode_coop(void* h, int msg, const uint8_t* json, uint32_t n, uint32_t i
   a.end = in_off + n;
   a.ir = ir;
   a.ir_cap = ir_cap;
-  int werr = hw_run_warp(coop_enc_body, &a);
+  int werr = hw_run_warp(coop_enc_body<SH>, &a);
   *out_n = 0;
   if (werr) {
     free(ir);
@@ -165,6 +169,13 @@ int hs_encode_coop(void* h, int msg, const uint8_t* json, uint32_t n, uint32_t i
   *out_n = res.size;
   free(ir);
   return st;
+}
+extern "C" {
+// tier 0: the small per-warp tables of the first kernel; tier 1: the large ones of the second
+int hs_encode_coop(void* h, int msg, const uint8_t* json, uint32_t n, uint32_t in_off, uint32_t out_off, uint8_t* out,
+                   uint32_t out_cap, uint32_t* out_n, int tier) {
+  return tier ? hs_encode_coop_t<CoopEncBig>(h, msg, json, n, in_off, out_off, out, out_cap, out_n)
+              : hs_encode_coop_t<CoopEnc>(h, msg, json, n, in_off, out_off, out, out_cap, out_n);
 }
 
 #ifdef GGR_HAVE_DECODE

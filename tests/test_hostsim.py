@@ -98,10 +98,10 @@ def test_decode_random(oracle, hsim):
 
 
 # ---- lock-step request-side parser (ggr_coop_enc.cuh) on 32 fibers ---------------------------
-def _check_coop_encode(hsim, name, js, i=0):
+def _check_coop_encode(hsim, name, js, i=0, tier=0):
     """the lock-step parser either leaves the item alone (200) or produces exactly the bytes of the
     per-thread path; 3xx = the fiber warp caught lanes at different collectives"""
-    rc, out = hsim.encode_coop(name, js, i % 16, (i * 5) % 16)
+    rc, out = hsim.encode_coop(name, js, i % 16, (i * 5) % 16, tier)
     assert rc in (0, 200), (name, js, rc)
     if rc == 200:
         return False
@@ -125,8 +125,8 @@ def test_coop_encode_random_and_damaged(hsim):
     rng = random.Random(23)
     handled = 0
     for i, (name, js) in enumerate(cases.random_encode_cases(150, seed0=4000)):
-        handled += _check_coop_encode(hsim, name, js, i)
-        handled += _check_coop_encode(hsim, name, cases.mutate_json(js, rng), i + 1)
+        handled += _check_coop_encode(hsim, name, js, i, i & 1)
+        handled += _check_coop_encode(hsim, name, cases.mutate_json(js, rng), i + 1, i & 1)
     assert handled > 500
 
 
@@ -138,11 +138,13 @@ def test_coop_encode_bench_shapes(hsim):
         names[hsim.msg(name)] = name
         return hsim.msg(name)
 
-    for kind, n, want in (("nested", 200, 150), ("flat", 100, 100)):
+    # tier 0 = small per-warp tables (first kernel), tier 1 = large tables (second kernel): together
+    # they must take every item of the benchmark shapes, or the per-thread parser becomes the tail
+    for kind, n, tier, want in (("nested", 200, 0, 180), ("nested", 200, 1, 200), ("flat", 100, 0, 100)):
         wl = getattr(benchgen, kind)(n, mi)
         blob = wl.req_json.tobytes()
         handled = 0
         for i in range(n):
             js = blob[int(wl.req_off[i]):int(wl.req_off[i + 1])]
-            handled += _check_coop_encode(hsim, names[int(wl.req_msg[i])], js, i)
-        assert handled >= want, (kind, handled)
+            handled += _check_coop_encode(hsim, names[int(wl.req_msg[i])], js, i, tier)
+        assert handled >= want, (kind, tier, handled)
