@@ -68,6 +68,19 @@ struct DevBuf {
   size_t cap = 0;
 };
 
+struct Scratch {
+  DevBuf ir, size, aux, sums, pend;
+};
+#define GGR_MAX_SLOTS 8
+struct Slot {
+  cudaStream_t st = nullptr;
+  cudaEvent_t ready = nullptr;
+  Scratch sc;
+  DevBuf d_in, d_off, d_msg, d_out, d_out_off, d_status;
+  uint64_t* h_total = nullptr;  // pinned: output bytes of the chunk in flight
+  uint64_t out_cap = 0;         // capacity handed to the kernels for that chunk
+};
+
 struct ggr_engine {
   int device = 0;
   int sm_count = 148;
@@ -77,13 +90,15 @@ struct ggr_engine {
   uint64_t launches = 0;
   bool use_coop = false;  // GGR_COOP=1 enables the warp-cooperative reply-side kernels (slower than the per-thread ones so far)
   std::mutex mu;
-  // scratch (device)
-  // scratch (device); size/aux/sums exist once per direction so that a request batch and a reply
-  // batch can be in flight on two streams at the same time
-  DevBuf ir, size[2], aux[2], sums[2], pend;
+  // scratch (device): one set per direction for the device-buffer entry points, so that a request
+  // batch and a reply batch can be in flight on two streams at the same time
+  Scratch dev_sc[2];
   bool use_coop_enc = true;  // GGR_COOP_ENC=0 disables the lock-step request-side parser (A/B runs)
-  // staging for the host-buffer entry points (device)
-  DevBuf d_in, d_off, d_msg, d_out, d_out_off, d_status;
+  // host-buffer entry points: the batch is cut into chunks that move through `n_slots` slots
+  // (stream + staging + scratch each), so that H2D, kernels and D2H of different chunks overlap
+  Slot slots[GGR_MAX_SLOTS];
+  int n_slots = 3;
+  int64_t chunk_items = 32768;
   // per-kernel timing
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -151,6 +166,14 @@ int ggr_engine_create(const ggr_config* cfg, ggr_engine** out) {
   if (e->sm_count <= 0) e->sm_count = 148;
   if (const char* nc = getenv("GGR_COOP")) e->use_coop = nc[0] == '1';
   if (const char* nc = getenv("GGR_COOP_ENC")) e->use_coop_enc = nc[0] != '0';
+  if (const char* nc = getenv("GGR_SLOTS")) {
+    int v = atoi(nc);
+    if (v >= 1 && v <= GGR_MAX_SLOTS) e->n_slots = v;
+  }
+  if (const char* nc = getenv("GGR_CHUNK_ITEMS")) {
+    long long v = atoll(nc);
+    if (v >= 128) e->chunk_items = v;
+  }
   e->order = (cfg && cfg->wire_order == GGR_ORDER_GO_LEGACY) ? ggr::ORDER_GO_LEGACY : ggr::ORDER_FIELD_NUMBER;
   if (ggr_encode_coop_init() != 0) {
     cudaGetLastError();
@@ -189,9 +212,24 @@ void ggr_engine_destroy(ggr_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  DevBuf* bufs[] = {&e->ir, &e->size[0], &e->size[1], &e->aux[0], &e->aux[1], &e->sums[0], &e->sums[1], &e->pend, &e->d_in, &e->d_off, &e->d_msg, &e->d_out, &e->d_out_off, &e->d_status};
-  for (DevBuf* b : bufs)
-    if (b->p) cudaFree(b->p);
+  auto free_scratch = [](Scratch& sc) {
+    DevBuf* bufs[] = {&sc.ir, &sc.size, &sc.aux, &sc.sums, &sc.pend};
+    for (DevBuf* b : bufs)
+      if (b->p) cudaFree(b->p);
+  };
+  free_scratch(e->dev_sc[0]);
+  free_scratch(e->dev_sc[1]);
+  for (int i = 0; i < GGR_MAX_SLOTS; i++) {
+    Slot& sl = e->slots[i];
+    if (sl.st) cudaStreamSynchronize(sl.st);
+    free_scratch(sl.sc);
+    DevBuf* bufs[] = {&sl.d_in, &sl.d_off, &sl.d_msg, &sl.d_out, &sl.d_out_off, &sl.d_status};
+    for (DevBuf* b : bufs)
+      if (b->p) cudaFree(b->p);
+    if (sl.h_total) cudaFreeHost(sl.h_total);
+    if (sl.ready) cudaEventDestroy(sl.ready);
+    if (sl.st) cudaStreamDestroy(sl.st);
+  }
   for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
   cudaStreamDestroy(e->stream);
   delete e;
@@ -286,7 +324,7 @@ int ggr_synchronize(ggr_engine* e) {
   return cuda_ok(e, cudaStreamSynchronize(e->stream), "cudaStreamSynchronize") ? GGR_SUCCESS : GGR_ERR_CUDA;
 }
 
-static int run_dev(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, const int32_t* msg_id, const uint8_t* in,
+static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode, int64_t n, const int32_t* msg_id, const uint8_t* in,
                    const uint64_t* in_off, uint64_t in_bytes, uint8_t* out, uint64_t out_cap, uint64_t* out_off,
                    int32_t* status, uint32_t flags, cudaStream_t st) {
   if (!e || !s || n < 0 || (n > 0 && (!msg_id || !in || !in_off || !out_off || !status))) return GGR_ERR_INVALID_ARGUMENT;
@@ -296,9 +334,8 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, c
     return cuda_ok(e, cudaMemsetAsync(out_off, 0, sizeof(uint64_t), st), "memset") ? GGR_SUCCESS : GGR_ERR_CUDA;
   }
   long long nb = (n + GGR_BLOCK - 1) / GGR_BLOCK;
-  const int d = encode ? 0 : 1;
-  if (!ensure(e, e->size[d], (size_t)n * 4) || !ensure(e, e->aux[d], (size_t)n * 4) || !ensure(e, e->sums[d], (size_t)nb * 8)) return GGR_ERR_CUDA;
-  if (encode && !ensure(e, e->ir, (size_t)in_bytes * 8 + (size_t)n * 128 + 256)) return GGR_ERR_CUDA;
+  if (!ensure(e, sc.size, (size_t)n * 4) || !ensure(e, sc.aux, (size_t)n * 4) || !ensure(e, sc.sums, (size_t)nb * 8)) return GGR_ERR_CUDA;
+  if (encode && !ensure(e, sc.ir, (size_t)in_bytes * 8 + (size_t)n * 128 + 256)) return GGR_ERR_CUDA;
   u32 n_msgs = (u32)s->cs.msg_names.size();
   const bool prof = e->profiling && e->ev_used + 8 <= 65536;
   size_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
@@ -306,22 +343,22 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, c
   if (encode) {
     if (e->use_coop_enc) {
       // lock-step parser first (one warp per item); what it leaves goes to the per-thread parser
-      if (!ensure(e, e->pend, (size_t)n * 8 + 64)) return GGR_ERR_CUDA;
-      u32* counters = (u32*)e->pend.p;  // [0] left by tier 1, [4] left by tier 2
+      if (!ensure(e, sc.pend, (size_t)n * 8 + 64)) return GGR_ERR_CUDA;
+      u32* counters = (u32*)sc.pend.p;  // [0] left by tier 1, [4] left by tier 2
       u32* pend1 = counters + 16;
       u32* pend2 = pend1 + n;
       size_t c0 = 0, c1 = 0;
       if (!cuda_ok(e, cudaMemsetAsync(counters, 0, 64, st), "memset")) return GGR_ERR_CUDA;
       if (prof) prof_mark(e, st, &m0);
-      ggr_launch_encode_coop_parse(st, 0, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)e->ir.p, (u32*)e->size[d].p,
-                                   (u32*)e->aux[d].p, status, nullptr, nullptr, pend1, counters, e->sm_count);
-      ggr_launch_encode_coop_parse(st, 1, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)e->ir.p, (u32*)e->size[d].p,
-                                   (u32*)e->aux[d].p, status, pend1, counters, pend2, counters + 4, e->sm_count);
+      ggr_launch_encode_coop_parse(st, 0, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
+                                   (u32*)sc.aux.p, status, nullptr, nullptr, pend1, counters, e->sm_count);
+      ggr_launch_encode_coop_parse(st, 1, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
+                                   (u32*)sc.aux.p, status, pend1, counters, pend2, counters + 4, e->sm_count);
       if (prof) prof_mark(e, st, &c0);
-      ggr_launch_encode_parse(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)e->ir.p, (u32*)e->size[d].p,
-                              (u32*)e->aux[d].p, status, (u64*)e->sums[d].p, pend2, counters + 4);
+      ggr_launch_encode_parse(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
+                              (u32*)sc.aux.p, status, (u64*)sc.sums.p, pend2, counters + 4);
       if (prof) prof_mark(e, st, &c1);
-      ggr_launch_block_sums(st, (unsigned)nb, n, (const u32*)e->size[d].p, (u64*)e->sums[d].p);
+      ggr_launch_block_sums(st, (unsigned)nb, n, (const u32*)sc.size.p, (u64*)sc.sums.p);
       if (prof) {
         e->spans.push_back({8, m0, c0});
         e->spans.push_back({0, c0, c1});
@@ -330,37 +367,37 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, c
       }
       e->launches += 3;
     } else {
-      ggr_launch_encode_parse(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)e->ir.p, (u32*)e->size[d].p,
-                              (u32*)e->aux[d].p, status, (u64*)e->sums[d].p, nullptr, nullptr);
+      ggr_launch_encode_parse(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
+                              (u32*)sc.aux.p, status, (u64*)sc.sums.p, nullptr, nullptr);
       if (prof) prof_mark(e, st, &m1);
     }
-    k_scan_blocks<<<1, 1024, 0, st>>>((u64*)e->sums[d].p, nb, out_off + n);
+    k_scan_blocks<<<1, 1024, 0, st>>>((u64*)sc.sums.p, nb, out_off + n);
     if (prof) prof_mark(e, st, &m2);
-    ggr_launch_encode_emit(st, (unsigned)nb, n, in, in_off, (const u8*)e->ir.p, (const u32*)e->size[d].p,
-                           (const u32*)e->aux[d].p, status, (const u64*)e->sums[d].p, out, out_cap, out_off);
+    ggr_launch_encode_emit(st, (unsigned)nb, n, in, in_off, (const u8*)sc.ir.p, (const u32*)sc.size.p,
+                           (const u32*)sc.aux.p, status, (const u64*)sc.sums.p, out, out_cap, out_off);
   } else {
     // Reply side: the warp-cooperative kernels take every regular item; the per-thread kernels
     // then walk only what was left pending (irregular field order, maps, malformed wire, ...).
     const bool coop = e->use_coop;
     size_t c0 = 0, c1 = 0;
     if (coop) {
-      ggr_launch_decode_coop_size(st, n, s->d_blob, n_msgs, msg_id, in, in_off, flags, (u32*)e->size[d].p, (u32*)e->aux[d].p, status);
+      ggr_launch_decode_coop_size(st, n, s->d_blob, n_msgs, msg_id, in, in_off, flags, (u32*)sc.size.p, (u32*)sc.aux.p, status);
       if (prof) {
         prof_mark(e, st, &c0);
         e->spans.push_back({6, m0, c0});
         m0 = c0;
       }
     }
-    ggr_launch_decode_size(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, flags, (u32*)e->size[d].p,
-                           (u32*)e->aux[d].p, status, (u64*)e->sums[d].p, coop ? 1 : 0);
+    ggr_launch_decode_size(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, flags, (u32*)sc.size.p,
+                           (u32*)sc.aux.p, status, (u64*)sc.sums.p, coop ? 1 : 0);
     if (prof) prof_mark(e, st, &m1);
-    k_scan_blocks<<<1, 1024, 0, st>>>((u64*)e->sums[d].p, nb, out_off + n);
+    k_scan_blocks<<<1, 1024, 0, st>>>((u64*)sc.sums.p, nb, out_off + n);
     if (prof) prof_mark(e, st, &m2);
-    ggr_launch_decode_write(st, (unsigned)nb, s->d_blob, n, msg_id, in, in_off, flags, (const u32*)e->size[d].p,
-                            (const u32*)e->aux[d].p, status, (const u64*)e->sums[d].p, out, out_cap, out_off);
+    ggr_launch_decode_write(st, (unsigned)nb, s->d_blob, n, msg_id, in, in_off, flags, (const u32*)sc.size.p,
+                            (const u32*)sc.aux.p, status, (const u64*)sc.sums.p, out, out_cap, out_off);
     if (coop) {
       if (prof) prof_mark(e, st, &c1);
-      ggr_launch_decode_coop_write(st, n, s->d_blob, msg_id, in, in_off, flags, (const u32*)e->size[d].p, (const u32*)e->aux[d].p,
+      ggr_launch_decode_coop_write(st, n, s->d_blob, msg_id, in, in_off, flags, (const u32*)sc.size.p, (const u32*)sc.aux.p,
                                    status, out, out_off);
       if (prof) {
         prof_mark(e, st, &m3);
@@ -389,7 +426,7 @@ int ggr_encode_batch_dev(ggr_engine* e, const ggr_schema* s, int64_t n, const in
                          int32_t* status, uint32_t flags, void* stream) {
   if (!e) return GGR_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(e->mu);
-  return run_dev(e, s, true, n, msg_id, in, in_off, in_bytes, out, out_cap, out_off, status, flags,
+  return run_dev(e, s, e->dev_sc[0], true, n, msg_id, in, in_off, in_bytes, out, out_cap, out_off, status, flags,
                  stream ? (cudaStream_t)stream : e->stream);
 }
 int ggr_decode_batch_dev(ggr_engine* e, const ggr_schema* s, int64_t n, const int32_t* msg_id, const uint8_t* in,
@@ -397,11 +434,60 @@ int ggr_decode_batch_dev(ggr_engine* e, const ggr_schema* s, int64_t n, const in
                          int32_t* status, uint32_t flags, void* stream) {
   if (!e) return GGR_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(e->mu);
-  return run_dev(e, s, false, n, msg_id, in, in_off, in_bytes, out, out_cap, out_off, status, flags,
+  return run_dev(e, s, e->dev_sc[1], false, n, msg_id, in, in_off, in_bytes, out, out_cap, out_off, status, flags,
                  stream ? (cudaStream_t)stream : e->stream);
 }
 
-// Host-buffer entry points: H2D, kernels, D2H on the engine stream.
+// Host-buffer entry points.  The batch is cut into chunks of `chunk_items`; chunk c runs on slot
+// c % n_slots (own stream, staging buffers and scratch): H2D of its inputs, the kernels, D2H of its
+// offsets / statuses / total, and - once the host knows where the chunk's bytes go in the packed
+// output - D2H of the payload.  Up to n_slots chunks are in flight, so the copies of one chunk
+// overlap the kernels of the others (the caller's buffers should be pinned for that to happen).
+static bool slot_init(ggr_engine* e, Slot& sl) {
+  if (sl.st) return true;
+  if (!cuda_ok(e, cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking), "cudaStreamCreate") ||
+      !cuda_ok(e, cudaEventCreateWithFlags(&sl.ready, cudaEventDisableTiming), "cudaEventCreate") ||
+      !cuda_ok(e, cudaHostAlloc((void**)&sl.h_total, 64, cudaHostAllocDefault), "cudaHostAlloc"))
+    return false;
+  return true;
+}
+
+struct ChunkJob {
+  int64_t i0, nc;
+  uint64_t base, bytes;
+};
+
+static int chunk_issue(ggr_engine* e, const ggr_schema* s, Slot& sl, bool encode, const ChunkJob& j, const int32_t* msg_id,
+                       const uint8_t* in, const uint64_t* in_off, uint64_t cap, uint64_t* out_off, int32_t* status, uint32_t flags,
+                       bool copy_inputs) {
+  const uint64_t phase = j.base & 15ull;
+  if (!ensure(e, sl.d_in, (size_t)(j.bytes + phase + 128)) || !ensure(e, sl.d_off, (size_t)(j.nc + 1) * 8) ||
+      !ensure(e, sl.d_msg, (size_t)j.nc * 4) || !ensure(e, sl.d_out, (size_t)cap + 64) ||
+      !ensure(e, sl.d_out_off, (size_t)(j.nc + 1) * 8) || !ensure(e, sl.d_status, (size_t)j.nc * 4))
+    return GGR_ERR_CUDA;
+  sl.out_cap = cap;
+  cudaStream_t st = sl.st;
+  u8* d_in = (u8*)sl.d_in.p;
+  if (copy_inputs) {
+    if (!cuda_ok(e, cudaMemcpyAsync(d_in + phase, in + j.base, j.bytes, cudaMemcpyHostToDevice, st), "H2D payload") ||
+        !cuda_ok(e, cudaMemsetAsync(d_in + phase + j.bytes, 0, 64, st), "pad") ||
+        !cuda_ok(e, cudaMemcpyAsync(sl.d_off.p, in_off + j.i0, (size_t)(j.nc + 1) * 8, cudaMemcpyHostToDevice, st), "H2D offsets") ||
+        !cuda_ok(e, cudaMemcpyAsync(sl.d_msg.p, msg_id + j.i0, (size_t)j.nc * 4, cudaMemcpyHostToDevice, st), "H2D ids"))
+      return GGR_ERR_CUDA;
+  }
+  // offsets are shipped as given: the kernels address the payload as d_in - (base - phase) + offset
+  const u8* d_in_virtual = d_in + phase - j.base;
+  int rc = run_dev(e, s, sl.sc, encode, j.nc, (const int32_t*)sl.d_msg.p, d_in_virtual, (const uint64_t*)sl.d_off.p, j.bytes,
+                   (uint8_t*)sl.d_out.p, cap, (uint64_t*)sl.d_out_off.p, (int32_t*)sl.d_status.p, flags, st);
+  if (rc != GGR_SUCCESS) return rc;
+  if (!cuda_ok(e, cudaMemcpyAsync(out_off + j.i0, sl.d_out_off.p, (size_t)j.nc * 8, cudaMemcpyDeviceToHost, st), "D2H offsets") ||
+      !cuda_ok(e, cudaMemcpyAsync(sl.h_total, (const uint64_t*)sl.d_out_off.p + j.nc, 8, cudaMemcpyDeviceToHost, st), "D2H total") ||
+      !cuda_ok(e, cudaMemcpyAsync(status + j.i0, sl.d_status.p, (size_t)j.nc * 4, cudaMemcpyDeviceToHost, st), "D2H status") ||
+      !cuda_ok(e, cudaEventRecord(sl.ready, st), "event"))
+    return GGR_ERR_CUDA;
+  return GGR_SUCCESS;
+}
+
 static int run_host(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, const int32_t* msg_id, const uint8_t* in,
                     const uint64_t* in_off, uint8_t* out, uint64_t out_cap, uint64_t* out_off, int32_t* status, uint32_t flags) {
   if (!e || !s || n < 0 || !out_off) return GGR_ERR_INVALID_ARGUMENT;
@@ -412,36 +498,65 @@ static int run_host(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, 
   if (!msg_id || !in || !in_off || !status || (!out && out_cap)) return GGR_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(e->mu);
   cudaSetDevice(e->device);
-  uint64_t base = in_off[0], in_bytes = in_off[n] - base;
-  // offsets are shipped as given; the device copy of the payload starts at a 16-byte phase equal
-  // to base & 15 so that offsets need no rewriting
-  uint64_t phase = base & 15ull;
-  if (!ensure(e, e->d_in, (size_t)(in_bytes + phase + 128)) || !ensure(e, e->d_off, (size_t)(n + 1) * 8) ||
-      !ensure(e, e->d_msg, (size_t)n * 4) || !ensure(e, e->d_out, (size_t)out_cap + 64) ||
-      !ensure(e, e->d_out_off, (size_t)(n + 1) * 8) || !ensure(e, e->d_status, (size_t)n * 4))
-    return GGR_ERR_CUDA;
-  cudaStream_t st = e->stream;
-  u8* d_in = (u8*)e->d_in.p;
-  if (!cuda_ok(e, cudaMemcpyAsync(d_in + phase, in + base, in_bytes, cudaMemcpyHostToDevice, st), "H2D payload") ||
-      !cuda_ok(e, cudaMemsetAsync(d_in + phase + in_bytes, 0, 64, st), "pad") ||
-      !cuda_ok(e, cudaMemcpyAsync(e->d_off.p, in_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st), "H2D offsets") ||
-      !cuda_ok(e, cudaMemcpyAsync(e->d_msg.p, msg_id, (size_t)n * 4, cudaMemcpyHostToDevice, st), "H2D ids"))
-    return GGR_ERR_CUDA;
-  // kernels address the payload as d_in - (base - phase) + offset
-  const u8* d_in_virtual = d_in + phase - base;
-  int rc = run_dev(e, s, encode, n, (const int32_t*)e->d_msg.p, d_in_virtual, (const uint64_t*)e->d_off.p, in_bytes,
-                   (uint8_t*)e->d_out.p, out_cap, (uint64_t*)e->d_out_off.p, (int32_t*)e->d_status.p, flags, st);
-  if (rc != GGR_SUCCESS) return rc;
-  if (!cuda_ok(e, cudaMemcpyAsync(out_off, e->d_out_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H offsets") ||
-      !cuda_ok(e, cudaMemcpyAsync(status, e->d_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st), "D2H status") ||
-      !cuda_ok(e, cudaStreamSynchronize(st), "sync"))
-    return GGR_ERR_CUDA;
-  uint64_t total = out_off[n];
-  if (total > out_cap) return GGR_ERR_NO_SPACE;
-  if (total && (!cuda_ok(e, cudaMemcpyAsync(out, e->d_out.p, total, cudaMemcpyDeviceToHost, st), "D2H payload") ||
-                !cuda_ok(e, cudaStreamSynchronize(st), "sync")))
-    return GGR_ERR_CUDA;
-  return GGR_SUCCESS;
+  for (int i = 0; i < e->n_slots; i++)
+    if (!slot_init(e, e->slots[i])) return GGR_ERR_CUDA;
+  const int64_t CH = e->chunk_items;
+  const int64_t nchunks = (n + CH - 1) / CH;
+  const uint64_t total_in = in_off[n] - in_off[0];
+  auto job = [&](int64_t c) {
+    ChunkJob j;
+    j.i0 = c * CH;
+    j.nc = n - j.i0 < CH ? n - j.i0 : CH;
+    j.base = in_off[j.i0];
+    j.bytes = in_off[j.i0 + j.nc] - j.base;
+    return j;
+  };
+  // device capacity of a chunk: its share of the caller's capacity with headroom; a chunk that
+  // needs more is re-run alone with exactly what it needs
+  auto chunk_cap = [&](const ChunkJob& j) -> uint64_t {
+    double share = total_in ? (double)j.bytes / (double)total_in : 1.0;
+    uint64_t c = (uint64_t)((double)out_cap * share * 1.5) + (uint64_t)j.nc * 16 + 4096;
+    return c < out_cap + 64 ? c : out_cap + 64;
+  };
+  uint64_t produced = 0;
+  int rc_final = GGR_SUCCESS;
+  int64_t issued = 0, retired = 0;
+  while (retired < nchunks) {
+    while (issued < nchunks && issued - retired < e->n_slots && rc_final == GGR_SUCCESS) {
+      ChunkJob j = job(issued);
+      int rc = chunk_issue(e, s, e->slots[issued % e->n_slots], encode, j, msg_id, in, in_off, chunk_cap(j), out_off, status, flags, true);
+      if (rc != GGR_SUCCESS) rc_final = rc;
+      else issued++;
+    }
+    if (retired == issued) break;  // nothing in flight (an issue failed)
+    ChunkJob j = job(retired);
+    Slot& sl = e->slots[retired % e->n_slots];
+    if (!cuda_ok(e, cudaEventSynchronize(sl.ready), "sync")) return GGR_ERR_CUDA;
+    uint64_t total = *sl.h_total;
+    if (total > sl.out_cap && rc_final == GGR_SUCCESS) {
+      // rare: the chunk's output outgrew its share; its inputs are still on the device
+      int rc = chunk_issue(e, s, sl, encode, j, msg_id, in, in_off, total, out_off, status, flags, false);
+      if (rc != GGR_SUCCESS) rc_final = rc;
+      else if (!cuda_ok(e, cudaEventSynchronize(sl.ready), "sync")) return GGR_ERR_CUDA;
+      total = *sl.h_total;
+    }
+    if (rc_final == GGR_SUCCESS) {
+      if (produced + total > out_cap) {
+        rc_final = GGR_ERR_NO_SPACE;
+      } else {
+        if (total && !cuda_ok(e, cudaMemcpyAsync(out + produced, sl.d_out.p, total, cudaMemcpyDeviceToHost, sl.st), "D2H payload"))
+          return GGR_ERR_CUDA;
+        if (produced)
+          for (int64_t k = 0; k < j.nc; k++) out_off[j.i0 + k] += produced;
+        produced += total;
+      }
+    }
+    retired++;
+  }
+  for (int i = 0; i < e->n_slots; i++)
+    if (!cuda_ok(e, cudaStreamSynchronize(e->slots[i].st), "sync")) return GGR_ERR_CUDA;
+  out_off[n] = produced;
+  return rc_final;
 }
 
 int ggr_encode_batch(ggr_engine* e, const ggr_schema* s, int64_t n, const int32_t* msg_id, const uint8_t* json,

@@ -26,6 +26,7 @@ k_encode_coop_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const 
   // persistent warps: warp w of block b takes slots b * CE_WARPS + w, + gridDim.x * CE_WARPS, ...
   const long long total = list ? (long long)*list_n : n;
   const Tables T = ggr_tables(blob);
+  const u64 a0 = in_off[0];  // IR regions are laid out relative to the first offset of the batch
   for (long long slot = (long long)blockIdx.x * CE_WARPS + warp; slot < total; slot += (long long)gridDim.x * CE_WARPS) {
     const long long item = list ? (long long)list[slot] : slot;
     const u64 a = in_off[item], b = in_off[item + 1];
@@ -35,8 +36,8 @@ k_encode_coop_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const 
     res.size = 0;
     res.first = GGR_NIL;
     if (m >= 0 && (u32)m < n_msgs && b >= a && b - a <= (u64)CE_MAX_INPUT - 16u) {
-      const u64 node_off = (a >> 1) + 8ull * (u64)item;
-      const u32 cap = (u32)(((b >> 1) + 8ull * (u64)(item + 1)) - node_off);
+      const u64 node_off = ((a - a0) >> 1) + 8ull * (u64)item;
+      const u32 cap = (u32)((((b - a0) >> 1) + 8ull * (u64)(item + 1)) - node_off);
       const u8* base = in + (a & ~15ull);
       const u32 s0 = (u32)(a & 15ull);
       ok = ce_parse_item(S[warp], lut, T, (u32)m, base, s0, s0 + (u32)(b - a), ir + node_off * 16, cap, &res);

@@ -37,6 +37,8 @@ _ENGINE_PATHS = {
     "default": {},
     "per_thread": {"GGR_COOP_ENC": "0", "GGR_COOP": "0"},
     "coop_reply": {"GGR_COOP": "1"},
+    # host entry points cut into many small chunks over two slots: exercises the copy/compute pipeline
+    "small_chunks": {"GGR_CHUNK_ITEMS": "128", "GGR_SLOTS": "2"},
 }
 
 
