@@ -333,7 +333,7 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     alg = {"encode_parse": J_in, "encode_emit": W_out, "decode_size": W_in, "decode_write": J_out,
            "encode_scan": 0, "decode_scan": 0, "decode_coop_size": W_in, "decode_coop_write": W_in + J_out,
-           "encode_coop_parse": J_in, "encode_block_sums": 4 * n}
+           "encode_coop_parse": J_in, "encode_block_sums": 4 * n, "encode_coop_emit": W_out}
     kern = {}
     for k, (tot_ms, cnt) in prof.items():
         if cnt:

@@ -35,7 +35,7 @@ enum { TK_LBRACE = 1, TK_RBRACE = 2, TK_LBRACK = 3, TK_RBRACK = 4, TK_COLON = 5,
 // node classes: containers first; everything >= CC_NULL is finished in the leaf phase
 enum { CC_MSG = 0, CC_LIST = 1, CC_MAP = 2, CC_ENTRY = 3, CC_NULL = 4, CC_STR = 5, CC_BYTES = 6, CC_INT = 7, CC_FLOAT = 8, CC_TS = 9, CC_N = 10 };
 
-struct CNode {       // 20 bytes
+struct CNode {       // 28 bytes
   u16 tok;           // token index of the value
   u16 parent;
   u16 next;          // next sibling in emit order (lists: document order)
@@ -45,6 +45,8 @@ struct CNode {       // 20 bytes
   u16 msg;           // CC_MSG: message type
   u8 cls, depth;
   u32 body;          // containers: payload bytes accumulated from the children
+  u32 full;          // bytes of this node in its parent's payload (tag, length prefix, payload)
+  u32 off;           // output offset of the node, relative to the item
 };
 
 // Per-warp working set (shared memory).  MT tokens / MQ quotes / MN nodes; aux is 12 bits, so
@@ -320,6 +322,8 @@ GGR_DEV u32 ce_new_node(SH& S, u32 tok, u32 parent, u32 gfield, u32 emit, u32 cl
   nd.cls = (u8)cls;
   nd.depth = (u8)depth;
   nd.body = 0;
+  nd.full = 0;
+  nd.off = 0;
   S.node[idx] = nd;
   return idx;
 }
@@ -625,7 +629,13 @@ GGR_DEV void ce_leaf(SH& S, EncCtx& cx, u32 ni) {
       payload += 1 + varint_size((u64)secs);
     }
     node_store(cx.ir, ni, payload, sidx != GGR_NIL ? sidx : nidx, next, nd.emit, node_meta(N_MSG, 0, f.tag));
-    wp_atomic_add(&S.node[nd.parent].body, f.tag_len + varint_size(payload) + payload);
+    const u32 tsfull = f.tag_len + varint_size(payload) + payload;
+    S.node[ni].full = tsfull;
+    wp_atomic_add(&S.node[nd.parent].body, tsfull);
+    // the seconds / nanos nodes have no entry of their own in the node table: the emitter writes
+    // them together with this node
+    if (sidx != GGR_NIL) cx.ioff[sidx] = 0xFFFFFFFFu;
+    if (nidx != GGR_NIL) cx.ioff[nidx] = 0xFFFFFFFFu;
     return;
   }
   Leaf l;
@@ -656,7 +666,10 @@ GGR_DEV void ce_leaf(SH& S, EncCtx& cx, u32 ni) {
   }
   const bool live = in_list || (f.flags & GF_PRESENCE) || !l.zero;
   node_store(cx.ir, ni, l.a, l.b, next, nd.emit, live ? node_meta(l.type, l.flags, tag) : node_meta(N_SKIP, 0, 0));
-  if (live) wp_atomic_add(&S.node[nd.parent].body, tag_len + l.body);
+  if (live) {
+    S.node[ni].full = tag_len + l.body;
+    wp_atomic_add(&S.node[nd.parent].body, tag_len + l.body);
+  }
 }
 
 // T5, one lane: container `ni` is complete; write its IR node and add its size to the parent.
@@ -685,17 +698,30 @@ GGR_DEV void ce_close_container(SH& S, EncCtx& cx, u32 ni) {
     node_store(cx.ir, ni, nd.body, head, next, nd.emit, node_meta(N_LIST, 0, 0));
     full = nd.body;
   }
+  S.node[ni].full = full;
   wp_atomic_add(&S.node[nd.parent].body, full);
+}
+
+// T6, one lane: container `ni` knows its offset; hand out offsets to its children.
+template <class SH>
+GGR_DEV void ce_place_children(SH& S, u32 ni) {
+  const CNode nd = S.node[ni];
+  u32 pos = nd.off + (nd.full - nd.body);  // header: tag and length prefix, if any
+  for (u32 c = nd.head; c != CE_NIL; c = S.node[c].next) {
+    S.node[c].off = pos;
+    pos += S.node[c].full;
+  }
 }
 
 // One item, all 32 lanes.  Returns true when the item was handled (IR written, *res filled);
 // false leaves it to the per-thread parser.
 template <class SH>
 GGR_DEV bool ce_parse_item(SH& S, const CeLut& lut, const Tables& T, u32 root_msg, const u8* in, u32 start, u32 end, u8* ir,
-                           u32 ir_cap, EncResult* res) {
+                           u32* ioff, u32 ir_cap, EncResult* res) {
   const u32 lane = wp_lane();
   res->size = 0;
   res->first = GGR_NIL;
+  res->n_nodes = 0;
   if (end > CE_MAX_INPUT || ir_cap == 0) return false;
   if (end == start) return true;  // reflection.go:354: "" skips protojson
   WP_SYNC();  // persistent warps: nobody still reads the previous item's state
@@ -721,6 +747,7 @@ GGR_DEV bool ce_parse_item(SH& S, const CeLut& lut, const Tables& T, u32 root_ms
   cx.ir = ir;
   cx.ir_cap = ir_cap;
   cx.n_nodes = 0;
+  cx.ioff = ioff;
   if (lane == 0) {
     u32 r0 = ce_new_node(S, 0, CE_NIL, 0, 0, CC_MSG, 0);
     S.node[r0].msg = (u16)root_msg;
@@ -779,7 +806,151 @@ GGR_DEV bool ce_parse_item(SH& S, const CeLut& lut, const Tables& T, u32 root_ms
     }
     WP_SYNC();
   }
+  // T6: offsets, top-down (the root message has no header)
+  if (lane == 0) {
+    S.node[0].full = S.node[0].body;
+    S.node[0].off = 0;
+  }
+  WP_SYNC();
+  for (u32 d = 0; d < S.max_depth; d++) {
+    for (u32 i = lane; i < n; i += 32) {
+      const u32 c = S.node[i].cls;
+      if (S.node[i].depth == d && c <= CC_ENTRY) ce_place_children(S, i);
+    }
+    WP_SYNC();
+  }
+  for (u32 i = lane; i < n; i += 32) ioff[i] = S.node[i].off;
   res->size = S.node[0].body;
   res->first = ce_link(S.node[0].head);
+  res->n_nodes = S.n_node;
   return true;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Pass B, lock-step: every IR node of an item parsed above knows its output offset, so the lanes
+// write nodes independently (one lane per node); long plain strings are then copied by the whole
+// warp, 128 bytes per step.
+// ------------------------------------------------------------------------------------------------
+#define CE_LONG_STR 96u
+#define CE_LONG_MAX 32u
+struct CoopEmit {
+  u32 src[CE_LONG_MAX], dst[CE_LONG_MAX], len[CE_LONG_MAX];
+  u32 n;
+};
+
+// one lane: node `i` (not a long plain string's payload)
+GGR_DEV void ce_emit_node(CoopEmit& E, const u8* in, u32 end, const u8* ir, const u32* ioff, u32 i, u8* out8, u32 base) {
+  const U4 nd = node_load(ir, i);
+  const u32 type = nd.w & 0xFu, flags = (nd.w >> 4) & 0xFu, tag = nd.w >> 8;
+  if (type == N_SKIP || type == N_MAP || (type == N_LIST && !(flags & NF_PACKED))) return;
+  const u32 off = ioff[i];
+  if (off == 0xFFFFFFFFu) return;  // written together with its parent (Timestamp fields)
+  Wr w;
+  const u32 o = base + off;
+  w.init(out8 + (o & ~7u), o & 7u);
+  switch (type) {
+    case N_VARINT: {
+      if (tag) put_varint(w, tag);
+      u64 v = (u64)nd.x | ((u64)nd.y << 32);
+      if (flags & NF_RAWKEY) {
+        u32 kind = nd.z >> 20;
+        if (kind == GK_SINT32) v = zigzag32((u32)v);
+        else if (kind == GK_SINT64) v = zigzag64(v);
+      }
+      put_varint(w, v);
+      break;
+    }
+    case N_FIX32:
+      if (tag) put_varint(w, tag);
+      w.put(nd.x, 4);
+      break;
+    case N_FIX64:
+      if (tag) put_varint(w, tag);
+      w.put(nd.x, 4);
+      w.put(nd.y, 4);
+      break;
+    case N_STR:
+      if (tag) put_varint(w, tag);
+      put_varint(w, nd.y);
+      if (!(flags & NF_ESC) && nd.y >= CE_LONG_STR) {
+        u32 k = wp_atomic_add(&E.n, 1u);
+        if (k < CE_LONG_MAX) {  // payload left to the whole warp
+          E.src[k] = nd.x + 1u;
+          E.dst[k] = (w.pos - (o & 7u)) + o;
+          E.len[k] = nd.y;
+          break;
+        }
+      }
+      copy_string(w, in, nd.x, end, nd.y, (flags & NF_ESC) != 0);
+      break;
+    case N_BYTES: {
+      if (tag) put_varint(w, tag);
+      put_varint(w, nd.y);
+      StrIter it;
+      it.init(in, nd.x, end);
+      u32 n;
+      b64_run<true, Wr>(it, (flags & NF_URL) != 0, (flags & NF_PADDED) ? 0u : 1u, &w, &n);
+      break;
+    }
+    case N_MSG:
+    case N_ENTRY: {
+      if (tag) put_varint(w, tag);
+      put_varint(w, nd.x);
+      // Timestamp: its seconds / nanos children are written here
+      u32 c = nd.y;
+      if (c != GGR_NIL && ioff[c] == 0xFFFFFFFFu) {
+        while (c != GGR_NIL) {
+          U4 cn = node_load(ir, c);
+          put_varint(w, cn.w >> 8);
+          put_varint(w, (u64)cn.x | ((u64)cn.y << 32));
+          c = cn.z & 0xFFFFFu;
+        }
+      }
+      break;
+    }
+    case N_LIST:
+      put_varint(w, tag);
+      put_varint(w, nd.x);
+      break;
+    default: break;
+  }
+  w.finish();
+}
+
+// all lanes: copy len bytes in[src..) -> out8[dst..), 4 bytes per lane and step once dst is aligned
+GGR_DEV void ce_copy_coop(const u8* in, u32 src, u8* out8, u32 dst, u32 len) {
+  const u32 lane = wp_lane();
+  u32 head = (4u - (dst & 3u)) & 3u;
+  if (head > len) head = len;
+  if (lane < head) out8[dst + lane] = in[src + lane];
+  src += head;
+  dst += head;
+  len -= head;
+  const u32 words = len >> 2;
+  const u32 sh = (src & 3u) * 8u;
+  const u8* sa = in + (src & ~3u);
+  for (u32 k = lane; k < words; k += 32) {
+    u32 lo = ggr_ld4(sa + 4u * k);
+    u32 v = lo;
+    if (sh) {
+      u32 hi = ggr_ld4(sa + 4u * k + 4u);
+      v = (lo >> sh) | (hi << (32u - sh));
+    }
+    ggr_st4(out8 + dst + 4u * k, v);
+  }
+  const u32 tail = len & 3u;
+  if (lane < tail) out8[dst + 4u * words + lane] = in[src + 4u * words + lane];
+}
+
+// One item, all 32 lanes.  out8: 8-byte aligned base, base: offset of the item's first byte from it.
+GGR_DEV void ce_emit_item(CoopEmit& E, const u8* in, u32 end, const u8* ir, const u32* ioff, u32 n_nodes, u8* out8, u32 base) {
+  const u32 lane = wp_lane();
+  WP_SYNC();
+  if (lane == 0) E.n = 0;
+  WP_SYNC();
+  for (u32 i = 1 + lane; i < n_nodes; i += 32) ce_emit_node(E, in, end, ir, ioff, i, out8, base);
+  WP_SYNC();
+  const u32 nl = E.n < CE_LONG_MAX ? E.n : CE_LONG_MAX;
+  for (u32 k = 0; k < nl; k++) ce_copy_coop(in, E.src[k], out8, E.dst[k], E.len[k]);
 }

@@ -73,6 +73,7 @@ struct EncCtx {
   u32 end;       // end offset of this item
   u8* ir;
   u32 ir_cap, n_nodes;
+  u32* ioff;     // lock-step parser only: output offset of every IR node (relative to the item)
 };
 
 GGR_DEV u32 zigzag32(u32 v) { return (v << 1) ^ (u32)((i32)v >> 31); }
@@ -553,6 +554,7 @@ GGR_DEV int map_entry_done(EncCtx& cx, Frame& fr, const FieldD& mapf, u32 key_ki
 struct EncResult {
   u32 size;   // wire bytes of the item
   u32 first;  // first top-level node (GGR_NIL when the message is empty)
+  u32 n_nodes;  // lock-step parser: IR nodes written (with offsets, for the lock-step emitter); 0 otherwise
 };
 
 // `active` is false for lanes that have no item (they only take part in the convergence votes);
@@ -561,6 +563,7 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
                          bool active = true, unsigned mask = GGR_FULL_MASK) {
   res->size = 0;
   res->first = GGR_NIL;
+  res->n_nodes = 0;
   bool finished = !active;
   int result = GST_OK;
   // reflection.go:354: "" and "{}" skip protojson entirely
@@ -572,6 +575,7 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
   cx.ir = ir;
   cx.ir_cap = ir_cap;
   cx.n_nodes = 0;
+  cx.ioff = nullptr;
   Rd r;
   if (!finished) {
     r.init(in, start, end);

@@ -69,7 +69,7 @@ struct DevBuf {
 };
 
 struct Scratch {
-  DevBuf ir, size, aux, sums, pend;
+  DevBuf ir, size, aux, sums, pend, ioff, nn;
 };
 #define GGR_MAX_SLOTS 8
 struct Slot {
@@ -213,7 +213,7 @@ void ggr_engine_destroy(ggr_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   auto free_scratch = [](Scratch& sc) {
-    DevBuf* bufs[] = {&sc.ir, &sc.size, &sc.aux, &sc.sums, &sc.pend};
+    DevBuf* bufs[] = {&sc.ir, &sc.size, &sc.aux, &sc.sums, &sc.pend, &sc.ioff, &sc.nn};
     for (DevBuf* b : bufs)
       if (b->p) cudaFree(b->p);
   };
@@ -338,12 +338,15 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
   if (encode && !ensure(e, sc.ir, (size_t)in_bytes * 8 + (size_t)n * 128 + 256)) return GGR_ERR_CUDA;
   u32 n_msgs = (u32)s->cs.msg_names.size();
   const bool prof = e->profiling && e->ev_used + 8 <= 65536;
-  size_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+  size_t m0 = 0, m1 = 0, m2 = 0, m3 = 0, mx = 0;
+  bool have_mx = false;
   if (prof) prof_mark(e, st, &m0);
   if (encode) {
     if (e->use_coop_enc) {
       // lock-step parser first (one warp per item); what it leaves goes to the per-thread parser
-      if (!ensure(e, sc.pend, (size_t)n * 8 + 64)) return GGR_ERR_CUDA;
+      if (!ensure(e, sc.pend, (size_t)n * 8 + 64) || !ensure(e, sc.ioff, (size_t)in_bytes * 2 + (size_t)n * 32 + 64) ||
+          !ensure(e, sc.nn, (size_t)n * 4))
+        return GGR_ERR_CUDA;
       u32* counters = (u32*)sc.pend.p;  // [0] left by tier 1, [4] left by tier 2
       u32* pend1 = counters + 16;
       u32* pend2 = pend1 + n;
@@ -351,9 +354,9 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
       if (!cuda_ok(e, cudaMemsetAsync(counters, 0, 64, st), "memset")) return GGR_ERR_CUDA;
       if (prof) prof_mark(e, st, &m0);
       ggr_launch_encode_coop_parse(st, 0, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
-                                   (u32*)sc.aux.p, status, nullptr, nullptr, pend1, counters, e->sm_count);
+                                   (u32*)sc.aux.p, status, (u32*)sc.ioff.p, (u32*)sc.nn.p, nullptr, nullptr, pend1, counters, e->sm_count);
       ggr_launch_encode_coop_parse(st, 1, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
-                                   (u32*)sc.aux.p, status, pend1, counters, pend2, counters + 4, e->sm_count);
+                                   (u32*)sc.aux.p, status, (u32*)sc.ioff.p, (u32*)sc.nn.p, pend1, counters, pend2, counters + 4, e->sm_count);
       if (prof) prof_mark(e, st, &c0);
       ggr_launch_encode_parse(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
                               (u32*)sc.aux.p, status, (u64*)sc.sums.p, pend2, counters + 4);
@@ -374,7 +377,22 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
     k_scan_blocks<<<1, 1024, 0, st>>>((u64*)sc.sums.p, nb, out_off + n);
     if (prof) prof_mark(e, st, &m2);
     ggr_launch_encode_emit(st, (unsigned)nb, n, in, in_off, (const u8*)sc.ir.p, (const u32*)sc.size.p,
-                           (const u32*)sc.aux.p, status, (const u64*)sc.sums.p, out, out_cap, out_off);
+                           (const u32*)sc.aux.p, status, (const u64*)sc.sums.p, out, out_cap, out_off,
+                           e->use_coop_enc ? (const u32*)sc.nn.p : nullptr);
+    if (e->use_coop_enc) {
+      size_t x1 = 0;
+      if (prof) {
+        prof_mark(e, st, &mx);
+        have_mx = true;
+      }
+      ggr_launch_encode_coop_emit(st, n, in, in_off, (const u8*)sc.ir.p, (const u32*)sc.ioff.p, (const u32*)sc.nn.p,
+                                  (const u32*)sc.size.p, status, out, out_off, e->sm_count);
+      if (prof) {
+        prof_mark(e, st, &x1);
+        e->spans.push_back({10, mx, x1});
+      }
+      e->launches += 1;
+    }
   } else {
     // Reply side: the warp-cooperative kernels take every regular item; the per-thread kernels
     // then walk only what was left pending (irregular field order, maps, malformed wire, ...).
@@ -415,7 +433,7 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
     int base = encode ? 0 : 3;
     if (!(encode && e->use_coop_enc)) e->spans.push_back({base + 0, m0, m1});
     e->spans.push_back({base + 1, m1, m2});
-    e->spans.push_back({base + 2, m2, m3});
+    e->spans.push_back({base + 2, m2, have_mx ? mx : m3});
   }
   e->launches += 3;
   return cuda_ok(e, cudaGetLastError(), "kernel launch") ? GGR_SUCCESS : GGR_ERR_CUDA;

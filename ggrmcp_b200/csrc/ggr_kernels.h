@@ -11,12 +11,15 @@ void ggr_launch_block_sums(cudaStream_t st, unsigned nb, long long n, const uint
 // tier 0: every item (list == nullptr); tier 1: the items of `list`; persistent warps sized by sm_count
 void ggr_launch_encode_coop_parse(cudaStream_t st, int tier, long long n, const uint8_t* blob, uint32_t n_msgs,
                                   const int32_t* msg_id, const uint8_t* in, const uint64_t* in_off, uint8_t* ir, uint32_t* size,
-                                  uint32_t* first, int32_t* status, const uint32_t* list, const uint32_t* list_n,
-                                  uint32_t* pending, uint32_t* n_pending, int sm_count);
+                                  uint32_t* first, int32_t* status, uint32_t* ioff, uint32_t* nnodes, const uint32_t* list,
+                                  const uint32_t* list_n, uint32_t* pending, uint32_t* n_pending, int sm_count);
+void ggr_launch_encode_coop_emit(cudaStream_t st, long long n, const uint8_t* in, const uint64_t* in_off, const uint8_t* ir,
+                                 const uint32_t* ioff, const uint32_t* nnodes, const uint32_t* size, const int32_t* status,
+                                 uint8_t* out, const uint64_t* out_off, int sm_count);
 int ggr_encode_coop_init();  // opts the kernels into their dynamic shared memory sizes
 void ggr_launch_encode_emit(cudaStream_t st, unsigned nb, long long n, const uint8_t* in, const uint64_t* in_off, const uint8_t* ir,
                             const uint32_t* size, const uint32_t* first, int32_t* status, const uint64_t* block_prefix,
-                            uint8_t* out, uint64_t out_cap, uint64_t* out_off);
+                            uint8_t* out, uint64_t out_cap, uint64_t* out_off, const uint32_t* skip);
 void ggr_launch_decode_size(cudaStream_t st, unsigned nb, const uint8_t* blob, long long n, uint32_t n_msgs, const int32_t* msg_id,
                             const uint8_t* in, const uint64_t* in_off, uint32_t flags, uint32_t* size, uint32_t* mode,
                             int32_t* status, uint64_t* block_sums, int after_coop);

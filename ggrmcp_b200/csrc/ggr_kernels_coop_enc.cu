@@ -15,8 +15,9 @@ template <class SH>
 __global__ void __launch_bounds__(CE_WARPS * 32)
 k_encode_coop_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const i32* __restrict__ msg_id,
                     const u8* __restrict__ in, const u64* __restrict__ in_off, u8* __restrict__ ir, u32* __restrict__ size,
-                    u32* __restrict__ first, i32* __restrict__ status, const u32* __restrict__ list,
-                    const u32* __restrict__ list_n, u32* __restrict__ pending, u32* __restrict__ n_pending) {
+                    u32* __restrict__ first, i32* __restrict__ status, u32* __restrict__ ioff, u32* __restrict__ nnodes,
+                    const u32* __restrict__ list, const u32* __restrict__ list_n, u32* __restrict__ pending,
+                    u32* __restrict__ n_pending) {
   extern __shared__ __align__(16) unsigned char smem[];
   CeLut& lut = *reinterpret_cast<CeLut*>(smem);
   SH* S = reinterpret_cast<SH*>(smem + ((sizeof(CeLut) + 15) & ~(size_t)15));
@@ -35,23 +36,46 @@ k_encode_coop_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const 
     EncResult res;
     res.size = 0;
     res.first = GGR_NIL;
+    res.n_nodes = 0;
     if (m >= 0 && (u32)m < n_msgs && b >= a && b - a <= (u64)CE_MAX_INPUT - 16u) {
       const u64 node_off = ((a - a0) >> 1) + 8ull * (u64)item;
       const u32 cap = (u32)((((b - a0) >> 1) + 8ull * (u64)(item + 1)) - node_off);
       const u8* base = in + (a & ~15ull);
       const u32 s0 = (u32)(a & 15ull);
-      ok = ce_parse_item(S[warp], lut, T, (u32)m, base, s0, s0 + (u32)(b - a), ir + node_off * 16, cap, &res);
+      ok = ce_parse_item(S[warp], lut, T, (u32)m, base, s0, s0 + (u32)(b - a), ir + node_off * 16, ioff + node_off, cap, &res);
     }
     if (lane == 0) {
       if (ok) {
         size[item] = res.size;
         first[item] = res.first;
         status[item] = GST_OK;
+        nnodes[item] = res.n_nodes;
       } else {
         size[item] = 0;
+        nnodes[item] = 0;
         pending[atomicAdd(n_pending, 1u)] = (u32)item;
       }
     }
+  }
+}
+
+// Pass B for the items parsed above (nnodes != 0): persistent warps, one item per warp at a time.
+// Runs after k_encode_emit, which has written out_off[] for every item and skipped these.
+__global__ void __launch_bounds__(CE_WARPS * 32)
+k_encode_coop_emit(long long n, const u8* __restrict__ in, const u64* __restrict__ in_off, const u8* __restrict__ ir,
+                   const u32* __restrict__ ioff, const u32* __restrict__ nnodes, const u32* __restrict__ size,
+                   const i32* __restrict__ status, u8* __restrict__ out, const u64* __restrict__ out_off) {
+  __shared__ CoopEmit E[CE_WARPS];
+  const u32 warp = threadIdx.x >> 5;
+  const u64 a0 = in_off[0];
+  for (long long item = (long long)blockIdx.x * CE_WARPS + warp; item < n; item += (long long)gridDim.x * CE_WARPS) {
+    const u32 nn = nnodes[item];
+    if (nn <= 1 || size[item] == 0 || status[item] != GST_OK) continue;
+    const u64 a = in_off[item], b = in_off[item + 1];
+    const u64 node_off = ((a - a0) >> 1) + 8ull * (u64)item;
+    const u64 goff = out_off[item];
+    ce_emit_item(E[warp], in + (a & ~15ull), (u32)(a & 15ull) + (u32)(b - a), ir + node_off * 16, ioff + node_off, nn,
+                 out + (goff & ~7ull), (u32)(goff & 7ull));
   }
 }
 
@@ -70,18 +94,27 @@ int ggr_encode_coop_init() {
 
 void ggr_launch_encode_coop_parse(cudaStream_t st, int tier, long long n, const uint8_t* blob, uint32_t n_msgs,
                                   const int32_t* msg_id, const uint8_t* in, const uint64_t* in_off, uint8_t* ir, uint32_t* size,
-                                  uint32_t* first, int32_t* status, const uint32_t* list, const uint32_t* list_n,
-                                  uint32_t* pending, uint32_t* n_pending, int sm_count) {
+                                  uint32_t* first, int32_t* status, uint32_t* ioff, uint32_t* nnodes, const uint32_t* list,
+                                  const uint32_t* list_n, uint32_t* pending, uint32_t* n_pending, int sm_count) {
   if (tier == 0) {
     // 4 resident blocks per SM (shared memory); never more blocks than items / CE_WARPS
     long long want = (n + CE_WARPS - 1) / CE_WARPS, cap = (long long)sm_count * 4;
     unsigned nb = (unsigned)(want < cap ? want : cap);
     k_encode_coop_parse<CoopEnc><<<nb, CE_WARPS * 32, ce_smem_bytes<CoopEnc>(), st>>>(
-        blob, n, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first, status, list, list_n, pending, n_pending);
+        blob, n, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending);
   } else {
     // the list length lives on the device: one block per SM (shared memory), warps stride over the list
     unsigned nb = (unsigned)sm_count;
     k_encode_coop_parse<CoopEncBig><<<nb, CE_WARPS * 32, ce_smem_bytes<CoopEncBig>(), st>>>(
-        blob, n, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first, status, list, list_n, pending, n_pending);
+        blob, n, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending);
   }
+}
+
+void ggr_launch_encode_coop_emit(cudaStream_t st, long long n, const uint8_t* in, const uint64_t* in_off, const uint8_t* ir,
+                                 const uint32_t* ioff, const uint32_t* nnodes, const uint32_t* size, const int32_t* status,
+                                 uint8_t* out, const uint64_t* out_off, int sm_count) {
+  long long want = (n + CE_WARPS - 1) / CE_WARPS, cap = (long long)sm_count * 8;
+  unsigned nb = (unsigned)(want < cap ? want : cap);
+  k_encode_coop_emit<<<nb, CE_WARPS * 32, 0, st>>>(n, in, (const u64*)in_off, ir, ioff, nnodes, size, status, out,
+                                                   (const u64*)out_off);
 }

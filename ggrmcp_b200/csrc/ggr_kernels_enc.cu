@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(GGR_BLOCK) k_block_sums(long long n, const u32
 __global__ void __launch_bounds__(GGR_BLOCK)
 k_encode_emit(long long n, const u8* __restrict__ in, const u64* __restrict__ in_off, const u8* __restrict__ ir,
               const u32* __restrict__ size, const u32* __restrict__ first, i32* __restrict__ status,
-              const u64* __restrict__ block_prefix, u8* __restrict__ out, u64 out_cap, u64* __restrict__ out_off) {
+              const u64* __restrict__ block_prefix, u8* __restrict__ out, u64 out_cap, u64* __restrict__ out_off,
+              const u32* __restrict__ skip) {
   long long i = (long long)blockIdx.x * GGR_BLOCK + threadIdx.x;
   u32 sz = i < n ? size[i] : 0;
   u32 tot;
@@ -84,6 +85,8 @@ k_encode_emit(long long n, const u8* __restrict__ in, const u64* __restrict__ in
     if (sz != 0 && status[i] == GST_OK) {
       if (off + sz > out_cap) {
         status[i] = GST_NO_SPACE;
+      } else if (skip && skip[i] > 1u) {
+        // written by the lock-step emitter (k_encode_coop_emit)
       } else {
         active = true;
         a = in_off[i];
@@ -115,7 +118,7 @@ void ggr_launch_block_sums(cudaStream_t st, unsigned nb, long long n, const uint
 }
 void ggr_launch_encode_emit(cudaStream_t st, unsigned nb, long long n, const uint8_t* in, const uint64_t* in_off, const uint8_t* ir,
                             const uint32_t* size, const uint32_t* first, int32_t* status, const uint64_t* block_prefix,
-                            uint8_t* out, uint64_t out_cap, uint64_t* out_off) {
-  k_encode_emit<<<nb, GGR_BLOCK, 0, st>>>(n, in, (const u64*)in_off, ir, size, first, status, (const u64*)block_prefix, out, (u64)out_cap, (u64*)out_off);
+                            uint8_t* out, uint64_t out_cap, uint64_t* out_off, const uint32_t* skip) {
+  k_encode_emit<<<nb, GGR_BLOCK, 0, st>>>(n, in, (const u64*)in_off, ir, size, first, status, (const u64*)block_prefix, out, (u64)out_cap, (u64*)out_off, skip);
 }
 const void* ggr_kernel_encode_parse() { return (const void*)k_encode_parse; }

@@ -137,10 +137,10 @@ int ggr_synchronize(ggr_engine* e);
 /* Per-kernel device timing (CUDA events recorded around every kernel the engine launches).
  * slots: 0 encode_parse, 1 encode_scan, 2 encode_emit, 3 decode_size, 4 decode_scan, 5 decode_write,
  *        6 decode_coop_size, 7 decode_coop_write (the warp-cooperative reply-side kernels),
- *        8 encode_coop_parse (lock-step request-side parser), 9 encode_block_sums.
+ *        8 encode_coop_parse (lock-step request-side parser), 9 encode_block_sums, 10 encode_coop_emit.
  * ggr_profile_read synchronizes, adds up the elapsed milliseconds and launch counts since the
  * last read into ms[GGR_PROFILE_SLOTS] / launches[GGR_PROFILE_SLOTS], and resets the recorder. */
-#define GGR_PROFILE_SLOTS 10
+#define GGR_PROFILE_SLOTS 11
 int ggr_profile_enable(ggr_engine* e, int on);
 int ggr_profile_read(ggr_engine* e, double* ms, uint64_t* launches);
 

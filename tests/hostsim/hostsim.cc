@@ -100,14 +100,24 @@ struct CoopEncArgs {
   const u8* in;
   u32 start, end;
   u8* ir;
+  u32* ioff;
   u32 ir_cap;
   EncResult res[32];
   bool ok[32];
+  // pass B
+  CoopEmit* E;
+  u8* out8;
+  u32 base;
 };
 template <class SH>
 static void coop_enc_body(void* p, u32 lane) {
   CoopEncArgs<SH>* a = (CoopEncArgs<SH>*)p;
-  a->ok[lane] = ce_parse_item(*a->S, *a->lut, a->T, a->msg, a->in, a->start, a->end, a->ir, a->ir_cap, &a->res[lane]);
+  a->ok[lane] = ce_parse_item(*a->S, *a->lut, a->T, a->msg, a->in, a->start, a->end, a->ir, a->ioff, a->ir_cap, &a->res[lane]);
+}
+template <class SH>
+static void coop_emit_body(void* p, u32 lane) {
+  CoopEncArgs<SH>* a = (CoopEncArgs<SH>*)p;
+  ce_emit_item(*a->E, a->in, a->end, a->ir, a->ioff, a->res[0].n_nodes, a->out8, a->base);
 }
 template <class SH>
 static int hs_encode_coop_t(void* h, int msg, const uint8_t* json, uint32_t n, uint32_t in_off, uint32_t out_off, uint8_t* out,
@@ -136,6 +146,8 @@ static int hs_encode_coop_t(void* h, int msg, const uint8_t* json, uint32_t n, u
   a.start = in_off;
   a.end = in_off + n;
   a.ir = ir;
+  std::vector<u32> ioff(ir_cap + 8, 0xDEADBEEFu);
+  a.ioff = ioff.data();
   a.ir_cap = ir_cap;
   int werr = hw_run_warp(coop_enc_body<SH>, &a);
   *out_n = 0;
@@ -160,11 +172,33 @@ static int hs_encode_coop_t(void* h, int msg, const uint8_t* json, uint32_t n, u
   }
   std::vector<uint8_t> ob_raw(out_off + res.size + 64, 0xDD);
   uint8_t* ob = (uint8_t*)(((uintptr_t)ob_raw.data() + 15) & ~(uintptr_t)15);
-  Wr w;
-  w.init(ob, out_off);
-  encode_emit(in, in_off + n, ir, res.first, w);
-  w.finish();
-  if (w.pos != out_off + res.size) st = 100;
+  std::vector<uint8_t> before(ob, ob + out_off + res.size + 32);
+  // pass B twice: the per-thread emitter as reference, then the lock-step emitter
+  std::vector<uint8_t> ref(res.size + 16);
+  {
+    std::vector<uint8_t> rb_raw(out_off + res.size + 64, 0xDD);
+    uint8_t* rb = (uint8_t*)(((uintptr_t)rb_raw.data() + 15) & ~(uintptr_t)15);
+    Wr w;
+    w.init(rb, out_off);
+    encode_emit(in, in_off + n, ir, res.first, w);
+    w.finish();
+    if (w.pos != out_off + res.size) st = 100;
+    memcpy(ref.data(), rb + out_off, res.size);
+  }
+  static CoopEmit E;
+  memset(&E, 0xAB, sizeof E);
+  a.E = &E;
+  a.out8 = ob;
+  a.base = out_off;
+  if (res.size) {
+    werr = hw_run_warp(coop_emit_body<SH>, &a);
+    if (werr) st = 320 + werr;
+  }
+  for (uint32_t i = 0; i < out_off && st == GST_OK; i++)
+    if (ob[i] != before[i]) st = 101;
+  for (uint32_t i = out_off + res.size; i < out_off + res.size + 32 && st == GST_OK; i++)
+    if (ob[i] != before[i]) st = 102;
+  if (st == GST_OK && memcmp(ob + out_off, ref.data(), res.size) != 0) st = 103;  // the two emitters disagree
   memcpy(out, ob + out_off, res.size);
   *out_n = res.size;
   free(ir);
