@@ -1,25 +1,29 @@
-// ggr_coop.cuh - warp-cooperative reply side: one warp per item, lanes work on different fields.
+// ggr_coop.cuh - lock-step reply side: one warp per item, protobuf wire -> protojson text.
 //
-// The per-thread walker (ggr_decode.cuh) keeps one lane busy per message and the other 31 mostly
-// idle on divergent paths.  Here the warp first lays the message out as a table of field entries
-// in shared memory and then processes entries, not messages:
-//   P1 discover : level by level (root, its sub-messages, theirs, ...) one lane scans one message's
-//                 top-level tags - length-delimited payloads are skipped in O(1) - and appends
-//                 one entry per field, linked to its parent message
-//   P2 size     : one lane per entry computes the JSON size of leaf values (string escape scan,
-//                 digit counts, ...): the bulk of the byte work, evenly spread
-//   P3 totals   : bottom-up, one lane per message adds up its children
-//   P4 offsets  : top-down, one lane per message hands out output offsets to its children
-//   P5 write    : one lane per entry writes its text at its offset (write kernel only)
-// Only the regular case is handled (fields in declaration order, no maps, table fits); anything
-// else - including every malformed item - is left to the general per-thread kernels, which are
-// the reference for semantics.  The code is written lane-by-lane against a small shared-state
-// struct so that the host simulation can run the same phases with the lanes in sequence.
+// The per-thread walker (ggr_decode.cuh) runs 32 unrelated state machines per warp.  Here the 32
+// lanes work on ONE item:
+//   R1 discover : level by level (root, its sub-messages, theirs, ...) one lane scans one message's
+//                 top-level tags - length-delimited payloads are skipped in O(1) - and appends one
+//                 table entry per field occurrence, linked to its parent message
+//   R2 classes  : the whole warp builds a "plain text" bit mask of the item (16 bytes per lane and
+//                 step) so that a string needs no per-byte scan unless it holds a quote, a
+//                 backslash, a control or a non-ASCII byte; entries are bucketed by kind
+//   R3 sizes    : one lane per leaf computes the size of its JSON text; message entries add up
+//                 bottom-up by depth; offsets go top-down
+//   -- the entry table is saved, the batch-wide scan of the item sizes runs --
+//   R4 write    : one lane per entry writes its text at its offset; long plain strings are copied
+//                 by the whole warp
+// Only the regular case is handled (fields in declaration order, no maps, table fits): anything
+// else - including every malformed item - is left to the per-thread kernels, which own the
+// semantics.  All lanes call the *_item functions together (see ggr_warp.cuh; the CPU tests run
+// them on 32 fibers).
 #pragma once
 #include "ggr_decode.cuh"
+#include "ggr_warp.cuh"
 
 #define GGR_COOP_ENTRIES 320
-#define GGR_COOP_LEVELS 24
+#define GGR_COOP_DEPTH 24
+#define GGR_COOP_MAX_WIRE 8192u  /* larger items: per-thread kernels */
 #define GGR_MODE_COOP 2u
 #define GGR_MODE_PENDING 0xFFu
 
@@ -30,84 +34,157 @@
 #define CF_PACKED 0x0010u      /* packed repeated scalars: the entry holds the whole run */
 #define CF_FIRST 0x0020u       /* first field written inside its parent: no leading comma */
 #define CF_TIMESTAMP 0x0040u   /* google.protobuf.Timestamp leaf */
+#define CF_PLAIN 0x0080u       /* string without quote / backslash / control / non-ASCII bytes */
+#define CF_CLASS_SHIFT 8
+enum { DC_MSG = 0, DC_STR = 1, DC_BYTES = 2, DC_VARINT = 3, DC_FIXED = 4, DC_FLOAT = 5, DC_TS = 6, DC_PACKED = 7, DC_N = 8 };
 
-struct CoopEnt {            // 32 bytes
+struct CoopEnt {            // 32 bytes: saved between the passes as two 16-byte words
   u32 vpos;                 // position right after the tag (length prefix / scalar bytes start)
   u32 vend;                 // end of the value
-  u32 gfield;               // global field index (0xFFFFFFFF for the root)
-  u16 parent, next;         // parent message entry; next sibling (0xFFFF = none)
+  u32 body;                 // length-delimited values: position of the payload
   u32 size;                 // full text size: separator + name + brackets + value
-  u32 off;                  // output offset of the full text
-  u16 first_child, last_child;
-  u16 flags, level;
-  u32 msg;                  // CF_MSG: message type index
+  u32 off;                  // output offset of the full text (relative to the item)
+  u16 parent, next;         // parent message entry; next sibling (0xFFFF = none)
+  u16 fc_msg;               // CF_MSG: message type until the entry is scanned, then its first child
+  u16 gfield;               // global field index (0xFFFF for the root)
+  u16 flags, depth;
 };
+#define GGR_COOP_ROOT 0xFFFFu
+#define CE_CLASS(e) (((e).flags >> CF_CLASS_SHIFT) & 0xFu)
 
+#define GGR_COOP_LONG 96u
+#define GGR_COOP_LONG_MAX 32u
 struct CoopShared {
   CoopEnt ent[GGR_COOP_ENTRIES];
-  u32 n_ent;
-  u32 bail;                 // nonzero: leave the item to the general kernels
-  u32 level_beg[GGR_COOP_LEVELS + 2];
+  u16 order[GGR_COOP_ENTRIES];            // leaves bucketed by class
+  u16 dmask[GGR_COOP_MAX_WIRE / 16 + 2];  // per 16-byte chunk: bytes that are not plain text
+  u16 dpre[GGR_COOP_MAX_WIRE / 16 + 2];   // number of chunks with a nonzero mask before this one
+  u32 cls_cnt[DC_N], cls_cur[DC_N];
+  u32 n_ent, bail, n_leaf, max_depth, q_end;
+  u16 queue[GGR_COOP_ENTRIES];            // message entries to scan, level by level
 };
 
-GGR_DEV u32 coop_alloc(CoopShared& S) {
-#if defined(__CUDA_ARCH__)
-  return atomicAdd(&S.n_ent, 1u);
-#else
-  return S.n_ent++;
-#endif
+GGR_DEV u32 coop_class(const FieldD& f, bool ts, bool packed) {
+  if (packed) return DC_PACKED;
+  if (ts) return DC_TS;
+  switch (f.kind) {
+    case GK_STRING: return DC_STR;
+    case GK_BYTES: return DC_BYTES;
+    case GK_FLOAT: case GK_DOUBLE: return DC_FLOAT;
+    case GK_FIXED32: case GK_FIXED64: case GK_SFIXED32: case GK_SFIXED64: return DC_FIXED;
+    default: return DC_VARINT;
+  }
 }
 
-// P1, one lane: scan the top-level fields of message entry `me` and append its children.
+// ---- plain byte access for the discovery pass: tags and lengths are one or two bytes, a
+// streaming reader with a 16-byte chunk and a shift register costs more than it saves here ----
+GGR_DEV bool br_varint(const u8* b, u32& pos, u32 lim, u64* out) {
+  if (pos >= lim) return false;
+  u32 c = b[pos++];
+  if (c < 0x80u) {
+    *out = c;
+    return true;
+  }
+  u64 v = c & 0x7Fu;
+  for (int i = 1; i < 10; i++) {
+    if (pos >= lim) return false;
+    c = b[pos++];
+    if (i == 9 && c > 1) return false;
+    v |= (u64)(c & 0x7Fu) << (7 * i);
+    if (c < 0x80u) {
+      *out = v;
+      return true;
+    }
+  }
+  return false;
+}
+// skips one value of wire type wt (groups: not handled here -> false, the caller bails)
+GGR_DEV bool br_skip(const u8* b, u32& pos, u32 lim, u32 wt) {
+  u64 v;
+  switch (wt) {
+    case 0: return br_varint(b, pos, lim, &v);
+    case 1: if (lim - pos < 8) return false; pos += 8; return true;
+    case 5: if (lim - pos < 4) return false; pos += 4; return true;
+    case 2:
+      if (!br_varint(b, pos, lim, &v) || v > (u64)(lim - pos)) return false;
+      pos += (u32)v;
+      return true;
+    default: return false;
+  }
+}
+// Is the scalar at pos (wire type wt) the zero value of its kind?  (implicit presence: not written)
+GGR_DEV bool coop_wire_zero(const u8* b, u32 pos, u32 lim, u32 wt, bool* ok) {
+  *ok = true;
+  u64 v;
+  if (wt == 0 || wt == 2) {  // varint: zigzag(0) = 0, false = 0, enum 0; length-delimited: empty
+    if (!br_varint(b, pos, lim, &v)) { *ok = false; return false; }
+    if (wt == 2 && v > (u64)(lim - pos)) { *ok = false; return false; }
+    return v == 0;
+  }
+  const u32 k = wt == 5 ? 4u : 8u;  // float / double: the bit pattern decides (-0.0 is set)
+  if (lim - pos < k) { *ok = false; return false; }
+  u32 any = 0;
+  for (u32 j = 0; j < k; j++) any |= b[pos + j];
+  return any == 0;
+}
+
+// R1, one lane: scan the top-level fields of message entry `me` and append its children.
 GGR_DEV void coop_scan_message(CoopShared& S, const DecCtx& cx, u32 me) {
   const Tables& T = cx.T;
-  CoopEnt m = S.ent[me];
-  MsgD md = ggr_msg(T, m.msg);
-  if (md.wkt != GGR_WKT_NONE) { S.bail = 1; return; }
-  Rd r;
-  r.init(cx.in, m.vpos, m.vend);
-  if (m.gfield != 0xFFFFFFFFu) {  // a field entry starts at its length prefix
+  const u8* const in = cx.in;
+  const CoopEnt m = S.ent[me];
+  const MsgD md = ggr_msg(T, m.fc_msg);
+  S.ent[me].fc_msg = 0xFFFFu;  // from here on: first child
+  if (md.wkt != GGR_WKT_NONE || m.depth + 1u >= GGR_COOP_DEPTH) { S.bail = 1; return; }
+  const u32 lim = m.vend;
+  u32 pos = m.vpos;
+  if (m.gfield != GGR_COOP_ROOT) {  // a field entry starts at its length prefix
     u64 len;
-    if (!rd_varint(r, m.vend, &len) || len != (u64)(m.vend - r.pos)) { S.bail = 1; return; }
+    if (!br_varint(in, pos, lim, &len) || len != (u64)(lim - pos)) { S.bail = 1; return; }
   }
   i32 last_decl = -1;
   u32 open = 0;        // emit index + 1 of the repeated field currently being collected
   u32 oneofs = 0;
   u32 prev = 0xFFFFu;  // previous child entry
   bool any = false;
-  while (r.pos < m.vend) {
+  while (pos < lim) {
     u64 tag;
-    if (!rd_varint(r, m.vend, &tag)) { S.bail = 1; return; }
-    u64 num64 = tag >> 3;
-    u32 wt = (u32)(tag & 7);
-    if (num64 == 0 || num64 > 0x1FFFFFFFull || wt == 4 || wt > 5) { S.bail = 1; return; }
-    u32 num = (u32)num64;
-    i32 ei = find_field(T, md, num);
+    if (!br_varint(in, pos, lim, &tag)) { S.bail = 1; return; }
+    const u64 num64 = tag >> 3;
+    const u32 wt = (u32)(tag & 7);
+    if (num64 == 0 || num64 > 0x1FFFFFFFull || wt == 3 || wt == 4 || wt > 5) { S.bail = 1; return; }
+    const u32 num = (u32)num64;
+    const i32 ei = find_field(T, md, num);
     if (ei < 0) {
-      if (!rd_skip_value(r, m.vend, num, wt)) { S.bail = 1; return; }
+      if (!br_skip(in, pos, lim, wt)) { S.bail = 1; return; }
       continue;
     }
-    FieldD f = ggr_field(T, md.field_first + (u32)ei);
-    bool packed_in = (f.flags & GF_PACKABLE) && wt == 2;
+    const u32 gf = md.field_first + (u32)ei;
+    const FieldD f = ggr_field(T, gf);
+    const bool packed_in = (f.flags & GF_PACKABLE) && wt == 2;
     if (wt != f.wt && !packed_in) {
-      if (!rd_skip_value(r, m.vend, num, wt)) { S.bail = 1; return; }
+      if (!br_skip(in, pos, lim, wt)) { S.bail = 1; return; }
       continue;
     }
-    if (f.flags & GF_MAP) { S.bail = 1; return; }
-    u32 vpos = r.pos;
+    if ((f.flags & GF_MAP) || gf >= 0xFFFFu) { S.bail = 1; return; }
+    const u32 vpos = pos;
+    // value extent: [vpos, vend), payload of length-delimited values at body
+    u32 body = pos, vend = pos;
+    if (wt == 2) {
+      u64 len;
+      if (!br_varint(in, body, lim, &len) || len > (u64)(lim - body)) { S.bail = 1; return; }
+      vend = body + (u32)len;
+    } else {
+      if (!br_skip(in, vend, lim, wt)) { S.bail = 1; return; }
+    }
+    pos = vend;
     u32 flags = 0;
-    bool repeated = (f.flags & GF_REPEATED) != 0;
+    const bool repeated = (f.flags & GF_REPEATED) != 0;
     if (repeated) {
       flags |= CF_ARR_ELEM;
-      if (packed_in) {  // an empty packed run contributes nothing (and opens nothing)
-        Rd t = r;
-        u64 len;
-        if (!rd_varint(t, m.vend, &len) || len > (u64)(m.vend - t.pos)) { S.bail = 1; return; }
-        if (len == 0) {
-          if (open != (u32)ei + 1 && (i32)f.decl_index <= last_decl) { S.bail = 1; return; }
-          r = t;
-          continue;
-        }
+      if (packed_in && vend == body) {  // an empty packed run contributes nothing (and opens nothing)
+        if (open != (u32)ei + 1 && (i32)f.decl_index <= last_decl) { S.bail = 1; return; }
+        continue;
       }
       if (open != (u32)ei + 1) {
         if ((i32)f.decl_index <= last_decl) { S.bail = 1; return; }
@@ -128,58 +205,97 @@ GGR_DEV void coop_scan_message(CoopShared& S, const DecCtx& cx, u32 me) {
       }
       last_decl = (i32)f.decl_index;
       if (f.kind != GK_MESSAGE && !(f.flags & GF_PRESENCE)) {
-        // implicit presence: zero values are not written
-        Rd t = r;
-        bool z;
-        if (f.wt == 2) {
-          u64 len;
-          if (!rd_varint(t, m.vend, &len) || len > (u64)(m.vend - t.pos)) { S.bail = 1; return; }
-          z = len == 0;
-        } else {
-          Cnt c;
-          c.pos = 0;
-          if (scalar_value<Cnt, false>(c, cx, t, m.vend, f.kind, f.child, false, &z) != GST_OK) { S.bail = 1; return; }
-        }
-        if (z) {
-          if (!rd_skip_value(r, m.vend, num, wt)) { S.bail = 1; return; }
-          continue;
-        }
+        bool ok;
+        const bool z = coop_wire_zero(in, vpos, lim, wt, &ok);
+        if (!ok) { S.bail = 1; return; }
+        if (z) continue;  // implicit presence: the zero value is not written
       }
     }
-    if (!rd_skip_value(r, m.vend, num, wt)) { S.bail = 1; return; }
-    u32 slot = coop_alloc(S);
+    const u32 slot = wp_atomic_add(&S.n_ent, 1u);
     if (slot >= GGR_COOP_ENTRIES) { S.bail = 1; return; }
     CoopEnt e;
     e.vpos = vpos;
-    e.vend = r.pos;
-    e.gfield = md.field_first + (u32)ei;
+    e.vend = vend;
+    e.gfield = (u16)gf;
     e.parent = (u16)me;
     e.next = 0xFFFFu;
     e.size = 0;
     e.off = 0;
-    e.first_child = e.last_child = 0xFFFFu;
-    e.level = (u16)(m.level + 1);
-    e.msg = 0;
+    e.fc_msg = 0xFFFFu;
+    e.depth = (u16)(m.depth + 1);
+    e.body = body;
     if (!any) flags |= CF_FIRST;
+    bool ts = false;
     if (f.kind == GK_MESSAGE) {
-      MsgD cd = ggr_msg(T, (u32)f.child);
-      if (cd.wkt == GGR_WKT_TIMESTAMP) flags |= CF_TIMESTAMP;
-      else if (cd.wkt != GGR_WKT_NONE) { S.bail = 1; return; }
-      else {
+      const u32 w = ggr_msg(T, (u32)f.child).wkt;
+      if (w == GGR_WKT_TIMESTAMP) {
+        flags |= CF_TIMESTAMP;
+        ts = true;
+      } else if (w != GGR_WKT_NONE || (u32)f.child >= 0xFFFFu) {
+        S.bail = 1;
+        return;
+      } else {
         flags |= CF_MSG;
-        e.msg = (u32)f.child;
+        e.fc_msg = (u16)f.child;
       }
     }
-    e.flags = (u16)flags;
+    const u32 cls = (flags & CF_MSG) ? DC_MSG : coop_class(f, ts, (flags & CF_PACKED) != 0);
+    e.flags = (u16)(flags | (cls << CF_CLASS_SHIFT));
     S.ent[slot] = e;
-    if (prev == 0xFFFFu) S.ent[me].first_child = (u16)slot;
+    if (flags & CF_MSG) S.queue[wp_atomic_add(&S.q_end, 1u)] = (u16)slot;
+    if (prev == 0xFFFFu) S.ent[me].fc_msg = (u16)slot;
     else S.ent[prev].next = (u16)slot;
     prev = slot;
     any = true;
   }
-  if (r.pos != m.vend) { S.bail = 1; return; }
   if (open && prev != 0xFFFFu) S.ent[prev].flags |= CF_ARR_LAST;
-  S.ent[me].last_child = (u16)prev;
+  wp_atomic_max(&S.max_depth, (u32)m.depth + 1u);
+}
+
+// flags in bit 7 of every byte -> 4 contiguous bits
+GGR_DEV u32 coop_pack4(u32 x) { return (((x >> 7) * 0x00204081u) >> 21) & 0xFu; }
+// per byte of w (bit 7 flags): not plain JSON string text (< 0x20, >= 0x80, '"', '\\')
+GGR_DEV u32 coop_dirty_flags(u32 w) {
+  const u32 lo7 = w & 0x7F7F7F7Fu;
+  u32 ge20 = lo7 + 0x60606060u;               // bit 7: (byte & 0x7F) >= 0x20
+  u32 q = (lo7 ^ 0x22222222u) + 0x7F7F7F7Fu;  // bit 7: (byte & 0x7F) != '"'
+  u32 b = (lo7 ^ 0x5C5C5C5Cu) + 0x7F7F7F7Fu;  // bit 7: (byte & 0x7F) != '\\'
+  return (w | ~(ge20 & q & b)) & 0x80808080u;
+}
+
+// R2, all lanes: dmask / dpre over the item's bytes [start, end)
+GGR_DEV void coop_plain_masks(CoopShared& S, const u8* in, u32 start, u32 end) {
+  const u32 lane = wp_lane();
+  const u32 lt = (1u << lane) - 1u;
+  const u32 nchunks = (end + 15u) >> 4;
+  u32 base = 0;
+  for (u32 cb = 0; cb < nchunks; cb += 32) {
+    const u32 ci = cb + lane;
+    u32 D = 0;
+    if (ci < nchunks) {
+      const U4 v = ggr_ld16(in + (ci << 4));
+      D = coop_pack4(coop_dirty_flags(v.x)) | (coop_pack4(coop_dirty_flags(v.y)) << 4) | (coop_pack4(coop_dirty_flags(v.z)) << 8) |
+          (coop_pack4(coop_dirty_flags(v.w)) << 12);
+    }
+    const u32 any = WP_BALLOT(D != 0);
+    if (ci < nchunks) {
+      S.dmask[ci] = (u16)D;
+      S.dpre[ci] = (u16)(base + wp_popc(any & lt));
+    }
+    base += wp_popc(any);
+  }
+  if (lane == 0) S.dpre[nchunks] = (u16)base;
+  WP_SYNC();
+}
+// no byte of [s, e) needs escaping or validation (s < e, within the masks' range)
+GGR_DEV bool coop_is_plain(const CoopShared& S, u32 s, u32 e) {
+  const u32 c0 = s >> 4, c1 = (e - 1u) >> 4;
+  u32 first = (u32)S.dmask[c0] & (0xFFFFu << (s & 15u));
+  const u32 lastmask = 0xFFFFu >> (15u - ((e - 1u) & 15u));
+  if (c0 == c1) return (first & lastmask) == 0;
+  if (first & 0xFFFFu) return false;
+  if ((u32)S.dmask[c1] & lastmask) return false;
+  return S.dpre[c1] == S.dpre[c0 + 1];
 }
 
 // Text that surrounds an entry's value: separator, key, brackets.
@@ -232,18 +348,18 @@ GGR_DEV int coop_leaf_value(W& w, const DecCtx& cx, const CoopEnt& e, const Fiel
   return scalar_value<W, true>(w, cx, r, e.vend, f.kind, f.child, false, &z);
 }
 
-// P2, one lane: size of entry e (leaf: full text; message: prefix/suffix only, children added in P3)
-GGR_DEV void coop_size_entry(CoopShared& S, const DecCtx& cx, u32 ei) {
-  CoopEnt e = S.ent[ei];
-  if (e.gfield == 0xFFFFFFFFu) {  // root: "{" ... "}"
-    S.ent[ei].size = 2;
-    return;
-  }
-  FieldD f = ggr_field(cx.T, e.gfield);
+// R3, one lane: size of leaf entry ei (full text) added to its parent
+GGR_DEV void coop_size_leaf(CoopShared& S, const DecCtx& cx, u32 ei, bool have_masks) {
+  const CoopEnt e = S.ent[ei];
+  const FieldD f = ggr_field(cx.T, e.gfield);
   u32 n = coop_prefix_len(cx, e, f.name_len);
   if (e.flags & CF_ARR_LAST) n += 1;
-  if (e.flags & CF_MSG) {
-    n += 2;
+  const u32 cls = CE_CLASS(e);
+  if (cls == DC_STR && have_masks && (e.vend == e.body || coop_is_plain(S, e.body, e.vend))) {
+    S.ent[ei].flags = (u16)(e.flags | CF_PLAIN);
+    n += 2u + (e.vend - e.body);
+  } else if (cls == DC_BYTES) {
+    n += 2u + ((e.vend - e.body + 2u) / 3u) * 4u;
   } else {
     Cnt c;
     c.pos = 0;
@@ -254,130 +370,226 @@ GGR_DEV void coop_size_entry(CoopShared& S, const DecCtx& cx, u32 ei) {
     n += c.pos;
   }
   S.ent[ei].size = n;
+  wp_atomic_add(&S.ent[e.parent].size, n);
 }
 
-// P3, one lane: message entry adds the sizes of its children (children are complete: deeper level)
-GGR_DEV void coop_total_message(CoopShared& S, u32 me) {
-  u32 sum = 0;
-  for (u32 c = S.ent[me].first_child; c != 0xFFFFu; c = S.ent[c].next) sum += S.ent[c].size;
-  S.ent[me].size += sum;
+// R3, one lane: message entry `me` has the sizes of all its children; add its own text and
+// pass the total up
+GGR_DEV void coop_close_message(CoopShared& S, const DecCtx& cx, u32 me) {
+  const CoopEnt m = S.ent[me];
+  u32 n = 2;  // { }
+  if (m.gfield != GGR_COOP_ROOT) {
+    const FieldD f = ggr_field(cx.T, m.gfield);
+    n += coop_prefix_len(cx, m, f.name_len);
+    if (m.flags & CF_ARR_LAST) n += 1;
+  }
+  const u32 total = m.size + n;
+  S.ent[me].size = total;
+  if (m.gfield != GGR_COOP_ROOT) wp_atomic_add(&S.ent[m.parent].size, total);
 }
 
-// P4, one lane: message entry hands out offsets to its children
+// R3, one lane: message entry hands out offsets to its children
 GGR_DEV void coop_offsets_message(CoopShared& S, const DecCtx& cx, u32 me) {
-  CoopEnt m = S.ent[me];
+  const CoopEnt m = S.ent[me];
   u32 pos = m.off;
-  if (m.gfield != 0xFFFFFFFFu) {
+  if (m.gfield != GGR_COOP_ROOT) {
     FieldD f = ggr_field(cx.T, m.gfield);
     pos += coop_prefix_len(cx, m, f.name_len);
   }
   pos += 1;  // '{'
-  for (u32 c = m.first_child; c != 0xFFFFu; c = S.ent[c].next) {
+  for (u32 c = m.fc_msg; c != 0xFFFFu; c = S.ent[c].next) {
     S.ent[c].off = pos;
     pos += S.ent[c].size;
   }
 }
 
-// P5, one lane: write entry e
-GGR_DEV int coop_write_entry(CoopShared& S, const DecCtx& cx, u32 ei, u8* out) {
-  CoopEnt e = S.ent[ei];
-  Wr w;
-  if (e.gfield == 0xFFFFFFFFu) {
-    w.init(out, e.off);
-    w.put1('{');
-    w.finish();
-    w.init(out, e.off + e.size - 1);
-    w.put1('}');
-    w.finish();
+// ---- R4: the item's text is assembled in shared memory, then copied out with aligned 16-byte
+// stores.  Entries are small (a key and a few dozen bytes), so a streaming writer with aligned
+// groups would spend its time on the unaligned edges of every entry; plain byte stores into
+// shared memory have no edges.
+#define GGR_COOP_STAGE 8192u /* items with more text than this: per-thread kernels */
+struct CoopStage {
+  u8 buf[GGR_COOP_STAGE + 48];  // [pad, pad + size): pad = destination address & 15
+  u32 lsrc[GGR_COOP_LONG_MAX], ldst[GGR_COOP_LONG_MAX], llen[GGR_COOP_LONG_MAX];
+  u32 n_long, bad;
+};
+// R4, one lane: text of entry e into the staging buffer at pad + e.off
+GGR_DEV int coop_write_entry(CoopStage& E, const DecCtx& cx, const CoopEnt& e, u32 pad) {
+  Sw w;
+  w.init(E.buf, pad + e.off);
+  if (e.gfield == GGR_COOP_ROOT) {
+    E.buf[pad + e.off] = '{';
+    E.buf[pad + e.off + e.size - 1] = '}';
     return GST_OK;
   }
-  FieldD f = ggr_field(cx.T, e.gfield);
-  w.init(out, e.off);
-  coop_put_prefix(w, cx, e, f);
+  const FieldD f = ggr_field(cx.T, e.gfield);
+  if (!(e.flags & CF_FIRST)) {
+    w.put1(',');
+    if (cx.flags & GGR_F_COMMA_SPACE) w.put1(' ');
+  }
+  if (!(e.flags & CF_ARR_ELEM) || (e.flags & CF_ARR_FIRST)) {
+    const u8* nm = cx.T.pool + f.name_off;
+    for (u32 j = 0; j < f.name_len; j++) w.put1(nm[j]);
+  }
+  if (e.flags & CF_ARR_FIRST) w.put1('[');
+  const u32 endpos = pad + e.off + e.size;
   if (e.flags & CF_MSG) {
     w.put1('{');
-    w.finish();
-    u32 tail = (e.flags & CF_ARR_LAST) ? 2u : 1u;
-    w.init(out, e.off + e.size - tail);
-    w.put1('}');
-    if (e.flags & CF_ARR_LAST) w.put1(']');
-    w.finish();
+    if (e.flags & CF_ARR_LAST) {
+      E.buf[endpos - 2] = '}';
+      E.buf[endpos - 1] = ']';
+    } else {
+      E.buf[endpos - 1] = '}';
+    }
     return GST_OK;
   }
-  int st = coop_leaf_value(w, cx, e, f);
+  int st = GST_OK;
+  if (e.flags & CF_PLAIN) {
+    const u32 len = e.vend - e.body;
+    w.put1('"');
+    bool handed = false;
+    if (len >= GGR_COOP_LONG) {
+      const u32 k = wp_atomic_add(&E.n_long, 1u);
+      if (k < GGR_COOP_LONG_MAX) {  // payload left to the whole warp
+        E.lsrc[k] = e.body;
+        E.ldst[k] = w.pos;
+        E.llen[k] = len;
+        handed = true;
+      }
+    }
+    if (!handed) {
+      const u8* src = cx.in + e.body;
+      for (u32 j = 0; j < len; j++) E.buf[w.pos + j] = src[j];
+    }
+    w.pos += len;
+    w.put1('"');
+  } else {
+    st = coop_leaf_value(w, cx, e, f);
+  }
   if (e.flags & CF_ARR_LAST) w.put1(']');
-  w.finish();
-  if (st == GST_OK && w.pos != e.off + e.size) st = GST_INTERNAL;
+  if (st == GST_OK && w.pos != endpos) st = GST_INTERNAL;
   return st;
 }
 
-// The whole item, driven by `nlanes` lanes; `lane` is this lane's index.  On the device all 32
-// lanes of a warp call this together (SYNC = __syncwarp); the host simulation calls the phase
-// helpers lane after lane instead (see coop_run_host below).
-#if defined(__CUDA_ARCH__)
-#define GGR_COOP_SYNC() __syncwarp()
-#else
-#define GGR_COOP_SYNC() do { } while (0)
-#endif
-
-// Returns true when the item was handled; *size gets the output size.  With out != nullptr the
-// text is also written at out[out_off ..).
-GGR_DEV bool coop_decode_item(CoopShared& S, const DecCtx& cx, u32 root_msg, u32 start, u32 end, u32 lane, u32 nlanes,
-                              u8* out, u32 out_off, u32* size, int* wstatus) {
+// Size pass of one item, all lanes.  Returns true when the item was handled: *size is its text
+// size and, when `save` != nullptr, the entry table (n entries, *n_out) has been stored there for
+// the write pass.
+GGR_DEV bool coop_size_item(CoopShared& S, const DecCtx& cx, u32 root_msg, u32 start, u32 end, U4* save, u32* n_out, u32* size) {
+  const u32 lane = wp_lane();
+  *size = 0;
+  *n_out = 0;
+  if (end > GGR_COOP_MAX_WIRE || root_msg >= 0xFFFFu) return false;
+  WP_SYNC();  // persistent warps: nobody still reads the previous item's state
   if (lane == 0) {
     S.n_ent = 1;
     S.bail = 0;
+    S.max_depth = 0;
     CoopEnt r0;
-    r0.vpos = start; r0.vend = end; r0.gfield = 0xFFFFFFFFu; r0.parent = 0xFFFFu; r0.next = 0xFFFFu;
-    r0.size = 0; r0.off = out_off; r0.first_child = r0.last_child = 0xFFFFu; r0.flags = CF_MSG | CF_FIRST; r0.level = 0;
-    r0.msg = root_msg;
+    r0.vpos = start; r0.vend = end; r0.gfield = GGR_COOP_ROOT; r0.parent = 0xFFFFu; r0.next = 0xFFFFu;
+    r0.size = 0; r0.off = 0; r0.fc_msg = (u16)root_msg; r0.depth = 0;
+    r0.flags = (u16)(CF_MSG | CF_FIRST | (DC_MSG << CF_CLASS_SHIFT));
+    r0.body = start;
     S.ent[0] = r0;
-    S.level_beg[0] = 0;
-    S.level_beg[1] = 1;
+    S.queue[0] = 0;
+    S.q_end = 1;
   }
-  GGR_COOP_SYNC();
-  // P1
-  u32 nlev = 0;
+  WP_SYNC();
+  // R1: level by level
+  u32 qb = 0;
   for (;;) {
-    u32 b = S.level_beg[nlev], e = S.level_beg[nlev + 1];
-    if (b == e) break;
-    for (u32 i = b + lane; i < e; i += nlanes)
-      if (S.ent[i].flags & CF_MSG) coop_scan_message(S, cx, i);
-    GGR_COOP_SYNC();
+    const u32 qe = S.q_end;
+    if (qb == qe) break;
+    WP_SYNC();
+    for (u32 i = qb + lane; i < qe; i += 32) coop_scan_message(S, cx, S.queue[i]);
+    WP_SYNC();
     if (S.bail) return false;
-    nlev++;
-    if (lane == 0) S.level_beg[nlev + 1] = S.n_ent < GGR_COOP_ENTRIES ? S.n_ent : GGR_COOP_ENTRIES;
-    GGR_COOP_SYNC();
-    if (nlev >= GGR_COOP_LEVELS) return false;
+    qb = qe;
   }
-  u32 n = S.n_ent;
-  if (n > GGR_COOP_ENTRIES) return false;
-  // P2
-  for (u32 i = lane; i < n; i += nlanes) coop_size_entry(S, cx, i);
-  GGR_COOP_SYNC();
+  const u32 n = S.n_ent;
+  // R2: plain-text masks, leaves bucketed by class
+  coop_plain_masks(S, cx.in, start, end);
+  if (lane < DC_N) S.cls_cnt[lane] = 0;
+  WP_SYNC();
+  for (u32 i = lane; i < n; i += 32) {
+    const u32 c = CE_CLASS(S.ent[i]);
+    if (c != DC_MSG) wp_atomic_add(&S.cls_cnt[c], 1u);
+  }
+  WP_SYNC();
+  if (lane == 0) {
+    u32 run = 0;
+    for (u32 c = 0; c < DC_N; c++) {
+      S.cls_cur[c] = run;
+      run += S.cls_cnt[c];
+    }
+    S.n_leaf = run;
+  }
+  WP_SYNC();
+  for (u32 i = lane; i < n; i += 32) {
+    const u32 c = CE_CLASS(S.ent[i]);
+    if (c != DC_MSG) S.order[wp_atomic_add(&S.cls_cur[c], 1u)] = (u16)i;
+  }
+  WP_SYNC();
+  // R3: leaf sizes, then messages bottom-up, then offsets top-down
+  const u32 n_leaf = S.n_leaf;
+  for (u32 k = lane; k < n_leaf; k += 32) coop_size_leaf(S, cx, S.order[k], true);
+  WP_SYNC();
   if (S.bail) return false;
-  // P3 bottom-up
-  for (i32 l = (i32)nlev - 1; l >= 0; l--) {
-    u32 b = S.level_beg[l], e = S.level_beg[l + 1];
-    for (u32 i = b + lane; i < e; i += nlanes)
-      if (S.ent[i].flags & CF_MSG) coop_total_message(S, i);
-    GGR_COOP_SYNC();
+  const u32 maxd = S.max_depth;
+  for (u32 dd = 0; dd <= maxd; dd++) {
+    const u32 d = maxd - dd;
+    for (u32 i = lane; i < n; i += 32)
+      if (S.ent[i].depth == d && (S.ent[i].flags & CF_MSG)) coop_close_message(S, cx, i);
+    WP_SYNC();
   }
   *size = S.ent[0].size;
-  if (!out) return true;
-  // P4 top-down
-  for (u32 l = 0; l < nlev; l++) {
-    u32 b = S.level_beg[l], e = S.level_beg[l + 1];
-    for (u32 i = b + lane; i < e; i += nlanes)
-      if (S.ent[i].flags & CF_MSG) coop_offsets_message(S, cx, i);
-    GGR_COOP_SYNC();
+  if (S.ent[0].size > GGR_COOP_STAGE) return false;  // the write pass stages the text in shared memory
+  if (!save) return true;
+  for (u32 d = 0; d <= maxd; d++) {
+    for (u32 i = lane; i < n; i += 32)
+      if (S.ent[i].depth == d && (S.ent[i].flags & CF_MSG)) coop_offsets_message(S, cx, i);
+    WP_SYNC();
   }
-  // P5
-  int st = GST_OK;
-  for (u32 i = lane; i < n; i += nlanes) {
-    int s2 = coop_write_entry(S, cx, i, out);
-    if (s2 != GST_OK) st = s2;
-  }
-  *wstatus = st;
+  // save the table: two 16-byte stores per entry
+  const U4* src = reinterpret_cast<const U4*>(S.ent);
+  for (u32 i = lane; i < 2 * n; i += 32) save[i] = src[i];
+  *n_out = n;
   return true;
+}
+
+// Write pass of one item, all lanes: `tab` holds the n entries the size pass saved; the text goes
+// to dst[0, size).
+GGR_DEV int coop_write_item(CoopStage& E, const DecCtx& cx, const U4* tab, u32 n, u8* dst, u32 size) {
+  const u32 lane = wp_lane();
+#if defined(__CUDA_ARCH__)
+  const u32 pad = (u32)(reinterpret_cast<unsigned long long>(dst) & 15ull);
+#else
+  const u32 pad = (u32)((uintptr_t)dst & 15u);
+#endif
+  u8* out16 = dst - pad;
+  WP_SYNC();  // persistent warps: the previous item has been copied out
+  if (lane == 0) {
+    E.n_long = 0;
+    E.bad = 0;
+  }
+  WP_SYNC();
+  for (u32 i = lane; i < n; i += 32) {
+    const U4 a = tab[2 * i], b = tab[2 * i + 1];
+    CoopEnt e;
+    e.vpos = a.x; e.vend = a.y; e.body = a.z; e.size = a.w;
+    e.off = b.x; e.parent = (u16)b.y; e.next = (u16)(b.y >> 16);
+    e.fc_msg = (u16)b.z; e.gfield = (u16)(b.z >> 16);
+    e.flags = (u16)b.w; e.depth = (u16)(b.w >> 16);
+    if (coop_write_entry(E, cx, e, pad) != GST_OK) E.bad = 1;
+  }
+  WP_SYNC();
+  const u32 nl = E.n_long < GGR_COOP_LONG_MAX ? E.n_long : GGR_COOP_LONG_MAX;
+  for (u32 k = 0; k < nl; k++) {
+    const u8* src = cx.in + E.lsrc[k];
+    u8* d = E.buf + E.ldst[k];
+    const u32 len = E.llen[k];
+    for (u32 j = lane; j < len; j += 32) d[j] = src[j];
+  }
+  WP_SYNC();
+  wp_copy_out(E.buf, out16, pad, size);
+  return E.bad ? GST_INTERNAL : GST_OK;
 }

@@ -35,7 +35,7 @@ enum { TK_LBRACE = 1, TK_RBRACE = 2, TK_LBRACK = 3, TK_RBRACK = 4, TK_COLON = 5,
 // node classes: containers first; everything >= CC_NULL is finished in the leaf phase
 enum { CC_MSG = 0, CC_LIST = 1, CC_MAP = 2, CC_ENTRY = 3, CC_NULL = 4, CC_STR = 5, CC_BYTES = 6, CC_INT = 7, CC_FLOAT = 8, CC_TS = 9, CC_N = 10 };
 
-struct CNode {       // 28 bytes
+struct CNode {       // 20 bytes
   u16 tok;           // token index of the value
   u16 parent;
   u16 next;          // next sibling in emit order (lists: document order)
@@ -44,9 +44,8 @@ struct CNode {       // 28 bytes
   u16 gfield;        // global field index
   u16 msg;           // CC_MSG: message type
   u8 cls, depth;
-  u32 body;          // containers: payload bytes accumulated from the children
-  u32 full;          // bytes of this node in its parent's payload (tag, length prefix, payload)
-  u32 off;           // output offset of the node, relative to the item
+  u32 body;          // containers: payload bytes accumulated from the children (their header length
+                     // goes to `tok` once they are closed); leaves: bytes in the parent's payload
 };
 
 // Per-warp working set (shared memory).  MT tokens / MQ quotes / MN nodes; aux is 12 bits, so
@@ -66,7 +65,7 @@ struct CoopEncT {
   u32 n_tok, n_q, n_node, q_end, n_leaf, max_depth, bail, cap;
 };
 typedef CoopEncT<1024, 512, 224> CoopEnc;        // tier 1: ~12 KB per warp
-typedef CoopEncT<4096, 2048, 1024> CoopEncBig;   // tier 2: ~48 KB per warp
+typedef CoopEncT<4096, 2048, 768> CoopEncBig;    // tier 2: ~53 KB per warp (4 warps must fit 227 KB)
 
 struct CeLut {
   u32 cls[256];  // CE_L* class bits
@@ -322,8 +321,6 @@ GGR_DEV u32 ce_new_node(SH& S, u32 tok, u32 parent, u32 gfield, u32 emit, u32 cl
   nd.cls = (u8)cls;
   nd.depth = (u8)depth;
   nd.body = 0;
-  nd.full = 0;
-  nd.off = 0;
   S.node[idx] = nd;
   return idx;
 }
@@ -630,7 +627,7 @@ GGR_DEV void ce_leaf(SH& S, EncCtx& cx, u32 ni) {
     }
     node_store(cx.ir, ni, payload, sidx != GGR_NIL ? sidx : nidx, next, nd.emit, node_meta(N_MSG, 0, f.tag));
     const u32 tsfull = f.tag_len + varint_size(payload) + payload;
-    S.node[ni].full = tsfull;
+    S.node[ni].body = tsfull;
     wp_atomic_add(&S.node[nd.parent].body, tsfull);
     // the seconds / nanos nodes have no entry of their own in the node table: the emitter writes
     // them together with this node
@@ -667,7 +664,7 @@ GGR_DEV void ce_leaf(SH& S, EncCtx& cx, u32 ni) {
   const bool live = in_list || (f.flags & GF_PRESENCE) || !l.zero;
   node_store(cx.ir, ni, l.a, l.b, next, nd.emit, live ? node_meta(l.type, l.flags, tag) : node_meta(N_SKIP, 0, 0));
   if (live) {
-    S.node[ni].full = tag_len + l.body;
+    S.node[ni].body = tag_len + l.body;
     wp_atomic_add(&S.node[nd.parent].body, tag_len + l.body);
   }
 }
@@ -698,18 +695,20 @@ GGR_DEV void ce_close_container(SH& S, EncCtx& cx, u32 ni) {
     node_store(cx.ir, ni, nd.body, head, next, nd.emit, node_meta(N_LIST, 0, 0));
     full = nd.body;
   }
-  S.node[ni].full = full;
+  S.node[ni].tok = (u16)(full - nd.body);  // header: tag and length prefix, if any (the token is no longer needed)
   wp_atomic_add(&S.node[nd.parent].body, full);
 }
 
-// T6, one lane: container `ni` knows its offset; hand out offsets to its children.
+// T6, one lane: container `ni` knows its offset; hand out offsets to its children.  The offsets
+// live in the token array, which is dead by now.
 template <class SH>
 GGR_DEV void ce_place_children(SH& S, u32 ni) {
   const CNode nd = S.node[ni];
-  u32 pos = nd.off + (nd.full - nd.body);  // header: tag and length prefix, if any
+  u32 pos = S.tok[ni] + nd.tok;
   for (u32 c = nd.head; c != CE_NIL; c = S.node[c].next) {
-    S.node[c].off = pos;
-    pos += S.node[c].full;
+    const CNode ch = S.node[c];
+    S.tok[c] = pos;
+    pos += ch.cls <= CC_ENTRY ? ch.body + ch.tok : ch.body;
   }
 }
 
@@ -808,8 +807,8 @@ GGR_DEV bool ce_parse_item(SH& S, const CeLut& lut, const Tables& T, u32 root_ms
   }
   // T6: offsets, top-down (the root message has no header)
   if (lane == 0) {
-    S.node[0].full = S.node[0].body;
-    S.node[0].off = 0;
+    S.node[0].tok = 0;
+    S.tok[0] = 0;
   }
   WP_SYNC();
   for (u32 d = 0; d < S.max_depth; d++) {
@@ -819,7 +818,7 @@ GGR_DEV bool ce_parse_item(SH& S, const CeLut& lut, const Tables& T, u32 root_ms
     }
     WP_SYNC();
   }
-  for (u32 i = lane; i < n; i += 32) ioff[i] = S.node[i].off;
+  for (u32 i = lane; i < n; i += 32) ioff[i] = S.tok[i];
   res->size = S.node[0].body;
   res->first = ce_link(S.node[0].head);
   res->n_nodes = S.n_node;
@@ -834,21 +833,22 @@ GGR_DEV bool ce_parse_item(SH& S, const CeLut& lut, const Tables& T, u32 root_ms
 // ------------------------------------------------------------------------------------------------
 #define CE_LONG_STR 96u
 #define CE_LONG_MAX 32u
+#define CE_STAGE 8192u /* items with more wire bytes than this: per-thread emitter */
 struct CoopEmit {
+  u8 buf[CE_STAGE + 48];  // [pad, pad + size): pad = destination address & 15
   u32 src[CE_LONG_MAX], dst[CE_LONG_MAX], len[CE_LONG_MAX];
   u32 n;
 };
 
-// one lane: node `i` (not a long plain string's payload)
-GGR_DEV void ce_emit_node(CoopEmit& E, const u8* in, u32 end, const u8* ir, const u32* ioff, u32 i, u8* out8, u32 base) {
+// one lane: bytes of node `i` into the staging buffer (long plain strings: payload left to the warp)
+GGR_DEV void ce_emit_node(CoopEmit& E, const u8* in, u32 end, const u8* ir, const u32* ioff, u32 i, u32 pad) {
   const U4 nd = node_load(ir, i);
   const u32 type = nd.w & 0xFu, flags = (nd.w >> 4) & 0xFu, tag = nd.w >> 8;
   if (type == N_SKIP || type == N_MAP || (type == N_LIST && !(flags & NF_PACKED))) return;
   const u32 off = ioff[i];
   if (off == 0xFFFFFFFFu) return;  // written together with its parent (Timestamp fields)
-  Wr w;
-  const u32 o = base + off;
-  w.init(out8 + (o & ~7u), o & 7u);
+  Sw w;
+  w.init(E.buf, pad + off);
   switch (type) {
     case N_VARINT: {
       if (tag) put_varint(w, tag);
@@ -873,16 +873,24 @@ GGR_DEV void ce_emit_node(CoopEmit& E, const u8* in, u32 end, const u8* ir, cons
     case N_STR:
       if (tag) put_varint(w, tag);
       put_varint(w, nd.y);
-      if (!(flags & NF_ESC) && nd.y >= CE_LONG_STR) {
-        u32 k = wp_atomic_add(&E.n, 1u);
-        if (k < CE_LONG_MAX) {  // payload left to the whole warp
-          E.src[k] = nd.x + 1u;
-          E.dst[k] = (w.pos - (o & 7u)) + o;
-          E.len[k] = nd.y;
-          break;
+      if (flags & NF_ESC) {
+        copy_string(w, in, nd.x, end, nd.y, true);
+      } else {
+        bool handed = false;
+        if (nd.y >= CE_LONG_STR) {
+          const u32 k = wp_atomic_add(&E.n, 1u);
+          if (k < CE_LONG_MAX) {
+            E.src[k] = nd.x + 1u;
+            E.dst[k] = w.pos;
+            E.len[k] = nd.y;
+            handed = true;
+          }
+        }
+        if (!handed) {
+          const u8* src = in + nd.x + 1u;
+          for (u32 j = 0; j < nd.y; j++) E.buf[w.pos + j] = src[j];
         }
       }
-      copy_string(w, in, nd.x, end, nd.y, (flags & NF_ESC) != 0);
       break;
     case N_BYTES: {
       if (tag) put_varint(w, tag);
@@ -890,7 +898,7 @@ GGR_DEV void ce_emit_node(CoopEmit& E, const u8* in, u32 end, const u8* ir, cons
       StrIter it;
       it.init(in, nd.x, end);
       u32 n;
-      b64_run<true, Wr>(it, (flags & NF_URL) != 0, (flags & NF_PADDED) ? 0u : 1u, &w, &n);
+      b64_run<true, Sw>(it, (flags & NF_URL) != 0, (flags & NF_PADDED) ? 0u : 1u, &w, &n);
       break;
     }
     case N_MSG:
@@ -915,42 +923,24 @@ GGR_DEV void ce_emit_node(CoopEmit& E, const u8* in, u32 end, const u8* ir, cons
       break;
     default: break;
   }
-  w.finish();
 }
 
-// all lanes: copy len bytes in[src..) -> out8[dst..), 4 bytes per lane and step once dst is aligned
-GGR_DEV void ce_copy_coop(const u8* in, u32 src, u8* out8, u32 dst, u32 len) {
+// One item, all 32 lanes: size bytes to dst.
+GGR_DEV void ce_emit_item(CoopEmit& E, const u8* in, u32 end, const u8* ir, const u32* ioff, u32 n_nodes, u8* dst, u32 size) {
   const u32 lane = wp_lane();
-  u32 head = (4u - (dst & 3u)) & 3u;
-  if (head > len) head = len;
-  if (lane < head) out8[dst + lane] = in[src + lane];
-  src += head;
-  dst += head;
-  len -= head;
-  const u32 words = len >> 2;
-  const u32 sh = (src & 3u) * 8u;
-  const u8* sa = in + (src & ~3u);
-  for (u32 k = lane; k < words; k += 32) {
-    u32 lo = ggr_ld4(sa + 4u * k);
-    u32 v = lo;
-    if (sh) {
-      u32 hi = ggr_ld4(sa + 4u * k + 4u);
-      v = (lo >> sh) | (hi << (32u - sh));
-    }
-    ggr_st4(out8 + dst + 4u * k, v);
-  }
-  const u32 tail = len & 3u;
-  if (lane < tail) out8[dst + 4u * words + lane] = in[src + 4u * words + lane];
-}
-
-// One item, all 32 lanes.  out8: 8-byte aligned base, base: offset of the item's first byte from it.
-GGR_DEV void ce_emit_item(CoopEmit& E, const u8* in, u32 end, const u8* ir, const u32* ioff, u32 n_nodes, u8* out8, u32 base) {
-  const u32 lane = wp_lane();
-  WP_SYNC();
+  const u32 pad = wp_align_pad(dst);
+  WP_SYNC();  // persistent warps: the previous item has been copied out
   if (lane == 0) E.n = 0;
   WP_SYNC();
-  for (u32 i = 1 + lane; i < n_nodes; i += 32) ce_emit_node(E, in, end, ir, ioff, i, out8, base);
+  for (u32 i = 1 + lane; i < n_nodes; i += 32) ce_emit_node(E, in, end, ir, ioff, i, pad);
   WP_SYNC();
   const u32 nl = E.n < CE_LONG_MAX ? E.n : CE_LONG_MAX;
-  for (u32 k = 0; k < nl; k++) ce_copy_coop(in, E.src[k], out8, E.dst[k], E.len[k]);
+  for (u32 k = 0; k < nl; k++) {
+    const u8* src = in + E.src[k];
+    u8* d = E.buf + E.dst[k];
+    const u32 len = E.len[k];
+    for (u32 j = lane; j < len; j += 32) d[j] = src[j];
+  }
+  WP_SYNC();
+  wp_copy_out(E.buf, dst - pad, pad, size);
 }

@@ -88,7 +88,7 @@ struct ggr_engine {
   cudaStream_t stream = nullptr;
   std::string err;
   uint64_t launches = 0;
-  bool use_coop = false;  // GGR_COOP=1 enables the warp-cooperative reply-side kernels (slower than the per-thread ones so far)
+  bool use_coop = true;  // GGR_COOP=0 disables the lock-step reply-side kernels (A/B runs)
   std::mutex mu;
   // scratch (device): one set per direction for the device-buffer entry points, so that a request
   // batch and a reply batch can be in flight on two streams at the same time
@@ -97,8 +97,8 @@ struct ggr_engine {
   // host-buffer entry points: the batch is cut into chunks that move through `n_slots` slots
   // (stream + staging + scratch each), so that H2D, kernels and D2H of different chunks overlap
   Slot slots[GGR_MAX_SLOTS];
-  int n_slots = 3;
-  int64_t chunk_items = 32768;
+  int n_slots = 4;
+  int64_t chunk_items = 16384;
   // per-kernel timing
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -164,7 +164,7 @@ int ggr_engine_create(const ggr_config* cfg, ggr_engine** out) {
   e->device = dev;
   cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, dev);
   if (e->sm_count <= 0) e->sm_count = 148;
-  if (const char* nc = getenv("GGR_COOP")) e->use_coop = nc[0] == '1';
+  if (const char* nc = getenv("GGR_COOP")) e->use_coop = nc[0] != '0';
   if (const char* nc = getenv("GGR_COOP_ENC")) e->use_coop_enc = nc[0] != '0';
   if (const char* nc = getenv("GGR_SLOTS")) {
     int v = atoi(nc);
@@ -175,7 +175,7 @@ int ggr_engine_create(const ggr_config* cfg, ggr_engine** out) {
     if (v >= 128) e->chunk_items = v;
   }
   e->order = (cfg && cfg->wire_order == GGR_ORDER_GO_LEGACY) ? ggr::ORDER_GO_LEGACY : ggr::ORDER_FIELD_NUMBER;
-  if (ggr_encode_coop_init() != 0) {
+  if (ggr_encode_coop_init() != 0 || ggr_decode_coop_init() != 0) {
     cudaGetLastError();
     delete e;
     return GGR_ERR_CUDA;
@@ -399,7 +399,9 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
     const bool coop = e->use_coop;
     size_t c0 = 0, c1 = 0;
     if (coop) {
-      ggr_launch_decode_coop_size(st, n, s->d_blob, n_msgs, msg_id, in, in_off, flags, (u32*)sc.size.p, (u32*)sc.aux.p, status);
+      if (!ensure(e, sc.ir, ggr_decode_coop_table_bytes(n)) || !ensure(e, sc.nn, (size_t)n * 4)) return GGR_ERR_CUDA;
+      ggr_launch_decode_coop_size(st, n, s->d_blob, n_msgs, msg_id, in, in_off, flags, (u32*)sc.size.p, (u32*)sc.aux.p, status,
+                                  sc.ir.p, (u32*)sc.nn.p, e->sm_count);
       if (prof) {
         prof_mark(e, st, &c0);
         e->spans.push_back({6, m0, c0});
@@ -415,8 +417,8 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
                             (const u32*)sc.aux.p, status, (const u64*)sc.sums.p, out, out_cap, out_off);
     if (coop) {
       if (prof) prof_mark(e, st, &c1);
-      ggr_launch_decode_coop_write(st, n, s->d_blob, msg_id, in, in_off, flags, (const u32*)sc.size.p, (const u32*)sc.aux.p,
-                                   status, out, out_off);
+      ggr_launch_decode_coop_write(st, n, s->d_blob, in, in_off, flags, (const u32*)sc.size.p, (const u32*)sc.aux.p, status, sc.ir.p,
+                                   (const u32*)sc.nn.p, out, out_off, e->sm_count);
       if (prof) {
         prof_mark(e, st, &m3);
         e->spans.push_back({3, m0, m1});

@@ -1,75 +1,91 @@
-// ggr_kernels_coop.cu - warp-cooperative reply-side kernels (one warp per item); see ggr_coop.cuh.
+// ggr_kernels_coop.cu - lock-step reply-side kernels (one warp per item, persistent warps); see
+// ggr_coop.cuh.  The size kernel saves every handled item's entry table (32 bytes per field
+// occurrence) so that the write kernel only has to write.
 #include "ggr_kernels.h"
 #include "ggr_coop.cuh"
 
 #define COOP_WARPS 4
+#define COOP_TAB_U4 (2 * GGR_COOP_ENTRIES) /* 16-byte words of table space per item */
 
 __global__ void __launch_bounds__(COOP_WARPS * 32)
 k_decode_coop_size(const u8* __restrict__ blob, long long n, u32 n_msgs, const i32* __restrict__ msg_id,
                    const u8* __restrict__ in, const u64* __restrict__ in_off, u32 flags, u32* __restrict__ size,
-                   u32* __restrict__ mode, i32* __restrict__ status) {
-  __shared__ CoopShared S[COOP_WARPS];
+                   u32* __restrict__ mode, i32* __restrict__ status, U4* __restrict__ tab, u32* __restrict__ nent) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  CoopShared* S = reinterpret_cast<CoopShared*>(smem);
   const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long item = (long long)blockIdx.x * COOP_WARPS + warp;
-  if (item >= n) return;
-  u64 a = in_off[item], b = in_off[item + 1];
-  i32 m = msg_id[item];
-  bool ok = false;
-  u32 sz = 0;
-  if (m >= 0 && (u32)m < n_msgs && b >= a && b - a <= 0x7FFFFFF0ull) {
-    DecCtx cx;
-    cx.T = ggr_tables(blob);
-    cx.in = in + (a & ~15ull);
-    cx.flags = flags;
-    u32 s0 = (u32)(a & 15ull);
-    int ws = GST_OK;
-    ok = coop_decode_item(S[warp], cx, (u32)m, s0, s0 + (u32)(b - a), lane, 32, nullptr, 0, &sz, &ws);
-  }
-  if (lane == 0) {
-    if (ok) {
-      size[item] = sz;
-      mode[item] = GGR_MODE_COOP;
-      status[item] = GST_OK;
-    } else {
-      mode[item] = GGR_MODE_PENDING;
+  DecCtx cx;
+  cx.T = ggr_tables(blob);
+  cx.flags = flags;
+  for (long long item = (long long)blockIdx.x * COOP_WARPS + warp; item < n; item += (long long)gridDim.x * COOP_WARPS) {
+    const u64 a = in_off[item], b = in_off[item + 1];
+    const i32 m = msg_id[item];
+    bool ok = false;
+    u32 sz = 0, ne = 0;
+    if (m >= 0 && (u32)m < n_msgs && b >= a && b - a <= (u64)GGR_COOP_MAX_WIRE - 16u) {
+      cx.in = in + (a & ~15ull);
+      const u32 s0 = (u32)(a & 15ull);
+      ok = coop_size_item(S[warp], cx, (u32)m, s0, s0 + (u32)(b - a), tab + (size_t)item * COOP_TAB_U4, &ne, &sz);
+    }
+    if (lane == 0) {
+      if (ok) {
+        size[item] = sz;
+        mode[item] = GGR_MODE_COOP;
+        status[item] = GST_OK;
+        nent[item] = ne;
+      } else {
+        mode[item] = GGR_MODE_PENDING;
+        nent[item] = 0;
+      }
     }
   }
 }
 
-__global__ void __launch_bounds__(COOP_WARPS * 32)
-k_decode_coop_write(const u8* __restrict__ blob, long long n, const i32* __restrict__ msg_id, const u8* __restrict__ in,
-                    const u64* __restrict__ in_off, u32 flags, const u32* __restrict__ size, const u32* __restrict__ mode,
-                    i32* __restrict__ status, u8* __restrict__ out, const u64* __restrict__ out_off) {
-  __shared__ CoopShared S[COOP_WARPS];
+#define COOP_WRITE_WARPS 4
+__global__ void __launch_bounds__(COOP_WRITE_WARPS * 32)
+k_decode_coop_write(const u8* __restrict__ blob, long long n, const u8* __restrict__ in, const u64* __restrict__ in_off,
+                    u32 flags, const u32* __restrict__ size, const u32* __restrict__ mode, i32* __restrict__ status,
+                    const U4* __restrict__ tab, const u32* __restrict__ nent, u8* __restrict__ out,
+                    const u64* __restrict__ out_off) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  CoopStage* E = reinterpret_cast<CoopStage*>(smem);
   const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long item = (long long)blockIdx.x * COOP_WARPS + warp;
-  if (item >= n) return;
-  if (mode[item] != GGR_MODE_COOP || status[item] != GST_OK) return;
-  u64 a = in_off[item], b = in_off[item + 1];
-  u64 goff = out_off[item];
   DecCtx cx;
   cx.T = ggr_tables(blob);
-  cx.in = in + (a & ~15ull);
   cx.flags = flags;
-  u32 s0 = (u32)(a & 15ull);
-  u32 sz = 0;
-  int ws = GST_OK;
-  bool ok = coop_decode_item(S[warp], cx, (u32)msg_id[item], s0, s0 + (u32)(b - a), lane, 32, out + (goff & ~7ull),
-                             (u32)(goff & 7ull), &sz, &ws);
-  bool bad = !ok || ws != GST_OK || sz != size[item];
-  if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) status[item] = GST_INTERNAL;
+  for (long long item = (long long)blockIdx.x * COOP_WRITE_WARPS + warp; item < n; item += (long long)gridDim.x * COOP_WRITE_WARPS) {
+    if (mode[item] != GGR_MODE_COOP || status[item] != GST_OK) continue;
+    const u64 a = in_off[item];
+    cx.in = in + (a & ~15ull);
+    int ws = coop_write_item(E[warp], cx, tab + (size_t)item * COOP_TAB_U4, nent[item], out + out_off[item], size[item]);
+    if (ws != GST_OK && lane == 0) status[item] = GST_INTERNAL;
+  }
+}
+
+static size_t coop_smem_bytes() { return sizeof(CoopShared) * COOP_WARPS; }
+size_t ggr_decode_coop_table_bytes(long long n) { return (size_t)n * COOP_TAB_U4 * 16; }
+int ggr_decode_coop_init() {
+  cudaError_t a = cudaFuncSetAttribute(k_decode_coop_size, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem_bytes());
+  cudaError_t b = cudaFuncSetAttribute(k_decode_coop_write, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(sizeof(CoopStage) * COOP_WRITE_WARPS));
+  return (a == cudaSuccess && b == cudaSuccess) ? 0 : -1;
+}
+static unsigned coop_grid(long long n, int sm_count) {
+  long long want = (n + COOP_WARPS - 1) / COOP_WARPS, cap = (long long)sm_count * 4;
+  return (unsigned)(want < cap ? want : cap);
 }
 
 void ggr_launch_decode_coop_size(cudaStream_t st, long long n, const uint8_t* blob, uint32_t n_msgs, const int32_t* msg_id,
                                  const uint8_t* in, const uint64_t* in_off, uint32_t flags, uint32_t* size, uint32_t* mode,
-                                 int32_t* status) {
-  unsigned nb = (unsigned)((n + COOP_WARPS - 1) / COOP_WARPS);
-  k_decode_coop_size<<<nb, COOP_WARPS * 32, 0, st>>>(blob, n, n_msgs, msg_id, in, (const u64*)in_off, flags, size, mode, status);
+                                 int32_t* status, void* tab, uint32_t* nent, int sm_count) {
+  k_decode_coop_size<<<coop_grid(n, sm_count), COOP_WARPS * 32, coop_smem_bytes(), st>>>(
+      blob, n, n_msgs, msg_id, in, (const u64*)in_off, flags, size, mode, status, (U4*)tab, nent);
 }
-void ggr_launch_decode_coop_write(cudaStream_t st, long long n, const uint8_t* blob, const int32_t* msg_id, const uint8_t* in,
-                                  const uint64_t* in_off, uint32_t flags, const uint32_t* size, const uint32_t* mode,
-                                  int32_t* status, uint8_t* out, const uint64_t* out_off) {
-  unsigned nb = (unsigned)((n + COOP_WARPS - 1) / COOP_WARPS);
-  k_decode_coop_write<<<nb, COOP_WARPS * 32, 0, st>>>(blob, n, msg_id, in, (const u64*)in_off, flags, size, mode, status, out,
-                                                     (const u64*)out_off);
+void ggr_launch_decode_coop_write(cudaStream_t st, long long n, const uint8_t* blob, const uint8_t* in, const uint64_t* in_off,
+                                  uint32_t flags, const uint32_t* size, const uint32_t* mode, int32_t* status, const void* tab,
+                                  const uint32_t* nent, uint8_t* out, const uint64_t* out_off, int sm_count) {
+  long long want = (n + COOP_WRITE_WARPS - 1) / COOP_WRITE_WARPS, cap = (long long)sm_count * 6;
+  unsigned nb = (unsigned)(want < cap ? want : cap);
+  k_decode_coop_write<<<nb, COOP_WRITE_WARPS * 32, sizeof(CoopStage) * COOP_WRITE_WARPS, st>>>(
+      blob, n, in, (const u64*)in_off, flags, size, mode, status, (const U4*)tab, nent, out, (const u64*)out_off);
 }

@@ -49,7 +49,7 @@ k_encode_coop_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const 
         size[item] = res.size;
         first[item] = res.first;
         status[item] = GST_OK;
-        nnodes[item] = res.n_nodes;
+        nnodes[item] = res.size <= CE_STAGE ? res.n_nodes : 0;  // larger items: per-thread emitter
       } else {
         size[item] = 0;
         nnodes[item] = 0;
@@ -65,17 +65,18 @@ __global__ void __launch_bounds__(CE_WARPS * 32)
 k_encode_coop_emit(long long n, const u8* __restrict__ in, const u64* __restrict__ in_off, const u8* __restrict__ ir,
                    const u32* __restrict__ ioff, const u32* __restrict__ nnodes, const u32* __restrict__ size,
                    const i32* __restrict__ status, u8* __restrict__ out, const u64* __restrict__ out_off) {
-  __shared__ CoopEmit E[CE_WARPS];
+  extern __shared__ __align__(16) unsigned char smem[];
+  CoopEmit* E = reinterpret_cast<CoopEmit*>(smem);
   const u32 warp = threadIdx.x >> 5;
   const u64 a0 = in_off[0];
   for (long long item = (long long)blockIdx.x * CE_WARPS + warp; item < n; item += (long long)gridDim.x * CE_WARPS) {
     const u32 nn = nnodes[item];
-    if (nn <= 1 || size[item] == 0 || status[item] != GST_OK) continue;
+    const u32 sz = size[item];
+    if (nn <= 1 || sz == 0 || status[item] != GST_OK) continue;
     const u64 a = in_off[item], b = in_off[item + 1];
     const u64 node_off = ((a - a0) >> 1) + 8ull * (u64)item;
-    const u64 goff = out_off[item];
     ce_emit_item(E[warp], in + (a & ~15ull), (u32)(a & 15ull) + (u32)(b - a), ir + node_off * 16, ioff + node_off, nn,
-                 out + (goff & ~7ull), (u32)(goff & 7ull));
+                 out + out_off[item], sz);
   }
 }
 
@@ -89,7 +90,9 @@ int ggr_encode_coop_init() {
                                        (int)ce_smem_bytes<CoopEnc>());
   cudaError_t b = cudaFuncSetAttribute(k_encode_coop_parse<CoopEncBig>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)ce_smem_bytes<CoopEncBig>());
-  return (a == cudaSuccess && b == cudaSuccess) ? 0 : -1;
+  cudaError_t c = cudaFuncSetAttribute(k_encode_coop_emit, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(sizeof(CoopEmit) * CE_WARPS));
+  return (a == cudaSuccess && b == cudaSuccess && c == cudaSuccess) ? 0 : -1;
 }
 
 void ggr_launch_encode_coop_parse(cudaStream_t st, int tier, long long n, const uint8_t* blob, uint32_t n_msgs,
@@ -113,8 +116,8 @@ void ggr_launch_encode_coop_parse(cudaStream_t st, int tier, long long n, const 
 void ggr_launch_encode_coop_emit(cudaStream_t st, long long n, const uint8_t* in, const uint64_t* in_off, const uint8_t* ir,
                                  const uint32_t* ioff, const uint32_t* nnodes, const uint32_t* size, const int32_t* status,
                                  uint8_t* out, const uint64_t* out_off, int sm_count) {
-  long long want = (n + CE_WARPS - 1) / CE_WARPS, cap = (long long)sm_count * 8;
+  long long want = (n + CE_WARPS - 1) / CE_WARPS, cap = (long long)sm_count * 6;
   unsigned nb = (unsigned)(want < cap ? want : cap);
-  k_encode_coop_emit<<<nb, CE_WARPS * 32, 0, st>>>(n, in, (const u64*)in_off, ir, ioff, nnodes, size, status, out,
+  k_encode_coop_emit<<<nb, CE_WARPS * 32, sizeof(CoopEmit) * CE_WARPS, st>>>(n, in, (const u64*)in_off, ir, ioff, nnodes, size, status, out,
                                                    (const u64*)out_off);
 }

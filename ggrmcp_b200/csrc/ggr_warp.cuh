@@ -208,3 +208,46 @@ GGR_DEV u32 wp_excl_scan_(u32 v, u32* total, int tag) {
   return x - v;
 }
 #define WP_EXCL_SCAN(v, total) wp_excl_scan_((v), (total), __LINE__)
+
+// ---- staging in shared memory --------------------------------------------------------------
+// The lock-step writers assemble an item's bytes in shared memory (plain byte stores, no
+// alignment edges) and copy them out with aligned 16-byte stores.
+// byte writer into a staging buffer (stands in for Wr / Cnt in the value formatters)
+struct Sw {
+  u8* p;
+  u32 pos;
+  GGR_DEV void init(u8* b, u32 start) { p = b; pos = start; }
+  GGR_DEV void put(u32 v, int k) {  // 1 <= k <= 4
+    p[pos] = (u8)v;
+    if (k > 1) p[pos + 1] = (u8)(v >> 8);
+    if (k > 2) p[pos + 2] = (u8)(v >> 16);
+    if (k > 3) p[pos + 3] = (u8)(v >> 24);
+    pos += (u32)k;
+  }
+  GGR_DEV void put1(u32 b) { p[pos++] = (u8)b; }
+  GGR_DEV void finish() {}
+};
+
+
+GGR_DEV u32 wp_align_pad(const u8* dst) {  // dst address & 15
+#if defined(__CUDA_ARCH__)
+  return (u32)(reinterpret_cast<unsigned long long>(dst) & 15ull);
+#else
+  return (u32)((uintptr_t)dst & 15u);
+#endif
+}
+// all lanes: buf[pad, pad + size) -> out16[pad, pad + size); out16 is 16-byte aligned, buf too
+GGR_DEV void wp_copy_out(const u8* buf, u8* out16, u32 pad, u32 size) {
+  const u32 lane = wp_lane();
+  const u32 lo = pad, hi = pad + size;
+  const u32 nchunks = (hi + 15u) >> 4;
+  for (u32 c = lane; c < nchunks; c += 32) {
+    const u32 c0 = c << 4, c1 = c0 + 16u;
+    if (c0 >= lo && c1 <= hi) {
+      ggr_st16(out16 + c0, *reinterpret_cast<const U4*>(buf + c0));
+    } else {
+      const u32 b0 = c0 > lo ? c0 : lo, b1 = c1 < hi ? c1 : hi;
+      for (u32 j = b0; j < b1; j++) out16[j] = buf[j];
+    }
+  }
+}

@@ -31,12 +31,12 @@ def hsim(fds_bytes):
     return hostsim.Schema(fds_bytes)
 
 
-# every GPU test runs against each kernel path: the default (lock-step request parser in front of
-# the per-thread kernels), the per-thread kernels alone, and the warp-cooperative reply kernels
+# every GPU test runs against each kernel path: the default (lock-step kernels in front of the
+# per-thread kernels on both sides), the per-thread kernels alone, the lock-step request side only
 _ENGINE_PATHS = {
     "default": {},
     "per_thread": {"GGR_COOP_ENC": "0", "GGR_COOP": "0"},
-    "coop_reply": {"GGR_COOP": "1"},
+    "lockstep_request_only": {"GGR_COOP": "0"},
     # host entry points cut into many small chunks over two slots: exercises the copy/compute pipeline
     "small_chunks": {"GGR_CHUNK_ITEMS": "128", "GGR_SLOTS": "2"},
 }

@@ -106,8 +106,7 @@ struct CoopEncArgs {
   bool ok[32];
   // pass B
   CoopEmit* E;
-  u8* out8;
-  u32 base;
+  u8* dst;
 };
 template <class SH>
 static void coop_enc_body(void* p, u32 lane) {
@@ -117,7 +116,7 @@ static void coop_enc_body(void* p, u32 lane) {
 template <class SH>
 static void coop_emit_body(void* p, u32 lane) {
   CoopEncArgs<SH>* a = (CoopEncArgs<SH>*)p;
-  ce_emit_item(*a->E, a->in, a->end, a->ir, a->ioff, a->res[0].n_nodes, a->out8, a->base);
+  ce_emit_item(*a->E, a->in, a->end, a->ir, a->ioff, a->res[0].n_nodes, a->dst, a->res[0].size);
 }
 template <class SH>
 static int hs_encode_coop_t(void* h, int msg, const uint8_t* json, uint32_t n, uint32_t in_off, uint32_t out_off, uint8_t* out,
@@ -185,12 +184,11 @@ static int hs_encode_coop_t(void* h, int msg, const uint8_t* json, uint32_t n, u
     if (w.pos != out_off + res.size) st = 100;
     memcpy(ref.data(), rb + out_off, res.size);
   }
-  static CoopEmit E;
+  alignas(16) static CoopEmit E;
   memset(&E, 0xAB, sizeof E);
   a.E = &E;
-  a.out8 = ob;
-  a.base = out_off;
-  if (res.size) {
+  a.dst = ob + out_off;
+  if (res.size && res.size <= CE_STAGE) {
     werr = hw_run_warp(coop_emit_body<SH>, &a);
     if (werr) st = 320 + werr;
   }
@@ -198,6 +196,7 @@ static int hs_encode_coop_t(void* h, int msg, const uint8_t* json, uint32_t n, u
     if (ob[i] != before[i]) st = 101;
   for (uint32_t i = out_off + res.size; i < out_off + res.size + 32 && st == GST_OK; i++)
     if (ob[i] != before[i]) st = 102;
+  if (res.size > CE_STAGE) memcpy(ob + out_off, ref.data(), res.size);  // too large to stage: per-thread emitter
   if (st == GST_OK && memcmp(ob + out_off, ref.data(), res.size) != 0) st = 103;  // the two emitters disagree
   memcpy(out, ob + out_off, res.size);
   *out_n = res.size;
@@ -241,31 +240,66 @@ int hs_decode(void* h, int msg, const uint8_t* wire, uint32_t n, uint32_t in_off
   return st;
 }
 
-// Cooperative reply-side path with the lanes run in sequence (nlanes = 1).  Returns 200 when
-// the cooperative code leaves the item to the general kernels.
+// Lock-step reply-side path on 32 fibers: size pass (saves the entry table), write pass.  Returns
+// 200 when the lock-step code leaves the item to the per-thread kernels, 3xx on a fiber-warp error.
+struct CoopDecArgs {
+  CoopShared* S;
+  CoopStage* E;
+  DecCtx cx;
+  u32 msg, start, end;
+  U4* tab;
+  u32 n[32], size[32];
+  bool ok[32];
+  u8* dst;
+  int ws[32];
+};
+static void coop_dec_size_body(void* p, u32 lane) {
+  CoopDecArgs* a = (CoopDecArgs*)p;
+  a->ok[lane] = coop_size_item(*a->S, a->cx, a->msg, a->start, a->end, a->tab, &a->n[lane], &a->size[lane]);
+}
+static void coop_dec_write_body(void* p, u32 lane) {
+  CoopDecArgs* a = (CoopDecArgs*)p;
+  a->ws[lane] = coop_write_item(*a->E, a->cx, a->tab, a->n[0], a->dst, a->size[0]);
+}
 int hs_decode_coop(void* h, int msg, const uint8_t* wire, uint32_t n, uint32_t in_off, uint32_t out_off, uint32_t flags,
                    uint8_t* out, uint32_t out_cap, uint32_t* out_n) {
   HsSchema* s = (HsSchema*)h;
   std::vector<uint8_t> inbuf_raw(in_off + n + 64 + 16, 0xEE);
   uint8_t* in = (uint8_t*)(((uintptr_t)inbuf_raw.data() + 15) & ~(uintptr_t)15);
   memcpy(in + in_off, wire, n);
-  DecCtx cx;
-  cx.T = ggr_tables(s->blob);
-  cx.in = in;
-  cx.flags = flags;
   static CoopShared S;
-  uint32_t size = 0;
-  int ws = GST_OK;
+  memset(&S, 0xAB, sizeof S);
+  std::vector<U4> tab(2 * GGR_COOP_ENTRIES);
+  CoopDecArgs a;
+  a.S = &S;
+  a.cx.T = ggr_tables(s->blob);
+  a.cx.in = in;
+  a.cx.flags = flags;
+  a.msg = (u32)msg;
+  a.start = in_off;
+  a.end = in_off + n;
+  a.tab = tab.data();
   *out_n = 0;
-  if (!coop_decode_item(S, cx, (u32)msg, in_off, in_off + n, 0, 1, nullptr, 0, &size, &ws)) return 200;
+  int werr = hw_run_warp(coop_dec_size_body, &a);
+  if (werr) return 300 + werr;
+  for (int l = 1; l < 32; l++)
+    if (a.ok[l] != a.ok[0] || (a.ok[0] && (a.size[l] != a.size[0] || a.n[l] != a.n[0]))) return 310;
+  if (!a.ok[0]) return 200;
+  const uint32_t size = a.size[0];
   if (size > out_cap) return GST_NO_SPACE;
   std::vector<uint8_t> ob_raw(out_off + size + 64, 0xDD);
   uint8_t* ob = (uint8_t*)(((uintptr_t)ob_raw.data() + 15) & ~(uintptr_t)15);
   std::vector<uint8_t> before(ob, ob + out_off + size + 32);
-  uint32_t size2 = 0;
-  if (!coop_decode_item(S, cx, (u32)msg, in_off, in_off + n, 0, 1, ob, out_off, &size2, &ws)) return 201;
-  int st = ws;
-  if (st == GST_OK && size2 != size) st = 100;
+  memset(&S, 0xCD, sizeof S);  // the write pass may rely on the saved table only
+  alignas(16) static CoopStage E;
+  memset(&E, 0xCD, sizeof E);
+  a.E = &E;
+  a.dst = ob + out_off;
+  werr = hw_run_warp(coop_dec_write_body, &a);
+  if (werr) return 320 + werr;
+  int st = GST_OK;
+  for (int l = 0; l < 32; l++)
+    if (a.ws[l] != GST_OK) st = a.ws[l];
   for (uint32_t i = 0; i < out_off && st == GST_OK; i++)
     if (ob[i] != before[i]) st = 101;
   for (uint32_t i = out_off + size; i < out_off + size + 32 && st == GST_OK; i++)

@@ -148,3 +148,50 @@ def test_coop_encode_bench_shapes(hsim):
             js = blob[int(wl.req_off[i]):int(wl.req_off[i + 1])]
             handled += _check_coop_encode(hsim, names[int(wl.req_msg[i])], js, i, tier)
         assert handled >= want, (kind, tier, handled)
+
+
+# ---- lock-step reply side (ggr_coop.cuh) on 32 fibers -----------------------------------------
+def _check_coop_decode(hsim, name, w, i=0, flags=0):
+    rc, out = hsim.decode_coop(name, w, flags, i % 16, (i * 5) % 16)
+    assert rc in (0, 200), (name, w.hex(), rc)
+    if rc == 200:
+        return False
+    est, ej = hsim.decode(name, w, flags, i % 16, (i * 5) % 16)
+    assert est == 0 and out == ej, (name, w.hex(), est, ej, out)
+    return True
+
+
+def test_coop_decode_vectors_and_edges(hsim):
+    handled = 0
+    for name, wire, js in cases.K_REPLIES:
+        rc, out = hsim.decode_coop(name, bytes.fromhex(wire), 0, 3, 5)
+        assert rc in (0, 200) and (rc == 200 or out == js)
+        handled += rc == 0
+    for i, (name, hexw) in enumerate(cases.DECODE_EDGE_HEX):
+        handled += _check_coop_decode(hsim, name, bytes.fromhex(hexw), i, i & 1)
+    assert handled > 30
+
+
+def test_coop_decode_random(hsim):
+    handled = 0
+    for i, (name, w) in enumerate(cases.random_decode_cases(120, seed0=7000)):
+        handled += _check_coop_decode(hsim, name, w, i, i & 1)
+    assert handled > 1500
+
+
+def test_coop_decode_bench_shapes(hsim):
+    import benchgen
+    names = {}
+
+    def mi(name):
+        names[hsim.msg(name)] = name
+        return hsim.msg(name)
+
+    for kind, n in (("nested", 200), ("flat", 100)):
+        wl = getattr(benchgen, kind)(n, mi)
+        blob = wl.rep_wire.tobytes()
+        handled = 0
+        for i in range(n):
+            w = blob[int(wl.rep_off[i]):int(wl.rep_off[i + 1])]
+            handled += _check_coop_decode(hsim, names[int(wl.rep_msg[i])], w, i)
+        assert handled == n, (kind, handled)
