@@ -227,11 +227,15 @@ GGR_DEV void ce_tokenize(SH& S, const CeLut& L, const u8* in, u32 start, u32 end
     u32 ti = tbase + (ex & 0xFFFFu), qi = qbase + (ex >> 16);
     tbase += tot & 0xFFFFu;
     qbase += tot >> 16;
-    u32 tot2;
-    const u32 ex2 = WP_EXCL_SCAN(wp_popc(EI) | (wp_popc(D) << 16), &tot2);
-    const u32 ei = ebase + (ex2 & 0xFFFFu), di = dbase + (ex2 >> 16);
-    ebase += tot2 & 0xFFFFu;
-    dbase += tot2 >> 16;
+    u32 ei = ebase, di = dbase;
+    if (WP_ANY((EI | D) != 0)) {  // most rounds hold neither escapes nor bytes for the full scanner
+      u32 tot2;
+      const u32 ex2 = WP_EXCL_SCAN(wp_popc(EI) | (wp_popc(D) << 16), &tot2);
+      ei += ex2 & 0xFFFFu;
+      di += ex2 >> 16;
+      ebase += tot2 & 0xFFFFu;
+      dbase += tot2 >> 16;
+    }
     const u32 qi0 = qi;
     for (u32 m = RQ; m; m &= m - 1u) {
       u32 j = wp_ffs0(m);
@@ -335,12 +339,40 @@ GGR_DEV u32 ce_leaf_class(const FieldD& f, bool timestamp) {
 }
 // `null`, exactly, followed by a delimiter
 GGR_DEV bool ce_is_null(const EncCtx& cx, u32 pos) {
-  Rd r;
-  r.init(cx.in, pos, cx.end);
-  if (!match_literal(r, LIT4('n', 'u', 'l', 'l'), 4, 0)) return false;
-  if (r.eof()) return true;
-  u32 c = r.peek();
+  const u8* p = cx.in + pos;
+  if (p[0] != 'n') return false;
+  if (cx.end - pos < 4u || p[1] != 'u' || p[2] != 'l' || p[3] != 'l') return false;
+  if (pos + 4u >= cx.end) return true;
+  const u32 c = p[4];
   return ggr_is_ws(c) || c == ',' || c == '}' || c == ']';
+}
+
+// KeyInfo of a string token known to hold no escapes and valid UTF-8 (tokenizer counts): plain
+// bytes [pos + 1, close)
+GGR_DEV void ce_key_info_plain(const u8* in, u32 pos, u32 close, KeyInfo* k) {
+  const u8* p = in + pos + 1u;
+  const u32 n = close - pos - 1u;
+  u32 h = GGR_KHASH_SEED;
+  u32 w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+  const u32 nw = (n + 3u) >> 2;
+  for (u32 i = 0; i < nw; i++) {
+    const u32 base = i << 2;
+    u32 x = p[base];
+    if (base + 1u < n) x |= (u32)p[base + 1u] << 8;
+    if (base + 2u < n) x |= (u32)p[base + 2u] << 16;
+    if (base + 3u < n) x |= (u32)p[base + 3u] << 24;
+    h = khash_mix(h, x);
+    if (i == 0) w0 = x;
+    else if (i == 1) w1 = x;
+    else if (i == 2) w2 = x;
+    else if (i == 3) w3 = x;
+  }
+  k->len = n;
+  k->hash = khash_finish(h, n);
+  k->w[0] = w0;
+  k->w[1] = w1;
+  k->w[2] = w2;
+  k->w[3] = w3;
 }
 
 // T3, one lane: members of the JSON object behind message node `ni`.
@@ -368,9 +400,14 @@ GGR_DEV void ce_walk_object(SH& S, const EncCtx& cx, u32 ni) {
     const u32 key_pos = TK_POS(kt);
     KeyInfo ki;
     {
-      Rd r;
-      r.init(cx.in, key_pos, cx.end);
-      if (scan_key(r, &ki) != GST_OK) { S.bail = 1; return; }
+      const u32 kq = TK_AUX(kt);
+      if (S.qslow[kq] == S.qslow[kq + 1] && S.qesc[kq] == S.qesc[kq + 1]) {
+        ce_key_info_plain(cx.in, key_pos, S.qpos[kq + 1], &ki);
+      } else {
+        Rd r;
+        r.init(cx.in, key_pos, cx.end);
+        if (scan_key(r, &ki) != GST_OK) { S.bail = 1; return; }
+      }
     }
     i32 ei;
     if (!hash_lookup(T, md.key_hash_first, md.key_hash_mask, ki, cx.in, key_pos, cx.end, &ei)) { S.bail = 1; return; }
