@@ -54,14 +54,16 @@ struct CoopEnt {            // 32 bytes: saved between the passes as two 16-byte
 
 #define GGR_COOP_LONG 96u
 #define GGR_COOP_LONG_MAX 32u
+#define GGR_COOP_DIRTY_MAX 64u
 struct CoopShared {
   CoopEnt ent[GGR_COOP_ENTRIES];
   u16 order[GGR_COOP_ENTRIES];            // leaves bucketed by class
   u16 dmask[GGR_COOP_MAX_WIRE / 16 + 2];  // per 16-byte chunk: bytes that are not plain text
   u16 dpre[GGR_COOP_MAX_WIRE / 16 + 2];   // number of chunks with a nonzero mask before this one
   u32 cls_cnt[DC_N], cls_cur[DC_N];
-  u32 n_ent, bail, n_leaf, max_depth, q_end;
+  u32 n_ent, bail, n_leaf, max_depth, q_end, n_dirty;
   u16 queue[GGR_COOP_ENTRIES];            // message entries to scan, level by level
+  u16 dlist[GGR_COOP_DIRTY_MAX];          // strings that need escaping / validation: sized by the whole warp
 };
 
 GGR_DEV u32 coop_class(const FieldD& f, bool ts, bool packed) {
@@ -348,6 +350,65 @@ GGR_DEV int coop_leaf_value(W& w, const DecCtx& cx, const CoopEnt& e, const Fiel
   return scalar_value<W, true>(w, cx, r, e.vend, f.kind, f.child, false, &z);
 }
 
+// ---- strings that hold quotes, backslashes, control or non-ASCII bytes: one byte per lane ----
+// JSON text length of one string byte (protojson): 1, 2 (\" \\ \b \f \n \r \t) or 6 (\u00XX)
+GGR_DEV u32 coop_esc_len(u32 c) {
+  if (c >= 0x20u) return (c == '"' || c == '\\') ? 2u : 1u;
+  return (c == 8u || c == 9u || c == 10u || c == 12u || c == 13u) ? 2u : 6u;
+}
+// all lanes: JSON text length of in[s, e) without the quotes; *ok = false on malformed UTF-8
+GGR_DEV u32 coop_dirty_size(const u8* in, u32 s, u32 e, bool* ok) {
+  const u32 lane = wp_lane();
+  u32 total = 0, carry = 0, bad = 0;
+  for (u32 p = s; p < e; p += 32) {
+    const u32 pos = p + lane;
+    const bool valid = pos < e;
+    const u32 c = valid ? in[pos] : 0u;
+    const u32 l = valid ? coop_esc_len(c) : 0u;
+    total += wp_popc(WP_BALLOT(valid)) + wp_popc(WP_BALLOT(l == 2u)) + 5u * wp_popc(WP_BALLOT(l == 6u));
+    const u32 HI = WP_BALLOT(c >= 0x80u);
+    if (HI | carry) {  // UTF-8: the continuation bytes the lead bytes announce == the ones present
+      const u32 c1 = pos + 1u < e ? in[pos + 1u] : 0u;
+      const bool lead = c >= 0xC0u;
+      const u32 LD = WP_BALLOT(lead);
+      const u32 L2 = WP_BALLOT(lead && c < 0xE0u), L3 = WP_BALLOT(lead && c >= 0xE0u && c < 0xF0u), L4 = WP_BALLOT(lead && c >= 0xF0u);
+      const bool b = lead && (c < 0xC2u || c > 0xF4u || (c == 0xE0u && c1 < 0xA0u) || (c == 0xEDu && c1 >= 0xA0u) ||
+                              (c == 0xF0u && c1 < 0x90u) || (c == 0xF4u && c1 >= 0x90u));
+      if (WP_BALLOT(b)) bad = 1;
+      const u64 EC = ((u64)(L2 | L3 | L4) << 1) | ((u64)(L3 | L4) << 2) | ((u64)L4 << 3);
+      if (((u32)EC | carry) != (HI & ~LD)) bad = 1;
+      carry = (u32)(EC >> 32);
+    }
+  }
+  *ok = !bad && !carry;
+  return total;
+}
+// all lanes: the escaped text of in[s, e) to d[0..)
+GGR_DEV void coop_dirty_write(const u8* in, u32 s, u32 e, u8* d) {
+  const u32 lane = wp_lane();
+  u32 base = 0;
+  for (u32 p = s; p < e; p += 32) {
+    const u32 pos = p + lane;
+    const bool valid = pos < e;
+    const u32 c = valid ? in[pos] : 0u;
+    const u32 l = valid ? coop_esc_len(c) : 0u;
+    u32 tot;
+    const u32 o = base + WP_EXCL_SCAN(l, &tot);
+    if (l == 1u) {
+      d[o] = (u8)c;
+    } else if (l == 2u) {
+      d[o] = '\\';
+      d[o + 1] = (u8)(c == 8u ? 'b' : c == 12u ? 'f' : c == 10u ? 'n' : c == 13u ? 'r' : c == 9u ? 't' : c);
+    } else if (l == 6u) {
+      const u32 hi = c >> 4, lo = c & 15u;
+      d[o] = '\\'; d[o + 1] = 'u'; d[o + 2] = '0'; d[o + 3] = '0';
+      d[o + 4] = (u8)('0' + hi);
+      d[o + 5] = (u8)(lo < 10u ? '0' + lo : 'a' + lo - 10u);
+    }
+    base += tot;
+  }
+}
+
 // R3, one lane: size of leaf entry ei (full text) added to its parent
 GGR_DEV void coop_size_leaf(CoopShared& S, const DecCtx& cx, u32 ei, bool have_masks) {
   const CoopEnt e = S.ent[ei];
@@ -360,6 +421,22 @@ GGR_DEV void coop_size_leaf(CoopShared& S, const DecCtx& cx, u32 ei, bool have_m
     n += 2u + (e.vend - e.body);
   } else if (cls == DC_BYTES) {
     n += 2u + ((e.vend - e.body + 2u) / 3u) * 4u;
+  } else if (cls == DC_STR && !(e.flags & (CF_PACKED | CF_TIMESTAMP))) {
+    // needs escaping / validation: the whole warp sizes it after this loop (the entry keeps the
+    // size of everything but the string's own text until then)
+    const u32 k = wp_atomic_add(&S.n_dirty, 1u);
+    if (k < GGR_COOP_DIRTY_MAX) {
+      S.dlist[k] = (u16)ei;
+      S.ent[ei].size = n + 2u;
+      return;
+    }
+    Cnt c;
+    c.pos = 0;
+    if (coop_leaf_value(c, cx, e, f) != GST_OK) {
+      S.bail = 1;
+      return;
+    }
+    n += c.pos;
   } else {
     Cnt c;
     c.pos = 0;
@@ -463,6 +540,20 @@ GGR_DEV int coop_write_entry(CoopStage& E, const DecCtx& cx, const CoopEnt& e, u
     }
     w.pos += len;
     w.put1('"');
+  } else if (CE_CLASS(e) == DC_STR && !(e.flags & (CF_PACKED | CF_TIMESTAMP))) {
+    // string that needs escaping: text left to the whole warp when the list has room
+    const u32 k = wp_atomic_add(&E.n_long, 1u);
+    if (k < GGR_COOP_LONG_MAX) {
+      w.put1('"');
+      E.lsrc[k] = e.body;
+      E.ldst[k] = w.pos;
+      E.llen[k] = (e.vend - e.body) | 0x80000000u;
+      const u32 tail = (e.flags & CF_ARR_LAST) ? 2u : 1u;
+      E.buf[endpos - tail] = '"';
+      if (e.flags & CF_ARR_LAST) E.buf[endpos - 1] = ']';
+      return GST_OK;
+    }
+    st = coop_leaf_value(w, cx, e, f);
   } else {
     st = coop_leaf_value(w, cx, e, f);
   }
@@ -484,6 +575,7 @@ GGR_DEV bool coop_size_item(CoopShared& S, const DecCtx& cx, u32 root_msg, u32 s
     S.n_ent = 1;
     S.bail = 0;
     S.max_depth = 0;
+    S.n_dirty = 0;
     CoopEnt r0;
     r0.vpos = start; r0.vend = end; r0.gfield = GGR_COOP_ROOT; r0.parent = 0xFFFFu; r0.next = 0xFFFFu;
     r0.size = 0; r0.off = 0; r0.fc_msg = (u16)root_msg; r0.depth = 0;
@@ -534,6 +626,21 @@ GGR_DEV bool coop_size_item(CoopShared& S, const DecCtx& cx, u32 root_msg, u32 s
   for (u32 k = lane; k < n_leaf; k += 32) coop_size_leaf(S, cx, S.order[k], true);
   WP_SYNC();
   if (S.bail) return false;
+  {
+    const u32 nd = S.n_dirty < GGR_COOP_DIRTY_MAX ? S.n_dirty : GGR_COOP_DIRTY_MAX;
+    for (u32 k = 0; k < nd; k++) {
+      const u32 ei = S.dlist[k];
+      bool ok;
+      const u32 js = coop_dirty_size(cx.in, S.ent[ei].body, S.ent[ei].vend, &ok);
+      if (!ok) return false;  // malformed UTF-8: the per-thread kernels report it
+      if (lane == 0) {
+        const u32 total = S.ent[ei].size + js;
+        S.ent[ei].size = total;
+        wp_atomic_add(&S.ent[S.ent[ei].parent].size, total);
+      }
+    }
+    WP_SYNC();
+  }
   const u32 maxd = S.max_depth;
   for (u32 dd = 0; dd <= maxd; dd++) {
     const u32 d = maxd - dd;
@@ -587,7 +694,9 @@ GGR_DEV int coop_write_item(CoopStage& E, const DecCtx& cx, const U4* tab, u32 n
     const u8* src = cx.in + E.lsrc[k];
     u8* d = E.buf + E.ldst[k];
     const u32 len = E.llen[k];
-    for (u32 j = lane; j < len; j += 32) d[j] = src[j];
+    if (len & 0x80000000u) coop_dirty_write(cx.in, E.lsrc[k], E.lsrc[k] + (len & 0x7FFFFFFFu), d);
+    else
+      for (u32 j = lane; j < len; j += 32) d[j] = src[j];
   }
   WP_SYNC();
   wp_copy_out(E.buf, out16, pad, size);

@@ -26,6 +26,7 @@
 #define CE_MAX_DEPTH 24
 #define CE_MAX_INPUT 65000u
 #define CE_NIL 0xFFFFu
+#define NF_SIMPLE 2u /* N_STR with NF_ESC: only two-character escapes (the tokenizer's O(1) sizing) */
 
 enum { TK_LBRACE = 1, TK_RBRACE = 2, TK_LBRACK = 3, TK_RBRACK = 4, TK_COLON = 5, TK_COMMA = 6, TK_STR = 7, TK_SCALAR = 8 };
 #define TK_POS(t) ((t) & 0xFFFFu)
@@ -685,7 +686,7 @@ GGR_DEV void ce_leaf(SH& S, EncCtx& cx, u32 ni) {
       l.type = N_STR;
       l.a = q;
       l.b = len;
-      l.flags = nesc ? NF_ESC : 0;
+      l.flags = nesc ? (NF_ESC | NF_SIMPLE) : 0;
       l.body = varint_size(len) + len;
       l.zero = len == 0;
       done = true;
@@ -911,7 +912,15 @@ GGR_DEV void ce_emit_node(CoopEmit& E, const u8* in, u32 end, const u8* ir, cons
       if (tag) put_varint(w, tag);
       put_varint(w, nd.y);
       if (flags & NF_ESC) {
-        copy_string(w, in, nd.x, end, nd.y, true);
+        u32 k = CE_LONG_MAX;
+        if (flags & NF_SIMPLE) k = wp_atomic_add(&E.n, 1u);
+        if (k < CE_LONG_MAX) {  // decoded by the whole warp
+          E.src[k] = nd.x + 1u;
+          E.dst[k] = w.pos;
+          E.len[k] = nd.y | 0x80000000u;
+        } else {
+          copy_string(w, in, nd.x, end, nd.y, true);
+        }
       } else {
         bool handed = false;
         if (nd.y >= CE_LONG_STR) {
@@ -962,6 +971,36 @@ GGR_DEV void ce_emit_node(CoopEmit& E, const u8* in, u32 end, const u8* ir, cons
   }
 }
 
+// escaped positions of 32 bytes from their backslash mask (run parity as in the tokenizer)
+GGR_DEV u32 ce_escaped32(u32 B, u32 cin, u32* cout) {
+  B &= ~cin;
+  const u64 follows = ((u64)B << 1) | cin;
+  const u32 EVEN = 0x55555555u;
+  const u32 odd_starts = B & ~EVEN & ~(u32)follows;
+  const u64 sum = (u64)odd_starts + B;
+  *cout = (u32)(sum >> 32) & 1u;
+  return (EVEN ^ (u32)(sum << 1)) & (u32)follows;
+}
+// all lanes: JSON string text at in[src..) with two-character escapes only -> dec_len raw bytes at d[0..)
+GGR_DEV void ce_unescape_coop(const u8* in, u32 src, u8* d, u32 dec_len) {
+  const u32 lane = wp_lane();
+  const u32 lt = (1u << lane) - 1u;
+  u32 carry = 0, produced = 0;
+  while (produced < dec_len) {
+    u32 c = in[src + lane];
+    const u32 Bm = WP_BALLOT(c == '\\');
+    u32 cout;
+    const u32 E = ce_escaped32(Bm, carry, &cout);
+    const u32 emitm = ~(Bm & ~E);  // escape introducers produce nothing
+    if ((E >> lane) & 1u) c = c == 'b' ? 8u : c == 'f' ? 12u : c == 'n' ? 10u : c == 'r' ? 13u : c == 't' ? 9u : c;
+    const u32 idx = produced + wp_popc(emitm & lt);
+    if (((emitm >> lane) & 1u) && idx < dec_len) d[idx] = (u8)c;
+    produced += wp_popc(emitm);
+    carry = cout;
+    src += 32;
+  }
+}
+
 // One item, all 32 lanes: size bytes to dst.
 GGR_DEV void ce_emit_item(CoopEmit& E, const u8* in, u32 end, const u8* ir, const u32* ioff, u32 n_nodes, u8* dst, u32 size) {
   const u32 lane = wp_lane();
@@ -976,7 +1015,9 @@ GGR_DEV void ce_emit_item(CoopEmit& E, const u8* in, u32 end, const u8* ir, cons
     const u8* src = in + E.src[k];
     u8* d = E.buf + E.dst[k];
     const u32 len = E.len[k];
-    for (u32 j = lane; j < len; j += 32) d[j] = src[j];
+    if (len & 0x80000000u) ce_unescape_coop(in, E.src[k], d, len & 0x7FFFFFFFu);
+    else
+      for (u32 j = lane; j < len; j += 32) d[j] = src[j];
   }
   WP_SYNC();
   wp_copy_out(E.buf, dst - pad, pad, size);

@@ -97,8 +97,8 @@ struct ggr_engine {
   // host-buffer entry points: the batch is cut into chunks that move through `n_slots` slots
   // (stream + staging + scratch each), so that H2D, kernels and D2H of different chunks overlap
   Slot slots[GGR_MAX_SLOTS];
-  int n_slots = 4;
-  int64_t chunk_items = 16384;
+  int n_slots = 6;
+  int64_t chunk_items = 8192;
   // per-kernel timing
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
