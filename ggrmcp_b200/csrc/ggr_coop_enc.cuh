@@ -63,6 +63,7 @@ struct CoopEncT {
   u16 queue[MN];
   u16 last_open[32];
   u32 cls_cnt[CC_N], cls_cur[CC_N];
+  u32 dep_beg[CE_MAX_DEPTH + 2], dep_cur[CE_MAX_DEPTH + 2];  // containers bucketed by depth (in `queue`)
   u32 n_tok, n_q, n_node, q_end, n_leaf, max_depth, bail, cap;
 };
 typedef CoopEncT<1024, 512, 224> CoopEnc;        // tier 1: ~12 KB per warp
@@ -192,16 +193,19 @@ GGR_DEV void ce_tokenize(SH& S, const CeLut& L, const u8* in, u32 start, u32 end
       if (((EC & 0xFFFFu) | ci) != (HI & ~C6)) S.bail = 1;
     }
     // escaped bytes: the carry into a chunk only matters through an all-backslash chunk
-    u32 co0, co1;
-    u32 E0 = ce_escaped(B, 0, &co0);
-    u32 E1 = ce_escaped(B, 1, &co1);
-    u32 Pm = WP_BALLOT(co0 != co1);
-    u32 Gm = WP_BALLOT(co0 != 0);
-    u32 np = ~Pm & lt;
-    u32 cin = np ? ((Gm >> (31u - wp_clz(np))) & 1u) : c_carry;
-    u32 E = cin ? E1 : E0;
-    u32 cout = cin ? co1 : co0;
-    c_carry = WP_SHFL(cout, 31);
+    u32 E = 0;
+    if (WP_ANY(B != 0) || c_carry) {  // most rounds hold no backslash at all
+      u32 co0, co1;
+      u32 E0 = ce_escaped(B, 0, &co0);
+      u32 E1 = ce_escaped(B, 1, &co1);
+      u32 Pm = WP_BALLOT(co0 != co1);
+      u32 Gm = WP_BALLOT(co0 != 0);
+      u32 np = ~Pm & lt;
+      u32 cin = np ? ((Gm >> (31u - wp_clz(np))) & 1u) : c_carry;
+      E = cin ? E1 : E0;
+      u32 cout = cin ? co1 : co0;
+      c_carry = WP_SHFL(cout, 31);
+    }
     u32 RQ = Q & ~E;
     // escape sequences: introducers, and escaped characters outside the simple set (incl. \u)
     const u32 EI = B & ~E;
@@ -809,12 +813,14 @@ GGR_DEV bool ce_parse_item(SH& S, const CeLut& lut, const Tables& T, u32 root_ms
     qb = qe;
   }
   const u32 n = S.n_node;
-  // T4: bucket the leaves by class, then one lane per leaf
+  // T4: bucket the leaves by class and the containers by depth (into `queue`, free since T3)
   if (lane < CC_N) S.cls_cnt[lane] = 0;
+  if (lane < CE_MAX_DEPTH + 2) S.dep_cur[lane] = 0;
   WP_SYNC();
   for (u32 i = lane; i < n; i += 32) {
-    u32 c = S.node[i].cls;
+    const u32 c = S.node[i].cls;
     if (c >= CC_NULL) wp_atomic_add(&S.cls_cnt[c], 1u);
+    else wp_atomic_add(&S.dep_cur[S.node[i].depth], 1u);
   }
   WP_SYNC();
   if (lane == 0) {
@@ -825,10 +831,21 @@ GGR_DEV bool ce_parse_item(SH& S, const CeLut& lut, const Tables& T, u32 root_ms
     }
     S.n_leaf = run;
   }
+  if (lane == 1) {
+    u32 run = 0;
+    for (u32 d = 0; d < CE_MAX_DEPTH + 1; d++) {
+      const u32 c = S.dep_cur[d];
+      S.dep_beg[d] = run;
+      S.dep_cur[d] = run;
+      run += c;
+    }
+    S.dep_beg[CE_MAX_DEPTH + 1] = run;
+  }
   WP_SYNC();
   for (u32 i = lane; i < n; i += 32) {
-    u32 c = S.node[i].cls;
+    const u32 c = S.node[i].cls;
     if (c >= CC_NULL) S.order[wp_atomic_add(&S.cls_cur[c], 1u)] = (u16)i;
+    else S.queue[wp_atomic_add(&S.dep_cur[S.node[i].depth], 1u)] = (u16)i;
   }
   WP_SYNC();
   const u32 n_leaf = S.n_leaf;
@@ -836,11 +853,10 @@ GGR_DEV bool ce_parse_item(SH& S, const CeLut& lut, const Tables& T, u32 root_ms
   WP_SYNC();
   if (S.bail) return false;
   // T5: containers, deepest first (the root, depth 0, has no node of its own in the IR)
-  for (u32 d = S.max_depth; d >= 1; d--) {
-    for (u32 i = lane; i < n; i += 32) {
-      CNode nd = S.node[i];
-      if (nd.depth == d && nd.cls <= CC_ENTRY) ce_close_container(S, cx, i);
-    }
+  const u32 maxd = S.max_depth;
+  for (u32 d = maxd; d >= 1; d--) {
+    const u32 b = S.dep_beg[d], e = S.dep_beg[d + 1];
+    for (u32 k = b + lane; k < e; k += 32) ce_close_container(S, cx, S.queue[k]);
     WP_SYNC();
   }
   // T6: offsets, top-down (the root message has no header)
@@ -849,11 +865,9 @@ GGR_DEV bool ce_parse_item(SH& S, const CeLut& lut, const Tables& T, u32 root_ms
     S.tok[0] = 0;
   }
   WP_SYNC();
-  for (u32 d = 0; d < S.max_depth; d++) {
-    for (u32 i = lane; i < n; i += 32) {
-      const u32 c = S.node[i].cls;
-      if (S.node[i].depth == d && c <= CC_ENTRY) ce_place_children(S, i);
-    }
+  for (u32 d = 0; d < maxd; d++) {
+    const u32 b = S.dep_beg[d], e = S.dep_beg[d + 1];
+    for (u32 k = b + lane; k < e; k += 32) ce_place_children(S, S.queue[k]);
     WP_SYNC();
   }
   for (u32 i = lane; i < n; i += 32) ioff[i] = S.tok[i];
