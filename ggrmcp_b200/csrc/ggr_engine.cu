@@ -54,6 +54,34 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(u64* __restrict__ sums, lo
   if (t == 1023) *total_out = part[1023];
 }
 
+// One thread per item: items whose input size lies in [min_bytes, max_bytes] go to `big` (the
+// lock-step kernels), the others to `small` (the per-thread kernels); order within the lists does
+// not matter.  mode != nullptr: every item starts as PENDING (reply side).
+__global__ void __launch_bounds__(256) k_route(long long n, const u64* __restrict__ in_off, u32 min_bytes, u32 max_bytes,
+                                               u32* __restrict__ big, u32* __restrict__ n_big, u32* __restrict__ small,
+                                               u32* __restrict__ n_small, u32* __restrict__ mode) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  bool is_big = false, is_small = false;
+  if (i < n) {
+    const u64 len = in_off[i + 1] - in_off[i];
+    is_big = len >= min_bytes && len <= max_bytes;
+    is_small = !is_big;
+    if (mode) mode[i] = 0xFFu;
+  }
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned mb = __ballot_sync(0xFFFFFFFFu, is_big), ms = __ballot_sync(0xFFFFFFFFu, is_small);
+  unsigned bb = 0, bs = 0;
+  if (lane == 0) {
+    if (mb) bb = atomicAdd(n_big, (u32)__popc(mb));
+    if (ms && small) bs = atomicAdd(n_small, (u32)__popc(ms));
+  }
+  bb = __shfl_sync(0xFFFFFFFFu, bb, 0);
+  bs = __shfl_sync(0xFFFFFFFFu, bs, 0);
+  const unsigned lt = (1u << lane) - 1u;
+  if (is_big) big[bb + __popc(mb & lt)] = (u32)i;
+  if (is_small && small) small[bs + __popc(ms & lt)] = (u32)i;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -94,6 +122,9 @@ struct ggr_engine {
   // batch and a reply batch can be in flight on two streams at the same time
   Scratch dev_sc[2];
   bool use_coop_enc = true;  // GGR_COOP_ENC=0 disables the lock-step request-side parser (A/B runs)
+  // items smaller than this go straight to the per-thread kernels, which are cheaper for them
+  // (GGR_LOCKSTEP_MIN_BYTES overrides both; 0 sends everything through the lock-step kernels)
+  uint32_t min_json = 1024, min_wire = 640;
   // host-buffer entry points: the batch is cut into chunks that move through `n_slots` slots
   // (stream + staging + scratch each), so that H2D, kernels and D2H of different chunks overlap
   Slot slots[GGR_MAX_SLOTS];
@@ -166,6 +197,7 @@ int ggr_engine_create(const ggr_config* cfg, ggr_engine** out) {
   if (e->sm_count <= 0) e->sm_count = 148;
   if (const char* nc = getenv("GGR_COOP")) e->use_coop = nc[0] != '0';
   if (const char* nc = getenv("GGR_COOP_ENC")) e->use_coop_enc = nc[0] != '0';
+  if (const char* nc = getenv("GGR_LOCKSTEP_MIN_BYTES")) e->min_json = e->min_wire = (uint32_t)strtoul(nc, nullptr, 10);
   if (const char* nc = getenv("GGR_SLOTS")) {
     int v = atoi(nc);
     if (v >= 1 && v <= GGR_MAX_SLOTS) e->n_slots = v;
@@ -344,22 +376,27 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
   if (encode) {
     if (e->use_coop_enc) {
       // lock-step parser first (one warp per item); what it leaves goes to the per-thread parser
-      if (!ensure(e, sc.pend, (size_t)n * 8 + 64) || !ensure(e, sc.ioff, (size_t)in_bytes * 2 + (size_t)n * 32 + 64) ||
+      if (!ensure(e, sc.pend, (size_t)n * 12 + 64) || !ensure(e, sc.ioff, (size_t)in_bytes * 2 + (size_t)n * 32 + 64) ||
           !ensure(e, sc.nn, (size_t)n * 4))
         return GGR_ERR_CUDA;
-      u32* counters = (u32*)sc.pend.p;  // [0] left by tier 1, [4] left by tier 2
-      u32* pend1 = counters + 16;
+      u32* counters = (u32*)sc.pend.p;  // [0] lock-step items, [4] left by tier 1, [8] per-thread items
+      u32* big = counters + 16;
+      u32* pend1 = big + n;
       u32* pend2 = pend1 + n;
       size_t c0 = 0, c1 = 0;
-      if (!cuda_ok(e, cudaMemsetAsync(counters, 0, 64, st), "memset")) return GGR_ERR_CUDA;
+      if (!cuda_ok(e, cudaMemsetAsync(counters, 0, 64, st), "memset") ||
+          !cuda_ok(e, cudaMemsetAsync(sc.nn.p, 0, (size_t)n * 4, st), "memset"))
+        return GGR_ERR_CUDA;
       if (prof) prof_mark(e, st, &m0);
+      // router: small (and oversized) items straight to the per-thread parser
+      k_route<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, in_off, e->min_json, 65000u - 16u, big, counters, pend2, counters + 8, nullptr);
       ggr_launch_encode_coop_parse(st, 0, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
-                                   (u32*)sc.aux.p, status, (u32*)sc.ioff.p, (u32*)sc.nn.p, nullptr, nullptr, pend1, counters, e->sm_count);
+                                   (u32*)sc.aux.p, status, (u32*)sc.ioff.p, (u32*)sc.nn.p, big, counters, pend1, counters + 4, e->sm_count);
       ggr_launch_encode_coop_parse(st, 1, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
-                                   (u32*)sc.aux.p, status, (u32*)sc.ioff.p, (u32*)sc.nn.p, pend1, counters, pend2, counters + 4, e->sm_count);
+                                   (u32*)sc.aux.p, status, (u32*)sc.ioff.p, (u32*)sc.nn.p, pend1, counters + 4, pend2, counters + 8, e->sm_count);
       if (prof) prof_mark(e, st, &c0);
       ggr_launch_encode_parse(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
-                              (u32*)sc.aux.p, status, (u64*)sc.sums.p, pend2, counters + 4);
+                              (u32*)sc.aux.p, status, (u64*)sc.sums.p, pend2, counters + 8);
       if (prof) prof_mark(e, st, &c1);
       ggr_launch_block_sums(st, (unsigned)nb, n, (const u32*)sc.size.p, (u64*)sc.sums.p);
       if (prof) {
@@ -368,7 +405,7 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
         prof_mark(e, st, &m1);
         e->spans.push_back({9, c1, m1});
       }
-      e->launches += 3;
+      e->launches += 4;
     } else {
       ggr_launch_encode_parse(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
                               (u32*)sc.aux.p, status, (u64*)sc.sums.p, nullptr, nullptr);
@@ -386,7 +423,8 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
         have_mx = true;
       }
       ggr_launch_encode_coop_emit(st, n, in, in_off, (const u8*)sc.ir.p, (const u32*)sc.ioff.p, (const u32*)sc.nn.p,
-                                  (const u32*)sc.size.p, status, out, out_off, e->sm_count);
+                                  (const u32*)sc.size.p, status, out, out_off, e->sm_count, (const u32*)sc.pend.p + 16,
+                                  (const u32*)sc.pend.p);
       if (prof) {
         prof_mark(e, st, &x1);
         e->spans.push_back({10, mx, x1});
@@ -399,9 +437,15 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
     const bool coop = e->use_coop;
     size_t c0 = 0, c1 = 0;
     if (coop) {
-      if (!ensure(e, sc.ir, ggr_decode_coop_table_bytes(n)) || !ensure(e, sc.nn, (size_t)n * 4)) return GGR_ERR_CUDA;
+      if (!ensure(e, sc.ir, ggr_decode_coop_table_bytes(n)) || !ensure(e, sc.nn, (size_t)n * 4) ||
+          !ensure(e, sc.pend, (size_t)n * 4 + 64))
+        return GGR_ERR_CUDA;
+      u32* counters = (u32*)sc.pend.p;
+      u32* big = counters + 16;
+      if (!cuda_ok(e, cudaMemsetAsync(counters, 0, 64, st), "memset")) return GGR_ERR_CUDA;
+      k_route<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, in_off, e->min_wire, 8192u - 16u, big, counters, nullptr, nullptr, (u32*)sc.aux.p);
       ggr_launch_decode_coop_size(st, n, s->d_blob, n_msgs, msg_id, in, in_off, flags, (u32*)sc.size.p, (u32*)sc.aux.p, status,
-                                  sc.ir.p, (u32*)sc.nn.p, e->sm_count);
+                                  sc.ir.p, (u32*)sc.nn.p, e->sm_count, big, counters);
       if (prof) {
         prof_mark(e, st, &c0);
         e->spans.push_back({6, m0, c0});
@@ -418,7 +462,7 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
     if (coop) {
       if (prof) prof_mark(e, st, &c1);
       ggr_launch_decode_coop_write(st, n, s->d_blob, in, in_off, flags, (const u32*)sc.size.p, (const u32*)sc.aux.p, status, sc.ir.p,
-                                   (const u32*)sc.nn.p, out, out_off, e->sm_count);
+                                   (const u32*)sc.nn.p, out, out_off, e->sm_count, (const u32*)sc.pend.p + 16, (const u32*)sc.pend.p);
       if (prof) {
         prof_mark(e, st, &m3);
         e->spans.push_back({3, m0, m1});
@@ -426,7 +470,7 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
         e->spans.push_back({5, m2, c1});
         e->spans.push_back({7, c1, m3});
       }
-      e->launches += 5;
+      e->launches += 6;
       return cuda_ok(e, cudaGetLastError(), "kernel launch") ? GGR_SUCCESS : GGR_ERR_CUDA;
     }
   }

@@ -15,7 +15,8 @@ void ggr_launch_encode_coop_parse(cudaStream_t st, int tier, long long n, const 
                                   const uint32_t* list_n, uint32_t* pending, uint32_t* n_pending, int sm_count);
 void ggr_launch_encode_coop_emit(cudaStream_t st, long long n, const uint8_t* in, const uint64_t* in_off, const uint8_t* ir,
                                  const uint32_t* ioff, const uint32_t* nnodes, const uint32_t* size, const int32_t* status,
-                                 uint8_t* out, const uint64_t* out_off, int sm_count);
+                                 uint8_t* out, const uint64_t* out_off, int sm_count, const uint32_t* list,
+                                 const uint32_t* list_n);
 int ggr_encode_coop_init();  // opts the kernels into their dynamic shared memory sizes
 void ggr_launch_encode_emit(cudaStream_t st, unsigned nb, long long n, const uint8_t* in, const uint64_t* in_off, const uint8_t* ir,
                             const uint32_t* size, const uint32_t* first, int32_t* status, const uint64_t* block_prefix,
@@ -29,10 +30,12 @@ void ggr_launch_decode_write(cudaStream_t st, unsigned nb, const uint8_t* blob, 
                              uint64_t out_cap, uint64_t* out_off);
 void ggr_launch_decode_coop_size(cudaStream_t st, long long n, const uint8_t* blob, uint32_t n_msgs, const int32_t* msg_id,
                                  const uint8_t* in, const uint64_t* in_off, uint32_t flags, uint32_t* size, uint32_t* mode,
-                                 int32_t* status, void* tab, uint32_t* nent, int sm_count);
+                                 int32_t* status, void* tab, uint32_t* nent, int sm_count, const uint32_t* list,
+                                 const uint32_t* list_n);
 void ggr_launch_decode_coop_write(cudaStream_t st, long long n, const uint8_t* blob, const uint8_t* in, const uint64_t* in_off,
                                   uint32_t flags, const uint32_t* size, const uint32_t* mode, int32_t* status, const void* tab,
-                                  const uint32_t* nent, uint8_t* out, const uint64_t* out_off, int sm_count);
+                                  const uint32_t* nent, uint8_t* out, const uint64_t* out_off, int sm_count,
+                                  const uint32_t* list, const uint32_t* list_n);
 size_t ggr_decode_coop_table_bytes(long long n);  // scratch the size kernel needs for the entry tables
 int ggr_decode_coop_init();
 const void* ggr_kernel_encode_parse();  // for cudaFuncGetAttributes (is the sm_100a image loadable?)

@@ -10,14 +10,18 @@
 __global__ void __launch_bounds__(COOP_WARPS * 32)
 k_decode_coop_size(const u8* __restrict__ blob, long long n, u32 n_msgs, const i32* __restrict__ msg_id,
                    const u8* __restrict__ in, const u64* __restrict__ in_off, u32 flags, u32* __restrict__ size,
-                   u32* __restrict__ mode, i32* __restrict__ status, U4* __restrict__ tab, u32* __restrict__ nent) {
+                   u32* __restrict__ mode, i32* __restrict__ status, U4* __restrict__ tab, u32* __restrict__ nent,
+                   const u32* __restrict__ list, const u32* __restrict__ list_n) {
   extern __shared__ __align__(16) unsigned char smem[];
   CoopShared* S = reinterpret_cast<CoopShared*>(smem);
   const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   DecCtx cx;
   cx.T = ggr_tables(blob);
   cx.flags = flags;
-  for (long long item = (long long)blockIdx.x * COOP_WARPS + warp; item < n; item += (long long)gridDim.x * COOP_WARPS) {
+  // the items of `list` (the router's choice: not too small, not too large); mode[] is PENDING for all others
+  const long long total = (long long)*list_n;
+  for (long long slot = (long long)blockIdx.x * COOP_WARPS + warp; slot < total; slot += (long long)gridDim.x * COOP_WARPS) {
+    const long long item = (long long)list[slot];
     const u64 a = in_off[item], b = in_off[item + 1];
     const i32 m = msg_id[item];
     bool ok = false;
@@ -46,14 +50,16 @@ __global__ void __launch_bounds__(COOP_WRITE_WARPS * 32)
 k_decode_coop_write(const u8* __restrict__ blob, long long n, const u8* __restrict__ in, const u64* __restrict__ in_off,
                     u32 flags, const u32* __restrict__ size, const u32* __restrict__ mode, i32* __restrict__ status,
                     const U4* __restrict__ tab, const u32* __restrict__ nent, u8* __restrict__ out,
-                    const u64* __restrict__ out_off) {
+                    const u64* __restrict__ out_off, const u32* __restrict__ list, const u32* __restrict__ list_n) {
   extern __shared__ __align__(16) unsigned char smem[];
   CoopStage* E = reinterpret_cast<CoopStage*>(smem);
   const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   DecCtx cx;
   cx.T = ggr_tables(blob);
   cx.flags = flags;
-  for (long long item = (long long)blockIdx.x * COOP_WRITE_WARPS + warp; item < n; item += (long long)gridDim.x * COOP_WRITE_WARPS) {
+  const long long total = (long long)*list_n;
+  for (long long slot = (long long)blockIdx.x * COOP_WRITE_WARPS + warp; slot < total; slot += (long long)gridDim.x * COOP_WRITE_WARPS) {
+    const long long item = (long long)list[slot];
     if (mode[item] != GGR_MODE_COOP || status[item] != GST_OK) continue;
     const u64 a = in_off[item];
     cx.in = in + (a & ~15ull);
@@ -77,15 +83,17 @@ static unsigned coop_grid(long long n, int sm_count) {
 
 void ggr_launch_decode_coop_size(cudaStream_t st, long long n, const uint8_t* blob, uint32_t n_msgs, const int32_t* msg_id,
                                  const uint8_t* in, const uint64_t* in_off, uint32_t flags, uint32_t* size, uint32_t* mode,
-                                 int32_t* status, void* tab, uint32_t* nent, int sm_count) {
+                                 int32_t* status, void* tab, uint32_t* nent, int sm_count, const uint32_t* list,
+                                 const uint32_t* list_n) {
   k_decode_coop_size<<<coop_grid(n, sm_count), COOP_WARPS * 32, coop_smem_bytes(), st>>>(
-      blob, n, n_msgs, msg_id, in, (const u64*)in_off, flags, size, mode, status, (U4*)tab, nent);
+      blob, n, n_msgs, msg_id, in, (const u64*)in_off, flags, size, mode, status, (U4*)tab, nent, list, list_n);
 }
 void ggr_launch_decode_coop_write(cudaStream_t st, long long n, const uint8_t* blob, const uint8_t* in, const uint64_t* in_off,
                                   uint32_t flags, const uint32_t* size, const uint32_t* mode, int32_t* status, const void* tab,
-                                  const uint32_t* nent, uint8_t* out, const uint64_t* out_off, int sm_count) {
+                                  const uint32_t* nent, uint8_t* out, const uint64_t* out_off, int sm_count,
+                                  const uint32_t* list, const uint32_t* list_n) {
   long long want = (n + COOP_WRITE_WARPS - 1) / COOP_WRITE_WARPS, cap = (long long)sm_count * 6;
   unsigned nb = (unsigned)(want < cap ? want : cap);
   k_decode_coop_write<<<nb, COOP_WRITE_WARPS * 32, sizeof(CoopStage) * COOP_WRITE_WARPS, st>>>(
-      blob, n, in, (const u64*)in_off, flags, size, mode, status, (const U4*)tab, nent, out, (const u64*)out_off);
+      blob, n, in, (const u64*)in_off, flags, size, mode, status, (const U4*)tab, nent, out, (const u64*)out_off, list, list_n);
 }

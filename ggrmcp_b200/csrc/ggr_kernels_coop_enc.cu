@@ -64,12 +64,15 @@ k_encode_coop_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const 
 __global__ void __launch_bounds__(CE_WARPS * 32)
 k_encode_coop_emit(long long n, const u8* __restrict__ in, const u64* __restrict__ in_off, const u8* __restrict__ ir,
                    const u32* __restrict__ ioff, const u32* __restrict__ nnodes, const u32* __restrict__ size,
-                   const i32* __restrict__ status, u8* __restrict__ out, const u64* __restrict__ out_off) {
+                   const i32* __restrict__ status, u8* __restrict__ out, const u64* __restrict__ out_off,
+                   const u32* __restrict__ list, const u32* __restrict__ list_n) {
   extern __shared__ __align__(16) unsigned char smem[];
   CoopEmit* E = reinterpret_cast<CoopEmit*>(smem);
   const u32 warp = threadIdx.x >> 5;
   const u64 a0 = in_off[0];
-  for (long long item = (long long)blockIdx.x * CE_WARPS + warp; item < n; item += (long long)gridDim.x * CE_WARPS) {
+  const long long total = (long long)*list_n;  // the router's lock-step items
+  for (long long slot = (long long)blockIdx.x * CE_WARPS + warp; slot < total; slot += (long long)gridDim.x * CE_WARPS) {
+    const long long item = (long long)list[slot];
     const u32 nn = nnodes[item];
     const u32 sz = size[item];
     if (nn <= 1 || sz == 0 || status[item] != GST_OK) continue;
@@ -115,9 +118,10 @@ void ggr_launch_encode_coop_parse(cudaStream_t st, int tier, long long n, const 
 
 void ggr_launch_encode_coop_emit(cudaStream_t st, long long n, const uint8_t* in, const uint64_t* in_off, const uint8_t* ir,
                                  const uint32_t* ioff, const uint32_t* nnodes, const uint32_t* size, const int32_t* status,
-                                 uint8_t* out, const uint64_t* out_off, int sm_count) {
+                                 uint8_t* out, const uint64_t* out_off, int sm_count, const uint32_t* list,
+                                 const uint32_t* list_n) {
   long long want = (n + CE_WARPS - 1) / CE_WARPS, cap = (long long)sm_count * 6;
   unsigned nb = (unsigned)(want < cap ? want : cap);
   k_encode_coop_emit<<<nb, CE_WARPS * 32, sizeof(CoopEmit) * CE_WARPS, st>>>(n, in, (const u64*)in_off, ir, ioff, nnodes, size, status, out,
-                                                   (const u64*)out_off);
+                                                                             (const u64*)out_off, list, list_n);
 }

@@ -34,11 +34,14 @@ def hsim(fds_bytes):
 # every GPU test runs against each kernel path: the default (lock-step kernels in front of the
 # per-thread kernels on both sides), the per-thread kernels alone, the lock-step request side only
 _ENGINE_PATHS = {
-    "default": {},
+    # everything through the lock-step kernels first (the size routing would send the small test items
+    # straight to the per-thread kernels)
+    "default": {"GGR_LOCKSTEP_MIN_BYTES": "0"},
+    "size_routing": {},
     "per_thread": {"GGR_COOP_ENC": "0", "GGR_COOP": "0"},
-    "lockstep_request_only": {"GGR_COOP": "0"},
+    "lockstep_request_only": {"GGR_COOP": "0", "GGR_LOCKSTEP_MIN_BYTES": "0"},
     # host entry points cut into many small chunks over two slots: exercises the copy/compute pipeline
-    "small_chunks": {"GGR_CHUNK_ITEMS": "128", "GGR_SLOTS": "2"},
+    "small_chunks": {"GGR_CHUNK_ITEMS": "128", "GGR_SLOTS": "2", "GGR_LOCKSTEP_MIN_BYTES": "0"},
 }
 
 
