@@ -26,6 +26,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+WORKLOAD_NAMES = {
+    "nested": "configs[2] nested+repeated ~4KB JSON (complex.proto ProcessNodeRequest/CreateDocumentRequest; replies Node/GetUserProfileResponse)",
+    "flat": "configs[1] 64K flat-scalar bench.Flat ~256B JSON",
+    "blob": "configs[3] bench.Blob 64KiB bytes replies (reply side only)",
+}
 METRIC = "tools_call_transcodes_per_sec"
 UNIT = "transcodes/s"
 
@@ -133,7 +138,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * t_sum / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": args.workload, "items_per_step": sample, "boundary": "InvokeMethod (arguments JSON <-> wire <-> protojson)"},
+        "config": {"workload": WORKLOAD_NAMES.get(args.workload, args.workload), "items_per_gpu": args.items,
+                   "items_per_step_timed": sample, "boundary": "InvokeMethod (arguments JSON -> wire, wire -> protojson)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d items of the %s workload per step, oracle C++ port, %d threads" % (sample, args.workload, cores)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -345,8 +351,14 @@ def main():
     roofline = None
     if dom:
         a = kern[dom]["gbs"]
+        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this
+        # very configuration (profiles/ncu_r1_final_lockstep_kernels_151552items.csv: dram__bytes_read.sum +
+        # dram__bytes_write.sum of k_encode_coop_parse, small-table tier); other configurations: not captured
+        traffic = None
+        if dom == "encode_coop_parse" and args.workload == "nested" and n == 148 * 1024:
+            traffic = int(559.120896e6 + 330.975744e6)
         roofline = {"bound": "hbm", "kernel": dom, "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
-                    "traffic": None, "peak_source": peak_src,
+                    "traffic": traffic, "peak_source": peak_src,
                     "step_read_gbs": (J_in + W_in) / (step_ms / 1000.0) / 1e9,
                     "step_total_gbs": (J_in + W_in + W_out + J_out) / (step_ms / 1000.0) / 1e9,
                     "kernels": kern}
@@ -363,9 +375,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
-        "config": {"workload": {"nested": "configs[2] nested+repeated ~4KB JSON (complex.proto ProcessNodeRequest/CreateDocumentRequest; replies Node/GetUserProfileResponse)",
-                                "flat": "configs[1] 64K flat-scalar bench.Flat ~256B JSON",
-                                "blob": "configs[3] bench.Blob 64KiB bytes replies (reply side only)"}[args.workload],
+        "config": {"workload": WORKLOAD_NAMES[args.workload],
                    "items_per_gpu": n, "boundary": "InvokeMethod (arguments JSON -> wire, wire -> protojson)",
                    "avg_bytes": {"J_in": J_in / n, "W_out": W_out / n, "W_in": W_in / n, "J_out": J_out / n},
                    "l2": "inputs exceed L2 (%.0f MB read per step)" % ((J_in + W_in) / 1e6), "parallelism": "shard-by-index x%d, no collective" % world},
