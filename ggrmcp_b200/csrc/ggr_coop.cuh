@@ -409,6 +409,73 @@ GGR_DEV void coop_dirty_write(const u8* in, u32 s, u32 e, u8* d) {
   }
 }
 
+// all lanes: copy len bytes in[src..) -> d[0..), 4 bytes per lane and step once d is 4-byte aligned
+GGR_DEV void coop_copy_words(const u8* in, u32 src, u8* d, u32 len) {
+  const u32 lane = wp_lane();
+  u32 head = (4u - (wp_align_pad(d) & 3u)) & 3u;
+  if (head > len) head = len;
+  if (lane < head) d[lane] = in[src + lane];
+  src += head;
+  d += head;
+  len -= head;
+  const u32 words = len >> 2;
+  const u32 sh = (src & 3u) * 8u;
+  const u8* sa = in + (src & ~3u);
+  for (u32 k = lane; k < words; k += 32) {
+    u32 lo = ggr_ld4(sa + 4u * k);
+    u32 v = lo;
+    if (sh) {
+      u32 hi = ggr_ld4(sa + 4u * k + 4u);
+      v = (lo >> sh) | (hi << (32u - sh));
+    }
+    ggr_st4(d + 4u * k, v);
+  }
+  const u32 tail = len & 3u;
+  if (lane < tail) d[4u * words + lane] = in[src + 4u * words + lane];
+}
+// all lanes: standard base64 (padded) of in[src, src + len) -> d[0..): 3 bytes per lane and step
+GGR_DEV void coop_base64(const u8* in, u32 src, u32 len, u8* d) {
+  const u32 lane = wp_lane();
+  const u32 groups = len / 3u;
+  for (u32 g = lane; g < groups; g += 32) {
+    const u8* p = in + src + 3u * g;
+    const u32 v = ((u32)p[0] << 16) | ((u32)p[1] << 8) | (u32)p[2];
+    u8* o = d + 4u * g;
+    o[0] = (u8)b64_char(v >> 18);
+    o[1] = (u8)b64_char((v >> 12) & 63u);
+    o[2] = (u8)b64_char((v >> 6) & 63u);
+    o[3] = (u8)b64_char(v & 63u);
+  }
+  const u32 rem = len - groups * 3u;
+  if (rem && lane == 0) {
+    const u8* p = in + src + 3u * groups;
+    u8* o = d + 4u * groups;
+    const u32 v = ((u32)p[0] << 16) | (rem == 2u ? (u32)p[1] << 8 : 0u);
+    o[0] = (u8)b64_char(v >> 18);
+    o[1] = (u8)b64_char((v >> 12) & 63u);
+    o[2] = rem == 2u ? (u8)b64_char((v >> 6) & 63u) : (u8)'=';
+    o[3] = '=';
+  }
+}
+// all lanes: does in[s, e) hold only plain text bytes?  512 bytes per step
+GGR_DEV bool coop_plain_check(const u8* in, u32 s, u32 e) {
+  const u32 lane = wp_lane();
+  u32 any = 0;
+  for (u32 c0 = s & ~15u; c0 < e; c0 += 512u) {
+    const u32 c = c0 + (lane << 4);
+    u32 D = 0;
+    if (c < e) {
+      const U4 v = ggr_ld16(in + c);
+      D = coop_pack4(coop_dirty_flags(v.x)) | (coop_pack4(coop_dirty_flags(v.y)) << 4) | (coop_pack4(coop_dirty_flags(v.z)) << 8) |
+          (coop_pack4(coop_dirty_flags(v.w)) << 12);
+      if (c < s) D &= 0xFFFFu << (s - c);
+      if (c + 16u > e) D &= 0xFFFFu >> (c + 16u - e);
+    }
+    any |= D;
+  }
+  return !WP_ANY(any != 0);
+}
+
 // R3, one lane: size of leaf entry ei (full text) added to its parent
 GGR_DEV void coop_size_leaf(CoopShared& S, const DecCtx& cx, u32 ei, bool have_masks) {
   const CoopEnt e = S.ent[ei];
@@ -491,12 +558,12 @@ struct CoopStage {
   u32 n_long, bad;
 };
 // R4, one lane: text of entry e into the staging buffer at pad + e.off
-GGR_DEV int coop_write_entry(CoopStage& E, const DecCtx& cx, const CoopEnt& e, u32 pad) {
+GGR_DEV int coop_write_entry(CoopStage& E, const DecCtx& cx, const CoopEnt& e, u8* B) {
   Sw w;
-  w.init(E.buf, pad + e.off);
+  w.init(B, e.off);
   if (e.gfield == GGR_COOP_ROOT) {
-    E.buf[pad + e.off] = '{';
-    E.buf[pad + e.off + e.size - 1] = '}';
+    B[e.off] = '{';
+    B[e.off + e.size - 1] = '}';
     return GST_OK;
   }
   const FieldD f = ggr_field(cx.T, e.gfield);
@@ -509,14 +576,14 @@ GGR_DEV int coop_write_entry(CoopStage& E, const DecCtx& cx, const CoopEnt& e, u
     for (u32 j = 0; j < f.name_len; j++) w.put1(nm[j]);
   }
   if (e.flags & CF_ARR_FIRST) w.put1('[');
-  const u32 endpos = pad + e.off + e.size;
+  const u32 endpos = e.off + e.size;
   if (e.flags & CF_MSG) {
     w.put1('{');
     if (e.flags & CF_ARR_LAST) {
-      E.buf[endpos - 2] = '}';
-      E.buf[endpos - 1] = ']';
+      B[endpos - 2] = '}';
+      B[endpos - 1] = ']';
     } else {
-      E.buf[endpos - 1] = '}';
+      B[endpos - 1] = '}';
     }
     return GST_OK;
   }
@@ -536,10 +603,24 @@ GGR_DEV int coop_write_entry(CoopStage& E, const DecCtx& cx, const CoopEnt& e, u
     }
     if (!handed) {
       const u8* src = cx.in + e.body;
-      for (u32 j = 0; j < len; j++) E.buf[w.pos + j] = src[j];
+      for (u32 j = 0; j < len; j++) B[w.pos + j] = src[j];
     }
     w.pos += len;
     w.put1('"');
+  } else if (CE_CLASS(e) == DC_BYTES && !(e.flags & CF_PACKED) && e.vend - e.body >= GGR_COOP_LONG) {
+    // long bytes field: base64 by the whole warp when the list has room
+    const u32 k = wp_atomic_add(&E.n_long, 1u);
+    if (k < GGR_COOP_LONG_MAX) {
+      w.put1('"');
+      E.lsrc[k] = e.body;
+      E.ldst[k] = w.pos;
+      E.llen[k] = (e.vend - e.body) | 0x40000000u;
+      const u32 tail = (e.flags & CF_ARR_LAST) ? 2u : 1u;
+      B[endpos - tail] = '"';
+      if (e.flags & CF_ARR_LAST) B[endpos - 1] = ']';
+      return GST_OK;
+    }
+    st = coop_leaf_value(w, cx, e, f);
   } else if (CE_CLASS(e) == DC_STR && !(e.flags & (CF_PACKED | CF_TIMESTAMP))) {
     // string that needs escaping: text left to the whole warp when the list has room
     const u32 k = wp_atomic_add(&E.n_long, 1u);
@@ -549,8 +630,8 @@ GGR_DEV int coop_write_entry(CoopStage& E, const DecCtx& cx, const CoopEnt& e, u
       E.ldst[k] = w.pos;
       E.llen[k] = (e.vend - e.body) | 0x80000000u;
       const u32 tail = (e.flags & CF_ARR_LAST) ? 2u : 1u;
-      E.buf[endpos - tail] = '"';
-      if (e.flags & CF_ARR_LAST) E.buf[endpos - 1] = ']';
+      B[endpos - tail] = '"';
+      if (e.flags & CF_ARR_LAST) B[endpos - 1] = ']';
       return GST_OK;
     }
     st = coop_leaf_value(w, cx, e, f);
@@ -569,7 +650,8 @@ GGR_DEV bool coop_size_item(CoopShared& S, const DecCtx& cx, u32 root_msg, u32 s
   const u32 lane = wp_lane();
   *size = 0;
   *n_out = 0;
-  if (end > GGR_COOP_MAX_WIRE || root_msg >= 0xFFFFu) return false;
+  if (root_msg >= 0xFFFFu) return false;
+  const bool have_masks = end <= GGR_COOP_MAX_WIRE;  // larger items: strings are classified one by one
   WP_SYNC();  // persistent warps: nobody still reads the previous item's state
   if (lane == 0) {
     S.n_ent = 1;
@@ -599,7 +681,7 @@ GGR_DEV bool coop_size_item(CoopShared& S, const DecCtx& cx, u32 root_msg, u32 s
   }
   const u32 n = S.n_ent;
   // R2: plain-text masks, leaves bucketed by class
-  coop_plain_masks(S, cx.in, start, end);
+  if (have_masks) coop_plain_masks(S, cx.in, start, end);
   if (lane < DC_N) S.cls_cnt[lane] = 0;
   WP_SYNC();
   for (u32 i = lane; i < n; i += 32) {
@@ -623,7 +705,7 @@ GGR_DEV bool coop_size_item(CoopShared& S, const DecCtx& cx, u32 root_msg, u32 s
   WP_SYNC();
   // R3: leaf sizes, then messages bottom-up, then offsets top-down
   const u32 n_leaf = S.n_leaf;
-  for (u32 k = lane; k < n_leaf; k += 32) coop_size_leaf(S, cx, S.order[k], true);
+  for (u32 k = lane; k < n_leaf; k += 32) coop_size_leaf(S, cx, S.order[k], have_masks);
   WP_SYNC();
   if (S.bail) return false;
   {
@@ -631,7 +713,15 @@ GGR_DEV bool coop_size_item(CoopShared& S, const DecCtx& cx, u32 root_msg, u32 s
     for (u32 k = 0; k < nd; k++) {
       const u32 ei = S.dlist[k];
       bool ok;
-      const u32 js = coop_dirty_size(cx.in, S.ent[ei].body, S.ent[ei].vend, &ok);
+      const u32 sb = S.ent[ei].body, se = S.ent[ei].vend;
+      u32 js;
+      if (se - sb >= 256u && coop_plain_check(cx.in, sb, se)) {  // long and plain (no masks for large items)
+        js = se - sb;
+        ok = true;
+        if (lane == 0) S.ent[ei].flags |= CF_PLAIN;
+      } else {
+        js = coop_dirty_size(cx.in, sb, se, &ok);
+      }
       if (!ok) return false;  // malformed UTF-8: the per-thread kernels report it
       if (lane == 0) {
         const u32 total = S.ent[ei].size + js;
@@ -649,7 +739,6 @@ GGR_DEV bool coop_size_item(CoopShared& S, const DecCtx& cx, u32 root_msg, u32 s
     WP_SYNC();
   }
   *size = S.ent[0].size;
-  if (S.ent[0].size > GGR_COOP_STAGE) return false;  // the write pass stages the text in shared memory
   if (!save) return true;
   for (u32 d = 0; d <= maxd; d++) {
     for (u32 i = lane; i < n; i += 32)
@@ -664,15 +753,12 @@ GGR_DEV bool coop_size_item(CoopShared& S, const DecCtx& cx, u32 root_msg, u32 s
 }
 
 // Write pass of one item, all lanes: `tab` holds the n entries the size pass saved; the text goes
-// to dst[0, size).
+// to dst[0, size).  Items whose text fits the staging buffer are assembled there and copied out
+// in aligned chunks; larger ones (a few entries around a huge leaf) are written in place.
 GGR_DEV int coop_write_item(CoopStage& E, const DecCtx& cx, const U4* tab, u32 n, u8* dst, u32 size) {
   const u32 lane = wp_lane();
-#if defined(__CUDA_ARCH__)
-  const u32 pad = (u32)(reinterpret_cast<unsigned long long>(dst) & 15ull);
-#else
-  const u32 pad = (u32)((uintptr_t)dst & 15u);
-#endif
-  u8* out16 = dst - pad;
+  const bool staged = size <= GGR_COOP_STAGE;
+  const u32 pad = wp_align_pad(dst);
   WP_SYNC();  // persistent warps: the previous item has been copied out
   if (lane == 0) {
     E.n_long = 0;
@@ -686,19 +772,31 @@ GGR_DEV int coop_write_item(CoopStage& E, const DecCtx& cx, const U4* tab, u32 n
     e.off = b.x; e.parent = (u16)b.y; e.next = (u16)(b.y >> 16);
     e.fc_msg = (u16)b.z; e.gfield = (u16)(b.z >> 16);
     e.flags = (u16)b.w; e.depth = (u16)(b.w >> 16);
-    if (coop_write_entry(E, cx, e, pad) != GST_OK) E.bad = 1;
+    // two call sites so that the staged one keeps plain shared-memory stores
+    const int st = staged ? coop_write_entry(E, cx, e, E.buf + pad) : coop_write_entry(E, cx, e, dst);
+    if (st != GST_OK) E.bad = 1;
   }
   WP_SYNC();
   const u32 nl = E.n_long < GGR_COOP_LONG_MAX ? E.n_long : GGR_COOP_LONG_MAX;
-  for (u32 k = 0; k < nl; k++) {
-    const u8* src = cx.in + E.lsrc[k];
-    u8* d = E.buf + E.ldst[k];
-    const u32 len = E.llen[k];
-    if (len & 0x80000000u) coop_dirty_write(cx.in, E.lsrc[k], E.lsrc[k] + (len & 0x7FFFFFFFu), d);
-    else
-      for (u32 j = lane; j < len; j += 32) d[j] = src[j];
+  if (staged) {
+    for (u32 k = 0; k < nl; k++) {
+      u8* d = E.buf + pad + E.ldst[k];
+      const u32 len = E.llen[k] & 0x3FFFFFFFu;
+      if (E.llen[k] & 0x80000000u) coop_dirty_write(cx.in, E.lsrc[k], E.lsrc[k] + len, d);
+      else if (E.llen[k] & 0x40000000u) coop_base64(cx.in, E.lsrc[k], len, d);
+      else
+        for (u32 j = lane; j < len; j += 32) d[j] = cx.in[E.lsrc[k] + j];
+    }
+    WP_SYNC();
+    wp_copy_out(E.buf, dst - pad, pad, size);
+  } else {
+    for (u32 k = 0; k < nl; k++) {
+      u8* d = dst + E.ldst[k];
+      const u32 len = E.llen[k] & 0x3FFFFFFFu;
+      if (E.llen[k] & 0x80000000u) coop_dirty_write(cx.in, E.lsrc[k], E.lsrc[k] + len, d);
+      else if (E.llen[k] & 0x40000000u) coop_base64(cx.in, E.lsrc[k], len, d);
+      else coop_copy_words(cx.in, E.lsrc[k], d, len);
+    }
   }
-  WP_SYNC();
-  wp_copy_out(E.buf, out16, pad, size);
   return E.bad ? GST_INTERNAL : GST_OK;
 }

@@ -130,6 +130,7 @@ struct ggr_engine {
   Slot slots[GGR_MAX_SLOTS];
   int n_slots = 6;
   int64_t chunk_items = 8192;
+  uint64_t chunk_bytes = 32ull << 20;
   // per-kernel timing
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -443,7 +444,7 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
       u32* counters = (u32*)sc.pend.p;
       u32* big = counters + 16;
       if (!cuda_ok(e, cudaMemsetAsync(counters, 0, 64, st), "memset")) return GGR_ERR_CUDA;
-      k_route<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, in_off, e->min_wire, 8192u - 16u, big, counters, nullptr, nullptr, (u32*)sc.aux.p);
+      k_route<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, in_off, e->min_wire, 0x3FFFFF00u, big, counters, nullptr, nullptr, (u32*)sc.aux.p);
       ggr_launch_decode_coop_size(st, n, s->d_blob, n_msgs, msg_id, in, in_off, flags, (u32*)sc.size.p, (u32*)sc.aux.p, status,
                                   sc.ir.p, (u32*)sc.nn.p, e->sm_count, big, counters);
       if (prof) {
@@ -564,13 +565,35 @@ static int run_host(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, 
   cudaSetDevice(e->device);
   for (int i = 0; i < e->n_slots; i++)
     if (!slot_init(e, e->slots[i])) return GGR_ERR_CUDA;
+  // chunk boundaries: at most chunk_items items and about chunk_bytes of input each (large items
+  // must not make a chunk - and its staging buffers - huge)
   const int64_t CH = e->chunk_items;
-  const int64_t nchunks = (n + CH - 1) / CH;
   const uint64_t total_in = in_off[n] - in_off[0];
+  std::vector<int64_t> starts;
+  if (total_in <= e->chunk_bytes * (uint64_t)((n + CH - 1) / CH)) {
+    for (int64_t i = 0; i < n; i += CH) starts.push_back(i);  // item count alone decides
+  } else {
+    int64_t i = 0;
+    while (i < n) {
+      starts.push_back(i);
+      int64_t hi = i + CH < n ? i + CH : n;
+      // first item index in (i, hi] whose prefix exceeds the byte budget
+      const uint64_t lim = in_off[i] + e->chunk_bytes;
+      int64_t lo = i + 1;
+      while (lo < hi) {
+        int64_t mid = (lo + hi) / 2;
+        if (in_off[mid] > lim) hi = mid;
+        else lo = mid + 1;
+      }
+      i = lo;
+    }
+  }
+  starts.push_back(n);
+  const int64_t nchunks = (int64_t)starts.size() - 1;
   auto job = [&](int64_t c) {
     ChunkJob j;
-    j.i0 = c * CH;
-    j.nc = n - j.i0 < CH ? n - j.i0 : CH;
+    j.i0 = starts[c];
+    j.nc = starts[c + 1] - j.i0;
     j.base = in_off[j.i0];
     j.bytes = in_off[j.i0 + j.nc] - j.base;
     return j;

@@ -26,7 +26,7 @@ k_decode_coop_size(const u8* __restrict__ blob, long long n, u32 n_msgs, const i
     const i32 m = msg_id[item];
     bool ok = false;
     u32 sz = 0, ne = 0;
-    if (m >= 0 && (u32)m < n_msgs && b >= a && b - a <= (u64)GGR_COOP_MAX_WIRE - 16u) {
+    if (m >= 0 && (u32)m < n_msgs && b >= a && b - a <= 0x3FFFFF00ull) {
       cx.in = in + (a & ~15ull);
       const u32 s0 = (u32)(a & 15ull);
       ok = coop_size_item(S[warp], cx, (u32)m, s0, s0 + (u32)(b - a), tab + (size_t)item * COOP_TAB_U4, &ne, &sz);

@@ -195,3 +195,50 @@ def test_coop_decode_bench_shapes(hsim):
             w = blob[int(wl.rep_off[i]):int(wl.rep_off[i + 1])]
             handled += _check_coop_decode(hsim, names[int(wl.rep_msg[i])], w, i)
         assert handled == n, (kind, handled)
+
+
+def test_coop_decode_large_leaves(hsim):
+    """items larger than the staging buffer are written in place: long plain / escaped / non-ASCII strings
+    and long bytes fields (base64) by the whole warp"""
+    import benchgen
+    names = {}
+
+    def mi(name):
+        names[hsim.msg(name)] = name
+        return hsim.msg(name)
+
+    wl = benchgen.blob(3, mi)
+    blob = wl.rep_wire.tobytes()
+    for i in range(3):
+        w = blob[int(wl.rep_off[i]):int(wl.rep_off[i + 1])]
+        assert _check_coop_decode(hsim, names[int(wl.rep_msg[i])], w, i, i & 1)
+
+    def varint(n):
+        o = b""
+        while n >= 0x80:
+            o += bytes([n & 0x7F | 0x80])
+            n >>= 7
+        return o + bytes([n])
+
+    rng = random.Random(3)
+    for it in range(120):
+        ln = rng.choice([0, 1, 2, 3, 95, 96, 97, 98, 255, 256, 257, 1000, 8190, 9000, 20000])
+        data = bytes(rng.randrange(256) for _ in range(ln))
+        sl = rng.choice([0, 5, 95, 96, 255, 256, 300, 2000, 8100, 8300, 15000])
+        kind = rng.random()
+        if kind < 0.5:
+            name = bytes(rng.choice(b"abcdefghij KLMN") for _ in range(sl))
+        elif kind < 0.75:
+            name = bytearray(rng.choice(b"abcdefghij KLMN") for _ in range(sl))
+            for _ in range(max(1, sl // 50)):
+                if sl:
+                    name[rng.randrange(sl)] = rng.choice(b'"\\\n\t\x01')
+            name = bytes(name)
+        else:
+            name = "".join(rng.choice("abc \u00e9\u65e5\u20ac\U0001F600") for _ in range(sl // 2)).encode()
+        w = b""
+        if ln or rng.random() < 0.3:
+            w += b"\x0a" + varint(len(data)) + data
+        if name:
+            w += b"\x12" + varint(len(name)) + name
+        assert _check_coop_decode(hsim, "bench.Blob", w, it, it & 1), (ln, sl)
