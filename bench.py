@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--items", type=int, default=0, help="items per GPU per step (default: config size)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer measurement (default: min(steps, 5))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-serial", action="store_true", help="end-to-end: request call, then reply call (default: both in flight)")
     ap.add_argument("--one-stream", action="store_true", help="serialize request and reply side on one stream")
     args = ap.parse_args()
     if args.items == 0:
@@ -300,14 +301,28 @@ def main():
         h_req_out_off = torch.empty((n + 1) * 8, dtype=torch.uint8).pin_memory()
         h_req_st = torch.empty(n * 4, dtype=torch.uint8).pin_memory()
 
-    def step_host():
-        if have_req:
-            rc = L.ggr_encode_batch(eng.h, schema.h, n, h_req_msg.data_ptr(), h_req.data_ptr(), h_req_off.data_ptr(), h_req_out.data_ptr(),
-                                    req_cap, h_req_out_off.data_ptr(), h_req_st.data_ptr(), 0)
-            assert rc == 0, rc
+    def host_request():
+        rc = L.ggr_encode_batch(eng.h, schema.h, n, h_req_msg.data_ptr(), h_req.data_ptr(), h_req_off.data_ptr(), h_req_out.data_ptr(),
+                                req_cap, h_req_out_off.data_ptr(), h_req_st.data_ptr(), 0)
+        assert rc == 0, rc
+
+    def host_reply():
         rc = L.ggr_decode_batch(eng.h, schema.h, n, h_rep_msg.data_ptr(), h_rep.data_ptr(), h_rep_off.data_ptr(), h_rep_out.data_ptr(),
                                 rep_cap, h_rep_out_off.data_ptr(), h_rep_st.data_ptr(), 0)
         assert rc == 0, rc
+
+    def step_host():
+        # a server has request batches and reply batches in flight at the same time: the two calls
+        # are issued from two host threads (the C ABI takes one batch per direction concurrently)
+        if have_req and not args.e2e_serial:
+            t = threading.Thread(target=host_request)
+            t.start()
+            host_reply()
+            t.join()
+            return
+        if have_req:
+            host_request()
+        host_reply()
 
     step_host()
     barrier()
@@ -380,7 +395,8 @@ def main():
                    "avg_bytes": {"J_in": J_in / n, "W_out": W_out / n, "W_in": W_in / n, "J_out": J_out / n},
                    "l2": "inputs exceed L2 (%.0f MB read per step)" % ((J_in + W_in) / 1e6), "parallelism": "shard-by-index x%d, no collective" % world},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                "timing": "wall clock around the C-ABI host-buffer calls (pinned buffers), max over ranks"},
+                "timing": "wall clock around the C-ABI host-buffer calls (pinned buffers; request batch and reply batch %s), max over ranks"
+                          % ("one after the other" if args.e2e_serial else "in flight together from two host threads")},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

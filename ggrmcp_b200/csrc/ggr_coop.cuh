@@ -668,6 +668,9 @@ GGR_DEV bool coop_size_item(CoopShared& S, const DecCtx& cx, u32 root_msg, u32 s
     S.q_end = 1;
   }
   WP_SYNC();
+  // R2 first: the plain-text masks read the whole item with coalesced 16-byte loads, which also brings
+  // its lines into L1 for the byte-wise discovery below
+  if (have_masks) coop_plain_masks(S, cx.in, start, end);
   // R1: level by level
   u32 qb = 0;
   for (;;) {
@@ -680,8 +683,7 @@ GGR_DEV bool coop_size_item(CoopShared& S, const DecCtx& cx, u32 root_msg, u32 s
     qb = qe;
   }
   const u32 n = S.n_ent;
-  // R2: plain-text masks, leaves bucketed by class
-  if (have_masks) coop_plain_masks(S, cx.in, start, end);
+  // leaves bucketed by class
   if (lane < DC_N) S.cls_cnt[lane] = 0;
   WP_SYNC();
   for (u32 i = lane; i < n; i += 32) {
@@ -759,6 +761,7 @@ GGR_DEV int coop_write_item(CoopStage& E, const DecCtx& cx, const U4* tab, u32 n
   const u32 lane = wp_lane();
   const bool staged = size <= GGR_COOP_STAGE;
   const u32 pad = wp_align_pad(dst);
+  if (n) wp_prefetch(cx.in, tab[0].y);  // entry 0 is the root: vend = end of the item
   WP_SYNC();  // persistent warps: the previous item has been copied out
   if (lane == 0) {
     E.n_long = 0;

@@ -1019,6 +1019,7 @@ GGR_DEV void ce_unescape_coop(const u8* in, u32 src, u8* d, u32 dec_len) {
 GGR_DEV void ce_emit_item(CoopEmit& E, const u8* in, u32 end, const u8* ir, const u32* ioff, u32 n_nodes, u8* dst, u32 size) {
   const u32 lane = wp_lane();
   const u32 pad = wp_align_pad(dst);
+  wp_prefetch(in, end);
   WP_SYNC();  // persistent warps: the previous item has been copied out
   if (lane == 0) E.n = 0;
   WP_SYNC();

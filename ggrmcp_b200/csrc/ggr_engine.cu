@@ -13,6 +13,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -115,9 +116,10 @@ struct ggr_engine {
   ggr::WireOrder order = ggr::ORDER_FIELD_NUMBER;
   cudaStream_t stream = nullptr;
   std::string err;
-  uint64_t launches = 0;
+  std::atomic<uint64_t> launches{0};
   bool use_coop = true;  // GGR_COOP=0 disables the lock-step reply-side kernels (A/B runs)
-  std::mutex mu;
+  std::mutex mu;         // device-buffer entry points, profiling state
+  std::mutex mu_host[2];  // host-buffer entry points: a request batch and a reply batch may run concurrently
   // scratch (device): one set per direction for the device-buffer entry points, so that a request
   // batch and a reply batch can be in flight on two streams at the same time
   Scratch dev_sc[2];
@@ -127,7 +129,7 @@ struct ggr_engine {
   uint32_t min_json = 1024, min_wire = 640;
   // host-buffer entry points: the batch is cut into chunks that move through `n_slots` slots
   // (stream + staging + scratch each), so that H2D, kernels and D2H of different chunks overlap
-  Slot slots[GGR_MAX_SLOTS];
+  Slot slots[2][GGR_MAX_SLOTS];  // per direction
   int n_slots = 6;
   int64_t chunk_items = 8192;
   uint64_t chunk_bytes = 32ull << 20;
@@ -252,8 +254,8 @@ void ggr_engine_destroy(ggr_engine* e) {
   };
   free_scratch(e->dev_sc[0]);
   free_scratch(e->dev_sc[1]);
-  for (int i = 0; i < GGR_MAX_SLOTS; i++) {
-    Slot& sl = e->slots[i];
+  for (int i = 0; i < 2 * GGR_MAX_SLOTS; i++) {
+    Slot& sl = e->slots[i / GGR_MAX_SLOTS][i % GGR_MAX_SLOTS];
     if (sl.st) cudaStreamSynchronize(sl.st);
     free_scratch(sl.sc);
     DevBuf* bufs[] = {&sl.d_in, &sl.d_off, &sl.d_msg, &sl.d_out, &sl.d_out_off, &sl.d_status};
@@ -269,7 +271,7 @@ void ggr_engine_destroy(ggr_engine* e) {
 }
 
 const char* ggr_last_error(const ggr_engine* e) { return e ? e->err.c_str() : "null engine"; }
-uint64_t ggr_launch_count(const ggr_engine* e) { return e ? e->launches : 0; }
+uint64_t ggr_launch_count(const ggr_engine* e) { return e ? e->launches.load() : 0; }
 
 int ggr_schema_register(ggr_engine* e, const uint8_t* fds, size_t n, ggr_schema** out) {
   if (!e || !fds || !out) return GGR_ERR_INVALID_ARGUMENT;
@@ -561,10 +563,16 @@ static int run_host(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, 
     return GGR_SUCCESS;
   }
   if (!msg_id || !in || !in_off || !status || (!out && out_cap)) return GGR_ERR_INVALID_ARGUMENT;
-  std::lock_guard<std::mutex> g(e->mu);
+  // one batch per direction at a time; with the profiler on everything is serialised (its event
+  // list is shared)
+  const int dir = encode ? 0 : 1;
+  std::unique_lock<std::mutex> gp(e->mu, std::defer_lock);
+  if (e->profiling) gp.lock();
+  std::lock_guard<std::mutex> g(e->mu_host[dir]);
   cudaSetDevice(e->device);
+  Slot* const slots = e->slots[dir];
   for (int i = 0; i < e->n_slots; i++)
-    if (!slot_init(e, e->slots[i])) return GGR_ERR_CUDA;
+    if (!slot_init(e, slots[i])) return GGR_ERR_CUDA;
   // chunk boundaries: at most chunk_items items and about chunk_bytes of input each (large items
   // must not make a chunk - and its staging buffers - huge)
   const int64_t CH = e->chunk_items;
@@ -611,13 +619,13 @@ static int run_host(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, 
   while (retired < nchunks) {
     while (issued < nchunks && issued - retired < e->n_slots && rc_final == GGR_SUCCESS) {
       ChunkJob j = job(issued);
-      int rc = chunk_issue(e, s, e->slots[issued % e->n_slots], encode, j, msg_id, in, in_off, chunk_cap(j), out_off, status, flags, true);
+      int rc = chunk_issue(e, s, slots[issued % e->n_slots], encode, j, msg_id, in, in_off, chunk_cap(j), out_off, status, flags, true);
       if (rc != GGR_SUCCESS) rc_final = rc;
       else issued++;
     }
     if (retired == issued) break;  // nothing in flight (an issue failed)
     ChunkJob j = job(retired);
-    Slot& sl = e->slots[retired % e->n_slots];
+    Slot& sl = slots[retired % e->n_slots];
     if (!cuda_ok(e, cudaEventSynchronize(sl.ready), "sync")) return GGR_ERR_CUDA;
     uint64_t total = *sl.h_total;
     if (total > sl.out_cap && rc_final == GGR_SUCCESS) {
@@ -641,7 +649,7 @@ static int run_host(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, 
     retired++;
   }
   for (int i = 0; i < e->n_slots; i++)
-    if (!cuda_ok(e, cudaStreamSynchronize(e->slots[i].st), "sync")) return GGR_ERR_CUDA;
+    if (!cuda_ok(e, cudaStreamSynchronize(slots[i].st), "sync")) return GGR_ERR_CUDA;
   out_off[n] = produced;
   return rc_final;
 }

@@ -251,3 +251,14 @@ GGR_DEV void wp_copy_out(const u8* buf, u8* out16, u32 pad, u32 size) {
     }
   }
 }
+
+// all lanes: ask for the lines of p[0, len) in L1 (one prefetch per 128-byte line and lane); the
+// writers then read small pieces of the item with plain loads
+GGR_DEV void wp_prefetch(const u8* p, u32 len) {
+#if defined(__CUDA_ARCH__)
+  for (u32 o = wp_lane() * 128u; o < len; o += 32u * 128u) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + o));
+#else
+  (void)p;
+  (void)len;
+#endif
+}
