@@ -67,7 +67,7 @@ struct CoopEncT {
   u32 n_tok, n_q, n_node, q_end, n_leaf, max_depth, bail, cap;
 };
 typedef CoopEncT<1024, 512, 224> CoopEnc;        // tier 1: ~12 KB per warp
-typedef CoopEncT<4096, 2048, 768> CoopEncBig;    // tier 2: ~53 KB per warp (4 warps must fit 227 KB)
+typedef CoopEncT<2048, 1024, 512> CoopEncBig;   // tier 2: ~26 KB per warp (two blocks of four warps per SM)
 
 struct CeLut {
   u32 cls[256];  // CE_L* class bits

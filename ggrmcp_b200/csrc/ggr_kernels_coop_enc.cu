@@ -1,7 +1,7 @@
 // ggr_kernels_coop_enc.cu - lock-step request-side pass A (one warp per item); see ggr_coop_enc.cuh.
 //
 // Two tiers of the same code: tier 1 with small per-warp tables (about 12 KB of shared memory per
-// warp, high occupancy) over every item, tier 2 with large tables (about 48 KB per warp) over what
+// warp, high occupancy) over every item, tier 2 with large tables (about 26 KB per warp) over what
 // tier 1 left because a table overflowed.  What tier 2 leaves too - malformed or unusual input -
 // goes to the per-thread parser.
 #include "ggr_kernels.h"
@@ -109,8 +109,8 @@ void ggr_launch_encode_coop_parse(cudaStream_t st, int tier, long long n, const 
     k_encode_coop_parse<CoopEnc><<<nb, CE_WARPS * 32, ce_smem_bytes<CoopEnc>(), st>>>(
         blob, n, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending);
   } else {
-    // the list length lives on the device: one block per SM (shared memory), warps stride over the list
-    unsigned nb = (unsigned)sm_count;
+    // the list length lives on the device: two blocks per SM (shared memory), warps stride over the list
+    unsigned nb = (unsigned)sm_count * 2u;
     k_encode_coop_parse<CoopEncBig><<<nb, CE_WARPS * 32, ce_smem_bytes<CoopEncBig>(), st>>>(
         blob, n, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending);
   }

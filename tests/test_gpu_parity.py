@@ -180,3 +180,27 @@ def test_flat_and_blob_configs(engine, schema, oracle):
         b = wb.rep_wire[int(wb.rep_off[i]):int(wb.rep_off[i + 1])].tobytes()
         rc, oj, _ = oracle.decode("bench.Blob", b)
         assert rc == 0 and oj == js[int(joff[i]):int(joff[i + 1])].tobytes()
+
+
+@pytest.mark.gpu
+def test_request_and_reply_batches_in_flight_together(engine, schema, oracle):
+    """the host entry points take one batch per direction concurrently (bench.py's end-to-end run does
+    exactly this from two threads): results must be those of the calls made one after the other"""
+    import threading
+    import benchgen
+    n = 20000
+    wl = benchgen.nested(n, schema.message)
+    ref_req = engine.encode_batch(schema, wl.req_msg, wl.req_json, wl.req_off)
+    ref_rep = engine.decode_batch(schema, wl.rep_msg, wl.rep_wire, wl.rep_off)
+    for _ in range(3):
+        got = {}
+
+        def req():
+            got["req"] = engine.encode_batch(schema, wl.req_msg, wl.req_json, wl.req_off)
+
+        t = threading.Thread(target=req)
+        t.start()
+        got["rep"] = engine.decode_batch(schema, wl.rep_msg, wl.rep_wire, wl.rep_off)
+        t.join()
+        for a, b in ((got["req"], ref_req), (got["rep"], ref_rep)):
+            assert (a[2] == 0).all() and (a[1] == b[1]).all() and a[0].tobytes() == b[0].tobytes()
