@@ -99,6 +99,7 @@ struct DevBuf {
 
 struct Scratch {
   DevBuf ir, size, aux, sums, pend, ioff, nn;
+  DevBuf wtext, woff, wsize;  // result wrapping: protojson texts, their offsets, body sizes
 };
 #define GGR_MAX_SLOTS 8
 struct Slot {
@@ -123,6 +124,7 @@ struct ggr_engine {
   // scratch (device): one set per direction for the device-buffer entry points, so that a request
   // batch and a reply batch can be in flight on two streams at the same time
   Scratch dev_sc[2];
+  DevBuf w_in, w_off, w_msg, w_ids, w_ids_off, w_out, w_out_off, w_status;  // staging of ggr_decode_wrap_batch
   bool use_coop_enc = true;  // GGR_COOP_ENC=0 disables the lock-step request-side parser (A/B runs)
   // items smaller than this go straight to the per-thread kernels, which are cheaper for them
   // (GGR_LOCKSTEP_MIN_BYTES overrides both; 0 sends everything through the lock-step kernels)
@@ -248,12 +250,17 @@ void ggr_engine_destroy(ggr_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   auto free_scratch = [](Scratch& sc) {
-    DevBuf* bufs[] = {&sc.ir, &sc.size, &sc.aux, &sc.sums, &sc.pend, &sc.ioff, &sc.nn};
+    DevBuf* bufs[] = {&sc.ir, &sc.size, &sc.aux, &sc.sums, &sc.pend, &sc.ioff, &sc.nn, &sc.wtext, &sc.woff, &sc.wsize};
     for (DevBuf* b : bufs)
       if (b->p) cudaFree(b->p);
   };
   free_scratch(e->dev_sc[0]);
   free_scratch(e->dev_sc[1]);
+  {
+    DevBuf* wb[] = {&e->w_in, &e->w_off, &e->w_msg, &e->w_ids, &e->w_ids_off, &e->w_out, &e->w_out_off, &e->w_status};
+    for (DevBuf* b : wb)
+      if (b->p) cudaFree(b->p);
+  }
   for (int i = 0; i < 2 * GGR_MAX_SLOTS; i++) {
     Slot& sl = e->slots[i / GGR_MAX_SLOTS][i % GGR_MAX_SLOTS];
     if (sl.st) cudaStreamSynchronize(sl.st);
@@ -505,6 +512,28 @@ int ggr_decode_batch_dev(ggr_engine* e, const ggr_schema* s, int64_t n, const in
                  stream ? (cudaStream_t)stream : e->stream);
 }
 
+// Reply half + result wrapping on device buffers: decode into scratch texts, size the bodies, scan,
+// write them.
+static int run_wrap_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, int64_t n, const int32_t* msg_id, const uint8_t* in,
+                        const uint64_t* in_off, uint64_t in_bytes, const uint8_t* ids, const uint64_t* ids_off, uint8_t* out,
+                        uint64_t out_cap, uint64_t* out_off, int32_t* status, uint32_t flags, cudaStream_t st) {
+  if (n > 0 && (!ids || !ids_off)) return GGR_ERR_INVALID_ARGUMENT;
+  if (n == 0) return run_dev(e, s, sc, false, n, msg_id, in, in_off, in_bytes, out, out_cap, out_off, status, flags, st);
+  if (!ensure(e, sc.wtext, (size_t)out_cap + 64) || !ensure(e, sc.woff, (size_t)(n + 1) * 8) || !ensure(e, sc.wsize, (size_t)n * 4))
+    return GGR_ERR_CUDA;
+  int rc = run_dev(e, s, sc, false, n, msg_id, in, in_off, in_bytes, (uint8_t*)sc.wtext.p, out_cap, (uint64_t*)sc.woff.p, status, flags, st);
+  if (rc != GGR_SUCCESS) return rc;
+  const long long nb = (n + GGR_BLOCK - 1) / GGR_BLOCK;
+  ggr_launch_wrap_size(st, n, (const uint8_t*)sc.wtext.p, (const uint64_t*)sc.woff.p, status, ids_off, (u32*)sc.wsize.p, e->sm_count);
+  ggr_launch_block_sums(st, (unsigned)nb, n, (const u32*)sc.wsize.p, (u64*)sc.sums.p);
+  k_scan_blocks<<<1, 1024, 0, st>>>((u64*)sc.sums.p, nb, out_off + n);
+  ggr_launch_offsets(st, (unsigned)nb, n, (const u32*)sc.wsize.p, (const u64*)sc.sums.p, out_off);
+  ggr_launch_wrap_write(st, n, (const uint8_t*)sc.wtext.p, (const uint64_t*)sc.woff.p, status, ids, ids_off, (const u32*)sc.wsize.p, out,
+                        out_cap, out_off, e->sm_count);
+  e->launches += 5;
+  return cuda_ok(e, cudaGetLastError(), "kernel launch") ? GGR_SUCCESS : GGR_ERR_CUDA;
+}
+
 // Host-buffer entry points.  The batch is cut into chunks of `chunk_items`; chunk c runs on slot
 // c % n_slots (own stream, staging buffers and scratch): H2D of its inputs, the kernels, D2H of its
 // offsets / statuses / total, and - once the host knows where the chunk's bytes go in the packed
@@ -652,6 +681,59 @@ static int run_host(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, 
     if (!cuda_ok(e, cudaStreamSynchronize(slots[i].st), "sync")) return GGR_ERR_CUDA;
   out_off[n] = produced;
   return rc_final;
+}
+
+int ggr_decode_wrap_batch_dev(ggr_engine* e, const ggr_schema* s, int64_t n, const int32_t* msg_id, const uint8_t* in,
+                              const uint64_t* in_off, uint64_t in_bytes, const uint8_t* ids, const uint64_t* ids_off,
+                              uint8_t* out, uint64_t out_cap, uint64_t* out_off, int32_t* status, uint32_t flags, void* stream) {
+  if (!e) return GGR_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(e->mu);
+  return run_wrap_dev(e, s, e->dev_sc[1], n, msg_id, in, in_off, in_bytes, ids, ids_off, out, out_cap, out_off, status, flags,
+                      stream ? (cudaStream_t)stream : e->stream);
+}
+
+// Host buffers: one pass (not chunked): H2D, reply kernels, wrapping kernels, D2H.
+int ggr_decode_wrap_batch(ggr_engine* e, const ggr_schema* s, int64_t n, const int32_t* msg_id, const uint8_t* wire,
+                          const uint64_t* wire_off, const uint8_t* ids, const uint64_t* ids_off, uint8_t* out,
+                          uint64_t out_cap, uint64_t* out_off, int32_t* status, uint32_t flags) {
+  if (!e || !s || n < 0 || !out_off) return GGR_ERR_INVALID_ARGUMENT;
+  if (n == 0) {
+    out_off[0] = 0;
+    return GGR_SUCCESS;
+  }
+  if (!msg_id || !wire || !wire_off || !ids || !ids_off || !status || (!out && out_cap)) return GGR_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(e->mu);
+  cudaSetDevice(e->device);
+  const uint64_t base = wire_off[0], in_bytes = wire_off[n] - base, phase = base & 15ull;
+  const uint64_t ibase = ids_off[0], id_bytes = ids_off[n] - ibase;
+  if (!ensure(e, e->w_in, (size_t)(in_bytes + phase + 128)) || !ensure(e, e->w_off, (size_t)(n + 1) * 8) ||
+      !ensure(e, e->w_msg, (size_t)n * 4) || !ensure(e, e->w_ids, (size_t)id_bytes + 64) ||
+      !ensure(e, e->w_ids_off, (size_t)(n + 1) * 8) || !ensure(e, e->w_out, (size_t)out_cap + 64) ||
+      !ensure(e, e->w_out_off, (size_t)(n + 1) * 8) || !ensure(e, e->w_status, (size_t)n * 4))
+    return GGR_ERR_CUDA;
+  cudaStream_t st = e->stream;
+  u8* d_in = (u8*)e->w_in.p;
+  if (!cuda_ok(e, cudaMemcpyAsync(d_in + phase, wire + base, in_bytes, cudaMemcpyHostToDevice, st), "H2D payload") ||
+      !cuda_ok(e, cudaMemsetAsync(d_in + phase + in_bytes, 0, 64, st), "pad") ||
+      !cuda_ok(e, cudaMemcpyAsync(e->w_off.p, wire_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st), "H2D offsets") ||
+      !cuda_ok(e, cudaMemcpyAsync(e->w_msg.p, msg_id, (size_t)n * 4, cudaMemcpyHostToDevice, st), "H2D ids") ||
+      !cuda_ok(e, cudaMemcpyAsync(e->w_ids.p, ids + ibase, id_bytes, cudaMemcpyHostToDevice, st), "H2D id tokens") ||
+      !cuda_ok(e, cudaMemcpyAsync(e->w_ids_off.p, ids_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st), "H2D id offsets"))
+    return GGR_ERR_CUDA;
+  int rc = run_wrap_dev(e, s, e->dev_sc[1], n, (const int32_t*)e->w_msg.p, d_in + phase - base, (const uint64_t*)e->w_off.p, in_bytes,
+                        (const uint8_t*)e->w_ids.p - ibase, (const uint64_t*)e->w_ids_off.p, (uint8_t*)e->w_out.p, out_cap,
+                        (uint64_t*)e->w_out_off.p, (int32_t*)e->w_status.p, flags, st);
+  if (rc != GGR_SUCCESS) return rc;
+  if (!cuda_ok(e, cudaMemcpyAsync(out_off, e->w_out_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H offsets") ||
+      !cuda_ok(e, cudaMemcpyAsync(status, e->w_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st), "D2H status") ||
+      !cuda_ok(e, cudaStreamSynchronize(st), "sync"))
+    return GGR_ERR_CUDA;
+  const uint64_t total = out_off[n];
+  if (total > out_cap) return GGR_ERR_NO_SPACE;
+  if (total && (!cuda_ok(e, cudaMemcpyAsync(out, e->w_out.p, total, cudaMemcpyDeviceToHost, st), "D2H payload") ||
+                !cuda_ok(e, cudaStreamSynchronize(st), "sync")))
+    return GGR_ERR_CUDA;
+  return GGR_SUCCESS;
 }
 
 int ggr_encode_batch(ggr_engine* e, const ggr_schema* s, int64_t n, const int32_t* msg_id, const uint8_t* json,

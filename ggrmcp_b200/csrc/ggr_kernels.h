@@ -38,5 +38,12 @@ void ggr_launch_decode_coop_write(cudaStream_t st, long long n, const uint8_t* b
                                   const uint32_t* list, const uint32_t* list_n);
 size_t ggr_decode_coop_table_bytes(long long n);  // scratch the size kernel needs for the entry tables
 int ggr_decode_coop_init();
+void ggr_launch_wrap_size(cudaStream_t st, long long n, const uint8_t* text, const uint64_t* text_off, const int32_t* status,
+                          const uint64_t* ids_off, uint32_t* size, int sm_count);
+void ggr_launch_offsets(cudaStream_t st, unsigned nb, long long n, const uint32_t* size, const uint64_t* block_prefix,
+                        uint64_t* out_off);
+void ggr_launch_wrap_write(cudaStream_t st, long long n, const uint8_t* text, const uint64_t* text_off, int32_t* status,
+                           const uint8_t* ids, const uint64_t* ids_off, const uint32_t* size, uint8_t* out, uint64_t out_cap,
+                           const uint64_t* out_off, int sm_count);
 const void* ggr_kernel_encode_parse();  // for cudaFuncGetAttributes (is the sm_100a image loadable?)
 int ggr_decode_max_rec();

@@ -70,6 +70,8 @@ def _load():
     dev_sig = [vp, vp, C.c_int64, vp, vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp, C.c_uint32, vp]
     L.ggr_encode_batch_dev.argtypes = dev_sig
     L.ggr_decode_batch_dev.argtypes = dev_sig
+    L.ggr_decode_wrap_batch.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_uint64, vp, vp, C.c_uint32]
+    L.ggr_decode_wrap_batch_dev.argtypes = [vp, vp, C.c_int64, vp, vp, vp, C.c_uint64, vp, vp, vp, C.c_uint64, vp, vp, C.c_uint32, vp]
     L.ggr_synchronize.argtypes = [vp]
     L.ggr_profile_enable.argtypes = [vp, C.c_int]
     L.ggr_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
@@ -174,6 +176,27 @@ class Engine:
         """Protobuf wire bytes -> protojson text.  Returns (bytes, offsets[n+1], status[n])."""
         cap = out_cap if out_cap is not None else len(data) * 3 + 64 * len(msg_ids) + 64
         return self._host(_load().ggr_decode_batch, schema, msg_ids, data, off, flags, cap)
+
+    def decode_wrap_batch(self, schema, msg_ids, data, off, ids, ids_off, flags=0, out_cap=None):
+        """Protobuf wire bytes -> complete MCP tools/call result bodies (handler.go:265-270, 290-297).
+        ids / ids_off: the JSON text of every request id.  Returns (bytes, offsets[n+1], status[n])."""
+        n = len(msg_ids)
+        msg_ids = np.ascontiguousarray(msg_ids, dtype=np.int32)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        ids = np.ascontiguousarray(ids, dtype=np.uint8)
+        ids_off = np.ascontiguousarray(ids_off, dtype=np.uint64)
+        assert len(off) == n + 1 and len(ids_off) == n + 1
+        cap = int(out_cap if out_cap is not None else len(data) * 4 + len(ids) + 160 * n + 64)
+        out = np.empty(max(cap, 1), dtype=np.uint8)
+        out_off = np.zeros(n + 1, dtype=np.uint64)
+        status = np.zeros(max(n, 1), dtype=np.int32)
+        rc = _load().ggr_decode_wrap_batch(self.h, schema.h, n, msg_ids.ctypes.data, data.ctypes.data if len(data) else out.ctypes.data,
+                                           off.ctypes.data, ids.ctypes.data if len(ids) else out.ctypes.data, ids_off.ctypes.data,
+                                           out.ctypes.data, cap, out_off.ctypes.data, status.ctypes.data, flags)
+        if rc != 0:
+            self._err(rc, "ggr_decode_wrap_batch")
+        return out[: int(out_off[n])], out_off, status[:n]
 
     # ---- device-resident buffers (raw device pointers, e.g. torch tensors' data_ptr()) ----
     def encode_batch_dev(self, schema, n, msg_ids_ptr, in_ptr, in_off_ptr, in_bytes, out_ptr, out_cap, out_off_ptr,

@@ -134,6 +134,25 @@ int ggr_decode_batch_dev(ggr_engine* e, const ggr_schema* s, int64_t n, const in
                          uint64_t* out_off, int32_t* status, uint32_t flags, void* stream);
 int ggr_synchronize(ggr_engine* e);
 
+/*
+ * Reply half plus result wrapping (handler.go:265-270 ToolCallResult / TextContent and
+ * handler.go:290-297 writeJSONResponse): out[out_off[i] .. out_off[i+1]) is the complete HTTP body
+ *   {"jsonrpc":"2.0","result":{"content":[{"type":"text","text":"<protojson text, escaped as
+ *   encoding/json does with HTML escaping>"}]},"id":<id token>}\n
+ * for request id token ids[ids_off[i] .. ids_off[i+1]) (the JSON text of the id: 1, "abc", ...).
+ * Items whose reply does not decode get status[i] != 0 and an empty body: the caller formats the
+ * isError result from the status (the error wording is Go's).
+ * The _dev form takes device pointers and enqueues on `stream`; out_cap also bounds the
+ * intermediate protojson texts.
+ */
+int ggr_decode_wrap_batch(ggr_engine* e, const ggr_schema* s, int64_t n, const int32_t* msg_id, const uint8_t* wire,
+                          const uint64_t* wire_off, const uint8_t* ids, const uint64_t* ids_off, uint8_t* out,
+                          uint64_t out_cap, uint64_t* out_off, int32_t* status, uint32_t flags);
+int ggr_decode_wrap_batch_dev(ggr_engine* e, const ggr_schema* s, int64_t n, const int32_t* msg_id, const uint8_t* in,
+                              const uint64_t* in_off, uint64_t in_bytes, const uint8_t* ids, const uint64_t* ids_off,
+                              uint8_t* out, uint64_t out_cap, uint64_t* out_off, int32_t* status, uint32_t flags,
+                              void* stream);
+
 /* Per-kernel device timing (CUDA events recorded around every kernel the engine launches).
  * slots: 0 encode_parse, 1 encode_scan, 2 encode_emit, 3 decode_size, 4 decode_scan, 5 decode_write,
  *        6 decode_coop_size, 7 decode_coop_write (the warp-cooperative reply-side kernels),

@@ -26,8 +26,18 @@ def lib():
         if hasattr(L, "hs_decode"):
             L.hs_decode.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                     C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.hs_wrap.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32)]
         _lib = L
     return _lib
+
+
+def wrap(text, id_tok):
+    """MCP result body around a protojson text (host simulation of ggr_wrap.cuh)"""
+    cap = len(text) * 6 + len(id_tok) + 128
+    out = C.create_string_buffer(cap)
+    n = C.c_uint32()
+    rc = lib().hs_wrap(text, len(text), id_tok, len(id_tok), out, cap, C.byref(n))
+    return rc, out.raw[: n.value]
 
 
 class Schema:

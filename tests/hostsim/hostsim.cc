@@ -13,6 +13,7 @@
 #include "../../ggrmcp_b200/csrc/ggr_schema.h"
 #include "../../ggrmcp_b200/csrc/ggr_encode.cuh"
 #include "../../ggrmcp_b200/csrc/ggr_coop_enc.cuh"
+#include "../../ggrmcp_b200/csrc/ggr_wrap.cuh"
 #ifdef GGR_HAVE_DECODE
 #include "../../ggrmcp_b200/csrc/ggr_decode.cuh"
 #include "../../ggrmcp_b200/csrc/ggr_coop.cuh"
@@ -209,6 +210,52 @@ int hs_encode_coop(void* h, int msg, const uint8_t* json, uint32_t n, uint32_t i
                    uint32_t out_cap, uint32_t* out_n, int tier) {
   return tier ? hs_encode_coop_t<CoopEncBig>(h, msg, json, n, in_off, out_off, out, out_cap, out_n)
               : hs_encode_coop_t<CoopEnc>(h, msg, json, n, in_off, out_off, out, out_cap, out_n);
+}
+
+// Result wrapping (ggr_wrap.cuh) on 32 fibers: size pass, then write pass.  Returns 300 + n on a
+// fiber-warp error, 100 when the passes disagree, 101/102 when bytes outside the body were touched.
+struct WrapArgs {
+  const u8* t;
+  u32 n;
+  const u8* id;
+  u32 idn;
+  u32 size[32];
+  u8* out;
+};
+static void wrap_size_body(void* p, u32 lane) {
+  WrapArgs* a = (WrapArgs*)p;
+  a->size[lane] = wrap_size_item(a->t, a->n, a->idn);
+}
+static void wrap_write_body(void* p, u32 lane) {
+  WrapArgs* a = (WrapArgs*)p;
+  wrap_write_item(a->t, a->n, a->id, a->idn, a->out);
+}
+int hs_wrap(const uint8_t* text, uint32_t n, const uint8_t* id, uint32_t idn, uint8_t* out, uint32_t out_cap, uint32_t* out_n) {
+  std::vector<uint8_t> tb(n + 64, 0xEE);
+  memcpy(tb.data() + 8, text, n);
+  WrapArgs a;
+  a.t = tb.data() + 8;
+  a.n = n;
+  a.id = id;
+  a.idn = idn;
+  *out_n = 0;
+  int werr = hw_run_warp(wrap_size_body, &a);
+  if (werr) return 300 + werr;
+  for (int l = 1; l < 32; l++)
+    if (a.size[l] != a.size[0]) return 310;
+  const uint32_t size = a.size[0];
+  if (size > out_cap) return GST_NO_SPACE;
+  std::vector<uint8_t> ob(size + 64, 0xDD);
+  a.out = ob.data() + 16;
+  werr = hw_run_warp(wrap_write_body, &a);
+  if (werr) return 320 + werr;
+  for (uint32_t i = 0; i < 16; i++)
+    if (ob[i] != 0xDD) return 101;
+  for (uint32_t i = 16 + size; i < size + 64; i++)
+    if (ob[i] != 0xDD) return 102;
+  memcpy(out, ob.data() + 16, size);
+  *out_n = size;
+  return 0;
 }
 
 #ifdef GGR_HAVE_DECODE

@@ -204,3 +204,28 @@ def test_request_and_reply_batches_in_flight_together(engine, schema, oracle):
         t.join()
         for a, b in ((got["req"], ref_req), (got["rep"], ref_rep)):
             assert (a[2] == 0).all() and (a[1] == b[1]).all() and a[0].tobytes() == b[0].tobytes()
+
+
+def test_result_bodies(engine, schema, oracle):
+    """reply half + MCP result wrapping on the device against the oracle's orc_response"""
+    from ggrmcp_b200.engine import pack
+    rng = random.Random(12)
+    items = cases.random_decode_cases(40) + [(n, bytes.fromhex(w)) for n, w, _ in cases.K_REPLIES]
+    ids = [rng.choice([b"1", b'"req-42"', b"9007199254740993", b'"\\u00e9"']) for _ in items]
+    msg = np.array([schema.message(n) for n, _ in items], np.int32)
+    data, off = pack([w for _, w in items])
+    idb, ioff = pack(ids)
+    out, ooff, st = engine.decode_wrap_batch(schema, msg, data, off, idb, ioff)
+    ok = 0
+    for i, (n, w) in enumerate(items):
+        ost, body = oracle.response(n, w, ids[i])
+        got = bytes(out[int(ooff[i]):int(ooff[i + 1])])
+        if st[i] == 11 and ost == 0:
+            continue  # documented gap
+        assert (ost == 0) == (st[i] == 0), (n, w.hex()[:80], ost, st[i])
+        if ost == 0:
+            assert got == body, (n, w.hex()[:80], got[:200], body[:200])
+            ok += 1
+        else:
+            assert got == b""
+    assert ok > len(items) // 2

@@ -242,3 +242,38 @@ def test_coop_decode_large_leaves(hsim):
         if name:
             w += b"\x12" + varint(len(name)) + name
         assert _check_coop_decode(hsim, "bench.Blob", w, it, it & 1), (ln, sl)
+
+
+# ---- MCP result wrapping (ggr_wrap.cuh) on 32 fibers ---------------------------------------------
+def _go_json_string(t):
+    """encoding/json appendString, escapeHTML = true, for valid UTF-8"""
+    out = bytearray(b'"')
+    for ch in t.decode("utf-8"):
+        c = ord(ch)
+        if ch in '"\\':
+            out += b"\\" + ch.encode()
+        elif ch in "\n\r\t\b\f":
+            out += {"\n": b"\\n", "\r": b"\\r", "\t": b"\\t", "\b": b"\\b", "\f": b"\\f"}[ch]
+        elif c < 0x20 or ch in "<>&" or c in (0x2028, 0x2029):
+            out += b"\\u%04x" % c
+        else:
+            out += ch.encode("utf-8")
+    return bytes(out + b'"')
+
+
+def test_wrap_result_bodies(oracle):
+    import hostsim
+    rng = random.Random(4)
+    alpha = 'abc {}[]:,"\\<>&\n\t\x01\u00e9\u65e5\u20ac\U0001F600\u2028\u2029\u00a8\u0080 xyz0123456789'
+    for it in range(1500):
+        n = rng.choice([0, 1, 2, 7, 8, 9, 31, 32, 33, 255, 256, 257, 300, 1000])
+        t = "".join(rng.choice(alpha) for _ in range(n)).encode("utf-8")
+        idt = rng.choice([b"1", b'"abc"', b"123456789", b'"x-' + b"y" * 40 + b'"'])
+        rc, out = hostsim.wrap(t, idt)
+        assert rc == 0
+        assert out == b'{"jsonrpc":"2.0","result":{"content":[{"type":"text","text":' + _go_json_string(t) + b'}]},"id":' + idt + b"}\n"
+    # and the oracle's own body for a real reply (K-vector)
+    name, wire, js = cases.K_REPLIES[0]
+    st, body = oracle.response(name, bytes.fromhex(wire), b"7")
+    rc, out = hostsim.wrap(js, b"7")
+    assert st == 0 and rc == 0 and out == body
