@@ -337,6 +337,42 @@ def main():
     e2e_value = world * n * e2e_steps / float(t_e.item())
     # parity spot check of the host path result against the resident path
     assert bytes(h_rep_out.numpy()[:64]) == bytes(d_rep_out[:64].cpu().numpy())
+
+    # the same, with the reply side producing complete MCP result bodies instead of the
+    # bare protojson texts: reported next to e2e, not instead of it
+    e2e_bodies = None
+    if have_req and not args.e2e_serial:
+        ids = np.frombuffer(b"".join(b"%d" % (i % 100000) for i in range(n)), np.uint8)
+        ids_off = np.zeros(n + 1, np.uint64)
+        ids_off[1:] = np.cumsum([len(b"%d" % (i % 100000)) for i in range(n)])
+        h_ids, h_ids_off = pinned(ids), pinned(ids_off)
+        body_cap = int(rep_cap * 1.5 + 128 * n)
+        h_body = torch.empty(body_cap, dtype=torch.uint8).pin_memory()
+
+        def host_reply_bodies():
+            rc = L.ggr_decode_wrap_batch(eng.h, schema.h, n, h_rep_msg.data_ptr(), h_rep.data_ptr(), h_rep_off.data_ptr(),
+                                         h_ids.data_ptr(), h_ids_off.data_ptr(), h_body.data_ptr(), body_cap,
+                                         h_rep_out_off.data_ptr(), h_rep_st.data_ptr(), 0)
+            assert rc == 0, rc
+
+        def step_bodies():
+            t = threading.Thread(target=host_request)
+            t.start()
+            host_reply_bodies()
+            t.join()
+
+        step_bodies()
+        assert int(h_rep_st.view(torch.int32).ne(0).sum()) == 0
+        assert bytes(h_body.numpy()[:61]) == b'{"jsonrpc":"2.0","result":{"content":[{"type":"text","text":"'
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_bodies()
+        torch.cuda.synchronize()
+        t_b = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t_b, op=dist.ReduceOp.MAX)
+        e2e_bodies = world * n * e2e_steps / float(t_b.item())
     h2d = J_in + W_in + 2 * (n + 1) * 8 * (2 if have_req else 1) // 2 + n * 4 * (2 if have_req else 1)
     d2h = W_out + J_out + ((n + 1) * 8 + n * 4) * (2 if have_req else 1)
 
@@ -396,7 +432,8 @@ def main():
                    "l2": "inputs exceed L2 (%.0f MB read per step)" % ((J_in + W_in) / 1e6), "parallelism": "shard-by-index x%d, no collective" % world},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                 "timing": "wall clock around the C-ABI host-buffer calls (pinned buffers; request batch and reply batch %s), max over ranks"
-                          % ("one after the other" if args.e2e_serial else "in flight together from two host threads")},
+                          % ("one after the other" if args.e2e_serial else "in flight together from two host threads"),
+                "with_result_bodies": e2e_bodies},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

@@ -106,7 +106,7 @@ struct Slot {
   cudaStream_t st = nullptr;
   cudaEvent_t ready = nullptr;
   Scratch sc;
-  DevBuf d_in, d_off, d_msg, d_out, d_out_off, d_status;
+  DevBuf d_in, d_off, d_msg, d_out, d_out_off, d_status, d_ids, d_ids_off;
   uint64_t* h_total = nullptr;  // pinned: output bytes of the chunk in flight
   uint64_t out_cap = 0;         // capacity handed to the kernels for that chunk
 };
@@ -124,7 +124,6 @@ struct ggr_engine {
   // scratch (device): one set per direction for the device-buffer entry points, so that a request
   // batch and a reply batch can be in flight on two streams at the same time
   Scratch dev_sc[2];
-  DevBuf w_in, w_off, w_msg, w_ids, w_ids_off, w_out, w_out_off, w_status;  // staging of ggr_decode_wrap_batch
   bool use_coop_enc = true;  // GGR_COOP_ENC=0 disables the lock-step request-side parser (A/B runs)
   // items smaller than this go straight to the per-thread kernels, which are cheaper for them
   // (GGR_LOCKSTEP_MIN_BYTES overrides both; 0 sends everything through the lock-step kernels)
@@ -256,16 +255,12 @@ void ggr_engine_destroy(ggr_engine* e) {
   };
   free_scratch(e->dev_sc[0]);
   free_scratch(e->dev_sc[1]);
-  {
-    DevBuf* wb[] = {&e->w_in, &e->w_off, &e->w_msg, &e->w_ids, &e->w_ids_off, &e->w_out, &e->w_out_off, &e->w_status};
-    for (DevBuf* b : wb)
-      if (b->p) cudaFree(b->p);
-  }
+
   for (int i = 0; i < 2 * GGR_MAX_SLOTS; i++) {
     Slot& sl = e->slots[i / GGR_MAX_SLOTS][i % GGR_MAX_SLOTS];
     if (sl.st) cudaStreamSynchronize(sl.st);
     free_scratch(sl.sc);
-    DevBuf* bufs[] = {&sl.d_in, &sl.d_off, &sl.d_msg, &sl.d_out, &sl.d_out_off, &sl.d_status};
+    DevBuf* bufs[] = {&sl.d_in, &sl.d_off, &sl.d_msg, &sl.d_out, &sl.d_out_off, &sl.d_status, &sl.d_ids, &sl.d_ids_off};
     for (DevBuf* b : bufs)
       if (b->p) cudaFree(b->p);
     if (sl.h_total) cudaFreeHost(sl.h_total);
@@ -553,9 +548,10 @@ struct ChunkJob {
   uint64_t base, bytes;
 };
 
+// ids != nullptr: reply side with result wrapping (the id tokens of the chunk travel with it)
 static int chunk_issue(ggr_engine* e, const ggr_schema* s, Slot& sl, bool encode, const ChunkJob& j, const int32_t* msg_id,
                        const uint8_t* in, const uint64_t* in_off, uint64_t cap, uint64_t* out_off, int32_t* status, uint32_t flags,
-                       bool copy_inputs) {
+                       bool copy_inputs, const uint8_t* ids = nullptr, const uint64_t* ids_off = nullptr) {
   const uint64_t phase = j.base & 15ull;
   if (!ensure(e, sl.d_in, (size_t)(j.bytes + phase + 128)) || !ensure(e, sl.d_off, (size_t)(j.nc + 1) * 8) ||
       !ensure(e, sl.d_msg, (size_t)j.nc * 4) || !ensure(e, sl.d_out, (size_t)cap + 64) ||
@@ -571,10 +567,23 @@ static int chunk_issue(ggr_engine* e, const ggr_schema* s, Slot& sl, bool encode
         !cuda_ok(e, cudaMemcpyAsync(sl.d_msg.p, msg_id + j.i0, (size_t)j.nc * 4, cudaMemcpyHostToDevice, st), "H2D ids"))
       return GGR_ERR_CUDA;
   }
+  uint64_t ibase = 0;
+  if (ids) {
+    ibase = ids_off[j.i0];
+    const uint64_t id_bytes = ids_off[j.i0 + j.nc] - ibase;
+    if (!ensure(e, sl.d_ids, (size_t)id_bytes + 64) || !ensure(e, sl.d_ids_off, (size_t)(j.nc + 1) * 8)) return GGR_ERR_CUDA;
+    if (copy_inputs &&
+        (!cuda_ok(e, cudaMemcpyAsync(sl.d_ids.p, ids + ibase, id_bytes, cudaMemcpyHostToDevice, st), "H2D id tokens") ||
+         !cuda_ok(e, cudaMemcpyAsync(sl.d_ids_off.p, ids_off + j.i0, (size_t)(j.nc + 1) * 8, cudaMemcpyHostToDevice, st), "H2D id offsets")))
+      return GGR_ERR_CUDA;
+  }
   // offsets are shipped as given: the kernels address the payload as d_in - (base - phase) + offset
   const u8* d_in_virtual = d_in + phase - j.base;
-  int rc = run_dev(e, s, sl.sc, encode, j.nc, (const int32_t*)sl.d_msg.p, d_in_virtual, (const uint64_t*)sl.d_off.p, j.bytes,
-                   (uint8_t*)sl.d_out.p, cap, (uint64_t*)sl.d_out_off.p, (int32_t*)sl.d_status.p, flags, st);
+  int rc = ids ? run_wrap_dev(e, s, sl.sc, j.nc, (const int32_t*)sl.d_msg.p, d_in_virtual, (const uint64_t*)sl.d_off.p, j.bytes,
+                              (const uint8_t*)sl.d_ids.p - ibase, (const uint64_t*)sl.d_ids_off.p, (uint8_t*)sl.d_out.p, cap,
+                              (uint64_t*)sl.d_out_off.p, (int32_t*)sl.d_status.p, flags, st)
+               : run_dev(e, s, sl.sc, encode, j.nc, (const int32_t*)sl.d_msg.p, d_in_virtual, (const uint64_t*)sl.d_off.p, j.bytes,
+                         (uint8_t*)sl.d_out.p, cap, (uint64_t*)sl.d_out_off.p, (int32_t*)sl.d_status.p, flags, st);
   if (rc != GGR_SUCCESS) return rc;
   if (!cuda_ok(e, cudaMemcpyAsync(out_off + j.i0, sl.d_out_off.p, (size_t)j.nc * 8, cudaMemcpyDeviceToHost, st), "D2H offsets") ||
       !cuda_ok(e, cudaMemcpyAsync(sl.h_total, (const uint64_t*)sl.d_out_off.p + j.nc, 8, cudaMemcpyDeviceToHost, st), "D2H total") ||
@@ -585,13 +594,14 @@ static int chunk_issue(ggr_engine* e, const ggr_schema* s, Slot& sl, bool encode
 }
 
 static int run_host(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, const int32_t* msg_id, const uint8_t* in,
-                    const uint64_t* in_off, uint8_t* out, uint64_t out_cap, uint64_t* out_off, int32_t* status, uint32_t flags) {
+                    const uint64_t* in_off, uint8_t* out, uint64_t out_cap, uint64_t* out_off, int32_t* status, uint32_t flags,
+                    const uint8_t* ids = nullptr, const uint64_t* ids_off = nullptr) {
   if (!e || !s || n < 0 || !out_off) return GGR_ERR_INVALID_ARGUMENT;
   if (n == 0) {
     out_off[0] = 0;
     return GGR_SUCCESS;
   }
-  if (!msg_id || !in || !in_off || !status || (!out && out_cap)) return GGR_ERR_INVALID_ARGUMENT;
+  if (!msg_id || !in || !in_off || !status || (!out && out_cap) || (ids != nullptr) != (ids_off != nullptr)) return GGR_ERR_INVALID_ARGUMENT;
   // one batch per direction at a time; with the profiler on everything is serialised (its event
   // list is shared)
   const int dir = encode ? 0 : 1;
@@ -648,7 +658,7 @@ static int run_host(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, 
   while (retired < nchunks) {
     while (issued < nchunks && issued - retired < e->n_slots && rc_final == GGR_SUCCESS) {
       ChunkJob j = job(issued);
-      int rc = chunk_issue(e, s, slots[issued % e->n_slots], encode, j, msg_id, in, in_off, chunk_cap(j), out_off, status, flags, true);
+      int rc = chunk_issue(e, s, slots[issued % e->n_slots], encode, j, msg_id, in, in_off, chunk_cap(j), out_off, status, flags, true, ids, ids_off);
       if (rc != GGR_SUCCESS) rc_final = rc;
       else issued++;
     }
@@ -659,7 +669,7 @@ static int run_host(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, 
     uint64_t total = *sl.h_total;
     if (total > sl.out_cap && rc_final == GGR_SUCCESS) {
       // rare: the chunk's output outgrew its share; its inputs are still on the device
-      int rc = chunk_issue(e, s, sl, encode, j, msg_id, in, in_off, total, out_off, status, flags, false);
+      int rc = chunk_issue(e, s, sl, encode, j, msg_id, in, in_off, total, out_off, status, flags, false, ids, ids_off);
       if (rc != GGR_SUCCESS) rc_final = rc;
       else if (!cuda_ok(e, cudaEventSynchronize(sl.ready), "sync")) return GGR_ERR_CUDA;
       total = *sl.h_total;
@@ -692,48 +702,12 @@ int ggr_decode_wrap_batch_dev(ggr_engine* e, const ggr_schema* s, int64_t n, con
                       stream ? (cudaStream_t)stream : e->stream);
 }
 
-// Host buffers: one pass (not chunked): H2D, reply kernels, wrapping kernels, D2H.
+// Host buffers: the chunked pipeline of the reply side, each chunk followed by the wrapping kernels.
 int ggr_decode_wrap_batch(ggr_engine* e, const ggr_schema* s, int64_t n, const int32_t* msg_id, const uint8_t* wire,
                           const uint64_t* wire_off, const uint8_t* ids, const uint64_t* ids_off, uint8_t* out,
                           uint64_t out_cap, uint64_t* out_off, int32_t* status, uint32_t flags) {
-  if (!e || !s || n < 0 || !out_off) return GGR_ERR_INVALID_ARGUMENT;
-  if (n == 0) {
-    out_off[0] = 0;
-    return GGR_SUCCESS;
-  }
-  if (!msg_id || !wire || !wire_off || !ids || !ids_off || !status || (!out && out_cap)) return GGR_ERR_INVALID_ARGUMENT;
-  std::lock_guard<std::mutex> g(e->mu);
-  cudaSetDevice(e->device);
-  const uint64_t base = wire_off[0], in_bytes = wire_off[n] - base, phase = base & 15ull;
-  const uint64_t ibase = ids_off[0], id_bytes = ids_off[n] - ibase;
-  if (!ensure(e, e->w_in, (size_t)(in_bytes + phase + 128)) || !ensure(e, e->w_off, (size_t)(n + 1) * 8) ||
-      !ensure(e, e->w_msg, (size_t)n * 4) || !ensure(e, e->w_ids, (size_t)id_bytes + 64) ||
-      !ensure(e, e->w_ids_off, (size_t)(n + 1) * 8) || !ensure(e, e->w_out, (size_t)out_cap + 64) ||
-      !ensure(e, e->w_out_off, (size_t)(n + 1) * 8) || !ensure(e, e->w_status, (size_t)n * 4))
-    return GGR_ERR_CUDA;
-  cudaStream_t st = e->stream;
-  u8* d_in = (u8*)e->w_in.p;
-  if (!cuda_ok(e, cudaMemcpyAsync(d_in + phase, wire + base, in_bytes, cudaMemcpyHostToDevice, st), "H2D payload") ||
-      !cuda_ok(e, cudaMemsetAsync(d_in + phase + in_bytes, 0, 64, st), "pad") ||
-      !cuda_ok(e, cudaMemcpyAsync(e->w_off.p, wire_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st), "H2D offsets") ||
-      !cuda_ok(e, cudaMemcpyAsync(e->w_msg.p, msg_id, (size_t)n * 4, cudaMemcpyHostToDevice, st), "H2D ids") ||
-      !cuda_ok(e, cudaMemcpyAsync(e->w_ids.p, ids + ibase, id_bytes, cudaMemcpyHostToDevice, st), "H2D id tokens") ||
-      !cuda_ok(e, cudaMemcpyAsync(e->w_ids_off.p, ids_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st), "H2D id offsets"))
-    return GGR_ERR_CUDA;
-  int rc = run_wrap_dev(e, s, e->dev_sc[1], n, (const int32_t*)e->w_msg.p, d_in + phase - base, (const uint64_t*)e->w_off.p, in_bytes,
-                        (const uint8_t*)e->w_ids.p - ibase, (const uint64_t*)e->w_ids_off.p, (uint8_t*)e->w_out.p, out_cap,
-                        (uint64_t*)e->w_out_off.p, (int32_t*)e->w_status.p, flags, st);
-  if (rc != GGR_SUCCESS) return rc;
-  if (!cuda_ok(e, cudaMemcpyAsync(out_off, e->w_out_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H offsets") ||
-      !cuda_ok(e, cudaMemcpyAsync(status, e->w_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st), "D2H status") ||
-      !cuda_ok(e, cudaStreamSynchronize(st), "sync"))
-    return GGR_ERR_CUDA;
-  const uint64_t total = out_off[n];
-  if (total > out_cap) return GGR_ERR_NO_SPACE;
-  if (total && (!cuda_ok(e, cudaMemcpyAsync(out, e->w_out.p, total, cudaMemcpyDeviceToHost, st), "D2H payload") ||
-                !cuda_ok(e, cudaStreamSynchronize(st), "sync")))
-    return GGR_ERR_CUDA;
-  return GGR_SUCCESS;
+  if (n > 0 && (!ids || !ids_off)) return GGR_ERR_INVALID_ARGUMENT;
+  return run_host(e, s, false, n, msg_id, wire, wire_off, out, out_cap, out_off, status, flags, ids, ids_off);
 }
 
 int ggr_encode_batch(ggr_engine* e, const ggr_schema* s, int64_t n, const int32_t* msg_id, const uint8_t* json,
