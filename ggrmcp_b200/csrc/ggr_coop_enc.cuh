@@ -65,6 +65,8 @@ struct CoopEncT {
   u32 cls_cnt[CC_N], cls_cur[CC_N];
   u32 dep_beg[CE_MAX_DEPTH + 2], dep_cur[CE_MAX_DEPTH + 2];  // containers bucketed by depth (in `queue`)
   u32 n_tok, n_q, n_node, q_end, n_leaf, max_depth, bail, cap;
+  // envelope mode: brackets nested deeper than the validators allow; what the envelope walk found
+  u32 deep, env, env_method, env_msg, env_args_tok, env_id_pos, env_id_len;
 };
 typedef CoopEncT<1024, 512, 224> CoopEnc;        // tier 1: ~12 KB per warp
 typedef CoopEncT<2048, 1024, 512> CoopEncBig;   // tier 2: ~26 KB per warp (two blocks of four warps per SM)
@@ -290,6 +292,7 @@ GGR_DEV void ce_match(SH& S) {
     // level of an opening bracket: depth after it; of a closing bracket: depth before it
     const i32 lvl = depth + (i32)wp_popc(OM & le) - (i32)wp_popc(CM & lt);
     const bool bad = (op || cl) && (lvl < 1 || lvl >= 32);
+    if (op && lvl > 10) S.deep = 1;  // envelope mode: validateDepth (pkg/mcp/validation.go:163-184) might refuse
     const u32 m = WP_MATCH_ANY((op || cl) ? (u32)lvl : 0x10000u + lane);
     if (bad) S.bail = 1;
     if (cl && !bad) {
@@ -626,6 +629,140 @@ GGR_DEV void ce_walk_map(SH& S, const EncCtx& cx, u32 ni) {
   wp_atomic_max(&S.max_depth, depth + 2);
 }
 
+// ---- request envelope: {"jsonrpc":"2.0","id":..,"method":"tools/call",
+// "params":{"name":"<tool>","arguments":{..}}} ----
+// plain string token (no escapes, valid UTF-8) equal to a literal
+template <class SH>
+GGR_DEV bool ce_tok_is(const SH& S, const u8* in, u32 tk, const char* lit, u32 n) {
+  const u32 k = TK_AUX(tk);
+  if (S.qslow[k] != S.qslow[k + 1] || S.qesc[k] != S.qesc[k + 1]) return false;
+  const u32 pos = TK_POS(tk);
+  if ((u32)S.qpos[k + 1] - pos - 1u != n) return false;
+  for (u32 j = 0; j < n; j++)
+    if (in[pos + 1u + j] != (u8)lit[j]) return false;
+  return true;
+}
+// One lane.  Handles exactly the bodies for which handler.go:83-95,215-231 + pkg/mcp/validation.go
+// accept the request AND json.Marshal(arguments) cannot change what protojson sees (together with
+// the checks in the walker and the leaf phase): every key once, exact-case names, id a plain ASCII
+// string or an integer of at most 15 digits, nesting within validateDepth's limit.  Everything else
+// sets bail: the caller reports the item as unsupported, never a different answer.
+template <class SH>
+GGR_DEV void ce_envelope(SH& S, const EncCtx& cx) {
+  const u8* in = cx.in;
+  const u32 n_tok = S.n_tok;
+  S.env_args_tok = CE_NIL;
+  if (S.deep || TK_KIND(S.tok[0]) != TK_LBRACE || TK_AUX(S.tok[0]) != n_tok - 1u) { S.bail = 1; return; }
+  const u32 close = n_tok - 1u;
+  u32 seen = 0, t = 1;
+  bool first = true, have_name = false;
+  while (t != close) {
+    if (!first) {
+      if (TK_KIND(S.tok[t]) != TK_COMMA) { S.bail = 1; return; }
+      t++;
+    }
+    first = false;
+    if (t + 2u >= close) { S.bail = 1; return; }
+    const u32 kt = S.tok[t];
+    if (TK_KIND(kt) != TK_STR || TK_KIND(S.tok[t + 1]) != TK_COLON) { S.bail = 1; return; }
+    const u32 vt = S.tok[t + 2];
+    const u32 vk = TK_KIND(vt);
+    u32 which;
+    if (ce_tok_is(S, in, kt, "jsonrpc", 7)) which = 0;
+    else if (ce_tok_is(S, in, kt, "id", 2)) which = 1;
+    else if (ce_tok_is(S, in, kt, "method", 6)) which = 2;
+    else if (ce_tok_is(S, in, kt, "params", 6)) which = 3;
+    else { S.bail = 1; return; }
+    if (seen & (1u << which)) { S.bail = 1; return; }
+    seen |= 1u << which;
+    if (which == 0) {
+      if (vk != TK_STR || !ce_tok_is(S, in, vt, "2.0", 3)) { S.bail = 1; return; }
+      t += 3;
+    } else if (which == 2) {
+      if (vk != TK_STR || !ce_tok_is(S, in, vt, "tools/call", 10)) { S.bail = 1; return; }
+      t += 3;
+    } else if (which == 1) {
+      const u32 pos = TK_POS(vt);
+      if (vk == TK_STR) {  // RequestID re-marshals the string: plain ASCII without HTML characters stays as it is
+        const u32 k = TK_AUX(vt);
+        if (S.qslow[k] != S.qslow[k + 1] || S.qesc[k] != S.qesc[k + 1]) { S.bail = 1; return; }
+        const u32 q1 = S.qpos[k + 1];
+        for (u32 j = pos + 1u; j < q1; j++) {
+          const u32 c = in[j];
+          if (c >= 0x80u || c == '<' || c == '>' || c == '&') { S.bail = 1; return; }
+        }
+        S.env_id_pos = pos;
+        S.env_id_len = q1 - pos + 1u;
+      } else if (vk == TK_SCALAR) {  // a number goes through float64: integers of at most 15 digits survive
+        u32 j = pos, digits = 0;
+        if (in[j] == '-') j++;
+        const u32 d0 = j;
+        while (j < cx.end && (u32)(in[j] - '0') < 10u) { j++; digits++; }
+        const u32 c = j < cx.end ? in[j] : 0u;
+        if (digits == 0 || digits > 15u || (digits > 1u && in[d0] == '0') || !(ggr_is_ws(c) || c == ',' || c == '}')) { S.bail = 1; return; }
+        S.env_id_pos = pos;
+        S.env_id_len = j - pos;
+      } else {
+        S.bail = 1;
+        return;
+      }
+      t += 3;
+    } else {  // params
+      if (vk != TK_LBRACE) { S.bail = 1; return; }
+      const u32 pclose = TK_AUX(vt);
+      u32 u = t + 3, pseen = 0;
+      bool pfirst = true;
+      while (u != pclose) {
+        if (!pfirst) {
+          if (TK_KIND(S.tok[u]) != TK_COMMA) { S.bail = 1; return; }
+          u++;
+        }
+        pfirst = false;
+        if (u + 2u >= pclose) { S.bail = 1; return; }
+        const u32 pk = S.tok[u];
+        if (TK_KIND(pk) != TK_STR || TK_KIND(S.tok[u + 1]) != TK_COLON) { S.bail = 1; return; }
+        const u32 pv = S.tok[u + 2];
+        if (ce_tok_is(S, in, pk, "name", 4)) {
+          if (pseen & 1u) { S.bail = 1; return; }
+          pseen |= 1u;
+          const u32 k = TK_AUX(pv);
+          if (TK_KIND(pv) != TK_STR || S.qslow[k] != S.qslow[k + 1] || S.qesc[k] != S.qesc[k + 1]) { S.bail = 1; return; }
+          const u32 p0 = TK_POS(pv), q1 = S.qpos[k + 1], len = q1 - p0 - 1u;
+          if (len == 0 || len > 128u) { S.bail = 1; return; }
+          for (u32 j = p0 + 1u; j < q1; j++) {  // isValidToolName (validation.go:227-232)
+            const u32 c = in[j];
+            if (!((c - 'a') < 26u || (c - 'A') < 26u || (c - '0') < 10u || c == '_' || c == '.')) { S.bail = 1; return; }
+          }
+          KeyInfo ki;
+          ce_key_info_plain(in, p0, q1, &ki);
+          const U4 tt = ggr_ld16(cx.T.tools);
+          i32 m;
+          if (!hash_lookup(cx.T, tt.x, tt.y, ki, in, p0, cx.end, &m)) { S.bail = 1; return; }
+          const u32 msg = ggr_u16(cx.T, tt.z + (u32)m);
+          if (msg == 0xFFFFu) { S.bail = 1; return; }  // streaming method
+          S.env_method = (u32)m;
+          S.env_msg = msg;
+          have_name = true;
+          u += 3;
+        } else if (ce_tok_is(S, in, pk, "arguments", 9)) {
+          if (pseen & 2u) { S.bail = 1; return; }
+          pseen |= 2u;
+          if (TK_KIND(pv) != TK_LBRACE) { S.bail = 1; return; }
+          S.env_args_tok = u + 2u;
+          u = TK_AUX(pv) + 1u;
+        } else {
+          S.bail = 1;
+          return;
+        }
+        if (u > pclose) { S.bail = 1; return; }
+      }
+      t = pclose + 1u;
+    }
+    if (t > close) { S.bail = 1; return; }
+  }
+  if (seen != 0xFu || !have_name) S.bail = 1;
+}
+
 GGR_DEV u32 ce_link(u32 x) { return x == CE_NIL ? GGR_NIL : x; }
 
 // T4, one lane: finish leaf node `ni` (IR node + size into its parent).
@@ -679,6 +816,18 @@ GGR_DEV void ce_leaf(SH& S, EncCtx& cx, u32 ni) {
   }
   Leaf l;
   bool done = false;
+  if (S.env && TK_KIND(tk) == TK_SCALAR) {
+    // json.Marshal(arguments) re-prints numbers from float64: only plain integers of at most 15 digits are
+    // guaranteed to come out as they went in
+    u32 j = TK_POS(tk), digits = 0;
+    const u32 c0 = cx.in[j];
+    if (c0 == '-' || (c0 - '0') < 10u) {
+      if (c0 == '-') j++;
+      while (j < cx.end && (u32)(cx.in[j] - '0') < 10u) { j++; digits++; }
+      const u32 c = j < cx.end ? cx.in[j] : 0u;
+      if (digits == 0 || digits > 15u || c == '.' || c == 'e' || c == 'E') { S.bail = 1; return; }
+    }
+  }
   if (nd.cls == CC_STR && TK_KIND(tk) == TK_STR) {
     // the tokenizer validated UTF-8 and counted simple escapes and the bytes that need the full
     // scanner (control characters, \u, bad escapes): without the latter the string is valid and its
@@ -758,19 +907,23 @@ GGR_DEV void ce_place_children(SH& S, u32 ni) {
 // false leaves it to the per-thread parser.
 template <class SH>
 GGR_DEV bool ce_parse_item(SH& S, const CeLut& lut, const Tables& T, u32 root_msg, const u8* in, u32 start, u32 end, u8* ir,
-                           u32* ioff, u32 ir_cap, EncResult* res) {
+                           u32* ioff, u32 ir_cap, EncResult* res, bool envelope = false) {
   const u32 lane = wp_lane();
   res->size = 0;
   res->first = GGR_NIL;
   res->n_nodes = 0;
+  res->method = 0;
+  res->id_pos = res->id_len = 0;
   if (end > CE_MAX_INPUT || ir_cap == 0) return false;
-  if (end == start) return true;  // reflection.go:354: "" skips protojson
+  if (end == start) return !envelope;  // reflection.go:354: "" skips protojson (an empty body is no request)
   WP_SYNC();  // persistent warps: nobody still reads the previous item's state
   if (lane == 0) {
     S.bail = 0;
     S.n_node = 0;
     S.q_end = 0;
     S.max_depth = 0;
+    S.deep = 0;
+    S.env = envelope ? 1u : 0u;
     S.cap = ir_cap < SH::MAX_NODE ? ir_cap : SH::MAX_NODE;
   }
   WP_SYNC();
@@ -789,8 +942,21 @@ GGR_DEV bool ce_parse_item(SH& S, const CeLut& lut, const Tables& T, u32 root_ms
   cx.ir_cap = ir_cap;
   cx.n_nodes = 0;
   cx.ioff = ioff;
+  u32 root_tok = 0;
+  if (envelope) {  // the message is the `arguments` object of the request, its type comes from the tool name
+    if (lane == 0) ce_envelope(S, cx);
+    WP_SYNC();
+    if (S.bail) return false;
+    res->method = S.env_method;
+    res->id_pos = S.env_id_pos;
+    res->id_len = S.env_id_len;
+    root_msg = S.env_msg;
+    root_tok = S.env_args_tok;
+    if (root_tok == CE_NIL) return true;  // no arguments: the empty message
+    WP_SYNC();
+  }
   if (lane == 0) {
-    u32 r0 = ce_new_node(S, 0, CE_NIL, 0, 0, CC_MSG, 0);
+    u32 r0 = ce_new_node(S, root_tok, CE_NIL, 0, 0, CC_MSG, 0);
     S.node[r0].msg = (u16)root_msg;
     S.queue[0] = (u16)r0;
     S.q_end = 1;

@@ -555,6 +555,8 @@ struct EncResult {
   u32 size;   // wire bytes of the item
   u32 first;  // first top-level node (GGR_NIL when the message is empty)
   u32 n_nodes;  // lock-step parser: IR nodes written (with offsets, for the lock-step emitter); 0 otherwise
+  // envelope mode (request bodies): method index, position and length of the id token in the body
+  u32 method, id_pos, id_len;
 };
 
 // `active` is false for lanes that have no item (they only take part in the convergence votes);

@@ -285,10 +285,12 @@ struct Tables {
   const u8* hash;
   const u8* u16s;
   const u8* pool;
+  const u8* tools;  // GgrToolsTrailer
 };
 GGR_DEV Tables ggr_tables(const u8* blob) {
   U4 h0 = ggr_ld16(blob), h1 = ggr_ld16(blob + 16), h2 = ggr_ld16(blob + 32), h3 = ggr_ld16(blob + 48);
   Tables t;
+  t.tools = blob + h0.y - 16;  // total_bytes - 16
   t.msgs = blob + h0.w;    // msgs_off
   t.fields = blob + h1.y;  // fields_off
   t.enums = blob + h1.w;   // enums_off

@@ -474,6 +474,17 @@ bool compile_schema(const uint8_t* fds, size_t n, WireOrder order, CompiledSchem
     out->tool_index[M.tool_name] = (int32_t)out->methods.size();
     out->methods.push_back(M);
   }
+  // ---- tool table for the request envelope: tool name -> method index (same key tables as the
+  // message keys), u16[tool_methods_first + m] = input message of method m (0xFFFF: streaming) ----
+  uint32_t tool_hash_first = 0, tool_hash_mask = 0, tool_methods_first = 0;
+  {
+    std::vector<std::pair<std::string, int32_t>> items;
+    for (size_t m = 0; m < out->methods.size(); m++) items.push_back({out->methods[m].tool_name, (int32_t)m});
+    tool_hash_first = B.add_table(items, &tool_hash_mask);
+    tool_methods_first = (uint32_t)B.u16.size();
+    for (auto& M : out->methods)
+      B.u16.push_back((M.client_streaming || M.server_streaming || M.input_msg >= 0xFFFF) ? (uint16_t)0xFFFF : (uint16_t)M.input_msg);
+  }
   // ---- serialize ----
   GgrSchemaHdr h;
   memset(&h, 0, sizeof h);
@@ -497,6 +508,10 @@ bool compile_schema(const uint8_t* fds, size_t n, WireOrder order, CompiledSchem
   h.pool_bytes = (uint32_t)B.pool.size();
   h.pool_off = append_section(o, B.pool.data(), B.pool.size());
   while (o.size() % 16) o.push_back(0);
+  {  // trailer (the last 16 bytes of the blob): GgrToolsTrailer
+    GgrToolsTrailer tt = {tool_hash_first, tool_hash_mask, tool_methods_first, (uint32_t)out->methods.size()};
+    append_section(o, &tt, sizeof tt);
+  }
   h.total_bytes = (uint32_t)o.size();
   memcpy(o.data(), &h, sizeof h);
   return true;

@@ -44,6 +44,12 @@ struct GgrSchemaHdr {  // 64 bytes
   uint32_t pool_bytes, pool_off;   // byte pool: key text, `"jsonName":` text, enum names
 };
 
+struct GgrToolsTrailer {  // the last 16 bytes of the blob (blob + total_bytes - 16)
+  uint32_t hash_first, hash_mask;  // tool name -> method index (GgrHashEnt table)
+  uint32_t methods_first;          // u16[methods_first + m] = input message of method m, 0xFFFF = streaming
+  uint32_t n_methods;
+};
+
 struct GgrMsg {  // 32 bytes
   uint32_t field_first;   // index of the first GgrField
   uint16_t n_fields;

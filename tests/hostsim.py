@@ -26,6 +26,8 @@ def lib():
         if hasattr(L, "hs_decode"):
             L.hs_decode.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                     C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.hs_request_coop.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint32,
+                                      C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int]
         L.hs_wrap.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32)]
         _lib = L
     return _lib
@@ -93,3 +95,16 @@ Schema.encode_coop = _encode_coop
 def load_schema(order=0):
     with open(os.path.join(ROOT, "tests", "golden", "schemas.binpb"), "rb") as fh:
         return Schema(fh.read(), order)
+
+
+def _request_coop(self, body, in_off=0, out_off=0, tier=0):
+    """request envelope through the lock-step parser: (rc, wire, method index, id token)"""
+    cap = len(body) + 64
+    out = C.create_string_buffer(cap)
+    n = C.c_uint32()
+    env = (C.c_uint32 * 3)()
+    rc = lib().hs_request_coop(self.h, body, len(body), in_off, out_off, out, cap, C.byref(n), env, tier)
+    return rc, out.raw[: n.value], int(env[0]), body[env[1]: env[1] + env[2]]
+
+
+Schema.request_coop = _request_coop

@@ -105,6 +105,7 @@ struct CoopEncArgs {
   u32 ir_cap;
   EncResult res[32];
   bool ok[32];
+  bool envelope = false;
   // pass B
   CoopEmit* E;
   u8* dst;
@@ -112,7 +113,7 @@ struct CoopEncArgs {
 template <class SH>
 static void coop_enc_body(void* p, u32 lane) {
   CoopEncArgs<SH>* a = (CoopEncArgs<SH>*)p;
-  a->ok[lane] = ce_parse_item(*a->S, *a->lut, a->T, a->msg, a->in, a->start, a->end, a->ir, a->ioff, a->ir_cap, &a->res[lane]);
+  a->ok[lane] = ce_parse_item(*a->S, *a->lut, a->T, a->msg, a->in, a->start, a->end, a->ir, a->ioff, a->ir_cap, &a->res[lane], a->envelope);
 }
 template <class SH>
 static void coop_emit_body(void* p, u32 lane) {
@@ -121,7 +122,7 @@ static void coop_emit_body(void* p, u32 lane) {
 }
 template <class SH>
 static int hs_encode_coop_t(void* h, int msg, const uint8_t* json, uint32_t n, uint32_t in_off, uint32_t out_off, uint8_t* out,
-                            uint32_t out_cap, uint32_t* out_n) {
+                            uint32_t out_cap, uint32_t* out_n, uint32_t* env_out = nullptr) {
   HsSchema* s = (HsSchema*)h;
   static CeLut lut;
   static bool lut_ok = false;
@@ -149,6 +150,7 @@ static int hs_encode_coop_t(void* h, int msg, const uint8_t* json, uint32_t n, u
   std::vector<u32> ioff(ir_cap + 8, 0xDEADBEEFu);
   a.ioff = ioff.data();
   a.ir_cap = ir_cap;
+  a.envelope = env_out != nullptr;
   int werr = hw_run_warp(coop_enc_body<SH>, &a);
   *out_n = 0;
   if (werr) {
@@ -165,6 +167,11 @@ static int hs_encode_coop_t(void* h, int msg, const uint8_t* json, uint32_t n, u
     return 200;
   }
   EncResult res = a.res[0];
+  if (env_out) {
+    env_out[0] = res.method;
+    env_out[1] = res.id_pos - in_off;
+    env_out[2] = res.id_len;
+  }
   int st = GST_OK;
   if (res.size > out_cap) {
     free(ir);
@@ -256,6 +263,13 @@ int hs_wrap(const uint8_t* text, uint32_t n, const uint8_t* id, uint32_t idn, ui
   memcpy(out, ob.data() + 16, size);
   *out_n = size;
   return 0;
+}
+
+// request envelope mode: body -> wire bytes of the arguments, env[3] = method index, id position, id length
+int hs_request_coop(void* h, const uint8_t* body, uint32_t n, uint32_t in_off, uint32_t out_off, uint8_t* out, uint32_t out_cap,
+                    uint32_t* out_n, uint32_t* env, int tier) {
+  return tier ? hs_encode_coop_t<CoopEncBig>(h, 0, body, n, in_off, out_off, out, out_cap, out_n, env)
+              : hs_encode_coop_t<CoopEnc>(h, 0, body, n, in_off, out_off, out, out_cap, out_n, env);
 }
 
 #ifdef GGR_HAVE_DECODE

@@ -277,3 +277,62 @@ def test_wrap_result_bodies(oracle):
     st, body = oracle.response(name, bytes.fromhex(wire), b"7")
     rc, out = hostsim.wrap(js, b"7")
     assert st == 0 and rc == 0 and out == body
+
+
+# ---- request envelope through the lock-step parser -----------------------------
+def _tool_by_input(oracle):
+    return {m["input"]: (i, m["tool"]) for i, m in reversed(list(enumerate(oracle.methods())))}
+
+
+def _check_request(oracle, hsim, body, i=0):
+    """handled (rc 0) => the oracle accepts the request and wire, method and id are identical;
+    anything else must come back as 'unsupported' (200), never as a different answer"""
+    r = oracle.request(body)
+    rc, wire, method, idt = hsim.request_coop(body, i % 16, (i * 3) % 16, i & 1)
+    assert rc in (0, 200), (body[:200], rc)
+    if rc == 0:
+        assert r["kind"] == 0 and wire == r["wire"] and method == r["method"] and idt == r["id"], (body[:300], r["kind"], r["status"])
+    return rc == 0
+
+
+def test_request_envelope_random(oracle, hsim):
+    by_input = _tool_by_input(oracle)
+    rng = random.Random(31)
+    handled = total = 0
+    for i, (name, js) in enumerate(cases.random_encode_cases(60, seed0=12000)):
+        k = oracle.msg(name)
+        if k not in by_input:
+            continue
+        tool = by_input[k][1].encode()
+        idt = rng.choice([b"1", b"42", b'"abc"', b"-7", b"123456789012345", b"1.0", b"1e3", b'"a<b"', b'"\\u00e9"',
+                          b"9007199254740993", b"null", b"0", b'"x y"'])
+        parts = {"jsonrpc": b'"jsonrpc":"2.0"', "id": b'"id":' + idt, "method": b'"method":"tools/call"',
+                 "params": b'"params":{"name":"' + tool + b'","arguments":' + js + b"}"}
+        keys = list(parts)
+        rng.shuffle(keys)
+        body = b"{" + b",".join(parts[k2] for k2 in keys) + b"}"
+        handled += _check_request(oracle, hsim, body, i)
+        total += 1
+        for variant in (body.replace(b'"jsonrpc":"2.0"', b'"jsonrpc":"1.0"'), body.replace(b'"method":"tools/call"', b'"method":"tools/list"'),
+                        body.replace(b'"arguments":', b'"Arguments":'), body.replace(b",", b" ,\n"), body[:-1] + b',"extra":1}',
+                        body.replace(b'"jsonrpc"', b'"JSONRPC"'), body.replace(b'"params":{', b'"params":{"name":"x",'),
+                        b'{"jsonrpc":"2.0","id":1,"method":"tools/call","params":{"name":"' + tool + b'"}}')[i % 8:i % 8 + 1]:
+            _check_request(oracle, hsim, variant, i)
+    assert total > 100 and handled > total // 4
+
+
+def test_request_envelope_vectors_and_bench_shapes(oracle, hsim):
+    import benchgen
+    from test_oracle import K_BODIES
+    for k, (body, args, wire, rmsg, rwire, pj, http) in enumerate(K_BODIES):
+        _check_request(oracle, hsim, body, k)
+    by_input = _tool_by_input(oracle)
+    wl = benchgen.nested(120, oracle.msg)
+    blob = wl.req_json.tobytes()
+    for i in range(120):
+        js = blob[int(wl.req_off[i]):int(wl.req_off[i + 1])]
+        tool = by_input[int(wl.req_msg[i])][1].encode()
+        body = b'{"jsonrpc":"2.0","id":%d,"method":"tools/call","params":{"name":"%s","arguments":%s}}' % (i, tool, js)
+        r = oracle.request(body)
+        rc, w, method, idt = hsim.request_coop(body, i % 16, (i * 3) % 16, 1)
+        assert rc == 0 and r["kind"] == 0 and w == r["wire"] and method == r["method"] and idt == r["id"]
