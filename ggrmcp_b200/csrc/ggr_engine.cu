@@ -83,6 +83,17 @@ __global__ void __launch_bounds__(256) k_route(long long n, const u64* __restric
   if (is_small && small) small[bs + __popc(ms & lt)] = (u32)i;
 }
 
+// status / size of the items of a list (request bodies the lock-step parser cannot take)
+__global__ void __launch_bounds__(256) k_mark(const u32* __restrict__ list, const u32* __restrict__ list_n, i32* __restrict__ status,
+                                              u32* __restrict__ size, u32* __restrict__ first, i32 value) {
+  const u32 i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= *list_n) return;
+  const u32 item = list[i];
+  status[item] = value;
+  size[item] = 0;
+  first[item] = 0xFFFFFu;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -396,9 +407,9 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
       // router: small (and oversized) items straight to the per-thread parser
       k_route<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, in_off, e->min_json, 65000u - 16u, big, counters, pend2, counters + 8, nullptr);
       ggr_launch_encode_coop_parse(st, 0, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
-                                   (u32*)sc.aux.p, status, (u32*)sc.ioff.p, (u32*)sc.nn.p, big, counters, pend1, counters + 4, e->sm_count);
+                                   (u32*)sc.aux.p, status, (u32*)sc.ioff.p, (u32*)sc.nn.p, big, counters, pend1, counters + 4, e->sm_count, nullptr, nullptr, -1);
       ggr_launch_encode_coop_parse(st, 1, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
-                                   (u32*)sc.aux.p, status, (u32*)sc.ioff.p, (u32*)sc.nn.p, pend1, counters + 4, pend2, counters + 8, e->sm_count);
+                                   (u32*)sc.aux.p, status, (u32*)sc.ioff.p, (u32*)sc.nn.p, pend1, counters + 4, pend2, counters + 8, e->sm_count, nullptr, nullptr, -1);
       if (prof) prof_mark(e, st, &c0);
       ggr_launch_encode_parse(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
                               (u32*)sc.aux.p, status, (u64*)sc.sums.p, pend2, counters + 8);
@@ -505,6 +516,45 @@ int ggr_decode_batch_dev(ggr_engine* e, const ggr_schema* s, int64_t n, const in
   std::lock_guard<std::mutex> g(e->mu);
   return run_dev(e, s, e->dev_sc[1], false, n, msg_id, in, in_off, in_bytes, out, out_cap, out_off, status, flags,
                  stream ? (cudaStream_t)stream : e->stream);
+}
+
+// Request bodies on device buffers: the lock-step parser in envelope mode (both
+// table tiers), nothing behind it - what it does not take is reported as GGR_ST_UNSUPPORTED.
+static int run_request_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, int64_t n, const uint8_t* in, const uint64_t* in_off,
+                           uint64_t in_bytes, uint8_t* out, uint64_t out_cap, uint64_t* out_off, int32_t* method, uint32_t* id_span,
+                           int32_t* status, cudaStream_t st) {
+  if (!e || !s || n < 0 || (n > 0 && (!in || !in_off || !out_off || !status || !method || !id_span))) return GGR_ERR_INVALID_ARGUMENT;
+  if (((uintptr_t)in & 15) || ((uintptr_t)out & 7)) return GGR_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(e->device);
+  if (n == 0) return cuda_ok(e, cudaMemsetAsync(out_off, 0, sizeof(uint64_t), st), "memset") ? GGR_SUCCESS : GGR_ERR_CUDA;
+  const long long nb = (n + GGR_BLOCK - 1) / GGR_BLOCK;
+  if (!ensure(e, sc.size, (size_t)n * 4) || !ensure(e, sc.aux, (size_t)n * 4) || !ensure(e, sc.sums, (size_t)nb * 8) ||
+      !ensure(e, sc.ir, (size_t)in_bytes * 8 + (size_t)n * 128 + 256) || !ensure(e, sc.pend, (size_t)n * 12 + 64) ||
+      !ensure(e, sc.ioff, (size_t)in_bytes * 2 + (size_t)n * 32 + 64) || !ensure(e, sc.nn, (size_t)n * 4))
+    return GGR_ERR_CUDA;
+  u32* counters = (u32*)sc.pend.p;
+  u32* big = counters + 16;
+  u32* pend1 = big + n;
+  u32* rest = pend1 + n;
+  if (!cuda_ok(e, cudaMemsetAsync(counters, 0, 64, st), "memset") || !cuda_ok(e, cudaMemsetAsync(sc.nn.p, 0, (size_t)n * 4, st), "memset"))
+    return GGR_ERR_CUDA;
+  const u32 n_msgs = (u32)s->cs.msg_names.size();
+  // bodies above the parser's input limit cannot be taken
+  k_route<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, in_off, 0u, 65000u - 16u, big, counters, rest, counters + 8, nullptr);
+  ggr_launch_encode_coop_parse(st, 0, n, s->d_blob, n_msgs, nullptr, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p, (u32*)sc.aux.p, status,
+                               (u32*)sc.ioff.p, (u32*)sc.nn.p, big, counters, pend1, counters + 4, e->sm_count, method, id_span, -1);
+  ggr_launch_encode_coop_parse(st, 1, n, s->d_blob, n_msgs, nullptr, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p, (u32*)sc.aux.p, status,
+                               (u32*)sc.ioff.p, (u32*)sc.nn.p, pend1, counters + 4, rest, counters + 8, e->sm_count, method, id_span,
+                               GGR_ST_UNSUPPORTED);
+  k_mark<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rest, counters + 8, status, (u32*)sc.size.p, (u32*)sc.aux.p, GGR_ST_UNSUPPORTED);
+  ggr_launch_block_sums(st, (unsigned)nb, n, (const u32*)sc.size.p, (u64*)sc.sums.p);
+  k_scan_blocks<<<1, 1024, 0, st>>>((u64*)sc.sums.p, nb, out_off + n);
+  ggr_launch_encode_emit(st, (unsigned)nb, n, in, in_off, (const u8*)sc.ir.p, (const u32*)sc.size.p, (const u32*)sc.aux.p, status,
+                         (const u64*)sc.sums.p, out, out_cap, out_off, (const u32*)sc.nn.p);
+  ggr_launch_encode_coop_emit(st, n, in, in_off, (const u8*)sc.ir.p, (const u32*)sc.ioff.p, (const u32*)sc.nn.p, (const u32*)sc.size.p,
+                              status, out, out_off, e->sm_count, big, counters);
+  e->launches += 8;
+  return cuda_ok(e, cudaGetLastError(), "kernel launch") ? GGR_SUCCESS : GGR_ERR_CUDA;
 }
 
 // Reply half + result wrapping on device buffers: decode into scratch texts, size the bodies, scan,
@@ -691,6 +741,57 @@ static int run_host(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, 
     if (!cuda_ok(e, cudaStreamSynchronize(slots[i].st), "sync")) return GGR_ERR_CUDA;
   out_off[n] = produced;
   return rc_final;
+}
+
+int ggr_request_batch_dev(ggr_engine* e, const ggr_schema* s, int64_t n, const uint8_t* in, const uint64_t* in_off,
+                          uint64_t in_bytes, uint8_t* out, uint64_t out_cap, uint64_t* out_off, int32_t* method, uint32_t* id_span,
+                          int32_t* status, void* stream) {
+  if (!e) return GGR_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(e->mu);
+  return run_request_dev(e, s, e->dev_sc[0], n, in, in_off, in_bytes, out, out_cap, out_off, method, id_span, status,
+                         stream ? (cudaStream_t)stream : e->stream);
+}
+
+// Host buffers, one pass: H2D, parser in envelope mode + emitters, D2H.
+int ggr_request_batch(ggr_engine* e, const ggr_schema* s, int64_t n, const uint8_t* body, const uint64_t* body_off, uint8_t* out,
+                      uint64_t out_cap, uint64_t* out_off, int32_t* method, uint32_t* id_span, int32_t* status) {
+  if (!e || !s || n < 0 || !out_off) return GGR_ERR_INVALID_ARGUMENT;
+  if (n == 0) {
+    out_off[0] = 0;
+    return GGR_SUCCESS;
+  }
+  if (!body || !body_off || !status || !method || !id_span || (!out && out_cap)) return GGR_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(e->mu_host[0]);
+  std::lock_guard<std::mutex> g2(e->mu);
+  cudaSetDevice(e->device);
+  if (!slot_init(e, e->slots[0][0])) return GGR_ERR_CUDA;
+  Slot& sl = e->slots[0][0];
+  const uint64_t base = body_off[0], in_bytes = body_off[n] - base, phase = base & 15ull;
+  if (!ensure(e, sl.d_in, (size_t)(in_bytes + phase + 128)) || !ensure(e, sl.d_off, (size_t)(n + 1) * 8) ||
+      !ensure(e, sl.d_out, (size_t)out_cap + 64) || !ensure(e, sl.d_out_off, (size_t)(n + 1) * 8) ||
+      !ensure(e, sl.d_status, (size_t)n * 4) || !ensure(e, sl.d_msg, (size_t)n * 4) || !ensure(e, sl.d_ids_off, (size_t)n * 8))
+    return GGR_ERR_CUDA;
+  cudaStream_t st = sl.st;
+  u8* d_in = (u8*)sl.d_in.p;
+  if (!cuda_ok(e, cudaMemcpyAsync(d_in + phase, body + base, in_bytes, cudaMemcpyHostToDevice, st), "H2D payload") ||
+      !cuda_ok(e, cudaMemsetAsync(d_in + phase + in_bytes, 0, 64, st), "pad") ||
+      !cuda_ok(e, cudaMemcpyAsync(sl.d_off.p, body_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st), "H2D offsets"))
+    return GGR_ERR_CUDA;
+  int rc = run_request_dev(e, s, sl.sc, n, d_in + phase - base, (const uint64_t*)sl.d_off.p, in_bytes, (uint8_t*)sl.d_out.p, out_cap,
+                           (uint64_t*)sl.d_out_off.p, (int32_t*)sl.d_msg.p, (uint32_t*)sl.d_ids_off.p, (int32_t*)sl.d_status.p, st);
+  if (rc != GGR_SUCCESS) return rc;
+  if (!cuda_ok(e, cudaMemcpyAsync(out_off, sl.d_out_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H offsets") ||
+      !cuda_ok(e, cudaMemcpyAsync(status, sl.d_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st), "D2H status") ||
+      !cuda_ok(e, cudaMemcpyAsync(method, sl.d_msg.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st), "D2H methods") ||
+      !cuda_ok(e, cudaMemcpyAsync(id_span, sl.d_ids_off.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st), "D2H id spans") ||
+      !cuda_ok(e, cudaStreamSynchronize(st), "sync"))
+    return GGR_ERR_CUDA;
+  const uint64_t total = out_off[n];
+  if (total > out_cap) return GGR_ERR_NO_SPACE;
+  if (total && (!cuda_ok(e, cudaMemcpyAsync(out, sl.d_out.p, total, cudaMemcpyDeviceToHost, st), "D2H payload") ||
+                !cuda_ok(e, cudaStreamSynchronize(st), "sync")))
+    return GGR_ERR_CUDA;
+  return GGR_SUCCESS;
 }
 
 int ggr_decode_wrap_batch_dev(ggr_engine* e, const ggr_schema* s, int64_t n, const int32_t* msg_id, const uint8_t* in,

@@ -17,7 +17,7 @@ k_encode_coop_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const 
                     const u8* __restrict__ in, const u64* __restrict__ in_off, u8* __restrict__ ir, u32* __restrict__ size,
                     u32* __restrict__ first, i32* __restrict__ status, u32* __restrict__ ioff, u32* __restrict__ nnodes,
                     const u32* __restrict__ list, const u32* __restrict__ list_n, u32* __restrict__ pending,
-                    u32* __restrict__ n_pending) {
+                    u32* __restrict__ n_pending, i32* __restrict__ method, u32* __restrict__ id_span, i32 final_status) {
   extern __shared__ __align__(16) unsigned char smem[];
   CeLut& lut = *reinterpret_cast<CeLut*>(smem);
   SH* S = reinterpret_cast<SH*>(smem + ((sizeof(CeLut) + 15) & ~(size_t)15));
@@ -31,7 +31,9 @@ k_encode_coop_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const 
   for (long long slot = (long long)blockIdx.x * CE_WARPS + warp; slot < total; slot += (long long)gridDim.x * CE_WARPS) {
     const long long item = list ? (long long)list[slot] : slot;
     const u64 a = in_off[item], b = in_off[item + 1];
-    const i32 m = msg_id[item];
+    // envelope mode (method != nullptr): the item is a whole request body, its message type comes from the tool name
+    const bool envelope = method != nullptr;
+    const i32 m = envelope ? 0 : msg_id[item];
     bool ok = false;
     EncResult res;
     res.size = 0;
@@ -42,7 +44,7 @@ k_encode_coop_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const 
       const u32 cap = (u32)((((b - a0) >> 1) + 8ull * (u64)(item + 1)) - node_off);
       const u8* base = in + (a & ~15ull);
       const u32 s0 = (u32)(a & 15ull);
-      ok = ce_parse_item(S[warp], lut, T, (u32)m, base, s0, s0 + (u32)(b - a), ir + node_off * 16, ioff + node_off, cap, &res);
+      ok = ce_parse_item(S[warp], lut, T, (u32)m, base, s0, s0 + (u32)(b - a), ir + node_off * 16, ioff + node_off, cap, &res, envelope);
     }
     if (lane == 0) {
       if (ok) {
@@ -50,10 +52,17 @@ k_encode_coop_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const 
         first[item] = res.first;
         status[item] = GST_OK;
         nnodes[item] = res.size <= CE_STAGE ? res.n_nodes : 0;  // larger items: per-thread emitter
+        if (envelope) {
+          method[item] = (i32)res.method;
+          id_span[2 * item] = res.id_pos - (u32)(a & 15ull);
+          id_span[2 * item + 1] = res.id_len;
+        }
       } else {
         size[item] = 0;
         nnodes[item] = 0;
-        pending[atomicAdd(n_pending, 1u)] = (u32)item;
+        first[item] = GGR_NIL;
+        if (final_status >= 0) status[item] = final_status;  // last tier of the envelope mode: no per-thread path
+        else pending[atomicAdd(n_pending, 1u)] = (u32)item;
       }
     }
   }
@@ -101,18 +110,19 @@ int ggr_encode_coop_init() {
 void ggr_launch_encode_coop_parse(cudaStream_t st, int tier, long long n, const uint8_t* blob, uint32_t n_msgs,
                                   const int32_t* msg_id, const uint8_t* in, const uint64_t* in_off, uint8_t* ir, uint32_t* size,
                                   uint32_t* first, int32_t* status, uint32_t* ioff, uint32_t* nnodes, const uint32_t* list,
-                                  const uint32_t* list_n, uint32_t* pending, uint32_t* n_pending, int sm_count) {
+                                  const uint32_t* list_n, uint32_t* pending, uint32_t* n_pending, int sm_count, int32_t* method,
+                                  uint32_t* id_span, int32_t final_status) {
   if (tier == 0) {
     // 4 resident blocks per SM (shared memory); never more blocks than items / CE_WARPS
     long long want = (n + CE_WARPS - 1) / CE_WARPS, cap = (long long)sm_count * 4;
     unsigned nb = (unsigned)(want < cap ? want : cap);
     k_encode_coop_parse<CoopEnc><<<nb, CE_WARPS * 32, ce_smem_bytes<CoopEnc>(), st>>>(
-        blob, n, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending);
+        blob, n, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending, method, id_span, final_status);
   } else {
     // the list length lives on the device: two blocks per SM (shared memory), warps stride over the list
     unsigned nb = (unsigned)sm_count * 2u;
     k_encode_coop_parse<CoopEncBig><<<nb, CE_WARPS * 32, ce_smem_bytes<CoopEncBig>(), st>>>(
-        blob, n, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending);
+        blob, n, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending, method, id_span, final_status);
   }
 }
 

@@ -70,6 +70,8 @@ def _load():
     dev_sig = [vp, vp, C.c_int64, vp, vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp, C.c_uint32, vp]
     L.ggr_encode_batch_dev.argtypes = dev_sig
     L.ggr_decode_batch_dev.argtypes = dev_sig
+    L.ggr_request_batch.argtypes = [vp, vp, C.c_int64, vp, vp, vp, C.c_uint64, vp, vp, vp, vp]
+    L.ggr_request_batch_dev.argtypes = [vp, vp, C.c_int64, vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp, vp, vp, vp]
     L.ggr_decode_wrap_batch.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_uint64, vp, vp, C.c_uint32]
     L.ggr_decode_wrap_batch_dev.argtypes = [vp, vp, C.c_int64, vp, vp, vp, C.c_uint64, vp, vp, vp, C.c_uint64, vp, vp, C.c_uint32, vp]
     L.ggr_synchronize.argtypes = [vp]
@@ -176,6 +178,25 @@ class Engine:
         """Protobuf wire bytes -> protojson text.  Returns (bytes, offsets[n+1], status[n])."""
         cap = out_cap if out_cap is not None else len(data) * 3 + 64 * len(msg_ids) + 64
         return self._host(_load().ggr_decode_batch, schema, msg_ids, data, off, flags, cap)
+
+    def request_batch(self, schema, bodies, off, out_cap=None):
+        """JSON-RPC tools/call request bodies -> (wire bytes, offsets[n+1], method[n], id_span[n, 2], status[n]);
+        status 11 (unsupported) = the device does not take this body."""
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        n = len(off) - 1
+        bodies = np.ascontiguousarray(bodies, dtype=np.uint8)
+        cap = int(out_cap if out_cap is not None else len(bodies) + 64)
+        out = np.empty(max(cap, 1), dtype=np.uint8)
+        out_off = np.zeros(n + 1, dtype=np.uint64)
+        method = np.full(max(n, 1), -1, dtype=np.int32)
+        id_span = np.zeros((max(n, 1), 2), dtype=np.uint32)
+        status = np.zeros(max(n, 1), dtype=np.int32)
+        rc = _load().ggr_request_batch(self.h, schema.h, n, bodies.ctypes.data if len(bodies) else out.ctypes.data, off.ctypes.data,
+                                       out.ctypes.data, cap, out_off.ctypes.data, method.ctypes.data, id_span.ctypes.data,
+                                       status.ctypes.data)
+        if rc != 0:
+            self._err(rc, "ggr_request_batch")
+        return out[: int(out_off[n])], out_off, method[:n], id_span[:n], status[:n]
 
     def decode_wrap_batch(self, schema, msg_ids, data, off, ids, ids_off, flags=0, out_cap=None):
         """Protobuf wire bytes -> complete MCP tools/call result bodies (handler.go:265-270, 290-297).

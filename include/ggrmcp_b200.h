@@ -135,6 +135,26 @@ int ggr_decode_batch_dev(ggr_engine* e, const ggr_schema* s, int64_t n, const in
 int ggr_synchronize(ggr_engine* e);
 
 /*
+ * Request bodies (handler.go:83-95 decode, pkg/mcp/validation.go, discovery.go:336-375 tool lookup,
+ * handler.go:224-231 json.Marshal(arguments), reflection.go:351-373 request half).  Item i is the
+ * HTTP body body[body_off[i] .. body_off[i+1]) of a JSON-RPC tools/call request.  For the bodies the
+ * device takes, status[i] == 0 and out holds the wire bytes of the arguments, method[i] the index
+ * of the tool's method (ggr_method_get) and id_span[2i], id_span[2i+1] position and length of the id
+ * token inside the body.  The device takes a body exactly when the reference accepts it and the
+ * canonicalisation of handler.go:224-231 cannot change what protojson sees: every key once, names in
+ * their exact case, id a plain ASCII string or an integer of at most 15 digits, numbers in the
+ * arguments plain integers of at most 15 digits, nesting within validateDepth's limit.  Every other
+ * body - malformed ones included - comes back with status[i] == GGR_ST_UNSUPPORTED and no output:
+ * the caller takes the reference's own path for it (error envelopes carry Go's wording).
+ */
+int ggr_request_batch(ggr_engine* e, const ggr_schema* s, int64_t n, const uint8_t* body, const uint64_t* body_off,
+                      uint8_t* out, uint64_t out_cap, uint64_t* out_off, int32_t* method, uint32_t* id_span,
+                      int32_t* status);
+int ggr_request_batch_dev(ggr_engine* e, const ggr_schema* s, int64_t n, const uint8_t* in, const uint64_t* in_off,
+                          uint64_t in_bytes, uint8_t* out, uint64_t out_cap, uint64_t* out_off, int32_t* method,
+                          uint32_t* id_span, int32_t* status, void* stream);
+
+/*
  * Reply half plus result wrapping (handler.go:265-270 ToolCallResult / TextContent and
  * handler.go:290-297 writeJSONResponse): out[out_off[i] .. out_off[i+1]) is the complete HTTP body
  *   {"jsonrpc":"2.0","result":{"content":[{"type":"text","text":"<protojson text, escaped as

@@ -229,3 +229,46 @@ def test_result_bodies(engine, schema, oracle):
         else:
             assert got == b""
     assert ok > len(items) // 2
+
+
+def test_request_bodies(engine, schema, oracle):
+    """request envelope on the device against orc_request: a body the device takes must
+    give the oracle's wire bytes, method and id; every other body must come back as unsupported (11)"""
+    from ggrmcp_b200.engine import pack
+    import benchgen
+    from test_oracle import K_BODIES
+    by_input = {m["input"]: (i, m["tool"]) for i, m in reversed(list(enumerate(oracle.methods())))}
+    rng = random.Random(77)
+    bodies = [b[0] for b in K_BODIES]
+    for i, (name, js) in enumerate(cases.random_encode_cases(40, seed0=15000)):
+        k = oracle.msg(name)
+        if k not in by_input:
+            continue
+        tool = by_input[k][1].encode()
+        idt = rng.choice([b"1", b"42", b'"abc"', b"-7", b"123456789012345", b"1.0", b'"a<b"', b"9007199254740993", b"null"])
+        body = b'{"jsonrpc":"2.0","id":' + idt + b',"method":"tools/call","params":{"name":"' + tool + b'","arguments":' + js + b"}}"
+        bodies.append(body)
+        bodies.append([body.replace(b'"2.0"', b'"1.0"'), body.replace(b"tools/call", b"tools/list"), body[:-1] + b',"x":1}',
+                       body.replace(b",", b" ,\n"), body[: len(body) // 2], b""][i % 6])
+    wl = benchgen.nested(400, oracle.msg)
+    blob = wl.req_json.tobytes()
+    for i in range(400):
+        js = blob[int(wl.req_off[i]):int(wl.req_off[i + 1])]
+        bodies.append(b'{"jsonrpc":"2.0","id":%d,"method":"tools/call","params":{"name":"%s","arguments":%s}}'
+                      % (i, by_input[int(wl.req_msg[i])][1].encode(), js))
+    data, off = pack(bodies)
+    out, ooff, method, id_span, st = engine.request_batch(schema, data, off)
+    taken = 0
+    for i, body in enumerate(bodies):
+        r = oracle.request(body)
+        got = bytes(out[int(ooff[i]):int(ooff[i + 1])])
+        assert st[i] in (0, 11), (body[:120], st[i])
+        if st[i] == 0:
+            idt = body[int(id_span[i][0]): int(id_span[i][0]) + int(id_span[i][1])]
+            assert r["kind"] == 0 and got == r["wire"] and int(method[i]) == r["method"] and idt == r["id"], (body[:200], r["kind"], r["status"])
+            # the method index means the same thing on both sides
+            assert schema.methods()[int(method[i])]["tool_name"] == oracle.methods()[r["method"]]["tool"]
+            taken += 1
+        else:
+            assert got == b""
+    assert taken >= 400  # every bench-shaped body at least
