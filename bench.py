@@ -282,6 +282,68 @@ def main():
     ms_max = float(t_ms.item())
     value = world * n * args.steps / (ms_max / 1000.0)
 
+    # ---- the same step at the HTTP-body boundary: request bodies in, result bodies out ----
+    bodies_value = None
+    if have_req and args.workload == "nested":
+        tool_of = {}
+        for mi in reversed(schema.methods()):
+            tool_of[mi["input_msg"]] = mi["tool_name"].encode()
+        jblob = wl.req_json.tobytes()
+        parts = []
+        for i in range(n):
+            parts.append(b'{"jsonrpc":"2.0","id":%d,"method":"tools/call","params":{"name":"%s","arguments":' % (i, tool_of[int(wl.req_msg[i])]))
+            parts.append(jblob[int(wl.req_off[i]):int(wl.req_off[i + 1])])
+            parts.append(b"}}")
+        lens = np.fromiter((len(parts[3 * i]) + len(parts[3 * i + 1]) + 2 for i in range(n)), np.uint64, n)
+        b_off = np.zeros(n + 1, np.uint64)
+        b_off[1:] = np.cumsum(lens)
+        b_all = np.frombuffer(b"".join(parts), np.uint8)
+        del parts
+        id_txt = [b"%d" % i for i in range(n)]
+        i_off = np.zeros(n + 1, np.uint64)
+        i_off[1:] = np.cumsum([len(t) for t in id_txt])
+        d_b, d_b_off = to_dev(b_all, 64), to_dev(b_off)
+        d_ids, d_ids_off = to_dev(np.frombuffer(b"".join(id_txt), np.uint8), 64), to_dev(i_off)
+        d_method = torch.empty(n, dtype=torch.int32, device=dev)
+        d_span = torch.empty(2 * n, dtype=torch.int32, device=dev)
+        body_cap = int(rep_cap * 1.5 + 128 * n)
+        d_body_out = torch.empty(body_cap, dtype=torch.uint8, device=dev)
+        d_body_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+
+        def step_bodies_resident():
+            rc = L0.ggr_request_batch_dev(eng.h, schema.h, n, d_b.data_ptr(), d_b_off.data_ptr(), len(b_all), d_req_out.data_ptr(), req_cap,
+                                          d_req_out_off.data_ptr(), d_method.data_ptr(), d_span.data_ptr(), d_req_st.data_ptr(), sp)
+            assert rc == 0, rc
+            rc = L0.ggr_decode_wrap_batch_dev(eng.h, schema.h, n, d_rep_msg.data_ptr(), d_rep.data_ptr(), d_rep_off.data_ptr(), W_in,
+                                              d_ids.data_ptr(), d_ids_off.data_ptr(), d_body_out.data_ptr(), body_cap,
+                                              d_body_off.data_ptr(), d_rep_st.data_ptr(), 0, sp2)
+            assert rc == 0, rc
+
+        L0 = ggrmcp_b200.engine._load()
+        for _ in range(3):
+            step_bodies_resident()
+        torch.cuda.synchronize()
+        assert int((d_req_st != 0).sum()) == 0, "request bodies not taken by the device"
+        assert int(d_req_out_off[n].item()) == W_out and int((d_rep_st != 0).sum()) == 0
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record(stream)
+        stream2.wait_event(b0)
+        for _ in range(args.steps):
+            step_bodies_resident()
+        bj = torch.cuda.Event()
+        bj.record(stream2)
+        stream.wait_event(bj)
+        b1.record(stream)
+        barrier()
+        t_b = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t_b, op=dist.ReduceOp.MAX)
+        bodies_value = {"value": world * n * args.steps / (float(t_b.item()) / 1000.0), "unit": UNIT,
+                        "boundary": "HTTP bodies: JSON-RPC request body -> method + wire, wire -> complete result body (rows A1-A10)",
+                        "request_body_bytes": int(len(b_all)), "result_body_bytes": int(d_body_off[n].item())}
+        del d_b, d_body_out
+
     # ---- end-to-end: host (pinned) buffers through the public C-ABI call, copies included ----
     e2e_steps = args.e2e_steps or min(args.steps, 5)
     L = ggrmcp_b200.engine._load()
@@ -430,6 +492,7 @@ def main():
                    "items_per_gpu": n, "boundary": "InvokeMethod (arguments JSON -> wire, wire -> protojson)",
                    "avg_bytes": {"J_in": J_in / n, "W_out": W_out / n, "W_in": W_in / n, "J_out": J_out / n},
                    "l2": "inputs exceed L2 (%.0f MB read per step)" % ((J_in + W_in) / 1e6), "parallelism": "shard-by-index x%d, no collective" % world},
+        "http_bodies": bodies_value,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                 "timing": "wall clock around the C-ABI host-buffer calls (pinned buffers; request batch and reply batch %s), max over ranks"
                           % ("one after the other" if args.e2e_serial else "in flight together from two host threads"),
