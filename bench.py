@@ -297,13 +297,13 @@ def main():
         lens = np.fromiter((len(parts[3 * i]) + len(parts[3 * i + 1]) + 2 for i in range(n)), np.uint64, n)
         b_off = np.zeros(n + 1, np.uint64)
         b_off[1:] = np.cumsum(lens)
-        b_all = np.frombuffer(b"".join(parts), np.uint8)
+        b_all = np.frombuffer(b"".join(parts), np.uint8).copy()
         del parts
         id_txt = [b"%d" % i for i in range(n)]
         i_off = np.zeros(n + 1, np.uint64)
         i_off[1:] = np.cumsum([len(t) for t in id_txt])
         d_b, d_b_off = to_dev(b_all, 64), to_dev(b_off)
-        d_ids, d_ids_off = to_dev(np.frombuffer(b"".join(id_txt), np.uint8), 64), to_dev(i_off)
+        d_ids, d_ids_off = to_dev(np.frombuffer(b"".join(id_txt), np.uint8).copy(), 64), to_dev(i_off)
         d_method = torch.empty(n, dtype=torch.int32, device=dev)
         d_span = torch.empty(2 * n, dtype=torch.int32, device=dev)
         body_cap = int(rep_cap * 1.5 + 128 * n)
@@ -404,7 +404,7 @@ def main():
     # bare protojson texts: reported next to e2e, not instead of it
     e2e_bodies = None
     if have_req and not args.e2e_serial:
-        ids = np.frombuffer(b"".join(b"%d" % (i % 100000) for i in range(n)), np.uint8)
+        ids = np.frombuffer(b"".join(b"%d" % (i % 100000) for i in range(n)), np.uint8).copy()
         ids_off = np.zeros(n + 1, np.uint64)
         ids_off[1:] = np.cumsum([len(b"%d" % (i % 100000)) for i in range(n)])
         h_ids, h_ids_off = pinned(ids), pinned(ids_off)

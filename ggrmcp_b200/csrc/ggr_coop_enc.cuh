@@ -944,6 +944,7 @@ GGR_DEV bool ce_parse_item(SH& S, const CeLut& lut, const Tables& T, u32 root_ms
   cx.ioff = ioff;
   u32 root_tok = 0;
   if (envelope) {  // the message is the `arguments` object of the request, its type comes from the tool name
+    WP_SYNC();  // every lane has read `bail` above before lane 0 may set it again
     if (lane == 0) ce_envelope(S, cx);
     WP_SYNC();
     if (S.bail) return false;

@@ -53,4 +53,26 @@ r2, rf2, rs2 = O.decode_batch(wl.rep_msg, wl.rep_wire, wl.rep_off, threads=2, ca
 assert int((s1 != 0).sum()) == 0 and int((s2 != 0).sum()) == 0
 assert bytes(o1[: int(f1[-1])]) == bytes(r1) and bytes(o2[: int(f2[-1])]) == bytes(r2)
 ok += 2 * wl.n
+# HTTP-body boundary: request bodies in, result bodies out
+from ggrmcp_b200.engine import pack
+tool_of = {}
+for mi in reversed(schema.methods()):
+    tool_of[mi["input_msg"]] = mi["tool_name"].encode()
+jb = wl.req_json.tobytes()
+bodies = [b'{"jsonrpc":"2.0","id":%d,"method":"tools/call","params":{"name":"%s","arguments":%s}}'
+          % (i, tool_of[int(wl.req_msg[i])], jb[int(wl.req_off[i]):int(wl.req_off[i + 1])]) for i in range(wl.n)]
+bodies += [b'{"jsonrpc":"2.0","id":1.5,"method":"tools/call","params":{"name":"x","arguments":{}}}', b"{", b""]
+data, off = pack(bodies)
+wout, woff, method, span, st = eng.request_batch(schema, data, off)
+for i in range(wl.n):
+    assert st[i] == 0 and bytes(wout[int(woff[i]):int(woff[i + 1])]) == bytes(r1[int(rf1[i]):int(rf1[i + 1])])
+assert list(st[wl.n:]) == [11, 11, 11]
+ids, ioff = pack([b"%d" % i for i in range(wl.n)])
+bout, boff, st = eng.decode_wrap_batch(schema, wl.rep_msg, wl.rep_wire, wl.rep_off, ids, ioff)
+names = {schema.message(n): n for n in ("com.example.complex.Node", "com.example.complex.GetUserProfileResponse")}
+rw = wl.rep_wire.tobytes()
+for i in range(0, wl.n, 7):
+    rc, body = O.response(names[int(wl.rep_msg[i])], rw[int(wl.rep_off[i]):int(wl.rep_off[i + 1])], b"%d" % i)
+    assert st[i] == 0 and bytes(bout[int(boff[i]):int(boff[i + 1])]) == body
+ok += 2 * wl.n
 print("ok items", ok)
