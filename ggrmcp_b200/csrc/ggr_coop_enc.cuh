@@ -765,6 +765,36 @@ GGR_DEV void ce_envelope(SH& S, const EncCtx& cx) {
 
 GGR_DEV u32 ce_link(u32 x) { return x == CE_NIL ? GGR_NIL : x; }
 
+// Envelope mode, one lane: a number literal that json.Marshal would re-print differently.  Returns false
+// when the literal is no float64 (range) or the re-printed text does not parse for the field.
+GGR_DEVN bool ce_leaf_number_via_float64(EncCtx& cx, u32 pos, const FieldD& f, Leaf* l) {
+  Leaf ld;
+  {
+    Rd r;
+    r.init(cx.in, pos, cx.end);
+    if (parse_scalar(cx, r, GK_DOUBLE, -1, &ld) != GST_OK) return false;
+    if (!r.eof()) {
+      const u32 c = r.peek();
+      if (!(ggr_is_ws(c) || c == ',' || c == '}' || c == ']')) return false;
+    }
+  }
+  const u64 bits = (u64)ld.a | ((u64)ld.b << 32);
+#if defined(__CUDA_ARCH__)
+  __align__(16) u8 buf[64];
+#else
+  alignas(16) u8 buf[64];
+#endif
+  for (int k = 0; k < 64; k++) buf[k] = 0;
+  Sw w;
+  w.init(buf, 0);
+  put_float_go(w, bits, false);  // encoding/json floatEncoder == protojson's number format
+  if (w.pos == 0 || w.pos > 30) return false;
+  Rd r2;
+  r2.init(buf, 0, w.pos, 1);  // a local buffer: not through the read-only path
+  if (parse_scalar(cx, r2, f.kind, f.child, l) != GST_OK) return false;
+  return r2.eof();
+}
+
 // T4, one lane: finish leaf node `ni` (IR node + size into its parent).
 template <class SH>
 GGR_DEV void ce_leaf(SH& S, EncCtx& cx, u32 ni) {
@@ -817,15 +847,19 @@ GGR_DEV void ce_leaf(SH& S, EncCtx& cx, u32 ni) {
   Leaf l;
   bool done = false;
   if (S.env && TK_KIND(tk) == TK_SCALAR) {
-    // json.Marshal(arguments) re-prints numbers from float64: only plain integers of at most 15 digits are
-    // guaranteed to come out as they went in
+    // json.Marshal(arguments) re-prints every number from float64 (handler.go:224-231): plain integers of at
+    // most 15 digits come out as they went in; any other literal is taken through the same round trip here -
+    // text -> float64 -> encoding/json's shortest text -> the field's own parser on that text
     u32 j = TK_POS(tk), digits = 0;
     const u32 c0 = cx.in[j];
     if (c0 == '-' || (c0 - '0') < 10u) {
       if (c0 == '-') j++;
       while (j < cx.end && (u32)(cx.in[j] - '0') < 10u) { j++; digits++; }
       const u32 c = j < cx.end ? cx.in[j] : 0u;
-      if (digits == 0 || digits > 15u || c == '.' || c == 'e' || c == 'E') { S.bail = 1; return; }
+      if (digits == 0 || digits > 15u || c == '.' || c == 'e' || c == 'E') {
+        if (!ce_leaf_number_via_float64(cx, TK_POS(tk), f, &l)) { S.bail = 1; return; }
+        done = true;
+      }
     }
   }
   if (nd.cls == CC_STR && TK_KIND(tk) == TK_STR) {

@@ -40,7 +40,7 @@ struct DecResult {
 // ---- wire readers ----
 GGR_DEV void rd_jump(Rd& r, u32 pos) {
   u32 e = r.end;
-  r.init(r.base, pos, e);
+  r.init(r.base, pos, e, r.rw);
 }
 // protowire.ConsumeVarint bounded by `lim`
 GGR_DEV bool rd_varint(Rd& r, u32 lim, u64* out) {

@@ -583,7 +583,7 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
     r.init(in, start, end);
     if (end - start == 2 && (r.peek4() & 0xFFFFu) == (u32)('{' | ('}' << 8))) finished = true;
   } else {
-    r.base = in; r.pos = r.end = r.fetch = 0; r.avail = 0; r.cur = 0; r.ch.x = r.ch.y = r.ch.z = r.ch.w = 0;
+    r.base = in; r.pos = r.end = r.fetch = 0; r.avail = 0; r.rw = 0; r.cur = 0; r.ch.x = r.ch.y = r.ch.z = r.ch.w = 0;
   }
 
   Frame stk[GGR_MAX_DEPTH];

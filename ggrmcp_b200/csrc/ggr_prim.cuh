@@ -155,6 +155,7 @@ struct Rd {
   int avail;  // valid bytes in cur
   u64 cur;    // next bytes of the stream, lowest byte first
   U4 ch;      // current 16-byte chunk
+  u32 rw;     // 1: the buffer was written by this thread (local scratch): plain loads, not the read-only path
 
   GGR_DEV u32 word() const {
     u32 i = (fetch >> 2) & 3u;
@@ -164,19 +165,20 @@ struct Rd {
   }
   GGR_DEV void fill() {
     if (avail <= 4) {
-      if ((fetch & 15u) == 0) ch = ggr_ld16(base + fetch);
+      if ((fetch & 15u) == 0) ch = rw ? ggr_ld16_rw(base + fetch) : ggr_ld16(base + fetch);
       u32 w = word();
       fetch += 4;
       cur |= (u64)w << (8 * avail);
       avail += 4;
     }
   }
-  GGR_DEV void init(const u8* b, u32 start, u32 e) {
+  GGR_DEV void init(const u8* b, u32 start, u32 e, u32 written_by_me = 0) {
     base = b;
     pos = start;
     end = e;
+    rw = written_by_me;
     fetch = start & ~3u;
-    ch = ggr_ld16(base + (start & ~15u));
+    ch = rw ? ggr_ld16_rw(base + (start & ~15u)) : ggr_ld16(base + (start & ~15u));
     u32 w = word();
     fetch += 4;
     int drop = (int)(start & 3u);

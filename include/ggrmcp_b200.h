@@ -141,9 +141,9 @@ int ggr_synchronize(ggr_engine* e);
  * device takes, status[i] == 0 and out holds the wire bytes of the arguments, method[i] the index
  * of the tool's method (ggr_method_get) and id_span[2i], id_span[2i+1] position and length of the id
  * token inside the body.  The device takes a body exactly when the reference accepts it and the
- * canonicalisation of handler.go:224-231 cannot change what protojson sees: every key once, names in
- * their exact case, id a plain ASCII string or an integer of at most 15 digits, numbers in the
- * arguments plain integers of at most 15 digits, nesting within validateDepth's limit.  Every other
+ * canonicalisation of handler.go:224-231 is reproduced exactly: every key once, names in their exact
+ * case, id a plain ASCII string or an integer of at most 15 digits, nesting within validateDepth's
+ * limit; numbers in the arguments take the reference's float64 round trip on the device.  Every other
  * body - malformed ones included - comes back with status[i] == GGR_ST_UNSUPPORTED and no output:
  * the caller takes the reference's own path for it (error envelopes carry Go's wording).
  */

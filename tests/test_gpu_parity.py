@@ -250,6 +250,10 @@ def test_request_bodies(engine, schema, oracle):
         bodies.append(body)
         bodies.append([body.replace(b'"2.0"', b'"1.0"'), body.replace(b"tools/call", b"tools/list"), body[:-1] + b',"x":1}',
                        body.replace(b",", b" ,\n"), body[: len(body) // 2], b""][i % 6])
+    for i, args in enumerate([b'{"f_double":1.5,"f_float":0.1,"f_int32":1e2,"f_uint64":18446744073709551615}', b'{"f_int64":9007199254740993}',
+                              b'{"f_double":1e400}', b'{"f_float":3.4028236e38}', b'{"r_double":[0.30000000000000004,-0.0,4.9e-324]}',
+                              b'{"f_sint64":-1.0,"f_fixed32":4294967295.0}', b'{"f_int32":1.5}']):
+        bodies.append(b'{"jsonrpc":"2.0","id":%d,"method":"tools/call","params":{"name":"bench_benchservice_echoall","arguments":%s}}' % (i, args))
     wl = benchgen.nested(400, oracle.msg)
     blob = wl.req_json.tobytes()
     for i in range(400):

@@ -336,3 +336,42 @@ def test_request_envelope_vectors_and_bench_shapes(oracle, hsim):
         r = oracle.request(body)
         rc, w, method, idt = hsim.request_coop(body, i % 16, (i * 3) % 16, 1)
         assert rc == 0 and r["kind"] == 0 and w == r["wire"] and method == r["method"] and idt == r["id"]
+
+
+def test_request_envelope_numbers(oracle, hsim):
+    """json.Marshal(arguments) passes every number through float64: literals that are not plain short integers
+    take the same round trip on the device (text -> float64 -> shortest text -> the field's parser)"""
+    rng = random.Random(5)
+    kinds = ["int32", "int64", "uint32", "uint64", "sint32", "sint64", "fixed32", "fixed64", "sfixed32", "sfixed64", "float", "double"]
+
+    def lit():
+        c = rng.random()
+        if c < 0.15:
+            return str(rng.randrange(-200, 200))
+        if c < 0.3:
+            return str(rng.choice([2**31 - 1, 2**31, -2**31, 2**32 - 1, 2**53, 2**53 + 1, 2**63 - 1, 2**63, -2**63, 2**64 - 1, 2**64,
+                                   9007199254740993, 123456789012345678]))
+        if c < 0.45:
+            return "%d.%s" % (rng.randrange(-50, 50), rng.choice(["0", "5", "25", "000", "10"]))
+        if c < 0.6:
+            return "%de%d" % (rng.randrange(-99, 99), rng.randrange(0, 22))
+        if c < 0.7:
+            return "%d.%de%s%d" % (rng.randrange(0, 9), rng.randrange(0, 999), rng.choice(["", "+", "-"]), rng.randrange(0, 40))
+        if c < 0.8:
+            return repr(rng.uniform(-1e6, 1e6))
+        if c < 0.9:
+            return rng.choice(["-0", "-0.0", "0.0", "1e400", "1e-400", "0.1", "3.4028235e38", "3.4028236e38", "1.7976931348623157e308",
+                               "4.9e-324", "16777217", "0.30000000000000004"])
+        return rng.choice(["1.5", "2.5", "1e21", "1e20", "123456789012345678901234567890", "0.000001", "0.0000001", "1E3", "1e+3", "-1e-7"])
+
+    handled = accepted_by_oracle = 0
+    for it in range(1500):
+        fs = rng.sample(kinds, rng.randrange(1, 5))
+        args = "{" + ",".join('"f_%s":%s' % (k, lit()) for k in fs)
+        if rng.random() < 0.3:
+            args += ',"r_double":[%s]' % ",".join(lit() for _ in range(rng.randrange(0, 4)))
+        args += "}"
+        body = ('{"jsonrpc":"2.0","id":%d,"method":"tools/call","params":{"name":"bench_benchservice_echoall","arguments":%s}}' % (it, args)).encode()
+        handled += _check_request(oracle, hsim, body, it)
+        accepted_by_oracle += oracle.request(body)["kind"] == 0
+    assert handled == accepted_by_oracle and handled > 200  # nothing the reference accepts is left to the host here
