@@ -795,8 +795,8 @@ GGR_DEVN bool ce_leaf_number_via_float64(EncCtx& cx, u32 pos, const FieldD& f, L
   return r2.eof();
 }
 
-// T4, one lane: finish leaf node `ni` (IR node + size into its parent).
-template <class SH>
+// T4, one lane: finish leaf node `ni` (IR node + size into its parent).  ENV: request-envelope mode.
+template <class SH, bool ENV>
 GGR_DEV void ce_leaf(SH& S, EncCtx& cx, u32 ni) {
   const CNode nd = S.node[ni];
   const u32 next = ce_link(nd.next);
@@ -846,7 +846,7 @@ GGR_DEV void ce_leaf(SH& S, EncCtx& cx, u32 ni) {
   }
   Leaf l;
   bool done = false;
-  if (S.env && TK_KIND(tk) == TK_SCALAR) {
+  if (ENV && TK_KIND(tk) == TK_SCALAR) {
     // json.Marshal(arguments) re-prints every number from float64 (handler.go:224-231): plain integers of at
     // most 15 digits come out as they went in; any other literal is taken through the same round trip here -
     // text -> float64 -> encoding/json's shortest text -> the field's own parser on that text
@@ -939,9 +939,10 @@ GGR_DEV void ce_place_children(SH& S, u32 ni) {
 
 // One item, all 32 lanes.  Returns true when the item was handled (IR written, *res filled);
 // false leaves it to the per-thread parser.
-template <class SH>
+template <class SH, bool ENV>
 GGR_DEV bool ce_parse_item(SH& S, const CeLut& lut, const Tables& T, u32 root_msg, const u8* in, u32 start, u32 end, u8* ir,
-                           u32* ioff, u32 ir_cap, EncResult* res, bool envelope = false) {
+                           u32* ioff, u32 ir_cap, EncResult* res) {
+  const bool envelope = ENV;
   const u32 lane = wp_lane();
   res->size = 0;
   res->first = GGR_NIL;
@@ -1050,7 +1051,7 @@ GGR_DEV bool ce_parse_item(SH& S, const CeLut& lut, const Tables& T, u32 root_ms
   }
   WP_SYNC();
   const u32 n_leaf = S.n_leaf;
-  for (u32 k = lane; k < n_leaf; k += 32) ce_leaf(S, cx, S.order[k]);
+  for (u32 k = lane; k < n_leaf; k += 32) ce_leaf<SH, ENV>(S, cx, S.order[k]);
   WP_SYNC();
   if (S.bail) return false;
   // T5: containers, deepest first (the root, depth 0, has no node of its own in the IR)

@@ -11,7 +11,7 @@
 
 // Every item the lock-step parser handles gets size / first / status written here; the others are
 // appended to `pending` (order irrelevant).  list != nullptr: items come from that list.
-template <class SH>
+template <class SH, bool ENV>
 __global__ void __launch_bounds__(CE_WARPS * 32)
 k_encode_coop_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const i32* __restrict__ msg_id,
                     const u8* __restrict__ in, const u64* __restrict__ in_off, u8* __restrict__ ir, u32* __restrict__ size,
@@ -32,7 +32,7 @@ k_encode_coop_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const 
     const long long item = list ? (long long)list[slot] : slot;
     const u64 a = in_off[item], b = in_off[item + 1];
     // envelope mode (method != nullptr): the item is a whole request body, its message type comes from the tool name
-    const bool envelope = method != nullptr;
+    const bool envelope = ENV;
     const i32 m = envelope ? 0 : msg_id[item];
     bool ok = false;
     EncResult res;
@@ -44,7 +44,7 @@ k_encode_coop_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const 
       const u32 cap = (u32)((((b - a0) >> 1) + 8ull * (u64)(item + 1)) - node_off);
       const u8* base = in + (a & ~15ull);
       const u32 s0 = (u32)(a & 15ull);
-      ok = ce_parse_item(S[warp], lut, T, (u32)m, base, s0, s0 + (u32)(b - a), ir + node_off * 16, ioff + node_off, cap, &res, envelope);
+      ok = ce_parse_item<SH, ENV>(S[warp], lut, T, (u32)m, base, s0, s0 + (u32)(b - a), ir + node_off * 16, ioff + node_off, cap, &res);
     }
     if (lane == 0) {
       if (ok) {
@@ -97,14 +97,26 @@ static size_t ce_smem_bytes() {
   return ((sizeof(CeLut) + 15) & ~(size_t)15) + sizeof(SH) * CE_WARPS;
 }
 
+template <class SH, bool ENV>
+static cudaError_t ce_opt_in() {
+  return cudaFuncSetAttribute(k_encode_coop_parse<SH, ENV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ce_smem_bytes<SH>());
+}
 int ggr_encode_coop_init() {
-  cudaError_t a = cudaFuncSetAttribute(k_encode_coop_parse<CoopEnc>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)ce_smem_bytes<CoopEnc>());
-  cudaError_t b = cudaFuncSetAttribute(k_encode_coop_parse<CoopEncBig>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)ce_smem_bytes<CoopEncBig>());
+  cudaError_t a = ce_opt_in<CoopEnc, false>(), b = ce_opt_in<CoopEncBig, false>();
+  cudaError_t a2 = ce_opt_in<CoopEnc, true>(), b2 = ce_opt_in<CoopEncBig, true>();
   cudaError_t c = cudaFuncSetAttribute(k_encode_coop_emit, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(sizeof(CoopEmit) * CE_WARPS));
-  return (a == cudaSuccess && b == cudaSuccess && c == cudaSuccess) ? 0 : -1;
+  return (a == cudaSuccess && b == cudaSuccess && a2 == cudaSuccess && b2 == cudaSuccess && c == cudaSuccess) ? 0 : -1;
+}
+
+template <class SH, bool ENV>
+static void ce_launch(cudaStream_t st, unsigned nb, long long n, const uint8_t* blob, uint32_t n_msgs, const int32_t* msg_id,
+                      const uint8_t* in, const uint64_t* in_off, uint8_t* ir, uint32_t* size, uint32_t* first, int32_t* status,
+                      uint32_t* ioff, uint32_t* nnodes, const uint32_t* list, const uint32_t* list_n, uint32_t* pending,
+                      uint32_t* n_pending, int32_t* method, uint32_t* id_span, int32_t final_status) {
+  k_encode_coop_parse<SH, ENV><<<nb, CE_WARPS * 32, ce_smem_bytes<SH>(), st>>>(
+      blob, n, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending, method,
+      id_span, final_status);
 }
 
 void ggr_launch_encode_coop_parse(cudaStream_t st, int tier, long long n, const uint8_t* blob, uint32_t n_msgs,
@@ -112,17 +124,18 @@ void ggr_launch_encode_coop_parse(cudaStream_t st, int tier, long long n, const 
                                   uint32_t* first, int32_t* status, uint32_t* ioff, uint32_t* nnodes, const uint32_t* list,
                                   const uint32_t* list_n, uint32_t* pending, uint32_t* n_pending, int sm_count, int32_t* method,
                                   uint32_t* id_span, int32_t final_status) {
+  const bool env = method != nullptr;
   if (tier == 0) {
     // 4 resident blocks per SM (shared memory); never more blocks than items / CE_WARPS
     long long want = (n + CE_WARPS - 1) / CE_WARPS, cap = (long long)sm_count * 4;
     unsigned nb = (unsigned)(want < cap ? want : cap);
-    k_encode_coop_parse<CoopEnc><<<nb, CE_WARPS * 32, ce_smem_bytes<CoopEnc>(), st>>>(
-        blob, n, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending, method, id_span, final_status);
+    if (env) ce_launch<CoopEnc, true>(st, nb, n, blob, n_msgs, msg_id, in, in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending, method, id_span, final_status);
+    else ce_launch<CoopEnc, false>(st, nb, n, blob, n_msgs, msg_id, in, in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending, method, id_span, final_status);
   } else {
     // the list length lives on the device: two blocks per SM (shared memory), warps stride over the list
     unsigned nb = (unsigned)sm_count * 2u;
-    k_encode_coop_parse<CoopEncBig><<<nb, CE_WARPS * 32, ce_smem_bytes<CoopEncBig>(), st>>>(
-        blob, n, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending, method, id_span, final_status);
+    if (env) ce_launch<CoopEncBig, true>(st, nb, n, blob, n_msgs, msg_id, in, in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending, method, id_span, final_status);
+    else ce_launch<CoopEncBig, false>(st, nb, n, blob, n_msgs, msg_id, in, in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending, method, id_span, final_status);
   }
 }
 

@@ -113,7 +113,8 @@ struct CoopEncArgs {
 template <class SH>
 static void coop_enc_body(void* p, u32 lane) {
   CoopEncArgs<SH>* a = (CoopEncArgs<SH>*)p;
-  a->ok[lane] = ce_parse_item(*a->S, *a->lut, a->T, a->msg, a->in, a->start, a->end, a->ir, a->ioff, a->ir_cap, &a->res[lane], a->envelope);
+  a->ok[lane] = a->envelope ? ce_parse_item<SH, true>(*a->S, *a->lut, a->T, a->msg, a->in, a->start, a->end, a->ir, a->ioff, a->ir_cap, &a->res[lane])
+                            : ce_parse_item<SH, false>(*a->S, *a->lut, a->T, a->msg, a->in, a->start, a->end, a->ir, a->ioff, a->ir_cap, &a->res[lane]);
 }
 template <class SH>
 static void coop_emit_body(void* p, u32 lane) {
