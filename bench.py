@@ -483,6 +483,27 @@ def main():
         rate, secs = cpu_oracle_rate(args.workload, sample, cores, repeats=2, min_seconds=10.0)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d items of the %s workload repeated for %.1f s, oracle C++ port on %d threads" % (sample, args.workload, secs, cores)}
+        if bodies_value is not None:
+            # the CPU port at the HTTP-body boundary (orc_request + orc_response: envelope decode, validation,
+            # canonicalisation, transcoding, result wrapping) on a bounded sample
+            import orc
+            S, _ = _ORC_CACHE[(args.workload, sample)]
+            k = min(sample, 32768)
+            sb_off = b_off[: k + 1].copy()
+            sb = b_all[: int(sb_off[k])]
+            omsg = {int(v): S.msg(name) for name, v in ((nm, schema.message(nm)) for nm in
+                    ("com.example.complex.Node", "com.example.complex.GetUserProfileResponse"))}
+            rmsg = np.array([omsg[int(v)] for v in wl.rep_msg[:k]], np.int32)
+            roff = wl.rep_off[: k + 1].copy()
+            t0 = time.perf_counter()
+            reps = 0
+            while reps < 1 or time.perf_counter() - t0 < 4.0:
+                _, _, _, oids, oioff, ost = S.request_batch(sb, sb_off, threads=cores)
+                S.response_batch(rmsg, wl.rep_wire[: int(roff[k])], roff, oids, oioff, threads=cores)
+                reps += 1
+            bodies_value["cpu_value"] = k * reps / (time.perf_counter() - t0)
+            bodies_value["cpu_sample"] = "%d bodies x %d, oracle C++ port on %d threads" % (k, reps, cores)
+            assert int((ost != 0).sum()) == 0
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -141,6 +141,37 @@ class Schema:
             raise MemoryError("oracle batch output does not fit (cap=%d)" % cap)
         return out[: int(out_off[n])], out_off, status
 
+    def request_batch(self, bodies, off, threads=1):
+        """HTTP request bodies -> (wire bytes, offsets, method[n], id tokens, id offsets, status[n])"""
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        n = len(off) - 1
+        bodies = np.ascontiguousarray(bodies, dtype=np.uint8)
+        cap = int(len(bodies) + 64 * n + 64)
+        out, out_off = np.empty(cap, np.uint8), np.empty(n + 1, np.uint64)
+        ids, ids_off = np.empty(cap, np.uint8), np.empty(n + 1, np.uint64)
+        method, status = np.empty(n, np.int32), np.empty(n, np.int32)
+        rc = lib().orc_request_batch(self.h, n, bodies.ctypes.data, off.ctypes.data, out.ctypes.data, cap, out_off.ctypes.data,
+                                     method.ctypes.data, ids.ctypes.data, cap, ids_off.ctypes.data, status.ctypes.data, 0, threads)
+        if rc != 0:
+            raise MemoryError("oracle batch output does not fit")
+        return out[: int(out_off[n])], out_off, method, ids[: int(ids_off[n])], ids_off, status
+
+    def response_batch(self, msg_ids, data, off, ids, ids_off, flags=0, threads=1, cap=None):
+        """reply wire bytes + id tokens -> complete result bodies"""
+        n = len(msg_ids)
+        msg_ids = np.ascontiguousarray(msg_ids, dtype=np.int32)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        ids = np.ascontiguousarray(ids, dtype=np.uint8)
+        ids_off = np.ascontiguousarray(ids_off, dtype=np.uint64)
+        cap = int(cap or len(data) * 8 + 256 * n + 64)
+        out, out_off, status = np.empty(cap, np.uint8), np.empty(n + 1, np.uint64), np.empty(n, np.int32)
+        rc = lib().orc_response_batch(self.h, n, msg_ids.ctypes.data, data.ctypes.data, off.ctypes.data, ids.ctypes.data, ids_off.ctypes.data,
+                                      out.ctypes.data, cap, out_off.ctypes.data, status.ctypes.data, flags, threads)
+        if rc != 0:
+            raise MemoryError("oracle batch output does not fit")
+        return out[: int(out_off[n])], out_off, status
+
     def encode_batch(self, msg_ids, data, off, flags=0, threads=1, cap=None):
         cap = cap or int(len(data) + 64 * len(msg_ids) + 64)
         return self._batch(lib().orc_encode_batch, msg_ids, data, off, flags, threads, cap)
