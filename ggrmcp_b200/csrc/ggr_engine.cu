@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -84,6 +85,13 @@ __global__ void __launch_bounds__(256) k_route(long long n, const u64* __restric
 }
 
 // status / size of the items of a list (request bodies the lock-step parser cannot take)
+// the chunk's output size straight into mapped host memory: the host learns it from the stream's
+// event alone, without a copy that would queue behind other chunks' payloads on the copy engine
+__global__ void k_publish_total(const u64* __restrict__ src, volatile u64* dst) {
+  *dst = *src;
+  __threadfence_system();
+}
+
 __global__ void __launch_bounds__(256) k_mark(const u32* __restrict__ list, const u32* __restrict__ list_n, i32* __restrict__ status,
                                               u32* __restrict__ size, u32* __restrict__ first, i32 value) {
   const u32 i = blockIdx.x * 256u + threadIdx.x;
@@ -116,9 +124,13 @@ struct Scratch {
 struct Slot {
   cudaStream_t st = nullptr;
   cudaEvent_t ready = nullptr;
+  // inputs on the device / kernels done (staging free for the next chunk's inputs) / payload on the host
+  // (output buffer free for the next chunk's kernels)
+  cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr;
   Scratch sc;
   DevBuf d_in, d_off, d_msg, d_out, d_out_off, d_status, d_ids, d_ids_off;
-  uint64_t* h_total = nullptr;  // pinned: output bytes of the chunk in flight
+  uint64_t* h_total = nullptr;  // pinned + mapped: output bytes of the chunk in flight (written by k_publish_total)
+  uint64_t* d_total_alias = nullptr;  // the device's address of h_total
   uint64_t out_cap = 0;         // capacity handed to the kernels for that chunk
 };
 
@@ -136,13 +148,18 @@ struct ggr_engine {
   // batch and a reply batch can be in flight on two streams at the same time
   Scratch dev_sc[2];
   bool use_coop_enc = true;  // GGR_COOP_ENC=0 disables the lock-step request-side parser (A/B runs)
+  bool trace = false;        // GGR_TRACE=1: host-buffer calls print a per-chunk timeline to stderr
   // items smaller than this go straight to the per-thread kernels, which are cheaper for them
   // (GGR_LOCKSTEP_MIN_BYTES overrides both; 0 sends everything through the lock-step kernels)
   uint32_t min_json = 1024, min_wire = 640;
   // host-buffer entry points: the batch is cut into chunks that move through `n_slots` slots
   // (stream + staging + scratch each), so that H2D, kernels and D2H of different chunks overlap
   Slot slots[2][GGR_MAX_SLOTS];  // per direction
-  int n_slots = 6;
+  // per direction: all input copies on one stream and all payload copies on another, in chunk order (copies
+  // issued on many streams are time-sliced by the copy engine: every chunk arrives late); the slot streams
+  // carry the kernels and the small size / status copies
+  cudaStream_t s_in[2] = {nullptr, nullptr}, s_out[2] = {nullptr, nullptr};
+  int n_slots = 4;
   int64_t chunk_items = 8192;
   uint64_t chunk_bytes = 32ull << 20;
   // per-kernel timing
@@ -212,6 +229,7 @@ int ggr_engine_create(const ggr_config* cfg, ggr_engine** out) {
   if (e->sm_count <= 0) e->sm_count = 148;
   if (const char* nc = getenv("GGR_COOP")) e->use_coop = nc[0] != '0';
   if (const char* nc = getenv("GGR_COOP_ENC")) e->use_coop_enc = nc[0] != '0';
+  if (const char* nc = getenv("GGR_TRACE")) e->trace = nc[0] != '0';
   if (const char* nc = getenv("GGR_LOCKSTEP_MIN_BYTES")) e->min_json = e->min_wire = (uint32_t)strtoul(nc, nullptr, 10);
   if (const char* nc = getenv("GGR_SLOTS")) {
     int v = atoi(nc);
@@ -220,6 +238,10 @@ int ggr_engine_create(const ggr_config* cfg, ggr_engine** out) {
   if (const char* nc = getenv("GGR_CHUNK_ITEMS")) {
     long long v = atoll(nc);
     if (v >= 128) e->chunk_items = v;
+  }
+  if (const char* nc = getenv("GGR_CHUNK_BYTES")) {
+    long long v = atoll(nc);
+    if (v >= (1 << 16)) e->chunk_bytes = (uint64_t)v;
   }
   e->order = (cfg && cfg->wire_order == GGR_ORDER_GO_LEGACY) ? ggr::ORDER_GO_LEGACY : ggr::ORDER_FIELD_NUMBER;
   if (ggr_encode_coop_init() != 0 || ggr_decode_coop_init() != 0) {
@@ -276,7 +298,14 @@ void ggr_engine_destroy(ggr_engine* e) {
       if (b->p) cudaFree(b->p);
     if (sl.h_total) cudaFreeHost(sl.h_total);
     if (sl.ready) cudaEventDestroy(sl.ready);
+    if (sl.ev_in) cudaEventDestroy(sl.ev_in);
+    if (sl.ev_k) cudaEventDestroy(sl.ev_k);
+    if (sl.ev_out) cudaEventDestroy(sl.ev_out);
     if (sl.st) cudaStreamDestroy(sl.st);
+  }
+  for (int d = 0; d < 2; d++) {
+    if (e->s_in[d]) cudaStreamDestroy(e->s_in[d]);
+    if (e->s_out[d]) cudaStreamDestroy(e->s_out[d]);
   }
   for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
   cudaStreamDestroy(e->stream);
@@ -579,16 +608,28 @@ static int run_wrap_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, int64_t
   return cuda_ok(e, cudaGetLastError(), "kernel launch") ? GGR_SUCCESS : GGR_ERR_CUDA;
 }
 
-// Host-buffer entry points.  The batch is cut into chunks of `chunk_items`; chunk c runs on slot
-// c % n_slots (own stream, staging buffers and scratch): H2D of its inputs, the kernels, D2H of its
-// offsets / statuses / total, and - once the host knows where the chunk's bytes go in the packed
-// output - D2H of the payload.  Up to n_slots chunks are in flight, so the copies of one chunk
-// overlap the kernels of the others (the caller's buffers should be pinned for that to happen).
+// Host-buffer entry points.  The batch is cut into chunks of `chunk_items` (and about `chunk_bytes`);
+// chunk c uses slot c % n_slots (staging buffers, scratch and a stream for its kernels).  Three kinds of
+// work overlap, each in chunk order on its own stream(s):
+//   input stream  : H2D of the chunk's payload, offsets and message ids (waits until the kernels that
+//                   last used the slot's staging buffers are done)
+//   slot stream   : the kernels (wait for the inputs and for the previous payload to have left the
+//                   slot's output buffer), then k_publish_total writes the chunk's output size into
+//                   mapped host memory and the `ready` event fires
+//   output stream : once the host has seen `ready` and knows where the chunk's bytes go in the packed
+//                   output: D2H of offsets, statuses and payload
+// Copies issued on many streams are time-sliced by the copy engines (every chunk arrives late) and a
+// small copy queues behind other chunks' payloads, which is why the copies of a direction share one
+// stream per engine and the size does not travel by copy.  The caller's buffers should be pinned.
 static bool slot_init(ggr_engine* e, Slot& sl) {
   if (sl.st) return true;
   if (!cuda_ok(e, cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking), "cudaStreamCreate") ||
       !cuda_ok(e, cudaEventCreateWithFlags(&sl.ready, cudaEventDisableTiming), "cudaEventCreate") ||
-      !cuda_ok(e, cudaHostAlloc((void**)&sl.h_total, 64, cudaHostAllocDefault), "cudaHostAlloc"))
+      !cuda_ok(e, cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming), "cudaEventCreate") ||
+      !cuda_ok(e, cudaEventCreateWithFlags(&sl.ev_k, cudaEventDisableTiming), "cudaEventCreate") ||
+      !cuda_ok(e, cudaEventCreateWithFlags(&sl.ev_out, cudaEventDisableTiming), "cudaEventCreate") ||
+      !cuda_ok(e, cudaHostAlloc((void**)&sl.h_total, 64, cudaHostAllocMapped), "cudaHostAlloc") ||
+      !cuda_ok(e, cudaHostGetDevicePointer((void**)&sl.d_total_alias, sl.h_total, 0), "cudaHostGetDevicePointer"))
     return false;
   return true;
 }
@@ -601,7 +642,8 @@ struct ChunkJob {
 // ids != nullptr: reply side with result wrapping (the id tokens of the chunk travel with it)
 static int chunk_issue(ggr_engine* e, const ggr_schema* s, Slot& sl, bool encode, const ChunkJob& j, const int32_t* msg_id,
                        const uint8_t* in, const uint64_t* in_off, uint64_t cap, uint64_t* out_off, int32_t* status, uint32_t flags,
-                       bool copy_inputs, const uint8_t* ids = nullptr, const uint64_t* ids_off = nullptr) {
+                       bool copy_inputs, cudaStream_t s_in, const uint8_t* ids = nullptr, const uint64_t* ids_off = nullptr,
+                       cudaEvent_t* tr = nullptr) {
   const uint64_t phase = j.base & 15ull;
   if (!ensure(e, sl.d_in, (size_t)(j.bytes + phase + 128)) || !ensure(e, sl.d_off, (size_t)(j.nc + 1) * 8) ||
       !ensure(e, sl.d_msg, (size_t)j.nc * 4) || !ensure(e, sl.d_out, (size_t)cap + 64) ||
@@ -611,10 +653,12 @@ static int chunk_issue(ggr_engine* e, const ggr_schema* s, Slot& sl, bool encode
   cudaStream_t st = sl.st;
   u8* d_in = (u8*)sl.d_in.p;
   if (copy_inputs) {
-    if (!cuda_ok(e, cudaMemcpyAsync(d_in + phase, in + j.base, j.bytes, cudaMemcpyHostToDevice, st), "H2D payload") ||
-        !cuda_ok(e, cudaMemsetAsync(d_in + phase + j.bytes, 0, 64, st), "pad") ||
-        !cuda_ok(e, cudaMemcpyAsync(sl.d_off.p, in_off + j.i0, (size_t)(j.nc + 1) * 8, cudaMemcpyHostToDevice, st), "H2D offsets") ||
-        !cuda_ok(e, cudaMemcpyAsync(sl.d_msg.p, msg_id + j.i0, (size_t)j.nc * 4, cudaMemcpyHostToDevice, st), "H2D ids"))
+    // the staging buffers are free once the kernels of the chunk that used this slot before are done
+    if (!cuda_ok(e, cudaStreamWaitEvent(s_in, sl.ev_k, 0), "wait") ||
+        !cuda_ok(e, cudaMemcpyAsync(d_in + phase, in + j.base, j.bytes, cudaMemcpyHostToDevice, s_in), "H2D payload") ||
+        !cuda_ok(e, cudaMemsetAsync(d_in + phase + j.bytes, 0, 64, s_in), "pad") ||
+        !cuda_ok(e, cudaMemcpyAsync(sl.d_off.p, in_off + j.i0, (size_t)(j.nc + 1) * 8, cudaMemcpyHostToDevice, s_in), "H2D offsets") ||
+        !cuda_ok(e, cudaMemcpyAsync(sl.d_msg.p, msg_id + j.i0, (size_t)j.nc * 4, cudaMemcpyHostToDevice, s_in), "H2D ids"))
       return GGR_ERR_CUDA;
   }
   uint64_t ibase = 0;
@@ -623,8 +667,15 @@ static int chunk_issue(ggr_engine* e, const ggr_schema* s, Slot& sl, bool encode
     const uint64_t id_bytes = ids_off[j.i0 + j.nc] - ibase;
     if (!ensure(e, sl.d_ids, (size_t)id_bytes + 64) || !ensure(e, sl.d_ids_off, (size_t)(j.nc + 1) * 8)) return GGR_ERR_CUDA;
     if (copy_inputs &&
-        (!cuda_ok(e, cudaMemcpyAsync(sl.d_ids.p, ids + ibase, id_bytes, cudaMemcpyHostToDevice, st), "H2D id tokens") ||
-         !cuda_ok(e, cudaMemcpyAsync(sl.d_ids_off.p, ids_off + j.i0, (size_t)(j.nc + 1) * 8, cudaMemcpyHostToDevice, st), "H2D id offsets")))
+        (!cuda_ok(e, cudaMemcpyAsync(sl.d_ids.p, ids + ibase, id_bytes, cudaMemcpyHostToDevice, s_in), "H2D id tokens") ||
+         !cuda_ok(e, cudaMemcpyAsync(sl.d_ids_off.p, ids_off + j.i0, (size_t)(j.nc + 1) * 8, cudaMemcpyHostToDevice, s_in), "H2D id offsets")))
+      return GGR_ERR_CUDA;
+  }
+  if (copy_inputs) {
+    // kernels: after this chunk's inputs, and after the previous payload has left the output buffer
+    if (tr) cudaEventRecord(tr[0], s_in);
+    if (!cuda_ok(e, cudaEventRecord(sl.ev_in, s_in), "event") || !cuda_ok(e, cudaStreamWaitEvent(st, sl.ev_in, 0), "wait") ||
+        !cuda_ok(e, cudaStreamWaitEvent(st, sl.ev_out, 0), "wait"))
       return GGR_ERR_CUDA;
   }
   // offsets are shipped as given: the kernels address the payload as d_in - (base - phase) + offset
@@ -635,11 +686,11 @@ static int chunk_issue(ggr_engine* e, const ggr_schema* s, Slot& sl, bool encode
                : run_dev(e, s, sl.sc, encode, j.nc, (const int32_t*)sl.d_msg.p, d_in_virtual, (const uint64_t*)sl.d_off.p, j.bytes,
                          (uint8_t*)sl.d_out.p, cap, (uint64_t*)sl.d_out_off.p, (int32_t*)sl.d_status.p, flags, st);
   if (rc != GGR_SUCCESS) return rc;
-  if (!cuda_ok(e, cudaMemcpyAsync(out_off + j.i0, sl.d_out_off.p, (size_t)j.nc * 8, cudaMemcpyDeviceToHost, st), "D2H offsets") ||
-      !cuda_ok(e, cudaMemcpyAsync(sl.h_total, (const uint64_t*)sl.d_out_off.p + j.nc, 8, cudaMemcpyDeviceToHost, st), "D2H total") ||
-      !cuda_ok(e, cudaMemcpyAsync(status + j.i0, sl.d_status.p, (size_t)j.nc * 4, cudaMemcpyDeviceToHost, st), "D2H status") ||
-      !cuda_ok(e, cudaEventRecord(sl.ready, st), "event"))
-    return GGR_ERR_CUDA;
+  if (!cuda_ok(e, cudaEventRecord(sl.ev_k, st), "event")) return GGR_ERR_CUDA;
+  if (tr) cudaEventRecord(tr[1], st);
+  k_publish_total<<<1, 1, 0, st>>>((const u64*)sl.d_out_off.p + j.nc, (volatile u64*)sl.d_total_alias);
+  e->launches++;
+  if (!cuda_ok(e, cudaGetLastError(), "k_publish_total") || !cuda_ok(e, cudaEventRecord(sl.ready, st), "event")) return GGR_ERR_CUDA;
   return GGR_SUCCESS;
 }
 
@@ -662,6 +713,10 @@ static int run_host(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, 
   Slot* const slots = e->slots[dir];
   for (int i = 0; i < e->n_slots; i++)
     if (!slot_init(e, slots[i])) return GGR_ERR_CUDA;
+  if (!e->s_in[dir] && (!cuda_ok(e, cudaStreamCreateWithFlags(&e->s_in[dir], cudaStreamNonBlocking), "cudaStreamCreate") ||
+                        !cuda_ok(e, cudaStreamCreateWithFlags(&e->s_out[dir], cudaStreamNonBlocking), "cudaStreamCreate")))
+    return GGR_ERR_CUDA;
+  const cudaStream_t s_in = e->s_in[dir], s_out = e->s_out[dir];
   // chunk boundaries: at most chunk_items items and about chunk_bytes of input each (large items
   // must not make a chunk - and its staging buffers - huge)
   const int64_t CH = e->chunk_items;
@@ -705,41 +760,92 @@ static int run_host(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, 
   uint64_t produced = 0;
   int rc_final = GGR_SUCCESS;
   int64_t issued = 0, retired = 0;
+  // GGR_TRACE: four timing events per chunk (inputs on the device, kernels done, sizes on the host,
+  // payload on the host) and the host's own clock around issue and wait
+  struct TraceRec { double issue0, issue1, wait0, wait1; };
+  std::vector<cudaEvent_t> tev;
+  std::vector<TraceRec> trec;
+  std::vector<uint64_t> chunk_base((size_t)nchunks, 0);
+  cudaEvent_t tbase = nullptr;
+  const auto thost0 = std::chrono::steady_clock::now();
+  auto hms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - thost0).count(); };
+  if (e->trace) {
+    tev.resize((size_t)nchunks * 4);
+    trec.resize((size_t)nchunks);
+    for (auto& ev : tev) cudaEventCreate(&ev);
+    cudaEventCreate(&tbase);
+    cudaEventRecord(tbase, s_in);
+  }
   while (retired < nchunks) {
     while (issued < nchunks && issued - retired < e->n_slots && rc_final == GGR_SUCCESS) {
       ChunkJob j = job(issued);
-      int rc = chunk_issue(e, s, slots[issued % e->n_slots], encode, j, msg_id, in, in_off, chunk_cap(j), out_off, status, flags, true, ids, ids_off);
+      if (e->trace) trec[issued].issue0 = hms();
+      int rc = chunk_issue(e, s, slots[issued % e->n_slots], encode, j, msg_id, in, in_off, chunk_cap(j), out_off, status, flags, true, s_in, ids, ids_off,
+                           e->trace ? &tev[(size_t)issued * 4] : nullptr);
+      if (e->trace) trec[issued].issue1 = hms();
       if (rc != GGR_SUCCESS) rc_final = rc;
       else issued++;
     }
     if (retired == issued) break;  // nothing in flight (an issue failed)
     ChunkJob j = job(retired);
     Slot& sl = slots[retired % e->n_slots];
+    if (e->trace) trec[retired].wait0 = hms();
     if (!cuda_ok(e, cudaEventSynchronize(sl.ready), "sync")) return GGR_ERR_CUDA;
+    if (e->trace) trec[retired].wait1 = hms();
     uint64_t total = *sl.h_total;
     if (total > sl.out_cap && rc_final == GGR_SUCCESS) {
       // rare: the chunk's output outgrew its share; its inputs are still on the device
-      int rc = chunk_issue(e, s, sl, encode, j, msg_id, in, in_off, total, out_off, status, flags, false, ids, ids_off);
+      int rc = chunk_issue(e, s, sl, encode, j, msg_id, in, in_off, total, out_off, status, flags, false, s_in, ids, ids_off);
       if (rc != GGR_SUCCESS) rc_final = rc;
       else if (!cuda_ok(e, cudaEventSynchronize(sl.ready), "sync")) return GGR_ERR_CUDA;
       total = *sl.h_total;
     }
+    // the chunk's kernels are complete (the host has seen `ready`): offsets, statuses and payload leave
+    // on the output stream, in chunk order
+    if (!cuda_ok(e, cudaMemcpyAsync(out_off + j.i0, sl.d_out_off.p, (size_t)j.nc * 8, cudaMemcpyDeviceToHost, s_out), "D2H offsets") ||
+        !cuda_ok(e, cudaMemcpyAsync(status + j.i0, sl.d_status.p, (size_t)j.nc * 4, cudaMemcpyDeviceToHost, s_out), "D2H status"))
+      return GGR_ERR_CUDA;
+    if (e->trace) cudaEventRecord(tev[(size_t)retired * 4 + 2], s_out);
+    chunk_base[retired] = produced;
     if (rc_final == GGR_SUCCESS) {
       if (produced + total > out_cap) {
         rc_final = GGR_ERR_NO_SPACE;
       } else {
-        if (total && !cuda_ok(e, cudaMemcpyAsync(out + produced, sl.d_out.p, total, cudaMemcpyDeviceToHost, sl.st), "D2H payload"))
+        if (total && !cuda_ok(e, cudaMemcpyAsync(out + produced, sl.d_out.p, total, cudaMemcpyDeviceToHost, s_out), "D2H payload"))
           return GGR_ERR_CUDA;
-        if (produced)
-          for (int64_t k = 0; k < j.nc; k++) out_off[j.i0 + k] += produced;
         produced += total;
       }
     }
+    if (!cuda_ok(e, cudaEventRecord(sl.ev_out, s_out), "event")) return GGR_ERR_CUDA;
+    if (e->trace) cudaEventRecord(tev[(size_t)retired * 4 + 3], s_out);
     retired++;
   }
   for (int i = 0; i < e->n_slots; i++)
     if (!cuda_ok(e, cudaStreamSynchronize(slots[i].st), "sync")) return GGR_ERR_CUDA;
+  if (!cuda_ok(e, cudaStreamSynchronize(s_in), "sync") || !cuda_ok(e, cudaStreamSynchronize(s_out), "sync")) return GGR_ERR_CUDA;
+  // the kernels number a chunk's output from 0: shift by what the chunks before it produced
+  for (int64_t c = 1; c < retired; c++) {
+    const uint64_t base = chunk_base[c];
+    if (!base) continue;
+    const ChunkJob j = job(c);
+    for (int64_t k = 0; k < j.nc; k++) out_off[j.i0 + k] += base;
+  }
   out_off[n] = produced;
+  if (e->trace) {
+    fprintf(stderr, "[ggr trace] %s batch: %lld items in %lld chunks, %d slots, %.2f ms on the host clock\n", encode ? "request" : "reply",
+            (long long)n, (long long)nchunks, e->n_slots, hms());
+    fprintf(stderr, "[ggr trace] chunk slot | host: issue..done wait..ready | device: inputs kernels sizes payload (ms)\n");
+    for (int64_t c = 0; c < nchunks; c++) {
+      float g[4] = {-1, -1, -1, -1};
+      for (int k = 0; k < 4; k++)
+        if (cudaEventElapsedTime(&g[k], tbase, tev[(size_t)c * 4 + k]) != cudaSuccess) g[k] = -1;
+      fprintf(stderr, "[ggr trace] %s %3lld %d | %7.3f %7.3f %7.3f %7.3f | %7.3f %7.3f %7.3f %7.3f\n", encode ? "req" : "rep", (long long)c, (int)(c % e->n_slots),
+              trec[c].issue0, trec[c].issue1, trec[c].wait0, trec[c].wait1, g[0], g[1], g[2], g[3]);
+    }
+    cudaGetLastError();
+    for (auto& ev : tev) cudaEventDestroy(ev);
+    cudaEventDestroy(tbase);
+  }
   return rc_final;
 }
 
