@@ -138,14 +138,17 @@ GGR_DEV void ce_tokenize(SH& S, const CeLut& L, const u8* in, u32 start, u32 end
   const u32 nchunks = (end + 15u) >> 4;
   u32 c_carry = 0, in_carry = 0, n_carry = 0, u_carry = 0;  // warp-uniform carries between rounds
   u32 tbase = 0, qbase = 0, dbase = 0, ebase = 0;
+  U4 vn;  // the next round's chunk is requested one round ahead
+  vn.x = vn.y = vn.z = vn.w = 0;
+  if (lane < nchunks) vn = ggr_ld16(in + (lane << 4));
   for (u32 cb = 0; cb < nchunks; cb += 32) {
     const u32 ci = cb + lane;
     const u32 off = ci << 4;
     u32 Q = 0, B = 0, X = 0, W = 0xFFFFu, D = 0, HI = 0;
-    U4 v;
-    v.x = v.y = v.z = v.w = 0;
+    const U4 v = vn;
+    vn.x = vn.y = vn.z = vn.w = 0;
+    if (ci + 32u < nchunks) vn = ggr_ld16(in + off + 512u);
     if (ci < nchunks) {
-      v = ggr_ld16(in + off);
       u32 lo = 0, hi = 0;
 #pragma unroll
       for (int j = 0; j < 4; j++) {
@@ -262,7 +265,7 @@ GGR_DEV void ce_tokenize(SH& S, const CeLut& L, const u8* in, u32 start, u32 end
       } else if (NS & bit) {
         kind = TK_SCALAR;
       } else {
-        kind = L.kind[ce_byte16(v, j)] & 0xFu;
+        kind = 0;  // structural character: ce_match looks it up (one lane per token there)
       }
       if (ti < SH::MAX_TOK) S.tok[ti] = (off + j) | (kind << 16) | (aux << 20);
       ti++;
@@ -278,14 +281,19 @@ GGR_DEV void ce_tokenize(SH& S, const CeLut& L, const u8* in, u32 start, u32 end
 
 // T2.  All lanes.  Fills the aux field of every bracket token with the index of its partner.
 template <class SH>
-GGR_DEV void ce_match(SH& S) {
+GGR_DEV void ce_match(SH& S, const CeLut& L, const u8* in) {
   const u32 lane = wp_lane();
   const u32 lt = (1u << lane) - 1u, le = lt | (1u << lane);
   const u32 n = S.n_tok;
   i32 depth = 0;
   for (u32 base = 0; base < n; base += 32) {
     const u32 i = base + lane;
-    const u32 t = i < n ? S.tok[i] : 0u;
+    u32 t = i < n ? S.tok[i] : (TK_SCALAR << 16);
+    if (TK_KIND(t) == 0) {  // structural character left open by the tokenizer
+      t |= (u32)(L.kind[in[TK_POS(t)]] & 0xFu) << 16;
+      S.tok[i] = t;
+    }
+    WP_SYNC();  // closing brackets read their partner's kind below
     const u32 k = TK_KIND(t);
     const bool op = k == TK_LBRACE || k == TK_LBRACK, cl = k == TK_RBRACE || k == TK_RBRACK;
     const u32 OM = WP_BALLOT(op), CM = WP_BALLOT(cl);
@@ -964,7 +972,7 @@ GGR_DEV bool ce_parse_item(SH& S, const CeLut& lut, const Tables& T, u32 root_ms
   WP_SYNC();
   ce_tokenize(S, lut, in, start, end);
   if (S.bail) return false;
-  ce_match(S);
+  ce_match(S, lut, in);
   if (S.bail) return false;
   const u32 n_tok = S.n_tok;
   // exactly one top-level value, an object
