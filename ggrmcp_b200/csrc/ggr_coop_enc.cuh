@@ -71,6 +71,22 @@ struct CoopEncT {
 typedef CoopEncT<1024, 512, 224> CoopEnc;        // tier 1: ~12 KB per warp
 typedef CoopEncT<2048, 1024, 512> CoopEncBig;   // tier 2: ~26 KB per warp (two blocks of four warps per SM)
 
+// Working set of the token-index kernel (k_encode_coop_tok): what ce_tokenize / ce_match touch.  Tier 1
+// runs T1 + T2 in a kernel of their own (small code, half the registers and shared memory of the
+// walker, so twice the warps per SM); the index travels through the item's IR region, which the
+// walker only starts to fill after it has copied the index into its own shared memory.
+template <int MT, int MQ>
+struct CoopTokT {
+  static const u32 MAX_TOK = MT, MAX_Q = MQ;
+  u32 tok[MT];
+  u16 qpos[MQ], qesc[MQ], qslow[MQ];
+  u16 last_open[32];
+  u32 n_tok, n_q, bail, deep;
+};
+typedef CoopTokT<1024, 512> CoopTok;  // same limits as CoopEnc
+// header {n_tok, n_q, bail, deep}, tok[n_tok], then qpos / qesc / qslow as (n_q + 1) / 2 words each
+GGR_DEV u32 ce_tok_bytes(u32 n_tok, u32 n_q) { return 16u + 4u * n_tok + 12u * ((n_q + 1u) >> 1); }
+
 struct CeLut {
   u32 cls[256];  // CE_L* class bits
   u8 kind[256];  // TK_* of the structural characters; bit 7: valid character after a backslash (simple escapes)
@@ -945,9 +961,49 @@ GGR_DEV void ce_place_children(SH& S, u32 ni) {
   }
 }
 
+// T1 + T2 of one item, all 32 lanes: the token index into the item's IR region (ir_cap nodes of 16
+// bytes).  An item whose index does not fit there, or that the tokenizer gives up on, is marked
+// `bail` for the walker.
+template <class TS>
+GGR_DEV void ce_tok_item(TS& S, const CeLut& lut, const u8* in, u32 start, u32 end, u8* ir, u32 ir_cap) {
+  const u32 lane = wp_lane();
+  if (end > CE_MAX_INPUT || ir_cap == 0 || end == start) return;  // decided by the walker before it looks at the index
+  u32* g = reinterpret_cast<u32*>(ir);
+  WP_SYNC();  // persistent warps: nobody still reads the previous item's state
+  if (lane == 0) {
+    S.bail = 0;
+    S.deep = 0;
+  }
+  WP_SYNC();
+  ce_tokenize(S, lut, in, start, end);
+  if (!S.bail) ce_match(S, lut, in);
+  const u32 n_tok = S.n_tok, n_q = S.n_q;
+  const bool bail = S.bail != 0 || ce_tok_bytes(n_tok, n_q) > ir_cap * 16u;
+  if (lane == 0) {
+    g[0] = n_tok;
+    g[1] = n_q;
+    g[2] = bail ? 1u : 0u;
+    g[3] = S.deep;
+  }
+  if (bail) return;
+  u32* gt = g + 4;
+  for (u32 i = lane; i < n_tok; i += 32) gt[i] = S.tok[i];
+  const u32 nw = (n_q + 1u) >> 1;
+  u32* gq = gt + n_tok;
+  const u32* qp = reinterpret_cast<const u32*>(S.qpos);
+  const u32* qe = reinterpret_cast<const u32*>(S.qesc);
+  const u32* qs = reinterpret_cast<const u32*>(S.qslow);
+  for (u32 i = lane; i < nw; i += 32) {
+    gq[i] = qp[i];
+    gq[nw + i] = qe[i];
+    gq[2u * nw + i] = qs[i];
+  }
+}
+
 // One item, all 32 lanes.  Returns true when the item was handled (IR written, *res filled);
 // false leaves it to the per-thread parser.
-template <class SH, bool ENV>
+// PRE: the token index was left in the IR region by ce_tok_item.
+template <class SH, bool ENV, bool PRE = false>
 GGR_DEV bool ce_parse_item(SH& S, const CeLut& lut, const Tables& T, u32 root_msg, const u8* in, u32 start, u32 end, u8* ir,
                            u32* ioff, u32 ir_cap, EncResult* res) {
   const bool envelope = ENV;
@@ -970,10 +1026,34 @@ GGR_DEV bool ce_parse_item(SH& S, const CeLut& lut, const Tables& T, u32 root_ms
     S.cap = ir_cap < SH::MAX_NODE ? ir_cap : SH::MAX_NODE;
   }
   WP_SYNC();
-  ce_tokenize(S, lut, in, start, end);
-  if (S.bail) return false;
-  ce_match(S, lut, in);
-  if (S.bail) return false;
+  if (PRE) {
+    const u32* g = reinterpret_cast<const u32*>(ir);
+    const u32 nt = g[0], nq = g[1];
+    if (g[2] != 0 || nt > SH::MAX_TOK || nq > SH::MAX_Q) return false;
+    const u32* gt = g + 4;
+    for (u32 i = lane; i < nt; i += 32) S.tok[i] = gt[i];
+    const u32 nw = (nq + 1u) >> 1;
+    const u32* gq = gt + nt;
+    u32* qp = reinterpret_cast<u32*>(S.qpos);
+    u32* qe = reinterpret_cast<u32*>(S.qesc);
+    u32* qs = reinterpret_cast<u32*>(S.qslow);
+    for (u32 i = lane; i < nw; i += 32) {
+      qp[i] = gq[i];
+      qe[i] = gq[nw + i];
+      qs[i] = gq[2u * nw + i];
+    }
+    if (lane == 0) {
+      S.n_tok = nt;
+      S.n_q = nq;
+      S.deep = g[3];
+    }
+    WP_SYNC();  // the index is in shared memory: from here on the region takes IR nodes
+  } else {
+    ce_tokenize(S, lut, in, start, end);
+    if (S.bail) return false;
+    ce_match(S, lut, in);
+    if (S.bail) return false;
+  }
   const u32 n_tok = S.n_tok;
   // exactly one top-level value, an object
   if (TK_KIND(S.tok[0]) != TK_LBRACE || TK_AUX(S.tok[0]) != n_tok - 1u) return false;

@@ -450,7 +450,7 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
         prof_mark(e, st, &m1);
         e->spans.push_back({9, c1, m1});
       }
-      e->launches += 4;
+      e->launches += 5;  // + the token-index kernel of tier 1
     } else {
       ggr_launch_encode_parse(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
                               (u32*)sc.aux.p, status, (u64*)sc.sums.p, nullptr, nullptr);
@@ -582,7 +582,7 @@ static int run_request_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, int6
                          (const u64*)sc.sums.p, out, out_cap, out_off, (const u32*)sc.nn.p);
   ggr_launch_encode_coop_emit(st, n, in, in_off, (const u8*)sc.ir.p, (const u32*)sc.ioff.p, (const u32*)sc.nn.p, (const u32*)sc.size.p,
                               status, out, out_off, e->sm_count, big, counters);
-  e->launches += 8;
+  e->launches += 9;
   return cuda_ok(e, cudaGetLastError(), "kernel launch") ? GGR_SUCCESS : GGR_ERR_CUDA;
 }
 

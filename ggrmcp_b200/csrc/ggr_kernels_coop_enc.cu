@@ -9,9 +9,35 @@
 
 #define CE_WARPS 4
 
+// Tier 1, first half: token index (T1 + T2) of every listed item into its IR region.  Seven blocks
+// per SM (28 warps: 72 registers, 7.3 KB of shared memory per warp) against four for the walker.
+#define CE_TOK_BLOCKS 7
+__global__ void __launch_bounds__(CE_WARPS * 32, CE_TOK_BLOCKS)
+k_encode_coop_tok(long long n, const u8* __restrict__ in, const u64* __restrict__ in_off, u8* __restrict__ ir,
+                  const u32* __restrict__ list, const u32* __restrict__ list_n) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  CeLut& lut = *reinterpret_cast<CeLut*>(smem);
+  CoopTok* S = reinterpret_cast<CoopTok*>(smem + ((sizeof(CeLut) + 15) & ~(size_t)15));
+  const u32 warp = threadIdx.x >> 5;
+  ce_lut_init(lut, threadIdx.x, CE_WARPS * 32);
+  __syncthreads();
+  const long long total = list ? (long long)*list_n : n;
+  const u64 a0 = in_off[0];
+  for (long long slot = (long long)blockIdx.x * CE_WARPS + warp; slot < total; slot += (long long)gridDim.x * CE_WARPS) {
+    const long long item = list ? (long long)list[slot] : slot;
+    const u64 a = in_off[item], b = in_off[item + 1];
+    if (b < a || b - a > (u64)CE_MAX_INPUT - 16u) continue;
+    const u64 node_off = ((a - a0) >> 1) + 8ull * (u64)item;
+    const u32 cap = (u32)((((b - a0) >> 1) + 8ull * (u64)(item + 1)) - node_off);
+    const u32 s0 = (u32)(a & 15ull);
+    ce_tok_item(S[warp], lut, in + (a & ~15ull), s0, s0 + (u32)(b - a), ir + node_off * 16, cap);
+  }
+}
+
 // Every item the lock-step parser handles gets size / first / status written here; the others are
 // appended to `pending` (order irrelevant).  list != nullptr: items come from that list.
-template <class SH, bool ENV>
+// PRE: the token index is already in the item's IR region (k_encode_coop_tok ran before).
+template <class SH, bool ENV, bool PRE>
 __global__ void __launch_bounds__(CE_WARPS * 32)
 k_encode_coop_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const i32* __restrict__ msg_id,
                     const u8* __restrict__ in, const u64* __restrict__ in_off, u8* __restrict__ ir, u32* __restrict__ size,
@@ -44,7 +70,7 @@ k_encode_coop_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const 
       const u32 cap = (u32)((((b - a0) >> 1) + 8ull * (u64)(item + 1)) - node_off);
       const u8* base = in + (a & ~15ull);
       const u32 s0 = (u32)(a & 15ull);
-      ok = ce_parse_item<SH, ENV>(S[warp], lut, T, (u32)m, base, s0, s0 + (u32)(b - a), ir + node_off * 16, ioff + node_off, cap, &res);
+      ok = ce_parse_item<SH, ENV, PRE>(S[warp], lut, T, (u32)m, base, s0, s0 + (u32)(b - a), ir + node_off * 16, ioff + node_off, cap, &res);
     }
     if (lane == 0) {
       if (ok) {
@@ -97,24 +123,26 @@ static size_t ce_smem_bytes() {
   return ((sizeof(CeLut) + 15) & ~(size_t)15) + sizeof(SH) * CE_WARPS;
 }
 
-template <class SH, bool ENV>
+template <class SH, bool ENV, bool PRE>
 static cudaError_t ce_opt_in() {
-  return cudaFuncSetAttribute(k_encode_coop_parse<SH, ENV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ce_smem_bytes<SH>());
+  return cudaFuncSetAttribute(k_encode_coop_parse<SH, ENV, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ce_smem_bytes<SH>());
 }
 int ggr_encode_coop_init() {
-  cudaError_t a = ce_opt_in<CoopEnc, false>(), b = ce_opt_in<CoopEncBig, false>();
-  cudaError_t a2 = ce_opt_in<CoopEnc, true>(), b2 = ce_opt_in<CoopEncBig, true>();
+  cudaError_t a = ce_opt_in<CoopEnc, false, true>(), b = ce_opt_in<CoopEncBig, false, false>();
+  cudaError_t a2 = ce_opt_in<CoopEnc, true, true>(), b2 = ce_opt_in<CoopEncBig, true, false>();
+  if (cudaFuncSetAttribute(k_encode_coop_tok, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ce_smem_bytes<CoopTok>()) != cudaSuccess)
+    return -1;
   cudaError_t c = cudaFuncSetAttribute(k_encode_coop_emit, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(sizeof(CoopEmit) * CE_WARPS));
   return (a == cudaSuccess && b == cudaSuccess && a2 == cudaSuccess && b2 == cudaSuccess && c == cudaSuccess) ? 0 : -1;
 }
 
-template <class SH, bool ENV>
+template <class SH, bool ENV, bool PRE>
 static void ce_launch(cudaStream_t st, unsigned nb, long long n, const uint8_t* blob, uint32_t n_msgs, const int32_t* msg_id,
                       const uint8_t* in, const uint64_t* in_off, uint8_t* ir, uint32_t* size, uint32_t* first, int32_t* status,
                       uint32_t* ioff, uint32_t* nnodes, const uint32_t* list, const uint32_t* list_n, uint32_t* pending,
                       uint32_t* n_pending, int32_t* method, uint32_t* id_span, int32_t final_status) {
-  k_encode_coop_parse<SH, ENV><<<nb, CE_WARPS * 32, ce_smem_bytes<SH>(), st>>>(
+  k_encode_coop_parse<SH, ENV, PRE><<<nb, CE_WARPS * 32, ce_smem_bytes<SH>(), st>>>(
       blob, n, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending, method,
       id_span, final_status);
 }
@@ -129,13 +157,16 @@ void ggr_launch_encode_coop_parse(cudaStream_t st, int tier, long long n, const 
     // 4 resident blocks per SM (shared memory); never more blocks than items / CE_WARPS
     long long want = (n + CE_WARPS - 1) / CE_WARPS, cap = (long long)sm_count * 4;
     unsigned nb = (unsigned)(want < cap ? want : cap);
-    if (env) ce_launch<CoopEnc, true>(st, nb, n, blob, n_msgs, msg_id, in, in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending, method, id_span, final_status);
-    else ce_launch<CoopEnc, false>(st, nb, n, blob, n_msgs, msg_id, in, in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending, method, id_span, final_status);
+    const long long cap_t = (long long)sm_count * CE_TOK_BLOCKS;
+    k_encode_coop_tok<<<(unsigned)(want < cap_t ? want : cap_t), CE_WARPS * 32, ce_smem_bytes<CoopTok>(), st>>>(
+        n, in, (const u64*)in_off, ir, list, list_n);
+    if (env) ce_launch<CoopEnc, true, true>(st, nb, n, blob, n_msgs, msg_id, in, in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending, method, id_span, final_status);
+    else ce_launch<CoopEnc, false, true>(st, nb, n, blob, n_msgs, msg_id, in, in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending, method, id_span, final_status);
   } else {
     // the list length lives on the device: two blocks per SM (shared memory), warps stride over the list
     unsigned nb = (unsigned)sm_count * 2u;
-    if (env) ce_launch<CoopEncBig, true>(st, nb, n, blob, n_msgs, msg_id, in, in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending, method, id_span, final_status);
-    else ce_launch<CoopEncBig, false>(st, nb, n, blob, n_msgs, msg_id, in, in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending, method, id_span, final_status);
+    if (env) ce_launch<CoopEncBig, true, false>(st, nb, n, blob, n_msgs, msg_id, in, in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending, method, id_span, final_status);
+    else ce_launch<CoopEncBig, false, false>(st, nb, n, blob, n_msgs, msg_id, in, in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending, method, id_span, final_status);
   }
 }
 

@@ -116,6 +116,19 @@ static void coop_enc_body(void* p, u32 lane) {
   a->ok[lane] = a->envelope ? ce_parse_item<SH, true>(*a->S, *a->lut, a->T, a->msg, a->in, a->start, a->end, a->ir, a->ioff, a->ir_cap, &a->res[lane])
                             : ce_parse_item<SH, false>(*a->S, *a->lut, a->T, a->msg, a->in, a->start, a->end, a->ir, a->ioff, a->ir_cap, &a->res[lane]);
 }
+// tier 1 as the kernels run it: token index into the IR region (k_encode_coop_tok), then the walker on it
+static CoopTok g_tok_state;
+template <class SH>
+static void coop_tok_body(void* p, u32 lane) {
+  CoopEncArgs<SH>* a = (CoopEncArgs<SH>*)p;
+  ce_tok_item(g_tok_state, *a->lut, a->in, a->start, a->end, a->ir, a->ir_cap);
+}
+template <class SH>
+static void coop_enc_pre_body(void* p, u32 lane) {
+  CoopEncArgs<SH>* a = (CoopEncArgs<SH>*)p;
+  a->ok[lane] = a->envelope ? ce_parse_item<SH, true, true>(*a->S, *a->lut, a->T, a->msg, a->in, a->start, a->end, a->ir, a->ioff, a->ir_cap, &a->res[lane])
+                            : ce_parse_item<SH, false, true>(*a->S, *a->lut, a->T, a->msg, a->in, a->start, a->end, a->ir, a->ioff, a->ir_cap, &a->res[lane]);
+}
 template <class SH>
 static void coop_emit_body(void* p, u32 lane) {
   CoopEncArgs<SH>* a = (CoopEncArgs<SH>*)p;
@@ -152,7 +165,14 @@ static int hs_encode_coop_t(void* h, int msg, const uint8_t* json, uint32_t n, u
   a.ioff = ioff.data();
   a.ir_cap = ir_cap;
   a.envelope = env_out != nullptr;
-  int werr = hw_run_warp(coop_enc_body<SH>, &a);
+  int werr;
+  if (SH::MAX_TOK == CoopEnc::MAX_TOK) {
+    memset(&g_tok_state, 0xAB, sizeof g_tok_state);
+    werr = hw_run_warp(coop_tok_body<SH>, &a);
+    if (!werr) werr = hw_run_warp(coop_enc_pre_body<SH>, &a);
+  } else {
+    werr = hw_run_warp(coop_enc_body<SH>, &a);
+  }
   *out_n = 0;
   if (werr) {
     free(ir);
