@@ -20,7 +20,8 @@ k_decode_coop_size(const u8* __restrict__ blob, long long n, u32 n_msgs, const i
   cx.flags = flags;
   // the items of `list` (the router's choice: not too small, not too large); mode[] is PENDING for all others
   const long long total = (long long)*list_n;
-  for (long long slot = (long long)blockIdx.x * COOP_WARPS + warp; slot < total; slot += (long long)gridDim.x * COOP_WARPS) {
+  u32* ticket = const_cast<u32*>(list_n) + 1;  // zeroed with the list length; +2 is the write kernel's
+  for (long long slot = wp_next_ticket(ticket); slot < total; slot = wp_next_ticket(ticket)) {
     const long long item = (long long)list[slot];
     const u64 a = in_off[item], b = in_off[item + 1];
     const i32 m = msg_id[item];
@@ -58,7 +59,8 @@ k_decode_coop_write(const u8* __restrict__ blob, long long n, const u8* __restri
   cx.T = ggr_tables(blob);
   cx.flags = flags;
   const long long total = (long long)*list_n;
-  for (long long slot = (long long)blockIdx.x * COOP_WRITE_WARPS + warp; slot < total; slot += (long long)gridDim.x * COOP_WRITE_WARPS) {
+  u32* ticket = const_cast<u32*>(list_n) + 2;
+  for (long long slot = wp_next_ticket(ticket); slot < total; slot = wp_next_ticket(ticket)) {
     const long long item = (long long)list[slot];
     if (mode[item] != GGR_MODE_COOP || status[item] != GST_OK) continue;
     const u64 a = in_off[item];

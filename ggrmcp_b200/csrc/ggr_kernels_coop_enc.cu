@@ -23,7 +23,12 @@ k_encode_coop_tok(long long n, const u8* __restrict__ in, const u64* __restrict_
   __syncthreads();
   const long long total = list ? (long long)*list_n : n;
   const u64 a0 = in_off[0];
-  for (long long slot = (long long)blockIdx.x * CE_WARPS + warp; slot < total; slot += (long long)gridDim.x * CE_WARPS) {
+  // the words after a list's length are zeroed with it and serve as ticket counters: +1 this kernel,
+  // +2 the walker, +3 the emitter
+  u32* ticket = list ? const_cast<u32*>(list_n) + 1 : nullptr;
+  const long long stride = ticket ? 0 : (long long)gridDim.x * CE_WARPS;
+  for (long long slot = ticket ? wp_next_ticket(ticket) : (long long)blockIdx.x * CE_WARPS + warp; slot < total;
+       slot = ticket ? wp_next_ticket(ticket) : slot + stride) {
     const long long item = list ? (long long)list[slot] : slot;
     const u64 a = in_off[item], b = in_off[item + 1];
     if (b < a || b - a > (u64)CE_MAX_INPUT - 16u) continue;
@@ -54,7 +59,10 @@ k_encode_coop_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const 
   const long long total = list ? (long long)*list_n : n;
   const Tables T = ggr_tables(blob);
   const u64 a0 = in_off[0];  // IR regions are laid out relative to the first offset of the batch
-  for (long long slot = (long long)blockIdx.x * CE_WARPS + warp; slot < total; slot += (long long)gridDim.x * CE_WARPS) {
+  u32* ticket = list ? const_cast<u32*>(list_n) + 2 : nullptr;
+  const long long stride = ticket ? 0 : (long long)gridDim.x * CE_WARPS;
+  for (long long slot = ticket ? wp_next_ticket(ticket) : (long long)blockIdx.x * CE_WARPS + warp; slot < total;
+       slot = ticket ? wp_next_ticket(ticket) : slot + stride) {
     const long long item = list ? (long long)list[slot] : slot;
     const u64 a = in_off[item], b = in_off[item + 1];
     // envelope mode (method != nullptr): the item is a whole request body, its message type comes from the tool name
@@ -106,7 +114,8 @@ k_encode_coop_emit(long long n, const u8* __restrict__ in, const u64* __restrict
   const u32 warp = threadIdx.x >> 5;
   const u64 a0 = in_off[0];
   const long long total = (long long)*list_n;  // the router's lock-step items
-  for (long long slot = (long long)blockIdx.x * CE_WARPS + warp; slot < total; slot += (long long)gridDim.x * CE_WARPS) {
+  u32* ticket = const_cast<u32*>(list_n) + 3;
+  for (long long slot = wp_next_ticket(ticket); slot < total; slot = wp_next_ticket(ticket)) {
     const long long item = (long long)list[slot];
     const u32 nn = nnodes[item];
     const u32 sz = size[item];

@@ -20,8 +20,18 @@ GGR_DEV u32 wp_match_any_(u32 v, int) { return __match_any_sync(0xFFFFFFFFu, v);
 GGR_DEV u32 wp_atomic_add(u32* p, u32 v) { return atomicAdd(p, v); }
 GGR_DEV u32 wp_atomic_or(u32* p, u32 v) { return atomicOr(p, v); }
 GGR_DEV u32 wp_atomic_max(u32* p, u32 v) { return atomicMax(p, v); }
+// Persistent warps draw their items by ticket (item sizes differ: with a fixed stride the kernel
+// waits for the unluckiest warp).  Lane 0 draws, the warp follows.  `ticket` is a zeroed word that
+// belongs to this launch alone.
+GGR_DEV long long wp_next_ticket(u32* ticket) {
+  u32 t = 0;
+  if ((threadIdx.x & 31u) == 0) t = atomicAdd(ticket, 1u);
+  return (long long)__shfl_sync(0xFFFFFFFFu, t, 0);
+}
 
 #else  // ---------------------------------------------------------------- host fibers
+
+inline long long wp_next_ticket(u32*) { return 0; }  // kernels only (the host pass of nvcc still parses them)
 
 #include <ucontext.h>
 
