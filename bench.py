@@ -452,7 +452,7 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     alg = {"encode_parse": J_in, "encode_emit": W_out, "decode_size": W_in, "decode_write": J_out,
            "encode_scan": 0, "decode_scan": 0, "decode_coop_size": W_in, "decode_coop_write": W_in + J_out,
-           "encode_coop_parse": J_in, "encode_block_sums": 4 * n, "encode_coop_emit": W_out}
+           "encode_coop_parse": J_in, "encode_block_sums": 4 * n, "encode_coop_emit": W_out, "encode_coop_tok": J_in}
     kern = {}
     for k, (tot_ms, cnt) in prof.items():
         if cnt:
@@ -465,11 +465,13 @@ def main():
     if dom:
         a = kern[dom]["gbs"]
         # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this
-        # very configuration (profiles/ncu_r1_final_lockstep_kernels_151552items.csv: dram__bytes_read.sum +
-        # dram__bytes_write.sum of k_encode_coop_parse, small-table tier); other configurations: not captured
+        # very configuration (profiles/ncu_r1_split_parse_kernels_151552items.csv: dram__bytes_read.sum +
+        # dram__bytes_write.sum of k_encode_coop_parse - the walker, which reads the text and the token index
+        # k_encode_coop_tok left for it - plus the large-table tier that shares its timing slot); other
+        # configurations: not captured
         traffic = None
         if dom == "encode_coop_parse" and args.workload == "nested" and n == 148 * 1024:
-            traffic = int(559.120896e6 + 330.975744e6)
+            traffic = int(980.283648e6 + 334.991104e6 + 36.943360e6 + 1.941504e6)
         roofline = {"bound": "hbm", "kernel": dom, "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
                     "traffic": traffic, "peak_source": peak_src,
                     "step_read_gbs": (J_in + W_in) / (step_ms / 1000.0) / 1e9,

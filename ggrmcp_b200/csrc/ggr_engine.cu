@@ -414,7 +414,7 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
   if (!ensure(e, sc.size, (size_t)n * 4) || !ensure(e, sc.aux, (size_t)n * 4) || !ensure(e, sc.sums, (size_t)nb * 8)) return GGR_ERR_CUDA;
   if (encode && !ensure(e, sc.ir, (size_t)in_bytes * 8 + (size_t)n * 128 + 256)) return GGR_ERR_CUDA;
   u32 n_msgs = (u32)s->cs.msg_names.size();
-  const bool prof = e->profiling && e->ev_used + 8 <= 65536;
+  const bool prof = e->profiling && e->ev_used + 12 <= 65536;
   size_t m0 = 0, m1 = 0, m2 = 0, m3 = 0, mx = 0;
   bool have_mx = false;
   if (prof) prof_mark(e, st, &m0);
@@ -435,6 +435,9 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
       if (prof) prof_mark(e, st, &m0);
       // router: small (and oversized) items straight to the per-thread parser
       k_route<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, in_off, e->min_json, 65000u - 16u, big, counters, pend2, counters + 8, nullptr);
+      ggr_launch_encode_coop_tok(st, n, in, in_off, (u8*)sc.ir.p, big, counters, e->sm_count);
+      size_t t1 = 0;
+      if (prof) prof_mark(e, st, &t1);
       ggr_launch_encode_coop_parse(st, 0, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
                                    (u32*)sc.aux.p, status, (u32*)sc.ioff.p, (u32*)sc.nn.p, big, counters, pend1, counters + 4, e->sm_count, nullptr, nullptr, -1);
       ggr_launch_encode_coop_parse(st, 1, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
@@ -445,7 +448,8 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
       if (prof) prof_mark(e, st, &c1);
       ggr_launch_block_sums(st, (unsigned)nb, n, (const u32*)sc.size.p, (u64*)sc.sums.p);
       if (prof) {
-        e->spans.push_back({8, m0, c0});
+        e->spans.push_back({11, m0, t1});  // router + token index
+        e->spans.push_back({8, t1, c0});    // walker, tier 2
         e->spans.push_back({0, c0, c1});
         prof_mark(e, st, &m1);
         e->spans.push_back({9, c1, m1});
@@ -570,6 +574,7 @@ static int run_request_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, int6
   const u32 n_msgs = (u32)s->cs.msg_names.size();
   // bodies above the parser's input limit cannot be taken
   k_route<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, in_off, 0u, 65000u - 16u, big, counters, rest, counters + 8, nullptr);
+  ggr_launch_encode_coop_tok(st, n, in, in_off, (u8*)sc.ir.p, big, counters, e->sm_count);
   ggr_launch_encode_coop_parse(st, 0, n, s->d_blob, n_msgs, nullptr, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p, (u32*)sc.aux.p, status,
                                (u32*)sc.ioff.p, (u32*)sc.nn.p, big, counters, pend1, counters + 4, e->sm_count, method, id_span, -1);
   ggr_launch_encode_coop_parse(st, 1, n, s->d_blob, n_msgs, nullptr, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p, (u32*)sc.aux.p, status,

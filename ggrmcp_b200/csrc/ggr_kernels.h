@@ -8,7 +8,10 @@ void ggr_launch_encode_parse(cudaStream_t st, unsigned nb, const uint8_t* blob, 
                              const uint8_t* in, const uint64_t* in_off, uint8_t* ir, uint32_t* size, uint32_t* first,
                              int32_t* status, uint64_t* block_sums, const uint32_t* list, const uint32_t* list_n);
 void ggr_launch_block_sums(cudaStream_t st, unsigned nb, long long n, const uint32_t* size, uint64_t* block_sums);
-// tier 0: every item (list == nullptr); tier 1: the items of `list`; persistent warps sized by sm_count
+// tier 0: the listed items, their token index left in the IR region by ggr_launch_encode_coop_tok; tier 1: the
+// items of `list`, everything in one kernel; persistent warps sized by sm_count
+void ggr_launch_encode_coop_tok(cudaStream_t st, long long n, const uint8_t* in, const uint64_t* in_off, uint8_t* ir,
+                                const uint32_t* list, const uint32_t* list_n, int sm_count);
 void ggr_launch_encode_coop_parse(cudaStream_t st, int tier, long long n, const uint8_t* blob, uint32_t n_msgs,
                                   const int32_t* msg_id, const uint8_t* in, const uint64_t* in_off, uint8_t* ir, uint32_t* size,
                                   uint32_t* first, int32_t* status, uint32_t* ioff, uint32_t* nnodes, const uint32_t* list,

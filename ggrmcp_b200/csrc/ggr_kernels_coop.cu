@@ -21,7 +21,9 @@ k_decode_coop_size(const u8* __restrict__ blob, long long n, u32 n_msgs, const i
   // the items of `list` (the router's choice: not too small, not too large); mode[] is PENDING for all others
   const long long total = (long long)*list_n;
   u32* ticket = const_cast<u32*>(list_n) + 1;  // zeroed with the list length; +2 is the write kernel's
-  for (long long slot = wp_next_ticket(ticket); slot < total; slot = wp_next_ticket(ticket)) {
+  u32 drawn = wp_ticket_draw(ticket);
+  for (long long slot = wp_ticket_take(drawn); slot < total; slot = wp_ticket_take(drawn)) {
+    drawn = wp_ticket_draw(ticket);
     const long long item = (long long)list[slot];
     const u64 a = in_off[item], b = in_off[item + 1];
     const i32 m = msg_id[item];
@@ -60,7 +62,9 @@ k_decode_coop_write(const u8* __restrict__ blob, long long n, const u8* __restri
   cx.flags = flags;
   const long long total = (long long)*list_n;
   u32* ticket = const_cast<u32*>(list_n) + 2;
-  for (long long slot = wp_next_ticket(ticket); slot < total; slot = wp_next_ticket(ticket)) {
+  u32 drawn = wp_ticket_draw(ticket);
+  for (long long slot = wp_ticket_take(drawn); slot < total; slot = wp_ticket_take(drawn)) {
+    drawn = wp_ticket_draw(ticket);
     const long long item = (long long)list[slot];
     if (mode[item] != GGR_MODE_COOP || status[item] != GST_OK) continue;
     const u64 a = in_off[item];

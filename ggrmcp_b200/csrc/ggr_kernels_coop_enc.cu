@@ -24,11 +24,13 @@ k_encode_coop_tok(long long n, const u8* __restrict__ in, const u64* __restrict_
   const long long total = list ? (long long)*list_n : n;
   const u64 a0 = in_off[0];
   // the words after a list's length are zeroed with it and serve as ticket counters: +1 this kernel,
-  // +2 the walker, +3 the emitter
+  // +2 the walker
   u32* ticket = list ? const_cast<u32*>(list_n) + 1 : nullptr;
   const long long stride = ticket ? 0 : (long long)gridDim.x * CE_WARPS;
-  for (long long slot = ticket ? wp_next_ticket(ticket) : (long long)blockIdx.x * CE_WARPS + warp; slot < total;
-       slot = ticket ? wp_next_ticket(ticket) : slot + stride) {
+  u32 drawn = ticket ? wp_ticket_draw(ticket) : 0u;
+  for (long long slot = ticket ? wp_ticket_take(drawn) : (long long)blockIdx.x * CE_WARPS + warp; slot < total;
+       slot = ticket ? wp_ticket_take(drawn) : slot + stride) {
+    if (ticket) drawn = wp_ticket_draw(ticket);
     const long long item = list ? (long long)list[slot] : slot;
     const u64 a = in_off[item], b = in_off[item + 1];
     if (b < a || b - a > (u64)CE_MAX_INPUT - 16u) continue;
@@ -61,8 +63,10 @@ k_encode_coop_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const 
   const u64 a0 = in_off[0];  // IR regions are laid out relative to the first offset of the batch
   u32* ticket = list ? const_cast<u32*>(list_n) + 2 : nullptr;
   const long long stride = ticket ? 0 : (long long)gridDim.x * CE_WARPS;
-  for (long long slot = ticket ? wp_next_ticket(ticket) : (long long)blockIdx.x * CE_WARPS + warp; slot < total;
-       slot = ticket ? wp_next_ticket(ticket) : slot + stride) {
+  u32 drawn = ticket ? wp_ticket_draw(ticket) : 0u;
+  for (long long slot = ticket ? wp_ticket_take(drawn) : (long long)blockIdx.x * CE_WARPS + warp; slot < total;
+       slot = ticket ? wp_ticket_take(drawn) : slot + stride) {
+    if (ticket) drawn = wp_ticket_draw(ticket);
     const long long item = list ? (long long)list[slot] : slot;
     const u64 a = in_off[item], b = in_off[item + 1];
     // envelope mode (method != nullptr): the item is a whole request body, its message type comes from the tool name
@@ -114,8 +118,9 @@ k_encode_coop_emit(long long n, const u8* __restrict__ in, const u64* __restrict
   const u32 warp = threadIdx.x >> 5;
   const u64 a0 = in_off[0];
   const long long total = (long long)*list_n;  // the router's lock-step items
-  u32* ticket = const_cast<u32*>(list_n) + 3;
-  for (long long slot = wp_next_ticket(ticket); slot < total; slot = wp_next_ticket(ticket)) {
+  // fixed stride here: an item takes a few microseconds, tickets for 150 K of them in a millisecond
+  // run into the rate of atomics on one address (measured: 1.15 ms with the stride, 1.23 ms by ticket)
+  for (long long slot = (long long)blockIdx.x * CE_WARPS + warp; slot < total; slot += (long long)gridDim.x * CE_WARPS) {
     const long long item = (long long)list[slot];
     const u32 nn = nnodes[item];
     const u32 sz = size[item];
@@ -156,6 +161,14 @@ static void ce_launch(cudaStream_t st, unsigned nb, long long n, const uint8_t* 
       id_span, final_status);
 }
 
+// token index of tier 1 (before ggr_launch_encode_coop_parse with tier 0, same list)
+void ggr_launch_encode_coop_tok(cudaStream_t st, long long n, const uint8_t* in, const uint64_t* in_off, uint8_t* ir,
+                                const uint32_t* list, const uint32_t* list_n, int sm_count) {
+  const long long want = (n + CE_WARPS - 1) / CE_WARPS, cap_t = (long long)sm_count * CE_TOK_BLOCKS;
+  k_encode_coop_tok<<<(unsigned)(want < cap_t ? want : cap_t), CE_WARPS * 32, ce_smem_bytes<CoopTok>(), st>>>(
+      n, in, (const u64*)in_off, ir, list, list_n);
+}
+
 void ggr_launch_encode_coop_parse(cudaStream_t st, int tier, long long n, const uint8_t* blob, uint32_t n_msgs,
                                   const int32_t* msg_id, const uint8_t* in, const uint64_t* in_off, uint8_t* ir, uint32_t* size,
                                   uint32_t* first, int32_t* status, uint32_t* ioff, uint32_t* nnodes, const uint32_t* list,
@@ -166,9 +179,6 @@ void ggr_launch_encode_coop_parse(cudaStream_t st, int tier, long long n, const 
     // 4 resident blocks per SM (shared memory); never more blocks than items / CE_WARPS
     long long want = (n + CE_WARPS - 1) / CE_WARPS, cap = (long long)sm_count * 4;
     unsigned nb = (unsigned)(want < cap ? want : cap);
-    const long long cap_t = (long long)sm_count * CE_TOK_BLOCKS;
-    k_encode_coop_tok<<<(unsigned)(want < cap_t ? want : cap_t), CE_WARPS * 32, ce_smem_bytes<CoopTok>(), st>>>(
-        n, in, (const u64*)in_off, ir, list, list_n);
     if (env) ce_launch<CoopEnc, true, true>(st, nb, n, blob, n_msgs, msg_id, in, in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending, method, id_span, final_status);
     else ce_launch<CoopEnc, false, true>(st, nb, n, blob, n_msgs, msg_id, in, in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending, method, id_span, final_status);
   } else {

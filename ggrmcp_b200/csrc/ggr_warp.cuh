@@ -23,15 +23,15 @@ GGR_DEV u32 wp_atomic_max(u32* p, u32 v) { return atomicMax(p, v); }
 // Persistent warps draw their items by ticket (item sizes differ: with a fixed stride the kernel
 // waits for the unluckiest warp).  Lane 0 draws, the warp follows.  `ticket` is a zeroed word that
 // belongs to this launch alone.
-GGR_DEV long long wp_next_ticket(u32* ticket) {
-  u32 t = 0;
-  if ((threadIdx.x & 31u) == 0) t = atomicAdd(ticket, 1u);
-  return (long long)__shfl_sync(0xFFFFFFFFu, t, 0);
-}
+// The draw for the next item is issued before the current one is processed (wp_ticket_draw), and
+// only read when the warp comes back for it (wp_ticket_take): the atomic's latency is off the path.
+GGR_DEV u32 wp_ticket_draw(u32* ticket) { return (threadIdx.x & 31u) == 0 ? atomicAdd(ticket, 1u) : 0u; }
+GGR_DEV long long wp_ticket_take(u32 drawn) { return (long long)__shfl_sync(0xFFFFFFFFu, drawn, 0); }
 
 #else  // ---------------------------------------------------------------- host fibers
 
-inline long long wp_next_ticket(u32*) { return 0; }  // kernels only (the host pass of nvcc still parses them)
+inline u32 wp_ticket_draw(u32*) { return 0; }  // kernels only (the host pass of nvcc still parses them)
+inline long long wp_ticket_take(u32) { return 0; }
 
 #include <ucontext.h>
 

@@ -235,7 +235,8 @@ class Engine:
             self._err(rc, "ggr_decode_batch_dev")
 
     KERNELS = ["encode_parse", "encode_scan", "encode_emit", "decode_size", "decode_scan", "decode_write",
-               "decode_coop_size", "decode_coop_write", "encode_coop_parse", "encode_block_sums", "encode_coop_emit"]
+               "decode_coop_size", "decode_coop_write", "encode_coop_parse", "encode_block_sums", "encode_coop_emit",
+               "encode_coop_tok"]
 
     def profile_enable(self, on=True):
         _load().ggr_profile_enable(self.h, 1 if on else 0)
