@@ -21,7 +21,9 @@
 #include "ggr_decode.cuh"
 #include "ggr_warp.cuh"
 
+#ifndef GGR_COOP_ENTRIES
 #define GGR_COOP_ENTRIES 320
+#endif
 #define GGR_COOP_DEPTH 24
 #define GGR_COOP_MAX_WIRE 8192u  /* larger items: per-thread kernels */
 #define GGR_MODE_COOP 2u

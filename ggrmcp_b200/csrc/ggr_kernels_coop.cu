@@ -83,7 +83,13 @@ int ggr_decode_coop_init() {
   return (a == cudaSuccess && b == cudaSuccess) ? 0 : -1;
 }
 static unsigned coop_grid(long long n, int sm_count) {
-  long long want = (n + COOP_WARPS - 1) / COOP_WARPS, cap = (long long)sm_count * 4;
+  // resident blocks per SM: what the entry tables in shared memory allow (4 with 320 entries per warp)
+  static int per_sm = 0;
+  if (per_sm == 0 &&
+      (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_coop_size, COOP_WARPS * 32, coop_smem_bytes()) != cudaSuccess ||
+       per_sm < 1))
+    per_sm = 4;
+  long long want = (n + COOP_WARPS - 1) / COOP_WARPS, cap = (long long)sm_count * per_sm;
   return (unsigned)(want < cap ? want : cap);
 }
 
