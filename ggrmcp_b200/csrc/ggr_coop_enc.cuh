@@ -67,6 +67,24 @@ struct CoopEncT {
   u32 n_tok, n_q, n_node, q_end, n_leaf, max_depth, bail, cap;
   // envelope mode: brackets nested deeper than the validators allow; what the envelope walk found
   u32 deep, env, env_method, env_msg, env_args_tok, env_id_pos, env_id_len;
+  // sink interface of ce_tokenize
+  static const bool STRUCT_KINDS = false;  // structural characters: kind filled in by ce_match
+  GGR_DEV void set_bail() { bail = 1; }
+  GGR_DEV void put_q(u32 qi, u32 pos, u32 esc, u32 slow) {
+    if (qi < MAX_Q) {
+      qpos[qi] = (u16)pos;
+      qesc[qi] = (u16)esc;
+      qslow[qi] = (u16)slow;
+    }
+  }
+  GGR_DEV void put_tok(u32 ti, u32 v) {
+    if (ti < MAX_TOK) tok[ti] = v;
+  }
+  GGR_DEV void finish(u32 nt, u32 nq, bool fail) {
+    n_tok = nt;
+    n_q = nq;
+    if (fail || nt > MAX_TOK || nq > MAX_Q) bail = 1;
+  }
 };
 typedef CoopEncT<1024, 512, 224> CoopEnc;        // tier 1: ~12 KB per warp
 typedef CoopEncT<2048, 1024, 512> CoopEncBig;   // tier 2: ~26 KB per warp (two blocks of four warps per SM)
@@ -82,6 +100,23 @@ struct CoopTokT {
   u16 qpos[MQ], qesc[MQ], qslow[MQ];
   u16 last_open[32];
   u32 n_tok, n_q, bail, deep;
+  static const bool STRUCT_KINDS = false;
+  GGR_DEV void set_bail() { bail = 1; }
+  GGR_DEV void put_q(u32 qi, u32 pos, u32 esc, u32 slow) {
+    if (qi < MAX_Q) {
+      qpos[qi] = (u16)pos;
+      qesc[qi] = (u16)esc;
+      qslow[qi] = (u16)slow;
+    }
+  }
+  GGR_DEV void put_tok(u32 ti, u32 v) {
+    if (ti < MAX_TOK) tok[ti] = v;
+  }
+  GGR_DEV void finish(u32 nt, u32 nq, bool fail) {
+    n_tok = nt;
+    n_q = nq;
+    if (fail || nt > MAX_TOK || nq > MAX_Q) bail = 1;
+  }
 };
 typedef CoopTokT<1024, 512> CoopTok;  // same limits as CoopEnc
 // header {n_tok, n_q, bail, deep}, tok[n_tok], then qpos / qesc / qslow as (n_q + 1) / 2 words each
@@ -125,6 +160,10 @@ GGR_DEV u32 ce_prefix_xor16(u32 x) {
 }
 GGR_DEV u32 ce_struct_kind(u32 c) {
   return c == '{' ? TK_LBRACE : c == '}' ? TK_RBRACE : c == '[' ? TK_LBRACK : c == ']' ? TK_RBRACK : c == ':' ? TK_COLON : c == ',' ? TK_COMMA : 0;
+}
+// the same for a byte known to be one of { } [ ] : , - from its bits: 0x04 closes, 0x20 braces, < 0x40 colon / comma
+GGR_DEV u32 ce_struct_kind_bits(u32 c) {
+  return c < 0x40u ? (c == ':' ? (u32)TK_COLON : (u32)TK_COMMA) : 1u + ((c >> 2) & 1u) + ((((c >> 5) & 1u) ^ 1u) << 1);
 }
 GGR_DEV void ce_lut_init(CeLut& L, u32 first, u32 step) {
   for (u32 b = first; b < 256; b += step) {
@@ -204,14 +243,14 @@ GGR_DEV void ce_tokenize(SH& S, const CeLut& L, const u8* in, u32 start, u32 end
           const u32 b1 = j < 15 ? ce_byte16(v, j + 1) : (ggr_ld4(in + off + 16) & 0xFFu);
           u32 len = b0 < 0xC2u ? 0u : b0 < 0xE0u ? 2u : b0 < 0xF0u ? 3u : b0 < 0xF5u ? 4u : 0u;
           if ((b0 == 0xE0u && b1 < 0xA0u) || (b0 == 0xEDu && b1 >= 0xA0u) || (b0 == 0xF0u && b1 < 0x90u) || (b0 == 0xF4u && b1 >= 0x90u)) len = 0;
-          if (len == 0) S.bail = 1;
+          if (len == 0) S.set_bail();
           else EC |= ((1u << (len - 1u)) - 1u) << (j + 1u);
         }
       }
       u32 ci = WP_SHFL_UP(EC >> 16, 1);
       if (lane == 0) ci = u_carry;
       u_carry = WP_SHFL(EC >> 16, 31);
-      if (((EC & 0xFFFFu) | ci) != (HI & ~C6)) S.bail = 1;
+      if (((EC & 0xFFFFu) | ci) != (HI & ~C6)) S.set_bail();
     }
     // escaped bytes: the carry into a chunk only matters through an all-backslash chunk
     u32 E = 0;
@@ -265,11 +304,7 @@ GGR_DEV void ce_tokenize(SH& S, const CeLut& L, const u8* in, u32 start, u32 end
     const u32 qi0 = qi;
     for (u32 m = RQ; m; m &= m - 1u) {
       u32 j = wp_ffs0(m);
-      if (qi < SH::MAX_Q) {
-        S.qpos[qi] = (u16)(off + j);
-        S.qesc[qi] = (u16)(ei + wp_popc(EI & ((1u << j) - 1u)));
-        S.qslow[qi] = (u16)(di + wp_popc(D & ((1u << j) - 1u)));
-      }
+      S.put_q(qi, off + j, ei + wp_popc(EI & ((1u << j) - 1u)), di + wp_popc(D & ((1u << j) - 1u)));
       qi++;
     }
     for (u32 m = T; m; m &= m - 1u) {
@@ -281,17 +316,14 @@ GGR_DEV void ce_tokenize(SH& S, const CeLut& L, const u8* in, u32 start, u32 end
       } else if (NS & bit) {
         kind = TK_SCALAR;
       } else {
-        kind = 0;  // structural character: ce_match looks it up (one lane per token there)
+        // structural character: ce_match looks it up (one lane per token there) unless the sink wants it now
+        kind = SH::STRUCT_KINDS ? ce_struct_kind_bits(ce_byte16(v, j)) : 0u;
       }
-      if (ti < SH::MAX_TOK) S.tok[ti] = (off + j) | (kind << 16) | (aux << 20);
+      S.put_tok(ti, (off + j) | (kind << 16) | (aux << 20));
       ti++;
     }
   }
-  if (lane == 0) {
-    S.n_tok = tbase;
-    S.n_q = qbase;
-    if (tbase > SH::MAX_TOK || qbase > SH::MAX_Q || in_carry || u_carry || tbase == 0) S.bail = 1;
-  }
+  if (lane == 0) S.finish(tbase, qbase, in_carry || u_carry || tbase == 0);
   WP_SYNC();
 }
 

@@ -148,6 +148,7 @@ struct ggr_engine {
   // batch and a reply batch can be in flight on two streams at the same time
   Scratch dev_sc[2];
   bool use_coop_enc = true;  // GGR_COOP_ENC=0 disables the lock-step request-side parser (A/B runs)
+  bool use_walk = true;      // GGR_WALK=0: the one-lane-per-object walker of round 1 instead of ggr_walk.cuh (A/B runs)
   bool trace = false;        // GGR_TRACE=1: host-buffer calls print a per-chunk timeline to stderr
   // items smaller than this go straight to the per-thread kernels, which are cheaper for them
   // (GGR_LOCKSTEP_MIN_BYTES overrides both; 0 sends everything through the lock-step kernels)
@@ -229,6 +230,7 @@ int ggr_engine_create(const ggr_config* cfg, ggr_engine** out) {
   if (e->sm_count <= 0) e->sm_count = 148;
   if (const char* nc = getenv("GGR_COOP")) e->use_coop = nc[0] != '0';
   if (const char* nc = getenv("GGR_COOP_ENC")) e->use_coop_enc = nc[0] != '0';
+  if (const char* nc = getenv("GGR_WALK")) e->use_walk = nc[0] != '0';
   if (const char* nc = getenv("GGR_TRACE")) e->trace = nc[0] != '0';
   if (const char* nc = getenv("GGR_LOCKSTEP_MIN_BYTES")) e->min_json = e->min_wire = (uint32_t)strtoul(nc, nullptr, 10);
   if (const char* nc = getenv("GGR_SLOTS")) {
@@ -244,7 +246,7 @@ int ggr_engine_create(const ggr_config* cfg, ggr_engine** out) {
     if (v >= (1 << 16)) e->chunk_bytes = (uint64_t)v;
   }
   e->order = (cfg && cfg->wire_order == GGR_ORDER_GO_LEGACY) ? ggr::ORDER_GO_LEGACY : ggr::ORDER_FIELD_NUMBER;
-  if (ggr_encode_coop_init() != 0 || ggr_decode_coop_init() != 0) {
+  if (ggr_encode_coop_init() != 0 || ggr_encode_walk_init() != 0 || ggr_decode_coop_init() != 0) {
     cudaGetLastError();
     delete e;
     return GGR_ERR_CUDA;
@@ -435,11 +437,19 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
       if (prof) prof_mark(e, st, &m0);
       // router: small (and oversized) items straight to the per-thread parser
       k_route<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, in_off, e->min_json, 65000u - 16u, big, counters, pend2, counters + 8, nullptr);
-      ggr_launch_encode_coop_tok(st, n, in, in_off, (u8*)sc.ir.p, big, counters, e->sm_count);
       size_t t1 = 0;
-      if (prof) prof_mark(e, st, &t1);
-      ggr_launch_encode_coop_parse(st, 0, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
-                                   (u32*)sc.aux.p, status, (u32*)sc.ioff.p, (u32*)sc.nn.p, big, counters, pend1, counters + 4, e->sm_count, nullptr, nullptr, -1);
+      if (e->use_walk) {
+        // token index, then the token-parallel walker (ggr_walk.cuh); what it leaves: the fused large-table kernel
+        ggr_launch_encode_tok2(st, n, in, in_off, (u8*)sc.ir.p, big, counters, e->sm_count);
+        if (prof) prof_mark(e, st, &t1);
+        ggr_launch_encode_walk(st, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p, (u32*)sc.aux.p, status,
+                               (u32*)sc.ioff.p, (u32*)sc.nn.p, big, counters, pend1, counters + 4, e->sm_count);
+      } else {
+        ggr_launch_encode_coop_tok(st, n, in, in_off, (u8*)sc.ir.p, big, counters, e->sm_count);
+        if (prof) prof_mark(e, st, &t1);
+        ggr_launch_encode_coop_parse(st, 0, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
+                                     (u32*)sc.aux.p, status, (u32*)sc.ioff.p, (u32*)sc.nn.p, big, counters, pend1, counters + 4, e->sm_count, nullptr, nullptr, -1);
+      }
       ggr_launch_encode_coop_parse(st, 1, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
                                    (u32*)sc.aux.p, status, (u32*)sc.ioff.p, (u32*)sc.nn.p, pend1, counters + 4, pend2, counters + 8, e->sm_count, nullptr, nullptr, -1);
       if (prof) prof_mark(e, st, &c0);
@@ -454,7 +464,7 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
         prof_mark(e, st, &m1);
         e->spans.push_back({9, c1, m1});
       }
-      e->launches += 5;  // + the token-index kernel of tier 1
+      e->launches += e->use_walk ? 6 : 5;  // + the token-index kernel of tier 1 (+ the place kernel of the token-parallel walker)
     } else {
       ggr_launch_encode_parse(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
                               (u32*)sc.aux.p, status, (u64*)sc.sums.p, nullptr, nullptr);

@@ -122,11 +122,12 @@ k_encode_coop_emit(long long n, const u8* __restrict__ in, const u64* __restrict
   // run into the rate of atomics on one address (measured: 1.15 ms with the stride, 1.23 ms by ticket)
   for (long long slot = (long long)blockIdx.x * CE_WARPS + warp; slot < total; slot += (long long)gridDim.x * CE_WARPS) {
     const long long item = (long long)list[slot];
-    const u32 nn = nnodes[item];
+    const u32 nw = nnodes[item];
+    const u32 nn = nw & 0xFFFFu;  // node count | index of the first node within the region << 16 (ggr_walk.cuh)
     const u32 sz = size[item];
     if (nn <= 1 || sz == 0 || status[item] != GST_OK) continue;
     const u64 a = in_off[item], b = in_off[item + 1];
-    const u64 node_off = ((a - a0) >> 1) + 8ull * (u64)item;
+    const u64 node_off = ((a - a0) >> 1) + 8ull * (u64)item + (u64)(nw >> 16);
     ce_emit_item(E[warp], in + (a & ~15ull), (u32)(a & 15ull) + (u32)(b - a), ir + node_off * 16, ioff + node_off, nn,
                  out + out_off[item], sz);
   }

@@ -39,6 +39,8 @@ _ENGINE_PATHS = {
     "default": {"GGR_LOCKSTEP_MIN_BYTES": "0"},
     "size_routing": {},
     "per_thread": {"GGR_COOP_ENC": "0", "GGR_COOP": "0"},
+    # the one-lane-per-object walker of round 1 in place of the token-parallel one (still the request-body path)
+    "old_walker": {"GGR_WALK": "0", "GGR_LOCKSTEP_MIN_BYTES": "0"},
     "lockstep_request_only": {"GGR_COOP": "0", "GGR_LOCKSTEP_MIN_BYTES": "0"},
     # host entry points cut into many small chunks over two slots: exercises the copy/compute pipeline
     "small_chunks": {"GGR_CHUNK_ITEMS": "128", "GGR_SLOTS": "2", "GGR_LOCKSTEP_MIN_BYTES": "0"},

@@ -20,6 +20,7 @@ def lib():
         L.hs_encode.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p,
                                 C.c_uint32, C.POINTER(C.c_uint32)]
         L.hs_encode_coop.argtypes = L.hs_encode.argtypes + [C.c_int]
+        L.hs_encode_walk.argtypes = L.hs_encode.argtypes
         if hasattr(L, "hs_decode_coop"):
             L.hs_decode_coop.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                          C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32)]
@@ -90,6 +91,18 @@ def _encode_coop(self, name, data, in_off=0, out_off=0, tier=0):
 
 
 Schema.encode_coop = _encode_coop
+
+
+def _encode_walk(self, name, data, in_off=0, out_off=0):
+    """token-parallel walker (ggr_walk.cuh): token index, walker, lock-step emitter"""
+    cap = len(data) + 64
+    out = C.create_string_buffer(cap)
+    n = C.c_uint32()
+    rc = lib().hs_encode_walk(self.h, self.msg(name), data, len(data), in_off, out_off, out, cap, C.byref(n))
+    return rc, out.raw[: n.value]
+
+
+Schema.encode_walk = _encode_walk
 
 
 def load_schema(order=0):

@@ -13,12 +13,15 @@
 #include "../../ggrmcp_b200/csrc/ggr_schema.h"
 #include "../../ggrmcp_b200/csrc/ggr_encode.cuh"
 #include "../../ggrmcp_b200/csrc/ggr_coop_enc.cuh"
+#include "../../ggrmcp_b200/csrc/ggr_walk.cuh"
 #include "../../ggrmcp_b200/csrc/ggr_wrap.cuh"
 #ifdef GGR_HAVE_DECODE
 #include "../../ggrmcp_b200/csrc/ggr_decode.cuh"
 #include "../../ggrmcp_b200/csrc/ggr_coop.cuh"
 #endif
 
+int g_cw_why = 0;
+extern "C" int hs_cw_why() { return g_cw_why; }
 struct HsSchema {
   ggr::CompiledSchema cs;
   uint8_t* blob;  // 16-byte aligned copy
@@ -230,6 +233,129 @@ static int hs_encode_coop_t(void* h, int msg, const uint8_t* json, uint32_t n, u
   memcpy(out, ob + out_off, res.size);
   *out_n = res.size;
   free(ir);
+  return st;
+}
+
+// Token-parallel walker (ggr_walk.cuh) on 32 fibers: token index (k_encode_tok2), walker (k_encode_walk),
+// then both emitters.  200: left to the next tier; 3xx: fiber-warp error.
+struct WalkArgs {
+  u32 sh[4];
+  CoopWalk* S;
+  CwPlaceSh* P;
+  const CwLut* lut;
+  Tables T;
+  u32 msg;
+  const u8* in;
+  u32 start, end;
+  u8* region;
+  u32* ioff;
+  u32 cap;
+  EncResult res[32];
+  bool ok[32];
+  CoopEmit* E;
+  u8* dst;
+};
+static void walk_tok_body(void* p, u32 lane) {
+  WalkArgs* a = (WalkArgs*)p;
+  cw_tok_item(a->sh, *a->lut, a->in, a->start, a->end, a->region, a->cap);
+}
+static void walk_place_body(void* p, u32 lane) {
+  WalkArgs* a = (WalkArgs*)p;
+  cw_place_item(*a->P, a->region, a->cap, CoopWalk::MAX_NODE);
+}
+static void walk_body(void* p, u32 lane) {
+  WalkArgs* a = (WalkArgs*)p;
+  a->ok[lane] = cw_type_item(*a->S, a->T, a->msg, a->in, a->start, a->end, a->region, a->ioff, a->cap, &a->res[lane]);
+}
+static void walk_emit_body(void* p, u32 lane) {
+  WalkArgs* a = (WalkArgs*)p;
+  const u32 shift = a->res[0].method;
+  ce_emit_item(*a->E, a->in, a->end, a->region + (size_t)shift * 16, a->ioff + shift, a->res[0].n_nodes, a->dst, a->res[0].size);
+}
+extern "C" int hs_encode_walk(void* h, int msg, const uint8_t* json, uint32_t n, uint32_t in_off, uint32_t out_off, uint8_t* out,
+                              uint32_t out_cap, uint32_t* out_n) {
+  HsSchema* s = (HsSchema*)h;
+  static CwLut lut;
+  static bool lut_ok = false;
+  if (!lut_ok) {
+    cw_lut_init(lut, 0, 1);
+    lut_ok = true;
+  }
+  std::vector<uint8_t> inbuf_raw(in_off + n + 64 + 16, 0xEE);
+  uint8_t* in = (uint8_t*)(((uintptr_t)inbuf_raw.data() + 15) & ~(uintptr_t)15);
+  memcpy(in + in_off, json, n);
+  uint32_t cap = n / 2 + 8;  // as the kernels lay the regions out: 8 bytes of IR per input byte + 128
+  uint8_t* region = (uint8_t*)aligned_alloc(16, (size_t)cap * 16 + 16);
+  memset(region, 0xCC, (size_t)cap * 16 + 16);
+  static CoopWalk S;
+  memset(&S, 0xAB, sizeof S);
+  static CwPlaceSh P;
+  memset(&P, 0xAB, sizeof P);
+  WalkArgs a;
+  a.S = &S;
+  a.P = &P;
+  a.lut = &lut;
+  a.T = ggr_tables(s->blob);
+  a.msg = (u32)msg;
+  a.in = in;
+  a.start = in_off;
+  a.end = in_off + n;
+  a.region = region;
+  std::vector<u32> ioff(cap + 8, 0xDEADBEEFu);
+  a.ioff = ioff.data();
+  a.cap = cap;
+  *out_n = 0;
+  int werr = hw_run_warp(walk_tok_body, &a);
+  if (getenv("HS_DEBUG")) {
+    const u32* hh = (const u32*)region;
+    fprintf(stderr, "tok: n_tok=%u n_q=%u bail=%u\n", hh[0], hh[1], hh[2]);
+    for (u32 i = 0; i < hh[0] && i < 200; i++) fprintf(stderr, " [%u p%u k%u c%u v%u s%u]", i, K3_POS(hh[4 + i]) - in_off, K3_KIND(hh[4 + i]), K3_C(hh[4 + i]), K3_V(hh[4 + i]), hh[4 + i] >> 21);
+    fprintf(stderr, "\n");
+  }
+  if (!werr) werr = hw_run_warp(walk_place_body, &a);
+  if (getenv("HS_DEBUG")) fprintf(stderr, "place: n_rec=%u\n", ((const u32*)region)[3]);
+  if (!werr) werr = hw_run_warp(walk_body, &a);
+  if (werr) {
+    free(region);
+    return 300 + werr;
+  }
+  for (int l = 1; l < 32; l++)
+    if (a.ok[l] != a.ok[0] || (a.ok[0] && (a.res[l].size != a.res[0].size || a.res[l].n_nodes != a.res[0].n_nodes))) {
+      free(region);
+      return 310;
+    }
+  if (region[(size_t)cap * 16] != 0xCC) {
+    free(region);
+    return 311;  // wrote past the region
+  }
+  if (!a.ok[0]) {
+    free(region);
+    return 200;
+  }
+  EncResult res = a.res[0];
+  int st = GST_OK;
+  if (res.size > out_cap) {
+    free(region);
+    return GST_NO_SPACE;
+  }
+  std::vector<uint8_t> ob_raw(out_off + res.size + 64, 0xDD);
+  uint8_t* ob = (uint8_t*)(((uintptr_t)ob_raw.data() + 15) & ~(uintptr_t)15);
+  std::vector<uint8_t> before(ob, ob + out_off + res.size + 32);
+  alignas(16) static CoopEmit E;
+  memset(&E, 0xAB, sizeof E);
+  a.E = &E;
+  a.dst = ob + out_off;
+  if (res.size && res.n_nodes > 1) {
+    werr = hw_run_warp(walk_emit_body, &a);
+    if (werr) st = 320 + werr;
+  }
+  for (uint32_t i = 0; i < out_off && st == GST_OK; i++)
+    if (ob[i] != before[i]) st = 101;
+  for (uint32_t i = out_off + res.size; i < out_off + res.size + 32 && st == GST_OK; i++)
+    if (ob[i] != before[i]) st = 102;
+  memcpy(out, ob + out_off, res.size);
+  *out_n = res.size;
+  free(region);
   return st;
 }
 extern "C" {
