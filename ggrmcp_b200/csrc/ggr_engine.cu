@@ -87,8 +87,9 @@ __global__ void __launch_bounds__(256) k_route(long long n, const u64* __restric
 // status / size of the items of a list (request bodies the lock-step parser cannot take)
 // the chunk's output size straight into mapped host memory: the host learns it from the stream's
 // event alone, without a copy that would queue behind other chunks' payloads on the copy engine
-__global__ void k_publish_total(const u64* __restrict__ src, volatile u64* dst) {
-  *dst = *src;
+__global__ void k_publish_total(const u64* __restrict__ src, const u64* __restrict__ src2, volatile u64* dst) {
+  dst[0] = *src;
+  dst[1] = src2 ? *src2 : 0ull;  // result wrapping: bytes of the intermediate protojson texts
   __threadfence_system();
 }
 
@@ -181,6 +182,19 @@ static cudaEvent_t prof_mark(ggr_engine* e, cudaStream_t st, size_t* idx) {
   cudaEventRecord(e->ev_pool[*idx], st);
   return e->ev_pool[*idx];
 }
+
+// the caller's current device is put back when an entry point returns
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
 
 static bool cuda_ok(ggr_engine* e, cudaError_t rc, const char* what) {
   if (rc == cudaSuccess) return true;
@@ -408,7 +422,7 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
                    int32_t* status, uint32_t flags, cudaStream_t st) {
   if (!e || !s || n < 0 || (n > 0 && (!msg_id || !in || !in_off || !out_off || !status))) return GGR_ERR_INVALID_ARGUMENT;
   if (((uintptr_t)in & 15) || ((uintptr_t)out & 7)) return GGR_ERR_INVALID_ARGUMENT;
-  cudaSetDevice(e->device);
+  DeviceGuard dg(e->device);
   if (n == 0) {
     return cuda_ok(e, cudaMemsetAsync(out_off, 0, sizeof(uint64_t), st), "memset") ? GGR_SUCCESS : GGR_ERR_CUDA;
   }
@@ -416,7 +430,7 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
   if (!ensure(e, sc.size, (size_t)n * 4) || !ensure(e, sc.aux, (size_t)n * 4) || !ensure(e, sc.sums, (size_t)nb * 8)) return GGR_ERR_CUDA;
   if (encode && !ensure(e, sc.ir, (size_t)in_bytes * 8 + (size_t)n * 128 + 256)) return GGR_ERR_CUDA;
   u32 n_msgs = (u32)s->cs.msg_names.size();
-  const bool prof = e->profiling && e->ev_used + 12 <= 65536;
+  const bool prof = e->profiling && e->ev_used + 16 <= 65536;
   size_t m0 = 0, m1 = 0, m2 = 0, m3 = 0, mx = 0;
   bool have_mx = false;
   if (prof) prof_mark(e, st, &m0);
@@ -442,8 +456,17 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
         // token index, then the token-parallel walker (ggr_walk.cuh); what it leaves: the fused large-table kernel
         ggr_launch_encode_tok2(st, n, in, in_off, (u8*)sc.ir.p, big, counters, e->sm_count);
         if (prof) prof_mark(e, st, &t1);
-        ggr_launch_encode_walk(st, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p, (u32*)sc.aux.p, status,
+        ggr_launch_encode_place(st, n, in_off, (u8*)sc.ir.p, big, counters, e->sm_count);
+        size_t t2 = 0, t3 = 0;
+        if (prof) prof_mark(e, st, &t2);
+        ggr_launch_encode_type(st, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p, (u32*)sc.aux.p, status,
                                (u32*)sc.ioff.p, (u32*)sc.nn.p, big, counters, pend1, counters + 4, e->sm_count);
+        if (prof) {
+          prof_mark(e, st, &t3);
+          e->spans.push_back({12, t1, t2});  // value records
+          e->spans.push_back({13, t2, t3});  // types, sizes, offsets
+          t1 = t3;                           // slot 8: what is left for the fused large-table kernel
+        }
       } else {
         ggr_launch_encode_coop_tok(st, n, in, in_off, (u8*)sc.ir.p, big, counters, e->sm_count);
         if (prof) prof_mark(e, st, &t1);
@@ -568,7 +591,7 @@ static int run_request_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, int6
                            int32_t* status, cudaStream_t st) {
   if (!e || !s || n < 0 || (n > 0 && (!in || !in_off || !out_off || !status || !method || !id_span))) return GGR_ERR_INVALID_ARGUMENT;
   if (((uintptr_t)in & 15) || ((uintptr_t)out & 7)) return GGR_ERR_INVALID_ARGUMENT;
-  cudaSetDevice(e->device);
+  DeviceGuard dg(e->device);
   if (n == 0) return cuda_ok(e, cudaMemsetAsync(out_off, 0, sizeof(uint64_t), st), "memset") ? GGR_SUCCESS : GGR_ERR_CUDA;
   const long long nb = (n + GGR_BLOCK - 1) / GGR_BLOCK;
   if (!ensure(e, sc.size, (size_t)n * 4) || !ensure(e, sc.aux, (size_t)n * 4) || !ensure(e, sc.sums, (size_t)nb * 8) ||
@@ -703,7 +726,8 @@ static int chunk_issue(ggr_engine* e, const ggr_schema* s, Slot& sl, bool encode
   if (rc != GGR_SUCCESS) return rc;
   if (!cuda_ok(e, cudaEventRecord(sl.ev_k, st), "event")) return GGR_ERR_CUDA;
   if (tr) cudaEventRecord(tr[1], st);
-  k_publish_total<<<1, 1, 0, st>>>((const u64*)sl.d_out_off.p + j.nc, (volatile u64*)sl.d_total_alias);
+  k_publish_total<<<1, 1, 0, st>>>((const u64*)sl.d_out_off.p + j.nc, ids ? (const u64*)sl.sc.woff.p + j.nc : nullptr,
+                                   (volatile u64*)sl.d_total_alias);
   e->launches++;
   if (!cuda_ok(e, cudaGetLastError(), "k_publish_total") || !cuda_ok(e, cudaEventRecord(sl.ready, st), "event")) return GGR_ERR_CUDA;
   return GGR_SUCCESS;
@@ -721,10 +745,11 @@ static int run_host(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, 
   // one batch per direction at a time; with the profiler on everything is serialised (its event
   // list is shared)
   const int dir = encode ? 0 : 1;
+  // lock order everywhere: mu_host[dir] before mu
+  std::lock_guard<std::mutex> g(e->mu_host[dir]);
   std::unique_lock<std::mutex> gp(e->mu, std::defer_lock);
   if (e->profiling) gp.lock();
-  std::lock_guard<std::mutex> g(e->mu_host[dir]);
-  cudaSetDevice(e->device);
+  DeviceGuard dg(e->device);
   Slot* const slots = e->slots[dir];
   for (int i = 0; i < e->n_slots; i++)
     if (!slot_init(e, slots[i])) return GGR_ERR_CUDA;
@@ -772,7 +797,7 @@ static int run_host(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, 
     uint64_t c = (uint64_t)((double)out_cap * share * 1.5) + (uint64_t)j.nc * 16 + 4096;
     return c < out_cap + 64 ? c : out_cap + 64;
   };
-  uint64_t produced = 0;
+  uint64_t produced = 0, needed = 0;  // bytes copied out / bytes the whole batch takes
   int rc_final = GGR_SUCCESS;
   int64_t issued = 0, retired = 0;
   // GGR_TRACE: four timing events per chunk (inputs on the device, kernels done, sizes on the host,
@@ -792,7 +817,8 @@ static int run_host(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, 
     cudaEventRecord(tbase, s_in);
   }
   while (retired < nchunks) {
-    while (issued < nchunks && issued - retired < e->n_slots && rc_final == GGR_SUCCESS) {
+    // a caller's buffer found too small does not stop the batch: the remaining chunks are still sized
+    while (issued < nchunks && issued - retired < e->n_slots && (rc_final == GGR_SUCCESS || rc_final == GGR_ERR_NO_SPACE)) {
       ChunkJob j = job(issued);
       if (e->trace) trec[issued].issue0 = hms();
       int rc = chunk_issue(e, s, slots[issued % e->n_slots], encode, j, msg_id, in, in_off, chunk_cap(j), out_off, status, flags, true, s_in, ids, ids_off,
@@ -807,14 +833,26 @@ static int run_host(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, 
     if (e->trace) trec[retired].wait0 = hms();
     if (!cuda_ok(e, cudaEventSynchronize(sl.ready), "sync")) return GGR_ERR_CUDA;
     if (e->trace) trec[retired].wait1 = hms();
-    uint64_t total = *sl.h_total;
-    if (total > sl.out_cap && rc_final == GGR_SUCCESS) {
-      // rare: the chunk's output outgrew its share; its inputs are still on the device
-      int rc = chunk_issue(e, s, sl, encode, j, msg_id, in, in_off, total, out_off, status, flags, false, s_in, ids, ids_off);
-      if (rc != GGR_SUCCESS) rc_final = rc;
-      else if (!cuda_ok(e, cudaEventSynchronize(sl.ready), "sync")) return GGR_ERR_CUDA;
-      total = *sl.h_total;
+    uint64_t total = sl.h_total[0], text_total = ids ? sl.h_total[1] : 0;
+    // rare: the chunk's output outgrew its share (its inputs are still on the device): run it again with what it
+    // needs.  With result wrapping the intermediate texts share the capacity; texts that did not fit make the
+    // wrapped total too small, so that case is re-run even when the caller's buffer is already known to be short
+    // (out_off[n] has to come back as the exact number of bytes needed).
+    for (int attempt = 0; attempt < 3 && (rc_final == GGR_SUCCESS || rc_final == GGR_ERR_NO_SPACE); attempt++) {
+      const bool text_short = text_total > sl.out_cap;
+      const bool out_short = total > sl.out_cap && rc_final == GGR_SUCCESS;
+      if (!text_short && !out_short) break;
+      const uint64_t want = (total > text_total ? total : text_total) + (ids ? text_total / 4 + 256 : 0);
+      int rc = chunk_issue(e, s, sl, encode, j, msg_id, in, in_off, want, out_off, status, flags, false, s_in, ids, ids_off);
+      if (rc != GGR_SUCCESS) {
+        rc_final = rc;
+        break;
+      }
+      if (!cuda_ok(e, cudaEventSynchronize(sl.ready), "sync")) return GGR_ERR_CUDA;
+      total = sl.h_total[0];
+      text_total = ids ? sl.h_total[1] : 0;
     }
+    needed += total;
     // the chunk's kernels are complete (the host has seen `ready`): offsets, statuses and payload leave
     // on the output stream, in chunk order
     if (!cuda_ok(e, cudaMemcpyAsync(out_off + j.i0, sl.d_out_off.p, (size_t)j.nc * 8, cudaMemcpyDeviceToHost, s_out), "D2H offsets") ||
@@ -845,7 +883,7 @@ static int run_host(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, 
     const ChunkJob j = job(c);
     for (int64_t k = 0; k < j.nc; k++) out_off[j.i0 + k] += base;
   }
-  out_off[n] = produced;
+  out_off[n] = rc_final == GGR_ERR_NO_SPACE ? needed : produced;  // GGR_ERR_NO_SPACE: the capacity that would do
   if (e->trace) {
     fprintf(stderr, "[ggr trace] %s batch: %lld items in %lld chunks, %d slots, %.2f ms on the host clock\n", encode ? "request" : "reply",
             (long long)n, (long long)nchunks, e->n_slots, hms());
@@ -884,7 +922,7 @@ int ggr_request_batch(ggr_engine* e, const ggr_schema* s, int64_t n, const uint8
   if (!body || !body_off || !status || !method || !id_span || (!out && out_cap)) return GGR_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(e->mu_host[0]);
   std::lock_guard<std::mutex> g2(e->mu);
-  cudaSetDevice(e->device);
+  DeviceGuard dg(e->device);
   if (!slot_init(e, e->slots[0][0])) return GGR_ERR_CUDA;
   Slot& sl = e->slots[0][0];
   const uint64_t base = body_off[0], in_bytes = body_off[n] - base, phase = base & 15ull;

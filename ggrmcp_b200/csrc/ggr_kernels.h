@@ -21,10 +21,12 @@ void ggr_launch_encode_coop_emit(cudaStream_t st, long long n, const uint8_t* in
                                  const uint32_t* ioff, const uint32_t* nnodes, const uint32_t* size, const int32_t* status,
                                  uint8_t* out, const uint64_t* out_off, int sm_count, const uint32_t* list,
                                  const uint32_t* list_n);
-// token index + token-parallel walker of the regular items (ggr_kernels_walk.cu); nnodes = node count | first node << 16
+// token index, value records, types + sizes of the regular items (ggr_kernels_walk.cu); nnodes = node count | first node << 16
 void ggr_launch_encode_tok2(cudaStream_t st, long long n, const uint8_t* in, const uint64_t* in_off, uint8_t* ir, const uint32_t* list,
                             const uint32_t* list_n, int sm_count);
-void ggr_launch_encode_walk(cudaStream_t st, long long n, const uint8_t* blob, uint32_t n_msgs, const int32_t* msg_id, const uint8_t* in,
+void ggr_launch_encode_place(cudaStream_t st, long long n, const uint64_t* in_off, uint8_t* ir, const uint32_t* list, const uint32_t* list_n,
+                             int sm_count);
+void ggr_launch_encode_type(cudaStream_t st, long long n, const uint8_t* blob, uint32_t n_msgs, const int32_t* msg_id, const uint8_t* in,
                             const uint64_t* in_off, uint8_t* ir, uint32_t* size, uint32_t* first, int32_t* status, uint32_t* ioff,
                             uint32_t* nnodes, const uint32_t* list, const uint32_t* list_n, uint32_t* pending, uint32_t* n_pending,
                             int sm_count);

@@ -127,17 +127,22 @@ void ggr_launch_encode_tok2(cudaStream_t st, long long n, const uint8_t* in, con
   k_encode_tok3<<<(unsigned)(want < cap ? want : cap), CW_WARPS * 32, 0, st>>>(in, (const u64*)in_off, ir, list, list_n);
 }
 
-void ggr_launch_encode_walk(cudaStream_t st, long long n, const uint8_t* blob, uint32_t n_msgs, const int32_t* msg_id, const uint8_t* in,
+void ggr_launch_encode_place(cudaStream_t st, long long n, const uint64_t* in_off, uint8_t* ir, const uint32_t* list, const uint32_t* list_n,
+                             int sm_count) {
+  static unsigned per_sm = 0;
+  if (!per_sm) per_sm = cw_grid((const void*)k_encode_place, CW_WARPS * 32, 0, 1ll << 40, 1);
+  const long long want = (n + CW_WARPS - 1) / CW_WARPS, cap = (long long)sm_count * per_sm;
+  k_encode_place<<<(unsigned)(want < cap ? want : cap), CW_WARPS * 32, 0, st>>>((const u64*)in_off, ir, list, list_n);
+}
+
+void ggr_launch_encode_type(cudaStream_t st, long long n, const uint8_t* blob, uint32_t n_msgs, const int32_t* msg_id, const uint8_t* in,
                             const uint64_t* in_off, uint8_t* ir, uint32_t* size, uint32_t* first, int32_t* status, uint32_t* ioff,
                             uint32_t* nnodes, const uint32_t* list, const uint32_t* list_n, uint32_t* pending, uint32_t* n_pending,
                             int sm_count) {
   static unsigned per_sm = 0;
   const size_t smem = sizeof(CoopWalk) * CW_WARPS;
-  static unsigned per_sm_p = 0;
-  if (!per_sm_p) per_sm_p = cw_grid((const void*)k_encode_place, CW_WARPS * 32, 0, 1ll << 40, 1);
   if (!per_sm) per_sm = cw_grid((const void*)k_encode_type, CW_WARPS * 32, smem, 1ll << 40, 1);
-  const long long want = (n + CW_WARPS - 1) / CW_WARPS, cap = (long long)sm_count * per_sm, cap_p = (long long)sm_count * per_sm_p;
-  k_encode_place<<<(unsigned)(want < cap_p ? want : cap_p), CW_WARPS * 32, 0, st>>>((const u64*)in_off, ir, list, list_n);
+  const long long want = (n + CW_WARPS - 1) / CW_WARPS, cap = (long long)sm_count * per_sm;
   k_encode_type<<<(unsigned)(want < cap ? want : cap), CW_WARPS * 32, smem, st>>>(blob, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first,
                                                                                   status, ioff, nnodes, list, list_n, pending, n_pending);
 }

@@ -236,7 +236,7 @@ class Engine:
 
     KERNELS = ["encode_parse", "encode_scan", "encode_emit", "decode_size", "decode_scan", "decode_write",
                "decode_coop_size", "decode_coop_write", "encode_coop_parse", "encode_block_sums", "encode_coop_emit",
-               "encode_coop_tok"]
+               "encode_coop_tok", "encode_place", "encode_type", "reserved14", "reserved15"]
 
     def profile_enable(self, on=True):
         _load().ggr_profile_enable(self.h, 1 if on else 0)

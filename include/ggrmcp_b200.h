@@ -177,10 +177,12 @@ int ggr_decode_wrap_batch_dev(ggr_engine* e, const ggr_schema* s, int64_t n, con
  * slots: 0 encode_parse, 1 encode_scan, 2 encode_emit, 3 decode_size, 4 decode_scan, 5 decode_write,
  *        6 decode_coop_size, 7 decode_coop_write (the warp-cooperative reply-side kernels),
  *        8 encode_coop_parse (lock-step request-side parser: walker over the token index, large-table tier),
- *        9 encode_block_sums, 10 encode_coop_emit, 11 encode_coop_tok (router + token index of the small-table tier).
+ *        9 encode_block_sums, 10 encode_coop_emit, 11 encode_coop_tok (router + token index),
+ *        12 encode_place (value records), 13 encode_type (types, sizes, offsets) of the token-parallel walker; with it
+ *        slot 8 holds only the fused large-table kernel that takes what the walker leaves.
  * ggr_profile_read synchronizes, adds up the elapsed milliseconds and launch counts since the
  * last read into ms[GGR_PROFILE_SLOTS] / launches[GGR_PROFILE_SLOTS], and resets the recorder. */
-#define GGR_PROFILE_SLOTS 12
+#define GGR_PROFILE_SLOTS 16
 int ggr_profile_enable(ggr_engine* e, int on);
 int ggr_profile_read(ggr_engine* e, double* ms, uint64_t* launches);
 

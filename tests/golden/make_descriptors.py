@@ -226,6 +226,87 @@ def bench_file():
     return fd
 
 
+def mixed_file():
+    """configs[4] (mixed replay): 28 generated unary methods Call00..Call27 over messages that mix every scalar
+    kind, enums, nested / repeated messages, maps, oneofs, proto3 optional and Timestamp - drawn from a seeded
+    generator (seed 0xB2000005, the config's seed) so the fixture is reproducible."""
+    import random
+    rng = random.Random(0xB2000005)
+    P = ".mixed"
+    fd = dpb.FileDescriptorProto(name="mixed.proto", package="mixed", syntax="proto3")
+    fd.dependency.append("google/protobuf/timestamp.proto")
+    e = fd.enum_type.add(name="Level")
+    for n, v in [("LEVEL_UNSPECIFIED", 0), ("LOW", 1), ("MID", 2), ("HIGH", 3), ("MAX", 100), ("BELOW", -1)]:
+        e.value.add(name=n, number=v)
+    words = ["id", "name", "count", "total", "flag", "score", "ratio", "data", "tag", "kind", "note", "owner", "size", "rank",
+             "price", "stamp", "label", "path", "mode", "limit", "offset", "token", "state", "weight", "key", "group", "zone"]
+    # a few shared leaf messages
+    subs = []
+    for k in range(6):
+        m = fd.message_type.add(name="Part%d" % k)
+        names = rng.sample(words, 4)
+        for i, nm in enumerate(names):
+            add_field(m, "%s_%d" % (nm, i), i + 1, rng.choice(["string", "int32", "int64", "bool", "double", "uint32", "bytes", "sint32"]))
+        subs.append(P + ".Part%d" % k)
+
+    def gen_message(name):
+        m = fd.message_type.add(name=name)
+        fq = P + "." + name
+        n_fields = rng.randint(4, 14)
+        numbers = list(range(1, n_fields + 1))
+        if rng.random() < 0.3:  # gaps and a high field number
+            numbers[-1] = rng.choice([100, 536, 2047, 70000])
+        used = set()
+        oneof_left = 0
+        have_oneof = False
+        decl = []
+        for i in range(n_fields):
+            while True:
+                nm = rng.choice(words) + rng.choice(["", "", "_x", "_value", "_list", "_id"])
+                if nm not in used:
+                    used.add(nm)
+                    break
+            decl.append((nm, numbers[i]))
+        if rng.random() < 0.25:
+            rng.shuffle(decl)  # declaration order != field number order
+        for nm, num in decl:
+            u = rng.random()
+            if oneof_left > 0:
+                add_field(m, nm, num, rng.choice(["string", "int32", "bool", rng.choice(subs), "enum:" + P + ".Level"]), oneof=0)
+                oneof_left -= 1
+            elif u < 0.40:
+                add_field(m, nm, num, rng.choice(SCALARS))
+            elif u < 0.46:
+                add_field(m, nm, num, "enum:" + P + ".Level")
+            elif u < 0.54:
+                add_field(m, nm, num, rng.choice(subs))
+            elif u < 0.66:
+                add_field(m, nm, num, rng.choice(SCALARS), repeated=True)
+            elif u < 0.70:
+                add_field(m, nm, num, "int32", repeated=True, packed=False)
+            elif u < 0.76:
+                add_field(m, nm, num, rng.choice(subs), repeated=True)
+            elif u < 0.86:
+                k, v = rng.choice([("string", "string"), ("string", "int32"), ("int32", "string"), ("string", rng.choice(subs)),
+                                   ("uint64", "bool"), ("string", "double")])
+                add_map(m, fq, nm, num, k, v)
+            elif u < 0.92 and not have_oneof:
+                m.oneof_decl.add(name="choice")
+                have_oneof = True
+                oneof_left = rng.randint(1, 2)
+                add_field(m, nm, num, rng.choice(["string", "int64"]), oneof=0)
+            elif u < 0.96:
+                add_field(m, nm, num, ".google.protobuf.Timestamp")
+            else:
+                add_field(m, nm, num, rng.choice(["string", "int32", "bool"]))
+        return fq
+
+    s = fd.service.add(name="MixedService")
+    for k in range(28):
+        add_method(s, "Call%02d" % k, gen_message("Req%02d" % k), gen_message("Rep%02d" % k))
+    return fd
+
+
 def build_set():
     fds = dpb.FileDescriptorSet()
     ts = fds.file.add()
@@ -238,6 +319,7 @@ def build_set():
     fds.file.append(hello_file())
     fds.file.append(complex_file())
     fds.file.append(bench_file())
+    fds.file.append(mixed_file())
     return fds
 
 

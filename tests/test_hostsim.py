@@ -150,6 +150,69 @@ def test_coop_encode_bench_shapes(hsim):
         assert handled >= want, (kind, tier, handled)
 
 
+# ---- token-parallel walker (ggr_walk.cuh: tokenizer without colons / commas, place, type) on 32 fibers -------
+def _check_walk(hsim, name, js, i=0):
+    """either leaves the item alone (200) or produces exactly the bytes of the per-thread path"""
+    rc, out = hsim.encode_walk(name, js, i % 16, (i * 5) % 16)
+    assert rc in (0, 200), (name, js, rc)
+    if rc == 200:
+        return False
+    est, ew = hsim.encode(name, js, i % 16, (i * 5) % 16)
+    assert est == 0 and out == ew, (name, js, est, ew.hex(), out.hex())
+    return True
+
+
+def test_walk_vectors_and_edges(hsim):
+    for name, js, wire in cases.K_REQUESTS:
+        rc, out = hsim.encode_walk(name, js, 3, 5)
+        assert rc == 0 and out.hex() == wire, (name, rc)
+    handled = sum(_check_walk(hsim, name, js, i) for i, (name, js, want) in enumerate(cases.ENCODE_EDGE))
+    assert handled > 20
+
+
+def test_walk_random_and_damaged(hsim):
+    rng = random.Random(29)
+    handled = 0
+    for i, (name, js) in enumerate(cases.random_encode_cases(150, seed0=5000)):
+        handled += _check_walk(hsim, name, js, i)
+        handled += _check_walk(hsim, name, cases.mutate_json(js, rng), i + 1)
+        handled += _check_walk(hsim, name, cases.mutate_json(cases.mutate_json(js, rng), rng), i + 2)
+    assert handled > 500
+
+
+def test_walk_structure_mutations(hsim):
+    """every single-character deletion / duplication / swap of a structural character of a small document:
+    the grammar checks of the tokenizer and the place kernel must never let a broken document through"""
+    name = "com.example.complex.ProcessNodeRequest"
+    js = b'{"root_node":{"children":[{"id":"a","value":"b"},{"children":[{"id":"c"}],"id":"d"},{"children":[]}],"id":"r","value":"v"}}'
+    n = 0
+    for i in range(len(js)):
+        if js[i:i + 1] in b'{}[]:,"':
+            for mut in (js[:i] + js[i + 1:], js[:i] + js[i:i + 1] + js[i:], js[:i] + b"," + js[i:], js[:i] + b":" + js[i:],
+                        js[:i] + b" " + js[i:], js[:i] + b"}" + js[i + 1:], js[:i] + b"]" + js[i + 1:]):
+                _check_walk(hsim, name, mut, i)
+                n += 1
+    assert n > 400
+
+
+def test_walk_bench_shapes(hsim):
+    import benchgen
+    names = {}
+
+    def mi(name):
+        names[hsim.msg(name)] = name
+        return hsim.msg(name)
+
+    for kind, n in (("nested", 250), ("flat", 100)):
+        wl = getattr(benchgen, kind)(n, mi)
+        blob = wl.req_json.tobytes()
+        handled = 0
+        for i in range(n):
+            js = blob[int(wl.req_off[i]):int(wl.req_off[i + 1])]
+            handled += _check_walk(hsim, names[int(wl.req_msg[i])], js, i)
+        assert handled == n, (kind, handled)
+
+
 # ---- lock-step reply side (ggr_coop.cuh) on 32 fibers -----------------------------------------
 def _check_coop_decode(hsim, name, w, i=0, flags=0):
     rc, out = hsim.decode_coop(name, w, flags, i % 16, (i * 5) % 16)
@@ -375,3 +438,33 @@ def test_request_envelope_numbers(oracle, hsim):
         handled += _check_request(oracle, hsim, body, it)
         accepted_by_oracle += oracle.request(body)["kind"] == 0
     assert handled == accepted_by_oracle and handled > 200  # nothing the reference accepts is left to the host here
+
+
+def test_mixed_replay_shapes(oracle, hsim):
+    """configs[4] (32 methods, Zipf sizes): the per-thread device code against the oracle on a sample, and the
+    token-parallel walker against the per-thread code"""
+    import benchgen
+    names = {}
+
+    def mi(name):
+        names[hsim.msg(name)] = name
+        return hsim.msg(name)
+
+    wl = benchgen.mixed(1500, mi)
+    assert len(set(wl.method.tolist())) >= 24  # the popular methods dominate, most of the 32 still show up
+    jb, wb = wl.req_json.tobytes(), wl.rep_wire.tobytes()
+    walked = 0
+    for i in range(wl.n):
+        js = jb[int(wl.req_off[i]):int(wl.req_off[i + 1])]
+        w = wb[int(wl.rep_off[i]):int(wl.rep_off[i + 1])]
+        if len(js) > 20000 or len(w) > 20000:
+            continue  # the large ones: GPU test
+        rn, pn = names[int(wl.req_msg[i])], names[int(wl.rep_msg[i])]
+        rc, ow, _ = oracle.encode(rn, js)
+        st, ew = hsim.encode(rn, js, i % 16, (i * 3) % 16)
+        assert rc == 0 and st == 0 and ew == ow, (rn, js[:300])
+        walked += _check_walk(hsim, rn, js, i)
+        rc, oj, _ = oracle.decode(pn, w)
+        st, ej = hsim.decode(pn, w, 0, i % 16, (i * 7) % 16)
+        assert rc == 0 and st == 0 and ej == oj, (pn, w.hex()[:300])
+    assert walked > 150  # floats, bytes, quoted numbers, timestamps: the fused kernel (profiles/README.md)
