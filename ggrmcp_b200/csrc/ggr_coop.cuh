@@ -21,11 +21,16 @@
 #include "ggr_decode.cuh"
 #include "ggr_warp.cuh"
 
+// Entry tables: every item owns GGR_COOP_TAB_ENTRIES slots of the saved table in HBM; the size pass works on a copy in
+// shared memory - 224 entries in the first tier (bench replies: 133 on average; 8.9 KB per warp with the masks below =
+// 24 warps per SM), the full 320 in the second tier, which takes the few items the first leaves because of the table
+// (one such item on the per-thread kernels costs half a millisecond of one lane: the tail of the whole batch).
+#define GGR_COOP_TAB_ENTRIES 320
 #ifndef GGR_COOP_ENTRIES
-#define GGR_COOP_ENTRIES 320
+#define GGR_COOP_ENTRIES 224
 #endif
 #define GGR_COOP_DEPTH 24
-#define GGR_COOP_MAX_WIRE 8192u  /* larger items: per-thread kernels */
+#define GGR_COOP_MAX_WIRE 4096u  /* larger items: no plain-text masks, strings are classified one by one */
 #define GGR_MODE_COOP 2u
 #define GGR_MODE_PENDING 0xFFu
 
@@ -57,16 +62,22 @@ struct CoopEnt {            // 32 bytes: saved between the passes as two 16-byte
 #define GGR_COOP_LONG 96u
 #define GGR_COOP_LONG_MAX 32u
 #define GGR_COOP_DIRTY_MAX 64u
-struct CoopShared {
-  CoopEnt ent[GGR_COOP_ENTRIES];
-  u16 order[GGR_COOP_ENTRIES];            // leaves bucketed by class
+template <int NE>
+struct CoopSharedT {
+  static const u32 ENTRIES = NE;
+  CoopEnt ent[NE];
+  union {
+    u16 order[NE];                        // R3: leaves bucketed by class
+    u16 queue[NE];                        // R1: message entries to scan, level by level (done before `order` is filled)
+  };
   u16 dmask[GGR_COOP_MAX_WIRE / 16 + 2];  // per 16-byte chunk: bytes that are not plain text
   u16 dpre[GGR_COOP_MAX_WIRE / 16 + 2];   // number of chunks with a nonzero mask before this one
   u32 cls_cnt[DC_N], cls_cur[DC_N];
   u32 n_ent, bail, n_leaf, max_depth, q_end, n_dirty;
-  u16 queue[GGR_COOP_ENTRIES];            // message entries to scan, level by level
   u16 dlist[GGR_COOP_DIRTY_MAX];          // strings that need escaping / validation: sized by the whole warp
 };
+typedef CoopSharedT<GGR_COOP_ENTRIES> CoopShared;      // first tier
+typedef CoopSharedT<GGR_COOP_TAB_ENTRIES> CoopSharedBig;  // second tier
 
 GGR_DEV u32 coop_class(const FieldD& f, bool ts, bool packed) {
   if (packed) return DC_PACKED;
@@ -133,7 +144,8 @@ GGR_DEV bool coop_wire_zero(const u8* b, u32 pos, u32 lim, u32 wt, bool* ok) {
 }
 
 // R1, one lane: scan the top-level fields of message entry `me` and append its children.
-GGR_DEV void coop_scan_message(CoopShared& S, const DecCtx& cx, u32 me) {
+template <class SH>
+GGR_DEV void coop_scan_message(SH& S, const DecCtx& cx, u32 me) {
   const Tables& T = cx.T;
   const u8* const in = cx.in;
   const CoopEnt m = S.ent[me];
@@ -216,7 +228,7 @@ GGR_DEV void coop_scan_message(CoopShared& S, const DecCtx& cx, u32 me) {
       }
     }
     const u32 slot = wp_atomic_add(&S.n_ent, 1u);
-    if (slot >= GGR_COOP_ENTRIES) { S.bail = 1; return; }
+    if (slot >= SH::ENTRIES) { S.bail = 1; return; }
     CoopEnt e;
     e.vpos = vpos;
     e.vend = vend;
@@ -268,7 +280,8 @@ GGR_DEV u32 coop_dirty_flags(u32 w) {
 }
 
 // R2, all lanes: dmask / dpre over the item's bytes [start, end)
-GGR_DEV void coop_plain_masks(CoopShared& S, const u8* in, u32 start, u32 end) {
+template <class SH>
+GGR_DEV void coop_plain_masks(SH& S, const u8* in, u32 start, u32 end) {
   const u32 lane = wp_lane();
   const u32 lt = (1u << lane) - 1u;
   const u32 nchunks = (end + 15u) >> 4;
@@ -292,7 +305,8 @@ GGR_DEV void coop_plain_masks(CoopShared& S, const u8* in, u32 start, u32 end) {
   WP_SYNC();
 }
 // no byte of [s, e) needs escaping or validation (s < e, within the masks' range)
-GGR_DEV bool coop_is_plain(const CoopShared& S, u32 s, u32 e) {
+template <class SH>
+GGR_DEV bool coop_is_plain(const SH& S, u32 s, u32 e) {
   const u32 c0 = s >> 4, c1 = (e - 1u) >> 4;
   u32 first = (u32)S.dmask[c0] & (0xFFFFu << (s & 15u));
   const u32 lastmask = 0xFFFFu >> (15u - ((e - 1u) & 15u));
@@ -479,7 +493,8 @@ GGR_DEV bool coop_plain_check(const u8* in, u32 s, u32 e) {
 }
 
 // R3, one lane: size of leaf entry ei (full text) added to its parent
-GGR_DEV void coop_size_leaf(CoopShared& S, const DecCtx& cx, u32 ei, bool have_masks) {
+template <class SH>
+GGR_DEV void coop_size_leaf(SH& S, const DecCtx& cx, u32 ei, bool have_masks) {
   const CoopEnt e = S.ent[ei];
   const FieldD f = ggr_field(cx.T, e.gfield);
   u32 n = coop_prefix_len(cx, e, f.name_len);
@@ -521,7 +536,8 @@ GGR_DEV void coop_size_leaf(CoopShared& S, const DecCtx& cx, u32 ei, bool have_m
 
 // R3, one lane: message entry `me` has the sizes of all its children; add its own text and
 // pass the total up
-GGR_DEV void coop_close_message(CoopShared& S, const DecCtx& cx, u32 me) {
+template <class SH>
+GGR_DEV void coop_close_message(SH& S, const DecCtx& cx, u32 me) {
   const CoopEnt m = S.ent[me];
   u32 n = 2;  // { }
   if (m.gfield != GGR_COOP_ROOT) {
@@ -535,7 +551,8 @@ GGR_DEV void coop_close_message(CoopShared& S, const DecCtx& cx, u32 me) {
 }
 
 // R3, one lane: message entry hands out offsets to its children
-GGR_DEV void coop_offsets_message(CoopShared& S, const DecCtx& cx, u32 me) {
+template <class SH>
+GGR_DEV void coop_offsets_message(SH& S, const DecCtx& cx, u32 me) {
   const CoopEnt m = S.ent[me];
   u32 pos = m.off;
   if (m.gfield != GGR_COOP_ROOT) {
@@ -554,7 +571,13 @@ GGR_DEV void coop_offsets_message(CoopShared& S, const DecCtx& cx, u32 me) {
 // groups would spend its time on the unaligned edges of every entry; plain byte stores into
 // shared memory have no edges.
 #define GGR_COOP_STAGE 8192u /* items with more text than this: per-thread kernels */
-struct CoopStage {
+struct
+#if defined(__CUDACC__)
+    __align__(16)
+#else
+    alignas(16)
+#endif
+        CoopStage {
   u8 buf[GGR_COOP_STAGE + 48];  // [pad, pad + size): pad = destination address & 15
   u32 lsrc[GGR_COOP_LONG_MAX], ldst[GGR_COOP_LONG_MAX], llen[GGR_COOP_LONG_MAX];
   u32 n_long, bad;
@@ -648,7 +671,8 @@ GGR_DEV int coop_write_entry(CoopStage& E, const DecCtx& cx, const CoopEnt& e, u
 // Size pass of one item, all lanes.  Returns true when the item was handled: *size is its text
 // size and, when `save` != nullptr, the entry table (n entries, *n_out) has been stored there for
 // the write pass.
-GGR_DEV bool coop_size_item(CoopShared& S, const DecCtx& cx, u32 root_msg, u32 start, u32 end, U4* save, u32* n_out, u32* size) {
+template <class SH>
+GGR_DEV bool coop_size_item(SH& S, const DecCtx& cx, u32 root_msg, u32 start, u32 end, U4* save, u32* n_out, u32* size) {
   const u32 lane = wp_lane();
   *size = 0;
   *n_out = 0;
@@ -764,7 +788,7 @@ GGR_DEV int coop_write_item(CoopStage& E, const DecCtx& cx, const U4* tab, u32 n
   const bool staged = size <= GGR_COOP_STAGE;
   const u32 pad = wp_align_pad(dst);
   if (n) wp_prefetch(cx.in, tab[0].y);  // entry 0 is the root: vend = end of the item
-  WP_SYNC();  // persistent warps: the previous item has been copied out
+  wp_copy_wait();  // persistent warps: the previous item's bulk copy has read the staging buffer
   if (lane == 0) {
     E.n_long = 0;
     E.bad = 0;

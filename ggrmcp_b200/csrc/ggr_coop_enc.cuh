@@ -1208,7 +1208,13 @@ GGR_DEV bool ce_parse_item(SH& S, const CeLut& lut, const Tables& T, u32 root_ms
 #define CE_LONG_STR 96u
 #define CE_LONG_MAX 32u
 #define CE_STAGE 8192u /* items with more wire bytes than this: per-thread emitter */
-struct CoopEmit {
+struct
+#if defined(__CUDACC__)
+    __align__(16)
+#else
+    alignas(16)
+#endif
+        CoopEmit {
   u8 buf[CE_STAGE + 48];  // [pad, pad + size): pad = destination address & 15
   u32 src[CE_LONG_MAX], dst[CE_LONG_MAX], len[CE_LONG_MAX];
   u32 n;
@@ -1342,7 +1348,7 @@ GGR_DEV void ce_emit_item(CoopEmit& E, const u8* in, u32 end, const u8* ir, cons
   const u32 lane = wp_lane();
   const u32 pad = wp_align_pad(dst);
   wp_prefetch(in, end);
-  WP_SYNC();  // persistent warps: the previous item has been copied out
+  wp_copy_wait();  // persistent warps: the previous item's bulk copy has read the staging buffer
   if (lane == 0) E.n = 0;
   WP_SYNC();
   for (u32 i = 1 + lane; i < n_nodes; i += 32) ce_emit_node(E, in, end, ir, ioff, i, pad);

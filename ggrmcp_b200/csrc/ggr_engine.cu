@@ -10,8 +10,10 @@
 // Items shard across GPUs by batch index on the caller's side (one engine per device); there is
 // no cross-GPU exchange on this path.
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <chrono>
@@ -138,6 +140,8 @@ struct Slot {
 struct ggr_engine {
   int device = 0;
   int sm_count = 148;
+  int numa_node = -1;            // of the GPU's PCI function (sysfs), -1 unknown
+  std::vector<int> node_cpus;    // CPUs of that node
   ggr::WireOrder order = ggr::ORDER_FIELD_NUMBER;
   cudaStream_t stream = nullptr;
   std::string err;
@@ -215,7 +219,108 @@ static bool ensure(ggr_engine* e, DevBuf& b, size_t bytes) {
   return true;
 }
 
+// ---- NUMA placement of the host side (no libnuma in the image: sysfs + sched_setaffinity + first touch) ----
+static std::vector<int> parse_cpulist(const char* path) {
+  std::vector<int> cpus;
+  FILE* f = fopen(path, "r");
+  if (!f) return cpus;
+  char buf[4096];
+  if (fgets(buf, sizeof buf, f)) {
+    const char* p = buf;
+    while (*p) {
+      char* end;
+      long a = strtol(p, &end, 10);
+      if (end == p) break;
+      long b = a;
+      if (*end == '-') {
+        p = end + 1;
+        b = strtol(p, &end, 10);
+      }
+      for (long c = a; c <= b && c < 4096; c++) cpus.push_back((int)c);
+      p = *end == ',' ? end + 1 : end;
+      if (*end != ',') break;
+    }
+  }
+  fclose(f);
+  return cpus;
+}
+static void find_numa(ggr_engine* e) {
+  char bdf[32] = {0};
+  if (cudaDeviceGetPCIBusId(bdf, sizeof bdf, e->device) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  for (char* c = bdf; *c; c++)
+    if (*c >= 'A' && *c <= 'Z') *c = (char)(*c - 'A' + 'a');
+  char path[128];
+  snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bdf);
+  FILE* f = fopen(path, "r");
+  if (!f) return;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  if (node < 0) return;
+  snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+  std::vector<int> cpus = parse_cpulist(path);
+  if (cpus.empty()) return;
+  e->numa_node = node;
+  e->node_cpus = cpus;
+}
+// binds the calling thread to the GPU's node for the lifetime of the object (old mask restored)
+struct NodeBind {
+  cpu_set_t old;
+  bool active = false;
+  explicit NodeBind(const ggr_engine* e) {
+    if (e->node_cpus.empty() || sched_getaffinity(0, sizeof old, &old) != 0) return;
+    cpu_set_t want;
+    CPU_ZERO(&want);
+    int n = 0;
+    for (int c : e->node_cpus)
+      if (c < CPU_SETSIZE && CPU_ISSET(c, &old)) {  // stay inside what the process may use (containers, taskset)
+        CPU_SET(c, &want);
+        n++;
+      }
+    if (n && sched_setaffinity(0, sizeof want, &want) == 0) active = true;
+  }
+  ~NodeBind() {
+    if (active) sched_setaffinity(0, sizeof old, &old);
+  }
+};
+
 extern "C" {
+
+int ggr_device_numa_node(const ggr_engine* e) { return e ? e->numa_node : -1; }
+int ggr_bind_thread_to_device(const ggr_engine* e) {
+  if (!e) return GGR_ERR_INVALID_ARGUMENT;
+  if (e->node_cpus.empty()) return GGR_SUCCESS;  // nothing known: leave the thread alone
+  cpu_set_t old, want;
+  if (sched_getaffinity(0, sizeof old, &old) != 0) return GGR_SUCCESS;
+  CPU_ZERO(&want);
+  int n = 0;
+  for (int c : e->node_cpus)
+    if (c < CPU_SETSIZE && CPU_ISSET(c, &old)) {
+      CPU_SET(c, &want);
+      n++;
+    }
+  if (n) sched_setaffinity(0, sizeof want, &want);
+  return GGR_SUCCESS;
+}
+int ggr_host_alloc(ggr_engine* e, size_t bytes, void** out) {
+  if (!e || !out) return GGR_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  DeviceGuard dg(e->device);
+  NodeBind nb(e);  // first touch decides the node of the pages: allocate and touch from the GPU's node
+  void* p = nullptr;
+  if (!cuda_ok(e, cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault), "cudaHostAlloc")) return GGR_ERR_CUDA;
+  for (size_t o = 0; o < bytes; o += 4096) ((volatile char*)p)[o] = 0;
+  *out = p;
+  return GGR_SUCCESS;
+}
+void ggr_host_free(ggr_engine* e, void* p) {
+  if (!e || !p) return;
+  DeviceGuard dg(e->device);
+  cudaFreeHost(p);
+}
 
 const char* ggr_status_string(int32_t st) {
   static const char* names[] = {"ok", "syntax", "unknown_field", "invalid_value", "range", "invalid_utf8", "duplicate",
@@ -242,6 +347,7 @@ int ggr_engine_create(const ggr_config* cfg, ggr_engine** out) {
   e->device = dev;
   cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, dev);
   if (e->sm_count <= 0) e->sm_count = 148;
+  find_numa(e);
   if (const char* nc = getenv("GGR_COOP")) e->use_coop = nc[0] != '0';
   if (const char* nc = getenv("GGR_COOP_ENC")) e->use_coop_enc = nc[0] != '0';
   if (const char* nc = getenv("GGR_WALK")) e->use_walk = nc[0] != '0';
@@ -411,6 +517,25 @@ int ggr_profile_read(ggr_engine* e, double* ms, uint64_t* launches) {
   return GGR_SUCCESS;
 }
 
+// Debug aid (not part of the public header): per-item path of the last device-buffer reply batch - 2 = lock-step
+// kernels, anything else = per-thread kernels - and the request side's list lengths {lock-step, left by the walker,
+// per-thread}.  Synchronizes the device.
+int ggr_debug_paths(ggr_engine* e, int64_t n, uint32_t* reply_mode, uint32_t* request_counts) {
+  if (!e) return GGR_ERR_INVALID_ARGUMENT;
+  DeviceGuard dg(e->device);
+  cudaDeviceSynchronize();
+  if (reply_mode && e->dev_sc[1].aux.p && e->dev_sc[1].aux.cap >= (size_t)n * 4)
+    cudaMemcpy(reply_mode, e->dev_sc[1].aux.p, (size_t)n * 4, cudaMemcpyDeviceToHost);
+  if (request_counts && e->dev_sc[0].pend.p) {
+    uint32_t c[16];
+    cudaMemcpy(c, e->dev_sc[0].pend.p, sizeof c, cudaMemcpyDeviceToHost);
+    request_counts[0] = c[0];
+    request_counts[1] = c[4];
+    request_counts[2] = c[8];
+  }
+  return GGR_SUCCESS;
+}
+
 int ggr_synchronize(ggr_engine* e) {
   if (!e) return GGR_ERR_INVALID_ARGUMENT;
   cudaSetDevice(e->device);
@@ -431,6 +556,7 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
   if (encode && !ensure(e, sc.ir, (size_t)in_bytes * 8 + (size_t)n * 128 + 256)) return GGR_ERR_CUDA;
   u32 n_msgs = (u32)s->cs.msg_names.size();
   const bool prof = e->profiling && e->ev_used + 16 <= 65536;
+  const u32 frame = (encode && (flags & GGR_F_GRPC_FRAME)) ? 5u : 0u;  // request side: message header in front of every item
   size_t m0 = 0, m1 = 0, m2 = 0, m3 = 0, mx = 0;
   bool have_mx = false;
   if (prof) prof_mark(e, st, &m0);
@@ -479,6 +605,7 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
       ggr_launch_encode_parse(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
                               (u32*)sc.aux.p, status, (u64*)sc.sums.p, pend2, counters + 8);
       if (prof) prof_mark(e, st, &c1);
+      if (frame) ggr_launch_frame_sizes(st, n, (u32*)sc.size.p, status);
       ggr_launch_block_sums(st, (unsigned)nb, n, (const u32*)sc.size.p, (u64*)sc.sums.p);
       if (prof) {
         e->spans.push_back({11, m0, t1});  // router + token index
@@ -491,13 +618,17 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
     } else {
       ggr_launch_encode_parse(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
                               (u32*)sc.aux.p, status, (u64*)sc.sums.p, nullptr, nullptr);
+      if (frame) {
+        ggr_launch_frame_sizes(st, n, (u32*)sc.size.p, status);
+        ggr_launch_block_sums(st, (unsigned)nb, n, (const u32*)sc.size.p, (u64*)sc.sums.p);
+      }
       if (prof) prof_mark(e, st, &m1);
     }
     k_scan_blocks<<<1, 1024, 0, st>>>((u64*)sc.sums.p, nb, out_off + n);
     if (prof) prof_mark(e, st, &m2);
     ggr_launch_encode_emit(st, (unsigned)nb, n, in, in_off, (const u8*)sc.ir.p, (const u32*)sc.size.p,
                            (const u32*)sc.aux.p, status, (const u64*)sc.sums.p, out, out_cap, out_off,
-                           e->use_coop_enc ? (const u32*)sc.nn.p : nullptr);
+                           e->use_coop_enc ? (const u32*)sc.nn.p : nullptr, frame);
     if (e->use_coop_enc) {
       size_t x1 = 0;
       if (prof) {
@@ -506,7 +637,7 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
       }
       ggr_launch_encode_coop_emit(st, n, in, in_off, (const u8*)sc.ir.p, (const u32*)sc.ioff.p, (const u32*)sc.nn.p,
                                   (const u32*)sc.size.p, status, out, out_off, e->sm_count, (const u32*)sc.pend.p + 16,
-                                  (const u32*)sc.pend.p);
+                                  (const u32*)sc.pend.p, frame);
       if (prof) {
         prof_mark(e, st, &x1);
         e->spans.push_back({10, mx, x1});
@@ -520,14 +651,14 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
     size_t c0 = 0, c1 = 0;
     if (coop) {
       if (!ensure(e, sc.ir, ggr_decode_coop_table_bytes(n)) || !ensure(e, sc.nn, (size_t)n * 4) ||
-          !ensure(e, sc.pend, (size_t)n * 4 + 64))
+          !ensure(e, sc.pend, (size_t)n * 8 + 64))
         return GGR_ERR_CUDA;
       u32* counters = (u32*)sc.pend.p;
       u32* big = counters + 16;
       if (!cuda_ok(e, cudaMemsetAsync(counters, 0, 64, st), "memset")) return GGR_ERR_CUDA;
       k_route<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, in_off, e->min_wire, 0x3FFFFF00u, big, counters, nullptr, nullptr, (u32*)sc.aux.p);
       ggr_launch_decode_coop_size(st, n, s->d_blob, n_msgs, msg_id, in, in_off, flags, (u32*)sc.size.p, (u32*)sc.aux.p, status,
-                                  sc.ir.p, (u32*)sc.nn.p, e->sm_count, big, counters);
+                                  sc.ir.p, (u32*)sc.nn.p, e->sm_count, big, counters, big + n, counters + 4);
       if (prof) {
         prof_mark(e, st, &c0);
         e->spans.push_back({6, m0, c0});
@@ -552,7 +683,7 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
         e->spans.push_back({5, m2, c1});
         e->spans.push_back({7, c1, m3});
       }
-      e->launches += 6;
+      e->launches += 7;
       return cuda_ok(e, cudaGetLastError(), "kernel launch") ? GGR_SUCCESS : GGR_ERR_CUDA;
     }
   }
@@ -617,9 +748,9 @@ static int run_request_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, int6
   ggr_launch_block_sums(st, (unsigned)nb, n, (const u32*)sc.size.p, (u64*)sc.sums.p);
   k_scan_blocks<<<1, 1024, 0, st>>>((u64*)sc.sums.p, nb, out_off + n);
   ggr_launch_encode_emit(st, (unsigned)nb, n, in, in_off, (const u8*)sc.ir.p, (const u32*)sc.size.p, (const u32*)sc.aux.p, status,
-                         (const u64*)sc.sums.p, out, out_cap, out_off, (const u32*)sc.nn.p);
+                         (const u64*)sc.sums.p, out, out_cap, out_off, (const u32*)sc.nn.p, 0);
   ggr_launch_encode_coop_emit(st, n, in, in_off, (const u8*)sc.ir.p, (const u32*)sc.ioff.p, (const u32*)sc.nn.p, (const u32*)sc.size.p,
-                              status, out, out_off, e->sm_count, big, counters);
+                              status, out, out_off, e->sm_count, big, counters, 0);
   e->launches += 9;
   return cuda_ok(e, cudaGetLastError(), "kernel launch") ? GGR_SUCCESS : GGR_ERR_CUDA;
 }
@@ -661,6 +792,7 @@ static int run_wrap_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, int64_t
 // stream per engine and the size does not travel by copy.  The caller's buffers should be pinned.
 static bool slot_init(ggr_engine* e, Slot& sl) {
   if (sl.st) return true;
+  NodeBind nb(e);
   if (!cuda_ok(e, cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking), "cudaStreamCreate") ||
       !cuda_ok(e, cudaEventCreateWithFlags(&sl.ready, cudaEventDisableTiming), "cudaEventCreate") ||
       !cuda_ok(e, cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming), "cudaEventCreate") ||

@@ -5,15 +5,18 @@
 #include "ggr_coop.cuh"
 
 #define COOP_WARPS 4
-#define COOP_TAB_U4 (2 * GGR_COOP_ENTRIES) /* 16-byte words of table space per item */
+#define COOP_TAB_U4 (2 * GGR_COOP_TAB_ENTRIES) /* 16-byte words of table space per item */
 
+// SH: the per-warp working set; the first tier (small tables, 24 warps per SM) appends what it leaves to `pending`,
+// the second tier (full tables) runs over that list and leaves the rest to the per-thread kernels (mode PENDING).
+template <class SH>
 __global__ void __launch_bounds__(COOP_WARPS * 32)
 k_decode_coop_size(const u8* __restrict__ blob, long long n, u32 n_msgs, const i32* __restrict__ msg_id,
                    const u8* __restrict__ in, const u64* __restrict__ in_off, u32 flags, u32* __restrict__ size,
                    u32* __restrict__ mode, i32* __restrict__ status, U4* __restrict__ tab, u32* __restrict__ nent,
-                   const u32* __restrict__ list, const u32* __restrict__ list_n) {
+                   const u32* __restrict__ list, const u32* __restrict__ list_n, u32* __restrict__ pending, u32* __restrict__ n_pending) {
   extern __shared__ __align__(16) unsigned char smem[];
-  CoopShared* S = reinterpret_cast<CoopShared*>(smem);
+  SH* S = reinterpret_cast<SH*>(smem);
   const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   DecCtx cx;
   cx.T = ggr_tables(blob);
@@ -21,15 +24,30 @@ k_decode_coop_size(const u8* __restrict__ blob, long long n, u32 n_msgs, const i
   // the items of `list` (the router's choice: not too small, not too large); mode[] is PENDING for all others
   const long long total = (long long)*list_n;
   u32* ticket = const_cast<u32*>(list_n) + 1;  // zeroed with the list length; +2 is the write kernel's
+  // two tickets in flight: the wire bytes of the item after the current one are asked for in L2 (bulk prefetch)
   u32 drawn = wp_ticket_draw(ticket);
-  for (long long slot = wp_ticket_take(drawn); slot < total; slot = wp_ticket_take(drawn)) {
+  long long slot = wp_ticket_take(drawn);
+  drawn = wp_ticket_draw(ticket);
+  while (slot < total) {
+    const long long next = wp_ticket_take(drawn);
     drawn = wp_ticket_draw(ticket);
+    if (next < total) {
+      const long long it2 = (long long)list[next];
+      const u64 a2 = in_off[it2], b2 = in_off[it2 + 1];
+      if (b2 > a2 && b2 - a2 < (1ull << 20)) wp_prefetch_l2(in + a2, (u32)(b2 - a2));
+    }
     const long long item = (long long)list[slot];
-    const u64 a = in_off[item], b = in_off[item + 1];
+    u64 a = in_off[item];
+    const u64 b = in_off[item + 1];
     const i32 m = msg_id[item];
     bool ok = false;
     u32 sz = 0, ne = 0;
-    if (m >= 0 && (u32)m < n_msgs && b >= a && b - a <= 0x3FFFFF00ull) {
+    bool framed_ok = true;
+    if (flags & GGR_DF_GRPC_FRAME) {  // a bad header: the per-thread kernel reports it
+      framed_ok = b >= a && ggr_frame_check(in, a, b) == GST_OK;
+      a += GGR_FRAME_BYTES;
+    }
+    if (framed_ok && m >= 0 && (u32)m < n_msgs && b >= a && b - a <= 0x3FFFFF00ull) {
       cx.in = in + (a & ~15ull);
       const u32 s0 = (u32)(a & 15ull);
       ok = coop_size_item(S[warp], cx, (u32)m, s0, s0 + (u32)(b - a), tab + (size_t)item * COOP_TAB_U4, &ne, &sz);
@@ -43,8 +61,10 @@ k_decode_coop_size(const u8* __restrict__ blob, long long n, u32 n_msgs, const i
       } else {
         mode[item] = GGR_MODE_PENDING;
         nent[item] = 0;
+        if (pending) pending[atomicAdd(n_pending, 1u)] = (u32)item;
       }
     }
+    slot = next;
   }
 }
 
@@ -63,30 +83,46 @@ k_decode_coop_write(const u8* __restrict__ blob, long long n, const u8* __restri
   const long long total = (long long)*list_n;
   u32* ticket = const_cast<u32*>(list_n) + 2;
   u32 drawn = wp_ticket_draw(ticket);
-  for (long long slot = wp_ticket_take(drawn); slot < total; slot = wp_ticket_take(drawn)) {
+  long long slot = wp_ticket_take(drawn);
+  drawn = wp_ticket_draw(ticket);
+  for (long long next = 0; slot < total; slot = next) {
+    next = wp_ticket_take(drawn);
     drawn = wp_ticket_draw(ticket);
+    if (next < total) {  // the next item's saved table and wire bytes: bulk prefetch into L2
+      const long long it2 = (long long)list[next];
+      const u32 ne2 = nent[it2];
+      const u64 a2 = in_off[it2], b2 = in_off[it2 + 1];
+      if (ne2 && b2 > a2 && b2 - a2 < (1ull << 20)) {
+        wp_prefetch_l2(in + a2, (u32)(b2 - a2));
+        wp_prefetch_l2(tab + (size_t)it2 * COOP_TAB_U4, ne2 * 32u);
+      }
+    }
     const long long item = (long long)list[slot];
     if (mode[item] != GGR_MODE_COOP || status[item] != GST_OK) continue;
-    const u64 a = in_off[item];
+    const u64 a = in_off[item] + ((flags & GGR_DF_GRPC_FRAME) ? GGR_FRAME_BYTES : 0u);
     cx.in = in + (a & ~15ull);
     int ws = coop_write_item(E[warp], cx, tab + (size_t)item * COOP_TAB_U4, nent[item], out + out_off[item], size[item]);
     if (ws != GST_OK && lane == 0) status[item] = GST_INTERNAL;
   }
+  wp_copy_drain();  // the staging buffers must outlive the bulk copies that read them
 }
 
-static size_t coop_smem_bytes() { return sizeof(CoopShared) * COOP_WARPS; }
+template <class SH>
+static size_t coop_smem_bytes() { return sizeof(SH) * COOP_WARPS; }
 size_t ggr_decode_coop_table_bytes(long long n) { return (size_t)n * COOP_TAB_U4 * 16; }
 int ggr_decode_coop_init() {
-  cudaError_t a = cudaFuncSetAttribute(k_decode_coop_size, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem_bytes());
+  cudaError_t a = cudaFuncSetAttribute(k_decode_coop_size<CoopShared>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem_bytes<CoopShared>());
+  if (cudaFuncSetAttribute(k_decode_coop_size<CoopSharedBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem_bytes<CoopSharedBig>()) != cudaSuccess) return -1;
   cudaError_t b = cudaFuncSetAttribute(k_decode_coop_write, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(sizeof(CoopStage) * COOP_WRITE_WARPS));
   return (a == cudaSuccess && b == cudaSuccess) ? 0 : -1;
 }
+template <class SH>
 static unsigned coop_grid(long long n, int sm_count) {
-  // resident blocks per SM: what the entry tables in shared memory allow (4 with 320 entries per warp)
+  // resident blocks per SM: what the entry tables in shared memory allow (6 with 224 entries per warp, 4 with 320)
   static int per_sm = 0;
   if (per_sm == 0 &&
-      (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_coop_size, COOP_WARPS * 32, coop_smem_bytes()) != cudaSuccess ||
+      (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_coop_size<SH>, COOP_WARPS * 32, coop_smem_bytes<SH>()) != cudaSuccess ||
        per_sm < 1))
     per_sm = 4;
   long long want = (n + COOP_WARPS - 1) / COOP_WARPS, cap = (long long)sm_count * per_sm;
@@ -96,9 +132,12 @@ static unsigned coop_grid(long long n, int sm_count) {
 void ggr_launch_decode_coop_size(cudaStream_t st, long long n, const uint8_t* blob, uint32_t n_msgs, const int32_t* msg_id,
                                  const uint8_t* in, const uint64_t* in_off, uint32_t flags, uint32_t* size, uint32_t* mode,
                                  int32_t* status, void* tab, uint32_t* nent, int sm_count, const uint32_t* list,
-                                 const uint32_t* list_n) {
-  k_decode_coop_size<<<coop_grid(n, sm_count), COOP_WARPS * 32, coop_smem_bytes(), st>>>(
-      blob, n, n_msgs, msg_id, in, (const u64*)in_off, flags, size, mode, status, (U4*)tab, nent, list, list_n);
+                                 const uint32_t* list_n, uint32_t* pending, uint32_t* n_pending) {
+  // first tier over the router's list, second tier (full tables; its list length lives on the device) over what is left
+  k_decode_coop_size<CoopShared><<<coop_grid<CoopShared>(n, sm_count), COOP_WARPS * 32, coop_smem_bytes<CoopShared>(), st>>>(
+      blob, n, n_msgs, msg_id, in, (const u64*)in_off, flags, size, mode, status, (U4*)tab, nent, list, list_n, pending, n_pending);
+  k_decode_coop_size<CoopSharedBig><<<(unsigned)sm_count, COOP_WARPS * 32, coop_smem_bytes<CoopSharedBig>(), st>>>(
+      blob, n, n_msgs, msg_id, in, (const u64*)in_off, flags, size, mode, status, (U4*)tab, nent, pending, n_pending, nullptr, nullptr);
 }
 void ggr_launch_decode_coop_write(cudaStream_t st, long long n, const uint8_t* blob, const uint8_t* in, const uint64_t* in_off,
                                   uint32_t flags, const uint32_t* size, const uint32_t* mode, int32_t* status, const void* tab,

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(CE_WARPS * 32)
 k_encode_coop_emit(long long n, const u8* __restrict__ in, const u64* __restrict__ in_off, const u8* __restrict__ ir,
                    const u32* __restrict__ ioff, const u32* __restrict__ nnodes, const u32* __restrict__ size,
                    const i32* __restrict__ status, u8* __restrict__ out, const u64* __restrict__ out_off,
-                   const u32* __restrict__ list, const u32* __restrict__ list_n) {
+                   const u32* __restrict__ list, const u32* __restrict__ list_n, u32 frame) {
   extern __shared__ __align__(16) unsigned char smem[];
   CoopEmit* E = reinterpret_cast<CoopEmit*>(smem);
   const u32 warp = threadIdx.x >> 5;
@@ -121,16 +121,32 @@ k_encode_coop_emit(long long n, const u8* __restrict__ in, const u64* __restrict
   // fixed stride here: an item takes a few microseconds, tickets for 150 K of them in a millisecond
   // run into the rate of atomics on one address (measured: 1.15 ms with the stride, 1.23 ms by ticket)
   for (long long slot = (long long)blockIdx.x * CE_WARPS + warp; slot < total; slot += (long long)gridDim.x * CE_WARPS) {
+    {  // the item this warp takes next: text, IR nodes and offsets asked for in L2 with bulk prefetches
+      const long long nslot = slot + (long long)gridDim.x * CE_WARPS;
+      if (nslot < total) {
+        const long long it2 = (long long)list[nslot];
+        const u32 nw2 = nnodes[it2];
+        const u64 a2 = in_off[it2], b2 = in_off[it2 + 1];
+        if ((nw2 & 0xFFFFu) > 1u && b2 > a2) {
+          const u64 no2 = ((a2 - a0) >> 1) + 8ull * (u64)it2 + (u64)(nw2 >> 16);
+          wp_prefetch_l2(in + a2, (u32)(b2 - a2));
+          wp_prefetch_l2(ir + no2 * 16, (nw2 & 0xFFFFu) * 16u);
+          wp_prefetch_l2(ioff + no2, (nw2 & 0xFFFFu) * 4u);
+        }
+      }
+    }
     const long long item = (long long)list[slot];
     const u32 nw = nnodes[item];
     const u32 nn = nw & 0xFFFFu;  // node count | index of the first node within the region << 16 (ggr_walk.cuh)
     const u32 sz = size[item];
-    if (nn <= 1 || sz == 0 || status[item] != GST_OK) continue;
+    if (nn <= 1 || sz <= frame || status[item] != GST_OK) continue;
     const u64 a = in_off[item], b = in_off[item + 1];
     const u64 node_off = ((a - a0) >> 1) + 8ull * (u64)item + (u64)(nw >> 16);
+    // frame: the 5-byte message header in front of the payload was written by k_encode_emit
     ce_emit_item(E[warp], in + (a & ~15ull), (u32)(a & 15ull) + (u32)(b - a), ir + node_off * 16, ioff + node_off, nn,
-                 out + out_off[item], sz);
+                 out + out_off[item] + frame, sz - frame);
   }
+  wp_copy_drain();  // the staging buffers must outlive the bulk copies that read them
 }
 
 template <class SH>
@@ -193,9 +209,9 @@ void ggr_launch_encode_coop_parse(cudaStream_t st, int tier, long long n, const 
 void ggr_launch_encode_coop_emit(cudaStream_t st, long long n, const uint8_t* in, const uint64_t* in_off, const uint8_t* ir,
                                  const uint32_t* ioff, const uint32_t* nnodes, const uint32_t* size, const int32_t* status,
                                  uint8_t* out, const uint64_t* out_off, int sm_count, const uint32_t* list,
-                                 const uint32_t* list_n) {
+                                 const uint32_t* list_n, uint32_t frame) {
   long long want = (n + CE_WARPS - 1) / CE_WARPS, cap = (long long)sm_count * 6;
   unsigned nb = (unsigned)(want < cap ? want : cap);
   k_encode_coop_emit<<<nb, CE_WARPS * 32, sizeof(CoopEmit) * CE_WARPS, st>>>(n, in, (const u64*)in_off, ir, ioff, nnodes, size, status, out,
-                                                                             (const u64*)out_off, list, list_n);
+                                                                             (const u64*)out_off, list, list_n, frame);
 }

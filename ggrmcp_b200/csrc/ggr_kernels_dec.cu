@@ -25,6 +25,11 @@ k_decode_size(const u8* __restrict__ blob, long long n, u32 n_msgs, const i32* _
       if (m < 0 || (u32)m >= n_msgs || b < a) st = GST_UNSUPPORTED;
       else if (b - a > 0x7FFFFFF0ull) st = GST_TOO_LARGE;
       else active = true;
+      if (active && (flags & GGR_DF_GRPC_FRAME)) {  // 0x00 | length (big endian) | message
+        st = ggr_frame_check(in, a, b);
+        active = st == GST_OK;
+        a += GGR_FRAME_BYTES;
+      }
     }
   }
   DecResult res;
@@ -76,7 +81,7 @@ k_decode_write(const u8* __restrict__ blob, long long n, const i32* __restrict__
         md = mode[i];
         if (md != 2u /* GGR_MODE_COOP: written by k_decode_coop_write */) {
           active = true;
-          a = in_off[i];
+          a = in_off[i] + ((flags & GGR_DF_GRPC_FRAME) ? GGR_FRAME_BYTES : 0u);
           b = in_off[i + 1];
           m = msg_id[i];
         }

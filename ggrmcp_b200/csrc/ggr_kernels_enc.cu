@@ -67,11 +67,17 @@ __global__ void __launch_bounds__(GGR_BLOCK) k_block_sums(long long n, const u32
   if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
 }
 
+// GGR_F_GRPC_FRAME: every item that encoded takes 5 more bytes (the message header); runs behind all parsers
+__global__ void __launch_bounds__(256) k_frame_sizes(long long n, u32* __restrict__ size, const i32* __restrict__ status) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i < n && status[i] == GST_OK) size[i] += GGR_FRAME_BYTES;
+}
+
 __global__ void __launch_bounds__(GGR_BLOCK)
 k_encode_emit(long long n, const u8* __restrict__ in, const u64* __restrict__ in_off, const u8* __restrict__ ir,
               const u32* __restrict__ size, const u32* __restrict__ first, i32* __restrict__ status,
               const u64* __restrict__ block_prefix, u8* __restrict__ out, u64 out_cap, u64* __restrict__ out_off,
-              const u32* __restrict__ skip) {
+              const u32* __restrict__ skip, u32 frame) {
   long long i = (long long)blockIdx.x * GGR_BLOCK + threadIdx.x;
   u32 sz = i < n ? size[i] : 0;
   u32 tot;
@@ -85,7 +91,7 @@ k_encode_emit(long long n, const u8* __restrict__ in, const u64* __restrict__ in
     if (sz != 0 && status[i] == GST_OK) {
       if (off + sz > out_cap) {
         status[i] = GST_NO_SPACE;
-      } else if (skip && skip[i] > 1u) {
+      } else if (skip && (skip[i] & 0xFFFFu) > 1u) {  // node count | first node << 16
         // written by the lock-step emitter (k_encode_coop_emit)
       } else {
         active = true;
@@ -98,12 +104,22 @@ k_encode_emit(long long n, const u8* __restrict__ in, const u64* __restrict__ in
   u64 node_off = active ? ((a - in_off[0]) >> 1) + 8ull * (u64)i : 0ull;
   const u8* base = in + (a & ~15ull);
   u32 s0 = (u32)(a & 15ull);
+  if (frame && i < n && sz != 0 && status[i] == GST_OK) {  // message header: every framed item, whoever writes its payload
+    const u32 len = sz - frame;
+    u8* h = out + off;
+    h[0] = 0;
+    h[1] = (u8)(len >> 24);
+    h[2] = (u8)(len >> 16);
+    h[3] = (u8)(len >> 8);
+    h[4] = (u8)len;
+  }
+  const u64 poff = off + frame;
   Wr w;
-  w.init(out + (off & ~7ull), (u32)(off & 7ull));
+  w.init(out + (poff & ~7ull), (u32)(poff & 7ull));
   encode_emit(base, s0 + (u32)(b - a), ir + node_off * 16, fst, w, active, GGR_FULL_MASK);
   if (active) {
     w.finish();
-    if (w.pos != (u32)(off & 7ull) + sz) status[i] = GST_INTERNAL;
+    if (w.pos != (u32)(poff & 7ull) + sz - frame) status[i] = GST_INTERNAL;
   }
 }
 
@@ -118,7 +134,10 @@ void ggr_launch_block_sums(cudaStream_t st, unsigned nb, long long n, const uint
 }
 void ggr_launch_encode_emit(cudaStream_t st, unsigned nb, long long n, const uint8_t* in, const uint64_t* in_off, const uint8_t* ir,
                             const uint32_t* size, const uint32_t* first, int32_t* status, const uint64_t* block_prefix,
-                            uint8_t* out, uint64_t out_cap, uint64_t* out_off, const uint32_t* skip) {
-  k_encode_emit<<<nb, GGR_BLOCK, 0, st>>>(n, in, (const u64*)in_off, ir, size, first, status, (const u64*)block_prefix, out, (u64)out_cap, (u64*)out_off, skip);
+                            uint8_t* out, uint64_t out_cap, uint64_t* out_off, const uint32_t* skip, uint32_t frame) {
+  k_encode_emit<<<nb, GGR_BLOCK, 0, st>>>(n, in, (const u64*)in_off, ir, size, first, status, (const u64*)block_prefix, out, (u64)out_cap, (u64*)out_off, skip, frame);
+}
+void ggr_launch_frame_sizes(cudaStream_t st, long long n, uint32_t* size, const int32_t* status) {
+  k_frame_sizes<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, size, status);
 }
 const void* ggr_kernel_encode_parse() { return (const void*)k_encode_parse; }

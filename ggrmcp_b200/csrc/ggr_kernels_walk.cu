@@ -75,9 +75,26 @@ k_encode_type(const u8* __restrict__ blob, u32 n_msgs, const i32* __restrict__ m
   const Tables T = ggr_tables(blob);
   const u64 a0 = in_off[0];
   u32* ticket = const_cast<u32*>(list_n) + 2;  // +1 the tokenizer, +3 the place kernel
+  // two tickets in flight: the item after the current one is known when the current one starts, and its token
+  // index, records and text are asked for in L2 (the phases below are chains of small dependent loads)
   u32 drawn = wp_ticket_draw(ticket);
-  for (long long slot = wp_ticket_take(drawn); slot < total; slot = wp_ticket_take(drawn)) {
+  long long slot = wp_ticket_take(drawn);
+  drawn = wp_ticket_draw(ticket);
+  while (slot < total) {
+    const long long next = wp_ticket_take(drawn);
     drawn = wp_ticket_draw(ticket);
+    if (next < total) {
+      const long long it2 = (long long)list[next];
+      const u64 a2 = in_off[it2], b2 = in_off[it2 + 1];
+      if (b2 > a2 && b2 - a2 <= (u64)CE_MAX_INPUT - 16u) {
+        const u64 no2 = ((a2 - a0) >> 1) + 8ull * (u64)it2;
+        const u32 cap2 = (u32)((((b2 - a0) >> 1) + 8ull * (u64)(it2 + 1)) - no2);
+        const u32 len2 = (u32)(b2 - a2);
+        wp_prefetch_l2(in + a2, len2);
+        wp_prefetch_l2(ir + no2 * 16, len2 + (len2 >> 1) + 64u);                       // header, tokens, records (typical sizes)
+        wp_prefetch_l2(ir + (no2 + cap2) * 16 - (len2 + (len2 >> 2)), len2 + (len2 >> 2));  // quote entries, from the end of the region
+      }
+    }
     const long long item = (long long)list[slot];
     const u64 a = in_off[item], b = in_off[item + 1];
     const i32 m = msg_id[item];
@@ -105,6 +122,7 @@ k_encode_type(const u8* __restrict__ blob, u32 n_msgs, const i32* __restrict__ m
         pending[atomicAdd(n_pending, 1u)] = (u32)item;
       }
     }
+    slot = next;
   }
 }
 

@@ -345,6 +345,15 @@ GGR_DEV FieldD ggr_field(const Tables& t, u32 idx) {
 }
 GGR_DEV u32 ggr_u16(const Tables& t, u32 idx) { return ggr_ld2(t.u16s + (size_t)idx * 2); }
 
+// gRPC message header in front of item [a, b): GST_OK, or why the item cannot be taken
+GGR_DEV int ggr_frame_check(const u8* in, u64 a, u64 b) {
+  if (b - a < 5ull) return GST_BAD_WIRE;
+  const u8* p = in + a;
+  if (p[0] == 1u) return GST_UNSUPPORTED;  // compressed message
+  if (p[0] != 0u) return GST_BAD_WIRE;
+  const u64 len = ((u64)p[1] << 24) | ((u64)p[2] << 16) | ((u64)p[3] << 8) | (u64)p[4];
+  return len == b - a - 5ull ? GST_OK : GST_BAD_WIRE;
+}
 GGR_DEV bool ggr_is_ws(u32 c) { return c == ' ' || c == '\n' || c == '\r' || c == '\t'; }
 // protobuf-go internal/encoding/json isNotDelim
 GGR_DEV bool ggr_not_delim(u32 c) {

@@ -101,6 +101,11 @@ struct GgrHashEnt {  // 32 bytes; name_len == 0xFFFFFFFF marks an empty slot
   uint32_t w[4];      // first 16 bytes of the name, zero padded (hits need no pool access)
 };
 
+// batch flags the kernels look at (mirror include/ggrmcp_b200.h)
+#define GGR_DF_COMMA_SPACE 0x1u
+#define GGR_DF_GRPC_FRAME 0x2u
+#define GGR_FRAME_BYTES 5u
+
 // per-item status (mirrors ggr_status in include/ggrmcp_b200.h)
 enum {
   GST_OK = 0, GST_SYNTAX = 1, GST_UNKNOWN_FIELD = 2, GST_INVALID_VALUE = 3, GST_RANGE = 4,

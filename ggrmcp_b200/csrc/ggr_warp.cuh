@@ -246,10 +246,31 @@ GGR_DEV u32 wp_align_pad(const u8* dst) {  // dst address & 15
   return (u32)((uintptr_t)dst & 15u);
 #endif
 }
-// all lanes: buf[pad, pad + size) -> out16[pad, pad + size); out16 is 16-byte aligned, buf too
+// all lanes: buf[pad, pad + size) -> out16[pad, pad + size); out16 is 16-byte aligned, buf too.
+// Device: the whole 16-byte chunks leave as ONE bulk copy shared -> global issued by lane 0 (cp.async.bulk, the
+// TMA's 1-D form: no per-lane address arithmetic, no store instructions, the warp does not wait for the data
+// to go); the partial chunks at both ends are byte stores.  The staging buffer may only be written again after
+// wp_copy_wait().
 GGR_DEV void wp_copy_out(const u8* buf, u8* out16, u32 pad, u32 size) {
   const u32 lane = wp_lane();
   const u32 lo = pad, hi = pad + size;
+#if defined(__CUDA_ARCH__)
+  const u32 f0 = (lo + 15u) & ~15u, f1 = hi & ~15u;  // whole chunks [f0, f1)
+  if (f1 > f0 + 48u) {
+    const u32 h1 = f0 < hi ? f0 : hi;
+    for (u32 j = lo + lane; j < h1; j += 32) out16[j] = buf[j];
+    for (u32 j = f1 + lane; j < hi; j += 32) out16[j] = buf[j];
+    __syncwarp();  // every lane's writes into the staging buffer are done
+    if (lane == 0) {
+      // generic-proxy writes to shared memory must be visible to the async proxy that reads them
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(buf + f0);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out16 + f0), "r"(sa), "r"(f1 - f0) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    return;
+  }
+#endif
   const u32 nchunks = (hi + 15u) >> 4;
   for (u32 c = lane; c < nchunks; c += 32) {
     const u32 c0 = c << 4, c1 = c0 + 16u;
@@ -260,6 +281,39 @@ GGR_DEV void wp_copy_out(const u8* buf, u8* out16, u32 pad, u32 size) {
       for (u32 j = b0; j < b1; j++) out16[j] = buf[j];
     }
   }
+}
+// all lanes: the bulk copy wp_copy_out issued has finished READING the staging buffer (it may be reused)
+GGR_DEV void wp_copy_wait() {
+#if defined(__CUDA_ARCH__)
+  if (wp_lane() == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncwarp();
+#else
+  WP_SYNC();
+#endif
+}
+// all lanes, before the kernel ends: every bulk copy of this warp is complete
+GGR_DEV void wp_copy_drain() {
+#if defined(__CUDA_ARCH__)
+  if (wp_lane() == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  __syncwarp();
+#endif
+}
+
+// all lanes (lane 0 acts): ask for [p, p + n) in L2 with one bulk prefetch (cp.async.bulk.prefetch.L2, the TMA's
+// prefetch form): the persistent warps call it for the item they will take NEXT, so that the dependent small loads
+// of the lock-step phases find their lines in L2 instead of waiting for HBM
+GGR_DEV void wp_prefetch_l2(const void* p, u32 n) {
+#if defined(__CUDA_ARCH__)
+  if ((threadIdx.x & 31u) == 0 && n) {
+    const unsigned long long a = reinterpret_cast<unsigned long long>(p);
+    const unsigned long long a16 = a & ~15ull;
+    const u32 bytes = (n + (u32)(a - a16) + 15u) & ~15u;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a16), "r"(bytes) : "memory");
+  }
+#else
+  (void)p;
+  (void)n;
+#endif
 }
 
 // all lanes: ask for the lines of p[0, len) in L1 (one prefetch per 128-byte line and lane); the

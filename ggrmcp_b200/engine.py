@@ -15,6 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.environ.get("GGR_LIB_PATH") or os.path.join(HERE, "libggrmcp_b200.so")  # override: A/B builds only
 
 F_COMMA_SPACE = 1
+F_GRPC_FRAME = 2  # 5-byte gRPC message header in front of every request wire / reply wire item
 ORDER_FIELD_NUMBER = 0
 ORDER_GO_LEGACY = 1
 STATUS_NAMES = ["ok", "syntax", "unknown_field", "invalid_value", "range", "invalid_utf8", "duplicate",
@@ -77,6 +78,10 @@ def _load():
     L.ggr_synchronize.argtypes = [vp]
     L.ggr_profile_enable.argtypes = [vp, C.c_int]
     L.ggr_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    L.ggr_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    L.ggr_host_free.argtypes = [vp, vp]
+    L.ggr_device_numa_node.argtypes = [vp]
+    L.ggr_bind_thread_to_device.argtypes = [vp]
     _lib = L
     return L
 
@@ -145,6 +150,32 @@ class Engine:
 
     def launch_count(self):
         return int(_load().ggr_launch_count(self.h))
+
+    # ---- host memory on the GPU's NUMA node (ggr_host_alloc) ----
+    def numa_node(self):
+        return int(_load().ggr_device_numa_node(self.h))
+
+    def bind_thread(self):
+        """binds the calling thread to the CPUs of the GPU's NUMA node (a per-GPU batching thread)"""
+        _load().ggr_bind_thread_to_device(self.h)
+
+    def host_array(self, nbytes):
+        """page-locked uint8 array of `nbytes` whose pages sit on the GPU's NUMA node; freed with the engine"""
+        p = C.c_void_p()
+        rc = _load().ggr_host_alloc(self.h, int(nbytes), C.byref(p))
+        if rc != 0:
+            self._err(rc, "ggr_host_alloc")
+        self._host_blocks = getattr(self, "_host_blocks", [])
+        self._host_blocks.append(p)
+        buf = (C.c_uint8 * max(int(nbytes), 1)).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.uint8, count=int(nbytes))
+
+    def host_copy(self, a):
+        """copy of a numpy array in NUMA-local page-locked memory (same dtype and shape)"""
+        a = np.ascontiguousarray(a)
+        h = self.host_array(a.nbytes)
+        h[:] = a.view(np.uint8).reshape(-1)
+        return h.view(a.dtype).reshape(a.shape)
 
     def synchronize(self):
         rc = _load().ggr_synchronize(self.h)
@@ -250,6 +281,9 @@ class Engine:
 
     def close(self):
         if self.h:
+            for p in getattr(self, "_host_blocks", []):
+                _load().ggr_host_free(self.h, p)
+            self._host_blocks = []
             _load().ggr_engine_destroy(self.h)
             self.h = None
 

@@ -74,6 +74,13 @@ enum {
 
 /* flags of the batch calls */
 #define GGR_F_COMMA_SPACE 0x1u /* protojson's per-binary detrand bit: ", " after commas */
+/* gRPC length-prefixed message framing (grpc-go rpc_util.go msgHeader, what conn.Invoke puts in front of the
+ * bytes proto.Marshal produced and strips from the reply, /root/reference/pkg/grpc/reflection.go:367-376 with the
+ * limits of pkg/grpc/connection.go:47-58): with this flag the request half writes every item as
+ * 0x00 | big-endian uint32 length | wire bytes (ready for a pass-through codec, no copy on the Go side), and the
+ * reply half takes items framed the same way (compressed flag 1 -> GGR_ST_UNSUPPORTED, a length that disagrees
+ * with the item -> GGR_ST_BAD_WIRE).  Items that fail produce no bytes at all, framed or not. */
+#define GGR_F_GRPC_FRAME 0x2u
 
 typedef struct {
   int32_t device;        /* CUDA device ordinal */
@@ -86,6 +93,20 @@ void ggr_engine_destroy(ggr_engine* e);
 const char* ggr_last_error(const ggr_engine* e); /* NUL-terminated, valid until the next call */
 const char* ggr_status_string(int32_t status);
 uint64_t ggr_launch_count(const ggr_engine* e);  /* kernels launched by this engine so far */
+
+/*
+ * Host memory for the batch buffers of the host entry points ("one pinned arena per GPU").
+ * ggr_host_alloc returns page-locked memory whose pages sit on the NUMA node the engine's GPU hangs off
+ * (the calling thread is bound to that node's CPUs while the pages are allocated and touched, then put
+ * back), so that the copies of the chunked pipeline do not cross the socket interconnect: with 8 GPUs on
+ * two sockets that is the difference between 18 and 36 GB/s per GPU (profiles/README.md).  A Go shim
+ * allocates its arenas here instead of in the Go heap.  ggr_device_numa_node: -1 when the platform does
+ * not say.  ggr_bind_thread_to_device binds the calling thread (a per-GPU batching thread) to the same CPUs.
+ */
+int ggr_host_alloc(ggr_engine* e, size_t bytes, void** out);
+void ggr_host_free(ggr_engine* e, void* p);
+int ggr_device_numa_node(const ggr_engine* e);
+int ggr_bind_thread_to_device(const ggr_engine* e);
 
 /* Registers a serialized google.protobuf.FileDescriptorSet; tables are compiled once and kept in
  * HBM.  Re-register after a Reconnect (pkg/grpc/discovery.go:187-235). */

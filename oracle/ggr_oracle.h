@@ -42,6 +42,8 @@ enum {
 /* flags */
 #define ORC_F_COMMA_SPACE 0x1u   /* protojson detrand bit: ", " instead of ","          */
 #define ORC_F_GO_LEGACY_ORDER 0x2u /* wire field order = Go order.LegacyFieldOrder      */
+#define ORC_F_GRPC_FRAME 0x4u      /* grpc-go rpc_util.go msgHeader: 1 byte compressed flag + big-endian uint32 length in front of
+                                      the request wire; replies arrive framed (what conn.Invoke adds / strips, reflection.go:367-376) */
 
 typedef struct orc_schema orc_schema;
 

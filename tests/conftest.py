@@ -61,8 +61,15 @@ def engine(request):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+    e.path_name = request.param
     yield e
     e.close()
+
+
+def heavy(engine, paths=("default", "size_routing")):
+    """full-size tests run on the two product paths only (the other engine paths repeat the small corpora)"""
+    if getattr(engine, "path_name", "default") not in paths:
+        pytest.skip("full-size test: runs on the %s path(s)" % "/".join(paths))
 
 
 @pytest.fixture(scope="session")

@@ -477,7 +477,7 @@ int hs_decode_coop(void* h, int msg, const uint8_t* wire, uint32_t n, uint32_t i
   memcpy(in + in_off, wire, n);
   static CoopShared S;
   memset(&S, 0xAB, sizeof S);
-  std::vector<U4> tab(2 * GGR_COOP_ENTRIES);
+  std::vector<U4> tab(2 * GGR_COOP_TAB_ENTRIES);
   CoopDecArgs a;
   a.S = &S;
   a.cx.T = ggr_tables(s->blob);

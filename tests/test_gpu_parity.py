@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import cases
+from conftest import heavy
 
 pytestmark = pytest.mark.gpu
 
@@ -125,6 +126,7 @@ def test_empty_and_ragged_batches(engine, schema, oracle):
 
 def test_full_size_properties(engine, schema, oracle):
     """BASELINE.json config sizes: round trip wire -> JSON -> wire and sampled oracle parity."""
+    heavy(engine)
     import benchgen
     n = 65536
     wl = benchgen.nested(n, schema.message)
@@ -162,6 +164,7 @@ def oracle_index(oracle, schema, engine_idx):
 
 
 def test_flat_and_blob_configs(engine, schema, oracle):
+    heavy(engine)
     import benchgen
     wl = benchgen.flat(65536, schema.message)
     wire, woff, st = engine.encode_batch(schema, wl.req_msg, wl.req_json, wl.req_off)
@@ -187,6 +190,7 @@ def test_flat_and_blob_configs(engine, schema, oracle):
 def test_request_and_reply_batches_in_flight_together(engine, schema, oracle):
     """the host entry points take one batch per direction concurrently (bench.py's end-to-end run does
     exactly this from two threads): results must be those of the calls made one after the other"""
+    heavy(engine, ('default', 'small_chunks'))
     import threading
     import benchgen
     n = 20000
@@ -317,6 +321,7 @@ def test_go_legacy_field_order(schema, oracle, fds_bytes):
 def test_small_output_capacity(engine, schema, oracle):
     """GGR_ERR_NO_SPACE: out_off[n] comes back as the capacity that would do, for one chunk and for many, in
     both directions and with result wrapping; the retry with that capacity gives the full result"""
+    heavy(engine, ('default', 'small_chunks'))
     import ctypes as C
     import benchgen
     from ggrmcp_b200 import engine as E
@@ -382,22 +387,101 @@ def test_wrap_heterogeneous_chunks(engine, schema, oracle):
     assert ost == 0 and bytes(out[int(ooff[300]):int(ooff[301])]) == body
 
 
+_mixed_cache = {}
+
+
 def test_mixed_replay(engine, schema, oracle):
     """configs[4]: 100 000 calls over 32 methods with Zipf-distributed sizes, every item against the oracle"""
+    heavy(engine, ('default', 'size_routing', 'per_thread'))
     import os
     import benchgen
-    wl = benchgen.mixed(100000, schema.message)
-    thr = os.cpu_count() or 8
-    # engine and oracle number messages independently: the oracle's ids through the method table
-    fds = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "schemas.binpb"), "rb").read()
-    plan, pairs = benchgen._mixed_plan(fds)
-    oreq = np.array([oracle.msg(a) for a, _ in pairs], np.int32)[wl.method]
-    orep = np.array([oracle.msg(b) for _, b in pairs], np.int32)[wl.method]
+    if not _mixed_cache:
+        wl = benchgen.mixed(100000, schema.message)
+        thr = os.cpu_count() or 8
+        # engine and oracle number messages independently: the oracle's ids through the method table
+        fds = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "schemas.binpb"), "rb").read()
+        plan, pairs = benchgen._mixed_plan(fds)
+        oreq = np.array([oracle.msg(a) for a, _ in pairs], np.int32)[wl.method]
+        orep = np.array([oracle.msg(b) for _, b in pairs], np.int32)[wl.method]
+        _mixed_cache["wl"] = wl
+        _mixed_cache["req"] = oracle.encode_batch(oreq, wl.req_json, wl.req_off, threads=thr)
+        _mixed_cache["rep"] = oracle.decode_batch(orep, wl.rep_wire, wl.rep_off, threads=thr)
+    wl = _mixed_cache["wl"]
+    ow, owoff, ost = _mixed_cache["req"]
+    oj, ojoff, ost2 = _mixed_cache["rep"]
     wire, woff, st = engine.encode_batch(schema, wl.req_msg, wl.req_json, wl.req_off)
-    ow, owoff, ost = oracle.encode_batch(oreq, wl.req_json, wl.req_off, threads=thr)
     assert (ost == 0).all() and (st == 0).all()
     assert (woff == owoff).all() and wire.tobytes() == ow.tobytes()
     js, joff, st = engine.decode_batch(schema, wl.rep_msg, wl.rep_wire, wl.rep_off)
-    oj, ojoff, ost = oracle.decode_batch(orep, wl.rep_wire, wl.rep_off, threads=thr)
-    assert (ost == 0).all() and (st == 0).all()
+    assert (ost2 == 0).all() and (st == 0).all()
     assert (joff == ojoff).all() and js.tobytes() == oj.tobytes()
+
+
+
+def test_single_process_device_set(oracle, fds_bytes):
+    """SURVEY 8e from ONE process: one engine + batching thread + NUMA-local pinned arena per device, the batch cut
+    by index, results gathered by index (threads, not torchrun).  On a one-GPU box two engines share the device."""
+    import torch
+    import benchgen
+    from ggrmcp_b200.shard import DeviceSet
+    ndev = torch.cuda.device_count()
+    devices = list(range(ndev)) if ndev > 1 else [0, 0]
+    ds = DeviceSet(fds_bytes, devices)
+    try:
+        names = {}
+
+        def mi(n):
+            names.setdefault(n, len(names))
+            return names[n]
+
+        wl = benchgen.nested(6001, mi)
+        inv = {v: k for k, v in names.items()}
+        req_names = [inv[int(m)] for m in wl.req_msg]
+        rep_names = [inv[int(m)] for m in wl.rep_msg]
+        wire, woff, st = ds.encode_batch(req_names, wl.req_json, wl.req_off)
+        js, joff, st2 = ds.decode_batch(rep_names, wl.rep_wire, wl.rep_off)
+        assert (st == 0).all() and (st2 == 0).all()
+        om = np.array([oracle.msg(n) for n in req_names], np.int32)
+        ow, owoff, _ = oracle.encode_batch(om, wl.req_json, wl.req_off, threads=8)
+        assert (woff == owoff).all() and wire.tobytes() == ow.tobytes()
+        om = np.array([oracle.msg(n) for n in rep_names], np.int32)
+        oj, ojoff, _ = oracle.decode_batch(om, wl.rep_wire, wl.rep_off, threads=8)
+        assert (joff == ojoff).all() and js.tobytes() == oj.tobytes()
+        for e in ds.engines:
+            assert e.numa_node() >= -1
+    finally:
+        ds.close()
+
+
+def test_grpc_framing(engine, schema, oracle):
+    """GGR_F_GRPC_FRAME against the oracle's ORC_F_GRPC_FRAME: the request half writes 0x00 | be32 length | wire, the reply
+    half takes framed items; bad headers get the oracle's status (reflection.go:367-376)"""
+    import struct
+    import benchgen
+    from ggrmcp_b200.engine import pack, unpack
+    F = 2
+    items = cases.random_encode_cases(60, seed0=41000) + [(n, js) for n, js, _ in cases.K_REQUESTS] + [(cases.A, b"{}"), (cases.A, b""), (cases.A, b"{")]
+    eo, es = _run(engine, schema, True, items, F)
+    for i, (n, b) in enumerate(items):
+        rc, ow, _ = oracle.encode(n, b, 4)
+        assert (rc == 0) == (es[i] == 0), (n, b[:100], rc, es[i])
+        assert eo[i] == (ow if rc == 0 else b""), (n, b[:100], eo[i][:40].hex(), ow[:40].hex())
+    wl = benchgen.nested(3000, schema.message)
+    wire, woff, st = engine.encode_batch(schema, wl.req_msg, wl.req_json, wl.req_off, F, out_cap=len(wl.req_json) + 5 * wl.n + 64)
+    plain, poff, _ = engine.encode_batch(schema, wl.req_msg, wl.req_json, wl.req_off)
+    assert (st == 0).all()
+    fr, pl = unpack(wire, woff), unpack(plain, poff)
+    assert all(f == b"\x00" + struct.pack(">I", len(p)) + p for f, p in zip(fr, pl))
+    # reply side: framed replies in, the same texts out
+    rep = unpack(wl.rep_wire, wl.rep_off)
+    framed = [b"\x00" + struct.pack(">I", len(p)) + p for p in rep]
+    data, off = pack(framed)
+    js, joff, st = engine.decode_batch(schema, wl.rep_msg, data, off, F)
+    js0, joff0, st0 = engine.decode_batch(schema, wl.rep_msg, wl.rep_wire, wl.rep_off)
+    assert (st == 0).all() and (joff == joff0).all() and js.tobytes() == js0.tobytes()
+    bad = [(cases.P + "Node", b"\x01\x00\x00\x00\x00"), (cases.P + "Node", b"\x00\x00\x00\x00\x09"), (cases.P + "Node", b"\x00\x00"),
+           (cases.P + "Node", b"\x00\x00\x00\x00\x00"), (cases.P + "Node", b"\x02\x00\x00\x00\x00")]
+    eo, es = _run(engine, schema, False, bad, F)
+    for i, (n, b) in enumerate(bad):
+        rc, oj, _ = oracle.decode(n, b, 4)
+        assert int(es[i]) == rc and eo[i] == (oj if rc == 0 else b""), (b.hex(), rc, int(es[i]))
