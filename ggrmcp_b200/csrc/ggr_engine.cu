@@ -143,6 +143,7 @@ struct ggr_engine {
   int numa_node = -1;            // of the GPU's PCI function (sysfs), -1 unknown
   std::vector<int> node_cpus;    // CPUs of that node
   ggr::WireOrder order = ggr::ORDER_FIELD_NUMBER;
+  bool short_names = false;      // GGR_NAMES_DESCRIPTOR_SET
   cudaStream_t stream = nullptr;
   std::string err;
   std::atomic<uint64_t> launches{0};
@@ -366,6 +367,7 @@ int ggr_engine_create(const ggr_config* cfg, ggr_engine** out) {
     if (v >= (1 << 16)) e->chunk_bytes = (uint64_t)v;
   }
   e->order = (cfg && cfg->wire_order == GGR_ORDER_GO_LEGACY) ? ggr::ORDER_GO_LEGACY : ggr::ORDER_FIELD_NUMBER;
+  e->short_names = cfg && cfg->tool_naming == GGR_NAMES_DESCRIPTOR_SET;
   if (ggr_encode_coop_init() != 0 || ggr_encode_walk_init() != 0 || ggr_decode_coop_init() != 0) {
     cudaGetLastError();
     delete e;
@@ -444,7 +446,7 @@ int ggr_schema_register(ggr_engine* e, const uint8_t* fds, size_t n, ggr_schema*
   s->eng = e;
   s->d_blob = nullptr;
   std::string err;
-  if (!ggr::compile_schema(fds, n, e->order, &s->cs, &err)) {
+  if (!ggr::compile_schema(fds, n, e->order, &s->cs, &err, e->short_names)) {
     e->err = err;
     delete s;
     return GGR_ERR_SCHEMA;

@@ -299,7 +299,7 @@ uint32_t append_section(std::vector<uint8_t>& out, const T* p, size_t n_bytes) {
 
 }  // namespace
 
-bool compile_schema(const uint8_t* fds, size_t n, WireOrder order, CompiledSchema* out, std::string* err) {
+bool compile_schema(const uint8_t* fds, size_t n, WireOrder order, CompiledSchema* out, std::string* err, bool short_service_names) {
   Parser P;
   {
     Cur c(fds, n);
@@ -455,6 +455,13 @@ bool compile_schema(const uint8_t* fds, size_t n, WireOrder order, CompiledSchem
     MethodInfo M;
     M.name = mi.name;
     M.service_name = mi.service;
+    if (short_service_names) {  // extractServiceNameForCompatibility: the last two segments of the full name
+      size_t d2 = mi.service.rfind('.');
+      if (d2 != std::string::npos && d2 > 0) {
+        size_t d1 = mi.service.rfind('.', d2 - 1);
+        if (d1 != std::string::npos) M.service_name = mi.service.substr(d1 + 1);
+      }
+    }
     M.full_name = mi.service + "." + mi.name;
     M.input_type = mi.in;
     M.output_type = mi.out;
@@ -465,7 +472,7 @@ bool compile_schema(const uint8_t* fds, size_t n, WireOrder order, CompiledSchem
     M.output_msg = b->second;
     M.client_streaming = mi.cs;
     M.server_streaming = mi.ss;
-    std::string t = mi.service;
+    std::string t = M.service_name;
     for (auto& ch : t) { if (ch == '.') ch = '_'; else if (ch >= 'A' && ch <= 'Z') ch = (char)(ch + 32); }
     std::string mn = mi.name;
     for (auto& ch : mn) if (ch >= 'A' && ch <= 'Z') ch = (char)(ch + 32);

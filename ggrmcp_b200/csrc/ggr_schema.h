@@ -38,7 +38,8 @@ struct CompiledSchema {
 };
 
 // Returns false and fills *err on malformed or unresolvable input.
-bool compile_schema(const uint8_t* fds, size_t n, WireOrder order, CompiledSchema* out, std::string* err);
+// short_service_names: the FileDescriptorSet route's tool names (pkg/descriptors/loader.go:221-235)
+bool compile_schema(const uint8_t* fds, size_t n, WireOrder order, CompiledSchema* out, std::string* err, bool short_service_names = false);
 
 uint32_t key_hash(const uint8_t* p, size_t n);
 

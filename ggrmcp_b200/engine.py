@@ -18,6 +18,8 @@ F_COMMA_SPACE = 1
 F_GRPC_FRAME = 2  # 5-byte gRPC message header in front of every request wire / reply wire item
 ORDER_FIELD_NUMBER = 0
 ORDER_GO_LEGACY = 1
+NAMES_REFLECTION = 0      # tool names from the full service name (reflection route)
+NAMES_DESCRIPTOR_SET = 1  # last package segment + service (FileDescriptorSet route, pkg/descriptors/loader.go:221-235)
 STATUS_NAMES = ["ok", "syntax", "unknown_field", "invalid_value", "range", "invalid_utf8", "duplicate",
                 "oneof_conflict", "depth", "too_large", "bad_wire", "unsupported", "no_space", "internal"]
 
@@ -27,7 +29,7 @@ class EngineError(RuntimeError):
 
 
 class _Config(C.Structure):
-    _fields_ = [("device", C.c_int32), ("wire_order", C.c_uint32), ("reserved", C.c_uint32 * 6)]
+    _fields_ = [("device", C.c_int32), ("wire_order", C.c_uint32), ("tool_naming", C.c_uint32), ("reserved", C.c_uint32 * 5)]
 
 
 class _MethodInfo(C.Structure):
@@ -126,9 +128,9 @@ class Schema:
 
 
 class Engine:
-    def __init__(self, device=0, wire_order=ORDER_FIELD_NUMBER):
+    def __init__(self, device=0, wire_order=ORDER_FIELD_NUMBER, tool_naming=NAMES_REFLECTION):
         L = _load()
-        cfg = _Config(device=device, wire_order=wire_order)
+        cfg = _Config(device=device, wire_order=wire_order, tool_naming=tool_naming)
         h = C.c_void_p()
         rc = L.ggr_engine_create(C.byref(cfg), C.byref(h))
         if rc != 0:

@@ -82,10 +82,20 @@ enum {
  * with the item -> GGR_ST_BAD_WIRE).  Items that fail produce no bytes at all, framed or not. */
 #define GGR_F_GRPC_FRAME 0x2u
 
+/* ggr_config.tool_naming: which discovery route the tool names follow */
+enum {
+  GGR_NAMES_REFLECTION = 0,     /* service name = full name: "com_example_complex_userprofileservice_getuserprofile"
+                                   (reflection route, /root/reference/pkg/grpc/reflection.go:235-243) */
+  GGR_NAMES_DESCRIPTOR_SET = 1  /* service name = last package segment + service, as the FileDescriptorSet route shortens it:
+                                   "complex_userprofileservice_getuserprofile"
+                                   (extractServiceNameForCompatibility, /root/reference/pkg/descriptors/loader.go:221-235) */
+};
+
 typedef struct {
   int32_t device;        /* CUDA device ordinal */
   uint32_t wire_order;   /* GGR_ORDER_* */
-  uint32_t reserved[6];
+  uint32_t tool_naming;  /* GGR_NAMES_* */
+  uint32_t reserved[5];
 } ggr_config;
 
 int ggr_engine_create(const ggr_config* cfg, ggr_engine** out);

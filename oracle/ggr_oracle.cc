@@ -318,6 +318,18 @@ orc_schema* orc_schema_new(const uint8_t* fds, size_t n, char* err, size_t errca
   }
   return s;
 }
+// naming: 0 = reflection route (full service name), 1 = FileDescriptorSet route (last package segment + service)
+orc_schema* orc_schema_new2(const uint8_t* fds, size_t n, int naming, char* err, size_t errcap) {
+  orc_schema* s = new orc_schema();
+  SchemaBuilder b(s->S);
+  b.short_service_names = naming == 1;
+  if (!b.build(fds, n)) {
+    set_err(err, errcap, b.err);
+    delete s;
+    return nullptr;
+  }
+  return s;
+}
 void orc_schema_free(orc_schema* s) { delete s; }
 int32_t orc_message_index(const orc_schema* s, const char* full_name) {
   auto it = s->S.msg_by_name.find(full_name);

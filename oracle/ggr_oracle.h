@@ -48,6 +48,8 @@ enum {
 typedef struct orc_schema orc_schema;
 
 orc_schema* orc_schema_new(const uint8_t* fds, size_t n, char* err, size_t errcap);
+/* naming: 0 reflection route (full service name), 1 FileDescriptorSet route (pkg/descriptors/loader.go:221-235) */
+orc_schema* orc_schema_new2(const uint8_t* fds, size_t n, int naming, char* err, size_t errcap);
 void orc_schema_free(orc_schema*);
 int32_t orc_message_index(const orc_schema*, const char* full_name);
 int32_t orc_method_count(const orc_schema*);

@@ -170,6 +170,7 @@ struct SchemaBuilder {
     bool cs, ss;
   };
   std::vector<PendingSvc> pending;
+  bool short_service_names = false;  // tool names of the FileDescriptorSet route
   explicit SchemaBuilder(Schema& s) : S(s) {}
 
   bool parse_enum(const uint8_t* p, size_t n, const std::string& scope) {
@@ -414,6 +415,13 @@ struct SchemaBuilder {
       md.server_streaming = ps.ss;
       // types.MethodInfo.GenerateToolName, /root/reference/pkg/types/service.go:53-61
       std::string t = ps.service_full;
+      if (short_service_names) {  // extractServiceNameForCompatibility, /root/reference/pkg/descriptors/loader.go:221-235
+        size_t d2 = t.rfind('.');
+        if (d2 != std::string::npos && d2 > 0) {
+          size_t d1 = t.rfind('.', d2 - 1);
+          if (d1 != std::string::npos) t = t.substr(d1 + 1);
+        }
+      }
       for (auto& c : t) {
         if (c == '.') c = '_';
         else if (c >= 'A' && c <= 'Z') c = (char)(c - 'A' + 'a');

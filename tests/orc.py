@@ -38,6 +38,8 @@ def lib():
         L = C.CDLL(LIB)
         L.orc_schema_new.restype = C.c_void_p
         L.orc_schema_new.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+        L.orc_schema_new2.restype = C.c_void_p
+        L.orc_schema_new2.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_char_p, C.c_size_t]
         L.orc_schema_free.argtypes = [C.c_void_p]
         L.orc_message_index.argtypes = [C.c_void_p, C.c_char_p]
         L.orc_message_index.restype = C.c_int32
@@ -78,9 +80,9 @@ def _take(ptr, n):
 
 
 class Schema:
-    def __init__(self, fds_bytes):
+    def __init__(self, fds_bytes, naming=0):
         err = C.create_string_buffer(256)
-        self.h = lib().orc_schema_new(fds_bytes, len(fds_bytes), err, 256)
+        self.h = lib().orc_schema_new2(fds_bytes, len(fds_bytes), naming, err, 256)
         if not self.h:
             raise ValueError(err.value.decode())
         self._idx = {}

@@ -184,3 +184,17 @@ def test_oracle_vs_upb():
             from google.protobuf import json_format
             m3 = json_format.Parse(text, pbgen.cls(name)())
             assert pbgen.wire(m3) == W, (name, seed)
+
+
+def test_descriptor_set_route_tool_names(fds_bytes):
+    """the FileDescriptorSet route shortens the service name to its last package segment
+    (/root/reference/pkg/descriptors/loader.go:221-235; names pinned by pkg/grpc/discovery_edge_cases_test.go:62-66)"""
+    import orc
+    S = orc.Schema(fds_bytes, naming=1)
+    tools = {m["tool"] for m in S.methods()}
+    assert "complex_userprofileservice_getuserprofile" in tools
+    assert "hello_helloservice_sayhello" in tools        # one package segment: unchanged
+    assert "com_example_complex_userprofileservice_getuserprofile" not in tools
+    body = b'{"jsonrpc":"2.0","method":"tools/call","id":1,"params":{"name":"complex_userprofileservice_getuserprofile","arguments":{"user_id":"u"}}}'
+    r = S.request(body)
+    assert r["kind"] == 0 and r["wire"] == bytes.fromhex("0a0175")
