@@ -1221,14 +1221,19 @@ struct
 };
 
 // one lane: bytes of node `i` into the staging buffer (long plain strings: payload left to the warp)
-GGR_DEV void ce_emit_node(CoopEmit& E, const u8* in, u32 end, const u8* ir, const u32* ioff, u32 i, u32 pad) {
+// STAGED: byte position p of the item lands in the staging buffer (plain shared-memory stores); otherwise - items too
+// large to stage - at G[p], the destination itself shifted so that the same positions apply (two instances: a pointer
+// that may be either makes every store a generic one, 1.11 -> 1.67 ms on configs[2])
+template <bool STAGED>
+GGR_DEV void ce_emit_node(CoopEmit& E, u8* G, const u8* in, u32 end, const u8* ir, const u32* ioff, u32 i, u32 pad) {
+  u8* const B = STAGED ? E.buf : G;
   const U4 nd = node_load(ir, i);
   const u32 type = nd.w & 0xFu, flags = (nd.w >> 4) & 0xFu, tag = nd.w >> 8;
   if (type == N_SKIP || type == N_MAP || (type == N_LIST && !(flags & NF_PACKED))) return;
   const u32 off = ioff[i];
   if (off == 0xFFFFFFFFu) return;  // written together with its parent (Timestamp fields)
   Sw w;
-  w.init(E.buf, pad + off);
+  w.init(B, pad + off);
   switch (type) {
     case N_VARINT: {
       if (tag) put_varint(w, tag);
@@ -1276,7 +1281,7 @@ GGR_DEV void ce_emit_node(CoopEmit& E, const u8* in, u32 end, const u8* ir, cons
         }
         if (!handed) {
           const u8* src = in + nd.x + 1u;
-          for (u32 j = 0; j < nd.y; j++) E.buf[w.pos + j] = src[j];
+          for (u32 j = 0; j < nd.y; j++) B[w.pos + j] = src[j];
         }
       }
       break;
@@ -1343,25 +1348,42 @@ GGR_DEV void ce_unescape_coop(const u8* in, u32 src, u8* d, u32 dec_len) {
   }
 }
 
-// One item, all 32 lanes: size bytes to dst.
+// One item, all 32 lanes: size bytes to dst.  Items that fit the staging buffer are assembled there and leave with one
+// bulk copy; larger ones (second tier of the walker: tens of KB of wire) are written in place.
 GGR_DEV void ce_emit_item(CoopEmit& E, const u8* in, u32 end, const u8* ir, const u32* ioff, u32 n_nodes, u8* dst, u32 size) {
   const u32 lane = wp_lane();
   const u32 pad = wp_align_pad(dst);
-  wp_prefetch(in, end);
+  const bool staged = size <= CE_STAGE;
+  wp_prefetch(in, end < 16384u ? end : 16384u);
   wp_copy_wait();  // persistent warps: the previous item's bulk copy has read the staging buffer
   if (lane == 0) E.n = 0;
   WP_SYNC();
-  for (u32 i = 1 + lane; i < n_nodes; i += 32) ce_emit_node(E, in, end, ir, ioff, i, pad);
-  WP_SYNC();
-  const u32 nl = E.n < CE_LONG_MAX ? E.n : CE_LONG_MAX;
-  for (u32 k = 0; k < nl; k++) {
-    const u8* src = in + E.src[k];
-    u8* d = E.buf + E.dst[k];
-    const u32 len = E.len[k];
-    if (len & 0x80000000u) ce_unescape_coop(in, E.src[k], d, len & 0x7FFFFFFFu);
-    else
-      for (u32 j = lane; j < len; j += 32) d[j] = src[j];
+  if (staged) {
+    for (u32 i = 1 + lane; i < n_nodes; i += 32) ce_emit_node<true>(E, nullptr, in, end, ir, ioff, i, pad);
+  } else {
+    for (u32 i = 1 + lane; i < n_nodes; i += 32) ce_emit_node<false>(E, dst - pad, in, end, ir, ioff, i, pad);
   }
   WP_SYNC();
-  wp_copy_out(E.buf, dst - pad, pad, size);
+  const u32 nl = E.n < CE_LONG_MAX ? E.n : CE_LONG_MAX;
+  if (staged) {
+    for (u32 k = 0; k < nl; k++) {
+      const u8* src = in + E.src[k];
+      u8* d = E.buf + E.dst[k];
+      const u32 len = E.len[k];
+      if (len & 0x80000000u) ce_unescape_coop(in, E.src[k], d, len & 0x7FFFFFFFu);
+      else
+        for (u32 j = lane; j < len; j += 32) d[j] = src[j];
+    }
+    WP_SYNC();
+    wp_copy_out(E.buf, dst - pad, pad, size);
+  } else {
+    for (u32 k = 0; k < nl; k++) {
+      const u8* src = in + E.src[k];
+      u8* d = dst - pad + E.dst[k];
+      const u32 len = E.len[k];
+      if (len & 0x80000000u) ce_unescape_coop(in, E.src[k], d, len & 0x7FFFFFFFu);
+      else
+        for (u32 j = lane; j < len; j += 32) d[j] = src[j];
+    }
+  }
 }

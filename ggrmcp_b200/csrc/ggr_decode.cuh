@@ -311,6 +311,11 @@ struct DecCtx {
   Tables T;
   const u8* in;
   u32 flags;
+  // scratch for maps whose entries arrive unsorted (what a Go backend sends: map iteration order): 16-byte
+  // (key, position) records handed out by a bump counter; nullptr: selection by repeated scans (quadratic)
+  U4* sort_pool = nullptr;
+  u32* sort_ctr = nullptr;
+  u32 sort_cap = 0;
 };
 
 template <class W>
@@ -722,6 +727,89 @@ GGR_DEV int put_map_field(W& w, const DecCtx& cx, Rd& r, const FieldD& f, u32 ps
     }
   }
   if (count == 0) return GST_OK;
+  // Unsorted entries (Go map iteration order; the usual case behind a Go backend): collect (key, position) of every
+  // entry into scratch, heap-sort them by key then position, emit in that order - of equal keys the last occurrence
+  // (map semantics: last wins).  O(k log k) key comparisons instead of k scans over the run.
+  if (!sorted && count > 8u && cx.sort_pool) {
+    const u32 base = ggr_atomic_add_u32(cx.sort_ctr, count);
+    if (base <= cx.sort_cap && count <= cx.sort_cap - base) {
+      U4* A = cx.sort_pool + base;
+      {
+        Rd t;
+        t.init(cx.in, run_start, run_end);
+        bool first_in_run = !SLOW;
+        u32 k = 0;
+        while (t.pos < run_end && k < count) {
+          if (!first_in_run) {
+            u64 tag;
+            if (!rd_varint(t, run_end, &tag)) return GST_BAD_WIRE;
+            if (tag != (u64)f.tag) {
+              if (!rd_skip_value(t, run_end, (u32)(tag >> 3), (u32)(tag & 7))) return GST_BAD_WIRE;
+              continue;
+            }
+          }
+          first_in_run = false;
+          const u32 at = t.pos;
+          u64 len;
+          if (!rd_varint(t, run_end, &len)) return GST_BAD_WIRE;
+          MapEnt me;
+          int st = parse_map_entry(t, t.pos + (u32)len, kf, vf, &me);
+          if (st != GST_OK) return st;
+          U4 rec = {(u32)me.key, (u32)(me.key >> 32), at, 0u};
+          A[k++] = rec;
+        }
+        if (k != count) return GST_INTERNAL;
+      }
+      auto less = [&](const U4& a, const U4& b) -> bool {
+        const int c = cmp_map_keys(cx, kf.kind, (u64)a.x | ((u64)a.y << 32), (u64)b.x | ((u64)b.y << 32));
+        return c < 0 || (c == 0 && a.z < b.z);
+      };
+      // heap sort (ascending): sift-down on a max-heap
+      auto sift = [&](u32 root, u32 n) {
+        U4 v = A[root];
+        for (;;) {
+          u32 child = 2u * root + 1u;
+          if (child >= n) break;
+          if (child + 1u < n && less(A[child], A[child + 1u])) child++;
+          if (!less(v, A[child])) break;
+          A[root] = A[child];
+          root = child;
+        }
+        A[root] = v;
+      };
+      for (u32 i = count / 2u; i-- > 0u;) sift(i, count);
+      for (u32 n = count; n > 1u; n--) {
+        const U4 top = A[0];
+        A[0] = A[n - 1u];
+        A[n - 1u] = top;
+        sift(0u, n - 1u);
+      }
+      w.put1('{');
+      u32 efirst2 = 1;
+      for (u32 i = 0; i < count; i++) {
+        const U4 e = A[i];
+        if (i + 1u < count) {  // an equal key follows: that later occurrence wins
+          const U4 nx = A[i + 1u];
+          if (cmp_map_keys(cx, kf.kind, (u64)e.x | ((u64)e.y << 32), (u64)nx.x | ((u64)nx.y << 32)) == 0) continue;
+        }
+        Rd t;
+        t.init(cx.in, e.z, run_end);
+        u64 len;
+        if (!rd_varint(t, run_end, &len)) return GST_BAD_WIRE;
+        MapEnt me;
+        int st = parse_map_entry(t, t.pos + (u32)len, kf, vf, &me);
+        if (st != GST_OK) return st;
+        put_sep(w, cx, efirst2);
+        st = put_map_key(w, cx, kf.kind, me.key);
+        if (st != GST_OK) return st;
+        w.put1(':');
+        st = put_map_value<W, SLOW>(w, cx, vf, me, rec);
+        if (st != GST_OK) return st;
+      }
+      w.put1('}');
+      return GST_OK;
+    }
+  }
   // pass 2: emit in key order.  Already sorted (the usual case for deterministic backends): one
   // sweep.  Otherwise selection by key: each round picks the smallest key above the last one
   // written, taking the LAST occurrence of that key (map semantics: last wins).
@@ -1211,11 +1299,14 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
 // Size pass: tries the fast walk, falls back to the slow walk for the whole item.
 // All lanes of `mask` call this together; lanes without an item pass active = false.
 GGR_DEV int decode_size(const Tables& T, u32 msg, const u8* in, u32 start, u32 end, u32 flags, DecResult* res,
-                        bool active = true, unsigned mask = GGR_FULL_MASK) {
+                        bool active = true, unsigned mask = GGR_FULL_MASK, U4* sort_pool = nullptr, u32* sort_ctr = nullptr, u32 sort_cap = 0) {
   DecCtx cx;
   cx.T = T;
   cx.in = in;
   cx.flags = flags;
+  cx.sort_pool = sort_pool;
+  cx.sort_ctr = sort_ctr;
+  cx.sort_cap = sort_cap;
   Cnt c;
   c.pos = 0;
   int st = walk_message<Cnt, false>(c, cx, msg, start, end, 0, active, mask);
@@ -1232,11 +1323,15 @@ GGR_DEV int decode_size(const Tables& T, u32 msg, const u8* in, u32 start, u32 e
 }
 
 GGR_DEV int decode_write(const Tables& T, u32 msg, const u8* in, u32 start, u32 end, u32 flags, u32 mode, u8* out,
-                         u32 out_off, u32* end_pos, bool active = true, unsigned mask = GGR_FULL_MASK) {
+                         u32 out_off, u32* end_pos, bool active = true, unsigned mask = GGR_FULL_MASK, U4* sort_pool = nullptr,
+                         u32* sort_ctr = nullptr, u32 sort_cap = 0) {
   DecCtx cx;
   cx.T = T;
   cx.in = in;
   cx.flags = flags;
+  cx.sort_pool = sort_pool;
+  cx.sort_ctr = sort_ctr;
+  cx.sort_cap = sort_cap;
   Wr w;
   w.init(out, out_off);
   bool slow = mode == GGR_MODE_SLOW;

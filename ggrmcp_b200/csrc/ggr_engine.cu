@@ -122,6 +122,7 @@ struct DevBuf {
 struct Scratch {
   DevBuf ir, size, aux, sums, pend, ioff, nn;
   DevBuf wtext, woff, wsize;  // result wrapping: protojson texts, their offsets, body sizes
+  DevBuf sortpool;            // reply side: (key, position) records of maps whose entries arrive unsorted
 };
 #define GGR_MAX_SLOTS 8
 struct Slot {
@@ -406,7 +407,7 @@ void ggr_engine_destroy(ggr_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   auto free_scratch = [](Scratch& sc) {
-    DevBuf* bufs[] = {&sc.ir, &sc.size, &sc.aux, &sc.sums, &sc.pend, &sc.ioff, &sc.nn, &sc.wtext, &sc.woff, &sc.wsize};
+    DevBuf* bufs[] = {&sc.ir, &sc.size, &sc.aux, &sc.sums, &sc.pend, &sc.ioff, &sc.nn, &sc.wtext, &sc.woff, &sc.wsize, &sc.sortpool};
     for (DevBuf* b : bufs)
       if (b->p) cudaFree(b->p);
   };
@@ -565,13 +566,14 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
   if (encode) {
     if (e->use_coop_enc) {
       // lock-step parser first (one warp per item); what it leaves goes to the per-thread parser
-      if (!ensure(e, sc.pend, (size_t)n * 12 + 64) || !ensure(e, sc.ioff, (size_t)in_bytes * 2 + (size_t)n * 32 + 64) ||
+      if (!ensure(e, sc.pend, (size_t)n * 16 + 64) || !ensure(e, sc.ioff, (size_t)in_bytes * 2 + (size_t)n * 32 + 64) ||
           !ensure(e, sc.nn, (size_t)n * 4))
         return GGR_ERR_CUDA;
-      u32* counters = (u32*)sc.pend.p;  // [0] lock-step items, [4] left by tier 1, [8] per-thread items
+      u32* counters = (u32*)sc.pend.p;  // [0] lock-step items, [4] left by the first tier, [8] per-thread items, [12] left by the walker's second tier
       u32* big = counters + 16;
       u32* pend1 = big + n;
       u32* pend2 = pend1 + n;
+      u32* pend1b = pend2 + n;
       size_t c0 = 0, c1 = 0;
       if (!cuda_ok(e, cudaMemsetAsync(counters, 0, 64, st), "memset") ||
           !cuda_ok(e, cudaMemsetAsync(sc.nn.p, 0, (size_t)n * 4, st), "memset"))
@@ -587,8 +589,11 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
         ggr_launch_encode_place(st, n, in_off, (u8*)sc.ir.p, big, counters, e->sm_count);
         size_t t2 = 0, t3 = 0;
         if (prof) prof_mark(e, st, &t2);
-        ggr_launch_encode_type(st, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p, (u32*)sc.aux.p, status,
-                               (u32*)sc.ioff.p, (u32*)sc.nn.p, big, counters, pend1, counters + 4, e->sm_count);
+        ggr_launch_encode_type(st, 0, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p, (u32*)sc.aux.p, status,
+                               (u32*)sc.ioff.p, (u32*)sc.nn.p, big, counters, pend1b, counters + 12, e->sm_count);
+        // second tier over what the first left (large items, the other leaf forms); what it leaves: pend1 -> the fused kernel
+        ggr_launch_encode_type(st, 1, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p, (u32*)sc.aux.p, status,
+                               (u32*)sc.ioff.p, (u32*)sc.nn.p, pend1b, counters + 12, pend1, counters + 4, e->sm_count);
         if (prof) {
           prof_mark(e, st, &t3);
           e->spans.push_back({12, t1, t2});  // value records
@@ -616,7 +621,7 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
         prof_mark(e, st, &m1);
         e->spans.push_back({9, c1, m1});
       }
-      e->launches += e->use_walk ? 6 : 5;  // + the token-index kernel of tier 1 (+ the place kernel of the token-parallel walker)
+      e->launches += e->use_walk ? 7 : 5;  // + the token-index kernel of tier 1 (+ the place kernel of the token-parallel walker)
     } else {
       ggr_launch_encode_parse(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
                               (u32*)sc.aux.p, status, (u64*)sc.sums.p, nullptr, nullptr);
@@ -651,6 +656,11 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
     // then walk only what was left pending (irregular field order, maps, malformed wire, ...).
     const bool coop = e->use_coop;
     size_t c0 = 0, c1 = 0;
+    // a map entry takes at least 4 bytes of wire; both passes sort, the fast walk may give way to the slow one
+    const uint64_t want_recs = in_bytes / 4 * 3 + 1024;
+    const uint32_t sort_cap = (uint32_t)(want_recs > 0x3FFFFFFFull ? 0x3FFFFFFFull : want_recs);
+    if (!ensure(e, sc.sortpool, (size_t)sort_cap * 16 + 16)) return GGR_ERR_CUDA;
+    if (!cuda_ok(e, cudaMemsetAsync(sc.sortpool.p, 0, 16, st), "memset")) return GGR_ERR_CUDA;
     if (coop) {
       if (!ensure(e, sc.ir, ggr_decode_coop_table_bytes(n)) || !ensure(e, sc.nn, (size_t)n * 4) ||
           !ensure(e, sc.pend, (size_t)n * 8 + 64))
@@ -668,12 +678,12 @@ static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode,
       }
     }
     ggr_launch_decode_size(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, flags, (u32*)sc.size.p,
-                           (u32*)sc.aux.p, status, (u64*)sc.sums.p, coop ? 1 : 0);
+                           (u32*)sc.aux.p, status, (u64*)sc.sums.p, coop ? 1 : 0, sc.sortpool.p, sort_cap);
     if (prof) prof_mark(e, st, &m1);
     k_scan_blocks<<<1, 1024, 0, st>>>((u64*)sc.sums.p, nb, out_off + n);
     if (prof) prof_mark(e, st, &m2);
     ggr_launch_decode_write(st, (unsigned)nb, s->d_blob, n, msg_id, in, in_off, flags, (const u32*)sc.size.p,
-                            (const u32*)sc.aux.p, status, (const u64*)sc.sums.p, out, out_cap, out_off);
+                            (const u32*)sc.aux.p, status, (const u64*)sc.sums.p, out, out_cap, out_off, sc.sortpool.p, sort_cap);
     if (coop) {
       if (prof) prof_mark(e, st, &c1);
       ggr_launch_decode_coop_write(st, n, s->d_blob, in, in_off, flags, (const u32*)sc.size.p, (const u32*)sc.aux.p, status, sc.ir.p,

@@ -26,7 +26,7 @@ void ggr_launch_encode_tok2(cudaStream_t st, long long n, const uint8_t* in, con
                             const uint32_t* list_n, int sm_count);
 void ggr_launch_encode_place(cudaStream_t st, long long n, const uint64_t* in_off, uint8_t* ir, const uint32_t* list, const uint32_t* list_n,
                              int sm_count);
-void ggr_launch_encode_type(cudaStream_t st, long long n, const uint8_t* blob, uint32_t n_msgs, const int32_t* msg_id, const uint8_t* in,
+void ggr_launch_encode_type(cudaStream_t st, int tier, long long n, const uint8_t* blob, uint32_t n_msgs, const int32_t* msg_id, const uint8_t* in,
                             const uint64_t* in_off, uint8_t* ir, uint32_t* size, uint32_t* first, int32_t* status, uint32_t* ioff,
                             uint32_t* nnodes, const uint32_t* list, const uint32_t* list_n, uint32_t* pending, uint32_t* n_pending,
                             int sm_count);
@@ -38,11 +38,12 @@ void ggr_launch_encode_emit(cudaStream_t st, unsigned nb, long long n, const uin
 void ggr_launch_frame_sizes(cudaStream_t st, long long n, uint32_t* size, const int32_t* status);  // GGR_F_GRPC_FRAME: + 5 bytes per item
 void ggr_launch_decode_size(cudaStream_t st, unsigned nb, const uint8_t* blob, long long n, uint32_t n_msgs, const int32_t* msg_id,
                             const uint8_t* in, const uint64_t* in_off, uint32_t flags, uint32_t* size, uint32_t* mode,
-                            int32_t* status, uint64_t* block_sums, int after_coop);
+                            int32_t* status, uint64_t* block_sums, int after_coop, void* sort_pool, uint32_t sort_cap);
 void ggr_launch_decode_write(cudaStream_t st, unsigned nb, const uint8_t* blob, long long n, const int32_t* msg_id,
                              const uint8_t* in, const uint64_t* in_off, uint32_t flags, const uint32_t* size,
                              const uint32_t* mode, int32_t* status, const uint64_t* block_prefix, uint8_t* out,
-                             uint64_t out_cap, uint64_t* out_off);
+                             uint64_t out_cap, uint64_t* out_off, void* sort_pool, uint32_t sort_cap);
+// sort_pool: 16 bytes of bump counter (zeroed per batch) followed by sort_cap 16-byte records: scratch of the unsorted-map path
 void ggr_launch_decode_coop_size(cudaStream_t st, long long n, const uint8_t* blob, uint32_t n_msgs, const int32_t* msg_id,
                                  const uint8_t* in, const uint64_t* in_off, uint32_t flags, uint32_t* size, uint32_t* mode,
                                  int32_t* status, void* tab, uint32_t* nent, int sm_count, const uint32_t* list,

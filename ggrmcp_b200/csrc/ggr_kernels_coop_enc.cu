@@ -121,20 +121,6 @@ k_encode_coop_emit(long long n, const u8* __restrict__ in, const u64* __restrict
   // fixed stride here: an item takes a few microseconds, tickets for 150 K of them in a millisecond
   // run into the rate of atomics on one address (measured: 1.15 ms with the stride, 1.23 ms by ticket)
   for (long long slot = (long long)blockIdx.x * CE_WARPS + warp; slot < total; slot += (long long)gridDim.x * CE_WARPS) {
-    {  // the item this warp takes next: text, IR nodes and offsets asked for in L2 with bulk prefetches
-      const long long nslot = slot + (long long)gridDim.x * CE_WARPS;
-      if (nslot < total) {
-        const long long it2 = (long long)list[nslot];
-        const u32 nw2 = nnodes[it2];
-        const u64 a2 = in_off[it2], b2 = in_off[it2 + 1];
-        if ((nw2 & 0xFFFFu) > 1u && b2 > a2) {
-          const u64 no2 = ((a2 - a0) >> 1) + 8ull * (u64)it2 + (u64)(nw2 >> 16);
-          wp_prefetch_l2(in + a2, (u32)(b2 - a2));
-          wp_prefetch_l2(ir + no2 * 16, (nw2 & 0xFFFFu) * 16u);
-          wp_prefetch_l2(ioff + no2, (nw2 & 0xFFFFu) * 4u);
-        }
-      }
-    }
     const long long item = (long long)list[slot];
     const u32 nw = nnodes[item];
     const u32 nn = nw & 0xFFFFu;  // node count | index of the first node within the region << 16 (ggr_walk.cuh)

@@ -6,7 +6,8 @@
 __global__ void __launch_bounds__(GGR_BLOCK)
 k_decode_size(const u8* __restrict__ blob, long long n, u32 n_msgs, const i32* __restrict__ msg_id,
               const u8* __restrict__ in, const u64* __restrict__ in_off, u32 flags, u32* __restrict__ size,
-              u32* __restrict__ mode, i32* __restrict__ status, u64* __restrict__ block_sums, int after_coop) {
+              u32* __restrict__ mode, i32* __restrict__ status, u64* __restrict__ block_sums, int after_coop,
+              U4* __restrict__ sort_pool, u32 sort_cap) {
   long long i = (long long)blockIdx.x * GGR_BLOCK + threadIdx.x;
   u32 sz = 0;
   u64 a = 0, b = 0;
@@ -39,7 +40,9 @@ k_decode_size(const u8* __restrict__ blob, long long n, u32 n_msgs, const i32* _
     Tables T = ggr_tables(blob);
     const u8* base = in + (a & ~15ull);
     u32 s0 = (u32)(a & 15ull);
-    int r = decode_size(T, (u32)m, base, s0, s0 + (u32)(b - a), flags, &res, active, GGR_FULL_MASK);
+    // the pool's first 16 bytes hold its bump counter
+    int r = decode_size(T, (u32)m, base, s0, s0 + (u32)(b - a), flags, &res, active, GGR_FULL_MASK, sort_pool ? sort_pool + 1 : nullptr,
+                        reinterpret_cast<u32*>(sort_pool), sort_cap);
     if (active) st = r;
   }
   if (i < n) {
@@ -62,7 +65,7 @@ __global__ void __launch_bounds__(GGR_BLOCK)
 k_decode_write(const u8* __restrict__ blob, long long n, const i32* __restrict__ msg_id, const u8* __restrict__ in,
                const u64* __restrict__ in_off, u32 flags, const u32* __restrict__ size, const u32* __restrict__ mode,
                i32* __restrict__ status, const u64* __restrict__ block_prefix, u8* __restrict__ out, u64 out_cap,
-               u64* __restrict__ out_off) {
+               u64* __restrict__ out_off, U4* __restrict__ sort_pool, u32 sort_cap) {
   long long i = (long long)blockIdx.x * GGR_BLOCK + threadIdx.x;
   u32 sz = i < n ? size[i] : 0;
   u32 tot;
@@ -93,7 +96,7 @@ k_decode_write(const u8* __restrict__ blob, long long n, const i32* __restrict__
   u32 s0 = (u32)(a & 15ull);
   u32 end_pos = 0;
   int st = decode_write(T, (u32)m, base, s0, s0 + (u32)(b - a), flags, md, out + (off & ~7ull), (u32)(off & 7ull), &end_pos,
-                        active, GGR_FULL_MASK);
+                        active, GGR_FULL_MASK, sort_pool ? sort_pool + 1 : nullptr, reinterpret_cast<u32*>(sort_pool), sort_cap);
   if (active) {
     if (st == GST_OK && end_pos != (u32)(off & 7ull) + sz) st = GST_INTERNAL;
     if (st != GST_OK) status[i] = st;
@@ -102,13 +105,15 @@ k_decode_write(const u8* __restrict__ blob, long long n, const i32* __restrict__
 
 void ggr_launch_decode_size(cudaStream_t st, unsigned nb, const uint8_t* blob, long long n, uint32_t n_msgs, const int32_t* msg_id,
                             const uint8_t* in, const uint64_t* in_off, uint32_t flags, uint32_t* size, uint32_t* mode,
-                            int32_t* status, uint64_t* block_sums, int after_coop) {
-  k_decode_size<<<nb, GGR_BLOCK, 0, st>>>(blob, n, n_msgs, msg_id, in, (const u64*)in_off, flags, size, mode, status, (u64*)block_sums, after_coop);
+                            int32_t* status, uint64_t* block_sums, int after_coop, void* sort_pool, uint32_t sort_cap) {
+  k_decode_size<<<nb, GGR_BLOCK, 0, st>>>(blob, n, n_msgs, msg_id, in, (const u64*)in_off, flags, size, mode, status, (u64*)block_sums, after_coop,
+                                          (U4*)sort_pool, sort_cap);
 }
 void ggr_launch_decode_write(cudaStream_t st, unsigned nb, const uint8_t* blob, long long n, const int32_t* msg_id,
                              const uint8_t* in, const uint64_t* in_off, uint32_t flags, const uint32_t* size,
                              const uint32_t* mode, int32_t* status, const uint64_t* block_prefix, uint8_t* out,
-                             uint64_t out_cap, uint64_t* out_off) {
-  k_decode_write<<<nb, GGR_BLOCK, 0, st>>>(blob, n, msg_id, in, (const u64*)in_off, flags, size, mode, status, (const u64*)block_prefix, out, (u64)out_cap, (u64*)out_off);
+                             uint64_t out_cap, uint64_t* out_off, void* sort_pool, uint32_t sort_cap) {
+  k_decode_write<<<nb, GGR_BLOCK, 0, st>>>(blob, n, msg_id, in, (const u64*)in_off, flags, size, mode, status, (const u64*)block_prefix, out, (u64)out_cap, (u64*)out_off,
+                                           (U4*)sort_pool, sort_cap);
 }
 int ggr_decode_max_rec() { return GGR_DEC_MAX_REC; }

@@ -15,7 +15,7 @@
 #define CW_PLACE_BLOCKS 12
 #endif
 #ifndef CW_WALK_BLOCKS
-#define CW_WALK_BLOCKS 7
+#define CW_WALK_BLOCKS 6 /* 80 registers, no spills: 1.71 ms against 1.78 with 7 blocks (72 registers, 264 bytes of spills) and 1.86 with 8 */
 #endif
 
 __global__ void __launch_bounds__(CW_WARPS * 32, CW_TOK_BLOCKS)
@@ -57,44 +57,37 @@ k_encode_place(const u64* __restrict__ in_off, u8* __restrict__ ir, const u32* _
     if (b <= a || b - a > (u64)CE_MAX_INPUT - 16u) continue;
     const u64 node_off = ((a - a0) >> 1) + 8ull * (u64)item;
     const u32 cap = (u32)((((b - a0) >> 1) + 8ull * (u64)(item + 1)) - node_off);
-    cw_place_item(S[warp], ir + node_off * 16, cap, CoopWalk::MAX_NODE);
+    cw_place_item(S[warp], ir + node_off * 16, cap, CoopWalkBig::MAX_NODE);
   }
 }
 
 // Every item the walker handles gets size / status / node count written here; the others are appended to
 // `pending` (order irrelevant).
-__global__ void __launch_bounds__(CW_WARPS * 32, CW_WALK_BLOCKS)
+// SH / FULL: first tier - 256 values per item, strings / plain integers / bools (small, spill-free kernel: every regular
+// item of configs[2]); second tier - 1024 values, every leaf form this walker knows, items of any wire size - over what the
+// first tier appended to `pending`.
+template <class SH, bool FULL>
+__global__ void __launch_bounds__(CW_WARPS * 32, FULL ? 1 : CW_WALK_BLOCKS)
 k_encode_type(const u8* __restrict__ blob, u32 n_msgs, const i32* __restrict__ msg_id, const u8* __restrict__ in,
               const u64* __restrict__ in_off, u8* __restrict__ ir, u32* __restrict__ size, u32* __restrict__ first,
               i32* __restrict__ status, u32* __restrict__ ioff, u32* __restrict__ nnodes, const u32* __restrict__ list,
               const u32* __restrict__ list_n, u32* __restrict__ pending, u32* __restrict__ n_pending) {
   extern __shared__ __align__(16) unsigned char smem[];
-  CoopWalk* S = reinterpret_cast<CoopWalk*>(smem);
+  SH* S = reinterpret_cast<SH*>(smem);
   const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long total = (long long)*list_n;
   const Tables T = ggr_tables(blob);
   const u64 a0 = in_off[0];
   u32* ticket = const_cast<u32*>(list_n) + 2;  // +1 the tokenizer, +3 the place kernel
-  // two tickets in flight: the item after the current one is known when the current one starts, and its token
-  // index, records and text are asked for in L2 (the phases below are chains of small dependent loads)
+  // two tickets in flight (the draw's latency stays off the path).  A bulk L2 prefetch of the next item's index, records
+  // and text (cp.async.bulk.prefetch.L2) was measured here and cost 4 %: the index was written by the two kernels in
+  // front of this one and is L2-resident already (profiles/README.md)
   u32 drawn = wp_ticket_draw(ticket);
   long long slot = wp_ticket_take(drawn);
   drawn = wp_ticket_draw(ticket);
   while (slot < total) {
     const long long next = wp_ticket_take(drawn);
     drawn = wp_ticket_draw(ticket);
-    if (next < total) {
-      const long long it2 = (long long)list[next];
-      const u64 a2 = in_off[it2], b2 = in_off[it2 + 1];
-      if (b2 > a2 && b2 - a2 <= (u64)CE_MAX_INPUT - 16u) {
-        const u64 no2 = ((a2 - a0) >> 1) + 8ull * (u64)it2;
-        const u32 cap2 = (u32)((((b2 - a0) >> 1) + 8ull * (u64)(it2 + 1)) - no2);
-        const u32 len2 = (u32)(b2 - a2);
-        wp_prefetch_l2(in + a2, len2);
-        wp_prefetch_l2(ir + no2 * 16, len2 + (len2 >> 1) + 64u);                       // header, tokens, records (typical sizes)
-        wp_prefetch_l2(ir + (no2 + cap2) * 16 - (len2 + (len2 >> 2)), len2 + (len2 >> 2));  // quote entries, from the end of the region
-      }
-    }
     const long long item = (long long)list[slot];
     const u64 a = in_off[item], b = in_off[item + 1];
     const i32 m = msg_id[item];
@@ -107,7 +100,7 @@ k_encode_type(const u8* __restrict__ blob, u32 n_msgs, const i32* __restrict__ m
       const u64 node_off = ((a - a0) >> 1) + 8ull * (u64)item;
       const u32 cap = (u32)((((b - a0) >> 1) + 8ull * (u64)(item + 1)) - node_off);
       const u32 s0 = (u32)(a & 15ull);
-      ok = cw_type_item(S[warp], T, (u32)m, in + (a & ~15ull), s0, s0 + (u32)(b - a), ir + node_off * 16, ioff + node_off, cap, &res);
+      ok = cw_type_item<SH, FULL>(S[warp], T, (u32)m, in + (a & ~15ull), s0, s0 + (u32)(b - a), ir + node_off * 16, ioff + node_off, cap, &res);
     }
     if (lane == 0) {
       if (ok) {
@@ -127,7 +120,10 @@ k_encode_type(const u8* __restrict__ blob, u32 n_msgs, const i32* __restrict__ m
 }
 
 int ggr_encode_walk_init() {
-  return cudaFuncSetAttribute(k_encode_type, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(CoopWalk) * CW_WARPS)) == cudaSuccess ? 0 : -1;
+  return (cudaFuncSetAttribute(k_encode_type<CoopWalk, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(CoopWalk) * CW_WARPS)) == cudaSuccess &&
+          cudaFuncSetAttribute(k_encode_type<CoopWalkBig, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(CoopWalkBig) * CW_WARPS)) == cudaSuccess)
+             ? 0
+             : -1;
 }
 
 static unsigned cw_grid(const void* fn, int threads, size_t smem, long long n, int sm_count) {
@@ -153,14 +149,23 @@ void ggr_launch_encode_place(cudaStream_t st, long long n, const uint64_t* in_of
   k_encode_place<<<(unsigned)(want < cap ? want : cap), CW_WARPS * 32, 0, st>>>((const u64*)in_off, ir, list, list_n);
 }
 
-void ggr_launch_encode_type(cudaStream_t st, long long n, const uint8_t* blob, uint32_t n_msgs, const int32_t* msg_id, const uint8_t* in,
+// tier 0: the listed items; tier 1: what tier 0 left (list / list_n = its pending list; the length lives on the device)
+void ggr_launch_encode_type(cudaStream_t st, int tier, long long n, const uint8_t* blob, uint32_t n_msgs, const int32_t* msg_id, const uint8_t* in,
                             const uint64_t* in_off, uint8_t* ir, uint32_t* size, uint32_t* first, int32_t* status, uint32_t* ioff,
                             uint32_t* nnodes, const uint32_t* list, const uint32_t* list_n, uint32_t* pending, uint32_t* n_pending,
                             int sm_count) {
-  static unsigned per_sm = 0;
-  const size_t smem = sizeof(CoopWalk) * CW_WARPS;
-  if (!per_sm) per_sm = cw_grid((const void*)k_encode_type, CW_WARPS * 32, smem, 1ll << 40, 1);
-  const long long want = (n + CW_WARPS - 1) / CW_WARPS, cap = (long long)sm_count * per_sm;
-  k_encode_type<<<(unsigned)(want < cap ? want : cap), CW_WARPS * 32, smem, st>>>(blob, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first,
-                                                                                  status, ioff, nnodes, list, list_n, pending, n_pending);
+  if (tier == 0) {
+    static unsigned per_sm = 0;
+    const size_t smem = sizeof(CoopWalk) * CW_WARPS;
+    if (!per_sm) per_sm = cw_grid((const void*)k_encode_type<CoopWalk, false>, CW_WARPS * 32, smem, 1ll << 40, 1);
+    const long long want = (n + CW_WARPS - 1) / CW_WARPS, cap = (long long)sm_count * per_sm;
+    k_encode_type<CoopWalk, false><<<(unsigned)(want < cap ? want : cap), CW_WARPS * 32, smem, st>>>(
+        blob, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending);
+  } else {
+    static unsigned per_sm = 0;
+    const size_t smem = sizeof(CoopWalkBig) * CW_WARPS;
+    if (!per_sm) per_sm = cw_grid((const void*)k_encode_type<CoopWalkBig, true>, CW_WARPS * 32, smem, 1ll << 40, 1);
+    k_encode_type<CoopWalkBig, true><<<(unsigned)sm_count * per_sm, CW_WARPS * 32, smem, st>>>(
+        blob, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending);
+  }
 }

@@ -345,6 +345,16 @@ GGR_DEV FieldD ggr_field(const Tables& t, u32 idx) {
 }
 GGR_DEV u32 ggr_u16(const Tables& t, u32 idx) { return ggr_ld2(t.u16s + (size_t)idx * 2); }
 
+GGR_DEV u32 ggr_atomic_add_u32(u32* p, u32 v) {
+#if defined(__CUDA_ARCH__)
+  return atomicAdd(p, v);
+#else
+  u32 o = *p;
+  *p = o + v;
+  return o;
+#endif
+}
+
 // gRPC message header in front of item [a, b): GST_OK, or why the item cannot be taken
 GGR_DEV int ggr_frame_check(const u8* in, u64 a, u64 b) {
   if (b - a < 5ull) return GST_BAD_WIRE;

@@ -450,7 +450,8 @@ struct CoopWalkT {
   u32 lvl_beg[CW_LEVELS + 2], lvl_cur[CW_LEVELS + 2];
   u32 bail, n_extra, cap;
 };
-typedef CoopWalkT<256> CoopWalk;
+typedef CoopWalkT<256> CoopWalk;       // first tier: 5.9 KB per warp
+typedef CoopWalkT<1024> CoopWalkBig;  // second tier: 18.6 KB per warp (large items, every leaf form)
 
 // ---- cold paths kept out of line: the hot loop of k_encode_type has to fit the instruction caches ----
 GGR_DEVN bool cw_long_name_equals(const u8* in, u32 quote_pos, u32 end, const u8* pool, u32 off, u32 len) {
@@ -573,14 +574,139 @@ GGR_DEV bool cw_scalar_is(const u8* in, u32 pos, u32 end, const char* lit, u32 n
   return ggr_is_ws(c) || c == ',' || c == '}' || c == ']';
 }
 
-// Leaf value of field f at token t.  false: not one of the forms handled here.
-GGR_DEV bool cw_leaf(const Tables& T, const CwIndex& X, const u8* in, u32 end, const FieldD& f, u32 t, CwLeaf* l) {
+// quoted plain integer: "[-]digits" filling the string exactly (protojson takes quoted numbers; no spaces, no escapes here)
+GGR_DEV bool cw_int_quoted(const u8* in, u32 pos, u32 close, bool* neg, u64* mag) {
+  u32 j = pos + 1u;
+  const bool n = j < close && in[j] == '-';
+  if (n) j++;
+  const u32 d0 = j;
+  u64 v = 0;
+  u32 nd = 0;
+  while (j < close && nd < 20u) {
+    const u32 c = (u32)in[j] - '0';
+    if (c >= 10u) return false;
+    v = v * 10u + c;
+    j++;
+    nd++;
+  }
+  if (j != close || nd == 0 || nd > 19u || (nd > 1u && in[d0] == '0')) return false;
+  *neg = n;
+  *mag = v;
+  return true;
+}
+
+// float / double from a plain decimal literal with at most 15 significant digits and a decimal exponent within
+// +-22: mantissa and power of ten are exact doubles, so one multiplication or division rounds correctly
+// (Clinger's fast path; everything else - and NaN / Infinity - goes to the full parser of the next tier).
+// lim: where the literal has to end (closing quote), or 0 for a bare token that ends at a delimiter.
+GGR_DEVN bool cw_float_literal(const u8* in, u32 pos, u32 end, u32 lim, bool is32, u64* bits) {
+  static const double P10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+  const u32 stop = lim ? lim : end;
+  u32 j = pos;
+  bool neg = false;
+  if (j < stop && in[j] == '-') { neg = true; j++; }
+  u64 m = 0;
+  u32 sig = 0, nint = 0;
+  const u32 i0 = j;
+  while (j < stop && (u32)(in[j] - '0') < 10u) {
+    const u32 c = in[j] - '0';
+    if (sig || c) { if (sig >= 15u) return false; m = m * 10u + c; sig++; }
+    j++;
+    nint++;
+  }
+  if (nint == 0 || (nint > 1u && in[i0] == '0')) return false;
+  i32 e10 = 0;
+  if (j < stop && in[j] == '.') {
+    j++;
+    u32 nfrac = 0;
+    while (j < stop && (u32)(in[j] - '0') < 10u) {
+      const u32 c = in[j] - '0';
+      if (sig || c) { if (sig >= 15u) return false; m = m * 10u + c; sig++; }
+      e10--;
+      j++;
+      nfrac++;
+    }
+    if (nfrac == 0) return false;
+  }
+  if (j < stop && (in[j] == 'e' || in[j] == 'E')) {
+    j++;
+    bool eneg = false;
+    if (j < stop && (in[j] == '+' || in[j] == '-')) { eneg = in[j] == '-'; j++; }
+    u32 ne = 0, ev = 0;
+    while (j < stop && (u32)(in[j] - '0') < 10u && ne < 4u) { ev = ev * 10u + (in[j] - '0'); j++; ne++; }
+    if (ne == 0 || (j < stop && (u32)(in[j] - '0') < 10u)) return false;
+    e10 += eneg ? -(i32)ev : (i32)ev;
+  }
+  if (lim) {
+    if (j != lim) return false;
+  } else if (j < end) {
+    const u32 c = in[j];
+    if (!(ggr_is_ws(c) || c == ',' || c == '}' || c == ']')) return false;
+  }
+  double d;
+  if (m == 0) d = 0.0;
+  else if (e10 >= 0 && e10 <= 22) d = (double)m * P10[e10];
+  else if (e10 < 0 && e10 >= -22) d = (double)m / P10[-e10];
+  else return false;
+  if (neg) d = -d;
+  if (is32) {
+    const float f = (float)d;
+    if ((double)f != d) return false;  // would round twice: the full parser rounds the decimal straight to float32
+    u32 b;
+    memcpy(&b, &f, 4);
+    *bits = b;
+  } else {
+    memcpy(bits, &d, 8);
+  }
+  return true;
+}
+
+// bytes field: the base64 text validated and counted exactly as the per-thread parser does (one lane walks the string)
+GGR_DEVN bool cw_bytes_leaf(const u8* in, u32 pos, u32 end, u32* n_out, u32* flags) {
+  Rd r;
+  r.init(in, pos, end);
+  StrInfo si;
+  if (scan_string<true>(r, &si) != GST_OK) return false;
+  StrIter it;
+  it.init(in, pos, end);
+  const bool url = (si.flags & SF_URLSAFE) != 0;
+  u32 n;
+  if (!b64_run<false, Cnt>(it, url, si.dec_len, (Cnt*)0, &n)) return false;
+  *n_out = n;
+  *flags = (url ? NF_URL : 0u) | ((si.dec_len & 3u) ? 0u : NF_PADDED);
+  return true;
+}
+
+// google.protobuf.Timestamp from a plain string token (no escapes): RFC 3339 as time.Parse + protojson accept it
+GGR_DEVN bool cw_timestamp(const u8* in, u32 pos, u32 end, i64* secs, i32* nanos) {
+  StrIter it;
+  it.init(in, pos, end);
+  return parse_timestamp(it, secs, nanos) == GST_OK;
+}
+
+// Leaf value of field f at token t, every form this tier takes.  false: left to the next tier.  Out of line: the hot
+// loop of k_encode_type (strings, plain integers, bools) must not carry this code's registers.
+GGR_DEVN bool cw_leaf_rare(const Tables& T, const CwIndex& X, const u8* in, u32 end, const FieldD& f, u32 t, CwLeaf* l) {
   const u32 k = K3_KIND(t), pos = K3_POS(t);
   switch (f.kind) {
     case GK_STRING: {
       if (k != K3_STR) return false;
       const CwQ q0 = cw_q(X, K3_Q(t)), q1 = cw_q(X, K3_Q(t) + 1u);
-      if (q0.slow != q1.slow) return false;  // control characters, \u, bad escapes: the full scanner
+      if (q0.slow != q1.slow) {
+        // \u escapes (what encoding/json writes for < > & and control characters), or bytes that are errors: the full
+        // scanner decides and gives the decoded length; the emitter decodes such a string with the per-thread iterator
+        Rd r;
+        r.init(in, pos, end);
+        StrInfo si;
+        if (scan_string<false>(r, &si) != GST_OK) return false;
+        l->type = N_STR;
+        l->a = pos;
+        l->b = si.dec_len;
+        l->flags = (si.flags & SF_ESCAPES) ? NF_ESC : 0u;
+        l->body = varint_size(si.dec_len) + si.dec_len;
+        l->zero = si.dec_len == 0;
+        return true;
+      }
       const u32 nesc = (q1.esc - q0.esc) & 0xFFFFu;
       const u32 len = q1.pos - pos - 1u - nesc;  // a simple escape decodes 2 bytes to 1
       l->type = N_STR;
@@ -607,6 +733,11 @@ GGR_DEV bool cw_leaf(const Tables& T, const CwIndex& X, const u8* in, u32 end, c
         bool neg;
         u64 mag;
         if (!cw_int_literal(in, pos, end, &neg, &mag) || !cw_int_value(f.kind, neg, mag, &v)) return false;
+      } else if (k == K3_STR && f.kind != GK_ENUM) {  // quoted number: how clients send 64-bit values
+        const CwQ q0 = cw_q(X, K3_Q(t)), q1 = cw_q(X, K3_Q(t) + 1u);
+        bool neg;
+        u64 mag;
+        if (q0.slow != q1.slow || q0.esc != q1.esc || !cw_int_quoted(in, pos, q1.pos, &neg, &mag) || !cw_int_value(f.kind, neg, mag, &v)) return false;
       } else if (k == K3_STR && f.kind == GK_ENUM) {  // enum by name
         const CwQ q0 = cw_q(X, K3_Q(t)), q1 = cw_q(X, K3_Q(t) + 1u);
         if (q0.slow != q1.slow || q0.esc != q1.esc) return false;
@@ -621,9 +752,74 @@ GGR_DEV bool cw_leaf(const Tables& T, const CwIndex& X, const u8* in, u32 end, c
       l->type = x.type; l->a = x.a; l->b = x.b; l->flags = 0; l->body = x.body; l->zero = x.zero;
       return true;
     }
+    case GK_FLOAT: case GK_DOUBLE: {
+      const bool is32 = f.kind == GK_FLOAT;
+      u64 bits;
+      if (k == K3_SCALAR) {
+        if (!cw_float_literal(in, pos, end, 0u, is32, &bits)) return false;
+      } else if (k == K3_STR) {
+        const CwQ q0 = cw_q(X, K3_Q(t)), q1 = cw_q(X, K3_Q(t) + 1u);
+        if (q0.slow != q1.slow || q0.esc != q1.esc || q1.pos <= pos + 1u || !cw_float_literal(in, pos + 1u, end, q1.pos, is32, &bits)) return false;
+      } else {
+        return false;
+      }
+      l->flags = 0;
+      l->zero = bits == 0;  // -0.0 is "set"
+      l->a = (u32)bits;
+      if (is32) { l->type = N_FIX32; l->b = 0; l->body = 4; }
+      else { l->type = N_FIX64; l->b = (u32)(bits >> 32); l->body = 8; }
+      return true;
+    }
+    case GK_BYTES: {
+      if (k != K3_STR) return false;
+      u32 n, fl;
+      if (!cw_bytes_leaf(in, pos, end, &n, &fl)) return false;
+      l->type = N_BYTES;
+      l->a = pos;
+      l->b = n;
+      l->flags = fl;
+      l->body = varint_size(n) + n;
+      l->zero = n == 0;
+      return true;
+    }
     default:
-      return false;  // float, double, bytes: the other tiers
+      return false;
   }
+}
+
+// The common leaves inline: strings sized in O(1) from the quote table, plain integer literals, bools.
+// FULL = false (the first tier of k_encode_type): nothing else - the kernel stays small and spill-free; FULL = true (second
+// tier, run over what the first leaves): every other form through cw_leaf_rare.
+template <bool FULL>
+GGR_DEV bool cw_leaf(const Tables& T, const CwIndex& X, const u8* in, u32 end, const FieldD& f, u32 t, CwLeaf* l) {
+  const u32 k = K3_KIND(t), pos = K3_POS(t);
+  if (f.kind == GK_STRING) {
+    if (k != K3_STR) return false;
+    const CwQ q0 = cw_q(X, K3_Q(t)), q1 = cw_q(X, K3_Q(t) + 1u);
+    if (q0.slow != q1.slow) return FULL ? cw_leaf_rare(T, X, in, end, f, t, l) : false;  // \u escapes, control characters
+    const u32 nesc = (q1.esc - q0.esc) & 0xFFFFu;
+    const u32 len = q1.pos - pos - 1u - nesc;  // a simple escape decodes 2 bytes to 1
+    l->type = N_STR;
+    l->a = pos;
+    l->b = len;
+    l->flags = nesc ? (NF_ESC | NF_SIMPLE) : 0u;
+    l->body = varint_size(len) + len;
+    l->zero = len == 0;
+    return true;
+  }
+  if (k == K3_SCALAR && f.kind != GK_FLOAT && f.kind != GK_DOUBLE && f.kind != GK_BOOL && f.kind != GK_BYTES) {
+    bool neg;
+    u64 mag, v;
+    if (cw_int_literal(in, pos, end, &neg, &mag) && cw_int_value(f.kind, neg, mag, &v)) {
+      Leaf x;
+      leaf_from_int(f.kind, v, &x);
+      l->type = x.type; l->a = x.a; l->b = x.b; l->flags = 0; l->body = x.body; l->zero = x.zero;
+      return true;
+    }
+    return false;  // 1.0, 1e2, out of range: the full parser decides
+  }
+  if (!FULL) return false;
+  return cw_leaf_rare(T, X, in, end, f, t, l);
 }
 
 // plain string tokens a < b (raw bytes, Go string order)?  Both known to hold no escapes.
@@ -639,6 +835,31 @@ GGR_DEV bool cw_plain_less(const u8* in, u32 a_pos, u32 a_end, u32 b_pos, u32 b_
   return na < nb;
 }
 
+// google.protobuf.Timestamp value at token t: a string in JSON, {seconds = 1, nanos = 2} on the wire; the two varints ride
+// in extra IR nodes behind the message node r and are written with it (offset marker 0xFFFFFFFF).  Out of line (rare).
+GGR_DEVN bool cw_ts_leaf(const CwIndex& X, const u8* in, u32 end, u32 t, u32 tag, u32 tag_len, u8* ir, u32* io, u32 r, u32 n_rec,
+                         u32* n_extra, u32 cap, u32* body) {
+  const CwQ q0 = cw_q(X, K3_Q(t)), q1 = cw_q(X, K3_Q(t) + 1u);
+  i64 secs = 0;
+  i32 nanos = 0;
+  if (K3_KIND(t) != K3_STR || q0.slow != q1.slow || q0.esc != q1.esc || !cw_timestamp(in, K3_POS(t), end, &secs, &nanos)) return false;
+  const u32 x = wp_atomic_add(n_extra, 2u);
+  if (n_rec + x + 2u > cap) return false;
+  const u32 sidx = n_rec + x, nidx = n_rec + x + 1u;
+  u32 payload = 0;
+  if (nanos != 0) payload += 1u + varint_size((u64)(u32)nanos);
+  if (secs != 0) payload += 1u + varint_size((u64)secs);
+  node_store(ir, nidx, (u32)nanos, 0, GGR_NIL, 1, nanos != 0 ? node_meta(N_VARINT, 0, 16) : node_meta(N_SKIP, 0, 0));
+  node_store(ir, sidx, (u32)(u64)secs, (u32)((u64)secs >> 32), nanos != 0 ? nidx : GGR_NIL, 0,
+             secs != 0 ? node_meta(N_VARINT, 0, 8) : node_meta(N_SKIP, 0, 0));
+  const u32 first_child = secs != 0 ? sidx : (nanos != 0 ? nidx : GGR_NIL);
+  node_store(ir, r, payload, first_child, GGR_NIL, 0, node_meta(N_MSG, 0, tag));
+  io[sidx] = 0xFFFFFFFFu;
+  io[nidx] = 0xFFFFFFFFu;
+  *body = tag_len + varint_size(payload) + payload;
+  return true;
+}
+
 // bytes of the key field of a map entry (tag, length, text) from its IR node
 GGR_DEV u32 cw_keypart_of(const u8* ir, u32 x) {
   const u32 klen = node_load(ir, x).y;
@@ -648,7 +869,7 @@ GGR_DEV u32 cw_keypart_of(const u8* ir, u32 x) {
 // One item, all 32 lanes.  Returns true when the item was handled (IR nodes + offsets written, *res
 // filled); false leaves it to the next tier.  region / cap: the item's IR region with the token index of
 // cw_tok_item and the value records of cw_place_item in it; ioff: one u32 per IR node of the region.
-template <class SH>
+template <class SH, bool FULL>
 GGR_DEV bool cw_type_item(SH& S, const Tables& T, u32 root_msg, const u8* in, u32 start, u32 end, u8* region, u32* ioff, u32 cap,
                           EncResult* res) {
   const u32 lane = wp_lane();
@@ -774,6 +995,7 @@ GGR_DEV bool cw_type_item(SH& S, const Tables& T, u32 root_msg, const u8* in, u3
         FieldD f;
         bool in_list = false;
         u32 key_pos = 0, key_end = 0, key_esc = 0;
+        bool is_ts = false;
         if (pc == CW_MSG || pc == CW_EMSG) {
           // member of a message: "key" : value
           const u32 kt = cw_ldg(X.tok + i - 1u);
@@ -811,9 +1033,15 @@ GGR_DEV bool cw_type_item(SH& S, const Tables& T, u32 root_msg, const u8* in, u3
                 cls = CW_MAP;
               } else if (f.flags & GF_REPEATED) {
                 if (k != K3_LBRACK) ok = (CW_WHY(107), false);
-                if (f.kind == GK_MESSAGE && ggr_msg(T, (u32)f.child).wkt != GGR_WKT_NONE) ok = (CW_WHY(108), false);
+                if (f.kind == GK_MESSAGE) {
+                  const u32 w = ggr_msg(T, (u32)f.child).wkt;
+                  if (w != GGR_WKT_NONE && w != GGR_WKT_TIMESTAMP) ok = (CW_WHY(108), false);
+                }
                 cls = (f.flags & GF_PACKED) ? CW_LISTP : CW_LIST;
                 hdr = f.tag_len;
+              } else if (f.kind == GK_MESSAGE && ggr_msg(T, (u32)f.child).wkt == GGR_WKT_TIMESTAMP) {
+                cls = CW_LEAF;
+                is_ts = true;
               } else if (f.kind == GK_MESSAGE) {
                 if (k != K3_LBRACE || (u32)f.child >= 0xFFFFu || ggr_msg(T, (u32)f.child).wkt != GGR_WKT_NONE) ok = (CW_WHY(109), false);
                 cls = CW_MSG;
@@ -828,7 +1056,10 @@ GGR_DEV bool cw_type_item(SH& S, const Tables& T, u32 root_msg, const u8* in, u3
           gf = S.gfield[p];
           f = ggr_field(T, gf);
           in_list = true;
-          if (f.kind == GK_MESSAGE) {
+          if (f.kind == GK_MESSAGE && ggr_msg(T, (u32)f.child).wkt == GGR_WKT_TIMESTAMP) {
+            cls = CW_LEAF;
+            is_ts = true;
+          } else if (f.kind == GK_MESSAGE) {
             if (k != K3_LBRACE || (u32)f.child >= 0xFFFFu) ok = (CW_WHY(110), false);
             cls = CW_MSG;
             aux = (u32)f.child;
@@ -868,9 +1099,11 @@ GGR_DEV bool cw_type_item(SH& S, const Tables& T, u32 root_msg, const u8* in, u3
         } else {
           ok = (CW_WHY(116), false);
         }
-        if (ok && (cls == CW_LEAF || cls == CW_ELEAF)) {
+        if (ok && is_ts) {
+          if (!FULL || !cw_ts_leaf(X, in, end, t, f.tag, f.tag_len, ir, io, r, n_rec, &S.n_extra, S.cap, &body)) ok = (CW_WHY(119), false);
+        } else if (ok && (cls == CW_LEAF || cls == CW_ELEAF)) {
           CwLeaf l;
-          if ((k != K3_STR && k != K3_SCALAR) || !cw_leaf(T, X, in, end, f, t, &l)) {
+          if ((k != K3_STR && k != K3_SCALAR) || !cw_leaf<FULL>(T, X, in, end, f, t, &l)) {
             ok = (CW_WHY(117), false);
           } else if (cls == CW_LEAF) {
             const bool packed = pc == CW_LISTP;
@@ -1008,7 +1241,8 @@ GGR_DEV bool cw_type_item(SH& S, const Tables& T, u32 root_msg, const u8* in, u3
     }
   }
   const u32 total = S.body[0];
-  if (total > CE_STAGE) return (CW_WHY(10), false);  // the lock-step emitter stages an item in shared memory; larger ones: other tiers
+  // the lock-step emitter stages an item in shared memory; larger ones are written in place - second tier only
+  if (total > (FULL ? 0x0FFFFFFFu : CE_STAGE)) return (CW_WHY(10), false);
   WP_SYNC();
   // ---- W5: offsets, top-down ----
   if (lane == 0) S.body[0] = 0;

@@ -241,6 +241,7 @@ static int hs_encode_coop_t(void* h, int msg, const uint8_t* json, uint32_t n, u
 struct WalkArgs {
   u32 sh[4];
   CoopWalk* S;
+  CoopWalkBig* SB;
   CwPlaceSh* P;
   const CwLut* lut;
   Tables T;
@@ -261,11 +262,15 @@ static void walk_tok_body(void* p, u32 lane) {
 }
 static void walk_place_body(void* p, u32 lane) {
   WalkArgs* a = (WalkArgs*)p;
-  cw_place_item(*a->P, a->region, a->cap, CoopWalk::MAX_NODE);
+  cw_place_item(*a->P, a->region, a->cap, CoopWalkBig::MAX_NODE);
 }
 static void walk_body(void* p, u32 lane) {
   WalkArgs* a = (WalkArgs*)p;
-  a->ok[lane] = cw_type_item(*a->S, a->T, a->msg, a->in, a->start, a->end, a->region, a->ioff, a->cap, &a->res[lane]);
+  a->ok[lane] = cw_type_item<CoopWalk, false>(*a->S, a->T, a->msg, a->in, a->start, a->end, a->region, a->ioff, a->cap, &a->res[lane]);
+}
+static void walk_body_full(void* p, u32 lane) {
+  WalkArgs* a = (WalkArgs*)p;
+  a->ok[lane] = cw_type_item<CoopWalkBig, true>(*a->SB, a->T, a->msg, a->in, a->start, a->end, a->region, a->ioff, a->cap, &a->res[lane]);
 }
 static void walk_emit_body(void* p, u32 lane) {
   WalkArgs* a = (WalkArgs*)p;
@@ -314,7 +319,12 @@ extern "C" int hs_encode_walk(void* h, int msg, const uint8_t* json, uint32_t n,
   }
   if (!werr) werr = hw_run_warp(walk_place_body, &a);
   if (getenv("HS_DEBUG")) fprintf(stderr, "place: n_rec=%u\n", ((const u32*)region)[3]);
+  static CoopWalkBig SB;
+  memset(&SB, 0xAB, sizeof SB);
+  a.SB = &SB;
   if (!werr) werr = hw_run_warp(walk_body, &a);
+  // what the first tier leaves goes to the second (all leaf forms, 1024 values, items of any size)
+  if (!werr && !a.ok[0] && !getenv("HS_WALK_TIER1_ONLY")) werr = hw_run_warp(walk_body_full, &a);
   if (werr) {
     free(region);
     return 300 + werr;
@@ -428,7 +438,11 @@ int hs_decode(void* h, int msg, const uint8_t* wire, uint32_t n, uint32_t in_off
   memcpy(in + in_off, wire, n);
   Tables T = ggr_tables(s->blob);
   DecResult res;
-  int st = decode_size(T, (u32)msg, in, in_off, in_off + n, flags, &res);
+  static std::vector<U4> pool(1 << 16);
+  static u32 pool_ctr;
+  pool_ctr = 0;
+  U4* sp = getenv("HS_NO_SORT_POOL") ? nullptr : pool.data();
+  int st = decode_size(T, (u32)msg, in, in_off, in_off + n, flags, &res, true, GGR_FULL_MASK, sp, &pool_ctr, (u32)pool.size());
   *out_n = 0;
   if (st == GST_OK) {
     if (res.size > out_cap) return GST_NO_SPACE;
@@ -436,7 +450,7 @@ int hs_decode(void* h, int msg, const uint8_t* wire, uint32_t n, uint32_t in_off
     uint8_t* ob = (uint8_t*)(((uintptr_t)ob_raw.data() + 15) & ~(uintptr_t)15);
     std::vector<uint8_t> before(ob, ob + out_off + res.size + 32);
     uint32_t end_pos = 0;
-    st = decode_write(T, (u32)msg, in, in_off, in_off + n, flags, res.mode, ob, out_off, &end_pos);
+    st = decode_write(T, (u32)msg, in, in_off, in_off + n, flags, res.mode, ob, out_off, &end_pos, true, GGR_FULL_MASK, sp, &pool_ctr, (u32)pool.size());
     if (st == GST_OK && end_pos != out_off + res.size) st = 100;
     for (uint32_t i = 0; i < out_off && st == GST_OK; i++)
       if (ob[i] != before[i]) st = 101;

@@ -468,3 +468,37 @@ def test_mixed_replay_shapes(oracle, hsim):
         st, ej = hsim.decode(pn, w, 0, i % 16, (i * 7) % 16)
         assert rc == 0 and st == 0 and ej == oj, (pn, w.hex()[:300])
     assert walked > 150  # floats, bytes, quoted numbers, timestamps: the fused kernel (profiles/README.md)
+
+
+def test_decode_unsorted_maps(oracle, hsim):
+    """maps as a Go backend sends them (iteration order, not key order), with duplicate keys: the sort-pool path of the
+    per-thread walker against the oracle, for string, signed and unsigned keys, in the fast and in the slow walk"""
+    rng = random.Random(44)
+
+    def varint(v):
+        out = bytearray()
+        while v >= 0x80:
+            out.append(v & 0x7F | 0x80)
+            v >>= 7
+        out.append(v)
+        return bytes(out)
+
+    def ld(num, payload):
+        return varint(num << 3 | 2) + varint(len(payload)) + payload
+
+    for trial in range(12):
+        n = rng.choice([9, 40, 300])
+        ent = []
+        for i in range(n):
+            k = "k%d_%s" % (rng.randrange(n), "x" * rng.randrange(3))
+            ent.append(ld(41, ld(1, k.encode()) + varint(2 << 3) + varint(rng.randrange(1 << 31))))              # m_str_int32
+        for i in range(n):
+            ent.append(ld(42, varint(1 << 3) + varint(rng.randrange(n) ^ ((1 << 64) - 1 if rng.random() < 0.3 else 0)) + ld(2, b"v%d" % i)))  # m_int32_str
+        for i in range(n // 2):
+            ent.append(ld(45, varint(1 << 3) + varint(rng.randrange(1 << 40)) + ld(2, bytes([i & 255]) * 3)))   # m_uint64_bytes
+        wire = b"".join(ent)
+        if trial & 1:
+            wire = varint(100 << 3 | 2) + varint(1) + b"z" + wire  # z_last first: fields out of declaration order -> slow walk
+        rc, oj, _ = oracle.decode(cases.A, wire)
+        st, ej = hsim.decode(cases.A, wire, 0, trial % 16, (trial * 3) % 16)
+        assert rc == 0 and st == 0 and ej == oj, (trial, n)
