@@ -316,6 +316,8 @@ struct DecCtx {
   U4* sort_pool = nullptr;
   u32* sort_ctr = nullptr;
   u32 sort_cap = 0;
+  // 1: `in` is scratch this thread wrote (the merged payload of a split sub-message): plain loads
+  u32 rw = 0;
 };
 
 template <class W>
@@ -453,12 +455,73 @@ GGR_DEV int scalar_value(W& w, const DecCtx& cx, Rd& r, u32 lim, u32 kind, i32 c
   return GST_OK;
 }
 
+// ---- split sub-messages (proto.Unmarshal merges, reflection.go:363) ----
+// A singular message field that occurs more than once on the wire is parsed occurrence after occurrence into the
+// same message: scalars last-wins, repeated fields append, sub-messages merge again.  That is what parsing the
+// concatenation of the payloads gives, once every occurrence is well-formed on its own (checked here, because a
+// truncated occurrence must not borrow bytes from the next one).  The concatenation lives in the scratch pool.
+GGR_DEV u8* dec_scratch(const DecCtx& cx, u32 bytes) {
+  if (!cx.sort_pool) return nullptr;
+  const u32 units = (bytes + 15u) / 16u + 1u;  // the readers fetch whole 16-byte chunks
+  const u32 base = ggr_atomic_add_u32(cx.sort_ctr, units);
+  if (base > cx.sort_cap || units > cx.sort_cap - base) return nullptr;
+  return reinterpret_cast<u8*>(cx.sort_pool + base);
+}
+// payloads of all length-delimited occurrences of field `num` among the top-level fields of cx.in[start, end)
+GGR_DEVN int merge_occurrences(const DecCtx& cx, u32 start, u32 end, u32 num, const u8** out, u32* out_len) {
+  u8* dst = nullptr;
+  u32 total = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    Rd t;
+    t.init(cx.in, start, end, cx.rw);
+    u32 at = 0;
+    while (t.pos < end) {
+      u64 tag;
+      if (!rd_varint(t, end, &tag)) return GST_BAD_WIRE;
+      const u64 n2 = tag >> 3;
+      const u32 wt = (u32)(tag & 7);
+      if (n2 == 0 || n2 > 0x1FFFFFFFull || wt == 4 || wt > 5) return GST_BAD_WIRE;
+      if ((u32)n2 != num || wt != 2) {
+        if (!rd_skip_value(t, end, (u32)n2, wt)) return GST_BAD_WIRE;
+        continue;
+      }
+      u64 len;
+      if (!rd_varint(t, end, &len) || len > (u64)(end - t.pos)) return GST_BAD_WIRE;
+      const u32 lim = t.pos + (u32)len;
+      if (pass == 0) {
+        total += (u32)len;
+        while (t.pos < lim) {  // the occurrence on its own
+          u64 tg;
+          if (!rd_varint(t, lim, &tg)) return GST_BAD_WIRE;
+          const u64 n3 = tg >> 3;
+          const u32 w3 = (u32)(tg & 7);
+          if (n3 == 0 || n3 > 0x1FFFFFFFull || w3 == 4 || w3 > 5) return GST_BAD_WIRE;
+          if (!rd_skip_value(t, lim, (u32)n3, w3)) return GST_BAD_WIRE;
+        }
+        if (t.pos != lim) return GST_BAD_WIRE;
+      } else {
+        for (u32 p = t.pos; p < lim; p++) dst[at++] = cx.in[p];
+        rd_jump(t, lim);
+      }
+    }
+    if (pass == 0) {
+      dst = dec_scratch(cx, total);
+      if (!dst) return GST_UNSUPPORTED;  // no pool (or exhausted): never a different answer
+    }
+  }
+  *out = dst;
+  *out_len = total;
+  return GST_OK;
+}
+
 // ---- map entries ----
 struct MapEnt {
   u64 key;      // numeric key / (pos | len << 32) of a string key's payload
   u32 val_pos;  // position of the value's payload-or-varint start (after its tag); 0 = absent
   u32 val_len;  // for LEN values: payload length
   u32 end;      // end of the entry payload
+  u32 beg;      // start of the entry payload
+  u32 multi;    // message value split over several occurrences inside the entry: merged when written
 };
 // Parses one map entry payload [r.pos, lim): key (field 1) and value (field 2), last wins.
 GGR_DEV int parse_map_entry(Rd& r, u32 lim, const FieldD& kf, const FieldD& vf, MapEnt* me) {
@@ -466,6 +529,8 @@ GGR_DEV int parse_map_entry(Rd& r, u32 lim, const FieldD& kf, const FieldD& vf, 
   me->val_pos = 0;
   me->val_len = 0;
   me->end = lim;
+  me->beg = r.pos;
+  me->multi = 0;
   bool str_key = kf.kind == GK_STRING;
   if (str_key) me->key = (u64)r.pos;  // empty string key: len 0 at any position
   u32 val_seen = 0;
@@ -499,7 +564,7 @@ GGR_DEV int parse_map_entry(Rd& r, u32 lim, const FieldD& kf, const FieldD& vf, 
         if (!rd_fixed64(r, lim, &me->key)) return GST_BAD_WIRE;
       }
     } else if (num == 2 && wt == vf.wt) {
-      if (vf.kind == GK_MESSAGE && val_seen) return GST_UNSUPPORTED;  // merging split map values
+      if (vf.kind == GK_MESSAGE && val_seen) me->multi = 1;  // split value: put_map_value merges
       val_seen = 1;
       me->val_pos = r.pos;
       if (wt == 2) {
@@ -521,8 +586,8 @@ GGR_DEV int cmp_map_keys(const DecCtx& cx, u32 kkind, u64 a, u64 b) {
   if (kkind == GK_STRING) {
     u32 la = (u32)(a >> 32), lb = (u32)(b >> 32);
     Rd ra, rb;
-    ra.init(cx.in, (u32)a, (u32)a + la);
-    rb.init(cx.in, (u32)b, (u32)b + lb);
+    ra.init(cx.in, (u32)a, (u32)a + la, cx.rw);
+    rb.init(cx.in, (u32)b, (u32)b + lb, cx.rw);
     u32 n = la < lb ? la : lb;
     while (n >= 4) {
       u32 x = ra.peek4(), y = rb.peek4();
@@ -555,7 +620,7 @@ template <class W>
 GGR_DEV int put_map_key(W& w, const DecCtx& cx, u32 kkind, u64 key) {
   if (kkind == GK_STRING) {
     Rd r;
-    r.init(cx.in, (u32)key, (u32)key + (u32)(key >> 32));
+    r.init(cx.in, (u32)key, (u32)key + (u32)(key >> 32), cx.rw);
     return put_json_string(w, r, (u32)(key >> 32));
   }
   w.put1('"');
@@ -587,6 +652,7 @@ struct DFrame {
   u32 scan;       // resume position of the current field's occurrence scan
   u32 cur_emit;   // emit index of the field being scanned
   u32 state;      // slow: 0 = advance to next field, 1 = inside repeated occurrences
+  const u8* base; // slow: the buffer the positions refer to (the input, or the merged payload of a split sub-message)
 };
 
 // Emits all entries of map field `f` found as a contiguous run of tags starting at r.pos
@@ -602,13 +668,26 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 msg, u32 start, u32 end, i
 
 template <class W, bool SLOW>
 GGR_DEV int put_map_value(W& w, const DecCtx& cx, const FieldD& vf, const MapEnt& me, int rec) {
+  if (vf.kind == GK_MESSAGE && me.multi) {
+    if (!SLOW) return GGR_NEED_SLOW;
+    MsgD vd = ggr_msg(cx.T, (u32)vf.child);
+    if (vd.wkt != GGR_WKT_NONE && vd.wkt != GGR_WKT_TIMESTAMP) return GST_UNSUPPORTED;
+    DecCtx mc = cx;
+    const u8* mb;
+    u32 ml;
+    int st = merge_occurrences(cx, me.beg, me.end, 2, &mb, &ml);
+    if (st != GST_OK) return st;
+    mc.in = mb;
+    mc.rw = 1;
+    return walk_message<W, SLOW>(w, mc, (u32)vf.child, 0, ml, rec + 1, true, ggr_activemask());
+  }
   if (vf.kind == GK_MESSAGE) {
     MsgD vd = ggr_msg(cx.T, (u32)vf.child);
     if (vd.wkt == GGR_WKT_TIMESTAMP) {
       i64 s = 0, n = 0;
       if (me.val_pos) {
         Rd r;
-        r.init(cx.in, me.val_pos, me.val_pos + me.val_len);
+        r.init(cx.in, me.val_pos, me.val_pos + me.val_len, cx.rw);
         int st = read_timestamp_payload(r, me.val_pos + me.val_len, &s, &n);
         if (st != GST_OK) return st;
       }
@@ -654,7 +733,7 @@ GGR_DEV int put_map_value(W& w, const DecCtx& cx, const FieldD& vf, const MapEnt
   }
   Rd r;
   u32 lim = me.end;
-  r.init(cx.in, me.val_pos, lim);
+  r.init(cx.in, me.val_pos, lim, cx.rw);
   if (vf.wt == 2) {
     // scalar_value re-reads the length prefix: step back is not possible, so emit directly
     bool z;
@@ -706,7 +785,7 @@ GGR_DEV int put_map_field(W& w, const DecCtx& cx, Rd& r, const FieldD& f, u32 ps
       run_start = pstart;
       run_end = pend;
       Rd t;
-      t.init(cx.in, pstart, pend);
+      t.init(cx.in, pstart, pend, cx.rw);
       while (t.pos < pend) {
         u64 tag;
         if (!rd_varint(t, pend, &tag)) return GST_BAD_WIRE;
@@ -736,7 +815,7 @@ GGR_DEV int put_map_field(W& w, const DecCtx& cx, Rd& r, const FieldD& f, u32 ps
       U4* A = cx.sort_pool + base;
       {
         Rd t;
-        t.init(cx.in, run_start, run_end);
+        t.init(cx.in, run_start, run_end, cx.rw);
         bool first_in_run = !SLOW;
         u32 k = 0;
         while (t.pos < run_end && k < count) {
@@ -793,7 +872,7 @@ GGR_DEV int put_map_field(W& w, const DecCtx& cx, Rd& r, const FieldD& f, u32 ps
           if (cmp_map_keys(cx, kf.kind, (u64)e.x | ((u64)e.y << 32), (u64)nx.x | ((u64)nx.y << 32)) == 0) continue;
         }
         Rd t;
-        t.init(cx.in, e.z, run_end);
+        t.init(cx.in, e.z, run_end, cx.rw);
         u64 len;
         if (!rd_varint(t, run_end, &len)) return GST_BAD_WIRE;
         MapEnt me;
@@ -822,7 +901,7 @@ GGR_DEV int put_map_field(W& w, const DecCtx& cx, Rd& r, const FieldD& f, u32 ps
     MapEnt best;
     bool have_best = false;
     Rd t;
-    t.init(cx.in, run_start, run_end);
+    t.init(cx.in, run_start, run_end, cx.rw);
     bool first_in_run = !SLOW;
     while (t.pos < run_end) {
       if (!first_in_run) {
@@ -884,13 +963,15 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
   DFrame fr;
   fr.end = end; fr.msg = root_msg; fr.last_decl = -1; fr.open = 0; fr.first = 1; fr.elem_first = 1; fr.oneofs = 0;
   fr.start = start; fr.scan = start; fr.cur_emit = 0; fr.state = 0;
+  fr.base = cx.in;
+  DecCtx lc = cx;  // slow walk: the context of the current frame (lc.in = fr.base)
   MsgD md;
   if (!finished && rec > GGR_DEC_MAX_REC) {
     result = GST_DEPTH;
     finished = true;
   }
   if (!finished) {
-    r.init(cx.in, start, end);
+    r.init(cx.in, start, end, cx.rw);
     md = ggr_msg(T, root_msg);
     if (md.wkt == GGR_WKT_TIMESTAMP) {
       i64 s, n;
@@ -1063,6 +1144,8 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
       }
     } else {
       // ================= slow walk =================
+      lc.in = fr.base;
+      lc.rw = fr.base != cx.in ? 1u : cx.rw;
       // fr.last_decl + 1 is the next declaration index to handle; fr.state == 1 means we are in
       // the middle of a repeated message field (resume scanning at fr.scan)
       if (fr.state == 0) {
@@ -1073,7 +1156,7 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
           if (md.n_fields == 0) {
             // still need to validate the bytes
             Rd t;
-            t.init(cx.in, fr.start, fr.end);
+            t.init(lc.in, fr.start, fr.end, lc.rw);
             while (t.pos < fr.end) {
               u64 tag;
               if (!rd_varint(t, fr.end, &tag)) GGR_RET(GST_BAD_WIRE);
@@ -1101,20 +1184,20 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
         Cnt c;
         c.pos = 0;
         Rd t;
-        t.init(cx.in, fr.start, fr.end);
-        int st = put_map_field<Cnt, true>(c, cx, t, f, fr.start, fr.end, rec);
+        t.init(lc.in, fr.start, fr.end, lc.rw);
+        int st = put_map_field<Cnt, true>(c, lc, t, f, fr.start, fr.end, rec);
         if (st != GST_OK) GGR_RET(st);
         if (c.pos == 0) continue;
-        put_sep(w, cx, fr.first);
+        put_sep(w, lc, fr.first);
         put_pool(w, T.pool, f.name_off, f.name_len);
-        st = put_map_field<W, true>(w, cx, t, f, fr.start, fr.end, rec);
+        st = put_map_field<W, true>(w, lc, t, f, fr.start, fr.end, rec);
         if (st != GST_OK) GGR_RET(st);
         continue;
       }
       bool repeated = (f.flags & GF_REPEATED) != 0;
       // scan for occurrences from fr.scan
       Rd t;
-      t.init(cx.in, fr.scan, fr.end);
+      t.init(lc.in, fr.scan, fr.end, lc.rw);
       u32 last_pos = 0, last_wt = 0;  // singular: position after the tag of the last occurrence
       u32 n_occ = 0;
       bool pushed = false;
@@ -1143,29 +1226,29 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
           u32 lim = t.pos + (u32)len;
           while (t.pos < lim) {
             if (!fr.open) {
-              put_sep(w, cx, fr.first);
+              put_sep(w, lc, fr.first);
               put_pool(w, T.pool, f.name_off, f.name_len);
               w.put1('[');
               fr.open = 1;
             }
-            put_sep(w, cx, fr.elem_first);
+            put_sep(w, lc, fr.elem_first);
             bool z;
-            int st = scalar_value<W, true>(w, cx, t, lim, f.kind, f.child, false, &z);
+            int st = scalar_value<W, true>(w, lc, t, lim, f.kind, f.child, false, &z);
             if (st != GST_OK) GGR_RET(st);
           }
           if (t.pos != lim) GGR_RET(GST_BAD_WIRE);
           continue;
         }
         if (!fr.open) {
-          put_sep(w, cx, fr.first);
+          put_sep(w, lc, fr.first);
           put_pool(w, T.pool, f.name_off, f.name_len);
           w.put1('[');
           fr.open = 1;
         }
-        put_sep(w, cx, fr.elem_first);
+        put_sep(w, lc, fr.elem_first);
         if (f.kind != GK_MESSAGE) {
           bool z;
-          int st = scalar_value<W, true>(w, cx, t, fr.end, f.kind, f.child, false, &z);
+          int st = scalar_value<W, true>(w, lc, t, fr.end, f.kind, f.child, false, &z);
           if (st != GST_OK) GGR_RET(st);
           continue;
         }
@@ -1207,7 +1290,7 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
       if (f.oneof >= 0) {
         bool later = false;
         Rd q;
-        q.init(cx.in, last_pos, fr.end);
+        q.init(lc.in, last_pos, fr.end, lc.rw);
         if (!rd_skip_value(q, fr.end, f.number, last_wt)) GGR_RET(GST_BAD_WIRE);
         while (q.pos < fr.end && !later) {
           u64 tag;
@@ -1223,14 +1306,59 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
         if (later) continue;
       }
       if (f.kind == GK_MESSAGE) {
-        if (n_occ > 1) GGR_RET(GST_UNSUPPORTED);  // merging split sub-messages is not implemented
+        MsgD cd = ggr_msg(T, (u32)f.child);
+        if (n_occ > 1) {
+          // split over several occurrences: walk the merged payload (its own buffer) as the child frame
+          if (cd.wkt != GGR_WKT_NONE && cd.wkt != GGR_WKT_TIMESTAMP) GGR_RET(GST_UNSUPPORTED);
+          u32 mstart = fr.start;
+          if (f.oneof >= 0) {  // a sibling set in between clears the member: only what follows it merges
+            Rd q;
+            q.init(lc.in, fr.start, fr.end, lc.rw);
+            while (q.pos < last_pos) {
+              u64 tag;
+              if (!rd_varint(q, fr.end, &tag)) GGR_RET(GST_BAD_WIRE);
+              u32 n3 = (u32)(tag >> 3), w3 = (u32)(tag & 7);
+              i32 e3 = find_field(T, md, n3);
+              bool sib = false;
+              if (e3 >= 0 && (u32)e3 != fr.cur_emit) {
+                FieldD g = ggr_field(T, md.field_first + (u32)e3);
+                sib = g.oneof == f.oneof && w3 == g.wt;
+              }
+              if (!rd_skip_value(q, fr.end, n3, w3)) GGR_RET(GST_BAD_WIRE);
+              if (sib) mstart = q.pos;
+            }
+          }
+          const u8* mb;
+          u32 ml;
+          int st = merge_occurrences(lc, mstart, fr.end, f.number, &mb, &ml);
+          if (st != GST_OK) GGR_RET(st);
+          put_sep(w, lc, fr.first);
+          put_pool(w, T.pool, f.name_off, f.name_len);
+          if (cd.wkt == GGR_WKT_TIMESTAMP) {
+            Rd q;
+            q.init(mb, 0, ml, 1);
+            i64 s, n;
+            st = read_timestamp_payload(q, ml, &s, &n);
+            if (st != GST_OK) GGR_RET(st);
+            st = put_timestamp(w, s, n);
+            if (st != GST_OK) GGR_RET(st);
+            continue;
+          }
+          if (depth >= GGR_DEC_MAX_DEPTH - 1) GGR_RET(GST_DEPTH);
+          stk[depth++] = fr;
+          fr.end = ml; fr.msg = (u32)f.child; fr.last_decl = -1; fr.open = 0; fr.first = 1; fr.elem_first = 1; fr.oneofs = 0;
+          fr.start = 0; fr.scan = 0; fr.cur_emit = 0; fr.state = 0;
+          fr.base = mb;
+          md = cd;
+          w.put1('{');
+          continue;
+        }
         Rd q;
-        q.init(cx.in, last_pos, fr.end);
+        q.init(lc.in, last_pos, fr.end, lc.rw);
         u64 len;
         if (!rd_varint(q, fr.end, &len) || len > (u64)(fr.end - q.pos)) GGR_RET(GST_BAD_WIRE);
         u32 lim = q.pos + (u32)len;
-        MsgD cd = ggr_msg(T, (u32)f.child);
-        put_sep(w, cx, fr.first);
+        put_sep(w, lc, fr.first);
         put_pool(w, T.pool, f.name_off, f.name_len);
         if (cd.wkt == GGR_WKT_TIMESTAMP) {
           i64 s, n;
@@ -1252,7 +1380,7 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
       // singular scalar: the last occurrence wins; every occurrence must still be valid
       {
         Rd q;
-        q.init(cx.in, fr.start, fr.end);
+        q.init(lc.in, fr.start, fr.end, lc.rw);
         // validate all occurrences (strings: UTF-8) the way proto.Unmarshal would
         while (q.pos < fr.end) {
           u64 tag;
@@ -1262,26 +1390,26 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
             bool z;
             Cnt c;
             c.pos = 0;
-            int st = scalar_value<Cnt, false>(c, cx, q, fr.end, f.kind, f.child, false, &z);
+            int st = scalar_value<Cnt, false>(c, lc, q, fr.end, f.kind, f.child, false, &z);
             if (st != GST_OK) GGR_RET(st);
           } else if (!rd_skip_value(q, fr.end, n3, w3)) {
             GGR_RET(GST_BAD_WIRE);
           }
         }
-        q.init(cx.in, last_pos, fr.end);
+        q.init(lc.in, last_pos, fr.end, lc.rw);
         if (!(f.flags & GF_PRESENCE)) {
           Rd t2 = q;
           bool z;
           Cnt c;
           c.pos = 0;
-          int st = scalar_value<Cnt, false>(c, cx, t2, fr.end, f.kind, f.child, false, &z);
+          int st = scalar_value<Cnt, false>(c, lc, t2, fr.end, f.kind, f.child, false, &z);
           if (st != GST_OK) GGR_RET(st);
           if (z) continue;
         }
-        put_sep(w, cx, fr.first);
+        put_sep(w, lc, fr.first);
         put_pool(w, T.pool, f.name_off, f.name_len);
         bool z;
-        int st = scalar_value<W, true>(w, cx, q, fr.end, f.kind, f.child, false, &z);
+        int st = scalar_value<W, true>(w, lc, q, fr.end, f.kind, f.child, false, &z);
         if (st != GST_OK) GGR_RET(st);
       }
     }

@@ -204,3 +204,71 @@ def status_compatible(oracle_st, engine_st):
     if oracle_st in WIRE_ERRS and engine_st in WIRE_ERRS:
         return True
     return False
+
+
+# ---- split sub-messages: proto.Unmarshal merges the occurrences of a singular message field ----
+def _vi(v):
+    out = bytearray()
+    v &= (1 << 64) - 1
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        out.append(b | (0x80 if v else 0))
+        if not v:
+            return bytes(out)
+
+
+def wire_field(num, wt, payload=b""):
+    """tag + value: wt 0 takes an int, wt 2 bytes (length added)"""
+    tag = _vi((num << 3) | wt)
+    if wt == 0:
+        return tag + _vi(payload)
+    if wt == 2:
+        return tag + _vi(len(payload)) + payload
+    return tag + payload
+
+
+def merge_cases():
+    """(message, wire) pairs: singular sub-messages (plain, oneof members, map values, Timestamps) that arrive in
+    several occurrences, nested, with repeated fields and maps inside, and with damaged occurrences"""
+    F = wire_field
+    inner_x = F(1, 0, 1)
+    inner_y = lambda t: F(2, 2, t)
+    out = [
+        F(17, 2, inner_x) + F(17, 2, inner_y(b"a")),
+        F(17, 2, inner_x) + F(1, 0, 9) + F(17, 2, F(1, 0, 2) + inner_y(b"q")) + F(17, 2, inner_y(b"z")),
+        F(17, 2, b"") + F(17, 2, b""),
+        F(17, 2, b"") + F(17, 2, inner_x) + F(17, 2, b""),
+        # nested: recursive (81) split, f_msg inside split again, scalars last-wins across the pieces
+        F(81, 2, F(17, 2, inner_x) + F(1, 0, 4)) + F(81, 2, F(17, 2, inner_y(b"b")) + F(1, 0, 5)),
+        F(81, 2, F(81, 2, F(17, 2, inner_x))) + F(81, 2, F(81, 2, F(17, 2, inner_y(b"deep")) + F(81, 2, F(1, 0, 3)))),
+        # repeated fields append, packed and not
+        F(81, 2, F(21, 2, bytes([1, 2])) + F(37, 2, inner_x)) + F(81, 2, F(21, 0, 3) + F(37, 2, inner_y(b"e2"))),
+        # maps across the pieces: one map, sorted keys, last wins
+        F(81, 2, F(41, 2, F(1, 2, b"b") + F(2, 0, 1))) + F(81, 2, F(41, 2, F(1, 2, b"a") + F(2, 0, 2)) + F(41, 2, F(1, 2, b"b") + F(2, 0, 3))),
+        # oneof: merged, cleared by a sibling in between, lost to a later sibling
+        F(53, 2, inner_x) + F(53, 2, inner_y(b"k")),
+        F(53, 2, inner_x) + F(51, 0, 7) + F(53, 2, inner_y(b"k")),
+        F(53, 2, inner_x) + F(51, 0, 7) + F(53, 2, inner_y(b"k")) + F(53, 2, F(1, 0, 8)),
+        F(53, 2, inner_x) + F(53, 2, inner_y(b"k")) + F(51, 0, 7),
+        F(53, 2, inner_x) + F(51, 2, b"xx") + F(53, 2, inner_y(b"k")),  # sibling with the wrong wire type: unknown, clears nothing
+        # map values split inside one entry; a later entry with the same key replaces (no merge across entries)
+        F(43, 2, F(1, 0, 5) + F(2, 2, inner_x) + F(2, 2, inner_y(b"v"))),
+        F(43, 2, F(1, 0, 5) + F(2, 2, inner_x) + F(2, 2, inner_y(b"v"))) + F(43, 2, F(1, 0, 5) + F(2, 2, inner_y(b"w"))),
+        F(43, 2, F(2, 2, inner_x) + F(1, 0, 6) + F(2, 2, b"") + F(2, 2, F(1, 0, 2))) + F(43, 2, F(1, 0, 1) + F(2, 2, inner_x)),
+        # Timestamp in pieces
+        F(71, 2, F(1, 0, 1700000000)) + F(71, 2, F(2, 0, 5000)),
+        F(71, 2, F(1, 0, 1700000000) + F(2, 0, 1)) + F(71, 2, F(1, 0, 1600000000)),
+        F(71, 2, b"") + F(71, 2, b""),
+        # damaged occurrences: each piece is parsed on its own
+        F(17, 2, b"\x08") + F(17, 2, b"\x01"),
+        F(17, 2, inner_x) + F(17, 2, b"\x12\x05ab"),
+        F(17, 2, inner_y(b"\xff")) + F(17, 2, inner_y(b"ok")),
+        F(43, 2, F(1, 0, 5) + F(2, 2, b"\x08") + F(2, 2, b"\x01")),
+        F(71, 2, b"\x08") + F(71, 2, b"\x01"),
+    ]
+    res = [(A, w) for w in out]
+    res.append((P + "CreateDocumentRequest", F(1, 2, F(1, 2, b"id")) + F(1, 2, F(5, 2, F(1, 2, F(1, 2, b"k") + F(2, 2, b"v")))) +
+                F(1, 2, F(5, 2, F(1, 2, F(1, 2, b"j") + F(2, 2, b"u"))) + F(2, 2, b"t"))))
+    res.append((P + "ProcessNodeRequest", F(1, 2, F(1, 2, b"n") + F(3, 2, F(1, 2, b"c1"))) + F(1, 2, F(3, 2, F(1, 2, b"c2")) + F(2, 2, b"val"))))
+    return res

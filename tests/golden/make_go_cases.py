@@ -44,6 +44,8 @@ def main():
         reply("dedge", name, bytes.fromhex(h), ids[i % len(ids)])
     for i, (name, w) in enumerate(cases.random_decode_cases(100, seed0=62000)):
         reply("drand", name, w, ids[i % len(ids)])
+    for i, (name, w) in enumerate(cases.merge_cases()):
+        reply("merge", name, w, ids[i % len(ids)])
     names = {}
 
     def mi(n):
