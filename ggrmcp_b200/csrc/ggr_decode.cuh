@@ -257,11 +257,7 @@ GGR_DEV void put_base64(W& w, Rd& r, u32 len) {
 template <class W>
 GGR_DEV int put_timestamp(W& w, i64 secs, i64 nanos) {
   if (secs < -62135596800ll || secs > 253402300799ll) return GST_RANGE;
-  if (nanos < 0 || nanos > 1000000000ll) return GST_RANGE;
-  if (nanos == 1000000000ll) {  // time.Unix normalizes
-    secs += 1;
-    nanos = 0;
-  }
+  if (nanos < 0 || nanos > 999999999ll) return GST_RANGE;  // upstream: nanos > secondsInNanos (999999999)
   i64 days = secs / 86400, rem = secs % 86400;
   if (rem < 0) {
     rem += 86400;
@@ -307,6 +303,33 @@ GGR_DEV int put_timestamp(W& w, i64 secs, i64 nanos) {
   return GST_OK;
 }
 
+// google.protobuf.Duration -> "[-]S[.fff[fff[fff]]]s" [upstream marshalDuration]
+template <class W>
+GGR_DEV int put_duration(W& w, i64 secs, i64 nanos) {
+  if (secs < -315576000000ll || secs > 315576000000ll) return GST_RANGE;
+  if (nanos < -999999999ll || nanos > 999999999ll) return GST_RANGE;
+  if ((secs > 0 && nanos < 0) || (secs < 0 && nanos > 0)) return GST_RANGE;  // signs of seconds and nanos do not match
+  w.put1('"');
+  if (secs < 0 || nanos < 0) {
+    w.put1('-');
+    secs = -secs;
+    nanos = -nanos;
+  }
+  put_dec_u64(w, (u64)secs);
+  u32 ns = (u32)nanos;
+  if (ns != 0) {
+    w.put1('.');
+    u32 a = ns / 1000000, b = ns / 1000 % 1000, c = ns % 1000;
+    w.put(('0' + a / 100) | (('0' + a / 10 % 10) << 8) | (('0' + a % 10) << 16), 3);
+    if (b != 0 || c != 0) {
+      w.put(('0' + b / 100) | (('0' + b / 10 % 10) << 8) | (('0' + b % 10) << 16), 3);
+      if (c != 0) w.put(('0' + c / 100) | (('0' + c / 10 % 10) << 8) | (('0' + c % 10) << 16), 3);
+    }
+  }
+  w.put('s' | ('"' << 8), 2);
+  return GST_OK;
+}
+
 struct DecCtx {
   Tables T;
   const u8* in;
@@ -318,6 +341,9 @@ struct DecCtx {
   u32 sort_cap = 0;
   // 1: `in` is scratch this thread wrote (the merged payload of a split sub-message): plain loads
   u32 rw = 0;
+  // errors protojson.Marshal raises (Timestamp / Duration out of range) are parked here while the walk goes on:
+  // proto.Unmarshal has read the whole item by then, so any wire error anywhere in the item comes first
+  int* late = nullptr;
 };
 
 template <class W>
@@ -453,6 +479,19 @@ GGR_DEV int scalar_value(W& w, const DecCtx& cx, Rd& r, u32 lim, u32 kind, i32 c
   else put_dec_u64(w, v);
   if (q) w.put1('"');
   return GST_OK;
+}
+
+// scalar_value as a call (the per-thread walkers have a dozen call sites; inlined, each one is 6-8 thousand
+// instructions): reads at `pos` with a reader of its own and returns the position after the value in the low 31 bits
+// of *next, the "zero value" flag in bit 31.  The caller jumps its reader there.
+template <class W, bool EMIT>
+GGR_DEVN int scalar_value_at(W& w, const DecCtx& cx, u32 pos, u32 lim, u32 kind, i32 child, u32* next) {
+  Rd r;
+  r.init(cx.in, pos, lim, cx.rw);
+  bool z = false;
+  const int st = scalar_value<W, EMIT>(w, cx, r, lim, kind, child, false, &z);
+  *next = r.pos | (z ? 0x80000000u : 0u);
+  return st;
 }
 
 // ---- split sub-messages (proto.Unmarshal merges, reflection.go:363) ----
@@ -617,7 +656,7 @@ GGR_DEV int cmp_map_keys(const DecCtx& cx, u32 kkind, u64 a, u64 b) {
 }
 
 template <class W>
-GGR_DEV int put_map_key(W& w, const DecCtx& cx, u32 kkind, u64 key) {
+GGR_DEVN int put_map_key(W& w, const DecCtx& cx, u32 kkind, u64 key) {
   if (kkind == GK_STRING) {
     Rd r;
     r.init(cx.in, (u32)key, (u32)key + (u32)(key >> 32), cx.rw);
@@ -666,41 +705,10 @@ struct DFrame {
 template <class W, bool SLOW>
 GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 msg, u32 start, u32 end, int rec, bool active, unsigned mask);
 
-template <class W, bool SLOW>
-GGR_DEV int put_map_value(W& w, const DecCtx& cx, const FieldD& vf, const MapEnt& me, int rec) {
-  if (vf.kind == GK_MESSAGE && me.multi) {
-    if (!SLOW) return GGR_NEED_SLOW;
-    MsgD vd = ggr_msg(cx.T, (u32)vf.child);
-    if (vd.wkt != GGR_WKT_NONE && vd.wkt != GGR_WKT_TIMESTAMP) return GST_UNSUPPORTED;
-    DecCtx mc = cx;
-    const u8* mb;
-    u32 ml;
-    int st = merge_occurrences(cx, me.beg, me.end, 2, &mb, &ml);
-    if (st != GST_OK) return st;
-    mc.in = mb;
-    mc.rw = 1;
-    return walk_message<W, SLOW>(w, mc, (u32)vf.child, 0, ml, rec + 1, true, ggr_activemask());
-  }
-  if (vf.kind == GK_MESSAGE) {
-    MsgD vd = ggr_msg(cx.T, (u32)vf.child);
-    if (vd.wkt == GGR_WKT_TIMESTAMP) {
-      i64 s = 0, n = 0;
-      if (me.val_pos) {
-        Rd r;
-        r.init(cx.in, me.val_pos, me.val_pos + me.val_len, cx.rw);
-        int st = read_timestamp_payload(r, me.val_pos + me.val_len, &s, &n);
-        if (st != GST_OK) return st;
-      }
-      return put_timestamp(w, s, n);
-    }
-    if (vd.wkt != GGR_WKT_NONE) return GST_UNSUPPORTED;
-    if (!me.val_pos) {
-      w.put('{' | ('}' << 8), 2);
-      return GST_OK;
-    }
-    // nested walk: only the lanes that arrive here together vote with each other
-    return walk_message<W, SLOW>(w, cx, (u32)vf.child, me.val_pos, me.val_pos + me.val_len, rec + 1, true, ggr_activemask());
-  }
+// Value of a scalar field that may be absent (map values, wrapper values): its text, or the text of the kind's zero
+// value when me.val_pos == 0.
+template <class W>
+GGR_DEV int put_scalar_or_default(W& w, const DecCtx& cx, const FieldD& vf, const MapEnt& me) {
   if (!me.val_pos) {
     // absent value: zero value of the kind
     switch (vf.kind) {
@@ -736,7 +744,6 @@ GGR_DEV int put_map_value(W& w, const DecCtx& cx, const FieldD& vf, const MapEnt
   r.init(cx.in, me.val_pos, lim, cx.rw);
   if (vf.wt == 2) {
     // scalar_value re-reads the length prefix: step back is not possible, so emit directly
-    bool z;
     if (vf.kind == GK_STRING) return put_json_string(w, r, me.val_len);
     put_base64(w, r, me.val_len);
     return GST_OK;
@@ -745,11 +752,128 @@ GGR_DEV int put_map_value(W& w, const DecCtx& cx, const FieldD& vf, const MapEnt
   return scalar_value<W, true>(w, cx, r, lim, vf.kind, vf.child, false, &z);
 }
 
+// Payload [r.pos, lim) of a wrapper message (google.protobuf.*Value): the last occurrence of field 1 wins, every
+// string occurrence is checked the way proto.Unmarshal checks it.
+GGR_DEV int parse_wrapper(const DecCtx& cx, Rd& r, u32 lim, const FieldD& vf, MapEnt* me) {
+  me->key = 0;
+  me->val_pos = 0;
+  me->val_len = 0;
+  me->end = lim;
+  me->beg = r.pos;
+  me->multi = 0;
+  while (r.pos < lim) {
+    u64 tag, v;
+    if (!rd_varint(r, lim, &tag)) return GST_BAD_WIRE;
+    u64 num = tag >> 3;
+    u32 wt = (u32)(tag & 7);
+    if (num == 0 || num > 0x1FFFFFFFull || wt == 4) return GST_BAD_WIRE;
+    if (num == 1 && wt == vf.wt) {
+      me->val_pos = r.pos;
+      if (wt == 2) {
+        if (!rd_varint(r, lim, &v) || v > (u64)(lim - r.pos)) return GST_BAD_WIRE;
+        me->val_pos = r.pos;
+        me->val_len = (u32)v;
+        if (vf.kind == GK_STRING) {
+          Cnt c;
+          c.pos = 0;
+          int st = put_json_string(c, r, (u32)v);
+          if (st != GST_OK) return st;
+        } else {
+          rd_jump(r, r.pos + (u32)v);
+        }
+      } else if (!rd_skip_value(r, lim, 1, wt)) {
+        return GST_BAD_WIRE;
+      }
+    } else if (!rd_skip_value(r, lim, (u32)num, wt)) {
+      return GST_BAD_WIRE;
+    }
+  }
+  return r.pos == lim ? GST_OK : GST_BAD_WIRE;
+}
+
+// A well-known type with a JSON form of its own, payload [r.pos, lim) (protojson well_known_types.go): Timestamp,
+// Duration, the nine wrappers (the bare value, its zero when unset), Empty.
+// Called, not inlined (a dozen call sites in the walkers): it reads the payload with a reader of its own, the caller
+// jumps to `lim` afterwards.
+template <class W>
+GGR_DEVN int put_wkt(W& w, const DecCtx& cx, u32 msg, u32 start, u32 lim) {
+  const MsgD cd = ggr_msg(cx.T, msg);
+  Rd r;
+  r.init(cx.in, start, lim, cx.rw);
+  if (cd.wkt == GGR_WKT_TIMESTAMP || cd.wkt == GGR_WKT_DURATION) {
+    i64 s, n;
+    int st = read_timestamp_payload(r, lim, &s, &n);
+    if (st != GST_OK) return st;
+    st = cd.wkt == GGR_WKT_TIMESTAMP ? put_timestamp(w, s, n) : put_duration(w, s, n);
+    if (st == GST_RANGE && cx.late) {
+      *cx.late = GST_RANGE;
+      return GST_OK;
+    }
+    return st;
+  }
+  if (cd.wkt == GGR_WKT_WRAPPER) {
+    const FieldD vf = ggr_field(cx.T, cd.field_first);
+    MapEnt me;
+    int st = parse_wrapper(cx, r, lim, vf, &me);
+    if (st != GST_OK) return st;
+    return put_scalar_or_default(w, cx, vf, me);
+  }
+  if (cd.wkt == GGR_WKT_EMPTY) {
+    while (r.pos < lim) {
+      u64 tag;
+      if (!rd_varint(r, lim, &tag)) return GST_BAD_WIRE;
+      u64 num = tag >> 3;
+      u32 wt = (u32)(tag & 7);
+      if (num == 0 || num > 0x1FFFFFFFull || wt == 4) return GST_BAD_WIRE;
+      if (!rd_skip_value(r, lim, (u32)num, wt)) return GST_BAD_WIRE;
+    }
+    if (r.pos != lim) return GST_BAD_WIRE;
+    w.put('{' | ('}' << 8), 2);
+    return GST_OK;
+  }
+  return GST_UNSUPPORTED;
+}
+
+template <class W, bool SLOW>
+GGR_DEVN int put_map_value(W& w, const DecCtx& cx, FieldD vf, MapEnt me, int rec) {
+  if (vf.kind == GK_MESSAGE && me.multi) {
+    if (!SLOW) return GGR_NEED_SLOW;
+    MsgD vd = ggr_msg(cx.T, (u32)vf.child);
+    if (vd.wkt == GGR_WKT_UNSUPPORTED) return GST_UNSUPPORTED;
+    DecCtx mc = cx;
+    const u8* mb;
+    u32 ml;
+    int st = merge_occurrences(cx, me.beg, me.end, 2, &mb, &ml);
+    if (st != GST_OK) return st;
+    mc.in = mb;
+    mc.rw = 1;
+    return walk_message<W, SLOW>(w, mc, (u32)vf.child, 0, ml, rec + 1, true, ggr_activemask());
+  }
+  if (vf.kind == GK_MESSAGE) {
+    MsgD vd = ggr_msg(cx.T, (u32)vf.child);
+    if (vd.wkt != GGR_WKT_NONE) {
+      // an absent value is the empty message
+      const u32 vs = me.val_pos ? me.val_pos : me.end, ve = me.val_pos ? me.val_pos + me.val_len : me.end;
+      return put_wkt(w, cx, (u32)vf.child, vs, ve);
+    }
+    if (!me.val_pos) {
+      w.put('{' | ('}' << 8), 2);
+      return GST_OK;
+    }
+    // nested walk: only the lanes that arrive here together vote with each other
+    return walk_message<W, SLOW>(w, cx, (u32)vf.child, me.val_pos, me.val_pos + me.val_len, rec + 1, true, ggr_activemask());
+  }
+  return put_scalar_or_default(w, cx, vf, me);
+}
+
 // Map field writer.  `r` is positioned right after the tag of the first entry (fast walk) and is
 // left after the last entry of the run.  In the slow walk the entries are all occurrences of the
 // field inside [pstart, pend).
 template <class W, bool SLOW>
-GGR_DEV int put_map_field(W& w, const DecCtx& cx, Rd& r, const FieldD& f, u32 pstart, u32 pend, int rec) {
+GGR_DEVN int put_map_field(W& w, const DecCtx& cx, u32 rpos, u32* rend, FieldD f, u32 pstart, u32 pend, int rec) {
+  Rd r;
+  r.init(cx.in, SLOW ? pstart : rpos, pend, cx.rw);
+  *rend = rpos;
   MsgD ed = ggr_msg(cx.T, (u32)f.child);
   FieldD kf = ggr_field(cx.T, ed.field_first), vf = ggr_field(cx.T, ed.field_first + 1);
   // pass 1: find the run / all occurrences, validate, check ordering
@@ -781,6 +905,7 @@ GGR_DEV int put_map_field(W& w, const DecCtx& cx, Rd& r, const FieldD& f, u32 ps
         count++;
       }
       run_end = r.pos;
+      *rend = run_end;
     } else {
       run_start = pstart;
       run_end = pend;
@@ -973,13 +1098,8 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
   if (!finished) {
     r.init(cx.in, start, end, cx.rw);
     md = ggr_msg(T, root_msg);
-    if (md.wkt == GGR_WKT_TIMESTAMP) {
-      i64 s, n;
-      result = read_timestamp_payload(r, end, &s, &n);
-      if (result == GST_OK) result = put_timestamp(w, s, n);
-      finished = true;
-    } else if (md.wkt != GGR_WKT_NONE) {
-      result = GST_UNSUPPORTED;
+    if (md.wkt != GGR_WKT_NONE) {
+      result = put_wkt(w, cx, root_msg, start, end);
       finished = true;
     } else {
       w.put1('{');
@@ -1031,8 +1151,10 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
         // the key text is written only when the map has entries (always true here)
         put_sep(w, cx, fr.first);
         put_pool(w, T.pool, f.name_off, f.name_len);
-        int st = put_map_field<W, false>(w, cx, r, f, r.pos, fr.end, rec);
+        u32 run_end;
+        int st = put_map_field<W, false>(w, cx, r.pos, &run_end, f, r.pos, fr.end, rec);
         if (st != GST_OK) GGR_RET(st);
+        rd_jump(r, run_end);
         continue;
       }
       if (f.flags & GF_REPEATED) {
@@ -1125,15 +1247,12 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
         if (!rd_varint(r, fr.end, &len) || len > (u64)(fr.end - r.pos)) GGR_RET(GST_BAD_WIRE);
         u32 lim = r.pos + (u32)len;
         MsgD cd = ggr_msg(T, (u32)f.child);
-        if (cd.wkt == GGR_WKT_TIMESTAMP) {
-          i64 s, n;
-          int st = read_timestamp_payload(r, lim, &s, &n);
+        if (cd.wkt != GGR_WKT_NONE) {
+          int st = put_wkt(w, cx, (u32)f.child, r.pos, lim);
           if (st != GST_OK) GGR_RET(st);
-          st = put_timestamp(w, s, n);
-          if (st != GST_OK) GGR_RET(st);
+          rd_jump(r, lim);
           continue;
         }
-        if (cd.wkt != GGR_WKT_NONE) GGR_RET(GST_UNSUPPORTED);
         if (depth >= GGR_DEC_MAX_DEPTH - 1) GGR_RET(GST_DEPTH);
         stk[depth++] = fr;
         fr.end = lim; fr.msg = (u32)f.child; fr.last_decl = -1; fr.open = 0; fr.first = 1; fr.elem_first = 1; fr.oneofs = 0;
@@ -1185,12 +1304,13 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
         c.pos = 0;
         Rd t;
         t.init(lc.in, fr.start, fr.end, lc.rw);
-        int st = put_map_field<Cnt, true>(c, lc, t, f, fr.start, fr.end, rec);
+        u32 unused_end;
+        int st = put_map_field<Cnt, true>(c, lc, fr.start, &unused_end, f, fr.start, fr.end, rec);
         if (st != GST_OK) GGR_RET(st);
         if (c.pos == 0) continue;
         put_sep(w, lc, fr.first);
         put_pool(w, T.pool, f.name_off, f.name_len);
-        st = put_map_field<W, true>(w, lc, t, f, fr.start, fr.end, rec);
+        st = put_map_field<W, true>(w, lc, fr.start, &unused_end, f, fr.start, fr.end, rec);
         if (st != GST_OK) GGR_RET(st);
         continue;
       }
@@ -1232,8 +1352,9 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
               fr.open = 1;
             }
             put_sep(w, lc, fr.elem_first);
-            bool z;
-            int st = scalar_value<W, true>(w, lc, t, lim, f.kind, f.child, false, &z);
+            u32 nx_;
+            int st = scalar_value_at<W, true>(w, lc, t.pos, lim, f.kind, f.child, &nx_);
+            rd_jump(t, nx_ & 0x7FFFFFFFu);
             if (st != GST_OK) GGR_RET(st);
           }
           if (t.pos != lim) GGR_RET(GST_BAD_WIRE);
@@ -1247,8 +1368,9 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
         }
         put_sep(w, lc, fr.elem_first);
         if (f.kind != GK_MESSAGE) {
-          bool z;
-          int st = scalar_value<W, true>(w, lc, t, fr.end, f.kind, f.child, false, &z);
+          u32 nx_;
+          int st = scalar_value_at<W, true>(w, lc, t.pos, fr.end, f.kind, f.child, &nx_);
+          rd_jump(t, nx_ & 0x7FFFFFFFu);
           if (st != GST_OK) GGR_RET(st);
           continue;
         }
@@ -1257,15 +1379,12 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
         if (!rd_varint(t, fr.end, &len) || len > (u64)(fr.end - t.pos)) GGR_RET(GST_BAD_WIRE);
         u32 lim = t.pos + (u32)len;
         MsgD cd = ggr_msg(T, (u32)f.child);
-        if (cd.wkt == GGR_WKT_TIMESTAMP) {
-          i64 s, n;
-          int st = read_timestamp_payload(t, lim, &s, &n);
+        if (cd.wkt != GGR_WKT_NONE) {
+          int st = put_wkt(w, lc, (u32)f.child, t.pos, lim);
           if (st != GST_OK) GGR_RET(st);
-          st = put_timestamp(w, s, n);
-          if (st != GST_OK) GGR_RET(st);
+          rd_jump(t, lim);
           continue;
         }
-        if (cd.wkt != GGR_WKT_NONE) GGR_RET(GST_UNSUPPORTED);
         if (depth >= GGR_DEC_MAX_DEPTH - 1) GGR_RET(GST_DEPTH);
         fr.state = 1;
         fr.scan = lim;
@@ -1309,7 +1428,7 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
         MsgD cd = ggr_msg(T, (u32)f.child);
         if (n_occ > 1) {
           // split over several occurrences: walk the merged payload (its own buffer) as the child frame
-          if (cd.wkt != GGR_WKT_NONE && cd.wkt != GGR_WKT_TIMESTAMP) GGR_RET(GST_UNSUPPORTED);
+          if (cd.wkt == GGR_WKT_UNSUPPORTED) GGR_RET(GST_UNSUPPORTED);
           u32 mstart = fr.start;
           if (f.oneof >= 0) {  // a sibling set in between clears the member: only what follows it merges
             Rd q;
@@ -1334,13 +1453,11 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
           if (st != GST_OK) GGR_RET(st);
           put_sep(w, lc, fr.first);
           put_pool(w, T.pool, f.name_off, f.name_len);
-          if (cd.wkt == GGR_WKT_TIMESTAMP) {
-            Rd q;
-            q.init(mb, 0, ml, 1);
-            i64 s, n;
-            st = read_timestamp_payload(q, ml, &s, &n);
-            if (st != GST_OK) GGR_RET(st);
-            st = put_timestamp(w, s, n);
+          if (cd.wkt != GGR_WKT_NONE) {
+            DecCtx mc = lc;
+            mc.in = mb;
+            mc.rw = 1;
+            st = put_wkt(w, mc, (u32)f.child, 0, ml);
             if (st != GST_OK) GGR_RET(st);
             continue;
           }
@@ -1360,15 +1477,11 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
         u32 lim = q.pos + (u32)len;
         put_sep(w, lc, fr.first);
         put_pool(w, T.pool, f.name_off, f.name_len);
-        if (cd.wkt == GGR_WKT_TIMESTAMP) {
-          i64 s, n;
-          int st = read_timestamp_payload(q, lim, &s, &n);
-          if (st != GST_OK) GGR_RET(st);
-          st = put_timestamp(w, s, n);
+        if (cd.wkt != GGR_WKT_NONE) {
+          int st = put_wkt(w, lc, (u32)f.child, q.pos, lim);
           if (st != GST_OK) GGR_RET(st);
           continue;
         }
-        if (cd.wkt != GGR_WKT_NONE) GGR_RET(GST_UNSUPPORTED);
         if (depth >= GGR_DEC_MAX_DEPTH - 1) GGR_RET(GST_DEPTH);
         stk[depth++] = fr;
         fr.end = lim; fr.msg = (u32)f.child; fr.last_decl = -1; fr.open = 0; fr.first = 1; fr.elem_first = 1; fr.oneofs = 0;
@@ -1390,7 +1503,10 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
             bool z;
             Cnt c;
             c.pos = 0;
-            int st = scalar_value<Cnt, false>(c, lc, q, fr.end, f.kind, f.child, false, &z);
+            u32 nz_;
+            int st = scalar_value_at<Cnt, false>(c, lc, q.pos, fr.end, f.kind, f.child, &nz_);
+            rd_jump(q, nz_ & 0x7FFFFFFFu);
+            z = (nz_ >> 31) != 0;
             if (st != GST_OK) GGR_RET(st);
           } else if (!rd_skip_value(q, fr.end, n3, w3)) {
             GGR_RET(GST_BAD_WIRE);
@@ -1402,14 +1518,18 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
           bool z;
           Cnt c;
           c.pos = 0;
-          int st = scalar_value<Cnt, false>(c, lc, t2, fr.end, f.kind, f.child, false, &z);
+          u32 nz_;
+          int st = scalar_value_at<Cnt, false>(c, lc, t2.pos, fr.end, f.kind, f.child, &nz_);
+          rd_jump(t2, nz_ & 0x7FFFFFFFu);
+          z = (nz_ >> 31) != 0;
           if (st != GST_OK) GGR_RET(st);
           if (z) continue;
         }
         put_sep(w, lc, fr.first);
         put_pool(w, T.pool, f.name_off, f.name_len);
-        bool z;
-        int st = scalar_value<W, true>(w, lc, q, fr.end, f.kind, f.child, false, &z);
+        u32 nx_;
+        int st = scalar_value_at<W, true>(w, lc, q.pos, fr.end, f.kind, f.child, &nx_);
+        rd_jump(q, nx_ & 0x7FFFFFFFu);
         if (st != GST_OK) GGR_RET(st);
       }
     }
@@ -1435,18 +1555,24 @@ GGR_DEV int decode_size(const Tables& T, u32 msg, const u8* in, u32 start, u32 e
   cx.sort_pool = sort_pool;
   cx.sort_ctr = sort_ctr;
   cx.sort_cap = sort_cap;
+  int late = GST_OK;
+  cx.late = &late;
   Cnt c;
   c.pos = 0;
   int st = walk_message<Cnt, false>(c, cx, msg, start, end, 0, active, mask);
   res->mode = GGR_MODE_FAST;
   bool need_slow = active && st == GGR_NEED_SLOW;
-  if (need_slow) c.pos = 0;
+  if (need_slow) {
+    c.pos = 0;
+    late = GST_OK;
+  }
   int st2 = walk_message<Cnt, true>(c, cx, msg, start, end, 0, need_slow, mask);
   if (need_slow) {
     st = st2;
     res->mode = GGR_MODE_SLOW;
   }
   res->size = c.pos;
+  if (st == GST_OK && late != GST_OK) st = late;
   return st;
 }
 

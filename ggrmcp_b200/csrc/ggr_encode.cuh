@@ -253,6 +253,60 @@ GGR_DEV int parse_timestamp(StrIter& it, i64* secs, i32* nanos) {
   return GST_OK;
 }
 
+// google.protobuf.Duration: "[+-]digits[.digits]s" exactly as protojson's parseDuration reads it (well_known_types.go):
+// one leading '0' or a run of digits starting with 1-9 or nothing, an optional '.' with up to nine digits, the 's' last
+GGR_DEV int parse_duration(StrIter& it, i64* secs, i32* nanos) {
+  bool neg = false;
+  u32 c = it.get();
+  if (c == '-' || c == '+') {
+    neg = c == '-';
+    it.adv();
+  }
+  if (it.eof()) return GST_INVALID_VALUE;
+  c = it.peek();
+  u64 sv = 0;
+  u32 nd = 0;
+  bool ovf = false;
+  if (c == 's') return GST_INVALID_VALUE;  // nothing in front of the suffix
+  if (c == '0') {
+    it.adv();
+  } else if (c - '1' < 9u) {
+    while (!it.eof() && it.peek() - '0' < 10u) {
+      const u32 d = it.peek() - '0';
+      if (sv > 922337203685477580ull || (sv == 922337203685477580ull && d > 7u)) ovf = true;  // strconv.ParseInt range
+      sv = sv * 10u + d;
+      nd++;
+      it.adv();
+    }
+  } else if (c != '.') {
+    return GST_INVALID_VALUE;
+  }
+  u32 ns = 0;
+  if (it.get() == '.') {
+    it.adv();
+    u32 k = 0;
+    while (!it.eof() && k < 9u && it.peek() - '0' < 10u) {
+      ns = ns * 10u + (it.peek() - '0');
+      k++;
+      it.adv();
+    }
+    for (; k < 9u; k++) ns *= 10u;
+  }
+  if (it.get() != 's') return GST_INVALID_VALUE;
+  it.adv();
+  if (!it.eof() || ovf) return GST_INVALID_VALUE;
+  i64 s = (i64)sv;
+  i32 n = (i32)ns;
+  if (neg) {
+    s = -s;
+    n = -n;
+  }
+  if (s < -315576000000ll || s > 315576000000ll) return GST_RANGE;
+  *secs = s;
+  *nanos = n;
+  return GST_OK;
+}
+
 // ---- scalar -> node payload ----
 struct Leaf {
   u32 type, a, b, body, flags;
@@ -559,6 +613,21 @@ struct EncResult {
   u32 method, id_pos, id_len;
 };
 
+// Rare value forms of encode_parse as calls (inlined they add 35 thousand instructions to the kernel): the text of a
+// Timestamp / Duration string, the value of a wrapper message.
+GGR_DEVN int parse_time_value(const u8* in, u32 quote_pos, u32 end, bool duration, i64* secs, i32* nanos) {
+  StrIter it;
+  it.init(in, quote_pos, end);
+  return duration ? parse_duration(it, secs, nanos) : parse_timestamp(it, secs, nanos);
+}
+GGR_DEVN int parse_scalar_at(EncCtx& cx, u32 pos, u32 kind, i32 child, Leaf* l, u32* next) {
+  Rd r;
+  r.init(cx.in, pos, cx.end);
+  const int st = parse_scalar(cx, r, kind, child, l);
+  *next = r.pos;
+  return st;
+}
+
 // `active` is false for lanes that have no item (they only take part in the convergence votes);
 // `mask` names the lanes that call this function together.
 GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start, u32 end, u8* ir, u32 ir_cap, EncResult* res,
@@ -780,37 +849,77 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
       if (f.kind == GK_MESSAGE) {
         vmsg = (u32)f.child;
         MsgD vd = ggr_msg(T, vmsg);
-        if (vd.wkt == GGR_WKT_TIMESTAMP) {
-          if (r.get() != '"') GGR_RET(GST_SYNTAX);
-          u32 q = r.pos;
-          StrInfo si;
-          int st = scan_string<false>(r, &si);
-          if (st != GST_OK) GGR_RET(st);
-          StrIter it;
-          it.init(in, q, end);
-          i64 secs;
-          i32 nanos;
-          st = parse_timestamp(it, &secs, &nanos);
-          if (st != GST_OK) GGR_RET(st);
-          u32 midx, sidx = GGR_NIL, nidx = GGR_NIL;
-          st = enc_new_node(cx, &midx);
-          if (st != GST_OK) GGR_RET(st);
-          u32 payload = 0;
-          if (nanos != 0) {
-            st = enc_new_node(cx, &nidx);
+        if (vd.wkt != GGR_WKT_NONE) {
+          // well-known types with a JSON form of their own: the value is finished here, as a message node with
+          // its leaves, and handed to the container
+          u32 midx, first = GGR_NIL, payload = 0;
+          int st;
+          if (vd.wkt == GGR_WKT_TIMESTAMP || vd.wkt == GGR_WKT_DURATION) {
+            if (r.get() != '"') GGR_RET(GST_SYNTAX);
+            u32 q = r.pos;
+            StrInfo si;
+            st = scan_string<false>(r, &si);
             if (st != GST_OK) GGR_RET(st);
-            node_store(ir, nidx, (u32)nanos, 0, GGR_NIL, 1, node_meta(N_VARINT, 0, 16));
-            payload += 1 + varint_size((u64)(u32)nanos);
-          }
-          if (secs != 0) {
-            st = enc_new_node(cx, &sidx);
+            i64 secs;
+            i32 nanos;
+            st = parse_time_value(in, q, end, vd.wkt == GGR_WKT_DURATION, &secs, &nanos);
             if (st != GST_OK) GGR_RET(st);
-            node_store(ir, sidx, (u32)(u64)secs, (u32)((u64)secs >> 32), nidx, 0, node_meta(N_VARINT, 0, 8));
-            payload += 1 + varint_size((u64)secs);
+            u32 sidx = GGR_NIL, nidx = GGR_NIL;
+            st = enc_new_node(cx, &midx);
+            if (st != GST_OK) GGR_RET(st);
+            if (nanos != 0) {
+              const u64 nv = (u64)(i64)nanos;  // int32 on the wire: sign-extended
+              st = enc_new_node(cx, &nidx);
+              if (st != GST_OK) GGR_RET(st);
+              node_store(ir, nidx, (u32)nv, (u32)(nv >> 32), GGR_NIL, 1, node_meta(N_VARINT, 0, 16));
+              payload += 1 + varint_size(nv);
+            }
+            if (secs != 0) {
+              st = enc_new_node(cx, &sidx);
+              if (st != GST_OK) GGR_RET(st);
+              node_store(ir, sidx, (u32)(u64)secs, (u32)((u64)secs >> 32), nidx, 0, node_meta(N_VARINT, 0, 8));
+              payload += 1 + varint_size((u64)secs);
+            }
+            first = sidx != GGR_NIL ? sidx : nidx;
+          } else if (vd.wkt == GGR_WKT_WRAPPER) {
+            // the bare value of field 1 (unmarshalWrapperType); the zero value leaves an empty message
+            const FieldD vf = ggr_field(T, vd.field_first);
+            Leaf l;
+            u32 after;
+            st = parse_scalar_at(cx, r.pos, vf.kind, vf.child, &l, &after);
+            if (st != GST_OK) GGR_RET(st);
+            r.init(in, after, end);
+            st = enc_new_node(cx, &midx);
+            if (st != GST_OK) GGR_RET(st);
+            if (!l.zero) {
+              u32 lidx;
+              st = enc_new_node(cx, &lidx);
+              if (st != GST_OK) GGR_RET(st);
+              node_store(ir, lidx, l.a, l.b, GGR_NIL, 0, node_meta(l.type, l.flags, vf.tag));
+              first = lidx;
+              payload = vf.tag_len + l.body;
+            }
+          } else if (vd.wkt == GGR_WKT_EMPTY) {
+            // an object without members (unmarshalEmpty; DiscardUnknown is off on this path)
+            if (r.get() != '{') GGR_RET(GST_SYNTAX);
+            r.skip(1);
+            skip_ws(r);
+            if (r.get() == '"') {
+              StrInfo si;
+              st = scan_string<false>(r, &si);
+              if (st != GST_OK) GGR_RET(st);
+              skip_ws(r);
+              if (r.get() != ':') GGR_RET(GST_SYNTAX);
+              GGR_RET(GST_UNKNOWN_FIELD);
+            }
+            if (r.get() != '}') GGR_RET(GST_SYNTAX);
+            r.skip(1);
+            st = enc_new_node(cx, &midx);
+            if (st != GST_OK) GGR_RET(st);
+          } else {
+            GGR_RET(GST_UNSUPPORTED);
           }
-          u32 first = sidx != GGR_NIL ? sidx : nidx;
           u32 body = varint_size(payload) + payload;
-          // hand the finished message value to the container
           if (fr.kind == FR_MAP) {
             node_store(ir, midx, payload, first, GGR_NIL, 1, node_meta(N_MSG, 0, f.tag));
             node_set_next(ir, fr.key_node, midx);
@@ -827,7 +936,6 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
           }
           continue;
         }
-        if (vd.wkt != GGR_WKT_NONE) GGR_RET(GST_UNSUPPORTED);
         if (r.get() != '{') GGR_RET(GST_SYNTAX);
         r.skip(1);
         if (depth >= GGR_MAX_DEPTH - 1) GGR_RET(GST_DEPTH);

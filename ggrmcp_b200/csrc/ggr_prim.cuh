@@ -206,6 +206,10 @@ struct Rd {
 // group of a message are written byte-wise because neighbouring messages (other threads) own
 // the rest of those groups.
 // ------------------------------------------------------------------------------------------
+// first group of an item whose leading bytes belong to the neighbour: byte stores, out of line (once per item)
+GGR_DEVN void wr_flush_partial(u8* a, u64 acc, u32 skip) {
+  for (u32 i = skip; i < 8; i++) a[i] = (u8)(acc >> (8 * i));
+}
 struct Wr {
   u8* base;
   u32 pos;   // offset of the next byte
@@ -223,7 +227,7 @@ struct Wr {
   GGR_DEV void flush_group() {
     u8* a = base + (pos - (u32)n);
     if (skip) {
-      for (u32 i = skip; i < 8; i++) a[i] = (u8)(acc >> (8 * i));
+      wr_flush_partial(a, acc, skip);
       skip = 0;
     } else {
       ggr_st8(a, acc);

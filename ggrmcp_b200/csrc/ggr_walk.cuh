@@ -1130,6 +1130,9 @@ GGR_DEV bool cw_type_item(SH& S, const Tables& T, u32 root_msg, const u8* in, u3
             }
           }
         }
+        // a null member: no bytes, but the emitter walks every record's node - it must not meet what an earlier
+        // batch left in this slot of the IR
+        if (ok && cls == CW_SKIP) node_store(ir, r, 0, 0, GGR_NIL, 0, node_meta(N_SKIP, 0, 0));
         if (!ok) S.bail = 1;
         S.gfield[r] = (u16)gf;
         S.cls[r] = (u8)cls;

@@ -686,6 +686,89 @@ struct PJUnmarshal {
     return true;
   }
 
+  // [upstream well_known_types.go unmarshalDuration / parseDuration]
+  static bool parse_duration(const Bytes& in, int64_t& secs, int32_t& nanos) {
+    size_t size = in.size();
+    if (size < 2 || in[size - 1] != 's') return false;
+    size_t i = 0, n = size - 1;
+    bool neg = false;
+    if (in[0] == '-') { neg = true; i = 1; }
+    else if (in[0] == '+') i = 1;
+    if (i == n) return false;
+    std::string intp;
+    if (in[i] == '0') {
+      i++;
+    } else if (in[i] >= '1' && in[i] <= '9') {
+      while (i < n && in[i] >= '0' && in[i] <= '9') intp.push_back(in[i++]);
+    } else if (in[i] != '.') {
+      return false;
+    }
+    bool has_frac = false;
+    char frac[9];
+    if (i < n) {
+      if (in[i] != '.') return false;
+      i++;
+      int k = 0;
+      while (i < n && k < 9 && in[i] >= '0' && in[i] <= '9') frac[k++] = in[i++];
+      if (i < n) return false;
+      for (; k < 9; k++) frac[k] = '0';
+      has_frac = true;
+    }
+    secs = 0;
+    if (!intp.empty()) {  // strconv.ParseInt(intp, 10, 64)
+      if (intp.size() > 19) return false;
+      unsigned long long v = 0;
+      for (char c : intp) v = v * 10 + (unsigned)(c - '0');
+      if (intp.size() == 19 && intp > "9223372036854775807") return false;
+      secs = (int64_t)v;
+    }
+    int64_t ns = 0;
+    if (has_frac)
+      for (int k = 0; k < 9; k++) ns = ns * 10 + (frac[k] - '0');
+    if (neg) {
+      if (secs > 0) secs = -secs;
+      if (ns > 0) ns = -ns;
+    }
+    nanos = (int32_t)ns;
+    return true;
+  }
+  bool duration(DynMsg& m) {
+    Tok t;
+    if (!tk.read(t)) return false;
+    if (t.kind != K_STRING) return unexpected(t);
+    int64_t secs;
+    int32_t nanos;
+    if (!parse_duration(t.str, secs, nanos)) return err.fail(ORC_INVALID_VALUE, "invalid google.protobuf.Duration value " + t.raw);
+    // validate seconds; no need to validate nanos because parseDuration would have covered that already
+    if (secs < -315576000000ll || secs > 315576000000ll)
+      return err.fail(ORC_RANGE, "google.protobuf.Duration value out of range: " + t.raw);
+    Val a, b;
+    a.u = (uint64_t)secs;
+    b.u = (uint64_t)(int64_t)nanos;
+    m.known[1].list = {a};
+    m.known[2].list = {b};
+    return true;
+  }
+  // [upstream unmarshalWrapperType: the value field read as a singular field of its kind]
+  bool wrapper(DynMsg& m) {
+    const FieldDesc* vf = m.d->find_number(1);
+    if (!vf) return err.fail(ORC_UNSUPPORTED, "wrapper without a value field");
+    Val v;
+    if (!scalar(*vf, vf->type, v)) return false;
+    m.known[1].list = {v};
+    return true;
+  }
+  // [upstream unmarshalEmpty: an object without members (DiscardUnknown is off on this path)]
+  bool empty(DynMsg&) {
+    Tok t;
+    if (!tk.read(t)) return false;
+    if (t.kind != K_OBJ_OPEN) return unexpected(t);
+    if (!tk.read(t)) return false;
+    if (t.kind == K_OBJ_CLOSE) return true;
+    if (t.kind == K_NAME) return err.fail(ORC_UNKNOWN_FIELD, "unknown field " + t.raw);
+    return unexpected(t);
+  }
+
   bool message(DynMsg& m) {
     if (--depth < 0) return err.fail(ORC_DEPTH, "exceeded max recursion depth");
     bool ok = message1(m);
@@ -694,6 +777,9 @@ struct PJUnmarshal {
   }
   bool message1(DynMsg& m) {
     if (m.d->wkt == WKT_TIMESTAMP) return timestamp(m);
+    if (m.d->wkt == WKT_DURATION) return duration(m);
+    if (m.d->wkt == WKT_WRAPPER) return wrapper(m);
+    if (m.d->wkt == WKT_EMPTY) return empty(m);
     if (m.d->wkt != WKT_NONE) return err.fail(ORC_UNSUPPORTED, "well-known type " + m.d->full_name + " not supported");
     Tok t;
     if (!tk.read(t)) return false;
@@ -934,15 +1020,66 @@ struct PJMarshal {
     if (a != m.known.end() && !a->second.list.empty()) secs = (int64_t)a->second.list[0].u;
     if (b != m.known.end() && !b->second.list.empty()) nanos = (int64_t)(int32_t)b->second.list[0].u;
     if (secs < kMinTs || secs > kMaxTs) return err.fail(ORC_RANGE, "google.protobuf.Timestamp: seconds out of range");
-    if (nanos < 0 || nanos > 1000000000) return err.fail(ORC_RANGE, "google.protobuf.Timestamp: nanos out of range");
+    if (nanos < 0 || nanos > 999999999) return err.fail(ORC_RANGE, "google.protobuf.Timestamp: nanos out of range");  // secondsInNanos = 999999999
     Bytes s = format_timestamp(secs, nanos);
     prepare(E_SCALAR);
     append_string((const uint8_t*)s.data(), s.size());
     return true;
   }
 
+  // [upstream marshalDuration]
+  bool duration(const DynMsg& m) {
+    int64_t secs = 0, nanos = 0;
+    auto a = m.known.find(1);
+    auto b = m.known.find(2);
+    if (a != m.known.end() && !a->second.list.empty()) secs = (int64_t)a->second.list[0].u;
+    if (b != m.known.end() && !b->second.list.empty()) nanos = (int64_t)(int32_t)b->second.list[0].u;
+    if (secs < -315576000000ll || secs > 315576000000ll) return err.fail(ORC_RANGE, "google.protobuf.Duration: seconds out of range");
+    if (nanos < -999999999 || nanos > 999999999) return err.fail(ORC_RANGE, "google.protobuf.Duration: nanos out of range");
+    if ((secs > 0 && nanos < 0) || (secs < 0 && nanos > 0))
+      return err.fail(ORC_RANGE, "google.protobuf.Duration: signs of seconds and nanos do not match");
+    std::string x;
+    if (secs < 0 || nanos < 0) {
+      x = "-";
+      secs = -secs;
+      nanos = -nanos;
+    }
+    char buf[48];
+    snprintf(buf, sizeof buf, "%lld.%09lld", (long long)secs, (long long)nanos);
+    x += buf;
+    auto trim = [&](const char* suf) {
+      size_t n = strlen(suf);
+      if (x.size() >= n && x.compare(x.size() - n, n, suf) == 0) x.resize(x.size() - n);
+    };
+    trim("000");
+    trim("000");
+    trim(".000");
+    x += "s";
+    prepare(E_SCALAR);
+    append_string((const uint8_t*)x.data(), x.size());
+    return true;
+  }
+  // [upstream marshalWrapperType: the value field written as a singular value, its default when unset]
+  bool wrapper(const DynMsg& m) {
+    const FieldDesc* vf = m.d->find_number(1);
+    if (!vf) return err.fail(ORC_UNSUPPORTED, "wrapper without a value field");
+    Val v;
+    auto a = m.known.find(1);
+    if (a != m.known.end() && !a->second.list.empty()) v = a->second.list[0];
+    return singular(*vf, vf->type, v);
+  }
+
   bool message(const DynMsg& m) {
     if (m.d->wkt == WKT_TIMESTAMP) return timestamp(m);
+    if (m.d->wkt == WKT_DURATION) return duration(m);
+    if (m.d->wkt == WKT_WRAPPER) return wrapper(m);
+    if (m.d->wkt == WKT_EMPTY) {  // [upstream marshalEmpty]
+      prepare(E_OBJ_OPEN);
+      out.push_back('{');
+      prepare(E_OBJ_CLOSE);
+      out.push_back('}');
+      return true;
+    }
     if (m.d->wkt != WKT_NONE) return err.fail(ORC_UNSUPPORTED, "well-known type " + m.d->full_name + " not supported");
     prepare(E_OBJ_OPEN);
     out.push_back('{');

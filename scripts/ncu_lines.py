@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--file", default="")
     ap.add_argument("--items", type=int, default=1)
     ap.add_argument("--top", type=int, default=60)
+    ap.add_argument("--inner", action="store_true", help="attribute to the innermost frame (the line itself) instead of the outermost one in --file")
     a = ap.parse_args()
     tmp = tempfile.mkdtemp()
     subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(a.obj)], cwd=tmp, stdout=subprocess.DEVNULL)
@@ -74,7 +75,7 @@ def main():
     tot = [0, 0, 0]
     for r, (_, _, ch) in zip(sass, insts):
         key = None
-        for f, l in reversed(ch):  # outermost frame first
+        for f, l in (ch if a.inner else reversed(ch)):  # chain: innermost first
             if not a.file or f == a.file:
                 key = (f, l)
                 break

@@ -48,6 +48,8 @@ K_REPLIES = [
 
 A = "bench.All"
 # (message, json, expected status name or None for "whatever the oracle says")
+WK = "wkt.Wkt"
+
 ENCODE_EDGE = [
     (A, b"", None), (A, b"{}", None), (A, b" { } ", None), (A, b"null", None), (A, b"[]", None), (A, b"{", None),
     (A, b'{"f_int32":1,}', None), (A, b'{"f_int32":1 "f_int64":2}', None), (A, b'{"f_int32":1}x', None),
@@ -145,7 +147,7 @@ DECODE_EDGE_HEX = [
 
 def random_encode_cases(n_per_msg=150, seed0=0, floats=True):
     """(message, json bytes) pairs rendered by python-protobuf in both key spellings."""
-    names = [A, P + "CreateDocumentRequest", P + "ProcessNodeRequest", P + "GetUserProfileResponse", "bench.Flat", "bench.Blob"]
+    names = [A, P + "CreateDocumentRequest", P + "ProcessNodeRequest", P + "GetUserProfileResponse", "bench.Flat", "bench.Blob", WK]
     out = []
     for name in names:
         for seed in range(seed0, seed0 + n_per_msg):
@@ -179,7 +181,7 @@ def mutate_json(j, rng):
 
 def random_decode_cases(n_per_msg=150, seed0=0, floats=True, mutators=True):
     names = [A, P + "CreateDocumentRequest", P + "StructuredMetadata", P + "Node", P + "GetUserProfileResponse", "bench.Flat",
-             P + "ProcessNodeResponse"]
+             P + "ProcessNodeResponse", WK]
     out = []
     for name in names:
         for seed in range(seed0, seed0 + n_per_msg):
@@ -272,3 +274,52 @@ def merge_cases():
                 F(1, 2, F(5, 2, F(1, 2, F(1, 2, b"j") + F(2, 2, b"u"))) + F(2, 2, b"t"))))
     res.append((P + "ProcessNodeRequest", F(1, 2, F(1, 2, b"n") + F(3, 2, F(1, 2, b"c1"))) + F(1, 2, F(3, 2, F(1, 2, b"c2")) + F(2, 2, b"val"))))
     return res
+
+
+# ---- well-known types with a JSON form of their own (protojson well_known_types.go): Duration, wrappers, Empty ----
+G = "google.protobuf."
+WKT_ENCODE = [(WK, j) for j in [
+    b'{"d":"1.5s"}', b'{"d":"0s"}', b'{"d":"-0s"}', b'{"d":".s"}', b'{"d":"-.s"}', b'{"d":"+3.s"}', b'{"d":".5s"}', b'{"d":"0.000000001s"}',
+    b'{"d":"-0.000000001s"}', b'{"d":"1.123456789s"}', b'{"d":"1.1234567890s"}', b'{"d":"01s"}', b'{"d":"00s"}', b'{"d":"1"}', b'{"d":"s"}',
+    b'{"d":"-s"}', b'{"d":"+s"}', b'{"d":""}', b'{"d":"1ss"}', b'{"d":"1s "}', b'{"d":" 1s"}', b'{"d":"1.5"}', b'{"d":"1,5s"}', b'{"d":"1e3s"}',
+    b'{"d":"315576000000s"}', b'{"d":"315576000000.999999999s"}', b'{"d":"-315576000000.999999999s"}', b'{"d":"315576000001s"}',
+    b'{"d":"-315576000001s"}', b'{"d":"9223372036854775807s"}', b'{"d":"9223372036854775808s"}', b'{"d":"99999999999999999999s"}',
+    b'{"d":"\\u0031s"}', b'{"d":"1\\u0073"}', b'{"d":1}', b'{"d":{}}', b'{"d":null}', b'{"d":"--1s"}', b'{"d":"1.-5s"}', b'{"d":"0.5s","rD":["1s","2s"],"mD":{"a":"3s","b":"-4.5s"}}',
+    b'{"rD":["1s",null]}', b'{"mD":{"a":null}}', b'{"oD":"1s","oSv":"x"}', b'{"oD":null,"oSv":"x"}', b'{"oD":"7s"}', b'{"oSv":""}',
+    b'{"e":{}}', b'{"e":{ }}', b'{"e":{"a":1}}', b'{"e":{"a"}}', b'{"e":[]}', b'{"e":null}', b'{"e":"x"}', b'{"e":{,}}', b'{"rE":[{},{}]}', b'{"rE":[{},{"x":1}]}',
+    b'{"bv":true}', b'{"bv":false}', b'{"bv":"true"}', b'{"bv":1}', b'{"bv":null}', b'{"i32":0}', b'{"i32":-5}', b'{"i32":"7"}', b'{"i32":2147483648}',
+    b'{"i32":1.0}', b'{"i32":{"value":1}}', b'{"i64":"-9223372036854775808"}', b'{"i64":5}', b'{"u32":4294967295}', b'{"u32":-1}',
+    b'{"u64":"18446744073709551615"}', b'{"u64":0}', b'{"fv":1.5}', b'{"fv":"NaN"}', b'{"fv":"-Infinity"}', b'{"fv":-0.0}', b'{"fv":0}', b'{"dv":1e300}',
+    b'{"dv":"1.25"}', b'{"dv":-0.0}', b'{"sv":"hello"}', b'{"sv":""}', b'{"sv":"\\u00e9\n"}', b'{"sv":5}', b'{"byv":"AQID"}', b'{"byv":""}', b'{"byv":"!"}',
+    b'{"rSv":["a","","b"]}', b'{"rSv":["a",null]}', b'{"rI32":[1,0,-1]}', b'{"mI64":{"1":"5","2":0}}', b'{"mI64":{"1":null}}',
+    b'{"ts":"2024-01-01T00:00:00Z","d":"1s","inner":{"d":"2s","inner":{"e":{},"sv":"deep"}}}', b'{"name":"n","bv":true,"i32":1,"i64":"2","u32":3,"u64":"4","fv":5,"dv":6,"sv":"7","byv":"OA=="}',
+]] + [(G + "Duration", b'"3s"'), (G + "Duration", b'{}'), (G + "Duration", b'{"seconds":3}'), (G + "Empty", b'{}'), (G + "Empty", b''),
+      (G + "Empty", b' { } '), (G + "Empty", b'{"a":1}'), (G + "StringValue", b'"x"'), (G + "StringValue", b'{}'), (G + "Int64Value", b'5'),
+      (G + "BoolValue", b'true'), ("wkt.HasStruct", b'{"x":1}'), ("wkt.HasStruct", b'{"s":{"a":1}}'), ("wkt.HasStruct", b'{"s":null,"x":2}')]
+
+
+def wkt_decode_cases():
+    F = wire_field
+    dur = lambda s, n: (F(1, 0, s) if s else b"") + (F(2, 0, n) if n else b"")
+    out = [(WK, w) for w in [
+        F(1, 2, dur(1, 500000000)), F(1, 2, b""), F(1, 2, dur(-1, -500000000)), F(1, 2, dur(0, -1)), F(1, 2, dur(1, -1)), F(1, 2, dur(-1, 1)),
+        F(1, 2, dur(315576000000, 999999999)), F(1, 2, dur(315576000001, 0)), F(1, 2, dur(-315576000001, 0)), F(1, 2, dur(0, 1000000000)),
+        F(1, 2, dur(0, -1000000000)), F(1, 2, dur(5, 123000)), F(1, 2, dur(5, 123000000)), F(1, 2, dur(5, 120)),
+        F(1, 2, F(1, 0, 1) + F(1, 0, 2) + F(3, 0, 9)), F(1, 2, b"\x08"), F(1, 2, dur(1, 0)) + F(1, 2, dur(0, 5)),
+        F(2, 2, dur(1, 0)) + F(2, 2, b"") + F(2, 2, dur(-2, -5)), F(3, 2, F(1, 2, b"k") + F(2, 2, dur(3, 0))) + F(3, 2, F(1, 2, b"a")),
+        F(3, 2, F(1, 2, b"k") + F(2, 2, dur(3, 0)) + F(2, 2, dur(0, 7))),
+        F(4, 2, b""), F(4, 2, F(9, 0, 1)), F(4, 2, b"\x08"), F(18, 2, b"") + F(18, 2, b""),
+        F(5, 2, b""), F(5, 2, F(1, 0, 1)), F(5, 2, F(1, 0, 0)), F(5, 2, F(1, 0, 1) + F(1, 0, 0)), F(5, 2, F(1, 2, b"x")),
+        F(6, 2, F(1, 0, -5)), F(6, 2, b""), F(7, 2, F(1, 0, -(1 << 63))), F(7, 2, b""), F(8, 2, F(1, 0, 4294967295)), F(9, 2, F(1, 0, (1 << 64) - 1)),
+        F(9, 2, b""), F(10, 2, F(1, 5, b"\x00\x00\xc0\x3f")), F(10, 2, F(1, 5, b"\x00\x00\xc0\x7f")), F(10, 2, b""), F(10, 2, F(1, 5, b"\x00\x00\x00\x80")),
+        F(11, 2, F(1, 1, b"\x00\x00\x00\x00\x00\x00\xf8\x3f")), F(11, 2, b""), F(12, 2, F(1, 2, b"hi")), F(12, 2, b""), F(12, 2, F(1, 2, b"\xff")),
+        F(12, 2, F(1, 2, b"\xff") + F(1, 2, b"ok")), F(12, 2, F(1, 2, b'q"\n')), F(13, 2, F(1, 2, b"\x01\x02\x03")), F(13, 2, b""),
+        F(14, 2, F(1, 2, b"a")) + F(14, 2, b"") + F(14, 2, F(1, 2, b"b")), F(20, 2, F(1, 0, 1)) + F(20, 2, b""),
+        F(15, 2, F(1, 0, 1) + F(2, 2, F(1, 0, 5))) + F(15, 2, F(1, 0, 2)), F(15, 2, F(1, 0, 1) + F(2, 2, F(1, 0, 5)) + F(2, 2, b"")),
+        F(16, 2, dur(7, 0)), F(16, 2, dur(7, 0)) + F(17, 2, F(1, 2, b"s")), F(17, 2, F(1, 2, b"s")) + F(16, 2, dur(7, 0)) + F(16, 2, dur(0, 9)),
+        F(12, 2, F(1, 2, b"a")) + F(21, 2, b"n") + F(12, 2, F(2, 0, 1)),
+        F(22, 2, F(1, 2, dur(2, 0)) + F(22, 2, F(4, 2, b"") + F(12, 2, F(1, 2, b"deep")))) + F(19, 2, F(1, 0, 1704110400)),
+    ]]
+    out += [(G + "Duration", dur(3, 0)), (G + "Duration", b""), (G + "Empty", b""), (G + "Empty", F(1, 0, 1)), (G + "StringValue", F(1, 2, b"x")),
+            (G + "StringValue", b""), (G + "Int64Value", F(1, 0, 5)), (G + "BoolValue", b""), ("wkt.HasStruct", F(2, 0, 1)), ("wkt.HasStruct", F(1, 2, b""))]
+    return out

@@ -16,7 +16,7 @@ import os
 import sys
 
 from google.protobuf import descriptor_pb2 as dpb
-from google.protobuf import timestamp_pb2, duration_pb2
+from google.protobuf import timestamp_pb2, duration_pb2, wrappers_pb2, empty_pb2, struct_pb2
 
 F = dpb.FieldDescriptorProto
 
@@ -307,6 +307,51 @@ def mixed_file():
     return fd
 
 
+def wkt_file():
+    """well-known types next to Timestamp: Duration, the nine wrappers and Empty as singular fields,
+    list elements, map values, oneof members and as the request / reply message of a method; Struct is there to be
+    refused"""
+    P = ".wkt"
+    G = ".google.protobuf."
+    fd = dpb.FileDescriptorProto(name="wkt.proto", package="wkt", syntax="proto3")
+    for dep in ("timestamp", "duration", "wrappers", "empty", "struct"):
+        fd.dependency.append("google/protobuf/%s.proto" % dep)
+    m = fd.message_type.add(name="Wkt")
+    W = P + ".Wkt"
+    add_field(m, "d", 1, G + "Duration")
+    add_field(m, "r_d", 2, G + "Duration", repeated=True)
+    add_map(m, W, "m_d", 3, "string", G + "Duration")
+    add_field(m, "e", 4, G + "Empty")
+    add_field(m, "bv", 5, G + "BoolValue")
+    add_field(m, "i32", 6, G + "Int32Value")
+    add_field(m, "i64", 7, G + "Int64Value")
+    add_field(m, "u32", 8, G + "UInt32Value")
+    add_field(m, "u64", 9, G + "UInt64Value")
+    add_field(m, "fv", 10, G + "FloatValue")
+    add_field(m, "dv", 11, G + "DoubleValue")
+    add_field(m, "sv", 12, G + "StringValue")
+    add_field(m, "byv", 13, G + "BytesValue")
+    add_field(m, "r_sv", 14, G + "StringValue", repeated=True)
+    add_map(m, W, "m_i64", 15, "int32", G + "Int64Value")
+    m.oneof_decl.add(name="choice")
+    add_field(m, "o_d", 16, G + "Duration", oneof=0)
+    add_field(m, "o_sv", 17, G + "StringValue", oneof=0)
+    add_field(m, "r_e", 18, G + "Empty", repeated=True)
+    add_field(m, "ts", 19, G + "Timestamp")
+    add_field(m, "r_i32", 20, G + "Int32Value", repeated=True)
+    add_field(m, "name", 21, "string")
+    add_field(m, "inner", 22, W)
+    m = fd.message_type.add(name="HasStruct")
+    add_field(m, "s", 1, G + "Struct")
+    add_field(m, "x", 2, "int32")
+    s = fd.service.add(name="WktService")
+    add_method(s, "Ping", G + "Empty", G + "Duration")
+    add_method(s, "Wait", G + "Duration", G + "Empty")
+    add_method(s, "Rename", G + "StringValue", G + "Int64Value")
+    add_method(s, "EchoWkt", W, W)
+    return fd
+
+
 def build_set():
     fds = dpb.FileDescriptorSet()
     ts = fds.file.add()
@@ -316,10 +361,15 @@ def build_set():
     # source_code_info is not needed on the hot path; strip to keep the fixture small
     ts.ClearField("source_code_info")
     du.ClearField("source_code_info")
+    for mod in (wrappers_pb2, empty_pb2, struct_pb2):
+        f = fds.file.add()
+        mod.DESCRIPTOR.CopyToProto(f)
+        f.ClearField("source_code_info")
     fds.file.append(hello_file())
     fds.file.append(complex_file())
     fds.file.append(bench_file())
     fds.file.append(mixed_file())
+    fds.file.append(wkt_file())
     return fds
 
 

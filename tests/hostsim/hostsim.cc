@@ -291,7 +291,13 @@ extern "C" int hs_encode_walk(void* h, int msg, const uint8_t* json, uint32_t n,
   memcpy(in + in_off, json, n);
   uint32_t cap = n / 2 + 8;  // as the kernels lay the regions out: 8 bytes of IR per input byte + 128
   uint8_t* region = (uint8_t*)aligned_alloc(16, (size_t)cap * 16 + 16);
-  memset(region, 0xCC, (size_t)cap * 16 + 16);
+  // what an earlier batch may have left there: well-formed IR nodes (a varint leaf with a two-byte tag), so that a
+  // record the walker forgets to write shows up in the output
+  memset(region + (size_t)cap * 16, 0xCC, 16);  // sentinel behind the region
+  for (size_t k = 0; k < (size_t)cap; k++) {
+    const u32 stale[4] = {5u, 0u, 0xFFFFFu, 1u /* N_VARINT */ | (0x150u << 8)};
+    memcpy(region + k * 16, stale, 16);
+  }
   static CoopWalk S;
   memset(&S, 0xAB, sizeof S);
   static CwPlaceSh P;

@@ -137,6 +137,11 @@ def fill(rng, msg, depth=0, p_field=0.35, floats=True):
         msg.seconds = rng.choice([0, 1704110400, -62135596800, 253402300799, rng.randint(-62135596800, 253402300799)])
         msg.nanos = rng.choice([0, 0, 500000000, 123000, 999999999, 1, rng.randint(0, 999999999)])
         return
+    if d.full_name == "google.protobuf.Duration":
+        sign = rng.choice([1, 1, -1])
+        msg.seconds = sign * rng.choice([0, 0, 1, 3600, 315576000000, rng.randint(0, 315576000000)])
+        msg.nanos = sign * rng.choice([0, 0, 500000000, 123000, 999999999, 1, rng.randint(0, 999999999)])
+        return
     for fd in d.fields:
         if rng.random() > p_field:
             continue

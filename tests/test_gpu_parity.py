@@ -106,6 +106,39 @@ def test_decode_random(engine, schema, oracle):
     _compare(items, eo, es, oo, os_, lambda n, b: False)
 
 
+def test_null_members_after_other_batches(engine, schema, oracle):
+    """a null member has no bytes, but the lock-step emitter still visits its IR slot: it must not find what an earlier
+    batch left there (found by the small_chunks path in round 2: 0x10 came out as 0xd0)"""
+    first = [(cases.A, b'{"f_int32":%d,"f_int64":"%d","f_uint32":%d,"f_string":"abc","f_sint32":-%d}' % (k + 300, k * 77 + 1, k + 7, k + 1))
+             for k in range(96)]
+    eo, es = _run(engine, schema, True, first)
+    oo, os_ = _oracle(oracle, True, first)
+    _compare(first, eo, es, oo, os_, lambda n, b: False)
+    for rep in range(3):
+        second = [(cases.A, b'{"f_int32":null,"f_int64":"%d","f_uint32":null,"f_string":null,"f_sint32":%d}' % (k * 7 + rep, k + 1))
+                  for k in range(96)] + [("wkt.HasStruct", b'{"s":null,"x":2}'), (cases.A, b'{"f_msg":null,"r_int32":null,"m_str_int32":null,"f_bool":true}')]
+        eo, es = _run(engine, schema, True, second)
+        oo, os_ = _oracle(oracle, True, second)
+        _compare(second, eo, es, oo, os_, lambda n, b: False)
+        assert all(x == 0 for x in os_)
+
+
+def test_wkt_duration_wrappers_empty(engine, schema, oracle):
+    """Duration, the nine wrappers and Empty (protojson well_known_types.go) in every position and as root messages,
+    both directions, every kernel path; Struct stays refused"""
+    items = cases.WKT_ENCODE
+    eo, es = _run(engine, schema, True, items)
+    oo, os_ = _oracle(oracle, True, items)
+    _compare(items, eo, es, oo, os_, lambda n, b: n == "wkt.HasStruct" and b"s" in b)
+    assert sum(1 for x in os_ if x == 0) >= 55
+    items = cases.wkt_decode_cases()
+    for flags in (0, 1):
+        eo, es = _run(engine, schema, False, items, flags)
+        oo, os_ = _oracle(oracle, False, items, flags)
+        _compare(items, eo, es, oo, os_, lambda n, b: False)
+    assert sum(1 for x in os_ if x == 0) >= 45
+
+
 def test_decode_merges_split_submessages(engine, schema, oracle):
     """singular sub-messages that arrive in several occurrences are merged the way proto.Unmarshal does
     (reflection.go:363): plain fields, oneof members, map values, Timestamps, damaged pieces"""

@@ -44,8 +44,7 @@ def test_encode_edge_cases(oracle, hsim):
         if want is not None:
             est, _ = hsim.encode(name, js)
             assert ["ok", "syntax", "unknown_field"][est] == want
-    # documented gaps: float/double parsing
-    assert all(b"float" in g or b"double" in g for g in gaps), gaps
+    assert not gaps, gaps
 
 
 def test_encode_random(oracle, hsim):
@@ -82,13 +81,36 @@ def _check_decode(oracle, hsim, name, w, i=0, flags=0):
 
 def test_decode_edge_cases(oracle, hsim):
     for i, (name, hx) in enumerate(cases.DECODE_EDGE_HEX):
-        r = _check_decode(oracle, hsim, name, bytes.fromhex(hx), i)
-        assert r == "ok" or hx.startswith("ba04"), hx
+        assert _check_decode(oracle, hsim, name, bytes.fromhex(hx), i) == "ok", hx
 
 
 def test_decode_random(oracle, hsim):
     for i, (name, w) in enumerate(cases.random_decode_cases(100)):
         assert _check_decode(oracle, hsim, name, w, i, i & 1) == "ok", (name, w.hex())
+
+
+def test_wkt_duration_wrappers_empty(oracle, hsim):
+    """Duration, the nine wrappers and Empty in every position (singular, list element, map value, oneof member, root
+    message) in both directions (protojson well_known_types.go); Struct is refused, never answered differently"""
+    n_ok = n_err = 0
+    for i, (name, js) in enumerate(cases.WKT_ENCODE):
+        ost, ow, _ = oracle.encode(name, js)
+        est, ew = hsim.encode(name, js, i % 16, (i * 5) % 16)
+        assert ost == est or (ost != 0 and est != 0 and {ost, est} <= {1, 3, 5}), (name, js, ost, est)
+        if ost == 0:
+            assert ew == ow, (name, js, ow.hex(), ew.hex())
+        n_ok += ost == 0
+        n_err += ost != 0
+    assert n_ok >= 55 and n_err >= 40
+    n_ok = 0
+    for i, (name, w) in enumerate(cases.wkt_decode_cases()):
+        ost, oj, _ = oracle.decode(name, w, i & 1)
+        est, ej = hsim.decode(name, w, i & 1, i % 16, (i * 5) % 16)
+        assert cases.status_compatible(ost, est), (name, w.hex(), ost, est)
+        if ost == 0:
+            assert ej == oj, (name, w.hex(), oj, ej)
+        n_ok += ost == 0
+    assert n_ok >= 45
 
 
 def test_decode_merges_split_submessages(oracle, hsim):

@@ -156,7 +156,7 @@ def test_oracle_vs_upb():
     """wire bytes: identical to upb's deterministic serialization; JSON: equal after parsing."""
     O = orc.load_schema()
     names = [cases.A, cases.P + "CreateDocumentRequest", cases.P + "ProcessNodeRequest", cases.P + "GetUserProfileResponse",
-             "bench.Flat", "bench.Blob"]
+             "bench.Flat", "bench.Blob", "wkt.Wkt"]
     for name in names:
         for seed in range(120):
             m = pbgen.random_message(name, seed, floats=True)
