@@ -143,6 +143,75 @@ GGR_DEV bool coop_wire_zero(const u8* b, u32 pos, u32 lim, u32 wt, bool* ok) {
   return any == 0;
 }
 
+// Eight bytes of the item at `pos` (two aligned 8-byte loads, the second one only inside the item's last 16-byte
+// chunk): tag, length prefix and the first value bytes of a field decode from registers - one round trip to the
+// memory system per field instead of one per varint (the tables in shared memory leave the L1 too small to hold
+// the items, so every dependent byte load is an L2 access).
+GGR_DEV u64 coop_window(const u8* in, u32 pos, u32 end_al) {
+  const u32 a = pos & ~7u;
+#if defined(__CUDA_ARCH__)
+  const u64 lo = __ldg(reinterpret_cast<const unsigned long long*>(in + a));
+  const u64 hi = a + 8u < end_al ? __ldg(reinterpret_cast<const unsigned long long*>(in + a + 8u)) : 0ull;
+#else
+  u64 lo, hi = 0;
+  memcpy(&lo, in + a, 8);
+  if (a + 8u < end_al) memcpy(&hi, in + a + 8u, 8);
+#endif
+  const u32 sh = (pos & 7u) * 8u;
+  return sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
+}
+// A field header out of the window W at pos: tag (one or two bytes) and, by wire type, the extent of the value.
+// Returns false when the bytes do not fit the window (long tags, lengths of three bytes and more, varints that run
+// past it): the caller then decodes byte by byte.  On success: *tag, *body (payload start of a length-delimited
+// value, else the value start), *vend, *zero (varint / fixed32 value is 0; length is 0) - bounds are the caller's.
+GGR_DEV bool coop_header(u64 W, u32 pos, u32* tag, u32* tag_len, u32* body, u32* vend, bool* zero) {
+  const u32 b0 = (u32)W & 0xFFu;
+  u32 t = b0, tl = 1;
+  if (b0 >= 0x80u) {
+    const u32 b1 = (u32)(W >> 8) & 0xFFu;
+    if (b1 >= 0x80u) return false;
+    t = (b0 & 0x7Fu) | (b1 << 7);
+    tl = 2;
+  }
+  *tag = t;
+  *tag_len = tl;
+  const u64 V = W >> (8u * tl);  // 6 or 7 value bytes
+  const u32 wt = t & 7u;
+  const u32 vpos = pos + tl;
+  if (wt == 2u) {
+    const u32 l0 = (u32)V & 0xFFu;
+    u32 len = l0, ll = 1;
+    if (l0 >= 0x80u) {
+      const u32 l1 = (u32)(V >> 8) & 0xFFu;
+      if (l1 >= 0x80u) return false;
+      len = (l0 & 0x7Fu) | (l1 << 7);
+      ll = 2;
+    }
+    *body = vpos + ll;
+    *vend = vpos + ll + len;
+    *zero = len == 0;
+    return true;
+  }
+  *body = vpos;
+  if (wt == 0u) {
+    // first byte without the continuation bit among the bytes the window holds
+    const u64 keep = tl == 1 ? 0x00FFFFFFFFFFFFFFull : 0x0000FFFFFFFFFFFFull;
+    const u64 stop = ~V & 0x8080808080808080ull & keep;
+    if (!stop) return false;
+    const u32 k = (u32)(wp_ctz64(stop) >> 3);  // index of the last byte of the varint
+    *vend = vpos + k + 1u;
+    const u64 bits = V & (0x7F7F7F7F7F7F7F7Full >> (8u * (7u - k)));
+    *zero = bits == 0;
+    return true;
+  }
+  if (wt == 5u) {
+    *vend = vpos + 4u;
+    *zero = (u32)V == 0u;
+    return true;
+  }
+  return false;  // fixed64 (the value does not fit), groups, invalid wire types
+}
+
 // R1, one lane: scan the top-level fields of message entry `me` and append its children.
 template <class SH>
 GGR_DEV void coop_scan_message(SH& S, const DecCtx& cx, u32 me) {
@@ -163,30 +232,41 @@ GGR_DEV void coop_scan_message(SH& S, const DecCtx& cx, u32 me) {
   u32 oneofs = 0;
   u32 prev = 0xFFFFu;  // previous child entry
   bool any = false;
+  const u32 end_al = (lim + 15u) & ~15u;  // the item's bytes are readable up to the end of their last 16-byte chunk
   while (pos < lim) {
-    u64 tag;
-    if (!br_varint(in, pos, lim, &tag)) { S.bail = 1; return; }
+    // the field header out of one 8-byte window; what does not fit it is decoded byte by byte
+    u32 wtag = 0, wtl = 0, wbody = 0, wvend = 0;
+    bool wzero = false;
+    const bool fast = coop_header(coop_window(in, pos, end_al), pos, &wtag, &wtl, &wbody, &wvend, &wzero) && wvend <= lim && wbody <= lim;
+    u64 tag = wtag;
+    if (fast) pos += wtl;
+    else if (!br_varint(in, pos, lim, &tag)) { S.bail = 1; return; }
     const u64 num64 = tag >> 3;
     const u32 wt = (u32)(tag & 7);
     if (num64 == 0 || num64 > 0x1FFFFFFFull || wt == 3 || wt == 4 || wt > 5) { S.bail = 1; return; }
     const u32 num = (u32)num64;
     const i32 ei = find_field(T, md, num);
     if (ei < 0) {
-      if (!br_skip(in, pos, lim, wt)) { S.bail = 1; return; }
+      if (fast) pos = wvend;
+      else if (!br_skip(in, pos, lim, wt)) { S.bail = 1; return; }
       continue;
     }
     const u32 gf = md.field_first + (u32)ei;
     const FieldD f = ggr_field(T, gf);
     const bool packed_in = (f.flags & GF_PACKABLE) && wt == 2;
     if (wt != f.wt && !packed_in) {
-      if (!br_skip(in, pos, lim, wt)) { S.bail = 1; return; }
+      if (fast) pos = wvend;
+      else if (!br_skip(in, pos, lim, wt)) { S.bail = 1; return; }
       continue;
     }
     if ((f.flags & GF_MAP) || gf >= 0xFFFFu) { S.bail = 1; return; }
     const u32 vpos = pos;
     // value extent: [vpos, vend), payload of length-delimited values at body
     u32 body = pos, vend = pos;
-    if (wt == 2) {
+    if (fast) {
+      body = wbody;
+      vend = wvend;
+    } else if (wt == 2) {
       u64 len;
       if (!br_varint(in, body, lim, &len) || len > (u64)(lim - body)) { S.bail = 1; return; }
       vend = body + (u32)len;
@@ -221,8 +301,8 @@ GGR_DEV void coop_scan_message(SH& S, const DecCtx& cx, u32 me) {
       }
       last_decl = (i32)f.decl_index;
       if (f.kind != GK_MESSAGE && !(f.flags & GF_PRESENCE)) {
-        bool ok;
-        const bool z = coop_wire_zero(in, vpos, lim, wt, &ok);
+        bool ok = true;
+        const bool z = fast ? wzero : coop_wire_zero(in, vpos, lim, wt, &ok);
         if (!ok) { S.bail = 1; return; }
         if (z) continue;  // implicit presence: the zero value is not written
       }

@@ -818,6 +818,72 @@ GGR_DEVN int put_wkt(W& w, const DecCtx& cx, u32 msg, u32 start, u32 lim) {
     if (st != GST_OK) return st;
     return put_scalar_or_default(w, cx, vf, me);
   }
+  if (cd.wkt == GGR_WKT_FIELDMASK) {
+    // [upstream marshalFieldMask] the paths camelCase, joined with ','.  A path that is not a dotted name, or that does
+    // not survive camelCase -> snake_case (upper-case letters, '_' not followed by a lower-case letter), is an error
+    // of Marshal: parked like the range errors.  proto.Unmarshal has checked every path's UTF-8 before.
+    w.put1('"');
+    u32 first = 1;
+    bool bad = false;
+    while (r.pos < lim) {
+      u64 tag, len;
+      if (!rd_varint(r, lim, &tag)) return GST_BAD_WIRE;
+      u64 num = tag >> 3;
+      u32 wt = (u32)(tag & 7);
+      if (num == 0 || num > 0x1FFFFFFFull || wt == 4) return GST_BAD_WIRE;
+      if (num != 1 || wt != 2) {
+        if (!rd_skip_value(r, lim, (u32)num, wt)) return GST_BAD_WIRE;
+        continue;
+      }
+      if (!rd_varint(r, lim, &len) || len > (u64)(lim - r.pos)) return GST_BAD_WIRE;
+      if (!first) w.put1(',');
+      first = 0;
+      bool seg_start = true, under = false;
+      for (u32 k = 0; k < (u32)len; k++) {
+        u32 c = r.peek();
+        r.skip(1);
+        if (c >= 0x80u) {  // not a name character; is it at least UTF-8?  (proto.Unmarshal's check comes first)
+          Rd v;
+          v.init(cx.in, r.pos - 1u, lim, cx.rw);
+          Cnt cn;
+          cn.pos = 0;
+          int st = put_json_string(cn, v, (u32)len - k);
+          if (st != GST_OK) return st;
+          bad = true;
+          rd_jump(r, r.pos - 1u + ((u32)len - k));
+          break;
+        }
+        const bool upper = c - 'A' < 26u, lower = c - 'a' < 26u, digit = c - '0' < 10u;
+        if (c == '.') {
+          if (seg_start || under) bad = true;
+          seg_start = true;
+          under = false;
+          w.put1(c);
+          continue;
+        }
+        if (upper || !(lower || c == '_' || (digit && !seg_start))) bad = true;
+        if (under && !lower) bad = true;  // '_' must be followed by a lower-case letter to come back from camelCase
+        seg_start = false;
+        if (c == '_') {
+          under = true;
+          continue;
+        }
+        w.put1(under ? c - ('a' - 'A') : c);
+        under = false;
+      }
+      if (seg_start || under) bad = true;  // empty path, trailing '.', trailing '_'
+    }
+    if (r.pos != lim) return GST_BAD_WIRE;
+    w.put1('"');
+    if (bad) {
+      if (cx.late) {
+        *cx.late = GST_INVALID_VALUE;
+        return GST_OK;
+      }
+      return GST_INVALID_VALUE;
+    }
+    return GST_OK;
+  }
   if (cd.wkt == GGR_WKT_EMPTY) {
     while (r.pos < lim) {
       u64 tag;
@@ -1089,7 +1155,8 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
   fr.end = end; fr.msg = root_msg; fr.last_decl = -1; fr.open = 0; fr.first = 1; fr.elem_first = 1; fr.oneofs = 0;
   fr.start = start; fr.scan = start; fr.cur_emit = 0; fr.state = 0;
   fr.base = cx.in;
-  DecCtx lc = cx;  // slow walk: the context of the current frame (lc.in = fr.base)
+  DecCtx lc;  // slow walk: the context of the current frame (lc.in = fr.base)
+  if (SLOW && !finished) lc = cx;
   MsgD md;
   if (!finished && rec > GGR_DEC_MAX_REC) {
     result = GST_DEPTH;

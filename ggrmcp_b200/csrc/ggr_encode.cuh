@@ -24,7 +24,8 @@
 #define GGR_NIL 0xFFFFFu
 #define GGR_MAX_NODES 0xFFFFFu
 
-enum { N_SKIP = 0, N_VARINT = 1, N_FIX32 = 2, N_FIX64 = 3, N_STR = 4, N_BYTES = 5, N_MSG = 6, N_LIST = 7, N_MAP = 8, N_ENTRY = 9 };
+enum { N_SKIP = 0, N_VARINT = 1, N_FIX32 = 2, N_FIX64 = 3, N_STR = 4, N_BYTES = 5, N_MSG = 6, N_LIST = 7, N_MAP = 8, N_ENTRY = 9,
+       N_FMPATH = 10 /* one path of a FieldMask: a = position of its first byte, b = byte count; written snake_case */ };
 #define NF_ESC 1u     /* string token has escapes: decode while copying */
 #define NF_PACKED 2u  /* N_LIST: packed */
 #define NF_URL 4u     /* N_BYTES: URL-safe alphabet */
@@ -615,6 +616,76 @@ struct EncResult {
 
 // Rare value forms of encode_parse as calls (inlined they add 35 thousand instructions to the kernel): the text of a
 // Timestamp / Duration string, the value of a wrapper message.
+// google.protobuf.FieldMask: "a,fooBar.baz" -> paths a, foo_bar.baz (protojson unmarshalFieldMask: TrimSpace, split
+// at ',', JSONSnakeCase, no '_' in the JSON form, the result a valid dotted name).  One N_FMPATH node per path, chained
+// behind *head; *payload = their wire bytes.  The token must be free of escapes: a mask written with escapes is left to
+// the caller as unsupported, never answered differently.
+GGR_DEVN int parse_field_mask(EncCtx& cx, u32 quote_pos, u32 close_pos, bool escapes, u32* head, u32* payload) {
+  *head = GGR_NIL;
+  *payload = 0;
+  if (escapes) return GST_UNSUPPORTED;
+  const u8* in = cx.in;
+  u32 b = quote_pos + 1u, e = close_pos;  // [b, e): the text between the quotes
+  // strings.TrimSpace: ' ' (the other ASCII spaces cannot stand unescaped in a JSON string) and the Unicode spaces
+  // U+0085, U+00A0, U+1680, U+2000-200A, U+2028, U+2029, U+202F, U+205F, U+3000
+  auto space_len = [&](u32 p, u32 lim) -> u32 {  // bytes of the space that starts at p (0: none)
+    const u32 c0 = in[p];
+    if (c0 == ' ') return 1u;
+    if (c0 == 0xC2u && p + 1u < lim && (in[p + 1u] == 0x85u || in[p + 1u] == 0xA0u)) return 2u;
+    if (p + 2u < lim) {
+      const u32 c1 = in[p + 1u], c2 = in[p + 2u];
+      if (c0 == 0xE1u && c1 == 0x9Au && c2 == 0x80u) return 3u;
+      if (c0 == 0xE2u && c1 == 0x80u && (c2 - 0x80u <= 0x0Au || c2 == 0xA8u || c2 == 0xA9u || c2 == 0xAFu)) return 3u;
+      if (c0 == 0xE2u && c1 == 0x81u && c2 == 0x9Fu) return 3u;
+      if (c0 == 0xE3u && c1 == 0x80u && c2 == 0x80u) return 3u;
+    }
+    return 0u;
+  };
+  for (u32 k; b < e && (k = space_len(b, e)) != 0u;) b += k;
+  while (e > b) {
+    u32 k = e - 1u;  // start of the last character
+    while (k > b && (in[k] & 0xC0u) == 0x80u) k--;
+    const u32 n = space_len(k, e);
+    if (n == 0u || k + n != e) break;
+    e = k;
+  }
+  if (b == e) return GST_OK;
+  u32 tail = GGR_NIL;
+  u32 p = b;
+  for (;;) {
+    // one path [p, q)
+    u32 q = p, extra = 0;
+    bool seg_start = true, valid = true;
+    while (q < e && in[q] != ',') {
+      const u32 c = in[q];
+      const bool upper = c - 'A' < 26u, lower = c - 'a' < 26u, digit = c - '0' < 10u;
+      if (c == '.') {
+        if (seg_start) valid = false;  // empty segment
+        seg_start = true;
+      } else {
+        if (upper) extra++;
+        // after JSONSnakeCase an upper-case letter is "_x": a letter either way; '_' itself is not allowed in the JSON form
+        if (!(upper || lower || (digit && !seg_start))) valid = false;
+        seg_start = false;
+      }
+      q++;
+    }
+    if (seg_start || !valid) return GST_INVALID_VALUE;  // empty path, trailing '.', foreign characters
+    const u32 out_len = (q - p) + extra;
+    u32 idx;
+    int st = enc_new_node(cx, &idx);
+    if (st != GST_OK) return st;
+    node_store(cx.ir, idx, p, q - p, GGR_NIL, 0, node_meta(N_FMPATH, 0, 0x0Au));
+    if (tail == GGR_NIL) *head = idx;
+    else node_set_next(cx.ir, tail, idx);
+    tail = idx;
+    *payload += 1u + varint_size(out_len) + out_len;
+    if (q >= e) break;
+    p = q + 1u;
+    if (p >= e) return GST_INVALID_VALUE;  // "a," : an empty last path
+  }
+  return GST_OK;
+}
 GGR_DEVN int parse_time_value(const u8* in, u32 quote_pos, u32 end, bool duration, i64* secs, i32* nanos) {
   StrIter it;
   it.init(in, quote_pos, end);
@@ -899,6 +970,16 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
               first = lidx;
               payload = vf.tag_len + l.body;
             }
+          } else if (vd.wkt == GGR_WKT_FIELDMASK) {
+            if (r.get() != '"') GGR_RET(GST_SYNTAX);
+            u32 q = r.pos;
+            StrInfo si;
+            st = scan_string<false>(r, &si);
+            if (st != GST_OK) GGR_RET(st);
+            st = enc_new_node(cx, &midx);
+            if (st != GST_OK) GGR_RET(st);
+            st = parse_field_mask(cx, q, r.pos - 1u, (si.flags & SF_ESCAPES) != 0, &first, &payload);
+            if (st != GST_OK) GGR_RET(st);
           } else if (vd.wkt == GGR_WKT_EMPTY) {
             // an object without members (unmarshalEmpty; DiscardUnknown is off on this path)
             if (r.get() != '{') GGR_RET(GST_SYNTAX);
@@ -1140,6 +1221,21 @@ GGR_DEV void encode_emit(const u8* in, u32 end, const u8* ir, u32 first, W& w, b
         put_varint(w, nd.y);
         copy_string(w, in, nd.x, end, nd.y, (flags & NF_ESC) != 0);
         break;
+      case N_FMPATH: {  // tag 0x0A, the length after JSONSnakeCase, then the text with "_x" for every "X"
+        u32 out_len = nd.y;
+        for (u32 k = 0; k < nd.y; k++) out_len += (u32)in[nd.x + k] - 'A' < 26u ? 1u : 0u;
+        w.put1(0x0Au);
+        put_varint(w, out_len);
+        for (u32 k = 0; k < nd.y; k++) {
+          u32 c = in[nd.x + k];
+          if (c - 'A' < 26u) {
+            w.put1('_');
+            c += 'a' - 'A';
+          }
+          w.put1(c);
+        }
+        break;
+      }
       case N_BYTES: {
         if (tag) put_varint(w, tag);
         put_varint(w, nd.y);

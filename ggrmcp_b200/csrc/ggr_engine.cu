@@ -105,6 +105,14 @@ __global__ void __launch_bounds__(256) k_mark(const u32* __restrict__ list, cons
   first[item] = 0xFFFFFu;
 }
 
+// GGR_POISON=1: what a previous batch may have left in a scratch buffer - IR nodes that are well formed (a varint leaf
+// with a two-byte tag), which as plain words are large sizes, offsets and list entries.  A kernel that reads a slot
+// nobody wrote in this call then produces wrong bytes in the parity tests instead of passing on fresh zeroes.
+__global__ void k_poison(uint4* p, size_t n16) {
+  const size_t i = (size_t)blockIdx.x * 256u + threadIdx.x;
+  if (i < n16) p[i] = make_uint4(5u, 0u, 0xFFFFFu, 1u | (0x150u << 8));
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -155,6 +163,7 @@ struct ggr_engine {
   // batch and a reply batch can be in flight on two streams at the same time
   Scratch dev_sc[2];
   bool use_coop_enc = true;  // GGR_COOP_ENC=0 disables the lock-step request-side parser (A/B runs)
+  bool poison = false;        // GGR_POISON=1 (tests): every call leaves its scratch full of well-formed stale records
   bool use_walk = true;      // GGR_WALK=0: the one-lane-per-object walker of round 1 instead of ggr_walk.cuh (A/B runs)
   bool trace = false;        // GGR_TRACE=1: host-buffer calls print a per-chunk timeline to stderr
   // items smaller than this go straight to the per-thread kernels, which are cheaper for them
@@ -353,6 +362,7 @@ int ggr_engine_create(const ggr_config* cfg, ggr_engine** out) {
   if (const char* nc = getenv("GGR_COOP")) e->use_coop = nc[0] != '0';
   if (const char* nc = getenv("GGR_COOP_ENC")) e->use_coop_enc = nc[0] != '0';
   if (const char* nc = getenv("GGR_WALK")) e->use_walk = nc[0] != '0';
+  if (const char* pz = getenv("GGR_POISON")) e->poison = pz[0] == '1';
   if (const char* nc = getenv("GGR_TRACE")) e->trace = nc[0] != '0';
   if (const char* nc = getenv("GGR_LOCKSTEP_MIN_BYTES")) e->min_json = e->min_wire = (uint32_t)strtoul(nc, nullptr, 10);
   if (const char* nc = getenv("GGR_SLOTS")) {
@@ -545,9 +555,25 @@ int ggr_synchronize(ggr_engine* e) {
   return cuda_ok(e, cudaStreamSynchronize(e->stream), "cudaStreamSynchronize") ? GGR_SUCCESS : GGR_ERR_CUDA;
 }
 
+static int run_dev_kernels(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode, int64_t n, const int32_t* msg_id, const uint8_t* in,
+                           const uint64_t* in_off, uint64_t in_bytes, uint8_t* out, uint64_t out_cap, uint64_t* out_off,
+                           int32_t* status, uint32_t flags, cudaStream_t st);
 static int run_dev(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode, int64_t n, const int32_t* msg_id, const uint8_t* in,
                    const uint64_t* in_off, uint64_t in_bytes, uint8_t* out, uint64_t out_cap, uint64_t* out_off,
                    int32_t* status, uint32_t flags, cudaStream_t st) {
+  const int rc = run_dev_kernels(e, s, sc, encode, n, msg_id, in, in_off, in_bytes, out, out_cap, out_off, status, flags, st);
+  if (e && e->poison) {  // after the last kernel of the call, in stream order
+    DevBuf* bufs[] = {&sc.ir, &sc.size, &sc.aux, &sc.sums, &sc.pend, &sc.ioff, &sc.nn};
+    for (DevBuf* b : bufs) {
+      const size_t n16 = b->cap / 16;
+      if (b->p && n16) k_poison<<<(unsigned)((n16 + 255) / 256), 256, 0, st>>>((uint4*)b->p, n16);
+    }
+  }
+  return rc;
+}
+static int run_dev_kernels(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool encode, int64_t n, const int32_t* msg_id, const uint8_t* in,
+                           const uint64_t* in_off, uint64_t in_bytes, uint8_t* out, uint64_t out_cap, uint64_t* out_off,
+                           int32_t* status, uint32_t flags, cudaStream_t st) {
   if (!e || !s || n < 0 || (n > 0 && (!msg_id || !in || !in_off || !out_off || !status))) return GGR_ERR_INVALID_ARGUMENT;
   if (((uintptr_t)in & 15) || ((uintptr_t)out & 7)) return GGR_ERR_INVALID_ARGUMENT;
   DeviceGuard dg(e->device);

@@ -3,7 +3,12 @@
 #include "ggr_decode.cuh"
 #include "ggr_scan.cuh"
 
-__global__ void __launch_bounds__(GGR_BLOCK, 6)
+// resident blocks per SM the per-thread reply kernels are compiled for (register cap = 65536 / (128 * GGR_DEC_MINB))
+#ifndef GGR_DEC_MINB
+#define GGR_DEC_MINB 8
+#endif
+
+__global__ void __launch_bounds__(GGR_BLOCK, GGR_DEC_MINB)
 k_decode_size(const u8* __restrict__ blob, long long n, u32 n_msgs, const i32* __restrict__ msg_id,
               const u8* __restrict__ in, const u64* __restrict__ in_off, u32 flags, u32* __restrict__ size,
               u32* __restrict__ mode, i32* __restrict__ status, u64* __restrict__ block_sums, int after_coop,
@@ -61,7 +66,7 @@ k_decode_size(const u8* __restrict__ blob, long long n, u32 n_msgs, const i32* _
   if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
 }
 
-__global__ void __launch_bounds__(GGR_BLOCK, 6)
+__global__ void __launch_bounds__(GGR_BLOCK, GGR_DEC_MINB)
 k_decode_write(const u8* __restrict__ blob, long long n, const i32* __restrict__ msg_id, const u8* __restrict__ in,
                const u64* __restrict__ in_off, u32 flags, const u32* __restrict__ size, const u32* __restrict__ mode,
                i32* __restrict__ status, const u64* __restrict__ block_prefix, u8* __restrict__ out, u64 out_cap,

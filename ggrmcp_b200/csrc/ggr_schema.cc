@@ -384,14 +384,15 @@ bool compile_schema(const uint8_t* fds, size_t n, WireOrder order, CompiledSchem
     if (m.full_name == "google.protobuf.Timestamp") gm.wkt = GGR_WKT_TIMESTAMP;
     else if (m.full_name == "google.protobuf.Duration") gm.wkt = GGR_WKT_DURATION;
     else if (m.full_name == "google.protobuf.Empty") gm.wkt = GGR_WKT_EMPTY;
+    else if (m.full_name == "google.protobuf.FieldMask" && m.fields.size() == 1 && m.fields[0].number == 1) gm.wkt = GGR_WKT_FIELDMASK;
     else if (m.full_name.rfind("google.protobuf.", 0) == 0) {
       // the nine wrappers: the JSON form is the bare value of field 1 (protojson marshalWrapperType)
       static const char* wr[] = {"DoubleValue", "FloatValue", "Int64Value", "UInt64Value", "Int32Value", "UInt32Value", "BoolValue",
                                  "StringValue", "BytesValue"};
       for (const char* w : wr)
         if (m.full_name == std::string("google.protobuf.") + w && m.fields.size() == 1 && m.fields[0].number == 1) gm.wkt = GGR_WKT_WRAPPER;
-      // recognised and refused: dynamic JSON (Struct / Value / ListValue), type URLs (Any), path lists
-      static const char* wk[] = {"Any", "Struct", "Value", "ListValue", "FieldMask"};
+      // recognised and refused: dynamic JSON (Struct / Value / ListValue), type URLs (Any)
+      static const char* wk[] = {"Any", "Struct", "Value", "ListValue"};
       for (const char* w : wk) if (m.full_name == std::string("google.protobuf.") + w) gm.wkt = GGR_WKT_UNSUPPORTED;
     }
     bool decl_is_emit = true;

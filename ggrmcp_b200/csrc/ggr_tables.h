@@ -19,7 +19,7 @@ enum {
   GK_UINT32 = 13, GK_ENUM = 14, GK_SFIXED32 = 15, GK_SFIXED64 = 16, GK_SINT32 = 17, GK_SINT64 = 18
 };
 
-enum { GGR_WKT_NONE = 0, GGR_WKT_TIMESTAMP = 1, GGR_WKT_DURATION = 2, GGR_WKT_WRAPPER = 3, GGR_WKT_EMPTY = 4, GGR_WKT_UNSUPPORTED = 99 };
+enum { GGR_WKT_NONE = 0, GGR_WKT_TIMESTAMP = 1, GGR_WKT_DURATION = 2, GGR_WKT_WRAPPER = 3, GGR_WKT_EMPTY = 4, GGR_WKT_FIELDMASK = 5, GGR_WKT_UNSUPPORTED = 99 };
 
 // GgrField.flags
 #define GF_REPEATED 0x01u

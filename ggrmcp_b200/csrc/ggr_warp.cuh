@@ -192,6 +192,13 @@ GGR_DEV u32 wp_popc(u32 x) {
   return (u32)__builtin_popcount(x);
 #endif
 }
+GGR_DEV u32 wp_ctz64(u64 x) {  // x != 0
+#if defined(__CUDA_ARCH__)
+  return (u32)(__ffsll((long long)x) - 1);
+#else
+  return (u32)__builtin_ctzll(x);
+#endif
+}
 GGR_DEV u32 wp_clz(u32 x) {
 #if defined(__CUDA_ARCH__)
   return (u32)__clz((int)x);

@@ -509,6 +509,50 @@ inline bool parse_rfc3339(const Bytes& s, int64_t& secs, int32_t& nanos) {
   if (frac_period && frac_digits > 9) return false;
   return true;
 }
+// [upstream internal/strs JSONSnakeCase / JSONCamelCase, protoreflect FullName.IsValid]
+inline std::string fm_snake(const std::string& s) {
+  std::string b;
+  for (unsigned char c : s) {
+    if (c >= 'A' && c <= 'Z') {
+      b.push_back('_');
+      c = (unsigned char)(c + ('a' - 'A'));
+    }
+    b.push_back((char)c);
+  }
+  return b;
+}
+inline std::string fm_camel(const std::string& s) {
+  std::string b;
+  bool was = false;
+  for (unsigned char c : s) {
+    if (c != '_') {
+      if (was && c >= 'a' && c <= 'z') c = (unsigned char)(c - ('a' - 'A'));
+      b.push_back((char)c);
+    }
+    was = c == '_';
+  }
+  return b;
+}
+inline bool fm_full_name_valid(const std::string& s) {
+  auto letter = [](unsigned char c) { return c == '_' || (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z'); };
+  auto ident = [&](size_t i) -> long {
+    if (i >= s.size() || !letter((unsigned char)s[i])) return -1;
+    size_t k = i + 1;
+    while (k < s.size() && (letter((unsigned char)s[k]) || (s[k] >= '0' && s[k] <= '9'))) k++;
+    return (long)(k - i);
+  };
+  long n = ident(0);
+  if (n < 0) return false;
+  size_t i = (size_t)n;
+  while (s.size() > i) {
+    if (s[i] != '.') return false;
+    i++;
+    n = ident(i);
+    if (n < 0) return false;
+    i += (size_t)n;
+  }
+  return true;
+}
 inline std::string format_timestamp(int64_t secs, int64_t nanos) {
   // time.Unix(secs, nanos).UTC() normalizes nanos into [0,1e9)
   secs += nanos / 1000000000;
@@ -758,6 +802,49 @@ struct PJUnmarshal {
     m.known[1].list = {v};
     return true;
   }
+  // [upstream unmarshalFieldMask: TrimSpace, split at ',', every path camelCase -> snake_case]
+  bool fieldmask(DynMsg& m) {
+    Tok t;
+    if (!tk.read(t)) return false;
+    if (t.kind != K_STRING) return unexpected(t);
+    std::string str(t.str.begin(), t.str.end());
+    // strings.TrimSpace: Unicode White_Space (ASCII set + U+0085, U+00A0, U+1680, U+2000-200A, U+2028/9, U+202F, U+205F, U+3000)
+    auto space_at = [&](size_t i, size_t& w) -> bool {
+      unsigned char c = (unsigned char)str[i];
+      if (c == ' ' || (c >= 9 && c <= 13)) { w = 1; return true; }
+      if (c < 0x80) return false;
+      int ww;
+      uint32_t r = utf8_decode((const uint8_t*)str.data() + i, str.size() - i, ww);
+      w = (size_t)ww;
+      return r == 0x85 || r == 0xA0 || r == 0x1680 || (r >= 0x2000 && r <= 0x200A) || r == 0x2028 || r == 0x2029 || r == 0x202F ||
+             r == 0x205F || r == 0x3000;
+    };
+    size_t b = 0, e = str.size(), w;
+    while (b < e && space_at(b, w)) b += w;
+    while (e > b) {  // last rune
+      size_t k = e - 1;
+      while (k > b && ((unsigned char)str[k] & 0xC0) == 0x80) k--;
+      if (!space_at(k, w) || k + w != e) break;
+      e = k;
+    }
+    str = str.substr(b, e - b);
+    if (str.empty()) return true;
+    FieldVal& fv = m.known[1];
+    size_t p = 0;
+    while (true) {
+      size_t c = str.find(',', p);
+      std::string s0 = str.substr(p, c == std::string::npos ? std::string::npos : c - p);
+      std::string sn = fm_snake(s0);
+      if (s0.find('_') != std::string::npos || !fm_full_name_valid(sn))
+        return err.fail(ORC_INVALID_VALUE, "google.protobuf.FieldMask.paths contains invalid path: \"" + s0 + "\"");
+      Val v;
+      v.s = Bytes(sn.begin(), sn.end());
+      fv.list.push_back(v);
+      if (c == std::string::npos) break;
+      p = c + 1;
+    }
+    return true;
+  }
   // [upstream unmarshalEmpty: an object without members (DiscardUnknown is off on this path)]
   bool empty(DynMsg&) {
     Tok t;
@@ -780,6 +867,7 @@ struct PJUnmarshal {
     if (m.d->wkt == WKT_DURATION) return duration(m);
     if (m.d->wkt == WKT_WRAPPER) return wrapper(m);
     if (m.d->wkt == WKT_EMPTY) return empty(m);
+    if (m.d->wkt == WKT_FIELDMASK) return fieldmask(m);
     if (m.d->wkt != WKT_NONE) return err.fail(ORC_UNSUPPORTED, "well-known type " + m.d->full_name + " not supported");
     Tok t;
     if (!tk.read(t)) return false;
@@ -1069,8 +1157,30 @@ struct PJMarshal {
     return singular(*vf, vf->type, v);
   }
 
+  // [upstream marshalFieldMask]
+  bool fieldmask(const DynMsg& m) {
+    std::string joined;
+    auto a = m.known.find(1);
+    if (a != m.known.end()) {
+      bool first = true;
+      for (const Val& v : a->second.list) {
+        std::string s(v.s.begin(), v.s.end());
+        if (!fm_full_name_valid(s)) return err.fail(ORC_INVALID_VALUE, "google.protobuf.FieldMask.paths contains invalid path: \"" + s + "\"");
+        std::string cc = fm_camel(s);
+        if (s != fm_snake(cc)) return err.fail(ORC_INVALID_VALUE, "google.protobuf.FieldMask.paths contains irreversible value \"" + s + "\"");
+        if (!first) joined.push_back(',');
+        first = false;
+        joined += cc;
+      }
+    }
+    prepare(E_SCALAR);
+    append_string((const uint8_t*)joined.data(), joined.size());
+    return true;
+  }
+
   bool message(const DynMsg& m) {
     if (m.d->wkt == WKT_TIMESTAMP) return timestamp(m);
+    if (m.d->wkt == WKT_FIELDMASK) return fieldmask(m);
     if (m.d->wkt == WKT_DURATION) return duration(m);
     if (m.d->wkt == WKT_WRAPPER) return wrapper(m);
     if (m.d->wkt == WKT_EMPTY) {  // [upstream marshalEmpty]

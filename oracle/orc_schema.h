@@ -23,7 +23,7 @@ enum {
   T_FIXED32 = 7, T_BOOL = 8, T_STRING = 9, T_GROUP = 10, T_MESSAGE = 11, T_BYTES = 12,
   T_UINT32 = 13, T_ENUM = 14, T_SFIXED32 = 15, T_SFIXED64 = 16, T_SINT32 = 17, T_SINT64 = 18
 };
-enum { WKT_NONE = 0, WKT_TIMESTAMP = 1, WKT_DURATION = 2, WKT_WRAPPER = 3, WKT_EMPTY = 4, WKT_OTHER = 99 };
+enum { WKT_NONE = 0, WKT_TIMESTAMP = 1, WKT_DURATION = 2, WKT_WRAPPER = 3, WKT_EMPTY = 4, WKT_FIELDMASK = 5, WKT_OTHER = 99 };
 
 struct EnumDesc {
   std::string full_name;
@@ -288,9 +288,9 @@ struct SchemaBuilder {
     if (m.full_name == "google.protobuf.Timestamp") m.wkt = WKT_TIMESTAMP;
     else if (m.full_name == "google.protobuf.Duration") m.wkt = WKT_DURATION;
     else if (m.full_name == "google.protobuf.Empty") m.wkt = WKT_EMPTY;
+    else if (m.full_name == "google.protobuf.FieldMask") m.wkt = WKT_FIELDMASK;
     else if (m.full_name == "google.protobuf.Any" || m.full_name == "google.protobuf.Struct" ||
-             m.full_name == "google.protobuf.Value" || m.full_name == "google.protobuf.ListValue" ||
-             m.full_name == "google.protobuf.FieldMask")
+             m.full_name == "google.protobuf.Value" || m.full_name == "google.protobuf.ListValue")
       m.wkt = WKT_OTHER;
     else {
       // [upstream genid wrappers: BoolValue, Int32Value, Int64Value, UInt32Value, UInt64Value, FloatValue, DoubleValue,

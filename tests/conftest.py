@@ -44,6 +44,10 @@ _ENGINE_PATHS = {
     "lockstep_request_only": {"GGR_COOP": "0", "GGR_LOCKSTEP_MIN_BYTES": "0"},
     # host entry points cut into many small chunks over two slots: exercises the copy/compute pipeline
     "small_chunks": {"GGR_CHUNK_ITEMS": "128", "GGR_SLOTS": "2", "GGR_LOCKSTEP_MIN_BYTES": "0"},
+    # every call leaves its scratch buffers full of well-formed stale records (IR nodes, sizes, list entries): a kernel
+    # that reads a slot nobody wrote in the current call shows up as wrong bytes (round 2: null members in the walker)
+    "poisoned": {"GGR_POISON": "1", "GGR_LOCKSTEP_MIN_BYTES": "0"},
+    "poisoned_size_routing": {"GGR_POISON": "1"},
 }
 
 

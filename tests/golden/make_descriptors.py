@@ -16,7 +16,7 @@ import os
 import sys
 
 from google.protobuf import descriptor_pb2 as dpb
-from google.protobuf import timestamp_pb2, duration_pb2, wrappers_pb2, empty_pb2, struct_pb2
+from google.protobuf import timestamp_pb2, duration_pb2, wrappers_pb2, empty_pb2, struct_pb2, field_mask_pb2
 
 F = dpb.FieldDescriptorProto
 
@@ -314,7 +314,7 @@ def wkt_file():
     P = ".wkt"
     G = ".google.protobuf."
     fd = dpb.FileDescriptorProto(name="wkt.proto", package="wkt", syntax="proto3")
-    for dep in ("timestamp", "duration", "wrappers", "empty", "struct"):
+    for dep in ("timestamp", "duration", "wrappers", "empty", "struct", "field_mask"):
         fd.dependency.append("google/protobuf/%s.proto" % dep)
     m = fd.message_type.add(name="Wkt")
     W = P + ".Wkt"
@@ -341,6 +341,8 @@ def wkt_file():
     add_field(m, "r_i32", 20, G + "Int32Value", repeated=True)
     add_field(m, "name", 21, "string")
     add_field(m, "inner", 22, W)
+    add_field(m, "fm", 23, G + "FieldMask")
+    add_field(m, "r_fm", 24, G + "FieldMask", repeated=True)
     m = fd.message_type.add(name="HasStruct")
     add_field(m, "s", 1, G + "Struct")
     add_field(m, "x", 2, "int32")
@@ -349,6 +351,7 @@ def wkt_file():
     add_method(s, "Wait", G + "Duration", G + "Empty")
     add_method(s, "Rename", G + "StringValue", G + "Int64Value")
     add_method(s, "EchoWkt", W, W)
+    add_method(s, "UpdateMask", G + "FieldMask", G + "FieldMask")
     return fd
 
 
@@ -361,7 +364,7 @@ def build_set():
     # source_code_info is not needed on the hot path; strip to keep the fixture small
     ts.ClearField("source_code_info")
     du.ClearField("source_code_info")
-    for mod in (wrappers_pb2, empty_pb2, struct_pb2):
+    for mod in (wrappers_pb2, empty_pb2, struct_pb2, field_mask_pb2):
         f = fds.file.add()
         mod.DESCRIPTOR.CopyToProto(f)
         f.ClearField("source_code_info")

@@ -46,6 +46,10 @@ def main():
         reply("drand", name, w, ids[i % len(ids)])
     for i, (name, w) in enumerate(cases.merge_cases()):
         reply("merge", name, w, ids[i % len(ids)])
+    for name, js in cases.WKT_ENCODE:
+        args("wkt", name, js)
+    for i, (name, w) in enumerate(cases.wkt_decode_cases()):
+        reply("wktrep", name, w, ids[i % len(ids)])
     names = {}
 
     def mi(n):

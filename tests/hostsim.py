@@ -57,7 +57,7 @@ class Schema:
         return i
 
     def encode(self, name, data, in_off=0, out_off=0):
-        cap = len(data) + 64
+        cap = 2 * len(data) + 64  # a FieldMask can double: "A," -> tag, length, "_a"
         out = C.create_string_buffer(cap)
         n = C.c_uint32()
         rc = lib().hs_encode(self.h, self.msg(name), data, len(data), in_off, out_off, out, cap, C.byref(n))

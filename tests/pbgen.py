@@ -142,6 +142,11 @@ def fill(rng, msg, depth=0, p_field=0.35, floats=True):
         msg.seconds = sign * rng.choice([0, 0, 1, 3600, 315576000000, rng.randint(0, 315576000000)])
         msg.nanos = sign * rng.choice([0, 0, 500000000, 123000, 999999999, 1, rng.randint(0, 999999999)])
         return
+    if d.full_name == "google.protobuf.FieldMask":
+        seg = lambda: rng.choice(["a", "foo", "foo_bar", "x1", "user_id", "display_name", "b2_c"])
+        for _ in range(rng.randint(0, 4)):
+            msg.paths.append(".".join(seg() for _ in range(rng.randint(1, 3))))
+        return
     for fd in d.fields:
         if rng.random() > p_field:
             continue
