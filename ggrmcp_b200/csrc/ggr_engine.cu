@@ -607,11 +607,12 @@ static int run_dev_kernels(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool
       if (prof) prof_mark(e, st, &m0);
       // router: small (and oversized) items straight to the per-thread parser
       k_route<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, in_off, e->min_json, 65000u - 16u, big, counters, pend2, counters + 8, nullptr);
-      size_t t1 = 0;
+      size_t t1 = 0, t_tok = 0;
       if (e->use_walk) {
         // token index, then the token-parallel walker (ggr_walk.cuh); what it leaves: the fused large-table kernel
         ggr_launch_encode_tok2(st, n, in, in_off, (u8*)sc.ir.p, big, counters, e->sm_count);
         if (prof) prof_mark(e, st, &t1);
+        t_tok = t1;
         ggr_launch_encode_place(st, n, in_off, (u8*)sc.ir.p, big, counters, e->sm_count);
         size_t t2 = 0, t3 = 0;
         if (prof) prof_mark(e, st, &t2);
@@ -629,6 +630,7 @@ static int run_dev_kernels(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool
       } else {
         ggr_launch_encode_coop_tok(st, n, in, in_off, (u8*)sc.ir.p, big, counters, e->sm_count);
         if (prof) prof_mark(e, st, &t1);
+        t_tok = t1;
         ggr_launch_encode_coop_parse(st, 0, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
                                      (u32*)sc.aux.p, status, (u32*)sc.ioff.p, (u32*)sc.nn.p, big, counters, pend1, counters + 4, e->sm_count, nullptr, nullptr, -1);
       }
@@ -641,7 +643,7 @@ static int run_dev_kernels(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool
       if (frame) ggr_launch_frame_sizes(st, n, (u32*)sc.size.p, status);
       ggr_launch_block_sums(st, (unsigned)nb, n, (const u32*)sc.size.p, (u64*)sc.sums.p);
       if (prof) {
-        e->spans.push_back({11, m0, t1});  // router + token index
+        e->spans.push_back({11, m0, t_tok});  // router + token index
         e->spans.push_back({8, t1, c0});    // walker, tier 2
         e->spans.push_back({0, c0, c1});
         prof_mark(e, st, &m1);
