@@ -143,74 +143,7 @@ GGR_DEV bool coop_wire_zero(const u8* b, u32 pos, u32 lim, u32 wt, bool* ok) {
   return any == 0;
 }
 
-// Eight bytes of the item at `pos` (two aligned 8-byte loads, the second one only inside the item's last 16-byte
-// chunk): tag, length prefix and the first value bytes of a field decode from registers - one round trip to the
-// memory system per field instead of one per varint (the tables in shared memory leave the L1 too small to hold
-// the items, so every dependent byte load is an L2 access).
-GGR_DEV u64 coop_window(const u8* in, u32 pos, u32 end_al) {
-  const u32 a = pos & ~7u;
-#if defined(__CUDA_ARCH__)
-  const u64 lo = __ldg(reinterpret_cast<const unsigned long long*>(in + a));
-  const u64 hi = a + 8u < end_al ? __ldg(reinterpret_cast<const unsigned long long*>(in + a + 8u)) : 0ull;
-#else
-  u64 lo, hi = 0;
-  memcpy(&lo, in + a, 8);
-  if (a + 8u < end_al) memcpy(&hi, in + a + 8u, 8);
-#endif
-  const u32 sh = (pos & 7u) * 8u;
-  return sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
-}
-// A field header out of the window W at pos: tag (one or two bytes) and, by wire type, the extent of the value.
-// Returns false when the bytes do not fit the window (long tags, lengths of three bytes and more, varints that run
-// past it): the caller then decodes byte by byte.  On success: *tag, *body (payload start of a length-delimited
-// value, else the value start), *vend, *zero (varint / fixed32 value is 0; length is 0) - bounds are the caller's.
-GGR_DEV bool coop_header(u64 W, u32 pos, u32* tag, u32* tag_len, u32* body, u32* vend, bool* zero) {
-  const u32 b0 = (u32)W & 0xFFu;
-  u32 t = b0, tl = 1;
-  if (b0 >= 0x80u) {
-    const u32 b1 = (u32)(W >> 8) & 0xFFu;
-    if (b1 >= 0x80u) return false;
-    t = (b0 & 0x7Fu) | (b1 << 7);
-    tl = 2;
-  }
-  *tag = t;
-  *tag_len = tl;
-  const u64 V = W >> (8u * tl);  // 6 or 7 value bytes
-  const u32 wt = t & 7u;
-  const u32 vpos = pos + tl;
-  if (wt == 2u) {
-    const u32 l0 = (u32)V & 0xFFu;
-    u32 len = l0, ll = 1;
-    if (l0 >= 0x80u) {
-      const u32 l1 = (u32)(V >> 8) & 0xFFu;
-      if (l1 >= 0x80u) return false;
-      len = (l0 & 0x7Fu) | (l1 << 7);
-      ll = 2;
-    }
-    *body = vpos + ll;
-    *vend = vpos + ll + len;
-    *zero = len == 0;
-    return true;
-  }
-  *body = vpos;
-  if (wt == 0u) {
-    // first byte without the continuation bit among the bytes the window holds
-    const u64 keep = tl == 1 ? 0x00FFFFFFFFFFFFFFull : 0x0000FFFFFFFFFFFFull;
-    const u64 stop = ~V & 0x8080808080808080ull & keep;
-    if (!stop) return false;
-    const u32 k = (u32)(wp_ctz64(stop) >> 3);  // index of the last byte of the varint
-    *vend = vpos + k + 1u;
-    const u64 bits = V & (0x7F7F7F7F7F7F7F7Full >> (8u * (7u - k)));
-    *zero = bits == 0;
-    return true;
-  }
-  if (wt == 5u) {
-    *vend = vpos + 4u;
-    *zero = (u32)V == 0u;
-    return true;
-  }
-  return false;  // fixed64 (the value does not fit), groups, invalid wire types
-}
+// coop_window / coop_header (a field header out of one 8-byte window): ggr_decode.cuh, shared with the slow walk
 
 // R1, one lane: scan the top-level fields of message entry `me` and append its children.
 template <class SH>
@@ -651,6 +584,9 @@ GGR_DEV void coop_offsets_message(SH& S, const DecCtx& cx, u32 me) {
 // groups would spend its time on the unaligned edges of every entry; plain byte stores into
 // shared memory have no edges.
 #define GGR_COOP_STAGE 8192u /* items with more text than this: per-thread kernels */
+#ifndef GGR_COOP_STAGE_BUF
+#define GGR_COOP_STAGE_BUF 8192u /* the writer's staging buffer; larger texts are written in place */
+#endif
 struct
 #if defined(__CUDACC__)
     __align__(16)
@@ -658,7 +594,7 @@ struct
     alignas(16)
 #endif
         CoopStage {
-  u8 buf[GGR_COOP_STAGE + 48];  // [pad, pad + size): pad = destination address & 15
+  u8 buf[GGR_COOP_STAGE_BUF + 48];  // [pad, pad + size): pad = destination address & 15
   u32 lsrc[GGR_COOP_LONG_MAX], ldst[GGR_COOP_LONG_MAX], llen[GGR_COOP_LONG_MAX];
   u32 n_long, bad;
 };
@@ -865,7 +801,7 @@ GGR_DEV bool coop_size_item(SH& S, const DecCtx& cx, u32 root_msg, u32 start, u3
 // in aligned chunks; larger ones (a few entries around a huge leaf) are written in place.
 GGR_DEV int coop_write_item(CoopStage& E, const DecCtx& cx, const U4* tab, u32 n, u8* dst, u32 size) {
   const u32 lane = wp_lane();
-  const bool staged = size <= GGR_COOP_STAGE;
+  const bool staged = size <= GGR_COOP_STAGE_BUF;
   const u32 pad = wp_align_pad(dst);
   if (n) wp_prefetch(cx.in, tab[0].y);  // entry 0 is the root: vend = end of the item
   wp_copy_wait();  // persistent warps: the previous item's bulk copy has read the staging buffer

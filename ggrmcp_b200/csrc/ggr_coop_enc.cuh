@@ -1208,6 +1208,9 @@ GGR_DEV bool ce_parse_item(SH& S, const CeLut& lut, const Tables& T, u32 root_ms
 #define CE_LONG_STR 96u
 #define CE_LONG_MAX 32u
 #define CE_STAGE 8192u /* items with more wire bytes than this: per-thread emitter */
+#ifndef CE_STAGE_BUF
+#define CE_STAGE_BUF 8192u /* the emitter's staging buffer; larger items (up to CE_STAGE and beyond) are written in place */
+#endif
 struct
 #if defined(__CUDACC__)
     __align__(16)
@@ -1215,7 +1218,7 @@ struct
     alignas(16)
 #endif
         CoopEmit {
-  u8 buf[CE_STAGE + 48];  // [pad, pad + size): pad = destination address & 15
+  u8 buf[CE_STAGE_BUF + 48];  // [pad, pad + size): pad = destination address & 15
   u32 src[CE_LONG_MAX], dst[CE_LONG_MAX], len[CE_LONG_MAX];
   u32 n;
 };
@@ -1353,7 +1356,7 @@ GGR_DEV void ce_unescape_coop(const u8* in, u32 src, u8* d, u32 dec_len) {
 GGR_DEV void ce_emit_item(CoopEmit& E, const u8* in, u32 end, const u8* ir, const u32* ioff, u32 n_nodes, u8* dst, u32 size) {
   const u32 lane = wp_lane();
   const u32 pad = wp_align_pad(dst);
-  const bool staged = size <= CE_STAGE;
+  const bool staged = size <= CE_STAGE_BUF;
   wp_prefetch(in, end < 16384u ? end : 16384u);
   wp_copy_wait();  // persistent warps: the previous item's bulk copy has read the staging buffer
   if (lane == 0) E.n = 0;

@@ -612,6 +612,9 @@ struct EncResult {
   u32 n_nodes;  // lock-step parser: IR nodes written (with offsets, for the lock-step emitter); 0 otherwise
   // envelope mode (request bodies): method index, position and length of the id token in the body
   u32 method, id_pos, id_len;
+  // items that fail in the per-thread parser: byte offset (from the item's start) of the key token for unknown / duplicate
+  // fields and oneof conflicts found while the key is at hand, else of the reader when the error was raised
+  u32 err_pos;
 };
 
 // Rare value forms of encode_parse as calls (inlined they add 35 thousand instructions to the kernel): the text of a
@@ -706,6 +709,7 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
   res->size = 0;
   res->first = GGR_NIL;
   res->n_nodes = 0;
+  res->err_pos = 0;
   bool finished = !active;
   int result = GST_OK;
   // reflection.go:354: "" and "{}" skip protojson entirely
@@ -749,6 +753,7 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
   while (ggr_any(mask, !finished)) {
    if (!finished) {
     int rr = GGR_STEP_CONT;
+    u32 ekey = 0xFFFFFFFFu;  // position of the member key read in this step (error reporting)
   for (int once = 0;; once++) {
     if (once) break;  // `continue` in the body below ends the step
     skip_ws(r);
@@ -789,6 +794,7 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
       }
       if (c != '"') GGR_RET(GST_SYNTAX);
       u32 key_pos = r.pos;
+      ekey = key_pos;
       StrInfo ks;
       KeyInfo ki;
       ks.dec_len = 0; ks.flags = 0;
@@ -1142,6 +1148,8 @@ GGR_DEV int encode_parse(const Tables& T, u32 root_msg, const u8* in, u32 start,
     if (rr != GGR_STEP_CONT) {
       finished = true;
       result = rr;
+      if (rr != GST_OK)
+        res->err_pos = (((rr == GST_UNKNOWN_FIELD || rr == GST_DUPLICATE || rr == GST_ONEOF) && ekey != 0xFFFFFFFFu) ? ekey : r.pos) - start;
     }
    }
   }

@@ -86,6 +86,49 @@ __global__ void __launch_bounds__(256) k_route(long long n, const u64* __restric
   if (is_small && small) small[bs + __popc(ms & lt)] = (u32)i;
 }
 
+// Large items on the per-thread kernels: 32 unrelated state machines in one warp run their steps one after the other
+// (measured on the mixed replay: 1 320 replies of 16-39 KB take 502 ms together, the largest of them 83 ms alone), so an
+// item of at least `big_bytes` gets a warp of its own - slot 32 k of `spread` holds the item, the 31 entries behind it
+// none (the buffer is filled with 0xFF bytes before) - and the list-mode launches run over that list.  The list is
+// ordered by size class, largest first (five classes, each twice the one below): the warps of a launch are scheduled in
+// list order, and a wave that starts with the long items ends when the short ones of the last wave would have.
+// cnt: [0] threads of the list-mode launches, [1] small items, [2..6] items per class, [7..11] placed per class.
+// Request side (list != nullptr): splits the per-thread list into `small` and `spread`.
+// Reply side (list == nullptr): every item the warp-cooperative kernels left pending (mode) that is large.
+// phase 0 counts the classes, phase 1 places the items; what does not fit `cap_items` stays with the small / whole-batch pass.
+__global__ void __launch_bounds__(256) k_spread(int phase, long long n, const u64* __restrict__ in_off, u32 big_bytes, const u32* __restrict__ list,
+                                                const u32* __restrict__ list_n, const u32* __restrict__ mode, u32* __restrict__ small,
+                                                u32* __restrict__ spread, u32* __restrict__ cnt, u32 cap_items) {
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (phase == 1 && t == 0) {
+    const u32 total = cnt[2] + cnt[3] + cnt[4] + cnt[5] + cnt[6];
+    cnt[0] = (total < cap_items ? total : cap_items) * 32u;
+  }
+  long long i = n;
+  if (list) {
+    if (t < (long long)*list_n) i = (long long)list[t];
+  } else if (t < n && mode[t] == 0xFFu) {
+    i = t;
+  }
+  if (i >= n) return;
+  const u64 len = in_off[i + 1] - in_off[i];
+  if (len < big_bytes) {
+    if (phase == 1 && small) small[atomicAdd(cnt + 1, 1u)] = (u32)i;
+    return;
+  }
+  u32 cls = 0;
+  for (u64 x = len / big_bytes; x > 1 && cls < 4u; x >>= 1) cls++;
+  if (phase == 0) {
+    atomicAdd(cnt + 2 + cls, 1u);
+    return;
+  }
+  u32 base = 0;
+  for (u32 c = cls + 1; c < 5u; c++) base += cnt[2 + c];
+  const u32 slot = base + atomicAdd(cnt + 7 + cls, 1u);
+  if (slot < cap_items) spread[(size_t)slot * 32] = (u32)i;
+  else if (small) small[atomicAdd(cnt + 1, 1u)] = (u32)i;
+}
+
 // status / size of the items of a list (request bodies the lock-step parser cannot take)
 // the chunk's output size straight into mapped host memory: the host learns it from the stream's
 // event alone, without a copy that would queue behind other chunks' payloads on the copy engine
@@ -131,8 +174,10 @@ struct Scratch {
   DevBuf ir, size, aux, sums, pend, ioff, nn;
   DevBuf wtext, woff, wsize;  // result wrapping: protojson texts, their offsets, body sizes
   DevBuf sortpool;            // reply side: (key, position) records of maps whose entries arrive unsorted
+  DevBuf spread;              // per-thread kernels: the list of large items, one per warp (k_spread)
 };
 #define GGR_MAX_SLOTS 8
+#define GGR_SPREAD_CAP 16384u /* large items that get a warp each per call and direction; the rest stay 32 to a warp */
 struct Slot {
   cudaStream_t st = nullptr;
   cudaEvent_t ready = nullptr;
@@ -169,6 +214,7 @@ struct ggr_engine {
   // items smaller than this go straight to the per-thread kernels, which are cheaper for them
   // (GGR_LOCKSTEP_MIN_BYTES overrides both; 0 sends everything through the lock-step kernels)
   uint32_t min_json = 1024, min_wire = 640;
+  uint32_t spread_min = 4096;  // per-thread kernels: items of at least this many bytes take a warp each (0: off)
   // host-buffer entry points: the batch is cut into chunks that move through `n_slots` slots
   // (stream + staging + scratch each), so that H2D, kernels and D2H of different chunks overlap
   Slot slots[2][GGR_MAX_SLOTS];  // per direction
@@ -365,6 +411,7 @@ int ggr_engine_create(const ggr_config* cfg, ggr_engine** out) {
   if (const char* pz = getenv("GGR_POISON")) e->poison = pz[0] == '1';
   if (const char* nc = getenv("GGR_TRACE")) e->trace = nc[0] != '0';
   if (const char* nc = getenv("GGR_LOCKSTEP_MIN_BYTES")) e->min_json = e->min_wire = (uint32_t)strtoul(nc, nullptr, 10);
+  if (const char* nc = getenv("GGR_SPREAD_MIN_BYTES")) e->spread_min = (uint32_t)strtoul(nc, nullptr, 10);
   if (const char* nc = getenv("GGR_SLOTS")) {
     int v = atoi(nc);
     if (v >= 1 && v <= GGR_MAX_SLOTS) e->n_slots = v;
@@ -417,7 +464,7 @@ void ggr_engine_destroy(ggr_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   auto free_scratch = [](Scratch& sc) {
-    DevBuf* bufs[] = {&sc.ir, &sc.size, &sc.aux, &sc.sums, &sc.pend, &sc.ioff, &sc.nn, &sc.wtext, &sc.woff, &sc.wsize, &sc.sortpool};
+    DevBuf* bufs[] = {&sc.ir, &sc.size, &sc.aux, &sc.sums, &sc.pend, &sc.ioff, &sc.nn, &sc.wtext, &sc.woff, &sc.wsize, &sc.sortpool, &sc.spread};
     for (DevBuf* b : bufs)
       if (b->p) cudaFree(b->p);
   };
@@ -637,8 +684,27 @@ static int run_dev_kernels(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool
       ggr_launch_encode_coop_parse(st, 1, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
                                    (u32*)sc.aux.p, status, (u32*)sc.ioff.p, (u32*)sc.nn.p, pend1, counters + 4, pend2, counters + 8, e->sm_count, nullptr, nullptr, -1);
       if (prof) prof_mark(e, st, &c0);
-      ggr_launch_encode_parse(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
-                              (u32*)sc.aux.p, status, (u64*)sc.sums.p, pend2, counters + 8);
+      if (e->spread_min) {
+        // the per-thread list, split: small items 32 to a warp, large ones a warp each (k_spread)
+        size_t max_big = (size_t)(in_bytes / e->spread_min) + 1;  // items of at least spread_min bytes
+        if (max_big > GGR_SPREAD_CAP) max_big = GGR_SPREAD_CAP;
+        if (!ensure(e, sc.spread, (max_big * 32 + (size_t)n) * 4 + 64)) return GGR_ERR_CUDA;
+        u32* sp_cnt = (u32*)sc.spread.p;
+        u32* sp_list = sp_cnt + 16;
+        u32* sp_small = sp_list + max_big * 32;
+        if (!cuda_ok(e, cudaMemsetAsync(sp_cnt, 0, 64, st), "memset") || !cuda_ok(e, cudaMemsetAsync(sp_list, 0xFF, max_big * 32 * 4, st), "memset"))
+          return GGR_ERR_CUDA;
+        for (int phase = 0; phase < 2; phase++)
+          k_spread<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(phase, n, in_off, e->spread_min, pend2, counters + 8, nullptr, sp_small, sp_list, sp_cnt, (u32)max_big);
+        ggr_launch_encode_parse(st, (unsigned)((max_big * 32 + GGR_BLOCK - 1) / GGR_BLOCK), s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p,
+                                (u32*)sc.size.p, (u32*)sc.aux.p, status, (u64*)sc.sums.p, sp_list, sp_cnt);
+        ggr_launch_encode_parse(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
+                                (u32*)sc.aux.p, status, (u64*)sc.sums.p, sp_small, sp_cnt + 1);
+        e->launches += 3;
+      } else {
+        ggr_launch_encode_parse(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
+                                (u32*)sc.aux.p, status, (u64*)sc.sums.p, pend2, counters + 8);
+      }
       if (prof) prof_mark(e, st, &c1);
       if (frame) ggr_launch_frame_sizes(st, n, (u32*)sc.size.p, status);
       ggr_launch_block_sums(st, (unsigned)nb, n, (const u32*)sc.size.p, (u64*)sc.sums.p);
@@ -705,6 +771,22 @@ static int run_dev_kernels(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool
         m0 = c0;
       }
     }
+    // large items the warp-cooperative kernels left: a warp each (k_spread), sized before and written after the pass over the batch
+    const bool spread = coop && e->spread_min != 0;
+    size_t max_big = spread ? (size_t)(in_bytes / e->spread_min) + 1 : 0;
+    if (max_big > GGR_SPREAD_CAP) max_big = GGR_SPREAD_CAP;
+    u32* sp_cnt = nullptr;
+    if (spread) {
+      if (!ensure(e, sc.spread, max_big * 32 * 4 + 64)) return GGR_ERR_CUDA;
+      sp_cnt = (u32*)sc.spread.p;
+      if (!cuda_ok(e, cudaMemsetAsync(sp_cnt, 0, 64, st), "memset") || !cuda_ok(e, cudaMemsetAsync(sp_cnt + 16, 0xFF, max_big * 32 * 4, st), "memset"))
+        return GGR_ERR_CUDA;
+      for (int phase = 0; phase < 2; phase++)
+        k_spread<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(phase, n, in_off, e->spread_min, nullptr, nullptr, (const u32*)sc.aux.p, nullptr, sp_cnt + 16, sp_cnt, (u32)max_big);
+      ggr_launch_decode_size(st, (unsigned)((max_big * 32 + GGR_BLOCK - 1) / GGR_BLOCK), s->d_blob, n, n_msgs, msg_id, in, in_off, flags,
+                             (u32*)sc.size.p, (u32*)sc.aux.p, status, (u64*)sc.sums.p, 1, sc.sortpool.p, sort_cap, sp_cnt + 16, sp_cnt);
+      e->launches += 4;
+    }
     ggr_launch_decode_size(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, flags, (u32*)sc.size.p,
                            (u32*)sc.aux.p, status, (u64*)sc.sums.p, coop ? 1 : 0, sc.sortpool.p, sort_cap);
     if (prof) prof_mark(e, st, &m1);
@@ -712,6 +794,10 @@ static int run_dev_kernels(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool
     if (prof) prof_mark(e, st, &m2);
     ggr_launch_decode_write(st, (unsigned)nb, s->d_blob, n, msg_id, in, in_off, flags, (const u32*)sc.size.p,
                             (const u32*)sc.aux.p, status, (const u64*)sc.sums.p, out, out_cap, out_off, sc.sortpool.p, sort_cap);
+    if (spread)
+      ggr_launch_decode_write(st, (unsigned)((max_big * 32 + GGR_BLOCK - 1) / GGR_BLOCK), s->d_blob, n, msg_id, in, in_off, flags,
+                              (const u32*)sc.size.p, (const u32*)sc.aux.p, status, (const u64*)sc.sums.p, out, out_cap, out_off, sc.sortpool.p,
+                              sort_cap, sp_cnt + 16, sp_cnt);
     if (coop) {
       if (prof) prof_mark(e, st, &c1);
       ggr_launch_decode_coop_write(st, n, s->d_blob, in, in_off, flags, (const u32*)sc.size.p, (const u32*)sc.aux.p, status, sc.ir.p,
@@ -736,6 +822,79 @@ static int run_dev_kernels(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool
   }
   e->launches += 3;
   return cuda_ok(e, cudaGetLastError(), "kernel launch") ? GGR_SUCCESS : GGR_ERR_CUDA;
+}
+
+// One failing request item through the per-thread parser again (the kernel that owns the request-side semantics),
+// this time asking where it failed; the text is composed on the host from the status, the position and the input bytes.
+int ggr_encode_diagnose(ggr_engine* e, const ggr_schema* s, int32_t msg_id, const uint8_t* json, uint64_t json_len, uint32_t flags,
+                        int32_t* status, uint32_t* err_pos, uint32_t* err_len, char* text, size_t text_cap) {
+  (void)flags;
+  if (!e || !s || (!json && json_len) || !status) return GGR_ERR_INVALID_ARGUMENT;
+  if (json_len > 0x1FFFF0ull) return GGR_ERR_TOO_LARGE;
+  std::lock_guard<std::mutex> g(e->mu);
+  DeviceGuard dg(e->device);
+  const size_t in_cap = ((size_t)json_len + 15) / 16 * 16 + 64;
+  const size_t ir_bytes = (size_t)json_len * 8 + 128 + 256;
+  // one allocation: input | offsets | message id | size, first, status, error position | block sums | IR
+  const size_t o_off = in_cap, o_msg = o_off + 16, o_res = o_msg + 16, o_sums = o_res + 16, o_ir = o_sums + 16;
+  uint8_t* d = nullptr;
+  if (!cuda_ok(e, cudaMalloc((void**)&d, o_ir + ir_bytes), "cudaMalloc(diagnose)")) return GGR_ERR_CUDA;
+  std::vector<uint8_t> h(o_ir, 0);
+  if (json_len) memcpy(h.data(), json, (size_t)json_len);
+  const uint64_t offs[2] = {0, json_len};
+  memcpy(h.data() + o_off, offs, 16);
+  memcpy(h.data() + o_msg, &msg_id, 4);
+  cudaStream_t st = e->stream;
+  int rc = GGR_SUCCESS;
+  uint32_t res[4] = {0, 0, 0, 0};
+  if (!cuda_ok(e, cudaMemcpyAsync(d, h.data(), o_ir, cudaMemcpyHostToDevice, st), "H2D(diagnose)")) rc = GGR_ERR_CUDA;
+  if (rc == GGR_SUCCESS) {
+    ggr_launch_encode_parse(st, 1, s->d_blob, 1, (u32)s->cs.msg_names.size(), (const int32_t*)(d + o_msg), d, (const uint64_t*)(d + o_off), d + o_ir,
+                            (u32*)(d + o_res), (u32*)(d + o_res + 4), (int32_t*)(d + o_res + 8), (uint64_t*)(d + o_sums), nullptr, nullptr,
+                            (u32*)(d + o_res + 12));
+    e->launches += 1;
+    if (!cuda_ok(e, cudaGetLastError(), "kernel launch") ||
+        !cuda_ok(e, cudaMemcpyAsync(res, d + o_res, 16, cudaMemcpyDeviceToHost, st), "D2H(diagnose)") ||
+        !cuda_ok(e, cudaStreamSynchronize(st), "sync(diagnose)"))
+      rc = GGR_ERR_CUDA;
+  }
+  cudaFree(d);
+  if (rc != GGR_SUCCESS) return rc;
+  const int32_t stt = (int32_t)res[2];
+  *status = stt;
+  uint32_t pos = stt != GGR_ST_OK ? res[3] : 0, len = 0;
+  if (pos > json_len) pos = (uint32_t)json_len;
+  // a key token at the position: its raw text (quotes included) is what protojson prints
+  if (stt != GGR_ST_OK && pos < json_len && json[pos] == '"') {
+    uint64_t q = pos + 1;
+    while (q < json_len && json[q] != '"') q += json[q] == '\\' ? 2 : 1;
+    if (q < json_len) len = (uint32_t)(q + 1 - pos);
+  }
+  if (err_pos) *err_pos = pos;
+  if (err_len) *err_len = len;
+  if (text && text_cap) {
+    std::string t;
+    if (stt == GGR_ST_OK) {
+      t = "";
+    } else {
+      // position as protojson reports it: line and column (in bytes), both from 1
+      uint32_t line = 1, col = 1;
+      for (uint32_t k = 0; k < pos; k++) {
+        if (json[k] == '\n') { line++; col = 1; }
+        else col++;
+      }
+      t = "proto: (line " + std::to_string(line) + ":" + std::to_string(col) + "): ";
+      const std::string tok = len ? std::string((const char*)json + pos, len) : std::string();
+      if (stt == GGR_ST_UNKNOWN_FIELD && len) t += "unknown field " + tok;
+      else if (stt == GGR_ST_DUPLICATE && len) t += "duplicate field " + tok;
+      else if (stt == GGR_ST_ONEOF && len) t += "error parsing " + tok + ", oneof is already set";
+      else t += ggr_status_string(stt);
+    }
+    const size_t k = t.size() < text_cap - 1 ? t.size() : text_cap - 1;
+    memcpy(text, t.data(), k);
+    text[k] = 0;
+  }
+  return GGR_SUCCESS;
 }
 
 int ggr_encode_batch_dev(ggr_engine* e, const ggr_schema* s, int64_t n, const int32_t* msg_id, const uint8_t* in,

@@ -6,7 +6,8 @@
 
 void ggr_launch_encode_parse(cudaStream_t st, unsigned nb, const uint8_t* blob, long long n, uint32_t n_msgs, const int32_t* msg_id,
                              const uint8_t* in, const uint64_t* in_off, uint8_t* ir, uint32_t* size, uint32_t* first,
-                             int32_t* status, uint64_t* block_sums, const uint32_t* list, const uint32_t* list_n);
+                             int32_t* status, uint64_t* block_sums, const uint32_t* list, const uint32_t* list_n,
+                             uint32_t* err_pos = nullptr);  // err_pos (optional): per item, where a failing item failed
 void ggr_launch_block_sums(cudaStream_t st, unsigned nb, long long n, const uint32_t* size, uint64_t* block_sums);
 // tier 0: the listed items, their token index left in the IR region by ggr_launch_encode_coop_tok; tier 1: the
 // items of `list`, everything in one kernel; persistent warps sized by sm_count
@@ -38,11 +39,14 @@ void ggr_launch_encode_emit(cudaStream_t st, unsigned nb, long long n, const uin
 void ggr_launch_frame_sizes(cudaStream_t st, long long n, uint32_t* size, const int32_t* status);  // GGR_F_GRPC_FRAME: + 5 bytes per item
 void ggr_launch_decode_size(cudaStream_t st, unsigned nb, const uint8_t* blob, long long n, uint32_t n_msgs, const int32_t* msg_id,
                             const uint8_t* in, const uint64_t* in_off, uint32_t flags, uint32_t* size, uint32_t* mode,
-                            int32_t* status, uint64_t* block_sums, int after_coop, void* sort_pool, uint32_t sort_cap);
+                            int32_t* status, uint64_t* block_sums, int after_coop, void* sort_pool, uint32_t sort_cap,
+                            const uint32_t* list = nullptr, const uint32_t* list_n = nullptr);
 void ggr_launch_decode_write(cudaStream_t st, unsigned nb, const uint8_t* blob, long long n, const int32_t* msg_id,
                              const uint8_t* in, const uint64_t* in_off, uint32_t flags, const uint32_t* size,
                              const uint32_t* mode, int32_t* status, const uint64_t* block_prefix, uint8_t* out,
-                             uint64_t out_cap, uint64_t* out_off, void* sort_pool, uint32_t sort_cap);
+                             uint64_t out_cap, uint64_t* out_off, void* sort_pool, uint32_t sort_cap, const uint32_t* list = nullptr,
+                             const uint32_t* list_n = nullptr);
+// list != nullptr (both): thread t takes item list[t] (entries >= n hold no item) - the spread list of large items
 // sort_pool: 16 bytes of bump counter (zeroed per batch) followed by sort_cap 16-byte records: scratch of the unsorted-map path
 void ggr_launch_decode_coop_size(cudaStream_t st, long long n, const uint8_t* blob, uint32_t n_msgs, const int32_t* msg_id,
                                  const uint8_t* in, const uint64_t* in_off, uint32_t flags, uint32_t* size, uint32_t* mode,

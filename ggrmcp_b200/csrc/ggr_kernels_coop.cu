@@ -69,7 +69,10 @@ k_decode_coop_size(const u8* __restrict__ blob, long long n, u32 n_msgs, const i
 }
 
 #define COOP_WRITE_WARPS 4
-__global__ void __launch_bounds__(COOP_WRITE_WARPS * 32)
+#ifndef COOP_WRITE_MINB
+#define COOP_WRITE_MINB 1
+#endif
+__global__ void __launch_bounds__(COOP_WRITE_WARPS * 32, COOP_WRITE_MINB)
 k_decode_coop_write(const u8* __restrict__ blob, long long n, const u8* __restrict__ in, const u64* __restrict__ in_off,
                     u32 flags, const u32* __restrict__ size, const u32* __restrict__ mode, i32* __restrict__ status,
                     const U4* __restrict__ tab, const u32* __restrict__ nent, u8* __restrict__ out,
@@ -143,7 +146,10 @@ void ggr_launch_decode_coop_write(cudaStream_t st, long long n, const uint8_t* b
                                   uint32_t flags, const uint32_t* size, const uint32_t* mode, int32_t* status, const void* tab,
                                   const uint32_t* nent, uint8_t* out, const uint64_t* out_off, int sm_count,
                                   const uint32_t* list, const uint32_t* list_n) {
-  long long want = (n + COOP_WRITE_WARPS - 1) / COOP_WRITE_WARPS, cap = (long long)sm_count * 6;
+  static int per_sm = 0;
+  if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_coop_write, COOP_WRITE_WARPS * 32, sizeof(CoopStage) * COOP_WRITE_WARPS) != cudaSuccess || per_sm < 1))
+    per_sm = 6;
+  long long want = (n + COOP_WRITE_WARPS - 1) / COOP_WRITE_WARPS, cap = (long long)sm_count * per_sm;
   unsigned nb = (unsigned)(want < cap ? want : cap);
   k_decode_coop_write<<<nb, COOP_WRITE_WARPS * 32, sizeof(CoopStage) * COOP_WRITE_WARPS, st>>>(
       blob, n, in, (const u64*)in_off, flags, size, mode, status, (const U4*)tab, nent, out, (const u64*)out_off, list, list_n);

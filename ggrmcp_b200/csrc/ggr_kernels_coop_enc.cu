@@ -196,7 +196,10 @@ void ggr_launch_encode_coop_emit(cudaStream_t st, long long n, const uint8_t* in
                                  const uint32_t* ioff, const uint32_t* nnodes, const uint32_t* size, const int32_t* status,
                                  uint8_t* out, const uint64_t* out_off, int sm_count, const uint32_t* list,
                                  const uint32_t* list_n, uint32_t frame) {
-  long long want = (n + CE_WARPS - 1) / CE_WARPS, cap = (long long)sm_count * 6;
+  static int per_sm = 0;  // resident blocks per SM: what the staging buffers in shared memory (and the registers) allow
+  if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_coop_emit, CE_WARPS * 32, sizeof(CoopEmit) * CE_WARPS) != cudaSuccess || per_sm < 1))
+    per_sm = 6;
+  long long want = (n + CE_WARPS - 1) / CE_WARPS, cap = (long long)sm_count * per_sm;
   unsigned nb = (unsigned)(want < cap ? want : cap);
   k_encode_coop_emit<<<nb, CE_WARPS * 32, sizeof(CoopEmit) * CE_WARPS, st>>>(n, in, (const u64*)in_off, ir, ioff, nnodes, size, status, out,
                                                                              (const u64*)out_off, list, list_n, frame);

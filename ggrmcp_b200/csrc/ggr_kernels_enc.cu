@@ -10,7 +10,7 @@ __global__ void __launch_bounds__(GGR_BLOCK, GGR_PARSE_MINB)
 k_encode_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const i32* __restrict__ msg_id,
                const u8* __restrict__ in, const u64* __restrict__ in_off, u8* __restrict__ ir,
                u32* __restrict__ size, u32* __restrict__ first, i32* __restrict__ status,
-               u64* __restrict__ block_sums, const u32* __restrict__ list, const u32* __restrict__ list_n) {
+               u64* __restrict__ block_sums, const u32* __restrict__ list, const u32* __restrict__ list_n, u32* __restrict__ err_pos) {
   // list mode (after the lock-step parser): thread t takes item list[t]; block sums come later
   long long i = (long long)blockIdx.x * GGR_BLOCK + threadIdx.x;
   if (list) {
@@ -52,6 +52,7 @@ k_encode_parse(const u8* __restrict__ blob, long long n, u32 n_msgs, const i32* 
     size[i] = sz;
     first[i] = res.first;
     status[i] = st;
+    if (err_pos) err_pos[i] = st != GST_OK ? res.err_pos : 0xFFFFFFFFu;  // ggr_encode_diagnose
   }
   if (list) return;
   u32 tot;
@@ -125,9 +126,9 @@ k_encode_emit(long long n, const u8* __restrict__ in, const u64* __restrict__ in
 
 void ggr_launch_encode_parse(cudaStream_t st, unsigned nb, const uint8_t* blob, long long n, uint32_t n_msgs, const int32_t* msg_id,
                              const uint8_t* in, const uint64_t* in_off, uint8_t* ir, uint32_t* size, uint32_t* first,
-                             int32_t* status, uint64_t* block_sums, const uint32_t* list, const uint32_t* list_n) {
+                             int32_t* status, uint64_t* block_sums, const uint32_t* list, const uint32_t* list_n, uint32_t* err_pos) {
   k_encode_parse<<<nb, GGR_BLOCK, 0, st>>>(blob, n, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first, status, (u64*)block_sums,
-                                           list, list_n);
+                                           list, list_n, err_pos);
 }
 void ggr_launch_block_sums(cudaStream_t st, unsigned nb, long long n, const uint32_t* size, uint64_t* block_sums) {
   k_block_sums<<<nb, GGR_BLOCK, 0, st>>>(n, size, (u64*)block_sums);

@@ -22,10 +22,12 @@ __global__ void __launch_bounds__(CW_WARPS * 32, CW_TOK_BLOCKS)
 k_encode_tok3(const u8* __restrict__ in, const u64* __restrict__ in_off, u8* __restrict__ ir, const u32* __restrict__ list,
               const u32* __restrict__ list_n) {
   __shared__ CwLut lut;
-  __shared__ u32 sh[CW_WARPS][4];
+  __shared__ CwTile tiles[CW_WARPS];  // per warp: two 2 KB stages of the item's text, filled by bulk copies (ggr_walk.cuh)
   const u32 warp = threadIdx.x >> 5;
   cw_lut_init(lut, threadIdx.x, CW_WARPS * 32);
+  if ((threadIdx.x & 31u) == 0) cw_tile_init(&tiles[warp]);
   __syncthreads();
+  u32 ph = 0;
   const long long total = (long long)*list_n;
   const u64 a0 = in_off[0];
   u32* ticket = const_cast<u32*>(list_n) + 1;  // zeroed with the list length
@@ -38,7 +40,7 @@ k_encode_tok3(const u8* __restrict__ in, const u64* __restrict__ in_off, u8* __r
     const u64 node_off = ((a - a0) >> 1) + 8ull * (u64)item;
     const u32 cap = (u32)((((b - a0) >> 1) + 8ull * (u64)(item + 1)) - node_off);
     const u32 s0 = (u32)(a & 15ull);
-    cw_tok_item(sh[warp], lut, in + (a & ~15ull), s0, s0 + (u32)(b - a), ir + node_off * 16, cap);
+    cw_tok_item(&tiles[warp], ph, lut, in + (a & ~15ull), s0, s0 + (u32)(b - a), ir + node_off * 16, cap);
   }
 }
 

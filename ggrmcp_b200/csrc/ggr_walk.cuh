@@ -106,8 +106,69 @@ GGR_DEV void cw_lut_init(CwLut& L, u32 first, u32 step) {
 // token's bit.
 GGR_DEV u32 cw_next(u32 T, u32 A) { return ((~T & 0x3FFFFu) + (A << 1)) & T; }
 
-// T1 of one item, all 32 lanes.  sh: four words of shared memory of this warp ({bail, n_tok, n_q}).
-GGR_DEV void cw_tok_item(u32* sh, const CwLut& LT, const u8* in, u32 start, u32 end, u8* region, u32 cap) {
+// ---- the item's text travels global -> shared memory by bulk asynchronous copies (cp.async.bulk, the TMA's 1-D form)
+// that complete on an mbarrier: two tiles of CW_TILE bytes per warp, tile t + 2 is requested as soon as every lane has
+// taken its 16 bytes of the last round of tile t, so that the copy of the next tiles runs under the mask arithmetic of
+// the current one and the lanes read their chunks with one conflict-free LDS.128 instead of a global load each.
+#ifndef CW_TOK_TMA
+#define CW_TOK_TMA 1                  /* 0: every lane loads its 16 bytes from global memory itself (the round-1/2 form) */
+#endif
+#define CW_TILE 2048u                 /* 128 chunks of 16 bytes = 4 rounds of the warp */
+#define CW_TILE_CHUNKS (CW_TILE / 16u)
+struct
+#if defined(__CUDACC__)
+    __align__(128)
+#else
+    alignas(128)
+#endif
+        CwTile {
+  u8 buf[2][CW_TILE];
+  unsigned long long bar[2];  // one mbarrier per stage (arrival count 1: the lane that issues the copy)
+};
+#if defined(__CUDACC__)
+// lane 0 of the warp, once per kernel (followed by a block-wide barrier)
+GGR_DEV void cw_tile_init(CwTile* tl) {
+#if defined(__CUDA_ARCH__)
+  const unsigned b0 = (unsigned)__cvta_generic_to_shared(&tl->bar[0]), b1 = (unsigned)__cvta_generic_to_shared(&tl->bar[1]);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b0) : "memory");
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b1) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+// one lane: bytes (a multiple of 16, > 0) from src (16-byte aligned) into stage stg; completes on the stage's barrier
+GGR_DEV void cw_tile_issue(CwTile* tl, u32 stg, const u8* src, u32 bytes) {
+#if defined(__CUDA_ARCH__)
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(&tl->bar[stg]);
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(&tl->buf[stg][0]);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+#endif
+}
+// all lanes: the copy into stage stg of the phase with this parity has landed
+GGR_DEV void cw_tile_wait(CwTile* tl, u32 stg, u32 parity) {
+#if defined(__CUDA_ARCH__)
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(&tl->bar[stg]);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "CW_TILE_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra CW_TILE_DONE;\n"
+      "bra CW_TILE_WAIT;\n"
+      "CW_TILE_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+#endif
+}
+#endif
+
+// T1 of one item, all 32 lanes.  tl: this warp's tile ring (device; the host simulation reads the text in place),
+// ph: the parities of the two stages' barriers, carried from item to item by the persistent warp.
+GGR_DEV void cw_tok_item(CwTile* tl, u32& ph, const CwLut& LT, const u8* in, u32 start, u32 end, u8* region, u32 cap) {
   const u32 lane = wp_lane();
   if (end > CE_MAX_INPUT || cap < 8u || end == start) return;  // decided again by the later kernels before they look at the index
   const u32* lut = LT.base.cls;
@@ -121,16 +182,50 @@ GGR_DEV void cw_tok_item(u32* sh, const CwLut& LT, const u8* in, u32 start, u32 
   u32 k_carry = 0;                                            // kind of the last token so far (0: none yet; 7 colon, 8 comma)
   u32 tbase = 0, qbase = 0, dbase = 0, ebase = 0;
   u32 bail = 0;
+#if defined(__CUDA_ARCH__) && CW_TOK_TMA
+  const u32 ntiles = (nchunks + CW_TILE_CHUNKS - 1u) / CW_TILE_CHUNKS;
+  if (lane == 0) {  // the first two tiles are on their way before the first round starts
+    cw_tile_issue(tl, 0, in, (nchunks < CW_TILE_CHUNKS ? nchunks : CW_TILE_CHUNKS) << 4);
+    if (ntiles > 1u) cw_tile_issue(tl, 1, in + CW_TILE, ((nchunks - CW_TILE_CHUNKS) < CW_TILE_CHUNKS ? (nchunks - CW_TILE_CHUNKS) : CW_TILE_CHUNKS) << 4);
+  }
+#else
+  (void)tl;
+  (void)ph;
   U4 vn;  // the next round's chunk is requested one round ahead
   vn.x = vn.y = vn.z = vn.w = 0;
   if (lane < nchunks) vn = ggr_ld16(in + (lane << 4));
+#endif
   for (u32 cb = 0; cb < nchunks; cb += 32) {
     const u32 ci = cb + lane;
     const u32 off = ci << 4;
     u32 Q = 0, B = 0, X = 0, W = 0xFFFFu, D = 0, HI = 0, XO = 0, XC = 0, XY = 0, XN = 0;
+#if defined(__CUDA_ARCH__) && CW_TOK_TMA
+    U4 v;
+    v.x = v.y = v.z = v.w = 0;
+    {
+      const u32 tile = cb / CW_TILE_CHUNKS, stg = tile & 1u, in_tile = cb & (CW_TILE_CHUNKS - 1u);
+      if (in_tile == 0) {  // first round of a tile: wait for its bytes
+        cw_tile_wait(tl, stg, (ph >> stg) & 1u);
+        ph ^= 1u << stg;
+      }
+      if (ci < nchunks) {
+        const uint4 q = *reinterpret_cast<const uint4*>(&tl->buf[stg][(in_tile + lane) << 4]);
+        v.x = q.x; v.y = q.y; v.z = q.z; v.w = q.w;
+      }
+      // last round of the tile: once every lane holds its chunk the stage is free for tile + 2
+      if ((in_tile == CW_TILE_CHUNKS - 32u || cb + 32u >= nchunks) && tile + 2u < ntiles) {
+        __syncwarp();
+        if (lane == 0) {
+          const u32 c0 = (tile + 2u) * CW_TILE_CHUNKS, left = nchunks - c0;
+          cw_tile_issue(tl, stg, in + ((size_t)c0 << 4), (left < CW_TILE_CHUNKS ? left : CW_TILE_CHUNKS) << 4);
+        }
+      }
+    }
+#else
     const U4 v = vn;
     vn.x = vn.y = vn.z = vn.w = 0;
     if (ci + 32u < nchunks) vn = ggr_ld16(in + off + 512u);
+#endif
     if (ci < nchunks) {
       u32 lo = 0, hi = 0, lo2 = 0, hi2 = 0;
 #pragma unroll
@@ -291,7 +386,6 @@ GGR_DEV void cw_tok_item(u32* sh, const CwLut& LT, const u8* in, u32 start, u32 
     }
   }
   const bool fail = WP_ANY(bail != 0) || in_carry || u_carry || tbase == 0 || tbase > tcap || qbase > qcap || k_carry != 2u;
-  (void)sh;
   if (lane == 0) {
     U4 h = {tbase, qbase, fail ? 1u : 0u, 0xFFFFFFFFu};
     ggr_st16(region, h);

@@ -212,6 +212,19 @@ class Engine:
         cap = out_cap if out_cap is not None else len(data) * 3 + 64 * len(msg_ids) + 64
         return self._host(_load().ggr_decode_batch, schema, msg_ids, data, off, flags, cap)
 
+    def encode_diagnose(self, schema, msg_id, js, flags=0):
+        """Error detail of one failing request item (ggr_encode_diagnose): (status, err_pos, err_len, text)."""
+        L = _load()
+        L.ggr_encode_diagnose.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_char_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_int32),
+                                          C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_char_p, C.c_size_t]
+        L.ggr_encode_diagnose.restype = C.c_int
+        st, pos, ln = C.c_int32(0), C.c_uint32(0), C.c_uint32(0)
+        buf = C.create_string_buffer(512)
+        rc = L.ggr_encode_diagnose(self.h, schema.h, int(msg_id), bytes(js), len(js), flags, C.byref(st), C.byref(pos), C.byref(ln), buf, 512)
+        if rc != 0:
+            self._err(rc, "ggr_encode_diagnose")
+        return st.value, pos.value, ln.value, buf.value.decode("utf-8", "replace")
+
     def request_batch(self, schema, bodies, off, out_cap=None):
         """JSON-RPC tools/call request bodies -> (wire bytes, offsets[n+1], method[n], id_span[n, 2], status[n]);
         status 11 (unsupported) = the device does not take this body."""

@@ -166,6 +166,20 @@ int ggr_decode_batch_dev(ggr_engine* e, const ggr_schema* s, int64_t n, const in
 int ggr_synchronize(ggr_engine* e);
 
 /*
+ * Error detail of ONE request item the batch calls reported with status != 0 (SURVEY.md 8b "Error conventions": the Go
+ * side returns `failed to parse input JSON: <protojson's error>`, reflection.go:356, and the reference's tests pin the
+ * substring `unknown field` with the offending name, tests/real_grpc_invocation_test.go:238-245).  The item goes through
+ * the device's per-thread parser once more (the kernel that decides every request-side error), which reports where it
+ * stopped: *err_pos is the byte offset inside json - of the member's key token for unknown fields, duplicate fields and
+ * oneof conflicts, of the reader otherwise - and *err_len the length of the key token there (quotes included; 0 when the
+ * position is no key).  text (optional, NUL-terminated, truncated to text_cap): `proto: (line L:C): unknown field "x"` /
+ * `duplicate field "x"` in protojson's wording, the status name behind the position for the other categories.
+ * Synchronous, rare-path (one small allocation per call); *status repeats the batch call's status of the item.
+ */
+int ggr_encode_diagnose(ggr_engine* e, const ggr_schema* s, int32_t msg_id, const uint8_t* json, uint64_t json_len,
+                        uint32_t flags, int32_t* status, uint32_t* err_pos, uint32_t* err_len, char* text, size_t text_cap);
+
+/*
  * Request bodies (handler.go:83-95 decode, pkg/mcp/validation.go, discovery.go:336-375 tool lookup,
  * handler.go:224-231 json.Marshal(arguments), reflection.go:351-373 request half).  Item i is the
  * HTTP body body[body_off[i] .. body_off[i+1]) of a JSON-RPC tools/call request.  For the bodies the

@@ -258,7 +258,8 @@ struct WalkArgs {
 };
 static void walk_tok_body(void* p, u32 lane) {
   WalkArgs* a = (WalkArgs*)p;
-  cw_tok_item(a->sh, *a->lut, a->in, a->start, a->end, a->region, a->cap);
+  u32 ph = 0;
+  cw_tok_item(nullptr, ph, *a->lut, a->in, a->start, a->end, a->region, a->cap);
 }
 static void walk_place_body(void* p, u32 lane) {
   WalkArgs* a = (WalkArgs*)p;

@@ -91,6 +91,39 @@ def test_encode_damaged(engine, schema, oracle):
             assert eo[i] == oo[i]
 
 
+def test_encode_diagnose(engine, schema, oracle):
+    """ggr_encode_diagnose: the status of the batch call again, the position of the offending key and - for unknown and
+    duplicate fields, the wording the reference's tests pin (tests/real_grpc_invocation_test.go:238-245) - the oracle's
+    message once protojson's position prefix is taken off"""
+    import re
+    name = "com.example.complex.GetUserProfileRequest"
+    mid = schema.message(name)
+    probes = [b'{"invalid_field":1}', b'{"user_id":"a",\n  "nope": {"x":[1,2]}}', b'{"user_id":"a","user_id":"b"}', b'{"user_id":5}',
+              b'{"user_id" "a"}', b'{"user_id":"a"', b'{"user_id":"ok"}', b'{ "userId":"a", "user_id":"b"}']
+    rng = random.Random(9)
+    items = [(name, p) for p in probes] + [(n, cases.mutate_json(j, rng)) for n, j in cases.random_encode_cases(40, seed0=900)]
+    eo, es = _run(engine, schema, True, items)
+    named = 0
+    for (n, js), st_batch in zip(items, es):
+        st, pos, ln, text = engine.encode_diagnose(schema, schema.message(n), js)
+        assert st == int(st_batch), (js, st, int(st_batch))
+        rc, _, err = oracle.encode(n, js)
+        assert (rc == 0) == (st == 0)
+        if st == 0:
+            assert text == ""
+            continue
+        assert pos <= len(js) and text.startswith("proto: (line ")
+        if st in (2, 6) and ln:  # unknown field / duplicate field: the raw key token
+            assert js[pos:pos + ln].startswith(b'"') and js[pos:pos + ln].endswith(b'"')
+            ours = re.sub(r"\(line \d+:\d+\): ", "", text)
+            if "map key" not in err:
+                assert ours == err, (js, ours, err)
+                named += 1
+    assert named >= 4
+    st, pos, ln, text = engine.encode_diagnose(schema, mid, probes[1])
+    assert (st, js_slice := probes[1][pos:pos + ln]) == (2, b'"nope"') and text == 'proto: (line 2:3): unknown field "nope"', (st, pos, ln, text)
+
+
 def test_decode_edges(engine, schema, oracle):
     items = [(n, bytes.fromhex(h)) for n, h in cases.DECODE_EDGE_HEX]
     for flags in (0, 1):

@@ -518,7 +518,8 @@ def test_decode_unsorted_maps(oracle, hsim):
         n = rng.choice([9, 40, 300])
         ent = []
         for i in range(n):
-            k = "k%d_%s" % (rng.randrange(n), "x" * rng.randrange(3))
+            # trials 4..: keys that agree in their first eight bytes and beyond (the sort records carry an 8-byte prefix)
+            k = ("k%d_%s" if trial < 4 else ("shared__%d_%s" if trial < 8 else "%04d%s"))  % (rng.randrange(n), "x" * rng.randrange(3) + "\0" * rng.randrange(2))
             ent.append(ld(41, ld(1, k.encode()) + varint(2 << 3) + varint(rng.randrange(1 << 31))))              # m_str_int32
         for i in range(n):
             ent.append(ld(42, varint(1 << 3) + varint(rng.randrange(n) ^ ((1 << 64) - 1 if rng.random() < 0.3 else 0)) + ld(2, b"v%d" % i)))  # m_int32_str
