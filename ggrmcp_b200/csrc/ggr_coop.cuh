@@ -21,6 +21,14 @@
 #include "ggr_decode.cuh"
 #include "ggr_warp.cuh"
 
+// why the lock-step tier left an item: recorded by the host simulation only (tests/hostsim: hs_coop_why = source line)
+#if !defined(__CUDA_ARCH__) && !defined(__CUDACC__)
+extern int g_coop_why;
+#define COOP_BAIL(S) ((S).bail = 1, g_coop_why = __LINE__)
+#else
+#define COOP_BAIL(S) ((S).bail = 1)
+#endif
+
 // Entry tables: every item owns GGR_COOP_TAB_ENTRIES slots of the saved table in HBM; the size pass works on a copy in
 // shared memory - 224 entries in the first tier (bench replies: 133 on average; 8.9 KB per warp with the masks below =
 // 24 warps per SM), the full 320 in the second tier, which takes the few items the first leaves because of the table
@@ -77,7 +85,10 @@ struct CoopSharedT {
   u16 dlist[GGR_COOP_DIRTY_MAX];          // strings that need escaping / validation: sized by the whole warp
 };
 typedef CoopSharedT<GGR_COOP_ENTRIES> CoopShared;      // first tier
-typedef CoopSharedT<GGR_COOP_TAB_ENTRIES> CoopSharedBig;  // second tier
+// second tier: replies of thousands of field occurrences (a 39 KB reply of the mixed replay holds 1 800: on one lane of the
+// per-thread kernels that is 40 ms per pass); 141 KB of shared memory = one warp per SM, the saved table goes to a pool
+#define GGR_COOP_BIG_ENTRIES 4096
+typedef CoopSharedT<GGR_COOP_BIG_ENTRIES> CoopSharedBig;
 
 GGR_DEV u32 coop_class(const FieldD& f, bool ts, bool packed) {
   if (packed) return DC_PACKED;
@@ -153,12 +164,12 @@ GGR_DEV void coop_scan_message(SH& S, const DecCtx& cx, u32 me) {
   const CoopEnt m = S.ent[me];
   const MsgD md = ggr_msg(T, m.fc_msg);
   S.ent[me].fc_msg = 0xFFFFu;  // from here on: first child
-  if (md.wkt != GGR_WKT_NONE || m.depth + 1u >= GGR_COOP_DEPTH) { S.bail = 1; return; }
+  if (md.wkt != GGR_WKT_NONE || m.depth + 1u >= GGR_COOP_DEPTH) { COOP_BAIL(S); return; }
   const u32 lim = m.vend;
   u32 pos = m.vpos;
   if (m.gfield != GGR_COOP_ROOT) {  // a field entry starts at its length prefix
     u64 len;
-    if (!br_varint(in, pos, lim, &len) || len != (u64)(lim - pos)) { S.bail = 1; return; }
+    if (!br_varint(in, pos, lim, &len) || len != (u64)(lim - pos)) { COOP_BAIL(S); return; }
   }
   i32 last_decl = -1;
   u32 open = 0;        // emit index + 1 of the repeated field currently being collected
@@ -173,15 +184,15 @@ GGR_DEV void coop_scan_message(SH& S, const DecCtx& cx, u32 me) {
     const bool fast = coop_header(coop_window(in, pos, end_al), pos, &wtag, &wtl, &wbody, &wvend, &wzero) && wvend <= lim && wbody <= lim;
     u64 tag = wtag;
     if (fast) pos += wtl;
-    else if (!br_varint(in, pos, lim, &tag)) { S.bail = 1; return; }
+    else if (!br_varint(in, pos, lim, &tag)) { COOP_BAIL(S); return; }
     const u64 num64 = tag >> 3;
     const u32 wt = (u32)(tag & 7);
-    if (num64 == 0 || num64 > 0x1FFFFFFFull || wt == 3 || wt == 4 || wt > 5) { S.bail = 1; return; }
+    if (num64 == 0 || num64 > 0x1FFFFFFFull || wt == 3 || wt == 4 || wt > 5) { COOP_BAIL(S); return; }
     const u32 num = (u32)num64;
     const i32 ei = find_field(T, md, num);
     if (ei < 0) {
       if (fast) pos = wvend;
-      else if (!br_skip(in, pos, lim, wt)) { S.bail = 1; return; }
+      else if (!br_skip(in, pos, lim, wt)) { COOP_BAIL(S); return; }
       continue;
     }
     const u32 gf = md.field_first + (u32)ei;
@@ -189,10 +200,10 @@ GGR_DEV void coop_scan_message(SH& S, const DecCtx& cx, u32 me) {
     const bool packed_in = (f.flags & GF_PACKABLE) && wt == 2;
     if (wt != f.wt && !packed_in) {
       if (fast) pos = wvend;
-      else if (!br_skip(in, pos, lim, wt)) { S.bail = 1; return; }
+      else if (!br_skip(in, pos, lim, wt)) { COOP_BAIL(S); return; }
       continue;
     }
-    if ((f.flags & GF_MAP) || gf >= 0xFFFFu) { S.bail = 1; return; }
+    if ((f.flags & GF_MAP) || gf >= 0xFFFFu) { COOP_BAIL(S); return; }
     const u32 vpos = pos;
     // value extent: [vpos, vend), payload of length-delimited values at body
     u32 body = pos, vend = pos;
@@ -201,10 +212,10 @@ GGR_DEV void coop_scan_message(SH& S, const DecCtx& cx, u32 me) {
       vend = wvend;
     } else if (wt == 2) {
       u64 len;
-      if (!br_varint(in, body, lim, &len) || len > (u64)(lim - body)) { S.bail = 1; return; }
+      if (!br_varint(in, body, lim, &len) || len > (u64)(lim - body)) { COOP_BAIL(S); return; }
       vend = body + (u32)len;
     } else {
-      if (!br_skip(in, vend, lim, wt)) { S.bail = 1; return; }
+      if (!br_skip(in, vend, lim, wt)) { COOP_BAIL(S); return; }
     }
     pos = vend;
     u32 flags = 0;
@@ -212,11 +223,11 @@ GGR_DEV void coop_scan_message(SH& S, const DecCtx& cx, u32 me) {
     if (repeated) {
       flags |= CF_ARR_ELEM;
       if (packed_in && vend == body) {  // an empty packed run contributes nothing (and opens nothing)
-        if (open != (u32)ei + 1 && (i32)f.decl_index <= last_decl) { S.bail = 1; return; }
+        if (open != (u32)ei + 1 && (i32)f.decl_index <= last_decl) { COOP_BAIL(S); return; }
         continue;
       }
       if (open != (u32)ei + 1) {
-        if ((i32)f.decl_index <= last_decl) { S.bail = 1; return; }
+        if ((i32)f.decl_index <= last_decl) { COOP_BAIL(S); return; }
         if (open && prev != 0xFFFFu) S.ent[prev].flags |= CF_ARR_LAST;
         last_decl = (i32)f.decl_index;
         open = (u32)ei + 1;
@@ -226,22 +237,22 @@ GGR_DEV void coop_scan_message(SH& S, const DecCtx& cx, u32 me) {
     } else {
       if (open && prev != 0xFFFFu) S.ent[prev].flags |= CF_ARR_LAST;
       open = 0;
-      if ((i32)f.decl_index <= last_decl) { S.bail = 1; return; }
+      if ((i32)f.decl_index <= last_decl) { COOP_BAIL(S); return; }
       if (f.oneof >= 0) {
         u32 bit = 1u << (f.oneof & 31);
-        if (oneofs & bit) { S.bail = 1; return; }
+        if (oneofs & bit) { COOP_BAIL(S); return; }
         oneofs |= bit;
       }
       last_decl = (i32)f.decl_index;
       if (f.kind != GK_MESSAGE && !(f.flags & GF_PRESENCE)) {
         bool ok = true;
         const bool z = fast ? wzero : coop_wire_zero(in, vpos, lim, wt, &ok);
-        if (!ok) { S.bail = 1; return; }
+        if (!ok) { COOP_BAIL(S); return; }
         if (z) continue;  // implicit presence: the zero value is not written
       }
     }
     const u32 slot = wp_atomic_add(&S.n_ent, 1u);
-    if (slot >= SH::ENTRIES) { S.bail = 1; return; }
+    if (slot >= SH::ENTRIES) { COOP_BAIL(S); return; }
     CoopEnt e;
     e.vpos = vpos;
     e.vend = vend;
@@ -261,7 +272,7 @@ GGR_DEV void coop_scan_message(SH& S, const DecCtx& cx, u32 me) {
         flags |= CF_TIMESTAMP;
         ts = true;
       } else if (w != GGR_WKT_NONE || (u32)f.child >= 0xFFFFu) {
-        S.bail = 1;
+        COOP_BAIL(S);
         return;
       } else {
         flags |= CF_MSG;
@@ -530,7 +541,7 @@ GGR_DEV void coop_size_leaf(SH& S, const DecCtx& cx, u32 ei, bool have_masks) {
     Cnt c;
     c.pos = 0;
     if (coop_leaf_value(c, cx, e, f) != GST_OK) {
-      S.bail = 1;
+      COOP_BAIL(S);
       return;
     }
     n += c.pos;
@@ -538,7 +549,7 @@ GGR_DEV void coop_size_leaf(SH& S, const DecCtx& cx, u32 ei, bool have_masks) {
     Cnt c;
     c.pos = 0;
     if (coop_leaf_value(c, cx, e, f) != GST_OK) {
-      S.bail = 1;
+      COOP_BAIL(S);
       return;
     }
     n += c.pos;
@@ -585,7 +596,9 @@ GGR_DEV void coop_offsets_message(SH& S, const DecCtx& cx, u32 me) {
 // shared memory have no edges.
 #define GGR_COOP_STAGE 8192u /* items with more text than this: per-thread kernels */
 #ifndef GGR_COOP_STAGE_BUF
-#define GGR_COOP_STAGE_BUF 8192u /* the writer's staging buffer; larger texts are written in place */
+/* the writer's staging buffer; larger texts are written in place.  6144 (configs[2]: texts up to 6.0 KB) with the kernel
+   compiled for 7 blocks per SM (72 registers): 1.08 -> 1.00 ms; for 8 blocks (64 registers, spills) 1.11 ms */
+#define GGR_COOP_STAGE_BUF 6144u
 #endif
 struct
 #if defined(__CUDACC__)
@@ -687,8 +700,11 @@ GGR_DEV int coop_write_entry(CoopStage& E, const DecCtx& cx, const CoopEnt& e, u
 // Size pass of one item, all lanes.  Returns true when the item was handled: *size is its text
 // size and, when `save` != nullptr, the entry table (n entries, *n_out) has been stored there for
 // the write pass.
+// pool != nullptr (second tier): the table is saved at pool + 2 * (*tab_off), *tab_off entries handed out by the bump
+// counter *pool_ctr (pool_cap entries in all; an exhausted pool leaves the item to the per-thread kernels).
 template <class SH>
-GGR_DEV bool coop_size_item(SH& S, const DecCtx& cx, u32 root_msg, u32 start, u32 end, U4* save, u32* n_out, u32* size) {
+GGR_DEV bool coop_size_item(SH& S, const DecCtx& cx, u32 root_msg, u32 start, u32 end, U4* save, u32* n_out, u32* size,
+                            U4* pool = nullptr, u32* pool_ctr = nullptr, u32 pool_cap = 0, u32* tab_off = nullptr) {
   const u32 lane = wp_lane();
   *size = 0;
   *n_out = 0;
@@ -783,6 +799,14 @@ GGR_DEV bool coop_size_item(SH& S, const DecCtx& cx, u32 root_msg, u32 start, u3
     WP_SYNC();
   }
   *size = S.ent[0].size;
+  if (pool) {
+    u32 base = 0;
+    if (lane == 0) base = ggr_atomic_add_u32(pool_ctr, n);
+    base = WP_SHFL(base, 0);
+    if (base > pool_cap || n > pool_cap - base) return false;
+    save = pool + 2 * (size_t)base;
+    *tab_off = base;
+  }
   if (!save) return true;
   for (u32 d = 0; d <= maxd; d++) {
     for (u32 i = lane; i < n; i += 32)

@@ -1209,7 +1209,9 @@ GGR_DEV bool ce_parse_item(SH& S, const CeLut& lut, const Tables& T, u32 root_ms
 #define CE_LONG_MAX 32u
 #define CE_STAGE 8192u /* items with more wire bytes than this: per-thread emitter */
 #ifndef CE_STAGE_BUF
-#define CE_STAGE_BUF 8192u /* the emitter's staging buffer; larger items (up to CE_STAGE and beyond) are written in place */
+/* the emitter's staging buffer; larger items (up to CE_STAGE and beyond) are written in place.  4864 + the lists = 5.3 KB per
+   warp = 10 blocks per SM instead of 6 with 8192 (configs[2]: wire items up to 4.6 KB; 1.11 -> 0.91 ms, profiles/README.md) */
+#define CE_STAGE_BUF 4864u
 #endif
 struct
 #if defined(__CUDACC__)

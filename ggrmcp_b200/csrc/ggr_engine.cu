@@ -174,6 +174,7 @@ struct Scratch {
   DevBuf ir, size, aux, sums, pend, ioff, nn;
   DevBuf wtext, woff, wsize;  // result wrapping: protojson texts, their offsets, body sizes
   DevBuf sortpool;            // reply side: (key, position) records of maps whose entries arrive unsorted
+  DevBuf tabpool, taboff;     // reply side, second lock-step tier: pooled entry tables and where each item's table starts
   DevBuf spread;              // per-thread kernels: the list of large items, one per warp (k_spread)
 };
 #define GGR_MAX_SLOTS 8
@@ -464,7 +465,7 @@ void ggr_engine_destroy(ggr_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   auto free_scratch = [](Scratch& sc) {
-    DevBuf* bufs[] = {&sc.ir, &sc.size, &sc.aux, &sc.sums, &sc.pend, &sc.ioff, &sc.nn, &sc.wtext, &sc.woff, &sc.wsize, &sc.sortpool, &sc.spread};
+    DevBuf* bufs[] = {&sc.ir, &sc.size, &sc.aux, &sc.sums, &sc.pend, &sc.ioff, &sc.nn, &sc.wtext, &sc.woff, &sc.wsize, &sc.sortpool, &sc.spread, &sc.tabpool, &sc.taboff};
     for (DevBuf* b : bufs)
       if (b->p) cudaFree(b->p);
   };
@@ -639,16 +640,19 @@ static int run_dev_kernels(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool
   if (encode) {
     if (e->use_coop_enc) {
       // lock-step parser first (one warp per item); what it leaves goes to the per-thread parser
-      if (!ensure(e, sc.pend, (size_t)n * 16 + 64) || !ensure(e, sc.ioff, (size_t)in_bytes * 2 + (size_t)n * 32 + 64) ||
+      if (!ensure(e, sc.pend, (size_t)n * 20 + 128) || !ensure(e, sc.ioff, (size_t)in_bytes * 2 + (size_t)n * 32 + 64) ||
           !ensure(e, sc.nn, (size_t)n * 4))
         return GGR_ERR_CUDA;
-      u32* counters = (u32*)sc.pend.p;  // [0] lock-step items, [4] left by the first tier, [8] per-thread items, [12] left by the walker's second tier
-      u32* big = counters + 16;
+      // [0] lock-step items, [4] left by the walker (all tiers), [8] per-thread items, [12] left by the walker's first tier,
+      // [16] left by its second tier; each list length is followed by the ticket counters of the kernels that run over the list
+      u32* counters = (u32*)sc.pend.p;
+      u32* big = counters + 32;
       u32* pend1 = big + n;
       u32* pend2 = pend1 + n;
       u32* pend1b = pend2 + n;
+      u32* pend1c = pend1b + n;
       size_t c0 = 0, c1 = 0;
-      if (!cuda_ok(e, cudaMemsetAsync(counters, 0, 64, st), "memset") ||
+      if (!cuda_ok(e, cudaMemsetAsync(counters, 0, 128, st), "memset") ||
           !cuda_ok(e, cudaMemsetAsync(sc.nn.p, 0, (size_t)n * 4, st), "memset"))
         return GGR_ERR_CUDA;
       if (prof) prof_mark(e, st, &m0);
@@ -665,9 +669,12 @@ static int run_dev_kernels(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool
         if (prof) prof_mark(e, st, &t2);
         ggr_launch_encode_type(st, 0, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p, (u32*)sc.aux.p, status,
                                (u32*)sc.ioff.p, (u32*)sc.nn.p, big, counters, pend1b, counters + 12, e->sm_count);
-        // second tier over what the first left (large items, the other leaf forms); what it leaves: pend1 -> the fused kernel
+        // second tier over what the first left (large items, the other leaf forms), third tier (thousands of values, one warp
+        // per SM) over what the second left; what that leaves: pend1 -> the fused kernel
         ggr_launch_encode_type(st, 1, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p, (u32*)sc.aux.p, status,
-                               (u32*)sc.ioff.p, (u32*)sc.nn.p, pend1b, counters + 12, pend1, counters + 4, e->sm_count);
+                               (u32*)sc.ioff.p, (u32*)sc.nn.p, pend1b, counters + 12, pend1c, counters + 16, e->sm_count);
+        ggr_launch_encode_type(st, 2, n, s->d_blob, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p, (u32*)sc.aux.p, status,
+                               (u32*)sc.ioff.p, (u32*)sc.nn.p, pend1c, counters + 16, pend1, counters + 4, e->sm_count);
         if (prof) {
           prof_mark(e, st, &t3);
           e->spans.push_back({12, t1, t2});  // value records
@@ -715,7 +722,7 @@ static int run_dev_kernels(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool
         prof_mark(e, st, &m1);
         e->spans.push_back({9, c1, m1});
       }
-      e->launches += e->use_walk ? 7 : 5;  // + the token-index kernel of tier 1 (+ the place kernel of the token-parallel walker)
+      e->launches += e->use_walk ? 8 : 5;  // + the token-index kernel of tier 1 (+ the place kernel of the token-parallel walker)
     } else {
       ggr_launch_encode_parse(st, (unsigned)nb, s->d_blob, n, n_msgs, msg_id, in, in_off, (u8*)sc.ir.p, (u32*)sc.size.p,
                               (u32*)sc.aux.p, status, (u64*)sc.sums.p, nullptr, nullptr);
@@ -737,7 +744,7 @@ static int run_dev_kernels(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool
         have_mx = true;
       }
       ggr_launch_encode_coop_emit(st, n, in, in_off, (const u8*)sc.ir.p, (const u32*)sc.ioff.p, (const u32*)sc.nn.p,
-                                  (const u32*)sc.size.p, status, out, out_off, e->sm_count, (const u32*)sc.pend.p + 16,
+                                  (const u32*)sc.size.p, status, out, out_off, e->sm_count, (const u32*)sc.pend.p + 32,
                                   (const u32*)sc.pend.p, frame);
       if (prof) {
         prof_mark(e, st, &x1);
@@ -756,15 +763,18 @@ static int run_dev_kernels(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool
     if (!ensure(e, sc.sortpool, (size_t)sort_cap * 16 + 16)) return GGR_ERR_CUDA;
     if (!cuda_ok(e, cudaMemsetAsync(sc.sortpool.p, 0, 16, st), "memset")) return GGR_ERR_CUDA;
     if (coop) {
+      // second tier's tables: a field occurrence takes at least 2 bytes of wire; the pool is capped at 4 M entries (128 MB)
+      const uint64_t want_ent = in_bytes / 2 + 4096;
+      const uint32_t pool_cap = (uint32_t)(want_ent > (4ull << 20) ? (4ull << 20) : want_ent);
       if (!ensure(e, sc.ir, ggr_decode_coop_table_bytes(n)) || !ensure(e, sc.nn, (size_t)n * 4) ||
-          !ensure(e, sc.pend, (size_t)n * 8 + 64))
+          !ensure(e, sc.pend, (size_t)n * 8 + 64) || !ensure(e, sc.tabpool, (size_t)pool_cap * 32 + 32) || !ensure(e, sc.taboff, (size_t)n * 4))
         return GGR_ERR_CUDA;
       u32* counters = (u32*)sc.pend.p;
       u32* big = counters + 16;
-      if (!cuda_ok(e, cudaMemsetAsync(counters, 0, 64, st), "memset")) return GGR_ERR_CUDA;
+      if (!cuda_ok(e, cudaMemsetAsync(counters, 0, 64, st), "memset") || !cuda_ok(e, cudaMemsetAsync(sc.tabpool.p, 0, 32, st), "memset")) return GGR_ERR_CUDA;
       k_route<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, in_off, e->min_wire, 0x3FFFFF00u, big, counters, nullptr, nullptr, (u32*)sc.aux.p);
       ggr_launch_decode_coop_size(st, n, s->d_blob, n_msgs, msg_id, in, in_off, flags, (u32*)sc.size.p, (u32*)sc.aux.p, status,
-                                  sc.ir.p, (u32*)sc.nn.p, e->sm_count, big, counters, big + n, counters + 4);
+                                  sc.ir.p, (u32*)sc.nn.p, e->sm_count, big, counters, big + n, counters + 4, sc.tabpool.p, pool_cap, (u32*)sc.taboff.p);
       if (prof) {
         prof_mark(e, st, &c0);
         e->spans.push_back({6, m0, c0});
@@ -801,7 +811,8 @@ static int run_dev_kernels(ggr_engine* e, const ggr_schema* s, Scratch& sc, bool
     if (coop) {
       if (prof) prof_mark(e, st, &c1);
       ggr_launch_decode_coop_write(st, n, s->d_blob, in, in_off, flags, (const u32*)sc.size.p, (const u32*)sc.aux.p, status, sc.ir.p,
-                                   (const u32*)sc.nn.p, out, out_off, e->sm_count, (const u32*)sc.pend.p + 16, (const u32*)sc.pend.p);
+                                   (const u32*)sc.nn.p, out, out_off, e->sm_count, (const u32*)sc.pend.p + 16, (const u32*)sc.pend.p, sc.tabpool.p,
+                                   (const u32*)sc.taboff.p);
       if (prof) {
         prof_mark(e, st, &m3);
         e->spans.push_back({3, m0, m1});

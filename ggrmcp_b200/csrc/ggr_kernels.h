@@ -51,11 +51,14 @@ void ggr_launch_decode_write(cudaStream_t st, unsigned nb, const uint8_t* blob, 
 void ggr_launch_decode_coop_size(cudaStream_t st, long long n, const uint8_t* blob, uint32_t n_msgs, const int32_t* msg_id,
                                  const uint8_t* in, const uint64_t* in_off, uint32_t flags, uint32_t* size, uint32_t* mode,
                                  int32_t* status, void* tab, uint32_t* nent, int sm_count, const uint32_t* list,
-                                 const uint32_t* list_n, uint32_t* pending, uint32_t* n_pending);
+                                 const uint32_t* list_n, uint32_t* pending, uint32_t* n_pending, void* pool, uint32_t pool_cap,
+                                 uint32_t* tab_off);
+// pool: 32 bytes of header (bump counter, zeroed per batch) + pool_cap saved entries of 32 bytes for the second tier's tables;
+// tab_off[item]: first pooled entry of an item whose nent has bit 31 set
 void ggr_launch_decode_coop_write(cudaStream_t st, long long n, const uint8_t* blob, const uint8_t* in, const uint64_t* in_off,
                                   uint32_t flags, const uint32_t* size, const uint32_t* mode, int32_t* status, const void* tab,
                                   const uint32_t* nent, uint8_t* out, const uint64_t* out_off, int sm_count,
-                                  const uint32_t* list, const uint32_t* list_n);
+                                  const uint32_t* list, const uint32_t* list_n, const void* pool, const uint32_t* tab_off);
 size_t ggr_decode_coop_table_bytes(long long n);  // scratch the size kernel needs for the entry tables
 int ggr_decode_coop_init();
 void ggr_launch_wrap_size(cudaStream_t st, long long n, const uint8_t* text, const uint64_t* text_off, const int32_t* status,

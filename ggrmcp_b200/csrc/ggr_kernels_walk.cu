@@ -59,7 +59,7 @@ k_encode_place(const u64* __restrict__ in_off, u8* __restrict__ ir, const u32* _
     if (b <= a || b - a > (u64)CE_MAX_INPUT - 16u) continue;
     const u64 node_off = ((a - a0) >> 1) + 8ull * (u64)item;
     const u32 cap = (u32)((((b - a0) >> 1) + 8ull * (u64)(item + 1)) - node_off);
-    cw_place_item(S[warp], ir + node_off * 16, cap, CoopWalkBig::MAX_NODE);
+    cw_place_item(S[warp], ir + node_off * 16, cap, CoopWalkHuge::MAX_NODE);
   }
 }
 
@@ -68,8 +68,9 @@ k_encode_place(const u64* __restrict__ in_off, u8* __restrict__ ir, const u32* _
 // SH / FULL: first tier - 256 values per item, strings / plain integers / bools (small, spill-free kernel: every regular
 // item of configs[2]); second tier - 1024 values, every leaf form this walker knows, items of any wire size - over what the
 // first tier appended to `pending`.
-template <class SH, bool FULL>
-__global__ void __launch_bounds__(CW_WARPS * 32, FULL ? 1 : CW_WALK_BLOCKS)
+// WARPS: warps per block (the third tier's table fills the shared memory of an SM: one)
+template <class SH, bool FULL, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, FULL ? 1 : CW_WALK_BLOCKS)
 k_encode_type(const u8* __restrict__ blob, u32 n_msgs, const i32* __restrict__ msg_id, const u8* __restrict__ in,
               const u64* __restrict__ in_off, u8* __restrict__ ir, u32* __restrict__ size, u32* __restrict__ first,
               i32* __restrict__ status, u32* __restrict__ ioff, u32* __restrict__ nnodes, const u32* __restrict__ list,
@@ -122,8 +123,9 @@ k_encode_type(const u8* __restrict__ blob, u32 n_msgs, const i32* __restrict__ m
 }
 
 int ggr_encode_walk_init() {
-  return (cudaFuncSetAttribute(k_encode_type<CoopWalk, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(CoopWalk) * CW_WARPS)) == cudaSuccess &&
-          cudaFuncSetAttribute(k_encode_type<CoopWalkBig, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(CoopWalkBig) * CW_WARPS)) == cudaSuccess)
+  return (cudaFuncSetAttribute(k_encode_type<CoopWalk, false, CW_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(CoopWalk) * CW_WARPS)) == cudaSuccess &&
+          cudaFuncSetAttribute(k_encode_type<CoopWalkBig, true, CW_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(CoopWalkBig) * CW_WARPS)) == cudaSuccess &&
+          cudaFuncSetAttribute(k_encode_type<CoopWalkHuge, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CoopWalkHuge)) == cudaSuccess)
              ? 0
              : -1;
 }
@@ -159,15 +161,19 @@ void ggr_launch_encode_type(cudaStream_t st, int tier, long long n, const uint8_
   if (tier == 0) {
     static unsigned per_sm = 0;
     const size_t smem = sizeof(CoopWalk) * CW_WARPS;
-    if (!per_sm) per_sm = cw_grid((const void*)k_encode_type<CoopWalk, false>, CW_WARPS * 32, smem, 1ll << 40, 1);
+    if (!per_sm) per_sm = cw_grid((const void*)k_encode_type<CoopWalk, false, CW_WARPS>, CW_WARPS * 32, smem, 1ll << 40, 1);
     const long long want = (n + CW_WARPS - 1) / CW_WARPS, cap = (long long)sm_count * per_sm;
-    k_encode_type<CoopWalk, false><<<(unsigned)(want < cap ? want : cap), CW_WARPS * 32, smem, st>>>(
+    k_encode_type<CoopWalk, false, CW_WARPS><<<(unsigned)(want < cap ? want : cap), CW_WARPS * 32, smem, st>>>(
+        blob, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending);
+  } else if (tier == 2) {
+    // third tier: one warp per SM over what the second left
+    k_encode_type<CoopWalkHuge, true, 1><<<(unsigned)sm_count, 32, sizeof(CoopWalkHuge), st>>>(
         blob, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending);
   } else {
     static unsigned per_sm = 0;
     const size_t smem = sizeof(CoopWalkBig) * CW_WARPS;
-    if (!per_sm) per_sm = cw_grid((const void*)k_encode_type<CoopWalkBig, true>, CW_WARPS * 32, smem, 1ll << 40, 1);
-    k_encode_type<CoopWalkBig, true><<<(unsigned)sm_count * per_sm, CW_WARPS * 32, smem, st>>>(
+    if (!per_sm) per_sm = cw_grid((const void*)k_encode_type<CoopWalkBig, true, CW_WARPS>, CW_WARPS * 32, smem, 1ll << 40, 1);
+    k_encode_type<CoopWalkBig, true, CW_WARPS><<<(unsigned)sm_count * per_sm, CW_WARPS * 32, smem, st>>>(
         blob, n_msgs, msg_id, in, (const u64*)in_off, ir, size, first, status, ioff, nnodes, list, list_n, pending, n_pending);
   }
 }

@@ -546,6 +546,10 @@ struct CoopWalkT {
 };
 typedef CoopWalkT<256> CoopWalk;       // first tier: 5.9 KB per warp
 typedef CoopWalkT<1024> CoopWalkBig;  // second tier: 18.6 KB per warp (large items, every leaf form)
+// third tier: request items of thousands of values (a 60 KB list of numbers holds 8 000); 22 bytes per value = 180 KB = one
+// warp per SM.  Such an item costs the per-thread parser tens of milliseconds of one lane (mixed replay: half of the
+// bytes of the items above 1 KB failed the second tier on the value count alone)
+typedef CoopWalkT<8192> CoopWalkHuge;
 
 // ---- cold paths kept out of line: the hot loop of k_encode_type has to fit the instruction caches ----
 GGR_DEVN bool cw_long_name_equals(const u8* in, u32 quote_pos, u32 end, const u8* pool, u32 off, u32 len) {
@@ -776,6 +780,18 @@ GGR_DEVN bool cw_timestamp(const u8* in, u32 pos, u32 end, i64* secs, i32* nanos
   StrIter it;
   it.init(in, pos, end);
   return parse_timestamp(it, secs, nanos) == GST_OK;
+}
+
+// A map key with \u escapes (what encoding/json writes for < > & in a key) or bytes the full scanner has to judge: decoded
+// length and node flags, false when the token is no valid string.  Out of line, full tiers only.
+GGR_DEVN bool cw_slow_key(const u8* in, u32 key_pos, u32 end, u32* dec_len, u32* flags) {
+  Rd r;
+  r.init(in, key_pos, end);
+  StrInfo si;
+  if (scan_string<false>(r, &si) != GST_OK) return false;
+  *dec_len = si.dec_len;
+  *flags = (si.flags & SF_ESCAPES) ? NF_ESC : 0u;
+  return true;
 }
 
 // Leaf value of field f at token t, every form this tier takes.  false: left to the next tier.  Out of line: the hot
@@ -1088,7 +1104,8 @@ GGR_DEV bool cw_type_item(SH& S, const Tables& T, u32 root_msg, const u8* in, u3
         u32 gf = 0, cls = CW_SKIP, aux = 0, hdr = 0, body = 0;
         FieldD f;
         bool in_list = false;
-        u32 key_pos = 0, key_end = 0, key_esc = 0;
+        u32 key_pos = 0, key_end = 0, key_esc = 0, key_dec = 0, key_flags = 0;
+        bool key_slow = false;
         bool is_ts = false;
         if (pc == CW_MSG || pc == CW_EMSG) {
           // member of a message: "key" : value
@@ -1170,15 +1187,16 @@ GGR_DEV bool cw_type_item(SH& S, const Tables& T, u32 root_msg, const u8* in, u3
           f = ggr_field(T, ed.field_first + 1u);  // the value field
           const u32 kt = cw_ldg(X.tok + i - 1u);
           const CwQ q0 = cw_q(X, K3_Q(kt)), q1 = cw_q(X, K3_Q(kt) + 1u);
-          if (q0.slow != q1.slow) ok = (CW_WHY(112), false);  // \u, control characters: the full scanner
           key_pos = K3_POS(kt);
           key_end = q1.pos;
           key_esc = (q1.esc - q0.esc) & 0xFFFFu;
+          key_slow = q0.slow != q1.slow;  // \u, control characters: the full scanner (full tiers; the first tier leaves the item)
+          if (key_slow && (!FULL || !cw_slow_key(in, key_pos, end, &key_dec, &key_flags))) ok = (CW_WHY(112), false);
           if (ok && r > (u32)S.first[p]) {  // Go emits map entries sorted by key; equal keys are an error
             const u32 pt = cw_ldg(X.tok + (u32)S.vtok[r - 1u] - 1u);
             const CwQ p0 = cw_q(X, K3_Q(pt)), p1 = cw_q(X, K3_Q(pt) + 1u);
-            if (p0.slow != p1.slow) ok = (CW_WHY(113), false);
-            else if (p0.esc == p1.esc && key_esc == 0u) ok = cw_plain_less(in, K3_POS(pt), p1.pos, key_pos, key_end);
+            if (p0.slow != p1.slow && !FULL) ok = (CW_WHY(113), false);
+            else if (p0.slow == p1.slow && !key_slow && p0.esc == p1.esc && key_esc == 0u) ok = cw_plain_less(in, K3_POS(pt), p1.pos, key_pos, key_end);
             else ok = cw_cmp_decoded(in, K3_POS(pt), key_pos, end) < 0;  // decoded bytes
           }
           in_list = true;
@@ -1208,7 +1226,7 @@ GGR_DEV bool cw_type_item(SH& S, const Tables& T, u32 root_msg, const u8* in, u3
           } else {
             // ENTRY { key = 1, value = 2 }: three IR nodes
             const u32 x = wp_atomic_add(&S.n_extra, 2u);
-            const u32 klen = key_end - key_pos - 1u - key_esc;  // a simple escape decodes 2 bytes to 1
+            const u32 klen = key_slow ? key_dec : key_end - key_pos - 1u - key_esc;  // a simple escape decodes 2 bytes to 1
             const u32 keypart = 1u + varint_size(klen) + klen;
             const u32 payload = keypart + f.tag_len + l.body;
             const FieldD mapf = ggr_field(T, gf);
@@ -1216,7 +1234,7 @@ GGR_DEV bool cw_type_item(SH& S, const Tables& T, u32 root_msg, const u8* in, u3
               ok = (CW_WHY(118), false);
             } else {
               node_store(ir, r, payload, GGR_NIL, GGR_NIL, 0, node_meta(N_ENTRY, 0, mapf.tag));
-              node_store(ir, n_rec + x, key_pos, klen, GGR_NIL, 0, node_meta(N_STR, key_esc ? (NF_ESC | NF_SIMPLE) : 0u, 0x0Au));
+              node_store(ir, n_rec + x, key_pos, klen, GGR_NIL, 0, node_meta(N_STR, key_slow ? key_flags : (key_esc ? (NF_ESC | NF_SIMPLE) : 0u), 0x0Au));
               node_store(ir, n_rec + x + 1u, l.a, l.b, GGR_NIL, 1, node_meta(l.type, l.flags, f.tag));
               aux = x;
               hdr = mapf.tag_len + varint_size(payload);  // offset of the key node within the entry
@@ -1287,7 +1305,11 @@ GGR_DEV bool cw_type_item(SH& S, const Tables& T, u32 root_msg, const u8* in, u3
           const u32 kt = cw_ldg(X.tok + i - 1u);
           const CwQ q0 = cw_q(X, K3_Q(kt)), q1 = cw_q(X, K3_Q(kt) + 1u);
           const u32 key_esc = (q1.esc - q0.esc) & 0xFFFFu;
-          const u32 key_pos = K3_POS(kt), klen = q1.pos - key_pos - 1u - key_esc;
+          const u32 key_pos = K3_POS(kt);
+          const bool kslow = q0.slow != q1.slow;  // judged in the type pass already: full tiers only
+          u32 kdec = 0, kflags = 0;
+          if (kslow && (!FULL || !cw_slow_key(in, key_pos, end, &kdec, &kflags))) S.bail = 1;
+          const u32 klen = kslow ? kdec : q1.pos - key_pos - 1u - key_esc;
           const u32 keypart = 1u + varint_size(klen) + klen;
           const FieldD mapf = ggr_field(T, gf);
           const MsgD ed = ggr_msg(T, (u32)mapf.child);
@@ -1301,7 +1323,7 @@ GGR_DEV bool cw_type_item(SH& S, const Tables& T, u32 root_msg, const u8* in, u3
           } else {
             const u32 eh = mapf.tag_len + varint_size(ent);
             node_store(ir, r, ent, GGR_NIL, GGR_NIL, 0, node_meta(N_ENTRY, 0, mapf.tag));
-            node_store(ir, n_rec + x, key_pos, klen, GGR_NIL, 0, node_meta(N_STR, key_esc ? (NF_ESC | NF_SIMPLE) : 0u, 0x0Au));
+            node_store(ir, n_rec + x, key_pos, klen, GGR_NIL, 0, node_meta(N_STR, kslow ? kflags : (key_esc ? (NF_ESC | NF_SIMPLE) : 0u), 0x0Au));
             node_store(ir, n_rec + x + 1u, payload, GGR_NIL, GGR_NIL, 1, node_meta(N_MSG, 0, vf.tag));
             S.aux[r] = (u16)x;
             h = eh + keypart + vf.tag_len + varint_size(payload);

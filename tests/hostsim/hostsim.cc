@@ -22,6 +22,8 @@
 
 int g_cw_why = 0;
 extern "C" int hs_cw_why() { return g_cw_why; }
+int g_coop_why = 0;
+extern "C" int hs_coop_why() { return g_coop_why; }
 struct HsSchema {
   ggr::CompiledSchema cs;
   uint8_t* blob;  // 16-byte aligned copy
@@ -263,7 +265,7 @@ static void walk_tok_body(void* p, u32 lane) {
 }
 static void walk_place_body(void* p, u32 lane) {
   WalkArgs* a = (WalkArgs*)p;
-  cw_place_item(*a->P, a->region, a->cap, CoopWalkBig::MAX_NODE);
+  cw_place_item(*a->P, a->region, a->cap, CoopWalkHuge::MAX_NODE);
 }
 static void walk_body(void* p, u32 lane) {
   WalkArgs* a = (WalkArgs*)p;
@@ -272,6 +274,11 @@ static void walk_body(void* p, u32 lane) {
 static void walk_body_full(void* p, u32 lane) {
   WalkArgs* a = (WalkArgs*)p;
   a->ok[lane] = cw_type_item<CoopWalkBig, true>(*a->SB, a->T, a->msg, a->in, a->start, a->end, a->region, a->ioff, a->cap, &a->res[lane]);
+}
+static CoopWalkHuge g_walk_huge;
+static void walk_body_huge(void* p, u32 lane) {
+  WalkArgs* a = (WalkArgs*)p;
+  a->ok[lane] = cw_type_item<CoopWalkHuge, true>(g_walk_huge, a->T, a->msg, a->in, a->start, a->end, a->region, a->ioff, a->cap, &a->res[lane]);
 }
 static void walk_emit_body(void* p, u32 lane) {
   WalkArgs* a = (WalkArgs*)p;
@@ -332,6 +339,11 @@ extern "C" int hs_encode_walk(void* h, int msg, const uint8_t* json, uint32_t n,
   if (!werr) werr = hw_run_warp(walk_body, &a);
   // what the first tier leaves goes to the second (all leaf forms, 1024 values, items of any size)
   if (!werr && !a.ok[0] && !getenv("HS_WALK_TIER1_ONLY")) werr = hw_run_warp(walk_body_full, &a);
+  // ... and what the second leaves (more than 1024 values) to the third
+  if (!werr && !a.ok[0] && !getenv("HS_WALK_TIER1_ONLY") && !getenv("HS_WALK_TIER2_ONLY")) {
+    memset(&g_walk_huge, 0xAB, sizeof g_walk_huge);
+    werr = hw_run_warp(walk_body_huge, &a);
+  }
   if (werr) {
     free(region);
     return 300 + werr;
@@ -486,6 +498,15 @@ static void coop_dec_size_body(void* p, u32 lane) {
   CoopDecArgs* a = (CoopDecArgs*)p;
   a->ok[lane] = coop_size_item(*a->S, a->cx, a->msg, a->start, a->end, a->tab, &a->n[lane], &a->size[lane]);
 }
+// second tier: tables of thousands of entries, saved in a pool (header of two U4, then the entries)
+static CoopSharedBig g_coop_big;
+static std::vector<U4> g_coop_pool;
+static u32 g_coop_toff[32];
+static void coop_dec_size_big_body(void* p, u32 lane) {
+  CoopDecArgs* a = (CoopDecArgs*)p;
+  a->ok[lane] = coop_size_item(g_coop_big, a->cx, a->msg, a->start, a->end, nullptr, &a->n[lane], &a->size[lane], g_coop_pool.data() + 2,
+                               reinterpret_cast<u32*>(g_coop_pool.data()), (u32)(g_coop_pool.size() / 2 - 1), &g_coop_toff[lane]);
+}
 static void coop_dec_write_body(void* p, u32 lane) {
   CoopDecArgs* a = (CoopDecArgs*)p;
   a->ws[lane] = coop_write_item(*a->E, a->cx, a->tab, a->n[0], a->dst, a->size[0]);
@@ -513,6 +534,20 @@ int hs_decode_coop(void* h, int msg, const uint8_t* wire, uint32_t n, uint32_t i
   if (werr) return 300 + werr;
   for (int l = 1; l < 32; l++)
     if (a.ok[l] != a.ok[0] || (a.ok[0] && (a.size[l] != a.size[0] || a.n[l] != a.n[0]))) return 310;
+  if (!a.ok[0] && !getenv("HS_COOP_TIER1_ONLY")) {  // what the first tier leaves goes to the second
+    g_coop_pool.assign(2 + 2 * (size_t)GGR_COOP_BIG_ENTRIES + 2 * 7, U4{0xCDCDCDCDu, 0xCDCDCDCDu, 0xCDCDCDCDu, 0xCDCDCDCDu});
+    memset(g_coop_pool.data(), 0, 32);
+    reinterpret_cast<u32*>(g_coop_pool.data())[0] = 7;  // not at the start of the pool
+    memset(&g_coop_big, 0xAB, sizeof g_coop_big);
+    werr = hw_run_warp(coop_dec_size_big_body, &a);
+    if (werr) return 300 + werr;
+    for (int l = 1; l < 32; l++)
+      if (a.ok[l] != a.ok[0] || (a.ok[0] && (a.size[l] != a.size[0] || a.n[l] != a.n[0] || g_coop_toff[l] != g_coop_toff[0]))) return 311;
+    if (a.ok[0]) {
+      if (g_coop_toff[0] != 7) return 312;
+      a.tab = g_coop_pool.data() + 2 + 2 * (size_t)g_coop_toff[0];
+    }
+  }
   if (!a.ok[0]) return 200;
   const uint32_t size = a.size[0];
   if (size > out_cap) return GST_NO_SPACE;

@@ -496,6 +496,34 @@ def test_mixed_replay_shapes(oracle, hsim):
         st, ej = hsim.decode(pn, w, 0, i % 16, (i * 7) % 16)
         assert rc == 0 and st == 0 and ej == oj, (pn, w.hex()[:300])
     assert walked > 150  # floats, bytes, quoted numbers, timestamps: the fused kernel (profiles/README.md)
+    # request side, large items: the three walker tiers (the third: up to 8192 values) against the oracle
+    huge = 0
+    for i in range(wl.n):
+        js = jb[int(wl.req_off[i]):int(wl.req_off[i + 1])]
+        if len(js) <= 20000 or len(js) > 64000:
+            continue
+        rn = names[int(wl.req_msg[i])]
+        rc, out = hsim.encode_walk(rn, js, i % 16, (i * 5) % 16)
+        assert rc in (0, 200), (rn, rc)
+        if rc == 0:
+            rc2, ow, _ = oracle.encode(rn, js)
+            assert rc2 == 0 and out == ow, (rn, len(js))
+            huge += 1
+    assert huge >= 5, huge
+    # reply side, both lock-step tiers (the second one: tables of up to 4096 entries saved in a pool) on every reply of
+    # the sample, the large ones included
+    taken = big = 0
+    for i in range(wl.n):
+        w = wb[int(wl.rep_off[i]):int(wl.rep_off[i + 1])]
+        pn = names[int(wl.rep_msg[i])]
+        rc, out = hsim.decode_coop(pn, w, 0, i % 16, (i * 5) % 16)
+        assert rc in (0, 200), (pn, rc)
+        if rc == 0:
+            rc2, oj, _ = oracle.decode(pn, w)
+            assert rc2 == 0 and out == oj, (pn, len(w))
+            taken += 1
+            big += len(w) > 6000
+    assert taken > wl.n // 3 and big >= 5, (taken, big)
 
 
 def test_decode_unsorted_maps(oracle, hsim):
