@@ -19,6 +19,9 @@
 // them on 32 fibers).
 #pragma once
 #include "ggr_decode.cuh"
+#ifndef COOP_WORD_COPY_MIN
+#define COOP_WORD_COPY_MIN 24u /* reply write kernel: 1.04 -> 1.02 ms against 12 */
+#endif
 #include "ggr_warp.cuh"
 
 // why the lock-step tier left an item: recorded by the host simulation only (tests/hostsim: hs_coop_why = source line)
@@ -67,8 +70,18 @@ struct CoopEnt {            // 32 bytes: saved between the passes as two 16-byte
 #define GGR_COOP_ROOT 0xFFFFu
 #define CE_CLASS(e) (((e).flags >> CF_CLASS_SHIFT) & 0xFu)
 
-#define GGR_COOP_LONG 96u
+#ifndef GGR_COOP_LONG
+#define GGR_COOP_LONG 96u /* plain strings of at least this many bytes are copied by the whole warp */
+#endif
+#ifndef GGR_COOP_LONG_MAX
 #define GGR_COOP_LONG_MAX 32u
+#endif
+#ifndef COOP_WIN_CACHE
+#define COOP_WIN_CACHE 0 /* 1: the scan keeps two 16-byte chunks in registers (measured: 1.76 -> 1.90 ms, not used) */
+#endif
+#ifndef COOP_COLD_LEAF
+#define COOP_COLD_LEAF 0 /* 1: float / timestamp sizing as a call (measured: 1.85 -> 1.90 ms, not used) */
+#endif
 #define GGR_COOP_DIRTY_MAX 64u
 template <int NE>
 struct CoopSharedT {
@@ -156,6 +169,33 @@ GGR_DEV bool coop_wire_zero(const u8* b, u32 pos, u32 lim, u32 wt, bool* ok) {
 
 // coop_window / coop_header (a field header out of one 8-byte window): ggr_decode.cuh, shared with the slow walk
 
+// The scan's window with a memory: the 16-byte chunk that holds `pos` and the one behind it stay in registers, so a
+// run of small fields (a handful of bytes each: the usual reply) costs one round trip to the L2 per chunk instead of
+// one per field.  Returns what coop_window returns: the 8 bytes at pos, bytes from end_al on read as zero.
+struct CoopWinCache {
+  u32 base;  // position of chunk a (a multiple of 16), 0xFFFFFFFF: nothing held
+  U4 a, b;
+  GGR_DEV u64 get(const u8* in, u32 pos, u32 end_al) {
+    const u32 c = pos & ~15u;
+    if (c != base) {
+      base = c;
+      a = ggr_ld16(in + c);
+      if (c + 16u < end_al) b = ggr_ld16(in + c + 16u);
+      else b.x = b.y = b.z = b.w = 0u;
+    }
+    const u32 k = (pos >> 2) & 3u, sh = (pos & 3u) * 8u;
+    const u32 w0 = k == 0u ? a.x : k == 1u ? a.y : k == 2u ? a.z : a.w;
+    const u32 w1 = k == 0u ? a.y : k == 1u ? a.z : k == 2u ? a.w : b.x;
+    const u32 w2 = k == 0u ? a.z : k == 1u ? a.w : k == 2u ? b.x : b.y;
+#if defined(__CUDA_ARCH__)
+    const u32 lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+#else
+    const u32 lo = sh ? (w0 >> sh) | (w1 << (32u - sh)) : w0, hi = sh ? (w1 >> sh) | (w2 << (32u - sh)) : w1;
+#endif
+    return (u64)lo | ((u64)hi << 32);
+  }
+};
+
 // R1, one lane: scan the top-level fields of message entry `me` and append its children.
 template <class SH>
 GGR_DEV void coop_scan_message(SH& S, const DecCtx& cx, u32 me) {
@@ -177,11 +217,20 @@ GGR_DEV void coop_scan_message(SH& S, const DecCtx& cx, u32 me) {
   u32 prev = 0xFFFFu;  // previous child entry
   bool any = false;
   const u32 end_al = (lim + 15u) & ~15u;  // the item's bytes are readable up to the end of their last 16-byte chunk
+#if COOP_WIN_CACHE
+  CoopWinCache cw;
+  cw.base = 0xFFFFFFFFu;
+#endif
   while (pos < lim) {
     // the field header out of one 8-byte window; what does not fit it is decoded byte by byte
     u32 wtag = 0, wtl = 0, wbody = 0, wvend = 0;
     bool wzero = false;
-    const bool fast = coop_header(coop_window(in, pos, end_al), pos, &wtag, &wtl, &wbody, &wvend, &wzero) && wvend <= lim && wbody <= lim;
+#if COOP_WIN_CACHE
+    const u64 win = cw.get(in, pos, end_al);
+#else
+    const u64 win = coop_window(in, pos, end_al);
+#endif
+    const bool fast = coop_header(win, pos, &wtag, &wtl, &wbody, &wvend, &wzero) && wvend <= lim && wbody <= lim;
     u64 tag = wtag;
     if (fast) pos += wtl;
     else if (!br_varint(in, pos, lim, &tag)) { COOP_BAIL(S); return; }
@@ -310,11 +359,15 @@ GGR_DEV void coop_plain_masks(SH& S, const u8* in, u32 start, u32 end) {
   const u32 lt = (1u << lane) - 1u;
   const u32 nchunks = (end + 15u) >> 4;
   u32 base = 0;
+  U4 vn;  // the next round's chunk is requested one round ahead
+  vn.x = vn.y = vn.z = vn.w = 0u;
+  if (lane < nchunks) vn = ggr_ld16(in + (lane << 4));
   for (u32 cb = 0; cb < nchunks; cb += 32) {
     const u32 ci = cb + lane;
     u32 D = 0;
+    const U4 v = vn;
+    if (ci + 32u < nchunks) vn = ggr_ld16(in + ((ci + 32u) << 4));
     if (ci < nchunks) {
-      const U4 v = ggr_ld16(in + (ci << 4));
       D = coop_pack4(coop_dirty_flags(v.x)) | (coop_pack4(coop_dirty_flags(v.y)) << 4) | (coop_pack4(coop_dirty_flags(v.z)) << 8) |
           (coop_pack4(coop_dirty_flags(v.w)) << 12);
     }
@@ -390,6 +443,14 @@ GGR_DEV int coop_leaf_value(W& w, const DecCtx& cx, const CoopEnt& e, const Fiel
   return scalar_value<W, true>(w, cx, r, e.vend, f.kind, f.child, false, &z);
 }
 
+// text size of a leaf value whose formatter is large (floats, timestamps); -1: the value is refused
+GGR_DEVN i32 coop_leaf_size_cold(const DecCtx& cx, const CoopEnt& e, const FieldD& f) {
+  Cnt c;
+  c.pos = 0;
+  if (coop_leaf_value(c, cx, e, f) != GST_OK) return -1;
+  return (i32)c.pos;
+}
+
 // ---- strings that hold quotes, backslashes, control or non-ASCII bytes: one byte per lane ----
 // JSON text length of one string byte (protojson): 1, 2 (\" \\ \b \f \n \r \t) or 6 (\u00XX)
 GGR_DEV u32 coop_esc_len(u32 c) {
@@ -400,15 +461,19 @@ GGR_DEV u32 coop_esc_len(u32 c) {
 GGR_DEV u32 coop_dirty_size(const u8* in, u32 s, u32 e, bool* ok) {
   const u32 lane = wp_lane();
   u32 total = 0, carry = 0, bad = 0;
+  u32 cn = s + lane < e ? in[s + lane] : 0u;  // the next round's bytes are requested one round ahead
   for (u32 p = s; p < e; p += 32) {
     const u32 pos = p + lane;
     const bool valid = pos < e;
-    const u32 c = valid ? in[pos] : 0u;
+    const u32 c = cn;
+    cn = pos + 32u < e ? in[pos + 32u] : 0u;
     const u32 l = valid ? coop_esc_len(c) : 0u;
     total += wp_popc(WP_BALLOT(valid)) + wp_popc(WP_BALLOT(l == 2u)) + 5u * wp_popc(WP_BALLOT(l == 6u));
     const u32 HI = WP_BALLOT(c >= 0x80u);
     if (HI | carry) {  // UTF-8: the continuation bytes the lead bytes announce == the ones present
-      const u32 c1 = pos + 1u < e ? in[pos + 1u] : 0u;
+      // the byte behind this lane's: the neighbour's, lane 31 takes lane 0's byte of the next round (0 past the end)
+      const u32 nb = WP_SHFL(c, (lane + 1u) & 31u), n0 = WP_SHFL(cn, 0);
+      const u32 c1 = lane == 31u ? n0 : nb;
       const bool lead = c >= 0xC0u;
       const u32 LD = WP_BALLOT(lead);
       const u32 L2 = WP_BALLOT(lead && c < 0xE0u), L3 = WP_BALLOT(lead && c >= 0xE0u && c < 0xF0u), L4 = WP_BALLOT(lead && c >= 0xF0u);
@@ -427,10 +492,12 @@ GGR_DEV u32 coop_dirty_size(const u8* in, u32 s, u32 e, bool* ok) {
 GGR_DEV void coop_dirty_write(const u8* in, u32 s, u32 e, u8* d) {
   const u32 lane = wp_lane();
   u32 base = 0;
+  u32 cn = s + lane < e ? in[s + lane] : 0u;  // the next round's bytes are requested one round ahead
   for (u32 p = s; p < e; p += 32) {
     const u32 pos = p + lane;
     const bool valid = pos < e;
-    const u32 c = valid ? in[pos] : 0u;
+    const u32 c = cn;
+    cn = pos + 32u < e ? in[pos + 32u] : 0u;
     const u32 l = valid ? coop_esc_len(c) : 0u;
     u32 tot;
     const u32 o = base + WP_EXCL_SCAN(l, &tot);
@@ -449,30 +516,6 @@ GGR_DEV void coop_dirty_write(const u8* in, u32 s, u32 e, u8* d) {
   }
 }
 
-// all lanes: copy len bytes in[src..) -> d[0..), 4 bytes per lane and step once d is 4-byte aligned
-GGR_DEV void coop_copy_words(const u8* in, u32 src, u8* d, u32 len) {
-  const u32 lane = wp_lane();
-  u32 head = (4u - (wp_align_pad(d) & 3u)) & 3u;
-  if (head > len) head = len;
-  if (lane < head) d[lane] = in[src + lane];
-  src += head;
-  d += head;
-  len -= head;
-  const u32 words = len >> 2;
-  const u32 sh = (src & 3u) * 8u;
-  const u8* sa = in + (src & ~3u);
-  for (u32 k = lane; k < words; k += 32) {
-    u32 lo = ggr_ld4(sa + 4u * k);
-    u32 v = lo;
-    if (sh) {
-      u32 hi = ggr_ld4(sa + 4u * k + 4u);
-      v = (lo >> sh) | (hi << (32u - sh));
-    }
-    ggr_st4(d + 4u * k, v);
-  }
-  const u32 tail = len & 3u;
-  if (lane < tail) d[4u * words + lane] = in[src + 4u * words + lane];
-}
 // all lanes: standard base64 (padded) of in[src, src + len) -> d[0..): 3 bytes per lane and step
 GGR_DEV void coop_base64(const u8* in, u32 src, u32 len, u8* d) {
   const u32 lane = wp_lane();
@@ -545,6 +588,15 @@ GGR_DEV void coop_size_leaf(SH& S, const DecCtx& cx, u32 ei, bool have_masks) {
       return;
     }
     n += c.pos;
+  } else if (COOP_COLD_LEAF && (cls == DC_FLOAT || cls == DC_TS)) {
+    // shortest-digits floats and timestamps: out of line, so that the size kernel's hot loop stays small (the kernel
+    // waited for instructions on 0.94 of its issue slots, profiles/ncu_r2_final_lockstep_kernels_151552items.csv)
+    const i32 v = coop_leaf_size_cold(cx, e, f);
+    if (v < 0) {
+      COOP_BAIL(S);
+      return;
+    }
+    n += (u32)v;
   } else {
     Cnt c;
     c.pos = 0;
@@ -626,8 +678,8 @@ GGR_DEV int coop_write_entry(CoopStage& E, const DecCtx& cx, const CoopEnt& e, u
     if (cx.flags & GGR_F_COMMA_SPACE) w.put1(' ');
   }
   if (!(e.flags & CF_ARR_ELEM) || (e.flags & CF_ARR_FIRST)) {
-    const u8* nm = cx.T.pool + f.name_off;
-    for (u32 j = 0; j < f.name_len; j++) w.put1(nm[j]);
+    coop_copy_bytes(B + w.pos, cx.T.pool + f.name_off, f.name_len);
+    w.pos += f.name_len;
   }
   if (e.flags & CF_ARR_FIRST) w.put1('[');
   const u32 endpos = e.off + e.size;
@@ -656,8 +708,7 @@ GGR_DEV int coop_write_entry(CoopStage& E, const DecCtx& cx, const CoopEnt& e, u
       }
     }
     if (!handed) {
-      const u8* src = cx.in + e.body;
-      for (u32 j = 0; j < len; j++) B[w.pos + j] = src[j];
+      coop_copy_bytes(B + w.pos, cx.in + e.body, len);
     }
     w.pos += len;
     w.put1('"');
@@ -834,8 +885,25 @@ GGR_DEV int coop_write_item(CoopStage& E, const DecCtx& cx, const U4* tab, u32 n
     E.bad = 0;
   }
   WP_SYNC();
+#ifndef COOP_WRITE_PIPE
+#define COOP_WRITE_PIPE 0 /* 1: the next round's saved entry is requested one round ahead (measured: 1.05 -> 1.08 ms, not used) */
+#endif
+  U4 an, bn;
+  an.x = an.y = an.z = an.w = bn.x = bn.y = bn.z = bn.w = 0u;
+  if (COOP_WRITE_PIPE && lane < n) {
+    an = tab[2 * lane];
+    bn = tab[2 * lane + 1];
+  }
   for (u32 i = lane; i < n; i += 32) {
+#if COOP_WRITE_PIPE
+    const U4 a = an, b = bn;
+    if (i + 32u < n) {
+      an = tab[2 * (i + 32u)];
+      bn = tab[2 * (i + 32u) + 1];
+    }
+#else
     const U4 a = tab[2 * i], b = tab[2 * i + 1];
+#endif
     CoopEnt e;
     e.vpos = a.x; e.vend = a.y; e.body = a.z; e.size = a.w;
     e.off = b.x; e.parent = (u16)b.y; e.next = (u16)(b.y >> 16);
@@ -853,8 +921,7 @@ GGR_DEV int coop_write_item(CoopStage& E, const DecCtx& cx, const U4* tab, u32 n
       const u32 len = E.llen[k] & 0x3FFFFFFFu;
       if (E.llen[k] & 0x80000000u) coop_dirty_write(cx.in, E.lsrc[k], E.lsrc[k] + len, d);
       else if (E.llen[k] & 0x40000000u) coop_base64(cx.in, E.lsrc[k], len, d);
-      else
-        for (u32 j = lane; j < len; j += 32) d[j] = cx.in[E.lsrc[k] + j];
+      else coop_copy_words(cx.in, E.lsrc[k], d, len);
     }
     WP_SYNC();
     wp_copy_out(E.buf, dst - pad, pad, size);

@@ -21,6 +21,9 @@
 // owns the error semantics).
 #pragma once
 #include "ggr_encode.cuh"
+#ifndef COOP_WORD_COPY_MIN
+#define COOP_WORD_COPY_MIN 8u /* request emitter: 0.78 -> 0.75 ms against 12 */
+#endif
 #include "ggr_warp.cuh"
 
 #define CE_MAX_DEPTH 24
@@ -1205,8 +1208,12 @@ GGR_DEV bool ce_parse_item(SH& S, const CeLut& lut, const Tables& T, u32 root_ms
 // write nodes independently (one lane per node); long plain strings are then copied by the whole
 // warp, 128 bytes per step.
 // ------------------------------------------------------------------------------------------------
-#define CE_LONG_STR 96u
+#ifndef CE_LONG_STR
+#define CE_LONG_STR 128u /* plain strings of at least this many bytes are copied by the whole warp (0.78 -> 0.75 ms against 96) */
+#endif
+#ifndef CE_LONG_MAX
 #define CE_LONG_MAX 32u
+#endif
 #define CE_STAGE 8192u /* items with more wire bytes than this: per-thread emitter */
 #ifndef CE_STAGE_BUF
 /* the emitter's staging buffer; larger items (up to CE_STAGE and beyond) are written in place.  4864 + the lists = 5.3 KB per
@@ -1229,13 +1236,12 @@ struct
 // STAGED: byte position p of the item lands in the staging buffer (plain shared-memory stores); otherwise - items too
 // large to stage - at G[p], the destination itself shifted so that the same positions apply (two instances: a pointer
 // that may be either makes every store a generic one, 1.11 -> 1.67 ms on configs[2])
+// nd, off: node i and its offset, loaded by the caller (one round ahead: CE_EMIT_PIPE)
 template <bool STAGED>
-GGR_DEV void ce_emit_node(CoopEmit& E, u8* G, const u8* in, u32 end, const u8* ir, const u32* ioff, u32 i, u32 pad) {
+GGR_DEV void ce_emit_node(CoopEmit& E, u8* G, const u8* in, u32 end, const u8* ir, const u32* ioff, u32 i, u32 pad, const U4 nd, const u32 off) {
   u8* const B = STAGED ? E.buf : G;
-  const U4 nd = node_load(ir, i);
   const u32 type = nd.w & 0xFu, flags = (nd.w >> 4) & 0xFu, tag = nd.w >> 8;
   if (type == N_SKIP || type == N_MAP || (type == N_LIST && !(flags & NF_PACKED))) return;
-  const u32 off = ioff[i];
   if (off == 0xFFFFFFFFu) return;  // written together with its parent (Timestamp fields)
   Sw w;
   w.init(B, pad + off);
@@ -1285,8 +1291,7 @@ GGR_DEV void ce_emit_node(CoopEmit& E, u8* G, const u8* in, u32 end, const u8* i
           }
         }
         if (!handed) {
-          const u8* src = in + nd.x + 1u;
-          for (u32 j = 0; j < nd.y; j++) B[w.pos + j] = src[j];
+          coop_copy_bytes(B + w.pos, in + nd.x + 1u, nd.y);
         }
       }
       break;
@@ -1355,6 +1360,35 @@ GGR_DEV void ce_unescape_coop(const u8* in, u32 src, u8* d, u32 dec_len) {
 
 // One item, all 32 lanes: size bytes to dst.  Items that fit the staging buffer are assembled there and leave with one
 // bulk copy; larger ones (second tier of the walker: tens of KB of wire) are written in place.
+#ifndef CE_EMIT_PIPE
+#define CE_EMIT_PIPE 1 /* the next round's node and offset are requested while this round's node is written (0: A/B builds) */
+#endif
+// one lane per node, nodes 1 .. n_nodes - 1
+#if CE_EMIT_PIPE
+#define CE_EMIT_LOOP(STG, GP)                                                             \
+  do {                                                                                    \
+    U4 ndn;                                                                               \
+    ndn.x = ndn.y = ndn.z = ndn.w = 0u;                                                   \
+    u32 offn = 0;                                                                         \
+    if (1u + lane < n_nodes) {                                                            \
+      ndn = node_load(ir, 1u + lane);                                                     \
+      offn = ioff[1u + lane];                                                             \
+    }                                                                                     \
+    for (u32 i = 1 + lane; i < n_nodes; i += 32) {                                        \
+      const U4 nd_ = ndn;                                                                 \
+      const u32 off_ = offn;                                                              \
+      if (i + 32u < n_nodes) {                                                            \
+        ndn = node_load(ir, i + 32u);                                                     \
+        offn = ioff[i + 32u];                                                             \
+      }                                                                                   \
+      ce_emit_node<STG>(E, GP, in, end, ir, ioff, i, pad, nd_, off_);                     \
+    }                                                                                     \
+  } while (0)
+#else
+#define CE_EMIT_LOOP(STG, GP) \
+  for (u32 i = 1 + lane; i < n_nodes; i += 32) ce_emit_node<STG>(E, GP, in, end, ir, ioff, i, pad, node_load(ir, i), ioff[i])
+#endif
+
 GGR_DEV void ce_emit_item(CoopEmit& E, const u8* in, u32 end, const u8* ir, const u32* ioff, u32 n_nodes, u8* dst, u32 size) {
   const u32 lane = wp_lane();
   const u32 pad = wp_align_pad(dst);
@@ -1364,31 +1398,27 @@ GGR_DEV void ce_emit_item(CoopEmit& E, const u8* in, u32 end, const u8* ir, cons
   if (lane == 0) E.n = 0;
   WP_SYNC();
   if (staged) {
-    for (u32 i = 1 + lane; i < n_nodes; i += 32) ce_emit_node<true>(E, nullptr, in, end, ir, ioff, i, pad);
+    CE_EMIT_LOOP(true, nullptr);
   } else {
-    for (u32 i = 1 + lane; i < n_nodes; i += 32) ce_emit_node<false>(E, dst - pad, in, end, ir, ioff, i, pad);
+    CE_EMIT_LOOP(false, dst - pad);
   }
   WP_SYNC();
   const u32 nl = E.n < CE_LONG_MAX ? E.n : CE_LONG_MAX;
   if (staged) {
     for (u32 k = 0; k < nl; k++) {
-      const u8* src = in + E.src[k];
       u8* d = E.buf + E.dst[k];
       const u32 len = E.len[k];
       if (len & 0x80000000u) ce_unescape_coop(in, E.src[k], d, len & 0x7FFFFFFFu);
-      else
-        for (u32 j = lane; j < len; j += 32) d[j] = src[j];
+      else coop_copy_words(in, E.src[k], d, len);
     }
     WP_SYNC();
     wp_copy_out(E.buf, dst - pad, pad, size);
   } else {
     for (u32 k = 0; k < nl; k++) {
-      const u8* src = in + E.src[k];
       u8* d = dst - pad + E.dst[k];
       const u32 len = E.len[k];
       if (len & 0x80000000u) ce_unescape_coop(in, E.src[k], d, len & 0x7FFFFFFFu);
-      else
-        for (u32 j = lane; j < len; j += 32) d[j] = src[j];
+      else coop_copy_words(in, E.src[k], d, len);
     }
   }
 }

@@ -225,6 +225,7 @@ struct ggr_engine {
   cudaStream_t s_in[2] = {nullptr, nullptr}, s_out[2] = {nullptr, nullptr};
   int n_slots = 4;
   int64_t chunk_items = 8192;
+  bool chunk_ramp = true;  // short chunks at both ends of a batch (GGR_CHUNK_RAMP=0: off)
   uint64_t chunk_bytes = 32ull << 20;
   // per-kernel timing
   bool profiling = false;
@@ -421,6 +422,7 @@ int ggr_engine_create(const ggr_config* cfg, ggr_engine** out) {
     long long v = atoll(nc);
     if (v >= 128) e->chunk_items = v;
   }
+  if (const char* nc = getenv("GGR_CHUNK_RAMP")) e->chunk_ramp = nc[0] != '0';
   if (const char* nc = getenv("GGR_CHUNK_BYTES")) {
     long long v = atoll(nc);
     if (v >= (1 << 16)) e->chunk_bytes = (uint64_t)v;
@@ -1104,22 +1106,38 @@ static int run_host(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, 
   const int64_t CH = e->chunk_items;
   const uint64_t total_in = in_off[n] - in_off[0];
   std::vector<int64_t> starts;
-  if (total_in <= e->chunk_bytes * (uint64_t)((n + CH - 1) / CH)) {
-    for (int64_t i = 0; i < n; i += CH) starts.push_back(i);  // item count alone decides
-  } else {
-    int64_t i = 0;
-    while (i < n) {
-      starts.push_back(i);
-      int64_t hi = i + CH < n ? i + CH : n;
-      // first item index in (i, hi] whose prefix exceeds the byte budget
-      const uint64_t lim = in_off[i] + e->chunk_bytes;
-      int64_t lo = i + 1;
+  {
+    // [i, return value): at most max_items items and about max_bytes of input (binary search on the offsets)
+    auto take = [&](int64_t i, int64_t stop, int64_t max_items, uint64_t max_bytes) -> int64_t {
+      int64_t hi = i + max_items < stop ? i + max_items : stop;
+      if (in_off[hi] - in_off[i] <= max_bytes) return hi;
+      const uint64_t lim = in_off[i] + max_bytes;
+      int64_t lo = i + 1;  // first item index in (i, hi] whose prefix exceeds the byte budget
       while (lo < hi) {
         int64_t mid = (lo + hi) / 2;
         if (in_off[mid] > lim) hi = mid;
         else lo = mid + 1;
       }
-      i = lo;
+      return lo;
+    };
+    // A batch of several chunks starts and ends with short ones (a quarter, then half a chunk): the output link idles
+    // until the first chunk's kernels are done and the input link idles while the last chunk drains, and both waits
+    // shrink with the chunk (profiles/README.md, host pipeline trace).
+    const bool ramp = e->chunk_ramp && n >= 4 * CH && CH >= 512;
+    const int64_t tail0 = ramp ? n - (CH / 2 + CH / 4) : n, tail1 = ramp ? n - CH / 4 : n;
+    int64_t i = 0;
+    while (i < n) {
+      starts.push_back(i);
+      const size_t k = starts.size();
+      int64_t items = CH, stop = tail0;
+      uint64_t bytes = e->chunk_bytes;
+      if (ramp && k <= 2) {
+        items = k == 1 ? CH / 4 : CH / 2;
+        bytes = k == 1 ? bytes / 4 : bytes / 2;
+      }
+      if (i >= tail1) stop = n;
+      else if (i >= tail0) stop = tail1;
+      i = take(i, stop, items, bytes);
     }
   }
   starts.push_back(n);

@@ -245,6 +245,68 @@ struct Sw {
   GGR_DEV void finish() {}
 };
 
+// all lanes: copy len bytes in[src..) -> d[0..), 4 bytes per lane and step once d is 4-byte aligned
+GGR_DEV void coop_copy_words(const u8* in, u32 src, u8* d, u32 len) {
+  const u32 lane = wp_lane();
+  u32 head = (4u - (u32)((uintptr_t)d & 3u)) & 3u;
+  if (head > len) head = len;
+  const u8* s = in + src;
+  if (lane < head) d[lane] = s[lane];
+  s += head;
+  d += head;
+  len -= head;
+  const u32 words = len >> 2;
+  const u32 mis = (u32)((uintptr_t)s & 3u), sh = mis * 8u;
+  const u8* sa = s - mis;
+  for (u32 k = lane; k < words; k += 32) {
+    u32 lo = ggr_ld4(sa + 4u * k);
+    u32 v = lo;
+    if (sh) {
+      u32 hi = ggr_ld4(sa + 4u * k + 4u);
+      v = (lo >> sh) | (hi << (32u - sh));
+    }
+    ggr_st4(d + 4u * k, v);
+  }
+  const u32 tail = len & 3u;
+  if (lane < tail) d[4u * words + lane] = s[4u * words + lane];
+}
+
+// One lane: len bytes of read-only data at s to d, four at a time - head bytes until d is word aligned, then aligned
+// word loads of the source brought into place by a funnel shift and one word store each (the byte loop was 28 % of
+// the reply write kernel's instructions and 57 % of the request emitter's, profiles/README.md).  A source word is only loaded
+// when it holds at least one byte of [s, s + len).
+#ifndef COOP_WORD_COPY_MIN
+#define COOP_WORD_COPY_MIN 12u /* shorter runs: byte by byte */
+#endif
+GGR_DEV void coop_copy_bytes(u8* d, const u8* s, u32 len) {
+  if (len >= COOP_WORD_COPY_MIN) {
+    const u32 head = (4u - (u32)((uintptr_t)d & 3u)) & 3u;
+    for (u32 j = 0; j < head; j++) d[j] = s[j];
+    d += head;
+    s += head;
+    len -= head;
+    const u32 mis = (u32)((uintptr_t)s & 3u), sh = mis * 8u;
+    const u8* sa = s - mis;
+    const u32 nw = len >> 2;
+    u32 lo = ggr_ld4(sa);
+    for (u32 i = 0; i < nw; i++) {
+      const u32 hi = (mis != 0u || i + 1u < nw) ? ggr_ld4(sa + 4u * (i + 1u)) : 0u;
+#if defined(__CUDA_ARCH__)
+      const u32 x = __funnelshift_r(lo, hi, sh);
+#else
+      const u32 x = sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
+#endif
+      ggr_st4(d + 4u * i, x);
+      lo = hi;
+    }
+    d += 4u * nw;
+    s += 4u * nw;
+    len -= 4u * nw;
+  }
+  for (u32 j = 0; j < len; j++) d[j] = s[j];
+}
+
+
 
 GGR_DEV u32 wp_align_pad(const u8* dst) {  // dst address & 15
 #if defined(__CUDA_ARCH__)

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--file", default="")
     ap.add_argument("--items", type=int, default=1)
     ap.add_argument("--top", type=int, default=60)
+    ap.add_argument("--section", default="", help="substring of the mangled name (object side) when KERNEL is a regex or matches several instances")
     ap.add_argument("--inner", action="store_true", help="attribute to the innermost frame (the line itself) instead of the outermost one in --file")
     a = ap.parse_args()
     tmp = tempfile.mkdtemp()
@@ -38,7 +39,7 @@ def main():
     fresh = False
     for ln in dis:
         if ln.startswith("\t.section") or ln.startswith("//-----"):
-            inside = (".text." in ln) and (a.kernel in ln)
+            inside = (".text." in ln) and ((a.section or a.kernel) in ln)
             continue
         if not inside:
             continue
