@@ -78,6 +78,15 @@ GGR_DEV CwQ cw_q(const CwIndex& X, u32 k) {
   CwQ q = {a & 0xFFFFu, a >> 16, b};
   return q;
 }
+// Key of the member whose value is token i (the token in front of it is the key's string): position of the key's text
+// | length << 16 | bit 31 = "a plain key" (no escapes, no bytes for the full scanner, shorter than 32 768 bytes)
+GGR_DEV u32 cw_key_pack(const CwIndex& X, u32 i) {
+  const u32 kt = cw_ldg(X.tok + i - 1u);
+  const CwQ q0 = cw_q(X, K3_Q(kt)), q1 = cw_q(X, K3_Q(kt) + 1u);
+  const u32 kp = K3_POS(kt), len = (q1.pos - kp - 1u) & 0xFFFFu;
+  const bool plain = K3_KIND(kt) == K3_STR && q0.slow == q1.slow && q0.esc == q1.esc && len < 0x8000u;
+  return plain ? (((kp + 1u) & 0xFFFFu) | (len << 16) | 0x80000000u) : 0u;
+}
 GGR_DEV u32 cw_rec_off(u32 n_tok) { return (16u + 4u * n_tok + 15u) & ~15u; }
 
 // second class table of the tokenizer: which structural character
@@ -528,6 +537,9 @@ enum {
   CW_LEAF = 5, CW_ELEAF = 6, CW_SKIP = 7                            // ELEAF: map entry with a scalar value; SKIP: null
 };
 
+#ifndef CW_TYPE_PRE
+#define CW_TYPE_PRE 0 /* 1: token, key and string quote entries of every record fetched with full lanes before the level pass (measured: 1.52 -> 1.63 ms, not used) */
+#endif
 template <int MN>
 struct CoopWalkT {
   static const u32 MAX_NODE = MN;
@@ -541,11 +553,17 @@ struct CoopWalkT {
   u8 hdr[MN];      // containers: bytes in front of the children's payload (leaves: tag length until closed)
   u32 body[MN];    // W3: containers: oneof mask, leaves: full size; W4: containers: payload; W5: absolute offset
   u32 ssz[MN];     // W3: containers: mask of fields seen; W4: sizes by slot, then offsets within the parent
+  // W3 prologue (first two tiers): the value's token and its member key, fetched for ALL records with full lanes before
+  // the level-by-level pass, whose lanes then start at the key's text instead of three dependent loads further up
+  static const bool PRE = CW_TYPE_PRE && MN <= 1024;
+  u32 tokw[PRE ? MN : 1];   // token of the value
+  u32 kinfo[PRE ? MN : 1];  // cw_key_pack of the member's key (0: no key or not a plain one)
+  u32 vinfo[PRE ? MN : 1];  // string values: cw_str_pack of the value
   u32 lvl_beg[CW_LEVELS + 2], lvl_cur[CW_LEVELS + 2];
   u32 bail, n_extra, cap;
 };
-typedef CoopWalkT<256> CoopWalk;       // first tier: 5.9 KB per warp
-typedef CoopWalkT<1024> CoopWalkBig;  // second tier: 18.6 KB per warp (large items, every leaf form)
+typedef CoopWalkT<256> CoopWalk;       // first tier: 8.9 KB per warp
+typedef CoopWalkT<1024> CoopWalkBig;  // second tier: 30.6 KB per warp (large items, every leaf form)
 // third tier: request items of thousands of values (a 60 KB list of numbers holds 8 000); 22 bytes per value = 180 KB = one
 // warp per SM.  Such an item costs the per-thread parser tens of milliseconds of one lane (mixed replay: half of the
 // bytes of the items above 1 KB failed the second tier on the value count alone)
@@ -900,15 +918,23 @@ GGR_DEVN bool cw_leaf_rare(const Tables& T, const CwIndex& X, const u8* in, u32 
 // The common leaves inline: strings sized in O(1) from the quote table, plain integer literals, bools.
 // FULL = false (the first tier of k_encode_type): nothing else - the kernel stays small and spill-free; FULL = true (second
 // tier, run over what the first leaves): every other form through cw_leaf_rare.
+// String token t by its two quote entries: raw length | simple escapes << 16 | bit 31 = "no bytes for the full scanner"
+// (0 when the counts do not fit: such a string takes the full scanner's path)
+GGR_DEV u32 cw_str_pack(const CwIndex& X, u32 t) {
+  const CwQ q0 = cw_q(X, K3_Q(t)), q1 = cw_q(X, K3_Q(t) + 1u);
+  const u32 nesc = (q1.esc - q0.esc) & 0xFFFFu, raw = (q1.pos - K3_POS(t) - 1u) & 0xFFFFu;
+  return (q0.slow == q1.slow && nesc < 0x8000u) ? (raw | (nesc << 16) | 0x80000000u) : 0u;
+}
+// vinf: cw_str_pack(X, t) when have_vinf (fetched by the prologue of W3), else computed here
 template <bool FULL>
-GGR_DEV bool cw_leaf(const Tables& T, const CwIndex& X, const u8* in, u32 end, const FieldD& f, u32 t, CwLeaf* l) {
+GGR_DEV bool cw_leaf(const Tables& T, const CwIndex& X, const u8* in, u32 end, const FieldD& f, u32 t, CwLeaf* l, u32 vinf = 0, bool have_vinf = false) {
   const u32 k = K3_KIND(t), pos = K3_POS(t);
   if (f.kind == GK_STRING) {
     if (k != K3_STR) return false;
-    const CwQ q0 = cw_q(X, K3_Q(t)), q1 = cw_q(X, K3_Q(t) + 1u);
-    if (q0.slow != q1.slow) return FULL ? cw_leaf_rare(T, X, in, end, f, t, l) : false;  // \u escapes, control characters
-    const u32 nesc = (q1.esc - q0.esc) & 0xFFFFu;
-    const u32 len = q1.pos - pos - 1u - nesc;  // a simple escape decodes 2 bytes to 1
+    if (!have_vinf) vinf = cw_str_pack(X, t);
+    if (!(vinf >> 31)) return FULL ? cw_leaf_rare(T, X, in, end, f, t, l) : false;  // \u escapes, control characters
+    const u32 nesc = (vinf >> 16) & 0x7FFFu;
+    const u32 len = (vinf & 0xFFFFu) - nesc;  // a simple escape decodes 2 bytes to 1
     l->type = N_STR;
     l->a = pos;
     l->b = len;
@@ -1074,6 +1100,13 @@ GGR_DEV bool cw_type_item(SH& S, const Tables& T, u32 root_msg, const u8* in, u3
     S.par[pos] = pd == CW_NONE ? (u16)CW_NONE : S.slot[pd];
     // the first child of a container is the next record of the document
     if (r + 1u < n_rec && (u32)S.aux[r + 1u] == r) S.first[pos] = S.slot[r + 1u];
+    if (SH::PRE) {  // full lanes, every record's chain of loads in flight at once
+      const u32 i = S.gfield[r];
+      const u32 t = cw_ldg(X.tok + i);
+      S.tokw[pos] = t;
+      S.kinfo[pos] = (K3_V(t) && i != 0u) ? cw_key_pack(X, i) : 0u;
+      S.vinfo[pos] = K3_KIND(t) == K3_STR ? cw_str_pack(X, t) : 0u;
+    }
   }
   WP_SYNC();
   // ---- W3: types, top-down ----
@@ -1098,7 +1131,7 @@ GGR_DEV bool cw_type_item(SH& S, const Tables& T, u32 root_msg, const u8* in, u3
         const u32 i = S.vtok[r];
         p = S.par[r];
         pc = S.cls[p];
-        const u32 t = cw_ldg(X.tok + i);
+        const u32 t = SH::PRE ? S.tokw[r] : cw_ldg(X.tok + i);
         const u32 k = K3_KIND(t);
         bool ok = true;
         u32 gf = 0, cls = CW_SKIP, aux = 0, hdr = 0, body = 0;
@@ -1109,15 +1142,15 @@ GGR_DEV bool cw_type_item(SH& S, const Tables& T, u32 root_msg, const u8* in, u3
         bool is_ts = false;
         if (pc == CW_MSG || pc == CW_EMSG) {
           // member of a message: "key" : value
-          const u32 kt = cw_ldg(X.tok + i - 1u);
-          const CwQ q0 = cw_q(X, K3_Q(kt)), q1 = cw_q(X, K3_Q(kt) + 1u);
-          if (q0.slow != q1.slow || q0.esc != q1.esc) ok = (CW_WHY(101), false);  // escapes in a key: the other tiers
+          const u32 kinf = SH::PRE ? S.kinfo[r] : cw_key_pack(X, i);
+          if (!(kinf >> 31)) ok = (CW_WHY(101), false);  // escapes in a key: the other tiers
           const MsgD md = ggr_msg(T, S.aux[p]);
           i32 ei = 0;
           if (ok) {
             KeyInfo ki;
-            cw_key_info(in, K3_POS(kt) + 1u, q1.pos - K3_POS(kt) - 1u, &ki);
-            ok = cw_hash_lookup(T, md.key_hash_first, md.key_hash_mask, ki, in, K3_POS(kt), end, &ei);
+            const u32 kpos = kinf & 0xFFFFu;
+            cw_key_info(in, kpos, (kinf >> 16) & 0x7FFFu, &ki);
+            ok = cw_hash_lookup(T, md.key_hash_first, md.key_hash_mask, ki, in, kpos - 1u, end, &ei);
           }
           if (ok && (u32)ei >= 32u) ok = (CW_WHY(102), false);
           if (ok) {
@@ -1215,7 +1248,7 @@ GGR_DEV bool cw_type_item(SH& S, const Tables& T, u32 root_msg, const u8* in, u3
           if (!FULL || !cw_ts_leaf(X, in, end, t, f.tag, f.tag_len, ir, io, r, n_rec, &S.n_extra, S.cap, &body)) ok = (CW_WHY(119), false);
         } else if (ok && (cls == CW_LEAF || cls == CW_ELEAF)) {
           CwLeaf l;
-          if ((k != K3_STR && k != K3_SCALAR) || !cw_leaf<FULL>(T, X, in, end, f, t, &l)) {
+          if ((k != K3_STR && k != K3_SCALAR) || !cw_leaf<FULL>(T, X, in, end, f, t, &l, SH::PRE ? S.vinfo[r] : 0u, SH::PRE)) {
             ok = (CW_WHY(117), false);
           } else if (cls == CW_LEAF) {
             const bool packed = pc == CW_LISTP;
