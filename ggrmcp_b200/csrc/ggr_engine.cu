@@ -226,6 +226,9 @@ struct ggr_engine {
   int n_slots = 4;
   int64_t chunk_items = 8192;
   bool chunk_ramp = true;  // short chunks at both ends of a batch (GGR_CHUNK_RAMP=0: off)
+  // host-buffer entry points: the issuing thread sleeps on the chunk events (cudaEventBlockingSync) instead of spinning -
+  // a gateway's cores are for its goroutines, and under a CPU quota spinning waiters throttle everybody (GGR_BLOCKING_SYNC=0: spin)
+  bool blocking_sync = true;
   uint64_t chunk_bytes = 32ull << 20;
   // per-kernel timing
   bool profiling = false;
@@ -423,6 +426,7 @@ int ggr_engine_create(const ggr_config* cfg, ggr_engine** out) {
     if (v >= 128) e->chunk_items = v;
   }
   if (const char* nc = getenv("GGR_CHUNK_RAMP")) e->chunk_ramp = nc[0] != '0';
+  if (const char* nc = getenv("GGR_BLOCKING_SYNC")) e->blocking_sync = nc[0] != '0';
   if (const char* nc = getenv("GGR_CHUNK_BYTES")) {
     long long v = atoll(nc);
     if (v >= (1 << 16)) e->chunk_bytes = (uint64_t)v;
@@ -1006,10 +1010,10 @@ static bool slot_init(ggr_engine* e, Slot& sl) {
   if (sl.st) return true;
   NodeBind nb(e);
   if (!cuda_ok(e, cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking), "cudaStreamCreate") ||
-      !cuda_ok(e, cudaEventCreateWithFlags(&sl.ready, cudaEventDisableTiming), "cudaEventCreate") ||
+      !cuda_ok(e, cudaEventCreateWithFlags(&sl.ready, cudaEventDisableTiming | (e->blocking_sync ? cudaEventBlockingSync : 0)), "cudaEventCreate") ||
       !cuda_ok(e, cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming), "cudaEventCreate") ||
       !cuda_ok(e, cudaEventCreateWithFlags(&sl.ev_k, cudaEventDisableTiming), "cudaEventCreate") ||
-      !cuda_ok(e, cudaEventCreateWithFlags(&sl.ev_out, cudaEventDisableTiming), "cudaEventCreate") ||
+      !cuda_ok(e, cudaEventCreateWithFlags(&sl.ev_out, cudaEventDisableTiming | (e->blocking_sync ? cudaEventBlockingSync : 0)), "cudaEventCreate") ||
       !cuda_ok(e, cudaHostAlloc((void**)&sl.h_total, 64, cudaHostAllocMapped), "cudaHostAlloc") ||
       !cuda_ok(e, cudaHostGetDevicePointer((void**)&sl.d_total_alias, sl.h_total, 0), "cudaHostGetDevicePointer"))
     return false;
@@ -1233,6 +1237,8 @@ static int run_host(ggr_engine* e, const ggr_schema* s, bool encode, int64_t n, 
     if (e->trace) cudaEventRecord(tev[(size_t)retired * 4 + 3], s_out);
     retired++;
   }
+  // the last chunk's payload is the last thing in flight: sleep on its event, the stream syncs below then find nothing to wait for
+  if (e->blocking_sync && retired > 0 && !cuda_ok(e, cudaEventSynchronize(slots[(retired - 1) % e->n_slots].ev_out), "sync")) return GGR_ERR_CUDA;
   for (int i = 0; i < e->n_slots; i++)
     if (!cuda_ok(e, cudaStreamSynchronize(slots[i].st), "sync")) return GGR_ERR_CUDA;
   if (!cuda_ok(e, cudaStreamSynchronize(s_in), "sync") || !cuda_ok(e, cudaStreamSynchronize(s_out), "sync")) return GGR_ERR_CUDA;
