@@ -785,7 +785,9 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                 "timing": "wall clock around the C-ABI host-buffer calls (NUMA-local page-locked buffers from ggr_host_alloc; request batch and "
                           "reply batch %s), max over ranks" % ("one after the other" if args.e2e_serial else "in flight together from two host threads"),
-                "with_result_bodies": e2e_bodies, "per_rank": e2e_per_rank, "pcie_probe_gbs_each_way_per_rank": probe,
+                "with_result_bodies": e2e_bodies, "per_rank": e2e_per_rank,
+                "host_wait": ("sleep" if (os.environ.get("GGR_BLOCKING_SYNC", "1" if host_cpus() < 4 * torch.cuda.device_count() else "0") != "0") else "spin")
+                             + " (usable CPUs %d, visible GPUs %d)" % (host_cpus(), torch.cuda.device_count()), "pcie_probe_gbs_each_way_per_rank": probe,
                 "numa_node": eng.numa_node()},
         "gpu_launches": int(launches),
         "clocks": clocks,

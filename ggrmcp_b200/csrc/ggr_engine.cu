@@ -226,9 +226,11 @@ struct ggr_engine {
   int n_slots = 4;
   int64_t chunk_items = 8192;
   bool chunk_ramp = true;  // short chunks at both ends of a batch (GGR_CHUNK_RAMP=0: off)
-  // host-buffer entry points: the issuing thread sleeps on the chunk events (cudaEventBlockingSync) instead of spinning -
-  // a gateway's cores are for its goroutines, and under a CPU quota spinning waiters throttle everybody (GGR_BLOCKING_SYNC=0: spin)
-  bool blocking_sync = true;
+  // host-buffer entry points: the issuing threads either spin on the chunk events (lowest latency: +2.4 % end to end on one GPU)
+  // or sleep on them (cudaEventBlockingSync).  Spinning waiters of 8 engines are 16 busy threads: under a container CPU quota
+  // they throttle every rank alike, so the default is to sleep when the quota leaves fewer than 4 CPUs per visible GPU
+  // (usable_cpus(): affinity mask cut by cgroup cpu.max); GGR_BLOCKING_SYNC=0 / 1 decides by hand
+  bool blocking_sync = false;
   uint64_t chunk_bytes = 32ull << 20;
   // per-kernel timing
   bool profiling = false;
@@ -328,6 +330,29 @@ static void find_numa(ggr_engine* e) {
   e->numa_node = node;
   e->node_cpus = cpus;
 }
+// CPUs this process may use: the affinity mask, cut by the container's CPU quota (cgroup v2 cpu.max, v1 cfs quota)
+static int usable_cpus() {
+  cpu_set_t m;
+  int n = sched_getaffinity(0, sizeof m, &m) == 0 ? CPU_COUNT(&m) : 1;
+  double quota = 0;
+  if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+    char q[32] = {0};
+    double per = 0;
+    if (fscanf(f, "%31s %lf", q, &per) == 2 && strcmp(q, "max") != 0 && per > 0) quota = atof(q) / per;
+    fclose(f);
+  } else if (FILE* f1 = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) {
+    double qv = 0, per = 0;
+    if (fscanf(f1, "%lf", &qv) != 1) qv = 0;
+    fclose(f1);
+    if (FILE* f2 = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) {
+      if (fscanf(f2, "%lf", &per) != 1) per = 0;
+      fclose(f2);
+    }
+    if (qv > 0 && per > 0) quota = qv / per;
+  }
+  if (quota > 0 && quota < n) n = (int)(quota + 0.999);
+  return n < 1 ? 1 : n;
+}
 // binds the calling thread to the GPU's node for the lifetime of the object (old mask restored)
 struct NodeBind {
   cpu_set_t old;
@@ -426,6 +451,7 @@ int ggr_engine_create(const ggr_config* cfg, ggr_engine** out) {
     if (v >= 128) e->chunk_items = v;
   }
   if (const char* nc = getenv("GGR_CHUNK_RAMP")) e->chunk_ramp = nc[0] != '0';
+  e->blocking_sync = usable_cpus() < 4 * ndev;
   if (const char* nc = getenv("GGR_BLOCKING_SYNC")) e->blocking_sync = nc[0] != '0';
   if (const char* nc = getenv("GGR_CHUNK_BYTES")) {
     long long v = atoll(nc);
