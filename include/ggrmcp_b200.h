@@ -156,6 +156,11 @@ int ggr_decode_batch(ggr_engine* e, const ggr_schema* s, int64_t n, const int32_
  * Same operations on buffers already resident in HBM (all pointers are device pointers on the
  * engine's device; `in` must be 16-byte aligned and readable 64 bytes past its end).  Work is
  * enqueued on `stream` (a cudaStream_t, NULL = the engine's own stream) and not synchronized.
+ * The calls of one direction (ggr_encode_batch_dev and ggr_request_batch_dev; ggr_decode_batch_dev and
+ * ggr_decode_wrap_batch_dev) work in the engine's one scratch area of that direction: two of them on DIFFERENT streams
+ * must be ordered by the caller (an event recorded behind the first, waited for by the second stream) - on the same
+ * stream they are ordered already; a request-side call and a reply-side call may overlap freely.  The host-buffer
+ * entry points above bring their own per-chunk scratch and take one batch per direction at a time.
  */
 int ggr_encode_batch_dev(ggr_engine* e, const ggr_schema* s, int64_t n, const int32_t* msg_id, const uint8_t* in,
                          const uint64_t* in_off, uint64_t in_bytes, uint8_t* out, uint64_t out_cap,
