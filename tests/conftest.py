@@ -44,6 +44,9 @@ _ENGINE_PATHS = {
     "lockstep_request_only": {"GGR_COOP": "0", "GGR_LOCKSTEP_MIN_BYTES": "0"},
     # host entry points cut into many small chunks over two slots: exercises the copy/compute pipeline
     "small_chunks": {"GGR_CHUNK_ITEMS": "128", "GGR_SLOTS": "2", "GGR_LOCKSTEP_MIN_BYTES": "0"},
+    # chunks cut by the byte budget, short chunks at both ends of a batch (the ramp needs chunks of at least 512 items and
+    # four of them), issuing threads asleep on blocking events instead of spinning
+    "ramped_chunks": {"GGR_CHUNK_ITEMS": "512", "GGR_CHUNK_BYTES": "400000", "GGR_SLOTS": "3", "GGR_BLOCKING_SYNC": "1"},
     # every call leaves its scratch buffers full of well-formed stale records (IR nodes, sizes, list entries): a kernel
     # that reads a slot nobody wrote in the current call shows up as wrong bytes (round 2: null members in the walker)
     "poisoned": {"GGR_POISON": "1", "GGR_LOCKSTEP_MIN_BYTES": "0"},

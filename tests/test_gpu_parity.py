@@ -266,7 +266,7 @@ def test_flat_and_blob_configs(engine, schema, oracle):
 def test_request_and_reply_batches_in_flight_together(engine, schema, oracle):
     """the host entry points take one batch per direction concurrently (bench.py's end-to-end run does
     exactly this from two threads): results must be those of the calls made one after the other"""
-    heavy(engine, ('default', 'small_chunks'))
+    heavy(engine, ('default', 'small_chunks', 'ramped_chunks'))
     import threading
     import benchgen
     n = 20000
@@ -395,7 +395,7 @@ def test_go_legacy_field_order(schema, oracle, fds_bytes):
 def test_small_output_capacity(engine, schema, oracle):
     """GGR_ERR_NO_SPACE: out_off[n] comes back as the capacity that would do, for one chunk and for many, in
     both directions and with result wrapping; the retry with that capacity gives the full result"""
-    heavy(engine, ('default', 'small_chunks'))
+    heavy(engine, ('default', 'small_chunks', 'ramped_chunks'))
     import ctypes as C
     import benchgen
     from ggrmcp_b200 import engine as E
@@ -418,6 +418,13 @@ def test_small_output_capacity(engine, schema, oracle):
     full_req = engine.encode_batch(schema, wl.req_msg, wl.req_json, wl.req_off)
     full_rep = engine.decode_batch(schema, wl.rep_msg, wl.rep_wire, wl.rep_off)
     full_wrap = engine.decode_wrap_batch(schema, wl.rep_msg, wl.rep_wire, wl.rep_off, idb, ioff)
+    # the chunked host path itself (chunk boundaries by items or bytes, short chunks at both ends) against the oracle
+    names = {schema.message(nm): oracle.msg(nm) for nm in ("com.example.complex.ProcessNodeRequest", "com.example.complex.CreateDocumentRequest",
+                                                           "com.example.complex.Node", "com.example.complex.GetUserProfileResponse")}
+    ow, owoff, _ = oracle.encode_batch(np.array([names[int(i)] for i in wl.req_msg], np.int32), wl.req_json, wl.req_off)
+    oj, ojoff, _ = oracle.decode_batch(np.array([names[int(i)] for i in wl.rep_msg], np.int32), wl.rep_wire, wl.rep_off)
+    assert full_req[0].tobytes() == ow.tobytes() and (full_req[1] == owoff).all() and (full_req[2] == 0).all()
+    assert full_rep[0].tobytes() == oj.tobytes() and (full_rep[1] == ojoff).all() and (full_rep[2] == 0).all()
     for fn, msg, data, off, extra, full in ((L.ggr_encode_batch, wl.req_msg, wl.req_json, wl.req_off, (), full_req),
                                             (L.ggr_decode_batch, wl.rep_msg, wl.rep_wire, wl.rep_off, (), full_rep),
                                             (L.ggr_decode_wrap_batch, wl.rep_msg, wl.rep_wire, wl.rep_off, (idb, ioff), full_wrap)):
