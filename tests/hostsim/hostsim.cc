@@ -575,3 +575,49 @@ int hs_decode_coop(void* h, int msg, const uint8_t* wire, uint32_t n, uint32_t i
 #endif
 
 }  // extern "C"
+
+// ---- byte-run copies of the lock-step emit / write kernels (ggr_warp.cuh): every alignment of source and destination and
+// every length up to `max_len` against memcpy; the bytes around the destination must stay untouched and no source word may
+// be read that holds no byte of the run (the source sits at the very end of a guarded buffer).  Returns 0 or a code that
+// names the failing case.
+struct CopyWordsArgs {
+  const uint8_t* in;
+  uint32_t src, len;
+  uint8_t* d;
+};
+static void copy_words_body(void* p, u32) {
+  CopyWordsArgs* a = (CopyWordsArgs*)p;
+  coop_copy_words(a->in, a->src, a->d, a->len);
+}
+extern "C" int hs_copy_selftest(uint32_t max_len) {
+  std::vector<uint8_t> src_raw(4096 + 64), dst_raw(4096 + 64), want(4096 + 64);
+  for (uint32_t sa = 0; sa < 4; sa++)
+    for (uint32_t da = 0; da < 4; da++)
+      for (uint32_t len = 0; len <= max_len; len++) {
+        // the run ends exactly at the end of the source buffer: a word load past it that holds no byte of the run reads
+        // into the 0xEE guard only if the buffer were longer - here it would run off the vector (caught by the sanitizers
+        // in CI builds; the arithmetic check below catches it always)
+        uint8_t* sbase = (uint8_t*)(((uintptr_t)src_raw.data() + 15) & ~(uintptr_t)15);
+        uint8_t* dbase = (uint8_t*)(((uintptr_t)dst_raw.data() + 15) & ~(uintptr_t)15);
+        uint8_t* s = sbase + 16 + sa;
+        for (uint32_t i = 0; i < len; i++) s[i] = (uint8_t)(1 + (i * 7 + sa * 3 + da) % 251);
+        memset(dbase, 0xAB, 2048);
+        uint8_t* d = dbase + 32 + da;
+        coop_copy_bytes(d, s, len);
+        for (uint32_t i = 0; i < 2048; i++) {
+          const bool inside = dbase + i >= d && dbase + i < d + len;
+          const uint8_t w = inside ? s[dbase + i - d] : 0xAB;
+          if (dbase[i] != w) return 1000000 + (int)(sa * 100000 + da * 10000 + len);
+        }
+        // the whole-warp form of the same copy
+        memset(dbase, 0xAB, 2048);
+        CopyWordsArgs a = {sbase, 16 + sa, len, d};
+        if (hw_run_warp(copy_words_body, &a)) return 3000000;
+        for (uint32_t i = 0; i < 2048; i++) {
+          const bool inside = dbase + i >= d && dbase + i < d + len;
+          const uint8_t w = inside ? s[dbase + i - d] : 0xAB;
+          if (dbase[i] != w) return 2000000 + (int)(sa * 100000 + da * 10000 + len);
+        }
+      }
+  return 0;
+}

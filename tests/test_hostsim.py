@@ -559,3 +559,13 @@ def test_decode_unsorted_maps(oracle, hsim):
         rc, oj, _ = oracle.decode(cases.A, wire)
         st, ej = hsim.decode(cases.A, wire, 0, trial % 16, (trial * 3) % 16)
         assert rc == 0 and st == 0 and ej == oj, (trial, n)
+
+
+def test_byte_run_copies(hsim):
+    """coop_copy_bytes / coop_copy_words (ggr_warp.cuh): every source and destination alignment, every length up to 300,
+    against a byte-wise reference; nothing outside the destination run may change"""
+    import ctypes as C
+    import hostsim
+    L = hostsim.lib()
+    L.hs_copy_selftest.argtypes = [C.c_uint32]
+    assert L.hs_copy_selftest(300) == 0
