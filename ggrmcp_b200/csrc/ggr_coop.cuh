@@ -295,8 +295,15 @@ GGR_DEV void coop_scan_message(SH& S, const DecCtx& cx, u32 me) {
       last_decl = (i32)f.decl_index;
       if (f.kind != GK_MESSAGE && !(f.flags & GF_PRESENCE)) {
         bool ok = true;
-        const bool z = fast ? wzero : coop_wire_zero(in, vpos, lim, wt, &ok);
+        bool z = fast ? wzero : coop_wire_zero(in, vpos, lim, wt, &ok);
         if (!ok) { COOP_BAIL(S); return; }
+        // a 32-bit kind keeps the low 32 bits of its varint (proto.Unmarshal): bits above them alone still make the zero value
+        if (!z && wt == 0 && vend - vpos >= 5u && (f.kind == GK_INT32 || f.kind == GK_UINT32 || f.kind == GK_SINT32 || f.kind == GK_ENUM)) {
+          u32 p = vpos;
+          u64 v = 0;
+          if (!br_varint(in, p, lim, &v)) { COOP_BAIL(S); return; }
+          z = (u32)v == 0u;
+        }
         if (z) continue;  // implicit presence: the zero value is not written
       }
     }

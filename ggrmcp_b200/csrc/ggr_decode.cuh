@@ -654,6 +654,7 @@ struct MapEnt {
   u32 end;      // end of the entry payload
   u32 beg;      // start of the entry payload
   u32 multi;    // message value split over several occurrences inside the entry: merged when written
+  u32 dup;      // a string key or a string value occurs more than once inside the entry: the earlier ones are never written
 };
 // Parses one map entry payload [r.pos, lim): key (field 1) and value (field 2), last wins.
 GGR_DEV int parse_map_entry(Rd& r, u32 lim, const FieldD& kf, const FieldD& vf, MapEnt* me) {
@@ -663,9 +664,10 @@ GGR_DEV int parse_map_entry(Rd& r, u32 lim, const FieldD& kf, const FieldD& vf, 
   me->end = lim;
   me->beg = r.pos;
   me->multi = 0;
+  me->dup = 0;
   bool str_key = kf.kind == GK_STRING;
   if (str_key) me->key = (u64)r.pos;  // empty string key: len 0 at any position
-  u32 val_seen = 0;
+  u32 val_seen = 0, key_seen = 0;
   while (r.pos < lim) {
     u64 tag, v;
     if (!rd_varint(r, lim, &tag)) return GST_BAD_WIRE;
@@ -675,6 +677,8 @@ GGR_DEV int parse_map_entry(Rd& r, u32 lim, const FieldD& kf, const FieldD& vf, 
     if (num == 1 && wt == kf.wt) {
       if (str_key) {
         if (!rd_varint(r, lim, &v) || v > (u64)(lim - r.pos)) return GST_BAD_WIRE;
+        if (key_seen) me->dup = 1;
+        key_seen = 1;
         me->key = (u64)r.pos | (v << 32);
         rd_jump(r, r.pos + (u32)v);
       } else if (wt == 0) {
@@ -697,6 +701,7 @@ GGR_DEV int parse_map_entry(Rd& r, u32 lim, const FieldD& kf, const FieldD& vf, 
       }
     } else if (num == 2 && wt == vf.wt) {
       if (vf.kind == GK_MESSAGE && val_seen) me->multi = 1;  // split value: put_map_value merges
+      if (vf.kind == GK_STRING && val_seen) me->dup = 1;
       val_seen = 1;
       me->val_pos = r.pos;
       if (wt == 2) {
@@ -899,7 +904,7 @@ GGR_DEVN int put_wkt(W& w, const DecCtx& cx, u32 msg, u32 start, u32 lim) {
     if (st != GST_OK) return st;
     st = cd.wkt == GGR_WKT_TIMESTAMP ? put_timestamp(w, s, n) : put_duration(w, s, n);
     if (st == GST_RANGE && cx.late) {
-      *cx.late = GST_RANGE;
+      if (*cx.late == GST_OK) *cx.late = GST_RANGE;  // Marshal stops at its first error: the first one parked stays
       return GST_OK;
     }
     return st;
@@ -970,7 +975,7 @@ GGR_DEVN int put_wkt(W& w, const DecCtx& cx, u32 msg, u32 start, u32 lim) {
     w.put1('"');
     if (bad) {
       if (cx.late) {
-        *cx.late = GST_INVALID_VALUE;
+        if (*cx.late == GST_OK) *cx.late = GST_INVALID_VALUE;
         return GST_OK;
       }
       return GST_INVALID_VALUE;
@@ -1025,6 +1030,49 @@ GGR_DEVN int put_map_value(W& w, const DecCtx& cx, FieldD vf, MapEnt me, int rec
   return put_scalar_or_default(w, cx, vf, me);
 }
 
+// proto.Unmarshal parses every occurrence, also the ones that never reach the text: a map entry whose key comes again
+// later (last wins), an earlier key or string value inside one entry.  Invalid UTF-8 or a malformed message in such a
+// place fails the item in Go; the writers only see what they write.  These two checks run in the SIZE pass (the pass that
+// decides an item's status) exactly where an occurrence is dropped.
+template <class W> struct IsCountingWriter { static const bool v = false; };
+template <> struct IsCountingWriter<Cnt> { static const bool v = true; };
+// the value of an entry that a later entry with the same key replaces: walked into a counter; what Marshal would have said
+// about it (ranges, field masks) does not count - Marshal never sees it
+template <bool SLOW>
+GGR_DEVN int check_shadowed_value(const DecCtx& cx, FieldD vf, MapEnt me, int rec) {
+  if (vf.kind != GK_STRING && vf.kind != GK_MESSAGE) return GST_OK;
+  Cnt c;
+  c.pos = 0;
+  DecCtx vc = cx;
+  int late = GST_OK;
+  vc.late = &late;
+  const int st = put_map_value<Cnt, SLOW>(c, vc, vf, me, rec);
+  return (st == GST_RANGE || st == GST_INVALID_VALUE) ? GST_OK : st;
+}
+// every string key / string value occurrence of the entry payload [beg, end) (parse_map_entry found it well-formed)
+GGR_DEVN int check_entry_strings(const DecCtx& cx, u32 beg, u32 end, bool str_key, bool str_val) {
+  Rd r;
+  r.init(cx.in, beg, end, cx.rw);
+  while (r.pos < end) {
+    u64 tag, v;
+    if (!rd_varint(r, end, &tag)) return GST_BAD_WIRE;
+    const u64 num = tag >> 3;
+    const u32 wt = (u32)(tag & 7);
+    if (wt == 2 && ((num == 1 && str_key) || (num == 2 && str_val))) {
+      if (!rd_varint(r, end, &v) || v > (u64)(end - r.pos)) return GST_BAD_WIRE;
+      Cnt c;
+      c.pos = 0;
+      const u32 next = r.pos + (u32)v;
+      const int st = put_json_string(c, r, (u32)v);
+      if (st != GST_OK) return st;
+      rd_jump(r, next);
+    } else if (!rd_skip_value(r, end, (u32)num, wt)) {
+      return GST_BAD_WIRE;
+    }
+  }
+  return GST_OK;
+}
+
 // Map field writer.  `r` is positioned right after the tag of the first entry (fast walk) and is
 // left after the last entry of the run.  In the slow walk the entries are all occurrences of the
 // field inside [pstart, pend).
@@ -1059,6 +1107,10 @@ GGR_DEVN int put_map_field(W& w, const DecCtx& cx, u32 rpos, u32* rend, FieldD f
         u32 lim = r.pos + (u32)len;
         int st = parse_map_entry(r, lim, kf, vf, &me);
         if (st != GST_OK) return st;
+        if (me.dup && IsCountingWriter<W>::v && !count_only) {
+          st = check_entry_strings(cx, me.beg, me.end, kf.kind == GK_STRING, vf.kind == GK_STRING);
+          if (st != GST_OK) return st;
+        }
         if (count > 0 && cmp_map_keys(cx, kf.kind, prev, me.key) >= 0) sorted = false;
         prev = me.key;
         count++;
@@ -1074,12 +1126,18 @@ GGR_DEVN int put_map_field(W& w, const DecCtx& cx, u32 rpos, u32* rend, FieldD f
         u64 tag;
         if (!rd_varint(t, pend, &tag)) return GST_BAD_WIRE;
         u32 wt = (u32)(tag & 7);
+        // this scan may be the only one that reads the message's other tags (a message whose declared fields are all maps)
+        if ((tag >> 3) == 0 || (tag >> 3) > 0x1FFFFFFFull || wt == 4 || wt > 5) return GST_BAD_WIRE;
         if (tag == (u64)f.tag) {
           u64 len;
           if (!rd_varint(t, pend, &len) || len > (u64)(pend - t.pos)) return GST_BAD_WIRE;
           MapEnt me;
           int st = parse_map_entry(t, t.pos + (u32)len, kf, vf, &me);
           if (st != GST_OK) return st;
+          if (me.dup && IsCountingWriter<W>::v && !count_only) {
+            st = check_entry_strings(cx, me.beg, me.end, kf.kind == GK_STRING, vf.kind == GK_STRING);
+            if (st != GST_OK) return st;
+          }
           if (count > 0 && cmp_map_keys(cx, kf.kind, prev, me.key) >= 0) sorted = false;
           prev = me.key;
           count++;
@@ -1187,7 +1245,19 @@ GGR_DEVN int put_map_field(W& w, const DecCtx& cx, u32 rpos, u32* rend, FieldD f
         const U4 e = A[i];
         if (i + 1u < count) {  // an equal key follows: that later occurrence wins
           const U4 nx = A[i + 1u];
-          if (cmp_rec(e, nx) == 0) continue;
+          if (cmp_rec(e, nx) == 0) {
+            if (IsCountingWriter<W>::v) {  // Unmarshal has parsed the entry all the same
+              Rd ts;
+              ts.init(cx.in, e.z, run_end, cx.rw);
+              u64 slen;
+              MapEnt sme;
+              if (!rd_varint(ts, run_end, &slen)) return GST_BAD_WIRE;
+              int sst = parse_map_entry(ts, ts.pos + (u32)slen, kf, vf, &sme);
+              if (sst == GST_OK) sst = check_shadowed_value<SLOW>(cx, vf, sme, rec);
+              if (sst != GST_OK) return sst;
+            }
+            continue;
+          }
         }
         Rd t;
         t.init(cx.in, e.z, run_end, cx.rw);
@@ -1246,7 +1316,12 @@ GGR_DEVN int put_map_field(W& w, const DecCtx& cx, u32 rpos, u32* rend, FieldD f
         continue;
       }
       if (have_last && cmp_map_keys(cx, kf.kind, me.key, last_key) <= 0) continue;
-      if (!have_best || cmp_map_keys(cx, kf.kind, me.key, best.key) <= 0) {
+      const int cb = have_best ? cmp_map_keys(cx, kf.kind, me.key, best.key) : -1;
+      if (cb <= 0) {
+        if (have_best && cb == 0 && IsCountingWriter<W>::v) {  // `best` is replaced by a later entry with its key
+          const int sst = check_shadowed_value<SLOW>(cx, vf, best, rec);
+          if (sst != GST_OK) return sst;
+        }
         best = me;  // smaller key, or a later occurrence of the same key
         have_best = true;
       }
@@ -1263,6 +1338,54 @@ GGR_DEVN int put_map_field(W& w, const DecCtx& cx, u32 rpos, u32* rend, FieldD f
     have_last = true;
   }
   w.put1('}');
+  return GST_OK;
+}
+
+template <class W, bool SLOW>
+GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 end, int rec, bool active, unsigned mask);
+
+// Slow walk, size pass: the occurrences of singular field f inside the frame [start, end) that never reach the text - every
+// occurrence but the last of a string field set several times (keep_pos = position behind the tag of the one that is
+// written), every occurrence of a oneof member that a sibling set later replaces (keep_pos = 0xFFFFFFFF).  proto.Unmarshal
+// has parsed them all the same: invalid UTF-8 or a malformed message inside one fails the item.
+GGR_DEVN int check_dropped_occurrences(const DecCtx& lc, const FieldD& f, u32 start, u32 end, u32 keep_pos, int rec) {
+  if (f.kind != GK_STRING && f.kind != GK_MESSAGE) return GST_OK;
+  Rd t;
+  t.init(lc.in, start, end, lc.rw);
+  while (t.pos < end) {
+    u64 tag;
+    if (!rd_varint(t, end, &tag)) return GST_BAD_WIRE;
+    const u64 n2 = tag >> 3;
+    const u32 wt = (u32)(tag & 7);
+    if (n2 == 0 || n2 > 0x1FFFFFFFull || wt == 4 || wt > 5) return GST_BAD_WIRE;
+    if ((u32)n2 != f.number || wt != 2u || t.pos == keep_pos) {
+      if (!rd_skip_value(t, end, (u32)n2, wt)) return GST_BAD_WIRE;
+      continue;
+    }
+    u64 len;
+    if (!rd_varint(t, end, &len) || len > (u64)(end - t.pos)) return GST_BAD_WIRE;
+    const u32 lim = t.pos + (u32)len;
+    Cnt c;
+    c.pos = 0;
+    if (f.kind == GK_STRING) {
+      const int st = put_json_string(c, t, (u32)len);
+      if (st != GST_OK) return st;
+    } else {
+      DecCtx vc = lc;
+      int late = GST_OK;
+      vc.late = &late;  // what Marshal would say about the value does not count: it never sees it
+      const MsgD cd = ggr_msg(lc.T, (u32)f.child);
+      int st;
+      if (cd.wkt != GGR_WKT_NONE) {
+        st = put_wkt(c, vc, (u32)f.child, t.pos, lim);
+      } else {
+        st = walk_message<Cnt, false>(c, vc, (u32)f.child, t.pos, lim, rec + 1, true, ggr_activemask());
+        if (st == GGR_NEED_SLOW) st = walk_message<Cnt, true>(c, vc, (u32)f.child, t.pos, lim, rec + 1, true, ggr_activemask());
+      }
+      if (st != GST_OK && st != GST_RANGE && st != GST_INVALID_VALUE) return st;
+    }
+    rd_jump(t, lim);
+  }
   return GST_OK;
 }
 
@@ -1617,7 +1740,17 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
           }
           if (!rd_skip_value(q, fr.end, n3, w3)) GGR_RET(GST_BAD_WIRE);
         }
-        if (later) continue;
+        if (later) {
+          if (IsCountingWriter<W>::v) {  // the member is replaced: Unmarshal has parsed its occurrences all the same
+            const int cs = check_dropped_occurrences(lc, f, fr.start, fr.end, 0xFFFFFFFFu, rec);
+            if (cs != GST_OK) GGR_RET(cs);
+          }
+          continue;
+        }
+      }
+      if (n_occ > 1 && f.kind == GK_STRING && IsCountingWriter<W>::v) {  // set several times: the last one is written
+        const int cs = check_dropped_occurrences(lc, f, fr.start, fr.end, last_pos, rec);
+        if (cs != GST_OK) GGR_RET(cs);
       }
       if (f.kind == GK_MESSAGE) {
         MsgD cd = ggr_msg(T, (u32)f.child);
