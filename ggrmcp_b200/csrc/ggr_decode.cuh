@@ -1774,6 +1774,10 @@ GGR_DEVN int walk_message(W& w, const DecCtx& cx, u32 root_msg, u32 start, u32 e
               if (!rd_skip_value(q, fr.end, n3, w3)) GGR_RET(GST_BAD_WIRE);
               if (sib) mstart = q.pos;
             }
+            if (mstart != fr.start && IsCountingWriter<W>::v) {  // the pieces in front of the sibling: parsed by Unmarshal, dropped here
+              const int cs = check_dropped_occurrences(lc, f, fr.start, mstart, 0xFFFFFFFFu, rec);
+              if (cs != GST_OK) GGR_RET(cs);
+            }
           }
           const u8* mb;
           u32 ml;

@@ -305,7 +305,8 @@ GGR_DEV bool parse_number(It& it, NumTok* t) {
       it.adv();
       c = it.get();
     } while (c - '0' < 10u);
-    if (exp > 100000000) return false;  // strconv.Atoi range failure surrogate (see oracle)
+    // beyond 10^8 the exponent stays clamped: an integer kind fails on it below (strconv.Atoi's range error, see oracle),
+    // strconv.ParseFloat goes on - 0.0e2964595747023549 is 0, 1e-99999999999 underflows to 0, 1e99999999999 is out of range
     if (eneg) exp = -exp;
   }
   if (!it.eof() && ggr_not_delim(it.get())) return false;
@@ -322,6 +323,7 @@ GGR_DEV bool parse_number(It& it, NumTok* t) {
 // Returns false when the token is not an integer in range [upstream normalizeToIntString +
 // strconv.ParseInt/ParseUint].
 GGR_DEV bool num_to_int(const NumTok& t, bool is_signed, int bits, u64* out) {
+  if (t.exp > 100000000 || t.exp < -100000000) return false;  // strconv.Atoi of the exponent fails (see oracle): no integer, whatever the digits
   if (t.m == 0 && !t.ovf) {
     *out = 0;
     return true;

@@ -120,6 +120,12 @@ ENCODE_EDGE = [
     (A, b'{"[ext]":1}', None), (A, b'{"f\\u005fint32":5}', None), (A, b'{"f_float":1.5}', None), (A, b'{"f_double":1.5}', None),
     (P + "ProcessNodeRequest", b'{"invalid_field":"value"}', "unknown_field"),
     ("google.protobuf.Timestamp", b'"2024-01-01T12:00:00Z"', None), ("google.protobuf.Timestamp", b'{}', None),
+    # exponents beyond 10^8 (found by fuzzing): strconv.ParseFloat goes on - a zero mantissa stays 0, a negative exponent
+    # underflows to 0, a positive one is out of range - while an integer kind fails on strconv.Atoi of the exponent
+    (A, b'{"f_double":0.0e002964595747023549}', None), (A, b'{"f_double":1e-99999999999,"f_float":-0e99999999999}', None),
+    (A, b'{"f_double":1e99999999999}', None), (A, b'{"f_int32":0e99999999999}', None), (A, b'{"f_uint64":"0e-99999999999"}', None),
+    (A, b'{"f_int64":0e100000000,"f_sint32":0e-100000000}', None), (A, b'{"f_int64":0e100000001}', None),
+    (A, b'{"r_double":[0e100000001,5e-100000001,0.0e00000000000000000000001]}', None),
 ]
 
 DECODE_EDGE_HEX = [
@@ -159,6 +165,10 @@ DECODE_EDGE_HEX = [
     # a 32-bit kind keeps the low 32 bits of its varint: bits above them alone are still the zero value (implicit presence)
     (P + "ProcessNodeResponse", "108080808090ffffffff01"), ("bench.Flat", "4080808080e0ffffffff01"), ("bench.Flat", "408080808010"),
     ("bench.Flat", "40808080801001"),
+    # a oneof member of message type in pieces with a sibling set in between: the pieces in front of the sibling are dropped,
+    # but proto.Unmarshal has parsed them (invalid UTF-8 / a truncated varint inside the dropped piece)
+    (A, "aa03031201ff980305aa03020801aa0303120161"), (A, "aa0303120161980305aa03020801aa0303120162"),
+    (A, "aa030208ff980305aa03020801aa0303120161"),
 ]
 
 
